@@ -1,0 +1,173 @@
+'''ctypes mirror of include/scg.h and loader of the in-tree CUDA library.
+
+This is the binding a maintainer of the reference would add: plain pointers and
+sizes, no torch types in the signatures.  The library is REQUIRED: there is no CPU fallback, `lib()`
+raises if `libscg_b200.so` is missing or cannot be loaded.
+'''
+
+import ctypes as C
+import os
+
+SCG_ABI_VERSION = 1
+SCG_MAX_NX = 12
+SCG_MAX_NU = 4
+SCG_MAX_OBS = 48
+SCG_MAX_INERTIAL = 4
+SCG_MAX_DIST = 4
+SCG_MAX_DIST_DIM = 12
+SCG_MAX_CON_ROWS = 96
+SCG_MAX_CON_NNZ = 512
+
+SCG_OK, SCG_EINVAL, SCG_ECUDA, SCG_ESTATE, SCG_ENOMEM = 0, -1, -2, -3, -4
+
+SCG_SYS_CARTPOLE, SCG_SYS_QUAD1D, SCG_SYS_QUAD2D, SCG_SYS_QUAD3D = 0, 1, 2, 3
+SCG_TASK_STABILIZATION, SCG_TASK_TRAJ_TRACKING = 0, 1
+SCG_COST_RL_REWARD, SCG_COST_QUADRATIC = 0, 1
+SCG_PREC_F64, SCG_PREC_F32 = 0, 1
+SCG_RNG_TABLE, SCG_RNG_PHILOX = 0, 1
+SCG_DIST_IMPULSE, SCG_DIST_STEP, SCG_DIST_UNIFORM, SCG_DIST_WHITE, SCG_DIST_PERIODIC = 0, 1, 2, 3, 4
+SCG_MODE_ACTION, SCG_MODE_DYNAMICS, SCG_MODE_OBSERVATION = 0, 1, 2
+SCG_RAND_NONE, SCG_RAND_UNIFORM, SCG_RAND_NORMAL = 0, 1, 2
+SCG_ACT_TANH, SCG_ACT_RELU, SCG_ACT_LEAKY_RELU = 0, 1, 2
+SCG_CON_LINEAR, SCG_CON_ABS = 0, 1
+
+ACTIVATIONS = {'tanh': SCG_ACT_TANH, 'relu': SCG_ACT_RELU, 'leaky_relu': SCG_ACT_LEAKY_RELU}
+
+_dbl_dd = C.c_double * SCG_MAX_DIST_DIM
+_dbl_nx = C.c_double * SCG_MAX_NX
+_dbl_nu = C.c_double * SCG_MAX_NU
+_dbl_in = C.c_double * SCG_MAX_INERTIAL
+_i32_nx = C.c_int32 * SCG_MAX_NX
+_i32_in = C.c_int32 * SCG_MAX_INERTIAL
+
+
+class scg_disturbance(C.Structure):
+    _fields_ = [
+        ('kind', C.c_int32), ('dim', C.c_int32), ('has_mask', C.c_int32), ('step_offset', C.c_int32),
+        ('magnitude', C.c_double), ('duration', C.c_double), ('decay_rate', C.c_double),
+        ('scale', C.c_double), ('frequency', C.c_double),
+        ('low', _dbl_dd), ('high', _dbl_dd), ('std', _dbl_dd), ('mask', _dbl_dd),
+    ]
+
+
+class scg_config(C.Structure):
+    _fields_ = [
+        ('struct_size', C.c_int32), ('abi_version', C.c_int32), ('system', C.c_int32), ('num_envs', C.c_int32),
+        ('env_index_offset', C.c_int32), ('device', C.c_int32), ('precision', C.c_int32), ('rng_mode', C.c_int32),
+        ('seed', C.c_uint64),
+        ('ctrl_freq', C.c_int32), ('pyb_freq', C.c_int32), ('ctrl_steps', C.c_int32),
+        ('task', C.c_int32), ('cost', C.c_int32), ('obs_goal_horizon', C.c_int32), ('obs_wrap_angle', C.c_int32),
+        ('normalized_action', C.c_int32), ('rew_exponential', C.c_int32), ('done_on_out_of_bound', C.c_int32),
+        ('done_on_violation', C.c_int32), ('use_constraint_penalty', C.c_int32), ('auto_reset', C.c_int32),
+        ('_pad0', C.c_int32),
+        ('constraint_penalty', C.c_double), ('norm_act_scale', C.c_double), ('goal_tolerance', C.c_double),
+        ('rew_state_weight', _dbl_nx), ('rew_act_weight', _dbl_nu), ('mse_weight', _dbl_nx),
+        ('Q', _dbl_nx), ('R', _dbl_nu), ('u_goal', _dbl_nu), ('act_low', _dbl_nu), ('act_high', _dbl_nu),
+        ('hover_thrust', C.c_double), ('state_low', _dbl_nx), ('state_high', _dbl_nx),
+        ('x_threshold', C.c_double), ('theta_threshold', C.c_double),
+        ('gravity', C.c_double), ('kf', C.c_double), ('km', C.c_double), ('arm', C.c_double),
+        ('pwm2rpm_scale', C.c_double), ('pwm2rpm_const', C.c_double), ('pwm_min', C.c_double), ('pwm_max', C.c_double),
+        ('inertial_nominal', _dbl_in), ('pole_width', C.c_double),
+        ('init_nominal', _dbl_nx), ('randomized_init', C.c_int32), ('randomized_inertial', C.c_int32),
+        ('init_rand_kind', _i32_nx), ('inertial_rand_kind', _i32_in),
+        ('init_rand_a', _dbl_nx), ('init_rand_b', _dbl_nx), ('inertial_rand_a', _dbl_in), ('inertial_rand_b', _dbl_in),
+        ('n_dist', C.c_int32 * 3), ('_pad1', C.c_int32),
+        ('dist', (scg_disturbance * SCG_MAX_DIST) * 3),
+    ]
+
+
+class scg_step_out(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        'd_obs', 'd_obs_f64', 'd_state_f64', 'd_rew', 'd_rew_f64', 'd_done', 'd_truncated', 'd_cviol', 'd_cvals', 'd_mse',
+        'd_out_of_bounds', 'd_goal_reached', 'd_current_step', 'd_terminal_obs', 'd_terminal_obs_f64', 'd_terminal_state_f64')]
+
+
+class scg_rollout_out(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        'd_obs', 'd_act', 'd_rew', 'd_mask', 'd_v', 'd_logp', 'd_terminal_v', 'd_ret', 'd_adv', 'd_cviol', 'd_cvals', 'd_mse',
+        'd_last_obs', 'd_last_val', 'd_ep_return_sum', 'd_ep_length_sum', 'd_ep_cviol_sum', 'd_ep_count')]
+
+
+class scg_rollout_args(C.Structure):
+    _fields_ = [
+        ('T', C.c_int32), ('obs_dim', C.c_int32), ('act_dim', C.c_int32), ('hidden_dim', C.c_int32),
+        ('activation', C.c_int32), ('use_gae', C.c_int32), ('deterministic', C.c_int32), ('envs_per_block', C.c_int32),
+        ('gamma', C.c_double), ('gae_lambda', C.c_double),
+        ('d_policy', C.c_void_p), ('d_eps', C.c_void_p),
+    ]
+
+
+# every symbol include/scg.h declares: name -> (restype, argtypes)
+_VP = C.c_void_p
+_SYMBOLS = {
+    'scg_abi_version': (C.c_int, []),
+    'scg_create': (C.c_int, [C.POINTER(scg_config), C.POINTER(_VP)]),
+    'scg_destroy': (None, [_VP]),
+    'scg_last_error': (C.c_char_p, [_VP]),
+    'scg_dims': (C.c_int, [_VP] + [C.POINTER(C.c_int32)] * 6),
+    'scg_set_reference': (C.c_int, [_VP, _VP, C.c_int32]),
+    'scg_set_constraints': (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP, _VP, _VP, _VP]),
+    'scg_set_episode_table': (C.c_int, [_VP, _VP, C.c_int32]),
+    'scg_set_noise_table': (C.c_int, [_VP, _VP, C.c_int32]),
+    'scg_reset': (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
+    'scg_step': (C.c_int, [_VP, _VP, _VP, C.POINTER(scg_step_out), _VP]),
+    'scg_rollout': (C.c_int, [_VP, C.POINTER(scg_rollout_args), C.POINTER(scg_rollout_out), _VP]),
+    'scg_policy_blob_floats': (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    'scg_policy_pack': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _VP, _VP]),
+    'scg_state_bytes': (C.c_int, [_VP, C.POINTER(C.c_size_t)]),
+    'scg_get_state': (C.c_int, [_VP, _VP, C.c_size_t, _VP]),
+    'scg_set_state': (C.c_int, [_VP, _VP, C.c_size_t, _VP]),
+    'scg_launch_count': (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
+    'scg_philox_selftest': (C.c_int, [C.c_int32, _VP, _VP, _VP, C.c_int32]),
+}
+
+LIB_NAME = 'libscg_b200.so'
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+_lib = None
+
+
+class ScgError(RuntimeError):
+    '''Raised when a C-ABI call fails; `code` is the SCG_E* value.'''
+
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+def lib():
+    '''Loads (once) and returns the CUDA library.  Fails loudly when it was not built.'''
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f'{LIB_PATH} is missing: build it with `python -m safe_control_gym_b200.build` '
+                              '(nvcc, sm_100a).  There is no CPU fallback for the rollout engine.')
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SYMBOLS.items():
+            fn = getattr(handle, name)   # AttributeError if a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        if handle.scg_abi_version() != SCG_ABI_VERSION:
+            raise ImportError(f'{LIB_NAME}: ABI version mismatch')
+        _lib = handle
+    return _lib
+
+
+def check(code, handle=None):
+    '''Maps a C-ABI return code onto the exception type the reference raises on this path.'''
+    if code == SCG_OK:
+        return
+    msg = lib().scg_last_error(handle)
+    msg = msg.decode() if msg else f'scg error {code}'
+    if code == SCG_EINVAL:
+        raise ValueError(msg)           # e.g. benchmark_env.py:141-142
+    if code == SCG_ESTATE:
+        raise RuntimeError(msg)         # benchmark_env.py:230-235
+    raise ScgError(code, msg)
+
+
+def new_config():
+    cfg = scg_config()
+    cfg.struct_size = C.sizeof(scg_config)
+    cfg.abi_version = SCG_ABI_VERSION
+    return cfg

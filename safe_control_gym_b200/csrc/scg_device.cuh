@@ -1,0 +1,687 @@
+// scg_device.cuh -- device-side environment logic of the B200 rollout engine.
+//
+// One lane owns one environment for the physics / env bookkeeping; the integrator state lives
+// in that lane's registers for the whole horizon.  Everything is templated on
+//   SYS : SCG_SYS_CARTPOLE / QUAD1D / QUAD2D / QUAD3D
+//   R   : double (SCG_PREC_F64, the reference's arithmetic: numpy / PyBullet double) or float.
+//
+// Reference semantics implemented here (paths relative to the reference root):
+//   Quadrotor.step            safe_control_gym/envs/gym_pybullet_drones/quadrotor.py:394-445
+//   _preprocess_control       quadrotor.py:722-747, quadrotor_utils.py:16-60
+//   BaseAviary physics        safe_control_gym/envs/gym_pybullet_drones/base_aviary.py:232-286,364-384
+//   CartPole.step             safe_control_gym/envs/gym_control/cartpole.py:238-264,479-583
+//   reward/done/info          quadrotor.py:819-923, cartpole.py:611-696
+//   BenchmarkEnv.after_step   safe_control_gym/envs/benchmark_env.py:447-502, extend_obs :422-445
+//   constraints               safe_control_gym/envs/constraints.py:97-130,274,445-447
+//   disturbances              safe_control_gym/envs/disturbances.py:54-259
+//   reset / randomisation     quadrotor.py:328-392, cartpole.py:266-352, benchmark_env.py:237-268
+// The 2D quadrotor is integrated in its plane (x, z, theta): PyBullet's full 3D update reduces to it
+// exactly because rotation about a fixed axis commutes; the CPU oracle keeps the
+// full quaternion form and the parity tests compare the two.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "scg.h"
+
+#define SCG_PI 3.14159265358979323846
+
+// ---------------------------------------------------------------------------------------------
+// math wrappers
+// ---------------------------------------------------------------------------------------------
+template <typename R> struct Mth;
+template <> struct Mth<double> {
+    static __device__ __forceinline__ double sin_(double x) { return sin(x); }
+    static __device__ __forceinline__ double cos_(double x) { return cos(x); }
+    static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double exp_(double x) { return exp(x); }
+    static __device__ __forceinline__ double log_(double x) { return log(x); }
+    static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+    static __device__ __forceinline__ double asin_(double x) { return asin(x); }
+    static __device__ __forceinline__ double atan2_(double y, double x) { return atan2(y, x); }
+    static __device__ __forceinline__ double fmod_(double x, double y) { return fmod(x, y); }
+    static __device__ __forceinline__ double pow_(double x, double y) { return pow(x, y); }
+};
+template <> struct Mth<float> {
+    static __device__ __forceinline__ float sin_(float x) { return sinf(x); }
+    static __device__ __forceinline__ float cos_(float x) { return cosf(x); }
+    static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float exp_(float x) { return expf(x); }
+    static __device__ __forceinline__ float log_(float x) { return logf(x); }
+    static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float asin_(float x) { return asinf(x); }
+    static __device__ __forceinline__ float atan2_(float y, float x) { return atan2f(y, x); }
+    static __device__ __forceinline__ float fmod_(float x, float y) { return fmodf(x, y); }
+    static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
+};
+
+// normalization.py:8-10 (numpy floored modulo)
+template <typename R> __device__ __forceinline__ R normalize_angle(R x) {
+    const R two_pi = (R)(2.0 * SCG_PI);
+    R y = Mth<R>::fmod_(x + (R)SCG_PI, two_pi);
+    if (y < (R)0) y += two_pi;
+    return y - (R)SCG_PI;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10, stream layout shared with the CPU oracle: ctr = (slot, idx, global env, stream),
+// key = (seed lo, seed hi).  One block per draw slot; uniform uses word 0, normal uses words 0,1.
+// ---------------------------------------------------------------------------------------------
+#define SCG_STREAM_EPISODE 1u
+#define SCG_STREAM_STEP 2u
+#define SCG_STREAM_POLICY 3u
+#define SCG_STREAM_RESET 4u
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double u01_d(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
+
+struct RngKey { uint32_t k0, k1, genv; };
+
+template <typename R> __device__ __forceinline__ R rng_uniform(const RngKey& k, uint32_t stream, uint32_t idx, uint32_t slot) {
+    uint32_t x[4]; philox4x32_10(slot, idx, k.genv, stream, k.k0, k.k1, x);
+    return (R)u01_d(x[0]);
+}
+template <typename R> __device__ __forceinline__ R rng_normal(const RngKey& k, uint32_t stream, uint32_t idx, uint32_t slot) {
+    uint32_t x[4]; philox4x32_10(slot, idx, k.genv, stream, k.k0, k.k1, x);
+    if (sizeof(R) == 8) {
+        return (R)(sqrt(-2.0 * log(u01_d(x[0]))) * cos(2.0 * SCG_PI * u01_d(x[1])));
+    } else {
+        float u0 = (float)u01_d(x[0]), u1 = (float)u01_d(x[1]);
+        // u0 may round to 1.0f (log -> 0) but never to 0: (x+0.5)/2^32 >= 1.16e-10
+        return (R)(sqrtf(-2.0f * logf(u0)) * cospif(2.0f * u1));
+    }
+}
+__device__ __forceinline__ int rng_randint(const RngKey& k, uint32_t stream, uint32_t idx, uint32_t slot, uint32_t n) {
+    uint32_t x[4]; philox4x32_10(slot, idx, k.genv, stream, k.k0, k.k1, x);
+    return (int)__umulhi(x[0], n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-side view of one handle
+// ---------------------------------------------------------------------------------------------
+template <int SYS> struct SysDims;
+template <> struct SysDims<SCG_SYS_CARTPOLE> { static constexpr int NX = 4, NU = 1, PS = 4; };
+template <> struct SysDims<SCG_SYS_QUAD1D> { static constexpr int NX = 2, NU = 1, PS = 4; };   // x, vx, z, vz (x only carries the init quirk)
+template <> struct SysDims<SCG_SYS_QUAD2D> { static constexpr int NX = 6, NU = 2, PS = 6; };   // x, vx, z, vz, theta, omega_y
+template <> struct SysDims<SCG_SYS_QUAD3D> { static constexpr int NX = 12, NU = 4, PS = 13; }; // pos3, quat4, vel3, omega_world3
+
+#define SCG_PS_MAX 13
+
+// Persistent per-env state, SoA in one device allocation ("state blob", checkpointable as one memcpy).
+struct DevState {
+    double* phys;        // [SCG_PS_MAX][N]
+    double* inertial;    // [SCG_MAX_INERTIAL][N]
+    float* cur_obs;      // [N][obs_dim] observation to feed the policy next
+    int32_t* ctrl_step;  // [N]
+    int32_t* episode;    // [N] resets done so far
+    uint32_t* total_steps; // [N]
+    int32_t* initial_reset; // [N]
+    int32_t* dist_off;   // [3*SCG_MAX_DIST][N]
+    float* ep_acc;       // [3][N] running episode return / length / violations
+};
+
+struct DevTables {
+    const scg_config* cfg;     // device copy
+    const double* x_goal;      // [L][nx]
+    int32_t L;
+    int32_t n_con;
+    const int32_t* con_kind;   // [n_con]
+    const int32_t* con_strict; // [n_con]
+    const int32_t* con_ptr;    // [n_con+1]
+    const int32_t* con_col;    // [nnz]
+    const double* con_val;     // [nnz]
+    const double* con_b;       // [n_con]
+    const double* ep_table;    // [K][N][P] or null
+    int32_t K, P;
+    const double* noise_table; // [Tn][N][D] or null
+    int32_t Tn, D;
+    int32_t n_off_slots;
+    int32_t obs_dim;
+    int32_t N;
+    DevState st;
+};
+
+// Everything the owner lane keeps in registers for one env.
+template <int SYS, typename R> struct EnvRegs {
+    R ps[SysDims<SYS>::PS];
+    R inertial[SCG_MAX_INERTIAL];
+    int ctrl_step;
+    int episode;
+    uint32_t total_steps;
+    float ep_ret, ep_len, ep_cv;
+};
+
+template <int SYS, typename R>
+__device__ __forceinline__ void env_load(const DevTables& T, int n, EnvRegs<SYS, R>& e) {
+    const int N = T.N;
+#pragma unroll
+    for (int j = 0; j < SysDims<SYS>::PS; ++j) e.ps[j] = (R)T.st.phys[(size_t)j * N + n];
+#pragma unroll
+    for (int j = 0; j < SCG_MAX_INERTIAL; ++j) e.inertial[j] = (R)T.st.inertial[(size_t)j * N + n];
+    e.ctrl_step = T.st.ctrl_step[n]; e.episode = T.st.episode[n]; e.total_steps = T.st.total_steps[n];
+    e.ep_ret = T.st.ep_acc[n]; e.ep_len = T.st.ep_acc[N + n]; e.ep_cv = T.st.ep_acc[2 * N + n];
+}
+template <int SYS, typename R>
+__device__ __forceinline__ void env_store(const DevTables& T, int n, const EnvRegs<SYS, R>& e) {
+    const int N = T.N;
+#pragma unroll
+    for (int j = 0; j < SysDims<SYS>::PS; ++j) T.st.phys[(size_t)j * N + n] = (double)e.ps[j];
+#pragma unroll
+    for (int j = 0; j < SCG_MAX_INERTIAL; ++j) T.st.inertial[(size_t)j * N + n] = (double)e.inertial[j];
+    T.st.ctrl_step[n] = e.ctrl_step; T.st.episode[n] = e.episode; T.st.total_steps[n] = e.total_steps;
+    T.st.ep_acc[n] = e.ep_ret; T.st.ep_acc[N + n] = e.ep_len; T.st.ep_acc[2 * N + n] = e.ep_cv;
+}
+
+// ---------------------------------------------------------------------------------------------
+// noise source for one control step of one env (table row or Philox stream)
+// ---------------------------------------------------------------------------------------------
+template <typename R> struct NoiseSrc {
+    const double* row;   // table row (may be null -> zeros) in table mode
+    bool philox;
+    RngKey key;
+    uint32_t stream, idx;
+    int slot;
+    __device__ __forceinline__ R u01() {
+        R v = philox ? rng_uniform<R>(key, stream, idx, (uint32_t)slot) : (row ? (R)row[slot] : (R)0);
+        ++slot; return v;
+    }
+    __device__ __forceinline__ R normal() {
+        R v = philox ? rng_normal<R>(key, stream, idx, (uint32_t)slot) : (row ? (R)row[slot] : (R)0);
+        ++slot; return v;
+    }
+};
+
+// DisturbanceList.apply for one mode (disturbances.py:54-62)
+template <typename R>
+__device__ __noinline__ void apply_disturbances(const scg_config* c, const int32_t* dist_off, int N_stride, int n,
+                                                int mode, int ctrl_step, int pyb_step, R* target, int tdim, NoiseSrc<R>& ns) {
+    const int nd = c->n_dist[mode];
+    for (int j = 0; j < nd; ++j) {
+        const scg_disturbance* d = &c->dist[mode][j];
+        const int kind = d->kind, dim = d->dim;
+        int off = d->step_offset;
+        if ((kind == SCG_DIST_IMPULSE || kind == SCG_DIST_STEP) && off < 0) off = dist_off[(size_t)(mode * SCG_MAX_DIST + j) * N_stride + n];
+        R common = (R)0;
+        if (kind == SCG_DIST_IMPULSE) {          // disturbances.py:108-123
+            if (ctrl_step >= off) {
+                int peak = (int)((double)off + d->duration / 2);
+                int po = abs(ctrl_step - peak);
+                common = ((double)po < d->duration / 2) ? (R)(d->magnitude * pow(d->decay_rate, (double)po)) : (R)0;
+            }
+        } else if (kind == SCG_DIST_STEP) {      // disturbances.py:153-163
+            common = (ctrl_step >= off) ? (R)d->magnitude : (R)0;
+        }
+        for (int k = 0; k < dim; ++k) {
+            R nz = common;
+            if (kind == SCG_DIST_UNIFORM) nz = (R)d->low[k] + (R)(d->high[k] - d->low[k]) * ns.u01();       // :187-192
+            else if (kind == SCG_DIST_WHITE) nz = (R)d->std[k] * ns.normal();                               // :215-223
+            else if (kind == SCG_DIST_PERIODIC) {                                                           // :249-259
+                R phase = (R)(-SCG_PI) + (R)(2.0 * SCG_PI) * ns.u01();
+                R t = (R)((double)pyb_step * (1.0 / (double)c->pyb_freq));
+                nz = (R)d->scale * Mth<R>::sin_((R)(2.0 * SCG_PI * d->frequency) * t + phase);
+            }
+            if (d->has_mask && kind != SCG_DIST_PERIODIC) nz *= (R)d->mask[k];
+            if (k < tdim) target[k] += nz;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// physics
+// ---------------------------------------------------------------------------------------------
+// quadrotor.py:722-747 + quadrotor_utils.py:16-60: thrust command(s) -> per-motor thrust kf*rpm^2
+template <int SYS, typename R>
+__device__ __forceinline__ void quad_motor_forces(const scg_config* c, const R* thrust, R f[4]) {
+    constexpr int NU = SysDims<SYS>::NU;
+    constexpr int n_motor = 4 / NU;
+    R mf[NU];
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+        R t = thrust[k] < (R)0 ? (R)0 : thrust[k];
+        R pwm = (Mth<R>::sqrt_(t / (R)n_motor / (R)c->kf) - (R)c->pwm2rpm_const) / (R)c->pwm2rpm_scale;
+        pwm = pwm < (R)c->pwm_min ? (R)c->pwm_min : pwm;
+        pwm = pwm > (R)c->pwm_max ? (R)c->pwm_max : pwm;
+        R rpm = (R)c->pwm2rpm_scale * pwm + (R)c->pwm2rpm_const;
+        mf[k] = rpm * rpm * (R)c->kf;
+    }
+    if (NU == 1) { f[0] = f[1] = f[2] = f[3] = mf[0]; }
+    else if (NU == 2) { f[0] = mf[0]; f[1] = mf[1 % NU]; f[2] = mf[1 % NU]; f[3] = mf[0]; }   // quadrotor_utils.py:39
+    else { f[0] = mf[0]; f[1] = mf[1 % NU]; f[2] = mf[2 % NU]; f[3] = mf[3 % NU]; }
+}
+
+// Bullet btQuaternion::getEulerZYX (pybullet.getEulerFromQuaternion, base_aviary.py:329)
+template <typename R> __device__ __forceinline__ void rpy_from_quat(const R q[4], R rpy[3]) {
+    R sqx = q[0] * q[0], sqy = q[1] * q[1], sqz = q[2] * q[2], squ = q[3] * q[3];
+    R sarg = (R)-2 * (q[0] * q[2] - q[3] * q[1]);
+    if (sarg <= (R)-0.99999) { rpy[1] = (R)(-0.5 * SCG_PI); rpy[0] = 0; rpy[2] = (R)2 * Mth<R>::atan2_(q[0], -q[1]); }
+    else if (sarg >= (R)0.99999) { rpy[1] = (R)(0.5 * SCG_PI); rpy[0] = 0; rpy[2] = (R)2 * Mth<R>::atan2_(-q[0], q[1]); }
+    else {
+        rpy[1] = Mth<R>::asin_(sarg);
+        rpy[0] = Mth<R>::atan2_((R)2 * (q[1] * q[2] + q[3] * q[0]), squ - sqx - sqy + sqz);
+        rpy[2] = Mth<R>::atan2_((R)2 * (q[0] * q[1] + q[3] * q[2]), squ + sqx - sqy - sqz);
+    }
+}
+template <typename R> __device__ __forceinline__ void rot_from_quat(const R q[4], R M[9]) {
+    R d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    R s = (R)2 / d;
+    R xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
+    R wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+    R xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs;
+    R yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+    M[0] = (R)1 - (yy + zz); M[1] = xy - wz; M[2] = xz + wy;
+    M[3] = xy + wz; M[4] = (R)1 - (xx + zz); M[5] = yz - wx;
+    M[6] = xz - wy; M[7] = yz + wx; M[8] = (R)1 - (xx + yy);
+}
+
+// advance one control step = `steps` Bullet sub-steps (base_aviary.py:243-282 / cartpole.py:552-583)
+template <int SYS, typename R> struct Physics;
+
+template <typename R> struct Physics<SCG_SYS_CARTPOLE, R> {
+    // ps = x, xdot, theta, thetadot ; inertial = pole_length, cart_mass, pole_mass
+    static __device__ __forceinline__ void advance(const scg_config* c, EnvRegs<SCG_SYS_CARTPOLE, R>& e, const R* force, const R* tap, bool has_tap, int steps, R dt) {
+        const R l = e.inertial[0], M = e.inertial[1], m = e.inertial[2], g = (R)c->gravity;
+        const R w = (R)c->pole_width;
+        const R Ic = m / (R)12 * (((R)2 * l) * ((R)2 * l) + w * w);   // box inertia PyBullet recomputes (cartpole.py:301-304,318-322)
+        const R a11 = M + m, a22 = Ic + m * l * l, ml = m * l;
+        R x = e.ps[0], xd = e.ps[1], th = e.ps[2], thd = e.ps[3];
+        for (int s = 0; s < steps; ++s) {
+            R st, ct; Mth<R>::sincos_(th, &st, &ct);
+            R Qx = force[0], Qth = (R)0;
+            if (has_tap) { Qx += tap[0]; Qth += tap[0] * l * ct - tap[1] * l * st; }
+            R a12 = ml * ct;
+            R b1 = Qx + ml * st * thd * thd, b2 = Qth + m * g * l * st;
+            R det = a11 * a22 - a12 * a12;
+            R xdd = (a22 * b1 - a12 * b2) / det, thdd = (a11 * b2 - a12 * b1) / det;
+            xd += xdd * dt; thd += thdd * dt;          // symplectic Euler: velocities first,
+            x += xd * dt; th += thd * dt;              // positions with the new velocities
+        }
+        e.ps[0] = x; e.ps[1] = xd; e.ps[2] = th; e.ps[3] = thd;
+    }
+    static __device__ __forceinline__ void state(const EnvRegs<SCG_SYS_CARTPOLE, R>& e, R* s) {
+        s[0] = e.ps[0]; s[1] = e.ps[1]; s[2] = e.ps[2]; s[3] = e.ps[3];
+    }
+    static __device__ __forceinline__ void set_init(EnvRegs<SCG_SYS_CARTPOLE, R>& e, const R* init) {
+        e.ps[0] = init[0]; e.ps[1] = init[1]; e.ps[2] = init[2]; e.ps[3] = init[3];
+    }
+};
+
+template <typename R> struct Physics<SCG_SYS_QUAD1D, R> {
+    // vertical motion only: orientation stays identity, thrust along world z
+    static __device__ __forceinline__ void advance(const scg_config* c, EnvRegs<SCG_SYS_QUAD1D, R>& e, const R f[4], const R* fd, bool has_dist, int steps, R dt) {
+        const R m = e.inertial[0];
+        R thrust = f[0] + f[1] + f[2] + f[3];
+        R Fz = thrust - m * (R)c->gravity; if (has_dist) Fz += fd[0];
+        R az = Fz / m;
+        R z = e.ps[2], vz = e.ps[3], x = e.ps[0], vx = e.ps[1];
+        for (int s = 0; s < steps; ++s) { vz += az * dt; z += vz * dt; x += vx * dt; }
+        e.ps[2] = z; e.ps[3] = vz; e.ps[0] = x;
+    }
+    static __device__ __forceinline__ void state(const EnvRegs<SCG_SYS_QUAD1D, R>& e, R* s) { s[0] = e.ps[2]; s[1] = e.ps[3]; }
+    static __device__ __forceinline__ void set_init(EnvRegs<SCG_SYS_QUAD1D, R>& e, const R* init) {
+        // quirk: 1D labels are init_x / init_x_dot and quadrotor.py:373-374 routes them to x; z starts at 0
+        e.ps[0] = init[0]; e.ps[1] = init[1]; e.ps[2] = (R)0; e.ps[3] = (R)0;
+    }
+};
+
+template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
+    // ps = x, vx, z, vz, theta, omega_y ; inertial = M, Ixx, Iyy, Izz
+    static __device__ __forceinline__ void advance(const scg_config* c, EnvRegs<SCG_SYS_QUAD2D, R>& e, const R f[4], const R* fd, bool has_dist, int steps, R dt) {
+        const R m = e.inertial[0], Iyy = e.inertial[2];
+        const R thrust = f[0] + f[1] + f[2] + f[3];
+        const R tau_y = (R)c->arm * (-f[0] + f[1] + f[2] - f[3]);      // r x F with the prop offsets of cf2x.urdf:42-78
+        const R alpha = tau_y / Iyy;
+        const R tm = thrust / m;
+        R fx = (R)0, fz = -(R)c->gravity;                              // gravity as force m*g over m
+        if (has_dist) { fx += fd[0] / m; fz += fd[1] / m; }
+        R x = e.ps[0], vx = e.ps[1], z = e.ps[2], vz = e.ps[3], th = e.ps[4], om = e.ps[5];
+        for (int s = 0; s < steps; ++s) {
+            R st, ct; Mth<R>::sincos_(th, &st, &ct);
+            vx += (st * tm + fx) * dt; vz += (ct * tm + fz) * dt; om += alpha * dt;
+            x += vx * dt; z += vz * dt; th += om * dt;
+        }
+        e.ps[0] = x; e.ps[1] = vx; e.ps[2] = z; e.ps[3] = vz; e.ps[4] = th; e.ps[5] = om;
+    }
+    static __device__ __forceinline__ void state(const EnvRegs<SCG_SYS_QUAD2D, R>& e, R* s) {
+        s[0] = e.ps[0]; s[1] = e.ps[1]; s[2] = e.ps[2]; s[3] = e.ps[3];
+        R th = e.ps[4];
+        // pitch as pybullet.getEulerFromQuaternion reports it for q = (0, sin(th/2), 0, cos(th/2)): asin(sin th),
+        // clamped at +-pi/2 when |sin th| >= 0.99999.  Identical to th while |th| < ~1.5663.
+        if (Mth<R>::abs_(th) > (R)1.5) {
+            R sarg = Mth<R>::sin_(th);
+            th = (sarg <= (R)-0.99999) ? (R)(-0.5 * SCG_PI) : (sarg >= (R)0.99999) ? (R)(0.5 * SCG_PI) : Mth<R>::asin_(sarg);
+        }
+        s[4] = th; s[5] = e.ps[5];
+    }
+    static __device__ __forceinline__ void set_init(EnvRegs<SCG_SYS_QUAD2D, R>& e, const R* init) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) e.ps[j] = init[j];                 // quadrotor.py:373-377
+    }
+};
+
+template <typename R> struct Physics<SCG_SYS_QUAD3D, R> {
+    // ps = pos[0..2], quat[3..6] (x,y,z,w), vel[7..9], omega_world[10..12]
+    static __device__ void advance(const scg_config* c, EnvRegs<SCG_SYS_QUAD3D, R>& e, const R f[4], const R* fd, bool has_dist, int steps, R dt) {
+        const R m = e.inertial[0];
+        const R J0 = e.inertial[1], J1 = e.inertial[2], J2 = e.inertial[3];
+        const R a = (R)c->arm;
+        const R thrust = f[0] + f[1] + f[2] + f[3];
+        const R tbx = a * (f[0] + f[1] - f[2] - f[3]);
+        const R tby = a * (-f[0] + f[1] + f[2] - f[3]);
+        const R tbz = (R)(c->km / c->kf) * (-f[0] + f[1] - f[2] + f[3]); // base_aviary.py:371-372: rpm^2*KM = f*KM/KF
+        R px = e.ps[0], py = e.ps[1], pz = e.ps[2];
+        R q[4] = {e.ps[3], e.ps[4], e.ps[5], e.ps[6]};
+        R vx = e.ps[7], vy = e.ps[8], vz = e.ps[9];
+        R wx = e.ps[10], wy = e.ps[11], wz = e.ps[12];
+        const R gz = -m * (R)c->gravity;
+        for (int s = 0; s < steps; ++s) {
+            R M[9]; rot_from_quat<R>(q, M);
+            R Fx = M[2] * thrust, Fy = M[5] * thrust, Fz = M[8] * thrust + gz;
+            if (has_dist) { Fx += fd[0]; Fy += fd[1]; Fz += fd[2]; }
+            // body rates, Euler's equation with the gyroscopic term (btMultiBody m_useGyroTerm)
+            R bx = M[0] * wx + M[3] * wy + M[6] * wz;
+            R by = M[1] * wx + M[4] * wy + M[7] * wz;
+            R bz = M[2] * wx + M[5] * wy + M[8] * wz;
+            R jx = J0 * bx, jy = J1 * by, jz = J2 * bz;
+            R dbx = (tbx - (by * jz - bz * jy)) / J0;
+            R dby = (tby - (bz * jx - bx * jz)) / J1;
+            R dbz = (tbz - (bx * jy - by * jx)) / J2;
+            R dwx = M[0] * dbx + M[1] * dby + M[2] * dbz;
+            R dwy = M[3] * dbx + M[4] * dby + M[5] * dbz;
+            R dwz = M[6] * dbx + M[7] * dby + M[8] * dbz;
+            vx += Fx / m * dt; vy += Fy / m * dt; vz += Fz / m * dt;
+            wx += dwx * dt; wy += dwy * dt; wz += dwz * dt;
+            px += vx * dt; py += vy * dt; pz += vz * dt;
+            // exponential-map orientation update with the NEW world angular velocity (btMultiBody::stepPositionsMultiDof)
+            R ang = Mth<R>::sqrt_(wx * wx + wy * wy + wz * wz);
+            if (ang * dt > (R)(0.25 * SCG_PI)) ang = (R)(0.25 * SCG_PI) / dt;
+            R k;
+            if (ang < (R)0.001) k = (R)0.5 * dt - dt * dt * dt * (R)0.020833333333 * ang * ang;
+            else k = Mth<R>::sin_((R)0.5 * ang * dt) / ang;
+            R ax = wx * k, ay = wy * k, az = wz * k, cw = Mth<R>::cos_(ang * dt * (R)0.5);
+            R n0 = cw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
+            R n1 = cw * q[1] + ay * q[3] + az * q[0] - ax * q[2];
+            R n2 = cw * q[2] + az * q[3] + ax * q[1] - ay * q[0];
+            R n3 = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
+            R nn = Mth<R>::sqrt_(n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3);
+            q[0] = n0 / nn; q[1] = n1 / nn; q[2] = n2 / nn; q[3] = n3 / nn;
+        }
+        e.ps[0] = px; e.ps[1] = py; e.ps[2] = pz; e.ps[3] = q[0]; e.ps[4] = q[1]; e.ps[5] = q[2]; e.ps[6] = q[3];
+        e.ps[7] = vx; e.ps[8] = vy; e.ps[9] = vz; e.ps[10] = wx; e.ps[11] = wy; e.ps[12] = wz;
+    }
+    static __device__ void state(const EnvRegs<SCG_SYS_QUAD3D, R>& e, R* s) {
+        R q[4] = {e.ps[3], e.ps[4], e.ps[5], e.ps[6]};
+        R rpy[3]; rpy_from_quat<R>(q, rpy);
+        R M[9]; rot_from_quat<R>(q, M);
+        s[0] = e.ps[0]; s[1] = e.ps[7]; s[2] = e.ps[1]; s[3] = e.ps[8]; s[4] = e.ps[2]; s[5] = e.ps[9];
+        s[6] = rpy[0]; s[7] = rpy[1]; s[8] = rpy[2];
+        const R wx = e.ps[10], wy = e.ps[11], wz = e.ps[12];
+        s[9] = M[0] * wx + M[3] * wy + M[6] * wz;      // R^T omega_world (quadrotor.py:795-797)
+        s[10] = M[1] * wx + M[4] * wy + M[7] * wz;
+        s[11] = M[2] * wx + M[5] * wy + M[8] * wz;
+    }
+    static __device__ void set_init(EnvRegs<SCG_SYS_QUAD3D, R>& e, const R* init) {
+        e.ps[0] = init[0]; e.ps[7] = init[1]; e.ps[1] = init[2]; e.ps[8] = init[3]; e.ps[2] = init[4]; e.ps[9] = init[5];
+        // pybullet.getQuaternionFromEuler (quadrotor.py:381)
+        R hr = init[6] * (R)0.5, hp = init[7] * (R)0.5, hy = init[8] * (R)0.5;
+        R sr, cr, sp, cp, sy, cy;
+        Mth<R>::sincos_(hr, &sr, &cr); Mth<R>::sincos_(hp, &sp, &cp); Mth<R>::sincos_(hy, &sy, &cy);
+        R q0 = sr * cp * cy - cr * sp * sy, q1 = cr * sp * cy + sr * cp * sy;
+        R q2 = cr * cp * sy - sr * sp * cy, q3 = cr * cp * cy + sr * sp * sy;
+        R nn = Mth<R>::sqrt_(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+        e.ps[3] = q0 / nn; e.ps[4] = q1 / nn; e.ps[5] = q2 / nn; e.ps[6] = q3 / nn;
+        e.ps[10] = init[9]; e.ps[11] = init[10]; e.ps[12] = init[11];  // quadrotor.py:379: p,q,r passed as WORLD angular velocity
+    }
+};
+// theta enters the 2D plane as the half-angle quaternion (0, sin(th/2), 0, cos(th/2)); nothing to convert.
+
+// ---------------------------------------------------------------------------------------------
+// observation / reset / step
+// ---------------------------------------------------------------------------------------------
+template <typename R> __device__ __forceinline__ const double* goal_row(const DevTables& T, const scg_config* c, int nx, int idx) {
+    if (c->task == SCG_TASK_STABILIZATION) return T.x_goal;
+    idx = idx > T.L - 1 ? T.L - 1 : idx;
+    return T.x_goal + (size_t)idx * nx;
+}
+
+// _get_observation + extend_obs (quadrotor.py:777-817, cartpole.py:585-609, benchmark_env.py:422-445)
+template <int SYS, typename R>
+__device__ __forceinline__ void make_obs(const DevTables& T, const scg_config* c, const R* state, int n, int ctrl_step, int pyb_step, bool at_reset,
+                                         NoiseSrc<R>& ns, R* obs) {
+    constexpr int NX = SysDims<SYS>::NX;
+#pragma unroll
+    for (int k = 0; k < NX; ++k) obs[k] = state[k];
+    if (c->n_dist[SCG_MODE_OBSERVATION] > 0)
+        apply_disturbances<R>(c, T.st.dist_off, T.N, n, SCG_MODE_OBSERVATION, ctrl_step, pyb_step, obs, NX, ns);
+    if (SYS == SCG_SYS_CARTPOLE && c->obs_wrap_angle) obs[2] = normalize_angle<R>(obs[2]);
+    if (c->cost == SCG_COST_RL_REWARD && c->obs_goal_horizon > 0) {
+        if (c->task == SCG_TASK_TRAJ_TRACKING) {
+            const int next_step = at_reset ? 1 : ctrl_step + 2;
+            for (int h = 0; h < c->obs_goal_horizon; ++h) {
+                const double* g = goal_row<R>(T, c, NX, next_step + h);
+#pragma unroll
+                for (int k = 0; k < NX; ++k) obs[NX * (1 + h) + k] = (R)g[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NX; ++k) obs[NX + k] = (R)T.x_goal[k];
+        }
+    }
+}
+
+// reset() of one env; leaves the new observation in obs[0..obs_dim)
+template <int SYS, typename R>
+__device__ __noinline__ void env_reset(const DevTables& T, const scg_config* c, int n, EnvRegs<SYS, R>& e, R* state, R* obs) {
+    constexpr int NX = SysDims<SYS>::NX;
+    const int k = e.episode;
+    const bool philox = c->rng_mode == SCG_RNG_PHILOX;
+    RngKey key; key.k0 = (uint32_t)c->seed; key.k1 = (uint32_t)(c->seed >> 32); key.genv = (uint32_t)(c->env_index_offset + n);
+    const double* row = (!philox && T.ep_table) ? T.ep_table + ((size_t)(k % T.K) * T.N + n) * T.P : nullptr;
+    e.ctrl_step = 0;
+    int slot = 0;
+    // disturbance reset draws (benchmark_env.py:336-337, disturbances.py:102-106,148-151)
+    for (int m = 0; m < 3; ++m)
+        for (int j = 0; j < c->n_dist[m]; ++j) {
+            const scg_disturbance* d = &c->dist[m][j];
+            if ((d->kind == SCG_DIST_IMPULSE || d->kind == SCG_DIST_STEP) && d->step_offset < 0) {
+                int v = row ? (int)row[slot] : (philox ? rng_randint(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)slot, (uint32_t)c->ctrl_steps) : 0);
+                T.st.dist_off[(size_t)(m * SCG_MAX_DIST + j) * T.N + n] = v; ++slot;
+            }
+        }
+    const int n_inertial = (SYS == SCG_SYS_CARTPOLE) ? 3 : 4;
+    // inertial properties, additive randomisation (benchmark_env.py:267)
+#pragma unroll
+    for (int j = 0; j < SCG_MAX_INERTIAL; ++j) {
+        double v = c->inertial_nominal[j];
+        if (c->randomized_inertial && j < n_inertial) {
+            if (row) v += row[slot + j];
+            else if (philox) {
+                if (c->inertial_rand_kind[j] == SCG_RAND_UNIFORM)
+                    v += c->inertial_rand_a[j] + (c->inertial_rand_b[j] - c->inertial_rand_a[j]) * rng_uniform<double>(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j));
+                else if (c->inertial_rand_kind[j] == SCG_RAND_NORMAL)
+                    v += c->inertial_rand_a[j] + c->inertial_rand_b[j] * rng_normal<double>(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j));
+            }
+        }
+        e.inertial[j] = (R)v;
+    }
+    slot += SCG_MAX_INERTIAL;
+    R init[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        double v = c->init_nominal[j];
+        if (c->randomized_init) {
+            if (row) v += row[slot + j];
+            else if (philox) {
+                if (c->init_rand_kind[j] == SCG_RAND_UNIFORM)
+                    v += c->init_rand_a[j] + (c->init_rand_b[j] - c->init_rand_a[j]) * rng_uniform<double>(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j));
+                else if (c->init_rand_kind[j] == SCG_RAND_NORMAL)
+                    v += c->init_rand_a[j] + c->init_rand_b[j] * rng_normal<double>(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j));
+            }
+        }
+        init[j] = (R)v;
+    }
+    e.episode = k + 1;
+    Physics<SYS, R>::set_init(e, init);
+    Physics<SYS, R>::state(e, state);
+    NoiseSrc<R> ns; ns.row = nullptr; ns.philox = philox; ns.key = key; ns.stream = SCG_STREAM_RESET; ns.idx = (uint32_t)k; ns.slot = 0;
+    make_obs<SYS, R>(T, c, state, n, 0, 0, true, ns, obs);
+}
+
+struct StepInfo {
+    int done, truncated, cviol, out_of_bounds, goal_reached, current_step;
+};
+
+// np.round(x, 8) (constraints.py:109): rint(x*1e8)/1e8, always evaluated in double like the reference
+__device__ __forceinline__ double round8(double x) { return rint(x * 1e8) / 1e8; }
+
+// One control step WITHOUT auto-reset.  action[NU] is the raw controller action.  On return `state` holds env.state,
+// obs the new observation, rew/mse the reward and info['mse'], cvals / cvals_f32 (nullable, global memory) the constraint values.
+template <int SYS, typename R>
+__device__ __forceinline__ void env_step(const DevTables& T, const scg_config* c, int n, EnvRegs<SYS, R>& e, const R* action, const double* noise_row,
+                                         R* state, R* obs, R& rew_out, R& mse_out, StepInfo& info, double* cvals, float* cvals_f32) {
+    constexpr int NX = SysDims<SYS>::NX, NU = SysDims<SYS>::NU;
+    const int steps = c->pyb_freq / c->ctrl_freq;
+    const R dt = (R)(1.0 / (double)c->pyb_freq);
+    const int pyb_step = e.ctrl_step * steps;
+    NoiseSrc<R> ns; ns.row = noise_row; ns.philox = c->rng_mode == SCG_RNG_PHILOX;
+    ns.key.k0 = (uint32_t)c->seed; ns.key.k1 = (uint32_t)(c->seed >> 32); ns.key.genv = (uint32_t)(c->env_index_offset + n);
+    ns.stream = SCG_STREAM_STEP; ns.idx = e.total_steps; ns.slot = 0;
+
+    R noisy[NU], clipped[NU];
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+        if (SYS == SCG_SYS_CARTPOLE) noisy[k] = c->normalized_action ? (R)c->hover_thrust * action[k] : action[k];              // cartpole.py:527-528
+        else noisy[k] = c->normalized_action ? ((R)1 + (R)c->norm_act_scale * action[k]) * (R)c->hover_thrust : action[k];     // quadrotor.py:772-773
+    }
+    if (c->n_dist[SCG_MODE_ACTION] > 0)
+        apply_disturbances<R>(c, T.st.dist_off, T.N, n, SCG_MODE_ACTION, e.ctrl_step, pyb_step, noisy, NU, ns);
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+        R t = noisy[k];
+        t = t < (R)c->act_low[k] ? (R)c->act_low[k] : t;
+        t = t > (R)c->act_high[k] ? (R)c->act_high[k] : t;
+        clipped[k] = t;
+    }
+    const bool has_dyn = c->n_dist[SCG_MODE_DYNAMICS] > 0;
+    R fd[3] = {(R)0, (R)0, (R)0};
+    if (has_dyn) {
+        const int ddim = (SYS == SCG_SYS_CARTPOLE) ? 2 : (SYS == SCG_SYS_QUAD1D) ? 1 : (SYS == SCG_SYS_QUAD2D) ? 2 : 3;
+        apply_disturbances<R>(c, T.st.dist_off, T.N, n, SCG_MODE_DYNAMICS, e.ctrl_step, pyb_step, fd, ddim, ns);
+    }
+    if (SYS == SCG_SYS_CARTPOLE) {
+        Physics<SYS, R>::advance(c, e, clipped, fd, has_dyn, steps, dt);
+    } else {
+        R f[4]; quad_motor_forces<SYS, R>(c, clipped, f);
+        Physics<SYS, R>::advance(c, e, f, fd, has_dyn, steps, dt);
+    }
+    Physics<SYS, R>::state(e, state);
+    make_obs<SYS, R>(T, c, state, n, e.ctrl_step, pyb_step, false, ns, obs);
+
+    // ---- reward (quadrotor.py:819-862, cartpole.py:611-652)
+    R rew;
+    if (c->cost == SCG_COST_RL_REWARD) {
+        const double* g = goal_row<R>(T, c, NX, e.ctrl_step + 1);
+        R dist = (R)0;
+#pragma unroll
+        for (int k = 0; k < NX; ++k) {
+            R sk = state[k];
+            if (SYS == SCG_SYS_CARTPOLE && k == 2) sk = normalize_angle<R>(sk);                                  // cartpole.py:620
+            R er = sk - (R)g[k];
+            dist += (R)c->rew_state_weight[k] * er * er;
+        }
+#pragma unroll
+        for (int k = 0; k < NU; ++k) {
+            R ae = (SYS == SCG_SYS_CARTPOLE) ? noisy[k] : noisy[k] - (R)c->u_goal[k];                             // cartpole.py:625 / quadrotor.py:829
+            dist += (R)c->rew_act_weight[k] * ae * ae;
+        }
+        rew = -dist;
+        if (c->rew_exponential) rew = Mth<R>::exp_(rew);
+    } else {
+        int idx = (SYS == SCG_SYS_CARTPOLE) ? e.ctrl_step : e.ctrl_step + 1;                                      // cartpole.py:648 / quadrotor.py:858
+        const double* g = goal_row<R>(T, c, NX, idx);
+        R l = (R)0;
+#pragma unroll
+        for (int k = 0; k < NX; ++k) { R er = state[k] - (R)g[k]; l += (R)0.5 * (R)c->Q[k] * er * er; }
+#pragma unroll
+        for (int k = 0; k < NU; ++k) { R ae = clipped[k] - (R)c->u_goal[k]; l += (R)0.5 * (R)c->R[k] * ae * ae; }
+        rew = -l;
+    }
+    // ---- done (quadrotor.py:864-894, cartpole.py:654-672)
+    int done = 0, goal_reached = 0, oob = 0;
+    if (c->task == SCG_TASK_STABILIZATION) {
+        R n2 = (R)0;
+#pragma unroll
+        for (int k = 0; k < NX; ++k) { R er = state[k] - (R)T.x_goal[k]; n2 += er * er; }
+        goal_reached = Mth<R>::sqrt_(n2) < (R)c->goal_tolerance;
+        done = goal_reached;
+    }
+    if (!done && c->done_on_out_of_bound) {
+        if (SYS == SCG_SYS_CARTPOLE) {
+            R x = state[0], th = state[2];
+            oob = (x < -(R)c->x_threshold) || (x > (R)c->x_threshold) || (th < -(R)c->theta_threshold) || (th > (R)c->theta_threshold);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NX; ++k) {
+                const bool masked = (SYS == SCG_SYS_QUAD3D) ? ((k % 2 == 0 && k < 6) || (k >= 6 && k < 9)) : (k % 2 == 0);  // quadrotor.py:878-883
+                if (masked) oob |= ((double)state[k] < c->state_low[k]) || ((double)state[k] > c->state_high[k]);
+            }
+        }
+        done = oob;
+    }
+    // ---- info['mse'] (quadrotor.py:907-922, cartpole.py:685-695)
+    R mse = (R)0;
+    {
+        const double* g = goal_row<R>(T, c, NX, e.ctrl_step + 1);
+#pragma unroll
+        for (int k = 0; k < NX; ++k) {
+            R sk = state[k];
+            if (c->task == SCG_TASK_TRAJ_TRACKING) {
+                const bool is_angle = (SYS == SCG_SYS_CARTPOLE && k == 2) || (SYS == SCG_SYS_QUAD2D && k == 4) || (SYS == SCG_SYS_QUAD3D && k >= 6 && k < 9);
+                if (is_angle) sk = normalize_angle<R>(sk);
+            }
+            R er = (sk - (R)g[k]) * (R)c->mse_weight[k];
+            mse += er * er;
+        }
+    }
+    // ---- after_step (benchmark_env.py:447-502)
+    e.ctrl_step += 1; e.total_steps += 1;
+    int cviol = 0;
+    if (T.n_con > 0) {
+        for (int r = 0; r < T.n_con; ++r) {
+            double acc = 0;
+            for (int p = T.con_ptr[r]; p < T.con_ptr[r + 1]; ++p) {
+                const int ci = T.con_col[p];
+                double z = 0;
+#pragma unroll
+                for (int k = 0; k < NX; ++k) if (ci == k) z = (double)state[k];
+#pragma unroll
+                for (int k = 0; k < NU; ++k) if (ci == NX + k) z = (double)noisy[k];                              // constraints.py:168-169
+                acc += T.con_val[p] * z;
+            }
+            if (T.con_kind[r] == SCG_CON_ABS) acc = fabs(acc);
+            const double g = round8(acc - T.con_b[r]);
+            if (cvals) cvals[r] = g;
+            if (cvals_f32) cvals_f32[r] = (float)g;
+            cviol |= T.con_strict[r] ? (g >= 0.0) : (g > 0.0);                                                    // constraints.py:126-129
+        }
+        if (cviol && c->done_on_violation) { done = 1; if (c->cost == SCG_COST_RL_REWARD && c->use_constraint_penalty) rew = (R)0; }
+        if (c->cost == SCG_COST_RL_REWARD && c->use_constraint_penalty && cviol) {
+            if (c->rew_exponential) rew = Mth<R>::exp_(Mth<R>::log_(rew) - (R)c->constraint_penalty);
+            else rew -= (R)c->constraint_penalty;
+        }
+    }
+    int truncated = 0;
+    if (e.ctrl_step >= c->ctrl_steps) { truncated = !done; done = 1; }
+    rew_out = rew; mse_out = mse;
+    info.done = done; info.truncated = truncated; info.cviol = cviol; info.out_of_bounds = oob; info.goal_reached = goal_reached; info.current_step = e.ctrl_step;
+}

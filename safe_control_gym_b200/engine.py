@@ -1,0 +1,223 @@
+'''EngineHandle: thin Python owner of one `scg_env` (a batch of N envs on one GPU).
+
+torch is used for device memory and streams only (plumbing): every output buffer is a torch.cuda tensor
+allocated here and handed to the C-ABI as a raw pointer; results are returned as those tensors.
+'''
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from safe_control_gym_b200 import _abi
+from safe_control_gym_b200.envs import disturbances as dist_mod
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def policy_blob_layout(obs_dim, act_dim, hid):
+    '''Float offsets of the packed policy blob (csrc/scg_kernels.cuh: blob_layout).'''
+    def pad4(x):
+        return (x + 3) & ~3
+    w1t = 0
+    b1 = w1t + obs_dim * 2 * hid
+    w2t = b1 + 2 * hid
+    b2 = w2t + 2 * hid * hid
+    w3 = b2 + 2 * hid
+    b3 = w3 + (act_dim + 1) * hid
+    logstd = b3 + pad4(act_dim + 1)
+    total = logstd + pad4(act_dim)
+    return dict(w1t=w1t, b1=b1, w2t=w2t, b2=b2, w3=w3, b3=b3, logstd=logstd, total=total)
+
+
+def pack_policy(ac, device):
+    '''MLPActorCritic (ppo_utils.py:197-238 layout: actor.pi_net.fcs.{0,1,2}, actor.logstd, critic.v_net.fcs.{0,1,2})
+    -> packed device blob, built with torch ops on the GPU (no host round trip).'''
+    a, c = ac.actor.pi_net.fcs, ac.critic.v_net.fcs
+    if len(a) != 3 or len(c) != 3:
+        raise NotImplementedError('the fused collector supports two hidden layers (hidden_dims=[h, h])')
+    obs_dim, hid, act_dim = a[0].in_features, a[0].out_features, a[2].out_features
+    L = policy_blob_layout(obs_dim, act_dim, hid)
+    blob = torch.zeros(L['total'], dtype=torch.float32, device=device)
+    with torch.no_grad():
+        f = lambda t: t.detach().to(device=device, dtype=torch.float32)
+        blob[L['w1t']:L['b1']] = torch.cat([f(a[0].weight).t(), f(c[0].weight).t()], dim=1).reshape(-1)        # [obs][2H]
+        blob[L['b1']:L['w2t']] = torch.cat([f(a[0].bias), f(c[0].bias)])
+        blob[L['w2t']:L['b2']] = torch.stack([f(a[1].weight).t(), f(c[1].weight).t()]).reshape(-1)             # [2][k][u]
+        blob[L['b2']:L['w3']] = torch.cat([f(a[1].bias), f(c[1].bias)])
+        blob[L['w3']:L['b3']] = torch.cat([f(a[2].weight), f(c[2].weight)], dim=0).reshape(-1)                 # [A+1][H]
+        blob[L['b3']:L['b3'] + act_dim + 1] = torch.cat([f(a[2].bias), f(c[2].bias)])
+        blob[L['logstd']:L['logstd'] + act_dim] = f(ac.actor.logstd)
+    return blob, (obs_dim, act_dim, hid)
+
+
+class EngineHandle:
+    def __init__(self, env, num_envs=1, auto_reset=False, rng_mode='table', seed=0, env_index_offset=0, device=None, precision=None):
+        self.lib = _abi.lib()
+        self.env = env
+        self.N = int(num_envs)
+        self.cfg = env.build_config(num_envs=num_envs, auto_reset=auto_reset, env_index_offset=env_index_offset,
+                                    rng_mode=rng_mode, seed=seed, device=device, precision=precision)
+        self.rng_mode = rng_mode
+        self.device_index = int(self.cfg.device)
+        self.device = torch.device('cuda', self.device_index)
+        h = C.c_void_p()
+        _abi.check(self.lib.scg_create(C.byref(self.cfg), C.byref(h)), None)
+        self.h = h
+        dims = [C.c_int32() for _ in range(6)]
+        _abi.check(self.lib.scg_dims(self.h, *[C.byref(d) for d in dims]), self.h)
+        self.nx, self.nu, self.obs_dim, _, self.P, self.D = [d.value for d in dims]
+        xg = env._x_goal_table()
+        _abi.check(self.lib.scg_set_reference(self.h, _np_ptr(xg), xg.shape[0]), self.h)
+        self.n_con = 0
+        if env.constraints is not None:
+            kind, strict, ptr, col, val, b = env.constraints.csr()
+            self.n_con = len(kind)
+            _abi.check(self.lib.scg_set_constraints(self.h, self.n_con, _np_ptr(kind), _np_ptr(strict), _np_ptr(ptr), _np_ptr(col),
+                                                    _np_ptr(val), _np_ptr(b)), self.h)
+        self._step_bufs = None
+
+    # -- tables ---------------------------------------------------------------------------------
+    def set_episode_table(self, tab, restart=False):
+        tab = np.ascontiguousarray(tab, dtype=np.float64)
+        assert tab.ndim == 3 and tab.shape[1] == self.N and tab.shape[2] == self.P, (tab.shape, self.N, self.P)
+        _abi.check(self.lib.scg_set_episode_table(self.h, _np_ptr(tab), tab.shape[0]), self.h)
+
+    def set_noise_table(self, tab):
+        tab = np.ascontiguousarray(tab, dtype=np.float64)
+        assert tab.ndim == 3 and tab.shape[1] == self.N and tab.shape[2] == self.D, (tab.shape, self.N, self.D)
+        _abi.check(self.lib.scg_set_noise_table(self.h, _np_ptr(tab), tab.shape[0]), self.h)
+
+    # -- env API --------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self, mask=None):
+        dev = self.device
+        obs = torch.empty(self.N, self.obs_dim, dtype=torch.float32, device=dev)
+        obs64 = torch.empty(self.N, self.obs_dim, dtype=torch.float64, device=dev)
+        st64 = torch.empty(self.N, self.nx, dtype=torch.float64, device=dev)
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, dtype=torch.uint8, device=dev).contiguous()
+        _abi.check(self.lib.scg_reset(self.h, _ptr(m), _ptr(obs), _ptr(obs64), _ptr(st64), self._stream()), self.h)
+        return {'obs': obs, 'obs_f64': obs64, 'state_f64': st64}
+
+    def _alloc_step(self):
+        dev, N, od, nx, nc = self.device, self.N, self.obs_dim, self.nx, max(self.n_con, 1)
+        f32, f64, u8, i32 = torch.float32, torch.float64, torch.uint8, torch.int32
+        b = {
+            'obs': torch.empty(N, od, dtype=f32, device=dev), 'obs_f64': torch.empty(N, od, dtype=f64, device=dev),
+            'state_f64': torch.empty(N, nx, dtype=f64, device=dev),
+            'rew': torch.empty(N, dtype=f32, device=dev), 'rew_f64': torch.empty(N, dtype=f64, device=dev),
+            'done': torch.empty(N, dtype=u8, device=dev), 'truncated': torch.empty(N, dtype=u8, device=dev),
+            'cviol': torch.empty(N, dtype=f32, device=dev), 'cvals': torch.zeros(N, nc, dtype=f64, device=dev),
+            'mse': torch.empty(N, dtype=f64, device=dev),
+            'out_of_bounds': torch.empty(N, dtype=u8, device=dev), 'goal_reached': torch.empty(N, dtype=u8, device=dev),
+            'current_step': torch.empty(N, dtype=i32, device=dev),
+            'terminal_obs': torch.empty(N, od, dtype=f32, device=dev), 'terminal_obs_f64': torch.empty(N, od, dtype=f64, device=dev),
+            'terminal_state_f64': torch.empty(N, nx, dtype=f64, device=dev),
+        }
+        return b
+
+    def step(self, actions, fresh_buffers=True):
+        '''actions: [N][nu] numpy / torch (float32 or float64).  Returns a dict of torch.cuda tensors.'''
+        dev = self.device
+        if isinstance(actions, np.ndarray):
+            actions = torch.from_numpy(np.ascontiguousarray(actions))
+        actions = actions.to(dev).reshape(self.N, self.nu).contiguous()
+        a32 = a64 = None
+        if actions.dtype == torch.float64:
+            a64 = actions
+        else:
+            a32 = actions.to(torch.float32)
+        b = self._alloc_step() if (fresh_buffers or self._step_bufs is None) else self._step_bufs
+        self._step_bufs = b
+        out = _abi.scg_step_out()
+        for name in ('obs', 'obs_f64', 'state_f64', 'rew', 'rew_f64', 'done', 'truncated', 'cviol', 'mse', 'out_of_bounds',
+                     'goal_reached', 'current_step', 'terminal_obs', 'terminal_obs_f64', 'terminal_state_f64'):
+            setattr(out, 'd_' + name, b[name].data_ptr())
+        out.d_cvals = b['cvals'].data_ptr() if self.n_con > 0 else None
+        _abi.check(self.lib.scg_step(self.h, _ptr(a32), _ptr(a64), C.byref(out), self._stream()), self.h)
+        return b
+
+    def rollout(self, policy_blob, dims, T, eps=None, activation='tanh', gamma=0.99, gae_lambda=0.95, use_gae=False,
+                deterministic=False, envs_per_block=0, want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode'), out=None):
+        '''One fused launch: T steps of policy + env for all N envs.  Returns PPOBuffer-shaped torch.cuda tensors.'''
+        dev, N = self.device, self.N
+        obs_dim, act_dim, hid = dims
+        f32 = torch.float32
+        if out is None:
+            out = {
+                'obs': torch.empty(T, N, obs_dim, dtype=f32, device=dev), 'act': torch.empty(T, N, act_dim, dtype=f32, device=dev),
+                'rew': torch.empty(T, N, 1, dtype=f32, device=dev), 'mask': torch.empty(T, N, 1, dtype=f32, device=dev),
+                'v': torch.empty(T, N, 1, dtype=f32, device=dev), 'logp': torch.empty(T, N, 1, dtype=f32, device=dev),
+                'terminal_v': torch.empty(T, N, 1, dtype=f32, device=dev),
+            }
+            if 'ret' in want or 'adv' in want:
+                out['ret'] = torch.empty(T, N, 1, dtype=f32, device=dev)
+                out['adv'] = torch.empty(T, N, 1, dtype=f32, device=dev)
+            if 'cviol' in want:
+                out['cviol'] = torch.empty(T, N, 1, dtype=f32, device=dev)
+            if 'cvals' in want and self.n_con > 0:
+                out['cvals'] = torch.empty(T, N, self.n_con, dtype=f32, device=dev)
+            if 'mse' in want:
+                out['mse'] = torch.empty(T, N, 1, dtype=f32, device=dev)
+            if 'last' in want:
+                out['last_obs'] = torch.empty(N, obs_dim, dtype=f32, device=dev)
+                out['last_val'] = torch.empty(N, 1, dtype=f32, device=dev)
+            if 'episode' in want:
+                out['ep_return_sum'] = torch.empty(N, dtype=f32, device=dev)
+                out['ep_length_sum'] = torch.empty(N, dtype=f32, device=dev)
+                out['ep_cviol_sum'] = torch.empty(N, dtype=f32, device=dev)
+                out['ep_count'] = torch.empty(N, dtype=torch.int32, device=dev)
+        ro = _abi.scg_rollout_out()
+        for name in ('obs', 'act', 'rew', 'mask', 'v', 'logp', 'terminal_v', 'ret', 'adv', 'cviol', 'cvals', 'mse', 'last_obs', 'last_val',
+                     'ep_return_sum', 'ep_length_sum', 'ep_cviol_sum', 'ep_count'):
+            setattr(ro, 'd_' + name, out[name].data_ptr() if name in out else None)
+        args = _abi.scg_rollout_args()
+        args.T, args.obs_dim, args.act_dim, args.hidden_dim = int(T), int(obs_dim), int(act_dim), int(hid)
+        args.activation = _abi.ACTIVATIONS[activation] if isinstance(activation, str) else int(activation)
+        args.use_gae, args.deterministic, args.envs_per_block = int(bool(use_gae)), int(bool(deterministic)), int(envs_per_block)
+        args.gamma, args.gae_lambda = float(gamma), float(gae_lambda)
+        args.d_policy = policy_blob.data_ptr()
+        if eps is not None:
+            assert eps.dtype == torch.float32 and eps.is_cuda and tuple(eps.shape) == (T, N, act_dim), (eps.dtype, eps.shape)
+            eps = eps.contiguous()
+        args.d_eps = eps.data_ptr() if eps is not None else None
+        _abi.check(self.lib.scg_rollout(self.h, C.byref(args), C.byref(ro), self._stream()), self.h)
+        return out
+
+    # -- checkpoint -----------------------------------------------------------------------------
+    def get_state(self):
+        n = C.c_size_t()
+        _abi.check(self.lib.scg_state_bytes(self.h, C.byref(n)), self.h)
+        buf = np.empty(n.value, dtype=np.uint8)
+        _abi.check(self.lib.scg_get_state(self.h, _np_ptr(buf), n.value, self._stream()), self.h)
+        return buf
+
+    def set_state(self, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        _abi.check(self.lib.scg_set_state(self.h, _np_ptr(buf), buf.size, self._stream()), self.h)
+
+    def launch_count(self):
+        n = C.c_uint64()
+        _abi.check(self.lib.scg_launch_count(self.h, C.byref(n)), self.h)
+        return n.value
+
+    def close(self):
+        if getattr(self, 'h', None) is not None and self.h:
+            self.lib.scg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
