@@ -1,5 +1,224 @@
-DEFAULT_CONFIG = {}
+'''PPO with the fused B200 rollout collector.
+
+Same controller API as safe_control_gym/controllers/ppo/ppo.py (`make('ppo', env_func, **config)`, `reset`, `learn`,
+`train_step`, `run`, `select_action`, `save`, `load`, `close`).  What changes is `train_step()`: the reference's
+host loop of `rollout_steps` x (`ac.step` -> `env.step` -> buffer push) (ppo.py:266-285) plus
+`compute_returns_and_advantages` (ppo.py:289-299) is ONE `scg_rollout` launch that leaves the PPOBuffer tensors
+(obs, act, rew, mask, v, logp, terminal_v, ret, adv) in HBM; the clipped-surrogate update then reads them in place.
+
+Multi-GPU (one process per GPU, torch.distributed/NCCL): every rank rolls out its own shard of the env batch
+(env index offset = rank * shard, so seeds stay `seed + global index`), the shards are exchanged with a single
+all-gather of the rollout buffer, and every rank applies the identical update (same permutation seed), which keeps
+the replicas in lock-step without a gradient all-reduce.
+'''
+
+import os
+import time
+
+import numpy as np
+import torch
+
+from safe_control_gym_b200.controllers.ppo.ppo_utils import PPOAgent
+from safe_control_gym_b200.engine import pack_policy
+from safe_control_gym_b200.envs.env_wrappers.record_episode_statistics import VecRecordEpisodeStatistics
+from safe_control_gym_b200.envs.env_wrappers.vectorized_env import make_vec_envs
+from safe_control_gym_b200.math_and_models.normalization import BaseNormalizer
+
+# defaults of safe_control_gym/controllers/ppo/ppo.yaml:1-39
+DEFAULT_CONFIG = dict(
+    hidden_dim=64, activation='tanh', norm_obs=False, norm_reward=False, clip_obs=10, clip_reward=10,
+    gamma=0.99, use_gae=False, gae_lambda=0.95, use_clipped_value=False, clip_param=0.2, target_kl=0.01, entropy_coef=0.01,
+    opt_epochs=10, mini_batch_size=64, actor_lr=0.0003, critic_lr=0.001, max_grad_norm=0.5,
+    max_env_steps=1000000, num_workers=1, rollout_batch_size=4, rollout_steps=100, deque_size=10, eval_batch_size=10,
+    log_interval=0, save_interval=0, num_checkpoints=0, eval_interval=0, eval_save_best=False, tensorboard=False,
+)
 
 
-class PPO:  # placeholder, replaced below in this round
-    pass
+class _Logger:
+    '''Stand-in for ExperimentLogger (utils/logging.py is observability only, out of scope): keeps the last scalars.'''
+
+    def __init__(self, output_dir):
+        self.output_dir, self.scalars = output_dir, {}
+
+    def info(self, msg):
+        print(msg, flush=True)
+
+    def add_scalars(self, data, step, prefix=''):
+        for k, v in data.items():
+            self.scalars[f'{prefix}/{k}'] = (step, float(v))
+
+    def dump_scalars(self):
+        pass
+
+    def load(self, step):
+        pass
+
+    def close(self):
+        pass
+
+
+def all_gather_rollout(out, keys=('obs', 'act', 'rew', 'mask', 'v', 'logp', 'terminal_v', 'ret', 'adv')):
+    '''One NCCL all-gather of the packed [T][n][F] rollout record; returns tensors laid out [G*T][n][.] (the update
+    samples transitions uniformly, so the rank-major order is as good as env-major).'''
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    keys = [k for k in keys if k in out]
+    widths = [out[k].shape[-1] for k in keys]
+    packed = torch.cat([out[k] for k in keys], dim=-1).contiguous()            # [T][n][F]
+    gathered = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(gathered, packed)
+    T, n, F = packed.shape
+    gathered = gathered.reshape(world * T, n, F)
+    res, o = {}, 0
+    for k, w in zip(keys, widths):
+        res[k] = gathered[..., o:o + w]
+        o += w
+    return res
+
+
+class PPO:
+    '''Proximal policy optimisation on the fused collector.'''
+
+    def __init__(self, env_func, training=True, checkpoint_path='model_latest.pt', output_dir='temp', use_gpu=True, seed=0,
+                 rng_mode='philox', device=None, precision=None, **kwargs):
+        cfg = dict(DEFAULT_CONFIG)
+        cfg.update(kwargs)
+        for k, v in cfg.items():
+            self.__dict__[k] = v
+        self.env_func, self.training = env_func, training
+        self.checkpoint_path, self.output_dir, self.seed = checkpoint_path, output_dir, seed
+        if self.norm_obs or self.norm_reward:
+            raise NotImplementedError('running obs/reward normalisers reduce over the whole batch every step '
+                                      '(normalization.py:106-113,148-159) and are not available in the fused collector')
+        import torch.distributed as dist
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', 0)) if self.world > 1 else 0
+        self.device = torch.device('cuda', int(device))
+        if self.rollout_batch_size % self.world != 0:
+            raise ValueError('rollout_batch_size must be divisible by the number of ranks')
+        self.local_batch = self.rollout_batch_size // self.world
+        self.env = make_vec_envs(env_func, None, self.local_batch, self.num_workers, seed, rng_mode=rng_mode, device=int(device),
+                                 precision=precision, env_index_offset=self.rank * self.local_batch)
+        self.env = VecRecordEpisodeStatistics(self.env, self.deque_size)
+        self.eval_env = None
+        self.agent = PPOAgent(self.env.observation_space, self.env.action_space, hidden_dim=self.hidden_dim,
+                              use_clipped_value=self.use_clipped_value, clip_param=self.clip_param, target_kl=self.target_kl,
+                              entropy_coef=self.entropy_coef, actor_lr=self.actor_lr, critic_lr=self.critic_lr,
+                              opt_epochs=self.opt_epochs, mini_batch_size=self.mini_batch_size, activation=self.activation)
+        self.agent.to(self.device)
+        self.obs_normalizer, self.reward_normalizer = BaseNormalizer(), BaseNormalizer()
+        self.logger = _Logger(output_dir)
+        self._perm_gen = torch.Generator(device=self.device)
+        self._perm_gen.manual_seed(int(seed) + 12345)      # identical on every rank
+        self.total_steps = 0
+        self._rollout_out = None
+
+    # ------------------------------------------------------------------------------------------
+    def reset(self):
+        if self.training:
+            self.env.add_tracker('constraint_violation', 0)
+            self.env.add_tracker('constraint_violation', 0, mode='queue')
+            self.total_steps = 0
+            obs, _ = self.env.reset()
+            self.obs = obs
+
+    def close(self):
+        self.env.close()
+        if self.eval_env is not None:
+            self.eval_env.close()
+        self.logger.close()
+
+    def save(self, path):
+        os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
+        state = {'agent': self.agent.state_dict(), 'obs_normalizer': {}, 'reward_normalizer': {}}
+        if self.training:
+            state.update({'total_steps': self.total_steps, 'obs': self.obs.detach().cpu().numpy(),
+                          'random_state': {'torch': torch.get_rng_state(), 'perm': self._perm_gen.get_state()},
+                          'env_random_state': self.env.get_env_random_state()})
+        torch.save(state, path)
+
+    def load(self, path):
+        state = torch.load(path, weights_only=False, map_location=self.device)
+        self.agent.load_state_dict(state['agent'])
+        if self.training and 'env_random_state' in state and isinstance(state['env_random_state'][0], dict):
+            self.total_steps = state['total_steps']
+            self.obs = torch.as_tensor(state['obs'], dtype=torch.float32, device=self.device)
+            self._perm_gen.set_state(state['random_state']['perm'].cpu())
+            self.env.set_env_random_state(state['env_random_state'])
+
+    def learn(self, env=None, **kwargs):
+        while self.total_steps < self.max_env_steps:
+            results = self.train_step()
+            if self.total_steps >= self.max_env_steps or (self.save_interval and self.total_steps % self.save_interval == 0):
+                if self.rank == 0:
+                    self.save(self.checkpoint_path)
+            if self.eval_interval and self.total_steps % self.eval_interval == 0:
+                results['eval'] = self.run(n_episodes=self.eval_batch_size)
+            if self.log_interval and self.total_steps % self.log_interval == 0:
+                self.log_step(results)
+
+    def select_action(self, obs, info=None):
+        with torch.inference_mode():
+            obs = torch.as_tensor(obs, dtype=torch.float32, device=self.device)
+            return self.agent.ac.act(obs).cpu().numpy()
+
+    # ------------------------------------------------------------------------------------------
+    def collect(self, T=None, deterministic=False, eps=None):
+        '''The fused collector: one kernel launch for the whole horizon (replaces ppo.py:266-299).'''
+        T = self.rollout_steps if T is None else T
+        blob, dims = pack_policy(self.agent.ac, self.device)
+        eng = self.env.unwrapped.engine
+        out = eng.rollout(blob, dims, T, eps=eps, activation=self.activation, gamma=self.gamma, gae_lambda=self.gae_lambda,
+                          use_gae=self.use_gae, deterministic=deterministic, out=self._rollout_out if eps is None else None)
+        if eps is None:
+            self._rollout_out = out
+        return out
+
+    def train_step(self):
+        self.agent.train()
+        start = time.time()
+        out = self.collect()
+        self.obs = out['last_obs']
+        self.env.record_rollout(out)
+        self.total_steps += self.rollout_batch_size * self.rollout_steps
+        batch = all_gather_rollout(out) if self.world > 1 else out
+        adv = batch['adv']
+        rollouts = dict(batch)
+        rollouts['adv'] = (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-6)          # ppo.py:300 (numpy std, ddof=0)
+        results = self.agent.update(rollouts, self.device, generator=self._perm_gen)
+        results.update({'step': self.total_steps, 'elapsed_time': time.time() - start})
+        return results
+
+    def run(self, env=None, render=False, n_episodes=10, verbose=False):
+        '''Deterministic evaluation (ppo.py:210-257) as one fused rollout over `n_episodes` fresh envs.'''
+        self.agent.eval()
+        if self.eval_env is None or self.eval_env.num_envs != n_episodes:
+            if self.eval_env is not None:
+                self.eval_env.close()
+            self.eval_env = make_vec_envs(self.env_func, None, n_episodes, 1, self.seed * 111, rng_mode=self.env.unwrapped.rng_mode,
+                                          device=self.device.index)
+        self.eval_env.reset()
+        blob, dims = pack_policy(self.agent.ac, self.device)
+        T = int(self.eval_env.proto.CTRL_STEPS)
+        out = self.eval_env.engine.rollout(blob, dims, T, activation=self.activation, deterministic=True, want=('cviol', 'mse', 'episode'))
+        mask = out['mask'][..., 0]
+        first_done = torch.where((mask == 0).any(0), (mask == 0).float().argmax(0), torch.full((n_episodes,), T - 1, device=self.device))
+        steps = torch.arange(T, device=self.device)[:, None]
+        live = (steps <= first_done[None, :]).float()
+        ep_returns = (out['rew'][..., 0] * live).sum(0)
+        ep_lengths = first_done + 1
+        res = {'ep_returns': ep_returns.cpu().numpy(), 'ep_lengths': ep_lengths.cpu().numpy(),
+               'constraint_violation': (out['cviol'][..., 0] * live).sum(0).cpu().numpy(),
+               'mse': ((out['mse'][..., 0] * live).sum(0) / ep_lengths).cpu().numpy()}
+        return res
+
+    def log_step(self, results):
+        step = results['step']
+        self.logger.add_scalars({'step': step, 'step_time': results['elapsed_time'], 'progress': step / self.max_env_steps}, step, prefix='time')
+        self.logger.add_scalars({k: results[k] for k in ['policy_loss', 'value_loss', 'entropy_loss', 'approx_kl']}, step, prefix='loss')
+        if len(self.env.return_queue) > 0:
+            r, l = np.asarray(self.env.return_queue), np.asarray(self.env.length_queue)
+            self.logger.add_scalars({'ep_length': l.mean(), 'ep_return': r.mean(), 'ep_reward': (r / l).mean()}, step, prefix='stat')
+        self.logger.dump_scalars()

@@ -238,22 +238,93 @@ __device__ __noinline__ void apply_disturbances(const scg_config* c, const int32
 }
 
 // ---------------------------------------------------------------------------------------------
+// hot per-step constants, staged once per CTA into shared memory (the scg_config in global memory is only
+// touched again on the rare paths: disturbances and resets)
+// ---------------------------------------------------------------------------------------------
+struct ConRow { double val; double b; int32_t col; int32_t flags; };   // flags: bit0 strict, bit1 abs
+
+template <typename R> struct HotCfg {
+    int steps, ctrl_steps, task, cost, normalized_action, rew_exponential, done_on_oob, done_on_violation, use_penalty;
+    int obs_goal_horizon, obs_wrap, philox, has_dist[3], n_con, con_fast, L;
+    R dt, hover, act_scale, goal_tol, penalty, x_thr, th_thr;
+    R gravity, kf, inv_nm_kf, pwm_c, pwm_s, inv_pwm_s, pwm_min, pwm_max, arm, km_over_kf, pole_w2;
+    R act_low[SCG_MAX_NU], act_high[SCG_MAX_NU], u_goal[SCG_MAX_NU], rew_act_w[SCG_MAX_NU], Rw[SCG_MAX_NU];
+    R rew_state_w[SCG_MAX_NX], mse_w[SCG_MAX_NX], Qw[SCG_MAX_NX];
+    double state_low[SCG_MAX_NX], state_high[SCG_MAX_NX];   // float32-rounded bounds, compared in double like numpy does
+    ConRow rows[SCG_MAX_CON_ROWS];
+};
+
+// executed by ONE thread of the CTA, followed by a __syncthreads() in the caller
+template <int SYS, typename R>
+__device__ __noinline__ void hot_load(const DevTables& T, HotCfg<R>* h) {
+    constexpr int NU = SysDims<SYS>::NU;
+    const scg_config* c = T.cfg;
+    h->steps = c->pyb_freq / c->ctrl_freq; h->ctrl_steps = c->ctrl_steps; h->task = c->task; h->cost = c->cost;
+    h->normalized_action = c->normalized_action; h->rew_exponential = c->rew_exponential; h->done_on_oob = c->done_on_out_of_bound;
+    h->done_on_violation = c->done_on_violation; h->use_penalty = c->use_constraint_penalty;
+    h->obs_goal_horizon = (c->cost == SCG_COST_RL_REWARD) ? c->obs_goal_horizon : 0; h->obs_wrap = c->obs_wrap_angle;
+    h->philox = c->rng_mode == SCG_RNG_PHILOX;
+    for (int m = 0; m < 3; ++m) h->has_dist[m] = c->n_dist[m] > 0;
+    h->L = T.L;
+    h->dt = (R)(1.0 / (double)c->pyb_freq); h->hover = (R)c->hover_thrust; h->act_scale = (R)c->norm_act_scale;
+    h->goal_tol = (R)c->goal_tolerance; h->penalty = (R)c->constraint_penalty; h->x_thr = (R)c->x_threshold; h->th_thr = (R)c->theta_threshold;
+    h->gravity = (R)c->gravity; h->kf = (R)c->kf; h->inv_nm_kf = (R)(1.0 / ((double)(4 / NU) * c->kf));
+    h->pwm_c = (R)c->pwm2rpm_const; h->pwm_s = (R)c->pwm2rpm_scale; h->inv_pwm_s = (R)(1.0 / c->pwm2rpm_scale);
+    h->pwm_min = (R)c->pwm_min; h->pwm_max = (R)c->pwm_max; h->arm = (R)c->arm; h->km_over_kf = (R)(c->km / c->kf);
+    h->pole_w2 = (R)(c->pole_width * c->pole_width);
+    for (int k = 0; k < SCG_MAX_NU; ++k) {
+        h->act_low[k] = (R)c->act_low[k]; h->act_high[k] = (R)c->act_high[k]; h->u_goal[k] = (R)c->u_goal[k];
+        h->rew_act_w[k] = (R)c->rew_act_weight[k]; h->Rw[k] = (R)c->R[k];
+    }
+    for (int k = 0; k < SCG_MAX_NX; ++k) {
+        h->rew_state_w[k] = (R)c->rew_state_weight[k]; h->mse_w[k] = (R)c->mse_weight[k]; h->Qw[k] = (R)c->Q[k];
+        h->state_low[k] = c->state_low[k]; h->state_high[k] = c->state_high[k];
+    }
+    h->n_con = T.n_con; h->con_fast = 1;
+    for (int r = 0; r < T.n_con; ++r) {
+        const int p0 = T.con_ptr[r], p1 = T.con_ptr[r + 1];
+        if (p1 - p0 > 1) h->con_fast = 0;
+        ConRow row; row.col = p1 > p0 ? T.con_col[p0] : 0; row.val = p1 > p0 ? T.con_val[p0] : 0.0; row.b = T.con_b[r];
+        row.flags = (T.con_strict[r] ? 1 : 0) | (T.con_kind[r] == SCG_CON_ABS ? 2 : 0);
+        h->rows[r] = row;
+    }
+}
+
+// small-angle sine / cosine (|x| <= 0.05): Taylor series, error below 1 ulp of the result scale in both precisions
+template <typename R> __device__ __forceinline__ void sincos_small(R x, R* s, R* c) {
+    const R x2 = x * x;
+    if (sizeof(R) == 8) {
+        R ps = (R)(-1.0 / 5040.0) + x2 * (R)(1.0 / 362880.0);
+        ps = (R)(1.0 / 120.0) + x2 * ps; ps = (R)(-1.0 / 6.0) + x2 * ps;
+        *s = x + x * x2 * ps;
+        R pc = (R)(-1.0 / 720.0) + x2 * ((R)(1.0 / 40320.0) - x2 * (R)(1.0 / 3628800.0));
+        pc = (R)(1.0 / 24.0) + x2 * pc; pc = (R)(-0.5) + x2 * pc;
+        *c = (R)1 + x2 * pc;
+    } else {
+        R ps = (R)(-1.0 / 6.0) + x2 * (R)(1.0 / 120.0);
+        *s = x + x * x2 * ps;
+        R pc = (R)(-0.5) + x2 * ((R)(1.0 / 24.0) - x2 * (R)(1.0 / 720.0));
+        *c = (R)1 + x2 * pc;
+    }
+}
+#define SCG_SMALL_ANGLE 0.05
+
+// ---------------------------------------------------------------------------------------------
 // physics
 // ---------------------------------------------------------------------------------------------
-// quadrotor.py:722-747 + quadrotor_utils.py:16-60: thrust command(s) -> per-motor thrust kf*rpm^2
+// quadrotor.py:722-747 + quadrotor_utils.py:16-60: clipped thrust command(s) -> per-motor thrust kf*rpm^2
 template <int SYS, typename R>
-__device__ __forceinline__ void quad_motor_forces(const scg_config* c, const R* thrust, R f[4]) {
+__device__ __forceinline__ void quad_motor_forces(const HotCfg<R>* h, const R* thrust, R f[4]) {
     constexpr int NU = SysDims<SYS>::NU;
-    constexpr int n_motor = 4 / NU;
     R mf[NU];
 #pragma unroll
     for (int k = 0; k < NU; ++k) {
         R t = thrust[k] < (R)0 ? (R)0 : thrust[k];
-        R pwm = (Mth<R>::sqrt_(t / (R)n_motor / (R)c->kf) - (R)c->pwm2rpm_const) / (R)c->pwm2rpm_scale;
-        pwm = pwm < (R)c->pwm_min ? (R)c->pwm_min : pwm;
-        pwm = pwm > (R)c->pwm_max ? (R)c->pwm_max : pwm;
-        R rpm = (R)c->pwm2rpm_scale * pwm + (R)c->pwm2rpm_const;
-        mf[k] = rpm * rpm * (R)c->kf;
+        R pwm = (Mth<R>::sqrt_(t * h->inv_nm_kf) - h->pwm_c) * h->inv_pwm_s;
+        pwm = pwm < h->pwm_min ? h->pwm_min : pwm;
+        pwm = pwm > h->pwm_max ? h->pwm_max : pwm;
+        R rpm = h->pwm_s * pwm + h->pwm_c;
+        mf[k] = rpm * rpm * h->kf;
     }
     if (NU == 1) { f[0] = f[1] = f[2] = f[3] = mf[0]; }
     else if (NU == 2) { f[0] = mf[0]; f[1] = mf[1 % NU]; f[2] = mf[1 % NU]; f[3] = mf[0]; }   // quadrotor_utils.py:39
@@ -272,10 +343,9 @@ template <typename R> __device__ __forceinline__ void rpy_from_quat(const R q[4]
         rpy[2] = Mth<R>::atan2_((R)2 * (q[0] * q[1] + q[3] * q[2]), squ + sqx - sqy - sqz);
     }
 }
-template <typename R> __device__ __forceinline__ void rot_from_quat(const R q[4], R M[9]) {
-    R d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
-    R s = (R)2 / d;
-    R xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
+// body -> world rotation of a UNIT quaternion (the integrator renormalises every sub-step, like Bullet)
+template <typename R> __device__ __forceinline__ void rot_from_unit_quat(const R q[4], R M[9]) {
+    R xs = q[0] + q[0], ys = q[1] + q[1], zs = q[2] + q[2];
     R wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
     R xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs;
     R yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
@@ -284,27 +354,35 @@ template <typename R> __device__ __forceinline__ void rot_from_quat(const R q[4]
     M[6] = xz - wy; M[7] = yz + wx; M[8] = (R)1 - (xx + yy);
 }
 
-// advance one control step = `steps` Bullet sub-steps (base_aviary.py:243-282 / cartpole.py:552-583)
+// advance one control step = `steps` Bullet sub-steps (base_aviary.py:243-282 / cartpole.py:552-583):
+// semi-implicit Euler per sub-step -- velocities with the accelerations at the current pose, then poses with the NEW velocities.
 template <int SYS, typename R> struct Physics;
 
 template <typename R> struct Physics<SCG_SYS_CARTPOLE, R> {
     // ps = x, xdot, theta, thetadot ; inertial = pole_length, cart_mass, pole_mass
-    static __device__ __forceinline__ void advance(const scg_config* c, EnvRegs<SCG_SYS_CARTPOLE, R>& e, const R* force, const R* tap, bool has_tap, int steps, R dt) {
-        const R l = e.inertial[0], M = e.inertial[1], m = e.inertial[2], g = (R)c->gravity;
-        const R w = (R)c->pole_width;
-        const R Ic = m / (R)12 * (((R)2 * l) * ((R)2 * l) + w * w);   // box inertia PyBullet recomputes (cartpole.py:301-304,318-322)
-        const R a11 = M + m, a22 = Ic + m * l * l, ml = m * l;
+    static __device__ __forceinline__ void advance(const HotCfg<R>* h, EnvRegs<SCG_SYS_CARTPOLE, R>& e, const R* force, const R* tap, bool has_tap) {
+        const R l = e.inertial[0], M = e.inertial[1], m = e.inertial[2], g = h->gravity, dt = h->dt;
+        const R Ic = m * (R)(1.0 / 12.0) * (((R)2 * l) * ((R)2 * l) + h->pole_w2);   // box inertia PyBullet recomputes (cartpole.py:301-304,318-322)
+        const R a11 = M + m, a22 = Ic + m * l * l, ml = m * l, mgl = m * g * l;
         R x = e.ps[0], xd = e.ps[1], th = e.ps[2], thd = e.ps[3];
+        R st, ct; Mth<R>::sincos_(th, &st, &ct);
+        const int steps = h->steps;
         for (int s = 0; s < steps; ++s) {
-            R st, ct; Mth<R>::sincos_(th, &st, &ct);
             R Qx = force[0], Qth = (R)0;
             if (has_tap) { Qx += tap[0]; Qth += tap[0] * l * ct - tap[1] * l * st; }
-            R a12 = ml * ct;
-            R b1 = Qx + ml * st * thd * thd, b2 = Qth + m * g * l * st;
-            R det = a11 * a22 - a12 * a12;
-            R xdd = (a22 * b1 - a12 * b2) / det, thdd = (a11 * b2 - a12 * b1) / det;
-            xd += xdd * dt; thd += thdd * dt;          // symplectic Euler: velocities first,
-            x += xd * dt; th += thd * dt;              // positions with the new velocities
+            const R a12 = ml * ct;
+            const R b1 = Qx + ml * st * thd * thd, b2 = Qth + mgl * st;
+            const R idet = (R)1 / (a11 * a22 - a12 * a12);
+            const R xdd = (a22 * b1 - a12 * b2) * idet, thdd = (a11 * b2 - a12 * b1) * idet;
+            xd += xdd * dt; thd += thdd * dt;
+            x += xd * dt;
+            const R dth = thd * dt; th += dth;
+            if (s + 1 < steps) {   // sin/cos of the new angle: rotate by the (small) increment, exact re-evaluation otherwise
+                if (Mth<R>::abs_(dth) <= (R)SCG_SMALL_ANGLE) {
+                    R sd, cd; sincos_small<R>(dth, &sd, &cd);
+                    const R s2 = st * cd + ct * sd; ct = ct * cd - st * sd; st = s2;
+                } else Mth<R>::sincos_(th, &st, &ct);
+            }
         }
         e.ps[0] = x; e.ps[1] = xd; e.ps[2] = th; e.ps[3] = thd;
     }
@@ -318,13 +396,13 @@ template <typename R> struct Physics<SCG_SYS_CARTPOLE, R> {
 
 template <typename R> struct Physics<SCG_SYS_QUAD1D, R> {
     // vertical motion only: orientation stays identity, thrust along world z
-    static __device__ __forceinline__ void advance(const scg_config* c, EnvRegs<SCG_SYS_QUAD1D, R>& e, const R f[4], const R* fd, bool has_dist, int steps, R dt) {
-        const R m = e.inertial[0];
+    static __device__ __forceinline__ void advance(const HotCfg<R>* h, EnvRegs<SCG_SYS_QUAD1D, R>& e, const R f[4], const R* fd, bool has_dist) {
+        const R m = e.inertial[0], dt = h->dt;
         R thrust = f[0] + f[1] + f[2] + f[3];
-        R Fz = thrust - m * (R)c->gravity; if (has_dist) Fz += fd[0];
+        R Fz = thrust - m * h->gravity; if (has_dist) Fz += fd[0];
         R az = Fz / m;
         R z = e.ps[2], vz = e.ps[3], x = e.ps[0], vx = e.ps[1];
-        for (int s = 0; s < steps; ++s) { vz += az * dt; z += vz * dt; x += vx * dt; }
+        for (int s = 0; s < h->steps; ++s) { vz += az * dt; z += vz * dt; x += vx * dt; }
         e.ps[2] = z; e.ps[3] = vz; e.ps[0] = x;
     }
     static __device__ __forceinline__ void state(const EnvRegs<SCG_SYS_QUAD1D, R>& e, R* s) { s[0] = e.ps[2]; s[1] = e.ps[3]; }
@@ -336,19 +414,29 @@ template <typename R> struct Physics<SCG_SYS_QUAD1D, R> {
 
 template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
     // ps = x, vx, z, vz, theta, omega_y ; inertial = M, Ixx, Iyy, Izz
-    static __device__ __forceinline__ void advance(const scg_config* c, EnvRegs<SCG_SYS_QUAD2D, R>& e, const R f[4], const R* fd, bool has_dist, int steps, R dt) {
-        const R m = e.inertial[0], Iyy = e.inertial[2];
+    // Within a control step thrust and torque are constant, so omega grows linearly and the per-sub-step angle increment
+    // delta_k = omega_k dt grows by the constant eps = alpha dt^2: sin/cos(theta_k) follow from two plane rotations per
+    // sub-step (3 sincos per control step instead of one per sub-step).
+    static __device__ __forceinline__ void advance(const HotCfg<R>* h, EnvRegs<SCG_SYS_QUAD2D, R>& e, const R f[4], const R* fd, bool has_dist) {
+        const R dt = h->dt;
+        const R inv_m = (R)1 / e.inertial[0];
         const R thrust = f[0] + f[1] + f[2] + f[3];
-        const R tau_y = (R)c->arm * (-f[0] + f[1] + f[2] - f[3]);      // r x F with the prop offsets of cf2x.urdf:42-78
-        const R alpha = tau_y / Iyy;
-        const R tm = thrust / m;
-        R fx = (R)0, fz = -(R)c->gravity;                              // gravity as force m*g over m
-        if (has_dist) { fx += fd[0] / m; fz += fd[1] / m; }
+        const R tau_y = h->arm * (-f[0] + f[1] + f[2] - f[3]);         // r x F with the prop offsets of cf2x.urdf:42-78
+        const R alpha = tau_y / e.inertial[2];
+        const R tm = thrust * inv_m;
+        R fx = (R)0, fz = -h->gravity;                                 // gravity enters as the force m g
+        if (has_dist) { fx += fd[0] * inv_m; fz += fd[1] * inv_m; }
         R x = e.ps[0], vx = e.ps[1], z = e.ps[2], vz = e.ps[3], th = e.ps[4], om = e.ps[5];
-        for (int s = 0; s < steps; ++s) {
-            R st, ct; Mth<R>::sincos_(th, &st, &ct);
-            vx += (st * tm + fx) * dt; vz += (ct * tm + fz) * dt; om += alpha * dt;
+        R st, ct; Mth<R>::sincos_(th, &st, &ct);
+        const R adt = alpha * dt, eps = adt * dt;
+        R sd, cd, se, ce;
+        Mth<R>::sincos_(om * dt, &sd, &cd);        // delta_0 = omega dt  (becomes delta_1 after the first eps rotation)
+        Mth<R>::sincos_(eps, &se, &ce);
+        for (int s = 0; s < h->steps; ++s) {
+            vx += (st * tm + fx) * dt; vz += (ct * tm + fz) * dt; om += adt;
             x += vx * dt; z += vz * dt; th += om * dt;
+            const R sd2 = sd * ce + cd * se; cd = cd * ce - sd * se; sd = sd2;        // delta += eps
+            const R st2 = st * cd + ct * sd; ct = ct * cd - st * sd; st = st2;        // theta += delta
         }
         e.ps[0] = x; e.ps[1] = vx; e.ps[2] = z; e.ps[3] = vz; e.ps[4] = th; e.ps[5] = om;
     }
@@ -371,50 +459,66 @@ template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
 
 template <typename R> struct Physics<SCG_SYS_QUAD3D, R> {
     // ps = pos[0..2], quat[3..6] (x,y,z,w), vel[7..9], omega_world[10..12]
-    static __device__ void advance(const scg_config* c, EnvRegs<SCG_SYS_QUAD3D, R>& e, const R f[4], const R* fd, bool has_dist, int steps, R dt) {
-        const R m = e.inertial[0];
+    static __device__ void advance(const HotCfg<R>* h, EnvRegs<SCG_SYS_QUAD3D, R>& e, const R f[4], const R* fd, bool has_dist) {
+        const R dt = h->dt;
+        const R m = e.inertial[0], inv_m = (R)1 / m;
         const R J0 = e.inertial[1], J1 = e.inertial[2], J2 = e.inertial[3];
-        const R a = (R)c->arm;
-        const R thrust = f[0] + f[1] + f[2] + f[3];
+        const R iJ0 = (R)1 / J0, iJ1 = (R)1 / J1, iJ2 = (R)1 / J2;
+        const R a = h->arm;
+        const R tm = (f[0] + f[1] + f[2] + f[3]) * inv_m;
         const R tbx = a * (f[0] + f[1] - f[2] - f[3]);
         const R tby = a * (-f[0] + f[1] + f[2] - f[3]);
-        const R tbz = (R)(c->km / c->kf) * (-f[0] + f[1] - f[2] + f[3]); // base_aviary.py:371-372: rpm^2*KM = f*KM/KF
+        const R tbz = h->km_over_kf * (-f[0] + f[1] - f[2] + f[3]);   // base_aviary.py:371-372: rpm^2*KM = f*KM/KF
         R px = e.ps[0], py = e.ps[1], pz = e.ps[2];
         R q[4] = {e.ps[3], e.ps[4], e.ps[5], e.ps[6]};
         R vx = e.ps[7], vy = e.ps[8], vz = e.ps[9];
         R wx = e.ps[10], wy = e.ps[11], wz = e.ps[12];
-        const R gz = -m * (R)c->gravity;
-        for (int s = 0; s < steps; ++s) {
-            R M[9]; rot_from_quat<R>(q, M);
-            R Fx = M[2] * thrust, Fy = M[5] * thrust, Fz = M[8] * thrust + gz;
-            if (has_dist) { Fx += fd[0]; Fy += fd[1]; Fz += fd[2]; }
+        R ax0 = (R)0, ay0 = (R)0, az0 = -h->gravity;
+        if (has_dist) { ax0 += fd[0] * inv_m; ay0 += fd[1] * inv_m; az0 += fd[2] * inv_m; }
+        const R half_dt = (R)0.5 * dt;
+        for (int s = 0; s < h->steps; ++s) {
+            R M[9]; rot_from_unit_quat<R>(q, M);
             // body rates, Euler's equation with the gyroscopic term (btMultiBody m_useGyroTerm)
-            R bx = M[0] * wx + M[3] * wy + M[6] * wz;
-            R by = M[1] * wx + M[4] * wy + M[7] * wz;
-            R bz = M[2] * wx + M[5] * wy + M[8] * wz;
-            R jx = J0 * bx, jy = J1 * by, jz = J2 * bz;
-            R dbx = (tbx - (by * jz - bz * jy)) / J0;
-            R dby = (tby - (bz * jx - bx * jz)) / J1;
-            R dbz = (tbz - (bx * jy - by * jx)) / J2;
-            R dwx = M[0] * dbx + M[1] * dby + M[2] * dbz;
-            R dwy = M[3] * dbx + M[4] * dby + M[5] * dbz;
-            R dwz = M[6] * dbx + M[7] * dby + M[8] * dbz;
-            vx += Fx / m * dt; vy += Fy / m * dt; vz += Fz / m * dt;
-            wx += dwx * dt; wy += dwy * dt; wz += dwz * dt;
+            const R bx = M[0] * wx + M[3] * wy + M[6] * wz;
+            const R by = M[1] * wx + M[4] * wy + M[7] * wz;
+            const R bz = M[2] * wx + M[5] * wy + M[8] * wz;
+            const R jx = J0 * bx, jy = J1 * by, jz = J2 * bz;
+            const R dbx = (tbx - (by * jz - bz * jy)) * iJ0;
+            const R dby = (tby - (bz * jx - bx * jz)) * iJ1;
+            const R dbz = (tbz - (bx * jy - by * jx)) * iJ2;
+            vx += (M[2] * tm + ax0) * dt; vy += (M[5] * tm + ay0) * dt; vz += (M[8] * tm + az0) * dt;
+            wx += (M[0] * dbx + M[1] * dby + M[2] * dbz) * dt;
+            wy += (M[3] * dbx + M[4] * dby + M[5] * dbz) * dt;
+            wz += (M[6] * dbx + M[7] * dby + M[8] * dbz) * dt;
             px += vx * dt; py += vy * dt; pz += vz * dt;
             // exponential-map orientation update with the NEW world angular velocity (btMultiBody::stepPositionsMultiDof)
-            R ang = Mth<R>::sqrt_(wx * wx + wy * wy + wz * wz);
-            if (ang * dt > (R)(0.25 * SCG_PI)) ang = (R)(0.25 * SCG_PI) / dt;
-            R k;
-            if (ang < (R)0.001) k = (R)0.5 * dt - dt * dt * dt * (R)0.020833333333 * ang * ang;
-            else k = Mth<R>::sin_((R)0.5 * ang * dt) / ang;
-            R ax = wx * k, ay = wy * k, az = wz * k, cw = Mth<R>::cos_(ang * dt * (R)0.5);
-            R n0 = cw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
-            R n1 = cw * q[1] + ay * q[3] + az * q[0] - ax * q[2];
-            R n2 = cw * q[2] + az * q[3] + ax * q[1] - ay * q[0];
-            R n3 = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
-            R nn = Mth<R>::sqrt_(n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3);
-            q[0] = n0 / nn; q[1] = n1 / nn; q[2] = n2 / nn; q[3] = n3 / nn;
+            const R w2 = wx * wx + wy * wy + wz * wz;
+            R k, cw;
+            if (w2 * half_dt * half_dt <= (R)(SCG_SMALL_ANGLE * SCG_SMALL_ANGLE)) {
+                // sin(|w| dt/2)/|w| and cos(|w| dt/2) as even power series in |w| dt/2: no square root, no trig
+                // (Bullet's own branch below 1e-3 rad/s, btTransformUtil, is this series truncated; the difference is < 1e-17)
+                const R y2 = w2 * half_dt * half_dt;
+                R ps, pc;
+                if (sizeof(R) == 8) {
+                    ps = (R)(-1.0 / 5040.0) + y2 * (R)(1.0 / 362880.0); ps = (R)(1.0 / 120.0) + y2 * ps; ps = (R)(-1.0 / 6.0) + y2 * ps;
+                    pc = (R)(-1.0 / 720.0) + y2 * ((R)(1.0 / 40320.0) - y2 * (R)(1.0 / 3628800.0)); pc = (R)(1.0 / 24.0) + y2 * pc; pc = (R)(-0.5) + y2 * pc;
+                } else {
+                    ps = (R)(-1.0 / 6.0) + y2 * (R)(1.0 / 120.0);
+                    pc = (R)(-0.5) + y2 * ((R)(1.0 / 24.0) - y2 * (R)(1.0 / 720.0));
+                }
+                k = half_dt * ((R)1 + y2 * ps); cw = (R)1 + y2 * pc;
+            } else {
+                R ang = Mth<R>::sqrt_(w2);
+                if (ang * dt > (R)(0.25 * SCG_PI)) ang = (R)(0.25 * SCG_PI) / dt;   // ANGULAR_MOTION_THRESHOLD
+                k = Mth<R>::sin_(half_dt * ang) / ang; cw = Mth<R>::cos_(half_dt * ang);
+            }
+            const R ax = wx * k, ay = wy * k, az = wz * k;
+            const R n0 = cw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
+            const R n1 = cw * q[1] + ay * q[3] + az * q[0] - ax * q[2];
+            const R n2 = cw * q[2] + az * q[3] + ax * q[1] - ay * q[0];
+            const R n3 = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
+            const R inn = (R)1 / Mth<R>::sqrt_(n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3);
+            q[0] = n0 * inn; q[1] = n1 * inn; q[2] = n2 * inn; q[3] = n3 * inn;
         }
         e.ps[0] = px; e.ps[1] = py; e.ps[2] = pz; e.ps[3] = q[0]; e.ps[4] = q[1]; e.ps[5] = q[2]; e.ps[6] = q[3];
         e.ps[7] = vx; e.ps[8] = vy; e.ps[9] = vz; e.ps[10] = wx; e.ps[11] = wy; e.ps[12] = wz;
@@ -422,7 +526,7 @@ template <typename R> struct Physics<SCG_SYS_QUAD3D, R> {
     static __device__ void state(const EnvRegs<SCG_SYS_QUAD3D, R>& e, R* s) {
         R q[4] = {e.ps[3], e.ps[4], e.ps[5], e.ps[6]};
         R rpy[3]; rpy_from_quat<R>(q, rpy);
-        R M[9]; rot_from_quat<R>(q, M);
+        R M[9]; rot_from_unit_quat<R>(q, M);
         s[0] = e.ps[0]; s[1] = e.ps[7]; s[2] = e.ps[1]; s[3] = e.ps[8]; s[4] = e.ps[2]; s[5] = e.ps[9];
         s[6] = rpy[0]; s[7] = rpy[1]; s[8] = rpy[2];
         const R wx = e.ps[10], wy = e.ps[11], wz = e.ps[12];
@@ -443,46 +547,58 @@ template <typename R> struct Physics<SCG_SYS_QUAD3D, R> {
         e.ps[10] = init[9]; e.ps[11] = init[10]; e.ps[12] = init[11];  // quadrotor.py:379: p,q,r passed as WORLD angular velocity
     }
 };
-// theta enters the 2D plane as the half-angle quaternion (0, sin(th/2), 0, cos(th/2)); nothing to convert.
 
 // ---------------------------------------------------------------------------------------------
 // observation / reset / step
 // ---------------------------------------------------------------------------------------------
-template <typename R> __device__ __forceinline__ const double* goal_row(const DevTables& T, const scg_config* c, int nx, int idx) {
-    if (c->task == SCG_TASK_STABILIZATION) return T.x_goal;
+__device__ __forceinline__ const double* goal_row(const DevTables& T, int task, int nx, int idx) {
+    if (task == SCG_TASK_STABILIZATION) return T.x_goal;
     idx = idx > T.L - 1 ? T.L - 1 : idx;
     return T.x_goal + (size_t)idx * nx;
 }
 
-// _get_observation + extend_obs (quadrotor.py:777-817, cartpole.py:585-609, benchmark_env.py:422-445)
-template <int SYS, typename R>
-__device__ __forceinline__ void make_obs(const DevTables& T, const scg_config* c, const R* state, int n, int ctrl_step, int pyb_step, bool at_reset,
-                                         NoiseSrc<R>& ns, R* obs) {
+// _get_observation + extend_obs (quadrotor.py:777-817, cartpole.py:585-609, benchmark_env.py:422-445).
+// The observation is handed element by element to `sink(k, value)` (global buffers or the CTA's shared tile).
+template <int SYS, typename R, typename Sink>
+__device__ __forceinline__ void make_obs(const DevTables& T, const HotCfg<R>* h, const R* state, int n, int ctrl_step, bool at_reset,
+                                         NoiseSrc<R>& ns, Sink sink) {
     constexpr int NX = SysDims<SYS>::NX;
+    if (h->has_dist[SCG_MODE_OBSERVATION]) {
+        R o[NX];
 #pragma unroll
-    for (int k = 0; k < NX; ++k) obs[k] = state[k];
-    if (c->n_dist[SCG_MODE_OBSERVATION] > 0)
-        apply_disturbances<R>(c, T.st.dist_off, T.N, n, SCG_MODE_OBSERVATION, ctrl_step, pyb_step, obs, NX, ns);
-    if (SYS == SCG_SYS_CARTPOLE && c->obs_wrap_angle) obs[2] = normalize_angle<R>(obs[2]);
-    if (c->cost == SCG_COST_RL_REWARD && c->obs_goal_horizon > 0) {
-        if (c->task == SCG_TASK_TRAJ_TRACKING) {
+        for (int k = 0; k < NX; ++k) o[k] = state[k];
+        apply_disturbances<R>(T.cfg, T.st.dist_off, T.N, n, SCG_MODE_OBSERVATION, ctrl_step, ctrl_step * h->steps, o, NX, ns);
+        if (SYS == SCG_SYS_CARTPOLE && h->obs_wrap) o[2] = normalize_angle<R>(o[2]);
+#pragma unroll
+        for (int k = 0; k < NX; ++k) sink(k, o[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < NX; ++k) {
+            R v = state[k];
+            if (SYS == SCG_SYS_CARTPOLE && k == 2 && h->obs_wrap) v = normalize_angle<R>(v);
+            sink(k, v);
+        }
+    }
+    if (h->obs_goal_horizon > 0) {
+        if (h->task == SCG_TASK_TRAJ_TRACKING) {
             const int next_step = at_reset ? 1 : ctrl_step + 2;
-            for (int h = 0; h < c->obs_goal_horizon; ++h) {
-                const double* g = goal_row<R>(T, c, NX, next_step + h);
+            for (int hh = 0; hh < h->obs_goal_horizon; ++hh) {
+                const double* g = goal_row(T, h->task, NX, next_step + hh);
 #pragma unroll
-                for (int k = 0; k < NX; ++k) obs[NX * (1 + h) + k] = (R)g[k];
+                for (int k = 0; k < NX; ++k) sink(NX * (1 + hh) + k, (R)g[k]);
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < NX; ++k) obs[NX + k] = (R)T.x_goal[k];
+            for (int k = 0; k < NX; ++k) sink(NX + k, (R)T.x_goal[k]);
         }
     }
 }
 
-// reset() of one env; leaves the new observation in obs[0..obs_dim)
+// reset() of one env (quadrotor.py:328-392, cartpole.py:266-352); the caller builds the observation with make_obs(at_reset)
 template <int SYS, typename R>
-__device__ __noinline__ void env_reset(const DevTables& T, const scg_config* c, int n, EnvRegs<SYS, R>& e, R* state, R* obs) {
+__device__ __noinline__ void env_reset(const DevTables& T, int n, EnvRegs<SYS, R>& e, R* state) {
     constexpr int NX = SysDims<SYS>::NX;
+    const scg_config* c = T.cfg;
     const int k = e.episode;
     const bool philox = c->rng_mode == SCG_RNG_PHILOX;
     RngKey key; key.k0 = (uint32_t)c->seed; key.k1 = (uint32_t)(c->seed >> 32); key.genv = (uint32_t)(c->env_index_offset + n);
@@ -533,155 +649,168 @@ __device__ __noinline__ void env_reset(const DevTables& T, const scg_config* c, 
     e.episode = k + 1;
     Physics<SYS, R>::set_init(e, init);
     Physics<SYS, R>::state(e, state);
-    NoiseSrc<R> ns; ns.row = nullptr; ns.philox = philox; ns.key = key; ns.stream = SCG_STREAM_RESET; ns.idx = (uint32_t)k; ns.slot = 0;
-    make_obs<SYS, R>(T, c, state, n, 0, 0, true, ns, obs);
+}
+
+// noise source of the reset-time observation (Philox stream RESET keyed by the episode; zero in table mode)
+template <typename R> __device__ __forceinline__ NoiseSrc<R> reset_noise(const DevTables& T, const HotCfg<R>* h, int n, int episode_done) {
+    NoiseSrc<R> ns; ns.row = nullptr; ns.philox = h->philox != 0;
+    ns.key.k0 = (uint32_t)T.cfg->seed; ns.key.k1 = (uint32_t)(T.cfg->seed >> 32); ns.key.genv = (uint32_t)(T.cfg->env_index_offset + n);
+    ns.stream = SCG_STREAM_RESET; ns.idx = (uint32_t)(episode_done - 1); ns.slot = 0;
+    return ns;
 }
 
 struct StepInfo {
     int done, truncated, cviol, out_of_bounds, goal_reached, current_step;
 };
 
-// np.round(x, 8) (constraints.py:109): rint(x*1e8)/1e8, always evaluated in double like the reference
-__device__ __forceinline__ double round8(double x) { return rint(x * 1e8) / 1e8; }
-
-// One control step WITHOUT auto-reset.  action[NU] is the raw controller action.  On return `state` holds env.state,
-// obs the new observation, rew/mse the reward and info['mse'], cvals / cvals_f32 (nullable, global memory) the constraint values.
+// One control step WITHOUT auto-reset and WITHOUT building the observation.  action[NU] is the raw controller action.
+// `zbuf` is this lane's column of a shared scratch [NX+NU][zstride] (doubles) used to index z = [state; input] by constraint column.
+// On return `state` holds env.state; `ns` is positioned for the observation noise (call make_obs next).
 template <int SYS, typename R>
-__device__ __forceinline__ void env_step(const DevTables& T, const scg_config* c, int n, EnvRegs<SYS, R>& e, const R* action, const double* noise_row,
-                                         R* state, R* obs, R& rew_out, R& mse_out, StepInfo& info, double* cvals, float* cvals_f32) {
+__device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h, int n, EnvRegs<SYS, R>& e, const R* action, const double* noise_row,
+                                         double* zbuf, int zstride, R* state, R& rew_out, R& mse_out, StepInfo& info,
+                                         double* cvals, float* cvals_f32, NoiseSrc<R>& ns) {
     constexpr int NX = SysDims<SYS>::NX, NU = SysDims<SYS>::NU;
-    const int steps = c->pyb_freq / c->ctrl_freq;
-    const R dt = (R)(1.0 / (double)c->pyb_freq);
-    const int pyb_step = e.ctrl_step * steps;
-    NoiseSrc<R> ns; ns.row = noise_row; ns.philox = c->rng_mode == SCG_RNG_PHILOX;
-    ns.key.k0 = (uint32_t)c->seed; ns.key.k1 = (uint32_t)(c->seed >> 32); ns.key.genv = (uint32_t)(c->env_index_offset + n);
+    const int pyb_step = e.ctrl_step * h->steps;
+    ns.row = noise_row; ns.philox = h->philox != 0;
+    ns.key.k0 = (uint32_t)T.cfg->seed; ns.key.k1 = (uint32_t)(T.cfg->seed >> 32); ns.key.genv = (uint32_t)(T.cfg->env_index_offset + n);
     ns.stream = SCG_STREAM_STEP; ns.idx = e.total_steps; ns.slot = 0;
 
     R noisy[NU], clipped[NU];
 #pragma unroll
     for (int k = 0; k < NU; ++k) {
-        if (SYS == SCG_SYS_CARTPOLE) noisy[k] = c->normalized_action ? (R)c->hover_thrust * action[k] : action[k];              // cartpole.py:527-528
-        else noisy[k] = c->normalized_action ? ((R)1 + (R)c->norm_act_scale * action[k]) * (R)c->hover_thrust : action[k];     // quadrotor.py:772-773
+        if (SYS == SCG_SYS_CARTPOLE) noisy[k] = h->normalized_action ? h->hover * action[k] : action[k];                      // cartpole.py:527-528
+        else noisy[k] = h->normalized_action ? ((R)1 + h->act_scale * action[k]) * h->hover : action[k];                       // quadrotor.py:772-773
     }
-    if (c->n_dist[SCG_MODE_ACTION] > 0)
-        apply_disturbances<R>(c, T.st.dist_off, T.N, n, SCG_MODE_ACTION, e.ctrl_step, pyb_step, noisy, NU, ns);
+    if (h->has_dist[SCG_MODE_ACTION])
+        apply_disturbances<R>(T.cfg, T.st.dist_off, T.N, n, SCG_MODE_ACTION, e.ctrl_step, pyb_step, noisy, NU, ns);
 #pragma unroll
     for (int k = 0; k < NU; ++k) {
         R t = noisy[k];
-        t = t < (R)c->act_low[k] ? (R)c->act_low[k] : t;
-        t = t > (R)c->act_high[k] ? (R)c->act_high[k] : t;
+        t = t < h->act_low[k] ? h->act_low[k] : t;
+        t = t > h->act_high[k] ? h->act_high[k] : t;
         clipped[k] = t;
     }
-    const bool has_dyn = c->n_dist[SCG_MODE_DYNAMICS] > 0;
+    const bool has_dyn = h->has_dist[SCG_MODE_DYNAMICS] != 0;
     R fd[3] = {(R)0, (R)0, (R)0};
     if (has_dyn) {
         const int ddim = (SYS == SCG_SYS_CARTPOLE) ? 2 : (SYS == SCG_SYS_QUAD1D) ? 1 : (SYS == SCG_SYS_QUAD2D) ? 2 : 3;
-        apply_disturbances<R>(c, T.st.dist_off, T.N, n, SCG_MODE_DYNAMICS, e.ctrl_step, pyb_step, fd, ddim, ns);
+        apply_disturbances<R>(T.cfg, T.st.dist_off, T.N, n, SCG_MODE_DYNAMICS, e.ctrl_step, pyb_step, fd, ddim, ns);
     }
     if (SYS == SCG_SYS_CARTPOLE) {
-        Physics<SYS, R>::advance(c, e, clipped, fd, has_dyn, steps, dt);
+        Physics<SYS, R>::advance(h, e, clipped, fd, has_dyn);
     } else {
-        R f[4]; quad_motor_forces<SYS, R>(c, clipped, f);
-        Physics<SYS, R>::advance(c, e, f, fd, has_dyn, steps, dt);
+        R f[4]; quad_motor_forces<SYS, R>(h, clipped, f);
+        Physics<SYS, R>::advance(h, e, f, fd, has_dyn);
     }
     Physics<SYS, R>::state(e, state);
-    make_obs<SYS, R>(T, c, state, n, e.ctrl_step, pyb_step, false, ns, obs);
 
-    // ---- reward (quadrotor.py:819-862, cartpole.py:611-652)
-    R rew;
-    if (c->cost == SCG_COST_RL_REWARD) {
-        const double* g = goal_row<R>(T, c, NX, e.ctrl_step + 1);
-        R dist = (R)0;
+    // ---- reward (quadrotor.py:819-862, cartpole.py:611-652) and info['mse'] (quadrotor.py:907-922, cartpole.py:685-695)
+    R rew, mse = (R)0;
+    {
+        const double* g = goal_row(T, h->task, NX, e.ctrl_step + 1);
+        R gk[NX];
+#pragma unroll
+        for (int k = 0; k < NX; ++k) gk[k] = (R)g[k];
+        if (h->cost == SCG_COST_RL_REWARD) {
+            R dist = (R)0;
+#pragma unroll
+            for (int k = 0; k < NX; ++k) {
+                R sk = state[k];
+                if (SYS == SCG_SYS_CARTPOLE && k == 2) sk = normalize_angle<R>(sk);                                  // cartpole.py:620
+                const R er = sk - gk[k];
+                dist += h->rew_state_w[k] * er * er;
+            }
+#pragma unroll
+            for (int k = 0; k < NU; ++k) {
+                const R ae = (SYS == SCG_SYS_CARTPOLE) ? noisy[k] : noisy[k] - h->u_goal[k];                          // cartpole.py:625 / quadrotor.py:829
+                dist += h->rew_act_w[k] * ae * ae;
+            }
+            rew = -dist;
+            if (h->rew_exponential) rew = Mth<R>::exp_(rew);
+        } else {
+            const int idx = (SYS == SCG_SYS_CARTPOLE) ? e.ctrl_step : e.ctrl_step + 1;                                // cartpole.py:648 / quadrotor.py:858
+            const double* gq = goal_row(T, h->task, NX, idx);
+            R l = (R)0;
+#pragma unroll
+            for (int k = 0; k < NX; ++k) { const R er = state[k] - (R)gq[k]; l += (R)0.5 * h->Qw[k] * er * er; }
+#pragma unroll
+            for (int k = 0; k < NU; ++k) { const R ae = clipped[k] - h->u_goal[k]; l += (R)0.5 * h->Rw[k] * ae * ae; }
+            rew = -l;
+        }
 #pragma unroll
         for (int k = 0; k < NX; ++k) {
             R sk = state[k];
-            if (SYS == SCG_SYS_CARTPOLE && k == 2) sk = normalize_angle<R>(sk);                                  // cartpole.py:620
-            R er = sk - (R)g[k];
-            dist += (R)c->rew_state_weight[k] * er * er;
+            if (h->task == SCG_TASK_TRAJ_TRACKING) {
+                const bool is_angle = (SYS == SCG_SYS_CARTPOLE && k == 2) || (SYS == SCG_SYS_QUAD2D && k == 4) || (SYS == SCG_SYS_QUAD3D && k >= 6 && k < 9);
+                if (is_angle) sk = normalize_angle<R>(sk);
+            }
+            const R er = (sk - gk[k]) * h->mse_w[k];
+            mse += er * er;
         }
-#pragma unroll
-        for (int k = 0; k < NU; ++k) {
-            R ae = (SYS == SCG_SYS_CARTPOLE) ? noisy[k] : noisy[k] - (R)c->u_goal[k];                             // cartpole.py:625 / quadrotor.py:829
-            dist += (R)c->rew_act_weight[k] * ae * ae;
-        }
-        rew = -dist;
-        if (c->rew_exponential) rew = Mth<R>::exp_(rew);
-    } else {
-        int idx = (SYS == SCG_SYS_CARTPOLE) ? e.ctrl_step : e.ctrl_step + 1;                                      // cartpole.py:648 / quadrotor.py:858
-        const double* g = goal_row<R>(T, c, NX, idx);
-        R l = (R)0;
-#pragma unroll
-        for (int k = 0; k < NX; ++k) { R er = state[k] - (R)g[k]; l += (R)0.5 * (R)c->Q[k] * er * er; }
-#pragma unroll
-        for (int k = 0; k < NU; ++k) { R ae = clipped[k] - (R)c->u_goal[k]; l += (R)0.5 * (R)c->R[k] * ae * ae; }
-        rew = -l;
     }
     // ---- done (quadrotor.py:864-894, cartpole.py:654-672)
     int done = 0, goal_reached = 0, oob = 0;
-    if (c->task == SCG_TASK_STABILIZATION) {
+    if (h->task == SCG_TASK_STABILIZATION) {
         R n2 = (R)0;
 #pragma unroll
-        for (int k = 0; k < NX; ++k) { R er = state[k] - (R)T.x_goal[k]; n2 += er * er; }
-        goal_reached = Mth<R>::sqrt_(n2) < (R)c->goal_tolerance;
+        for (int k = 0; k < NX; ++k) { const R er = state[k] - (R)T.x_goal[k]; n2 += er * er; }
+        goal_reached = Mth<R>::sqrt_(n2) < h->goal_tol;
         done = goal_reached;
     }
-    if (!done && c->done_on_out_of_bound) {
+    if (!done && h->done_on_oob) {
         if (SYS == SCG_SYS_CARTPOLE) {
-            R x = state[0], th = state[2];
-            oob = (x < -(R)c->x_threshold) || (x > (R)c->x_threshold) || (th < -(R)c->theta_threshold) || (th > (R)c->theta_threshold);
+            const R x = state[0], th = state[2];
+            oob = (x < -h->x_thr) || (x > h->x_thr) || (th < -h->th_thr) || (th > h->th_thr);
         } else {
 #pragma unroll
             for (int k = 0; k < NX; ++k) {
                 const bool masked = (SYS == SCG_SYS_QUAD3D) ? ((k % 2 == 0 && k < 6) || (k >= 6 && k < 9)) : (k % 2 == 0);  // quadrotor.py:878-883
-                if (masked) oob |= ((double)state[k] < c->state_low[k]) || ((double)state[k] > c->state_high[k]);
+                if (masked) oob |= ((double)state[k] < h->state_low[k]) || ((double)state[k] > h->state_high[k]);
             }
         }
         done = oob;
     }
-    // ---- info['mse'] (quadrotor.py:907-922, cartpole.py:685-695)
-    R mse = (R)0;
-    {
-        const double* g = goal_row<R>(T, c, NX, e.ctrl_step + 1);
-#pragma unroll
-        for (int k = 0; k < NX; ++k) {
-            R sk = state[k];
-            if (c->task == SCG_TASK_TRAJ_TRACKING) {
-                const bool is_angle = (SYS == SCG_SYS_CARTPOLE && k == 2) || (SYS == SCG_SYS_QUAD2D && k == 4) || (SYS == SCG_SYS_QUAD3D && k >= 6 && k < 9);
-                if (is_angle) sk = normalize_angle<R>(sk);
-            }
-            R er = (sk - (R)g[k]) * (R)c->mse_weight[k];
-            mse += er * er;
-        }
-    }
     // ---- after_step (benchmark_env.py:447-502)
     e.ctrl_step += 1; e.total_steps += 1;
     int cviol = 0;
-    if (T.n_con > 0) {
-        for (int r = 0; r < T.n_con; ++r) {
-            double acc = 0;
-            for (int p = T.con_ptr[r]; p < T.con_ptr[r + 1]; ++p) {
-                const int ci = T.con_col[p];
-                double z = 0;
+    const int n_con = h->n_con;
+    if (n_con > 0) {
+        // z = [state ; current_noisy_physical_action] (constraints.py:166-171), indexed by column through the shared scratch
 #pragma unroll
-                for (int k = 0; k < NX; ++k) if (ci == k) z = (double)state[k];
+        for (int k = 0; k < NX; ++k) zbuf[k * zstride] = (double)state[k];
 #pragma unroll
-                for (int k = 0; k < NU; ++k) if (ci == NX + k) z = (double)noisy[k];                              // constraints.py:168-169
-                acc += T.con_val[p] * z;
+        for (int k = 0; k < NU; ++k) zbuf[(NX + k) * zstride] = (double)noisy[k];
+        if (h->con_fast) {
+#pragma unroll 4
+            for (int r = 0; r < n_con; ++r) {
+                const ConRow row = h->rows[r];
+                double acc = __dmul_rn(row.val, zbuf[row.col * zstride]);
+                if (row.flags & 2) acc = fabs(acc);
+                const double gi = rint(__dsub_rn(acc, row.b) * 1e8);   // np.round(g, 8) = rint(g*1e8)/1e8 (constraints.py:109)
+                cviol |= (row.flags & 1) ? (gi >= 0.0) : (gi > 0.0);   // constraints.py:126-129
+                if (cvals) cvals[r] = gi / 1e8;
+                if (cvals_f32) cvals_f32[r] = (float)(gi / 1e8);
             }
-            if (T.con_kind[r] == SCG_CON_ABS) acc = fabs(acc);
-            const double g = round8(acc - T.con_b[r]);
-            if (cvals) cvals[r] = g;
-            if (cvals_f32) cvals_f32[r] = (float)g;
-            cviol |= T.con_strict[r] ? (g >= 0.0) : (g > 0.0);                                                    // constraints.py:126-129
+        } else {
+            for (int r = 0; r < n_con; ++r) {
+                double acc = 0;
+                for (int p = T.con_ptr[r]; p < T.con_ptr[r + 1]; ++p) acc += T.con_val[p] * zbuf[T.con_col[p] * zstride];
+                if (T.con_kind[r] == SCG_CON_ABS) acc = fabs(acc);
+                const double gi = rint((acc - T.con_b[r]) * 1e8);
+                cviol |= T.con_strict[r] ? (gi >= 0.0) : (gi > 0.0);
+                if (cvals) cvals[r] = gi / 1e8;
+                if (cvals_f32) cvals_f32[r] = (float)(gi / 1e8);
+            }
         }
-        if (cviol && c->done_on_violation) { done = 1; if (c->cost == SCG_COST_RL_REWARD && c->use_constraint_penalty) rew = (R)0; }
-        if (c->cost == SCG_COST_RL_REWARD && c->use_constraint_penalty && cviol) {
-            if (c->rew_exponential) rew = Mth<R>::exp_(Mth<R>::log_(rew) - (R)c->constraint_penalty);
-            else rew -= (R)c->constraint_penalty;
+        if (cviol && h->done_on_violation) { done = 1; if (h->cost == SCG_COST_RL_REWARD && h->use_penalty) rew = (R)0; }
+        if (h->cost == SCG_COST_RL_REWARD && h->use_penalty && cviol) {
+            if (h->rew_exponential) rew = Mth<R>::exp_(Mth<R>::log_(rew) - h->penalty);
+            else rew -= h->penalty;
         }
     }
     int truncated = 0;
-    if (e.ctrl_step >= c->ctrl_steps) { truncated = !done; done = 1; }
+    if (e.ctrl_step >= h->ctrl_steps) { truncated = !done; done = 1; }
     rew_out = rew; mse_out = mse;
     info.done = done; info.truncated = truncated; info.cviol = cviol; info.out_of_bounds = oob; info.goal_reached = goal_reached; info.current_step = e.ctrl_step;
 }

@@ -96,36 +96,55 @@ __device__ __forceinline__ float hidden_act_rt(float x, int act) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// observation sinks
+// ---------------------------------------------------------------------------------------------
+struct GlobalObsSink {      // row `n` of up to three [N][obs_dim] global buffers
+    float* a; float* b; double* c; size_t base;
+    template <typename R> __device__ __forceinline__ void operator()(int k, R v) const {
+        if (a) a[base + k] = (float)v;
+        if (b) b[base + k] = (float)v;
+        if (c) c[base + k] = (double)v;
+    }
+};
+struct SmemObsSink {        // column of the CTA's [obs_dim][EP] float tile
+    float* col; int stride;
+    template <typename R> __device__ __forceinline__ void operator()(int k, R v) const { col[k * stride] = (float)v; }
+};
+
+// ---------------------------------------------------------------------------------------------
 // lane-per-env kernels (gym-style API)
 // ---------------------------------------------------------------------------------------------
+#define SCG_LANE_BLOCK 128
+
 struct ResetArgs {
     const uint8_t* mask; float* obs; double* obs_f64; double* state_f64;
 };
 
 template <int SYS, typename R>
-__global__ void __launch_bounds__(128) reset_kernel(DevTables T, ResetArgs A) {
+__global__ void __launch_bounds__(SCG_LANE_BLOCK) reset_kernel(DevTables T, ResetArgs A) {
     constexpr int NX = SysDims<SYS>::NX;
+    __shared__ HotCfg<R> s_hot;
+    if (threadIdx.x == 0) hot_load<SYS, R>(T, &s_hot);
+    __syncthreads();
+    const HotCfg<R>* h = &s_hot;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= T.N) return;
-    const scg_config* c = T.cfg;
     const int od = T.obs_dim;
     if (A.mask && !A.mask[n]) {
-        // untouched env: still report its current observation / state
+        // untouched env: still report its current observation
         if (A.obs) for (int k = 0; k < od; ++k) A.obs[(size_t)n * od + k] = T.st.cur_obs[(size_t)n * od + k];
         return;
     }
     EnvRegs<SYS, R> e;
     env_load<SYS, R>(T, n, e);
-    R state[NX], obs[SCG_MAX_OBS];
-    env_reset<SYS, R>(T, c, n, e, state, obs);
+    R state[NX];
+    env_reset<SYS, R>(T, n, e, state);
     e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
     T.st.initial_reset[n] = 1;
     env_store<SYS, R>(T, n, e);
-    for (int k = 0; k < od; ++k) {
-        T.st.cur_obs[(size_t)n * od + k] = (float)obs[k];
-        if (A.obs) A.obs[(size_t)n * od + k] = (float)obs[k];
-        if (A.obs_f64) A.obs_f64[(size_t)n * od + k] = (double)obs[k];
-    }
+    NoiseSrc<R> ns = reset_noise<R>(T, h, n, e.episode);
+    GlobalObsSink sink{T.st.cur_obs, A.obs, A.obs_f64, (size_t)n * od};
+    make_obs<SYS, R>(T, h, state, n, 0, true, ns, sink);
     if (A.state_f64) for (int k = 0; k < NX; ++k) A.state_f64[(size_t)n * NX + k] = (double)state[k];
 }
 
@@ -134,8 +153,13 @@ struct StepArgs {
 };
 
 template <int SYS, typename R>
-__global__ void __launch_bounds__(128) step_kernel(DevTables T, StepArgs A) {
+__global__ void __launch_bounds__(SCG_LANE_BLOCK) step_kernel(DevTables T, StepArgs A) {
     constexpr int NX = SysDims<SYS>::NX, NU = SysDims<SYS>::NU;
+    __shared__ HotCfg<R> s_hot;
+    __shared__ double s_z[(NX + NU) * SCG_LANE_BLOCK];
+    if (threadIdx.x == 0) hot_load<SYS, R>(T, &s_hot);
+    __syncthreads();
+    const HotCfg<R>* h = &s_hot;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= T.N) return;
     const scg_config* c = T.cfg;
@@ -145,25 +169,28 @@ __global__ void __launch_bounds__(128) step_kernel(DevTables T, StepArgs A) {
     R action[NU];
 #pragma unroll
     for (int k = 0; k < NU; ++k) action[k] = A.act_f64 ? (R)A.act_f64[(size_t)n * NU + k] : (R)A.act[(size_t)n * NU + k];
-    const double* nrow = (c->rng_mode == SCG_RNG_TABLE && T.noise_table && T.D > 0) ? T.noise_table + ((size_t)(A.noise_cursor % T.Tn) * T.N + n) * T.D : nullptr;
-    R state[NX], obs[SCG_MAX_OBS], rew, mse; StepInfo info;
-    double* cv = A.out.d_cvals ? A.out.d_cvals + (size_t)n * nc : nullptr;
-    env_step<SYS, R>(T, c, n, e, action, nrow, state, obs, rew, mse, info, cv, nullptr);
-    e.ep_ret += (float)rew; e.ep_len += 1.f; e.ep_cv += (float)info.cviol;
+    const double* nrow = (!h->philox && T.noise_table && T.D > 0) ? T.noise_table + ((size_t)(A.noise_cursor % T.Tn) * T.N + n) * T.D : nullptr;
+    R state[NX], rew, mse; StepInfo info; NoiseSrc<R> ns;
     const scg_step_out& o = A.out;
-    if (o.d_terminal_obs) for (int k = 0; k < od; ++k) o.d_terminal_obs[(size_t)n * od + k] = (float)obs[k];
-    if (o.d_terminal_obs_f64) for (int k = 0; k < od; ++k) o.d_terminal_obs_f64[(size_t)n * od + k] = (double)obs[k];
+    double* cv = o.d_cvals ? o.d_cvals + (size_t)n * nc : nullptr;
+    env_step<SYS, R>(T, h, n, e, action, nrow, s_z + threadIdx.x, SCG_LANE_BLOCK, state, rew, mse, info, cv, nullptr, ns);
+    e.ep_ret += (float)rew; e.ep_len += 1.f; e.ep_cv += (float)info.cviol;
+    const bool reset_now = info.done && c->auto_reset;
+    {   // observation of the transition: the returned obs unless the env auto-resets, always the terminal obs
+        GlobalObsSink term{o.d_terminal_obs, nullptr, o.d_terminal_obs_f64, (size_t)n * od};
+        GlobalObsSink cur{reset_now ? nullptr : T.st.cur_obs, reset_now ? nullptr : o.d_obs, reset_now ? nullptr : o.d_obs_f64, (size_t)n * od};
+        auto both = [&](int k, R v) { term(k, v); cur(k, v); };
+        make_obs<SYS, R>(T, h, state, n, e.ctrl_step - 1, false, ns, both);
+    }
     if (o.d_terminal_state_f64) for (int k = 0; k < NX; ++k) o.d_terminal_state_f64[(size_t)n * NX + k] = (double)state[k];
-    if (info.done && c->auto_reset) {   // dummy_vec_env.py:33-38
-        env_reset<SYS, R>(T, c, n, e, state, obs);
+    if (reset_now) {   // dummy_vec_env.py:33-38
+        env_reset<SYS, R>(T, n, e, state);
         e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
+        NoiseSrc<R> rs = reset_noise<R>(T, h, n, e.episode);
+        GlobalObsSink sink{T.st.cur_obs, o.d_obs, o.d_obs_f64, (size_t)n * od};
+        make_obs<SYS, R>(T, h, state, n, 0, true, rs, sink);
     }
     env_store<SYS, R>(T, n, e);
-    for (int k = 0; k < od; ++k) {
-        T.st.cur_obs[(size_t)n * od + k] = (float)obs[k];
-        if (o.d_obs) o.d_obs[(size_t)n * od + k] = (float)obs[k];
-        if (o.d_obs_f64) o.d_obs_f64[(size_t)n * od + k] = (double)obs[k];
-    }
     if (o.d_state_f64) for (int k = 0; k < NX; ++k) o.d_state_f64[(size_t)n * NX + k] = (double)state[k];
     if (o.d_rew) o.d_rew[n] = (float)rew;
     if (o.d_rew_f64) o.d_rew_f64[n] = (double)rew;
@@ -314,6 +341,8 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
     static_assert(NT / E >= A + 1, "layer 3 needs A+1 lane groups");
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ HotCfg<R> s_hot;
+    __shared__ double s_z[(NX + A) * E];
 
     const scg_config* c = T.cfg;
     const int od = T.obs_dim, N = T.N, nc = T.n_con;
@@ -330,6 +359,8 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
 
     // ---- stage the packed policy into shared memory with one TMA bulk copy
     if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+    if (tid == 32) hot_load<SYS, R>(T, &s_hot);
+    const HotCfg<R>* h = &s_hot;
     __syncthreads();
     if (tid == 0) {
         const uint32_t bytes = (uint32_t)L.total * 4u;
@@ -395,22 +426,25 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
             R action[A];
 #pragma unroll
             for (int k = 0; k < A; ++k) action[k] = (R)act[k];
-            const double* nrow = (c->rng_mode == SCG_RNG_TABLE && T.noise_table && T.D > 0)
+            const double* nrow = (!h->philox && T.noise_table && T.D > 0)
                                      ? T.noise_table + ((size_t)((P.noise_cursor + t) % T.Tn) * N + n) * T.D : nullptr;
-            R state[NX], obs[SCG_MAX_OBS], rew, mse; StepInfo info;
+            R state[NX], rew, mse; StepInfo info; NoiseSrc<R> ns;
             float* cvp = P.out.d_cvals ? P.out.d_cvals + (tn0 + tid) * nc : nullptr;
-            env_step<SYS, R>(T, c, n, e, action, nrow, state, obs, rew, mse, info, nullptr, cvp);
+            env_step<SYS, R>(T, h, n, e, action, nrow, s_z + tid, E, state, rew, mse, info, nullptr, cvp, ns);
             e.ep_ret += (float)rew; e.ep_len += 1.f; e.ep_cv += (float)info.cviol;
             if (info.done) {
                 if (info.truncated) {                                  // ppo.py:274-283
                     trunc = 1;
-                    for (int k = 0; k < od; ++k) s_tobs[k * EP + tid] = (float)obs[k];
+                    make_obs<SYS, R>(T, h, state, n, e.ctrl_step - 1, false, ns, SmemObsSink{s_tobs + tid, EP});
                 }
                 ep_count += 1; ep_ret_sum += e.ep_ret; ep_len_sum += e.ep_len; ep_cv_sum += e.ep_cv;
                 e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
-                env_reset<SYS, R>(T, c, n, e, state, obs);             // dummy_vec_env.py:33-38
+                env_reset<SYS, R>(T, n, e, state);                     // dummy_vec_env.py:33-38
+                NoiseSrc<R> rs = reset_noise<R>(T, h, n, e.episode);
+                make_obs<SYS, R>(T, h, state, n, 0, true, rs, SmemObsSink{s_obs + tid, EP});
+            } else {
+                make_obs<SYS, R>(T, h, state, n, e.ctrl_step - 1, false, ns, SmemObsSink{s_obs + tid, EP});
             }
-            for (int k = 0; k < od; ++k) s_obs[k * EP + tid] = (float)obs[k];
             const size_t tn = tn0 + tid;
             if (A == 2) *reinterpret_cast<float2*>(P.out.d_act + tn * A) = make_float2(act[0], act[1 % A]);
             else if (A == 4) *reinterpret_cast<float4*>(P.out.d_act + tn * A) = make_float4(act[0], act[1 % A], act[2 % A], act[3 % A]);
