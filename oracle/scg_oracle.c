@@ -71,22 +71,25 @@ void scg_oracle_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, 
 #define STREAM_POLICY 3u
 #define STREAM_RESET 4u
 
-static void draw_block(uint64_t seed, uint32_t stream, uint32_t genv, uint32_t idx, uint32_t slot, uint32_t x[4]) {
-    uint32_t ctr[4] = {slot, idx, genv, stream};
+/* draw slot j of (stream, idx) = words 2(j&1), 2(j&1)+1 of Philox block j>>1: counter = (j>>1, idx, global env, stream) */
+static void draw_words(uint64_t seed, uint32_t stream, uint32_t genv, uint32_t idx, uint32_t slot, uint32_t* w0, uint32_t* w1) {
+    uint32_t ctr[4] = {slot >> 1, idx, genv, stream};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t x[4];
     philox4x32_10(ctr, key, x);
+    *w0 = (slot & 1u) ? x[2] : x[0]; *w1 = (slot & 1u) ? x[3] : x[1];
 }
 static double u01(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
 static double draw_uniform(uint64_t seed, uint32_t stream, uint32_t genv, uint32_t idx, uint32_t slot) {
-    uint32_t x[4]; draw_block(seed, stream, genv, idx, slot, x); return u01(x[0]);
+    uint32_t w0, w1; draw_words(seed, stream, genv, idx, slot, &w0, &w1); return u01(w0);
 }
 static double draw_normal(uint64_t seed, uint32_t stream, uint32_t genv, uint32_t idx, uint32_t slot) {
-    uint32_t x[4]; draw_block(seed, stream, genv, idx, slot, x);
-    return sqrt(-2.0 * log(u01(x[0]))) * cos(2.0 * PI_D * u01(x[1]));
+    uint32_t w0, w1; draw_words(seed, stream, genv, idx, slot, &w0, &w1);
+    return sqrt(-2.0 * log(u01(w0))) * cos(2.0 * PI_D * u01(w1));
 }
 static double draw_randint(uint64_t seed, uint32_t stream, uint32_t genv, uint32_t idx, uint32_t slot, uint32_t n) {
-    uint32_t x[4]; draw_block(seed, stream, genv, idx, slot, x);
-    return (double)(uint32_t)(((uint64_t)x[0] * (uint64_t)n) >> 32);
+    uint32_t w0, w1; draw_words(seed, stream, genv, idx, slot, &w0, &w1);
+    return (double)(uint32_t)(((uint64_t)w0 * (uint64_t)n) >> 32);
 }
 
 /* ------------------------------------------------------------------------------------------ */

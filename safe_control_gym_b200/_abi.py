@@ -121,7 +121,7 @@ _SYMBOLS = {
     'scg_philox_selftest': (C.c_int, [C.c_int32, _VP, _VP, _VP, C.c_int32]),
 }
 
-LIB_NAME = 'libscg_b200.so'
+LIB_NAME = os.environ.get('SCG_LIB_NAME', 'libscg_b200.so')   # SCG_LIB_NAME: developer builds (e.g. the -DSCG_PROF variant)
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 _lib = None

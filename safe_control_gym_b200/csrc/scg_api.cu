@@ -270,10 +270,12 @@ extern "C++" {
 template <int SYS, typename R, int HID, int E>
 static int launch_rollout(scg_env* e, const RolloutParams& P, cudaStream_t s) {
     constexpr int NT = 256;
-    const RolloutSmem<HID, E> S(e->obs_dim, e->nu);
+    const RolloutSmem<HID, E> S(e->obs_dim, e->nu, e->L * e->nx * (int)(sizeof(R) / 4));
     const size_t smem = (size_t)S.total_floats * sizeof(float);
     auto kern = rollout_kernel<SYS, R, HID, E, NT>;
     CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the kernel lives out of shared memory (weights, tiles, tables): ask for the largest carve-out so several CTAs fit per SM
+    CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     const int G = (e->cfg.num_envs + E - 1) / E;
     kern<<<G, NT, smem, s>>>(e->tab, P);
     CUDA_TRY(e, cudaGetLastError());
@@ -283,6 +285,10 @@ static int launch_rollout(scg_env* e, const RolloutParams& P, cudaStream_t s) {
 template <int SYS, typename R>
 static int dispatch_rollout(scg_env* e, const scg_rollout_args* a, const RolloutParams& P, cudaStream_t s) {
     const int E = a->envs_per_block;
+#ifdef SCG_PROF
+    if (a->hidden_dim == 64 && (E == 0 || E == 32)) return launch_rollout<SYS, R, 64, 32>(e, P, s);
+    return fail(e, SCG_EINVAL, "SCG_PROF build: only hidden 64 / E 32");
+#else
     switch (a->hidden_dim) {
         case 32:
             if (E == 0 || E == 32) return launch_rollout<SYS, R, 32, 32>(e, P, s);
@@ -297,6 +303,7 @@ static int dispatch_rollout(scg_env* e, const scg_rollout_args* a, const Rollout
         default: return fail(e, SCG_EINVAL, "scg_rollout: hidden_dim must be 32, 64 or 128");
     }
     return fail(e, SCG_EINVAL, "scg_rollout: unsupported envs_per_block for this hidden_dim");
+#endif
 }
 }  // extern C++
 
@@ -317,7 +324,13 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
     RolloutParams P;
     P.T = a->T; P.activation = a->activation; P.use_gae = a->use_gae; P.deterministic = a->deterministic;
     P.gamma = (float)a->gamma; P.lam = (float)a->gae_lambda; P.gamma_d = a->gamma; P.lam_d = a->gae_lambda;
-    P.policy = a->d_policy; P.eps = a->d_eps; P.noise_cursor = e->noise_cursor; P.out = *out;
+    P.policy = a->d_policy; P.eps = a->d_eps; P.noise_cursor = e->noise_cursor; P.out = *out; P.prof = nullptr;
+#ifdef SCG_PROF
+    static long long* d_prof = nullptr;
+    if (!d_prof) cudaMalloc((void**)&d_prof, 16 * sizeof(long long));
+    cudaMemset(d_prof, 0, 16 * sizeof(long long));
+    P.prof = d_prof;
+#endif
     cudaStream_t s = (cudaStream_t)stream;
     const bool dbl = e->cfg.precision == SCG_PREC_F64;
     switch (e->cfg.system) {
@@ -327,6 +340,20 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
         default: return fail(e, SCG_EINVAL, "scg_rollout: the fused collector supports cartpole, quadrotor 2D and 3D");
     }
     if (rc) return rc;
+#ifdef SCG_PROF
+    {
+        long long hp[16]; cudaMemcpy(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost);
+        const char* nm[16] = {"eps+obs_write", "mlp", "sample", "env_step", "make_obs/reset", "stores", "barrier", "-", "  es:preproc", "  es:physics", "  es:reward+mse", "  es:done", "  es:constraints", "-", "-", "tail(mlp+gae)"};
+        fprintf(stderr, "[SCG_PROF] CTA0 cycles per step (T=%d):", a->T);
+        for (int i = 0; i < 16; ++i) if (nm[i][0] != '-') fprintf(stderr, " %s=%.0f", nm[i], i == 15 ? (double)hp[i] : (double)hp[i] / a->T);
+        fprintf(stderr, "\n");
+        long long mp[8]; cudaMemcpyFromSymbol(mp, g_mlp_prof, sizeof(mp)); long long z8[8] = {0}; cudaMemcpyToSymbol(g_mlp_prof, z8, sizeof(z8));
+        const char* mn[8] = {"L1", "L1epi", "bar1", "L2", "L2epi", "bar2", "L3", "bar3"};
+        fprintf(stderr, "[SCG_PROF] mlp_forward cycles per call (%d calls):", a->T + 1);
+        for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.0f", mn[i], (double)mp[i] / (a->T + 1));
+        fprintf(stderr, "\n");
+    }
+#endif
     e->launches += 1; e->noise_cursor += a->T;
     return SCG_OK;
 }
@@ -341,16 +368,17 @@ int scg_policy_pack(int32_t obs_dim, int32_t act_dim, int32_t hid, const float* 
     if (!aw || !ab || !cw || !cb || !logstd || !blob) return SCG_EINVAL;
     const BlobLayout L = blob_layout(obs_dim, act_dim, hid);
     memset(blob, 0, sizeof(float) * L.total);
+    if ((obs_dim & 1) || (hid & 3)) return SCG_EINVAL;   // pair-major layout: even input width, hidden multiple of 4
     for (int k = 0; k < obs_dim; ++k)
-        for (int u = 0; u < hid; ++u) {
-            blob[L.w1t + k * 2 * hid + u] = aw[0][(size_t)u * obs_dim + k];          // nn.Linear weight is [out][in]
-            blob[L.w1t + k * 2 * hid + hid + u] = cw[0][(size_t)u * obs_dim + k];
+        for (int u = 0; u < hid; ++u) {   // W1P [k/2][2H][2]; nn.Linear weight is [out][in]
+            blob[L.w1t + ((k >> 1) * 2 * hid + u) * 2 + (k & 1)] = aw[0][(size_t)u * obs_dim + k];
+            blob[L.w1t + ((k >> 1) * 2 * hid + hid + u) * 2 + (k & 1)] = cw[0][(size_t)u * obs_dim + k];
         }
     for (int u = 0; u < hid; ++u) { blob[L.b1 + u] = ab[0][u]; blob[L.b1 + hid + u] = cb[0][u]; }
     for (int k = 0; k < hid; ++k)
-        for (int u = 0; u < hid; ++u) {
-            blob[L.w2t + k * hid + u] = aw[1][(size_t)u * hid + k];
-            blob[L.w2t + hid * hid + k * hid + u] = cw[1][(size_t)u * hid + k];
+        for (int u = 0; u < hid; ++u) {   // W2P [net][k/2][H][2]
+            blob[L.w2t + ((k >> 1) * hid + u) * 2 + (k & 1)] = aw[1][(size_t)u * hid + k];
+            blob[L.w2t + hid * hid + ((k >> 1) * hid + u) * 2 + (k & 1)] = cw[1][(size_t)u * hid + k];
         }
     for (int u = 0; u < hid; ++u) { blob[L.b2 + u] = ab[1][u]; blob[L.b2 + hid + u] = cb[1][u]; }
     for (int o = 0; o < act_dim; ++o)

@@ -66,7 +66,7 @@ template <typename R> __device__ __forceinline__ R normalize_angle(R x) {
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10, stream layout shared with the CPU oracle: ctr = (slot, idx, global env, stream),
-// key = (seed lo, seed hi).  One block per draw slot; uniform uses word 0, normal uses words 0,1.
+// key = (seed lo, seed hi).  Two draw slots per block (2 words each); uniform / randint use the first word, normal both.
 // ---------------------------------------------------------------------------------------------
 #define SCG_STREAM_EPISODE 1u
 #define SCG_STREAM_STEP 2u
@@ -88,23 +88,31 @@ __device__ __forceinline__ double u01_d(uint32_t x) { return ((double)x + 0.5) *
 
 struct RngKey { uint32_t k0, k1, genv; };
 
-template <typename R> __device__ __forceinline__ R rng_uniform(const RngKey& k, uint32_t stream, uint32_t idx, uint32_t slot) {
-    uint32_t x[4]; philox4x32_10(slot, idx, k.genv, stream, k.k0, k.k1, x);
-    return (R)u01_d(x[0]);
+// draw slot j of (stream, idx) = words 2(j&1), 2(j&1)+1 of block j>>1
+__device__ __forceinline__ void rng_words(const RngKey& k, uint32_t stream, uint32_t idx, uint32_t slot, uint32_t& w0, uint32_t& w1) {
+    uint32_t x[4]; philox4x32_10(slot >> 1, idx, k.genv, stream, k.k0, k.k1, x);
+    w0 = (slot & 1u) ? x[2] : x[0]; w1 = (slot & 1u) ? x[3] : x[1];
 }
-template <typename R> __device__ __forceinline__ R rng_normal(const RngKey& k, uint32_t stream, uint32_t idx, uint32_t slot) {
-    uint32_t x[4]; philox4x32_10(slot, idx, k.genv, stream, k.k0, k.k1, x);
+template <typename R> __device__ __forceinline__ R normal_from_words(uint32_t w0, uint32_t w1) {
     if (sizeof(R) == 8) {
-        return (R)(sqrt(-2.0 * log(u01_d(x[0]))) * cos(2.0 * SCG_PI * u01_d(x[1])));
+        return (R)(sqrt(-2.0 * log(u01_d(w0))) * cos(2.0 * SCG_PI * u01_d(w1)));
     } else {
-        float u0 = (float)u01_d(x[0]), u1 = (float)u01_d(x[1]);
+        float u0 = (float)u01_d(w0), u1 = (float)u01_d(w1);
         // u0 may round to 1.0f (log -> 0) but never to 0: (x+0.5)/2^32 >= 1.16e-10
         return (R)(sqrtf(-2.0f * logf(u0)) * cospif(2.0f * u1));
     }
 }
+template <typename R> __device__ __forceinline__ R rng_uniform(const RngKey& k, uint32_t stream, uint32_t idx, uint32_t slot) {
+    uint32_t w0, w1; rng_words(k, stream, idx, slot, w0, w1);
+    return (R)u01_d(w0);
+}
+template <typename R> __device__ __forceinline__ R rng_normal(const RngKey& k, uint32_t stream, uint32_t idx, uint32_t slot) {
+    uint32_t w0, w1; rng_words(k, stream, idx, slot, w0, w1);
+    return normal_from_words<R>(w0, w1);
+}
 __device__ __forceinline__ int rng_randint(const RngKey& k, uint32_t stream, uint32_t idx, uint32_t slot, uint32_t n) {
-    uint32_t x[4]; philox4x32_10(slot, idx, k.genv, stream, k.k0, k.k1, x);
-    return (int)__umulhi(x[0], n);
+    uint32_t w0, w1; rng_words(k, stream, idx, slot, w0, w1);
+    return (int)__umulhi(w0, n);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -251,6 +259,12 @@ template <typename R> struct HotCfg {
     R act_low[SCG_MAX_NU], act_high[SCG_MAX_NU], u_goal[SCG_MAX_NU], rew_act_w[SCG_MAX_NU], Rw[SCG_MAX_NU];
     R rew_state_w[SCG_MAX_NX], mse_w[SCG_MAX_NX], Qw[SCG_MAX_NX];
     double state_low[SCG_MAX_NX], state_high[SCG_MAX_NX];   // float32-rounded bounds, compared in double like numpy does
+    // reset / randomisation (rare path, but a warp executes it whenever ANY of its lanes terminates)
+    uint32_t key0, key1, genv0;
+    int randomized_init, randomized_inertial, n_off_draws;
+    int init_kind[SCG_MAX_NX], inertial_kind[SCG_MAX_INERTIAL];
+    double init_nominal[SCG_MAX_NX], init_a[SCG_MAX_NX], init_b[SCG_MAX_NX];
+    double inertial_nominal[SCG_MAX_INERTIAL], inertial_a[SCG_MAX_INERTIAL], inertial_b[SCG_MAX_INERTIAL];
     ConRow rows[SCG_MAX_CON_ROWS];
 };
 
@@ -280,6 +294,10 @@ __device__ __noinline__ void hot_load(const DevTables& T, HotCfg<R>* h) {
         h->rew_state_w[k] = (R)c->rew_state_weight[k]; h->mse_w[k] = (R)c->mse_weight[k]; h->Qw[k] = (R)c->Q[k];
         h->state_low[k] = c->state_low[k]; h->state_high[k] = c->state_high[k];
     }
+    h->key0 = (uint32_t)c->seed; h->key1 = (uint32_t)(c->seed >> 32); h->genv0 = (uint32_t)c->env_index_offset;
+    h->randomized_init = c->randomized_init; h->randomized_inertial = c->randomized_inertial; h->n_off_draws = T.n_off_slots;
+    for (int k = 0; k < SCG_MAX_NX; ++k) { h->init_kind[k] = c->init_rand_kind[k]; h->init_nominal[k] = c->init_nominal[k]; h->init_a[k] = c->init_rand_a[k]; h->init_b[k] = c->init_rand_b[k]; }
+    for (int k = 0; k < SCG_MAX_INERTIAL; ++k) { h->inertial_kind[k] = c->inertial_rand_kind[k]; h->inertial_nominal[k] = c->inertial_nominal[k]; h->inertial_a[k] = c->inertial_rand_a[k]; h->inertial_b[k] = c->inertial_rand_b[k]; }
     h->n_con = T.n_con; h->con_fast = 1;
     for (int r = 0; r < T.n_con; ++r) {
         const int p0 = T.con_ptr[r], p1 = T.con_ptr[r + 1];
@@ -551,16 +569,17 @@ template <typename R> struct Physics<SCG_SYS_QUAD3D, R> {
 // ---------------------------------------------------------------------------------------------
 // observation / reset / step
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ const double* goal_row(const DevTables& T, int task, int nx, int idx) {
-    if (task == SCG_TASK_STABILIZATION) return T.x_goal;
-    idx = idx > T.L - 1 ? T.L - 1 : idx;
-    return T.x_goal + (size_t)idx * nx;
+// X_GOAL row (clamped like quadrotor.py:837); GT = storage type of the table (double in global memory, R in the CTA's shared copy)
+template <typename GT> __device__ __forceinline__ const GT* goal_row(const GT* xg, int L, int task, int nx, int idx) {
+    if (task == SCG_TASK_STABILIZATION) return xg;
+    idx = idx > L - 1 ? L - 1 : idx;
+    return xg + idx * nx;
 }
 
 // _get_observation + extend_obs (quadrotor.py:777-817, cartpole.py:585-609, benchmark_env.py:422-445).
 // The observation is handed element by element to `sink(k, value)` (global buffers or the CTA's shared tile).
-template <int SYS, typename R, typename Sink>
-__device__ __forceinline__ void make_obs(const DevTables& T, const HotCfg<R>* h, const R* state, int n, int ctrl_step, bool at_reset,
+template <int SYS, typename R, typename GT, typename Sink>
+__device__ __forceinline__ void make_obs(const DevTables& T, const HotCfg<R>* h, const GT* xg, const R* state, int n, int ctrl_step, bool at_reset,
                                          NoiseSrc<R>& ns, Sink sink) {
     constexpr int NX = SysDims<SYS>::NX;
     if (h->has_dist[SCG_MODE_OBSERVATION]) {
@@ -583,49 +602,50 @@ __device__ __forceinline__ void make_obs(const DevTables& T, const HotCfg<R>* h,
         if (h->task == SCG_TASK_TRAJ_TRACKING) {
             const int next_step = at_reset ? 1 : ctrl_step + 2;
             for (int hh = 0; hh < h->obs_goal_horizon; ++hh) {
-                const double* g = goal_row(T, h->task, NX, next_step + hh);
+                const GT* g = goal_row<GT>(xg, h->L, h->task, NX, next_step + hh);
 #pragma unroll
                 for (int k = 0; k < NX; ++k) sink(NX * (1 + hh) + k, (R)g[k]);
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < NX; ++k) sink(NX + k, (R)T.x_goal[k]);
+            for (int k = 0; k < NX; ++k) sink(NX + k, (R)xg[k]);
         }
     }
 }
 
 // reset() of one env (quadrotor.py:328-392, cartpole.py:266-352); the caller builds the observation with make_obs(at_reset)
 template <int SYS, typename R>
-__device__ __noinline__ void env_reset(const DevTables& T, int n, EnvRegs<SYS, R>& e, R* state) {
+__device__ __forceinline__ void env_reset(const DevTables& T, const HotCfg<R>* h, int n, EnvRegs<SYS, R>& e, R* state) {
     constexpr int NX = SysDims<SYS>::NX;
-    const scg_config* c = T.cfg;
     const int k = e.episode;
-    const bool philox = c->rng_mode == SCG_RNG_PHILOX;
-    RngKey key; key.k0 = (uint32_t)c->seed; key.k1 = (uint32_t)(c->seed >> 32); key.genv = (uint32_t)(c->env_index_offset + n);
+    const bool philox = h->philox != 0;
+    RngKey key; key.k0 = h->key0; key.k1 = h->key1; key.genv = h->genv0 + (uint32_t)n;
     const double* row = (!philox && T.ep_table) ? T.ep_table + ((size_t)(k % T.K) * T.N + n) * T.P : nullptr;
     e.ctrl_step = 0;
     int slot = 0;
-    // disturbance reset draws (benchmark_env.py:336-337, disturbances.py:102-106,148-151)
-    for (int m = 0; m < 3; ++m)
-        for (int j = 0; j < c->n_dist[m]; ++j) {
-            const scg_disturbance* d = &c->dist[m][j];
-            if ((d->kind == SCG_DIST_IMPULSE || d->kind == SCG_DIST_STEP) && d->step_offset < 0) {
-                int v = row ? (int)row[slot] : (philox ? rng_randint(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)slot, (uint32_t)c->ctrl_steps) : 0);
-                T.st.dist_off[(size_t)(m * SCG_MAX_DIST + j) * T.N + n] = v; ++slot;
+    if (h->n_off_draws > 0) {
+        // disturbance reset draws (benchmark_env.py:336-337, disturbances.py:102-106,148-151)
+        const scg_config* c = T.cfg;
+        for (int m = 0; m < 3; ++m)
+            for (int j = 0; j < c->n_dist[m]; ++j) {
+                const scg_disturbance* d = &c->dist[m][j];
+                if ((d->kind == SCG_DIST_IMPULSE || d->kind == SCG_DIST_STEP) && d->step_offset < 0) {
+                    int v = row ? (int)row[slot] : (philox ? rng_randint(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)slot, (uint32_t)h->ctrl_steps) : 0);
+                    T.st.dist_off[(size_t)(m * SCG_MAX_DIST + j) * T.N + n] = v; ++slot;
+                }
             }
-        }
+    }
     const int n_inertial = (SYS == SCG_SYS_CARTPOLE) ? 3 : 4;
     // inertial properties, additive randomisation (benchmark_env.py:267)
 #pragma unroll
     for (int j = 0; j < SCG_MAX_INERTIAL; ++j) {
-        double v = c->inertial_nominal[j];
-        if (c->randomized_inertial && j < n_inertial) {
+        double v = h->inertial_nominal[j];
+        if (h->randomized_inertial && j < n_inertial) {
             if (row) v += row[slot + j];
-            else if (philox) {
-                if (c->inertial_rand_kind[j] == SCG_RAND_UNIFORM)
-                    v += c->inertial_rand_a[j] + (c->inertial_rand_b[j] - c->inertial_rand_a[j]) * rng_uniform<double>(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j));
-                else if (c->inertial_rand_kind[j] == SCG_RAND_NORMAL)
-                    v += c->inertial_rand_a[j] + c->inertial_rand_b[j] * rng_normal<double>(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j));
+            else if (philox && h->inertial_kind[j] != SCG_RAND_NONE) {
+                uint32_t w0, w1; rng_words(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j), w0, w1);
+                if (h->inertial_kind[j] == SCG_RAND_UNIFORM) v += h->inertial_a[j] + (h->inertial_b[j] - h->inertial_a[j]) * u01_d(w0);
+                else v += h->inertial_a[j] + h->inertial_b[j] * normal_from_words<double>(w0, w1);
             }
         }
         e.inertial[j] = (R)v;
@@ -634,14 +654,13 @@ __device__ __noinline__ void env_reset(const DevTables& T, int n, EnvRegs<SYS, R
     R init[NX];
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
-        double v = c->init_nominal[j];
-        if (c->randomized_init) {
+        double v = h->init_nominal[j];
+        if (h->randomized_init) {
             if (row) v += row[slot + j];
-            else if (philox) {
-                if (c->init_rand_kind[j] == SCG_RAND_UNIFORM)
-                    v += c->init_rand_a[j] + (c->init_rand_b[j] - c->init_rand_a[j]) * rng_uniform<double>(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j));
-                else if (c->init_rand_kind[j] == SCG_RAND_NORMAL)
-                    v += c->init_rand_a[j] + c->init_rand_b[j] * rng_normal<double>(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j));
+            else if (philox && h->init_kind[j] != SCG_RAND_NONE) {
+                uint32_t w0, w1; rng_words(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j), w0, w1);
+                if (h->init_kind[j] == SCG_RAND_UNIFORM) v += h->init_a[j] + (h->init_b[j] - h->init_a[j]) * u01_d(w0);
+                else v += h->init_a[j] + h->init_b[j] * normal_from_words<double>(w0, w1);
             }
         }
         init[j] = (R)v;
@@ -654,7 +673,7 @@ __device__ __noinline__ void env_reset(const DevTables& T, int n, EnvRegs<SYS, R
 // noise source of the reset-time observation (Philox stream RESET keyed by the episode; zero in table mode)
 template <typename R> __device__ __forceinline__ NoiseSrc<R> reset_noise(const DevTables& T, const HotCfg<R>* h, int n, int episode_done) {
     NoiseSrc<R> ns; ns.row = nullptr; ns.philox = h->philox != 0;
-    ns.key.k0 = (uint32_t)T.cfg->seed; ns.key.k1 = (uint32_t)(T.cfg->seed >> 32); ns.key.genv = (uint32_t)(T.cfg->env_index_offset + n);
+    ns.key.k0 = h->key0; ns.key.k1 = h->key1; ns.key.genv = h->genv0 + (uint32_t)n;
     ns.stream = SCG_STREAM_RESET; ns.idx = (uint32_t)(episode_done - 1); ns.slot = 0;
     return ns;
 }
@@ -663,17 +682,24 @@ struct StepInfo {
     int done, truncated, cviol, out_of_bounds, goal_reached, current_step;
 };
 
+#ifdef SCG_PROF
+#define SCG_TICK(i) do { if (prof_t) prof_t[i] = clock64(); } while (0)
+#else
+#define SCG_TICK(i) do { } while (0)
+#endif
+
 // One control step WITHOUT auto-reset and WITHOUT building the observation.  action[NU] is the raw controller action.
 // `zbuf` is this lane's column of a shared scratch [NX+NU][zstride] (doubles) used to index z = [state; input] by constraint column.
 // On return `state` holds env.state; `ns` is positioned for the observation noise (call make_obs next).
-template <int SYS, typename R>
-__device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h, int n, EnvRegs<SYS, R>& e, const R* action, const double* noise_row,
-                                         double* zbuf, int zstride, R* state, R& rew_out, R& mse_out, StepInfo& info,
-                                         double* cvals, float* cvals_f32, NoiseSrc<R>& ns) {
+template <int SYS, typename R, typename GT>
+__device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h, const GT* xg, int n, EnvRegs<SYS, R>& e, const R* action, const double* noise_row,
+                                         double* __restrict__ zbuf, int zstride, R* state, R& rew_out, R& mse_out, StepInfo& info,
+                                         double* cvals, float* cvals_f32, NoiseSrc<R>& ns, long long* prof_t = nullptr) {
     constexpr int NX = SysDims<SYS>::NX, NU = SysDims<SYS>::NU;
     const int pyb_step = e.ctrl_step * h->steps;
+    SCG_TICK(0);
     ns.row = noise_row; ns.philox = h->philox != 0;
-    ns.key.k0 = (uint32_t)T.cfg->seed; ns.key.k1 = (uint32_t)(T.cfg->seed >> 32); ns.key.genv = (uint32_t)(T.cfg->env_index_offset + n);
+    ns.key.k0 = h->key0; ns.key.k1 = h->key1; ns.key.genv = h->genv0 + (uint32_t)n;
     ns.stream = SCG_STREAM_STEP; ns.idx = e.total_steps; ns.slot = 0;
 
     R noisy[NU], clipped[NU];
@@ -697,6 +723,7 @@ __device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h,
         const int ddim = (SYS == SCG_SYS_CARTPOLE) ? 2 : (SYS == SCG_SYS_QUAD1D) ? 1 : (SYS == SCG_SYS_QUAD2D) ? 2 : 3;
         apply_disturbances<R>(T.cfg, T.st.dist_off, T.N, n, SCG_MODE_DYNAMICS, e.ctrl_step, pyb_step, fd, ddim, ns);
     }
+    SCG_TICK(1);
     if (SYS == SCG_SYS_CARTPOLE) {
         Physics<SYS, R>::advance(h, e, clipped, fd, has_dyn);
     } else {
@@ -704,11 +731,12 @@ __device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h,
         Physics<SYS, R>::advance(h, e, f, fd, has_dyn);
     }
     Physics<SYS, R>::state(e, state);
+    SCG_TICK(2);
 
     // ---- reward (quadrotor.py:819-862, cartpole.py:611-652) and info['mse'] (quadrotor.py:907-922, cartpole.py:685-695)
     R rew, mse = (R)0;
     {
-        const double* g = goal_row(T, h->task, NX, e.ctrl_step + 1);
+        const GT* g = goal_row<GT>(xg, h->L, h->task, NX, e.ctrl_step + 1);
         R gk[NX];
 #pragma unroll
         for (int k = 0; k < NX; ++k) gk[k] = (R)g[k];
@@ -730,7 +758,7 @@ __device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h,
             if (h->rew_exponential) rew = Mth<R>::exp_(rew);
         } else {
             const int idx = (SYS == SCG_SYS_CARTPOLE) ? e.ctrl_step : e.ctrl_step + 1;                                // cartpole.py:648 / quadrotor.py:858
-            const double* gq = goal_row(T, h->task, NX, idx);
+            const GT* gq = goal_row<GT>(xg, h->L, h->task, NX, idx);
             R l = (R)0;
 #pragma unroll
             for (int k = 0; k < NX; ++k) { const R er = state[k] - (R)gq[k]; l += (R)0.5 * h->Qw[k] * er * er; }
@@ -749,12 +777,13 @@ __device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h,
             mse += er * er;
         }
     }
+    SCG_TICK(3);
     // ---- done (quadrotor.py:864-894, cartpole.py:654-672)
     int done = 0, goal_reached = 0, oob = 0;
     if (h->task == SCG_TASK_STABILIZATION) {
         R n2 = (R)0;
 #pragma unroll
-        for (int k = 0; k < NX; ++k) { const R er = state[k] - (R)T.x_goal[k]; n2 += er * er; }
+        for (int k = 0; k < NX; ++k) { const R er = state[k] - (R)xg[k]; n2 += er * er; }
         goal_reached = Mth<R>::sqrt_(n2) < h->goal_tol;
         done = goal_reached;
     }
@@ -771,6 +800,7 @@ __device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h,
         }
         done = oob;
     }
+    SCG_TICK(4);
     // ---- after_step (benchmark_env.py:447-502)
     e.ctrl_step += 1; e.total_steps += 1;
     int cviol = 0;
@@ -782,15 +812,25 @@ __device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h,
 #pragma unroll
         for (int k = 0; k < NU; ++k) zbuf[(NX + k) * zstride] = (double)noisy[k];
         if (h->con_fast) {
+            // violated <=> np.round(g, 8) > 0 (>= 0 if strict) <=> g*1e8 > 0.5 (>= -0.5): rint() rounds half to even
+            // (constraints.py:109,126-129); no stores inside this loop so the rows pipeline
 #pragma unroll 4
             for (int r = 0; r < n_con; ++r) {
                 const ConRow row = h->rows[r];
                 double acc = __dmul_rn(row.val, zbuf[row.col * zstride]);
                 if (row.flags & 2) acc = fabs(acc);
-                const double gi = rint(__dsub_rn(acc, row.b) * 1e8);   // np.round(g, 8) = rint(g*1e8)/1e8 (constraints.py:109)
-                cviol |= (row.flags & 1) ? (gi >= 0.0) : (gi > 0.0);   // constraints.py:126-129
-                if (cvals) cvals[r] = gi / 1e8;
-                if (cvals_f32) cvals_f32[r] = (float)(gi / 1e8);
+                const double t8 = __dsub_rn(acc, row.b) * 1e8;
+                cviol |= (row.flags & 1) ? (t8 >= -0.5) : (t8 > 0.5);
+            }
+            if (cvals || cvals_f32) {
+                for (int r = 0; r < n_con; ++r) {
+                    const ConRow row = h->rows[r];
+                    double acc = __dmul_rn(row.val, zbuf[row.col * zstride]);
+                    if (row.flags & 2) acc = fabs(acc);
+                    const double g8 = rint(__dsub_rn(acc, row.b) * 1e8) / 1e8;   // np.round(g, 8)
+                    if (cvals) cvals[r] = g8;
+                    if (cvals_f32) cvals_f32[r] = (float)g8;
+                }
             }
         } else {
             for (int r = 0; r < n_con; ++r) {
@@ -809,6 +849,7 @@ __device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h,
             else rew -= h->penalty;
         }
     }
+    SCG_TICK(5);
     int truncated = 0;
     if (e.ctrl_step >= h->ctrl_steps) { truncated = !done; done = 1; }
     rew_out = rew; mse_out = mse;

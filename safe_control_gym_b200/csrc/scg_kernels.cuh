@@ -13,14 +13,16 @@
 
 // ---------------------------------------------------------------------------------------------
 // policy blob layout (floats), produced by scg_policy_pack() / the python packer:
-//   W1T [OBS][2H]   layer-1 weights, k-major, actor units 0..H-1 then critic units H..2H-1
+//   W1P [OBS/2][2H][2] layer-1 weights, input-PAIR major: (w[k][u], w[k+1][u]) adjacent; actor units 0..H-1, critic H..2H-1
 //   b1  [2H]
-//   W2T [2][H][H]   layer-2 weights per net, k-major
+//   W2P [2][H/2][H][2] layer-2 weights per net, input-pair major
 //   b2  [2H]
 //   W3  [A+1][H]    A actor output rows then the critic row
 //   b3  [pad4(A+1)]
 //   logstd [pad4(A)]
 // every section is a multiple of 4 floats so that the whole blob can be staged with one TMA bulk copy.
+// The pair-major order feeds Blackwell's packed FP32 pipe: one FFMA2 multiplies an (input k, k+1) activation pair
+// with the matching weight pair and accumulates the even / odd partial sums of a unit.
 // ---------------------------------------------------------------------------------------------
 struct BlobLayout {
     int w1t, b1, w2t, b2, w3, b3, logstd, total;
@@ -89,10 +91,31 @@ template <int ACT> __device__ __forceinline__ float hidden_act(float x) {
     if (ACT == SCG_ACT_RELU) return fmaxf(x, 0.0f);
     return x > 0.0f ? x : 0.01f * x;
 }
-__device__ __forceinline__ float hidden_act_rt(float x, int act) {
-    if (act == SCG_ACT_TANH) return tanh_fast(x);
-    if (act == SCG_ACT_RELU) return fmaxf(x, 0.0f);
-    return x > 0.0f ? x : 0.01f * x;
+// hidden activation over a register tile; the (CTA-uniform) kind is switched once per tile, not per element
+template <int TU> __device__ __forceinline__ void apply_hidden_act(float (&acc)[4][TU], int act) {
+    if (act == SCG_ACT_TANH) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < TU; ++j) acc[i][j] = tanh_fast(acc[i][j]);
+    } else if (act == SCG_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < TU; ++j) acc[i][j] = fmaxf(acc[i][j], 0.0f);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < TU; ++j) acc[i][j] = acc[i][j] > 0.0f ? acc[i][j] : 0.01f * acc[i][j];
+    }
+}
+
+// Activation tiles (observations and hidden features) are stored "pair-swizzled": feature pair kp = k/2, env group eg = e/4,
+// half = (e/2)&1; the 16-byte chunk ((kp*2+half)*EG+eg) holds (x[e][k], x[e][k+1], x[e+1][k], x[e+1][k+1]) for the even env e
+// of the half.  A thread's 4 envs x 2 features are two conflict-free LDS.128 and arrive as ready-made float2 operands.
+template <int E> __device__ __forceinline__ int tile_idx(int k, int e) {
+    return ((((k >> 1) * 2 + ((e >> 1) & 1)) * (E / 4) + (e >> 2)) << 2) + ((e & 1) << 1) + (k & 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -106,9 +129,9 @@ struct GlobalObsSink {      // row `n` of up to three [N][obs_dim] global buffer
         if (c) c[base + k] = (double)v;
     }
 };
-struct SmemObsSink {        // column of the CTA's [obs_dim][EP] float tile
-    float* col; int stride;
-    template <typename R> __device__ __forceinline__ void operator()(int k, R v) const { col[k * stride] = (float)v; }
+template <int E> struct TileObsSink {   // env `e` of the CTA's pair-swizzled observation tile (see tile_idx)
+    float* tile; int e;
+    template <typename R> __device__ __forceinline__ void operator()(int k, R v) const { tile[tile_idx<E>(k, e)] = (float)v; }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -138,13 +161,13 @@ __global__ void __launch_bounds__(SCG_LANE_BLOCK) reset_kernel(DevTables T, Rese
     EnvRegs<SYS, R> e;
     env_load<SYS, R>(T, n, e);
     R state[NX];
-    env_reset<SYS, R>(T, n, e, state);
+    env_reset<SYS, R>(T, h, n, e, state);
     e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
     T.st.initial_reset[n] = 1;
     env_store<SYS, R>(T, n, e);
     NoiseSrc<R> ns = reset_noise<R>(T, h, n, e.episode);
     GlobalObsSink sink{T.st.cur_obs, A.obs, A.obs_f64, (size_t)n * od};
-    make_obs<SYS, R>(T, h, state, n, 0, true, ns, sink);
+    make_obs<SYS, R, double>(T, h, T.x_goal, state, n, 0, true, ns, sink);
     if (A.state_f64) for (int k = 0; k < NX; ++k) A.state_f64[(size_t)n * NX + k] = (double)state[k];
 }
 
@@ -173,22 +196,22 @@ __global__ void __launch_bounds__(SCG_LANE_BLOCK) step_kernel(DevTables T, StepA
     R state[NX], rew, mse; StepInfo info; NoiseSrc<R> ns;
     const scg_step_out& o = A.out;
     double* cv = o.d_cvals ? o.d_cvals + (size_t)n * nc : nullptr;
-    env_step<SYS, R>(T, h, n, e, action, nrow, s_z + threadIdx.x, SCG_LANE_BLOCK, state, rew, mse, info, cv, nullptr, ns);
+    env_step<SYS, R, double>(T, h, T.x_goal, n, e, action, nrow, s_z + threadIdx.x, SCG_LANE_BLOCK, state, rew, mse, info, cv, nullptr, ns);
     e.ep_ret += (float)rew; e.ep_len += 1.f; e.ep_cv += (float)info.cviol;
     const bool reset_now = info.done && c->auto_reset;
     {   // observation of the transition: the returned obs unless the env auto-resets, always the terminal obs
         GlobalObsSink term{o.d_terminal_obs, nullptr, o.d_terminal_obs_f64, (size_t)n * od};
         GlobalObsSink cur{reset_now ? nullptr : T.st.cur_obs, reset_now ? nullptr : o.d_obs, reset_now ? nullptr : o.d_obs_f64, (size_t)n * od};
         auto both = [&](int k, R v) { term(k, v); cur(k, v); };
-        make_obs<SYS, R>(T, h, state, n, e.ctrl_step - 1, false, ns, both);
+        make_obs<SYS, R, double>(T, h, T.x_goal, state, n, e.ctrl_step - 1, false, ns, both);
     }
     if (o.d_terminal_state_f64) for (int k = 0; k < NX; ++k) o.d_terminal_state_f64[(size_t)n * NX + k] = (double)state[k];
     if (reset_now) {   // dummy_vec_env.py:33-38
-        env_reset<SYS, R>(T, n, e, state);
+        env_reset<SYS, R>(T, h, n, e, state);
         e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
         NoiseSrc<R> rs = reset_noise<R>(T, h, n, e.episode);
         GlobalObsSink sink{T.st.cur_obs, o.d_obs, o.d_obs_f64, (size_t)n * od};
-        make_obs<SYS, R>(T, h, state, n, 0, true, rs, sink);
+        make_obs<SYS, R, double>(T, h, T.x_goal, state, n, 0, true, rs, sink);
     }
     env_store<SYS, R>(T, n, e);
     if (o.d_state_f64) for (int k = 0; k < NX; ++k) o.d_state_f64[(size_t)n * NX + k] = (double)state[k];
@@ -216,139 +239,156 @@ struct RolloutParams {
     const float* eps;    // [T][N][A] or null
     long long noise_cursor;
     scg_rollout_out out;
+    long long* prof;     // SCG_PROF builds: per-phase cycle counters of CTA 0 (nullable)
 };
 
 // shared memory carve-up (floats), all offsets multiples of 4
 template <int HID, int E> struct RolloutSmem {
-    static constexpr int EP = E + 4;   // padded env stride of the observation tiles
-    int blob, obs, tobs, h1, h2, out, total_floats;
-    __host__ __device__ RolloutSmem(int obs_dim, int act_dim) {
+    int blob, obs, tobs, h1, h2, out, xg, total_floats;
+    // xg_floats: size of the shared X_GOAL copy in float units (L * nx * sizeof(R) / 4)
+    __host__ __device__ RolloutSmem(int obs_dim, int act_dim, int xg_floats) {
         BlobLayout L = blob_layout(obs_dim, act_dim, HID);
         blob = 0;
         obs = blob + L.total;
-        tobs = obs + obs_dim * EP;
-        h1 = tobs + obs_dim * EP;
+        h1 = obs + obs_dim * E;
         h2 = h1 + 2 * HID * E;
-        out = h2 + 2 * HID * E;
-        total_floats = out + pad4i((act_dim + 1) * E);
+        tobs = h2;                       // aliases h2: see rollout_kernel (c)
+        out = h2 + (2 * HID * E > obs_dim * E ? 2 * HID * E : obs_dim * E);
+        xg = out + pad4i((act_dim + 1) * E);
+        total_floats = xg + pad4i(xg_floats);
     }
 };
 
 // One fused actor+critic forward for the CTA's E envs.
-//   in  : s_in  [obs_dim][EP]  (float observations, env-minor)
+//   in  : s_in  pair-swizzled observation tile (tile_idx)
 //   out : s_out [A+1][E]       (A action means, then the value)
 // Layers 1 and 2 are register-tiled FP32 GEMMs: each thread owns a (4 envs x TU units) tile, weights and
 // activations stream from shared memory as 128-bit loads (weights broadcast across the env groups of a warp,
 // activations broadcast across its unit groups).
+#ifdef SCG_PROF
+__device__ long long g_mlp_prof[8];
+#define MLP_TICK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_mlp_prof[i] += clock64() - mt; mt = clock64(); } while (0)
+#else
+#define MLP_TICK(i) do { } while (0)
+#endif
+
 template <int HID, int E, int NT, int A>
 __device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const BlobLayout L, const float* __restrict__ s_in, float* __restrict__ s_h1,
                                          float* __restrict__ s_h2, float* __restrict__ s_out, int obs_dim, int act) {
-    constexpr int EP = E + 4;
     constexpr int EG = E / 4;              // env groups
     constexpr int UG = NT / EG;            // unit groups
     constexpr int TU = (2 * HID) / UG;     // units per thread
-    static_assert(TU == 2 || TU == 4 || TU == 8, "unsupported tile");
+    static_assert(TU == 2 || TU == 4, "unsupported tile");
     static_assert(HID % TU == 0 && (2 * HID) % UG == 0, "tile must not straddle nets");
     const int tid = threadIdx.x;
     const int eg = tid % EG, ug = tid / EG;
-    const int e0 = eg * 4, u0 = ug * TU;
+    const int u0 = ug * TU;
     const int net = u0 / HID, ul0 = u0 % HID;
 
-    float acc[4][TU];
+#ifdef SCG_PROF
+    long long mt = clock64();
+#endif
+    float2 acc[4][TU];   // (even-k, odd-k) partial sums of env i x unit j
+    // one input pair: 4 envs x (k, k+1) activations, TU units x (k, k+1) weights -> 4*TU packed FMAs (FFMA2)
+    auto pair_step = [&](const float* __restrict__ a_chunk, const float* __restrict__ w_chunk) {
+        const float4 a01 = *reinterpret_cast<const float4*>(a_chunk);                 // envs 0,1 of the group
+        const float4 a23 = *reinterpret_cast<const float4*>(a_chunk + EG * 4);        // envs 2,3 (the other half)
+        const float2 av[4] = {make_float2(a01.x, a01.y), make_float2(a01.z, a01.w), make_float2(a23.x, a23.y), make_float2(a23.z, a23.w)};
+        float2 wv[TU];
+#pragma unroll
+        for (int j = 0; j < TU; j += 2) {
+            const float4 w = *reinterpret_cast<const float4*>(w_chunk + 2 * j);
+            wv[j] = make_float2(w.x, w.y); wv[j + 1] = make_float2(w.z, w.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < TU; ++j) acc[i][j] = __ffma2_rn(av[i], wv[j], acc[i][j]);
+    };
+    auto finish = [&](float* __restrict__ dst, int dst_unit0) {   // reduce pairs, activate, store pair-swizzled as the next layer's input
+        float h[4][TU];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < TU; ++j) h[i][j] = acc[i][j].x + acc[i][j].y;
+        apply_hidden_act<TU>(h, act);
+#pragma unroll
+        for (int j = 0; j < TU; j += 2) {
+            float* d = dst + ((((dst_unit0 + j) >> 1) * 2) * EG + eg) * 4;
+            *reinterpret_cast<float4*>(d) = make_float4(h[0][j], h[0][j + 1], h[1][j], h[1][j + 1]);
+            *reinterpret_cast<float4*>(d + EG * 4) = make_float4(h[2][j], h[2][j + 1], h[3][j], h[3][j + 1]);
+        }
+    };
     // ---- layer 1: [E x obs] . [obs x 2H]
     {
         const float* b1 = s_blob + L.b1 + u0;
 #pragma unroll
-        for (int j = 0; j < TU; ++j) { float b = b1[j]; acc[0][j] = b; acc[1][j] = b; acc[2][j] = b; acc[3][j] = b; }
-        const float* w = s_blob + L.w1t + u0;
-        const float* a = s_in + e0;
-#pragma unroll 4
-        for (int k = 0; k < obs_dim; ++k) {
-            const float4 av = *reinterpret_cast<const float4*>(a + k * EP);
-            float wv[TU];
-            if (TU == 2) { float2 t = *reinterpret_cast<const float2*>(w + k * 2 * HID); wv[0] = t.x; wv[1] = t.y; }
-            else {
-#pragma unroll
-                for (int j = 0; j < TU; j += 4) { float4 t = *reinterpret_cast<const float4*>(w + k * 2 * HID + j); wv[j] = t.x; wv[j + 1] = t.y; wv[j + 2] = t.z; wv[j + 3] = t.w; }
-            }
-#pragma unroll
-            for (int j = 0; j < TU; ++j) {
-                acc[0][j] = fmaf(av.x, wv[j], acc[0][j]); acc[1][j] = fmaf(av.y, wv[j], acc[1][j]);
-                acc[2][j] = fmaf(av.z, wv[j], acc[2][j]); acc[3][j] = fmaf(av.w, wv[j], acc[3][j]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < TU; ++j) {
-            float4 h;
-            h.x = hidden_act_rt(acc[0][j], act); h.y = hidden_act_rt(acc[1][j], act); h.z = hidden_act_rt(acc[2][j], act); h.w = hidden_act_rt(acc[3][j], act);
-            *reinterpret_cast<float4*>(s_h1 + (u0 + j) * E + e0) = h;
-        }
+        for (int j = 0; j < TU; ++j) { const float b = b1[j]; acc[0][j] = make_float2(b, 0.f); acc[1][j] = acc[0][j]; acc[2][j] = acc[0][j]; acc[3][j] = acc[0][j]; }
+        const float* w = s_blob + L.w1t + u0 * 2;
+        const float* a = s_in + eg * 4;
+        const int npair = obs_dim >> 1;
+#pragma unroll 2
+        for (int kp = 0; kp < npair; ++kp) pair_step(a + kp * (2 * EG * 4), w + kp * (2 * HID * 2));
+        MLP_TICK(0);
+        finish(s_h1 + net * (HID / 2) * (2 * EG * 4), ul0);
+        MLP_TICK(1);
     }
     __syncthreads();
+    MLP_TICK(2);
     // ---- layer 2: per net [E x H] . [H x H]
     {
         const float* b2 = s_blob + L.b2 + u0;
 #pragma unroll
-        for (int j = 0; j < TU; ++j) { float b = b2[j]; acc[0][j] = b; acc[1][j] = b; acc[2][j] = b; acc[3][j] = b; }
-        const float* w = s_blob + L.w2t + net * HID * HID + ul0;
-        const float* a = s_h1 + net * HID * E + e0;
-#pragma unroll 8
-        for (int k = 0; k < HID; ++k) {
-            const float4 av = *reinterpret_cast<const float4*>(a + k * E);
-            float wv[TU];
-            if (TU == 2) { float2 t = *reinterpret_cast<const float2*>(w + k * HID); wv[0] = t.x; wv[1] = t.y; }
-            else {
-#pragma unroll
-                for (int j = 0; j < TU; j += 4) { float4 t = *reinterpret_cast<const float4*>(w + k * HID + j); wv[j] = t.x; wv[j + 1] = t.y; wv[j + 2] = t.z; wv[j + 3] = t.w; }
-            }
-#pragma unroll
-            for (int j = 0; j < TU; ++j) {
-                acc[0][j] = fmaf(av.x, wv[j], acc[0][j]); acc[1][j] = fmaf(av.y, wv[j], acc[1][j]);
-                acc[2][j] = fmaf(av.z, wv[j], acc[2][j]); acc[3][j] = fmaf(av.w, wv[j], acc[3][j]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < TU; ++j) {
-            float4 h;
-            h.x = hidden_act_rt(acc[0][j], act); h.y = hidden_act_rt(acc[1][j], act); h.z = hidden_act_rt(acc[2][j], act); h.w = hidden_act_rt(acc[3][j], act);
-            *reinterpret_cast<float4*>(s_h2 + (u0 + j) * E + e0) = h;
-        }
+        for (int j = 0; j < TU; ++j) { const float b = b2[j]; acc[0][j] = make_float2(b, 0.f); acc[1][j] = acc[0][j]; acc[2][j] = acc[0][j]; acc[3][j] = acc[0][j]; }
+        const float* w = s_blob + L.w2t + net * HID * HID + ul0 * 2;
+        const float* a = s_h1 + net * (HID / 2) * (2 * EG * 4) + eg * 4;
+#pragma unroll 4
+        for (int kp = 0; kp < HID / 2; ++kp) pair_step(a + kp * (2 * EG * 4), w + kp * (HID * 2));
+        MLP_TICK(3);
+        finish(s_h2 + net * (HID / 2) * (2 * EG * 4), ul0);
+        MLP_TICK(4);
     }
     __syncthreads();
+    MLP_TICK(5);
     // ---- layer 3: A action means from the actor features, 1 value from the critic features
     {
         const int g = tid / E, e = tid % E;
         if (g < A + 1) {
             const float* w = s_blob + L.w3 + g * HID;
-            const float* h = s_h2 + (g < A ? 0 : HID) * E + e;
-            float s0 = s_blob[L.b3 + g], s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            const float* hh = s_h2 + (g < A ? 0 : (HID / 2) * (2 * EG * 4)) + ((((e >> 1) & 1) * EG + (e >> 2)) << 2) + ((e & 1) << 1);
+            float2 s0 = make_float2(s_blob[L.b3 + g], 0.f), s1 = make_float2(0.f, 0.f);
 #pragma unroll 4
-            for (int k = 0; k < HID; k += 4) {
-                const float4 wv = *reinterpret_cast<const float4*>(w + k);
-                s0 = fmaf(wv.x, h[(k + 0) * E], s0); s1 = fmaf(wv.y, h[(k + 1) * E], s1);
-                s2 = fmaf(wv.z, h[(k + 2) * E], s2); s3 = fmaf(wv.w, h[(k + 3) * E], s3);
+            for (int kp = 0; kp < HID / 2; kp += 2) {
+                const float4 wv = *reinterpret_cast<const float4*>(w + 2 * kp);
+                const float2 h0 = *reinterpret_cast<const float2*>(hh + kp * (2 * EG * 4));
+                const float2 h1 = *reinterpret_cast<const float2*>(hh + (kp + 1) * (2 * EG * 4));
+                s0 = __ffma2_rn(h0, make_float2(wv.x, wv.y), s0);
+                s1 = __ffma2_rn(h1, make_float2(wv.z, wv.w), s1);
             }
-            s_out[g * E + e] = (s0 + s1) + (s2 + s3);
+            s_out[g * E + e] = (s0.x + s0.y) + (s1.x + s1.y);
         }
     }
+    MLP_TICK(6);
     __syncthreads();
+    MLP_TICK(7);
 }
 
 template <int SYS, typename R, int HID, int E, int NT>
 __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams P) {
     constexpr int NX = SysDims<SYS>::NX, A = SysDims<SYS>::NU;
-    constexpr int EP = E + 4;
     static_assert(NT / E >= A + 1, "layer 3 needs A+1 lane groups");
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ HotCfg<R> s_hot;
     __shared__ double s_z[(NX + A) * E];
+    __shared__ float s_eps[A * E];
+    __shared__ uint32_t s_tsteps0[E];
 
     const scg_config* c = T.cfg;
     const int od = T.obs_dim, N = T.N, nc = T.n_con;
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * E;
-    const RolloutSmem<HID, E> S(od, A);
+    const RolloutSmem<HID, E> S(od, A, T.L * NX * (int)(sizeof(R) / 4));
     const BlobLayout L = blob_layout(od, A, HID);
     float* s_blob = smem + S.blob;
     float* s_obs = smem + S.obs;
@@ -356,6 +396,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
     float* s_h1 = smem + S.h1;
     float* s_h2 = smem + S.h2;
     float* s_out = smem + S.out;
+    R* s_xg = reinterpret_cast<R*>(smem + S.xg);      // X_GOAL [L][nx] in the integrator's precision
 
     // ---- stage the packed policy into shared memory with one TMA bulk copy
     if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
@@ -373,43 +414,76 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
     const bool live = owner && n < N;
     EnvRegs<SYS, R> e;
     if (live) env_load<SYS, R>(T, n, e);
+    if (owner) s_tsteps0[tid] = live ? e.total_steps : 0u;
+    for (int i = tid; i < T.L * NX; i += NT) s_xg[i] = (R)T.x_goal[i];
     for (int i = tid; i < E * od; i += NT) {
         const int ee = i / od, k = i % od;
-        s_obs[k * EP + ee] = (n0 + ee < N) ? T.st.cur_obs[(size_t)(n0 + ee) * od + k] : 0.f;
-        s_tobs[k * EP + ee] = 0.f;
+        s_obs[tile_idx<E>(k, ee)] = (n0 + ee < N) ? T.st.cur_obs[(size_t)(n0 + ee) * od + k] : 0.f;
     }
     float ep_ret_sum = 0.f, ep_len_sum = 0.f, ep_cv_sum = 0.f; int ep_count = 0;
     mbar_wait(&s_bar, 0);
     __syncthreads();
-    float sd[A], lsd[A];
+    float sd[A], lsd[A], inv2var[A];
 #pragma unroll
-    for (int k = 0; k < A; ++k) { lsd[k] = s_blob[L.logstd + k]; sd[k] = expf(lsd[k]); }
+    for (int k = 0; k < A; ++k) { lsd[k] = s_blob[L.logstd + k]; sd[k] = expf(lsd[k]); inv2var[k] = 1.0f / (2.f * sd[k] * sd[k]); }
     const float log_sqrt_2pi = 0.91893853320467267f;
     const bool philox_eps = (P.eps == nullptr);
-    RngKey pkey; pkey.k0 = (uint32_t)c->seed; pkey.k1 = (uint32_t)(c->seed >> 32); pkey.genv = (uint32_t)(c->env_index_offset + n);
+    // obs write-out: element i = tid + j*NT of the [E][od] record maps to (env i / od, dim i % od); advance incrementally
+    const int ow_k = tid % od, ow_e = tid / od, ow_dk = NT % od, ow_de = NT / od;
 
+#ifdef SCG_PROF
+    long long pacc[16]; for (int i = 0; i < 16; ++i) pacc[i] = 0;
+    long long pt[8];
+#define PROF_ON (P.prof != nullptr && tid == 0)
+#endif
     for (int t = 0; t < P.T; ++t) {
         const size_t tn0 = (size_t)t * N + n0;
-        // standard-normal draws for this step (table mode): issue the loads before the MLP hides their latency
+#ifdef SCG_PROF
+        long long k0 = clock64();
+#endif
+        // standard-normal draws of this step: table mode -> owner lanes issue the loads now (latency hidden by the MLP);
+        // Philox mode -> the LAST lane group (idle during layer 3) generates them into shared memory, off the owners' critical path
         float z[A];
 #pragma unroll
         for (int k = 0; k < A; ++k) z[k] = 0.f;
-        if (live && !P.deterministic) {
+        if (!P.deterministic) {
             if (!philox_eps) {
+                if (live) {
 #pragma unroll
-                for (int k = 0; k < A; ++k) z[k] = __ldg(P.eps + (tn0 + tid) * A + k);
-            } else {
+                    for (int k = 0; k < A; ++k) z[k] = __ldg(P.eps + (tn0 + tid) * A + k);
+                }
+            } else if (tid >= NT - E) {
+                const int ee = tid - (NT - E);
+                if (n0 + ee < N) {
+                    RngKey pk; pk.k0 = h->key0; pk.k1 = h->key1; pk.genv = h->genv0 + (uint32_t)(n0 + ee);
+                    const uint32_t idx = s_tsteps0[ee] + (uint32_t)t;     // == that env's total_steps
 #pragma unroll
-                for (int k = 0; k < A; ++k) z[k] = rng_normal<float>(pkey, SCG_STREAM_POLICY, e.total_steps, (uint32_t)k);
+                    for (int k = 0; k < A; k += 2) {                      // one Philox block serves two action dims
+                        uint32_t x[4]; philox4x32_10((uint32_t)(k >> 1), idx, pk.genv, SCG_STREAM_POLICY, pk.k0, pk.k1, x);
+                        s_eps[k * E + ee] = normal_from_words<float>(x[0], x[1]);
+                        if (k + 1 < A) s_eps[(k + 1) * E + ee] = normal_from_words<float>(x[2], x[3]);
+                    }
+                }
             }
         }
         // (a) PPOBuffer.obs[t] <- observation tile (coalesced), then the policy forward
         {
             float* dst = P.out.d_obs + tn0 * od;
             const int lim = (N - n0 < E ? N - n0 : E) * od;
-            for (int i = tid; i < lim; i += NT) dst[i] = s_obs[(i % od) * EP + (i / od)];
+            int k = ow_k, ee = ow_e;
+            for (int i = tid; i < lim; i += NT) {
+                dst[i] = s_obs[tile_idx<E>(k, ee)];
+                k += ow_dk; ee += ow_de;
+                if (k >= od) { k -= od; ee += 1; }
+            }
         }
+#ifdef SCG_PROF
+        long long k1 = clock64();
+#endif
         mlp_forward<HID, E, NT, A>(s_blob, L, s_obs, s_h1, s_h2, s_out, od, P.activation);
+#ifdef SCG_PROF
+        long long k2 = clock64(), k3 = k2, k4 = k2, k5 = k2;
+#endif
 
         // (b) owner lanes: sample, step the env, emit the record
         int trunc = 0;
@@ -417,10 +491,11 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
             float act[A], logp = 0.f;
 #pragma unroll
             for (int k = 0; k < A; ++k) {
+                const float zk = (philox_eps && !P.deterministic) ? s_eps[k * E + tid] : z[k];
                 const float mu = s_out[k * E + tid];
-                act[k] = fmaf(sd[k], z[k], mu);                       // Normal.sample (ppo_utils.py:228)
+                act[k] = fmaf(sd[k], zk, mu);                         // Normal.sample (ppo_utils.py:228)
                 const float d = act[k] - mu;
-                logp += -(d * d) / (2.f * sd[k] * sd[k]) - lsd[k] - log_sqrt_2pi;   // distributions.py:12-21
+                logp += -(d * d) * inv2var[k] - lsd[k] - log_sqrt_2pi;   // distributions.py:12-21
             }
             const float val = s_out[A * E + tid];
             R action[A];
@@ -430,21 +505,30 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
                                      ? T.noise_table + ((size_t)((P.noise_cursor + t) % T.Tn) * N + n) * T.D : nullptr;
             R state[NX], rew, mse; StepInfo info; NoiseSrc<R> ns;
             float* cvp = P.out.d_cvals ? P.out.d_cvals + (tn0 + tid) * nc : nullptr;
-            env_step<SYS, R>(T, h, n, e, action, nrow, s_z + tid, E, state, rew, mse, info, nullptr, cvp, ns);
+#ifdef SCG_PROF
+            k3 = clock64();
+            env_step<SYS, R, R>(T, h, s_xg, n, e, action, nrow, s_z + tid, E, state, rew, mse, info, nullptr, cvp, ns, pt);
+            k4 = clock64();
+#else
+            env_step<SYS, R, R>(T, h, s_xg, n, e, action, nrow, s_z + tid, E, state, rew, mse, info, nullptr, cvp, ns);
+#endif
             e.ep_ret += (float)rew; e.ep_len += 1.f; e.ep_cv += (float)info.cviol;
+            int obs_step = e.ctrl_step - 1; bool obs_reset = false;
             if (info.done) {
-                if (info.truncated) {                                  // ppo.py:274-283
+                if (info.truncated) {                                  // ppo.py:274-283: critic on the terminal observation
                     trunc = 1;
-                    make_obs<SYS, R>(T, h, state, n, e.ctrl_step - 1, false, ns, SmemObsSink{s_tobs + tid, EP});
+                    make_obs<SYS, R, R>(T, h, s_xg, state, n, e.ctrl_step - 1, false, ns, TileObsSink<E>{s_tobs, tid});
                 }
                 ep_count += 1; ep_ret_sum += e.ep_ret; ep_len_sum += e.ep_len; ep_cv_sum += e.ep_cv;
                 e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
-                env_reset<SYS, R>(T, n, e, state);                     // dummy_vec_env.py:33-38
-                NoiseSrc<R> rs = reset_noise<R>(T, h, n, e.episode);
-                make_obs<SYS, R>(T, h, state, n, 0, true, rs, SmemObsSink{s_obs + tid, EP});
-            } else {
-                make_obs<SYS, R>(T, h, state, n, e.ctrl_step - 1, false, ns, SmemObsSink{s_obs + tid, EP});
+                env_reset<SYS, R>(T, h, n, e, state);                  // dummy_vec_env.py:33-38
+                ns = reset_noise<R>(T, h, n, e.episode);
+                obs_step = 0; obs_reset = true;
             }
+            make_obs<SYS, R, R>(T, h, s_xg, state, n, obs_step, obs_reset, ns, TileObsSink<E>{s_obs, tid});
+#ifdef SCG_PROF
+            k5 = clock64();
+#endif
             const size_t tn = tn0 + tid;
             if (A == 2) *reinterpret_cast<float2*>(P.out.d_act + tn * A) = make_float2(act[0], act[1 % A]);
             else if (A == 4) *reinterpret_cast<float4*>(P.out.d_act + tn * A) = make_float4(act[0], act[1 % A], act[2 % A], act[3 % A]);
@@ -457,19 +541,34 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
             if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
             if (!trunc) P.out.d_terminal_v[tn] = 0.f;
         }
+#ifdef SCG_PROF
+        long long k6 = clock64();
+#endif
         // (c) critic on the terminal observation of time-limit truncated envs (rare, CTA-uniform branch)
-        if (__syncthreads_or(trunc)) {
+        const int any_trunc = __syncthreads_or(trunc);
+#ifdef SCG_PROF
+        if (PROF_ON) {
+            long long k7 = clock64();
+            pacc[0] += k1 - k0; pacc[1] += k2 - k1; pacc[2] += k3 - k2; pacc[3] += k4 - k3; pacc[4] += k5 - k4; pacc[5] += k6 - k5; pacc[6] += k7 - k6;
+            for (int i = 0; i < 5; ++i) pacc[8 + i] += pt[i + 1] - pt[i];
+        }
+#endif
+        if (any_trunc) {
             mlp_forward<HID, E, NT, A>(s_blob, L, s_tobs, s_h1, s_h2, s_out, od, P.activation);
             if (live && trunc) P.out.d_terminal_v[tn0 + tid] = s_out[A * E + tid];
             __syncthreads();
         }
     }
+#ifdef SCG_PROF
+    if (PROF_ON && blockIdx.x == 0) for (int i = 0; i < 16; ++i) P.prof[i] = pacc[i];
+    long long g0 = clock64();
+#endif
     // ---- bootstrap value of the last observation, state write-back, GAE
     mlp_forward<HID, E, NT, A>(s_blob, L, s_obs, s_h1, s_h2, s_out, od, P.activation);
     if (live) {
         env_store<SYS, R>(T, n, e);
         for (int k = 0; k < od; ++k) {
-            const float v = s_obs[k * EP + tid];
+            const float v = s_obs[tile_idx<E>(k, tid)];
             T.st.cur_obs[(size_t)n * od + k] = v;
             if (P.out.d_last_obs) P.out.d_last_obs[(size_t)n * od + k] = v;
         }
@@ -479,18 +578,36 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
         if (P.out.d_ret && P.out.d_adv) {
             // compute_returns_and_advantages (ppo_utils.py:374-400): float32 ret / td recursions, float64 GAE accumulator
             float ret = lval, vnext = lval; double adv = 0.0;
-            for (int t = P.T - 1; t >= 0; --t) {
-                const size_t tn = (size_t)t * N + n;
-                const float r = P.out.d_rew[tn] + P.gamma * P.out.d_terminal_v[tn];
-                P.out.d_rew[tn] = r;                                   // rews += gamma * terminal_v, in place (ppo_utils.py:389)
-                const float m = P.out.d_mask[tn], v = P.out.d_v[tn];
-                ret = r + P.gamma * m * ret;
-                if (!P.use_gae) adv = (double)(ret - v);
-                else { const float td = r + P.gamma * m * vnext - v; adv = adv * P.lam_d * P.gamma_d * (double)m + (double)td; }
-                P.out.d_ret[tn] = ret; P.out.d_adv[tn] = (float)adv; vnext = v;
+            constexpr int CH = 8;            // loads of CH steps are issued together: the scan itself is a serial chain
+            for (int t1 = P.T; t1 > 0; t1 -= CH) {
+                const int cnt = t1 < CH ? t1 : CH;
+                float rr[CH], tv[CH], mm[CH], vv[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    if (j < cnt) {
+                        const size_t tn = (size_t)(t1 - 1 - j) * N + n;
+                        rr[j] = P.out.d_rew[tn]; tv[j] = P.out.d_terminal_v[tn]; mm[j] = P.out.d_mask[tn]; vv[j] = P.out.d_v[tn];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    if (j < cnt) {
+                        const size_t tn = (size_t)(t1 - 1 - j) * N + n;
+                        const float r = rr[j] + P.gamma * tv[j];
+                        P.out.d_rew[tn] = r;                               // rews += gamma * terminal_v, in place (ppo_utils.py:389)
+                        const float m = mm[j], v = vv[j];
+                        ret = r + P.gamma * m * ret;
+                        if (!P.use_gae) adv = (double)(ret - v);
+                        else { const float td = r + P.gamma * m * vnext - v; adv = adv * P.lam_d * P.gamma_d * (double)m + (double)td; }
+                        P.out.d_ret[tn] = ret; P.out.d_adv[tn] = (float)adv; vnext = v;
+                    }
+                }
             }
         }
     }
+#ifdef SCG_PROF
+    if (PROF_ON && blockIdx.x == 0) P.prof[15] = clock64() - g0;
+#endif
 }
 
 // Philox known-answer hook

@@ -43,13 +43,18 @@ def pack_policy(ac, device):
     if len(a) != 3 or len(c) != 3:
         raise NotImplementedError('the fused collector supports two hidden layers (hidden_dims=[h, h])')
     obs_dim, hid, act_dim = a[0].in_features, a[0].out_features, a[2].out_features
+    if obs_dim % 2 or hid % 4:
+        raise NotImplementedError('the fused collector needs an even observation width and hidden_dim % 4 == 0')
     L = policy_blob_layout(obs_dim, act_dim, hid)
     blob = torch.zeros(L['total'], dtype=torch.float32, device=device)
     with torch.no_grad():
         f = lambda t: t.detach().to(device=device, dtype=torch.float32)
-        blob[L['w1t']:L['b1']] = torch.cat([f(a[0].weight).t(), f(c[0].weight).t()], dim=1).reshape(-1)        # [obs][2H]
+        # pair-major layouts (csrc/scg_kernels.cuh): W1P [obs/2][2H][2], W2P [net][H/2][H][2]
+        w1 = torch.cat([f(a[0].weight).t(), f(c[0].weight).t()], dim=1)                                          # [obs][2H]
+        blob[L['w1t']:L['b1']] = w1.reshape(obs_dim // 2, 2, 2 * hid).permute(0, 2, 1).reshape(-1)
         blob[L['b1']:L['w2t']] = torch.cat([f(a[0].bias), f(c[0].bias)])
-        blob[L['w2t']:L['b2']] = torch.stack([f(a[1].weight).t(), f(c[1].weight).t()]).reshape(-1)             # [2][k][u]
+        w2 = torch.stack([f(a[1].weight).t(), f(c[1].weight).t()])                                               # [2][k][u]
+        blob[L['w2t']:L['b2']] = w2.reshape(2, hid // 2, 2, hid).permute(0, 1, 3, 2).reshape(-1)
         blob[L['b2']:L['w3']] = torch.cat([f(a[1].bias), f(c[1].bias)])
         blob[L['w3']:L['b3']] = torch.cat([f(a[2].weight), f(c[2].weight)], dim=0).reshape(-1)                 # [A+1][H]
         blob[L['b3']:L['b3'] + act_dim + 1] = torch.cat([f(a[2].bias), f(c[2].bias)])
