@@ -1,0 +1,54 @@
+'''In-tree build of the CUDA library (sm_100a) and of the CPU oracle used by the tests.
+
+    python -m safe_control_gym_b200.build [--force] [--prof]
+
+nvcc cross-compiles without a GPU.  The resulting libscg_b200.so sits next to this file (git-ignored, but shipped
+to the GPU box with the working tree).
+'''
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, 'csrc')
+SOURCES = ['scg_api.cu', 'scg_kernels.cuh', 'scg_device.cuh']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-shared', '-Xcompiler', '-fPIC']
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_cuda(force=False, prof=False, verbose=True):
+    out = os.path.join(HERE, 'libscg_b200_prof.so' if prof else 'libscg_b200.so')
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(ROOT, 'include', 'scg.h')]
+    if not force and not _stale(out, deps):
+        return out
+    nvcc = os.environ.get('NVCC', 'nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + (['-DSCG_PROF'] if prof else []) + ['-I', os.path.join(ROOT, 'include'), '-o', out,
+                                                                     os.path.join(CSRC, 'scg_api.cu')]
+    if verbose:
+        print(' '.join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+    return out
+
+
+def build_oracle(force=False):
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as orc
+    return orc.build(force=force)
+
+
+def main(argv=None):
+    argv = sys.argv[1:] if argv is None else argv
+    build_cuda(force='--force' in argv, prof='--prof' in argv)
+    build_oracle(force='--force' in argv)
+
+
+if __name__ == '__main__':
+    main()

@@ -65,10 +65,9 @@ def all_gather_rollout(out, keys=('obs', 'act', 'rew', 'mask', 'v', 'logp', 'ter
     keys = [k for k in keys if k in out]
     widths = [out[k].shape[-1] for k in keys]
     packed = torch.cat([out[k] for k in keys], dim=-1).contiguous()            # [T][n][F]
-    gathered = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
-    dist.all_gather_into_tensor(gathered, packed)
     T, n, F = packed.shape
-    gathered = gathered.reshape(world * T, n, F)
+    gathered = torch.empty((world * T, n, F), dtype=packed.dtype, device=packed.device)    # rank-major concatenation
+    dist.all_gather_into_tensor(gathered, packed)
     res, o = {}, 0
     for k, w in zip(keys, widths):
         res[k] = gathered[..., o:o + w]

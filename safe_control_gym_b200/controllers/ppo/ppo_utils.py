@@ -115,7 +115,7 @@ class PPOAgent:
                 batch = {k: v[idx] for k, v in flat.items()}
                 policy_loss, entropy_loss, approx_kl = self.compute_policy_loss(batch)
                 # update only when there is no KL constraint or it is satisfied (ppo_utils.py:128)
-                if self.target_kl <= 0 or float(approx_kl) <= 1.5 * self.target_kl:
+                if self.target_kl <= 0 or float(approx_kl.detach()) <= 1.5 * self.target_kl:
                     self.actor_opt.zero_grad(set_to_none=True)
                     (policy_loss + self.entropy_coef * entropy_loss).backward()
                     self.actor_opt.step()

@@ -1,0 +1,114 @@
+'''Analytic invariants and cross-checks of the oracle's quadrotor physics (unpinned by PyBullet data, see oracle header).'''
+import numpy as np
+import pytest
+
+import helpers as H
+
+
+def _quad(quad_type, **kw):
+    base = dict(quad_type=quad_type, ctrl_freq=50, pyb_freq=1000, task='stabilization', randomized_init=False,
+                task_info={'stabilization_goal': [0, 1] if quad_type == 2 else [0, 0, 1], 'stabilization_goal_tolerance': 0.0},
+                done_on_out_of_bound=False, cost='rl_reward')
+    base.update(kw)
+    return H.make_env('quadrotor', **base)
+
+
+@pytest.mark.parametrize('qt', [2, 3])
+def test_hover_is_an_equilibrium(qt):
+    '''thrust = M g  =>  zero acceleration.'''
+    env = _quad(qt)
+    nx, nu = env.state_dim, env.action_dim
+    o = H.make_oracle(env, 1, auto_reset=False)
+    s0 = np.zeros(nx); s0[2 if qt == 2 else 4] = 1.0
+    o.set_env_state(0, s0)
+    hover = np.full((1, nu), 0.027 * 9.8 / nu)
+    for _ in range(100):
+        out = o.step(hover)
+    # cmd2pwm -> rpm -> kf rpm^2 round-trips the thrust to ~1e-16 relative; the residual acceleration integrates to < 1e-12
+    np.testing.assert_allclose(out['state'][0], s0, atol=1e-11)
+
+
+def test_free_fall_matches_symplectic_euler_closed_form():
+    '''Zero thrust is clipped to the minimum motor thrust; with M such that min thrust is negligible use the closed form
+    z_k = z0 - a dt^2 k(k+1)/2 of semi-implicit Euler with a = g - T_min/m.'''
+    env = _quad(2)
+    o = H.make_oracle(env, 1, auto_reset=False)
+    o.set_env_state(0, np.array([0, 0, 1.0, 0, 0, 0.0]))
+    out = o.step(np.zeros((1, 2)))
+    tmin = 2 * float(np.float32(env.physical_action_bounds[0][0]))
+    # thrust after the pwm round trip equals the clipped command up to rounding
+    a = 9.8 - tmin / 0.027
+    k, dt = 20, 1e-3
+    np.testing.assert_allclose(out['state'][0][2], 1.0 - a * dt * dt * k * (k + 1) / 2, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(out['state'][0][3], -a * dt * k, rtol=0, atol=1e-12)
+
+
+def test_planar_3d_run_equals_2d_run():
+    '''A 3D quadrotor started in the x-z plane with f = [F0, F1, F1, F0] must reproduce the 2D env (quadrotor_utils.py:39).'''
+    e2, e3 = _quad(2), _quad(3)
+    o2, o3 = H.make_oracle(e2, 1, auto_reset=False), H.make_oracle(e3, 1, auto_reset=False)
+    s2 = np.array([0.1, 0.2, 1.0, -0.1, 0.15, 0.3])
+    s3 = np.zeros(12); s3[[0, 1, 4, 5, 7, 10]] = s2
+    o2.set_env_state(0, s2); o3.set_env_state(0, s3)
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        t = rng.uniform(0.1318, 0.1328, size=2)     # total thrust of motor pairs (0,3) and (1,2); pitch stays far from +-90 deg
+        r2 = o2.step(t.reshape(1, 2))
+        r3 = o3.step(np.array([[t[0] / 2, t[1] / 2, t[1] / 2, t[0] / 2]]))
+        np.testing.assert_allclose(r3['state'][0][[0, 1, 4, 5, 7, 10]], r2['state'][0], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(r3['state'][0][[2, 3, 6, 8, 9, 11]], 0, atol=1e-13)
+
+
+def test_substepped_integrator_converges_to_the_symbolic_ode():
+    '''As pyb_freq -> inf the oracle converges (first order) to an RK integration of the reference's symbolic 2D model
+    (quadrotor.py:506-509) evaluated with the same lever arm (0.028).'''
+    from scipy.integrate import solve_ivp
+    m, Iyy, g, arm = 0.027, 1.4e-5, 9.8, 0.028
+    T1, T2 = 0.14, 0.135
+
+    def f(t, x):
+        return [x[1], np.sin(x[4]) * (T1 + T2) / m, x[3], np.cos(x[4]) * (T1 + T2) / m - g, x[5], arm * (T2 - T1) / Iyy]
+    s0 = np.array([0, 0, 1.0, 0, 0.05, 0.0])
+    ref = solve_ivp(f, (0, 0.2), s0, rtol=1e-12, atol=1e-14).y[:, -1]
+    errs = []
+    for pyb in (500, 1000, 2000, 4000):
+        env = _quad(2, pyb_freq=pyb)
+        o = H.make_oracle(env, 1, auto_reset=False)
+        o.set_env_state(0, s0)
+        for _ in range(10):
+            out = o.step(np.array([[T1, T2]]))
+        errs.append(np.abs(out['state'][0] - ref).max())
+    ratios = np.asarray(errs[:-1]) / np.asarray(errs[1:])
+    assert np.all(ratios > 1.8) and np.all(ratios < 2.2), (errs, ratios)     # O(dt)
+
+
+def test_torque_free_rotation_conserves_angular_momentum():
+    '''3D, hover thrust, initial body rates: |J w| stays constant to O(dt) (gyroscopic term present).'''
+    env = _quad(3)
+    o = H.make_oracle(env, 1, auto_reset=False)
+    s = np.zeros(12); s[4] = 1.0; s[9:12] = [2.0, -1.0, 3.0]
+    o.set_env_state(0, s)
+    J = np.array([1.4e-5, 1.4e-5, 2.17e-5])
+    L0 = np.linalg.norm(J * s[9:12])
+    hover = np.full((1, 4), 0.027 * 9.8 / 4)
+    for _ in range(25):
+        out = o.step(hover)
+    L1 = np.linalg.norm(J * out['state'][0][9:12])
+    assert abs(L1 - L0) / L0 < 2e-3
+
+
+def test_cartpole_energy_drift_is_small_without_input():
+    env = H.make_env('cartpole', ctrl_freq=50, pyb_freq=1000, randomized_init=False, done_on_out_of_bound=False,
+                     task_info={'stabilization_goal': [0], 'stabilization_goal_tolerance': 0.0})
+    o = H.make_oracle(env, 1, auto_reset=False)
+    s = np.array([0.0, 0.3, 0.4, -0.2])
+    o.set_env_state(0, s)
+    M, m, l, g = 1.0, 0.1, 0.5, 9.8
+    Ic = m / 12 * (1.0 + 0.05**2)
+
+    def energy(x):
+        return 0.5 * (M + m) * x[1]**2 + m * l * np.cos(x[2]) * x[1] * x[3] + 0.5 * (Ic + m * l * l) * x[3]**2 + m * g * l * np.cos(x[2])
+    e0 = energy(s)
+    for _ in range(100):
+        out = o.step(np.zeros((1, 1)))
+    assert abs(energy(out['state'][0]) - e0) / abs(e0) < 5e-3
