@@ -161,9 +161,9 @@ def run_ours(args):
     # ---- end-to-end through the collector with HOST buffers: weights H2D, full PPOBuffer record D2H, every step
     rec_keys = ('obs', 'act', 'rew', 'mask', 'v', 'logp', 'terminal_v', 'ret', 'adv')
     host_params = [p.detach().cpu().pin_memory() for p in ac.parameters()]
-    host_out = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in rec_keys}
+    host_flat = torch.empty(out['_flat'].shape, dtype=torch.float32).pin_memory()      # the whole record is one flat buffer
     h2d_bytes = sum(p.numel() * 4 for p in host_params)
-    d2h_bytes = sum(v.numel() * 4 for v in host_out.values())
+    d2h_bytes = host_flat.numel() * 4
 
     def e2e_step():
         with torch.no_grad():
@@ -171,10 +171,9 @@ def run_ours(args):
                 p.copy_(hp, non_blocking=True)
         b_, d_ = pack_policy(ac, dev)
         o = eng.rollout(b_, d_, T_HORIZON, use_gae=True, want=want, out=out)
-        for k in rec_keys:
-            host_out[k].copy_(o[k], non_blocking=True)
+        host_flat.copy_(o['_flat'], non_blocking=True)
         torch.cuda.synchronize()
-        return float(host_out['rew'][0, 0, 0])
+        return float(host_flat[0])
 
     for _ in range(2):
         e2e_step()

@@ -57,21 +57,20 @@ class _Logger:
         pass
 
 
-def all_gather_rollout(out, keys=('obs', 'act', 'rew', 'mask', 'v', 'logp', 'terminal_v', 'ret', 'adv')):
-    '''One NCCL all-gather of the packed [T][n][F] rollout record; returns tensors laid out [G*T][n][.] (the update
-    samples transitions uniformly, so the rank-major order is as good as env-major).'''
+def all_gather_rollout(out):
+    '''THE collective of the path: one NCCL all-gather of the flat rollout record (engine.rollout allocates every PPOBuffer key
+    inside one buffer).  Returns per-key views shaped [G][T*n][width] -- zero copies on either side.'''
     import torch.distributed as dist
     world = dist.get_world_size()
-    keys = [k for k in keys if k in out]
-    widths = [out[k].shape[-1] for k in keys]
-    packed = torch.cat([out[k] for k in keys], dim=-1).contiguous()            # [T][n][F]
-    T, n, F = packed.shape
-    gathered = torch.empty((world * T, n, F), dtype=packed.dtype, device=packed.device)    # rank-major concatenation
-    dist.all_gather_into_tensor(gathered, packed)
+    flat = out['_flat']
+    gathered = torch.empty(world * flat.numel(), dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(gathered, flat)
+    gathered = gathered.view(world, flat.numel())
+    T, n = out['_TN']
     res, o = {}, 0
-    for k, w in zip(keys, widths):
-        res[k] = gathered[..., o:o + w]
-        o += w
+    for k, w in out['_layout']:
+        res[k] = gathered[:, o:o + T * n * w].view(world, T * n, w)
+        o += T * n * w
     return res
 
 
@@ -182,7 +181,7 @@ class PPO:
         self.obs = out['last_obs']
         self.env.record_rollout(out)
         self.total_steps += self.rollout_batch_size * self.rollout_steps
-        batch = all_gather_rollout(out) if self.world > 1 else out
+        batch = all_gather_rollout(out) if self.world > 1 else {k: v for k, v in out.items() if not k.startswith('_')}
         adv = batch['adv']
         rollouts = dict(batch)
         rollouts['adv'] = (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-6)          # ppo.py:300 (numpy std, ddof=0)

@@ -102,9 +102,12 @@ class PPOAgent:
         return 0.5 * (v_cur - batch['ret']).pow(2).mean()
 
     def update(self, rollouts, device=None, generator=None):
-        '''rollouts: dict of [T][N][.] device tensors.  Minibatches are index-gathered on the GPU.'''
-        flat = {k: v.reshape(-1, v.shape[-1]) for k, v in rollouts.items() if k in ('obs', 'act', 'logp', 'adv', 'ret', 'v')}
-        total = flat['obs'].shape[0]
+        '''rollouts: dict of device tensors, [T][N][w] (one rank) or [G][T*n][w] views of the all-gathered record.
+        Minibatches are index-gathered on the GPU (two-level index, so the strided gathered views are never copied).'''
+        flat = {k: v.reshape(v.shape[0], -1, v.shape[-1]) if v.dim() == 3 else v for k, v in rollouts.items()
+                if k in ('obs', 'act', 'logp', 'adv', 'ret', 'v')}
+        d0, d1 = flat['obs'].shape[0], flat['obs'].shape[1]
+        total = d0 * d1
         num_mini_batch = total // self.mini_batch_size
         assert num_mini_batch != 0, 'num_mini_batch is 0'
         sums = torch.zeros(4, device=flat['obs'].device)
@@ -112,7 +115,7 @@ class PPOAgent:
             perm = torch.randperm(total, device=flat['obs'].device, generator=generator)
             for i in range(num_mini_batch):
                 idx = perm[i * self.mini_batch_size:(i + 1) * self.mini_batch_size]
-                batch = {k: v[idx] for k, v in flat.items()}
+                batch = {k: v[idx // d1, idx % d1] for k, v in flat.items()}
                 policy_loss, entropy_loss, approx_kl = self.compute_policy_loss(batch)
                 # update only when there is no KL constraint or it is satisfied (ppo_utils.py:128)
                 if self.target_kl <= 0 or float(approx_kl.detach()) <= 1.5 * self.target_kl:

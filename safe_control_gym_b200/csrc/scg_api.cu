@@ -267,9 +267,8 @@ int scg_step(scg_env* e, const float* d_act, const double* d_act_f64, const scg_
 }
 
 extern "C++" {
-template <int SYS, typename R, int HID, int E>
+template <int SYS, typename R, int HID, int E, int NT>
 static int launch_rollout(scg_env* e, const RolloutParams& P, cudaStream_t s) {
-    constexpr int NT = 256;
     const RolloutSmem<HID, E> S(e->obs_dim, e->nu, e->L * e->nx * (int)(sizeof(R) / 4));
     const size_t smem = (size_t)S.total_floats * sizeof(float);
     auto kern = rollout_kernel<SYS, R, HID, E, NT>;
@@ -282,23 +281,32 @@ static int launch_rollout(scg_env* e, const RolloutParams& P, cudaStream_t s) {
     return SCG_OK;
 }
 
+// envs_per_block -> (E, threads): a CTA always runs 8 threads per env (4x4 register tiles at hidden 64), so smaller E means
+// smaller CTAs and MORE of them per SM: the serial env-step section of one CTA then overlaps the MLP phase of its neighbours.
 template <int SYS, typename R>
 static int dispatch_rollout(scg_env* e, const scg_rollout_args* a, const RolloutParams& P, cudaStream_t s) {
-    const int E = a->envs_per_block;
+    int E = a->envs_per_block;
 #ifdef SCG_PROF
-    if (a->hidden_dim == 64 && (E == 0 || E == 32)) return launch_rollout<SYS, R, 64, 32>(e, P, s);
-    return fail(e, SCG_EINVAL, "SCG_PROF build: only hidden 64 / E 32");
+    if (a->hidden_dim == 64 && (E == 0 || E == 32)) return launch_rollout<SYS, R, 64, 32, 256>(e, P, s);
+    if (a->hidden_dim == 64 && E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, s);
+    return fail(e, SCG_EINVAL, "SCG_PROF build: only hidden 64 / E 32 or 16");
 #else
     switch (a->hidden_dim) {
         case 32:
-            if (E == 0 || E == 32) return launch_rollout<SYS, R, 32, 32>(e, P, s);
+            if (E == 0) E = 16;
+            if (E == 32) return launch_rollout<SYS, R, 32, 32, 256>(e, P, s);
+            if (E == 16) return launch_rollout<SYS, R, 32, 16, 128>(e, P, s);
             break;
         case 64:
-            if (E == 0 || E == 32) return launch_rollout<SYS, R, 64, 32>(e, P, s);
-            if (E == 16) return launch_rollout<SYS, R, 64, 16>(e, P, s);
+            if (E == 0) E = 16;
+            if (E == 32) return launch_rollout<SYS, R, 64, 32, 256>(e, P, s);
+            if (E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, s);
+            if (E == 8) return launch_rollout<SYS, R, 64, 8, 64>(e, P, s);
             break;
         case 128:
-            if (E == 0 || E == 16) return launch_rollout<SYS, R, 128, 16>(e, P, s);
+            if (E == 0) E = 16;
+            if (E == 16) return launch_rollout<SYS, R, 128, 16, 256>(e, P, s);
+            if (E == 8) return launch_rollout<SYS, R, 128, 8, 128>(e, P, s);
             break;
         default: return fail(e, SCG_EINVAL, "scg_rollout: hidden_dim must be 32, 64 or 128");
     }
@@ -343,9 +351,9 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
 #ifdef SCG_PROF
     {
         long long hp[16]; cudaMemcpy(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost);
-        const char* nm[16] = {"eps+obs_write", "mlp", "sample", "env_step", "make_obs/reset", "stores", "barrier", "-", "  es:preproc", "  es:physics", "  es:reward+mse", "  es:done", "  es:constraints", "-", "-", "tail(mlp+gae)"};
+        const char* nm[8] = {"eps+obs_write", "mlp", "sample+pre+physics", "helpers/done(wait)", "finalize+reset+stores", "end barrier", "-", "tail(mlp+gae)"};
         fprintf(stderr, "[SCG_PROF] CTA0 cycles per step (T=%d):", a->T);
-        for (int i = 0; i < 16; ++i) if (nm[i][0] != '-') fprintf(stderr, " %s=%.0f", nm[i], i == 15 ? (double)hp[i] : (double)hp[i] / a->T);
+        for (int i = 0; i < 8; ++i) if (nm[i][0] != '-') fprintf(stderr, " %s=%.0f", nm[i], i == 7 ? (double)hp[i] : (double)hp[i] / a->T);
         fprintf(stderr, "\n");
         long long mp[8]; cudaMemcpyFromSymbol(mp, g_mlp_prof, sizeof(mp)); long long z8[8] = {0}; cudaMemcpyToSymbol(g_mlp_prof, z8, sizeof(z8));
         const char* mn[8] = {"L1", "L1epi", "bar1", "L2", "L2epi", "bar2", "L3", "bar3"};

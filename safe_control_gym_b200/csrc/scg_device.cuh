@@ -59,8 +59,11 @@ template <> struct Mth<float> {
 // normalization.py:8-10 (numpy floored modulo)
 template <typename R> __device__ __forceinline__ R normalize_angle(R x) {
     const R two_pi = (R)(2.0 * SCG_PI);
-    R y = Mth<R>::fmod_(x + (R)SCG_PI, two_pi);
-    if (y < (R)0) y += two_pi;
+    R y = x + (R)SCG_PI;
+    if (!(y >= (R)0 && y < two_pi)) {        // the floored modulo is the identity on [0, 2pi): skip fmod on the common path
+        y = Mth<R>::fmod_(y, two_pi);
+        if (y < (R)0) y += two_pi;
+    }
     return y - (R)SCG_PI;
 }
 
@@ -688,98 +691,115 @@ struct StepInfo {
 #define SCG_TICK(i) do { } while (0)
 #endif
 
-// One control step WITHOUT auto-reset and WITHOUT building the observation.  action[NU] is the raw controller action.
-// `zbuf` is this lane's column of a shared scratch [NX+NU][zstride] (doubles) used to index z = [state; input] by constraint column.
-// On return `state` holds env.state; `ns` is positioned for the observation noise (call make_obs next).
-template <int SYS, typename R, typename GT>
-__device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h, const GT* xg, int n, EnvRegs<SYS, R>& e, const R* action, const double* noise_row,
-                                         double* __restrict__ zbuf, int zstride, R* state, R& rew_out, R& mse_out, StepInfo& info,
-                                         double* cvals, float* cvals_f32, NoiseSrc<R>& ns, long long* prof_t = nullptr) {
-    constexpr int NX = SysDims<SYS>::NX, NU = SysDims<SYS>::NU;
+// ---------------------------------------------------------------------------------------------
+// One control step, split into phases so that the fused collector can spread them over warps:
+//   env_pre (action map, action / dynamics disturbances, clip)  ->  env_physics  ->  { env_reward_mse | env_done | env_constraints }
+//   ->  env_finalize (penalty, done_on_violation, time limit).   `env_step` chains them on one lane (gym-style kernels).
+// ---------------------------------------------------------------------------------------------
+template <int SYS, typename R> struct StepCtx {
+    R noisy[SysDims<SYS>::NU];     // current_noisy_physical_action
+    R clipped[SysDims<SYS>::NU];   // current_clipped_action
+    R fd[3];                       // dynamics disturbance force
+    bool has_dyn;
+};
+
+// quadrotor.py:722-747 / cartpole.py:479-502 + the dynamics disturbance draw (quadrotor.py:413-435, cartpole.py:540-551)
+template <int SYS, typename R>
+__device__ __forceinline__ void env_pre(const DevTables& T, const HotCfg<R>* h, int n, const EnvRegs<SYS, R>& e, const R* action, const double* noise_row,
+                                        StepCtx<SYS, R>& cx, NoiseSrc<R>& ns) {
+    constexpr int NU = SysDims<SYS>::NU;
     const int pyb_step = e.ctrl_step * h->steps;
-    SCG_TICK(0);
     ns.row = noise_row; ns.philox = h->philox != 0;
     ns.key.k0 = h->key0; ns.key.k1 = h->key1; ns.key.genv = h->genv0 + (uint32_t)n;
     ns.stream = SCG_STREAM_STEP; ns.idx = e.total_steps; ns.slot = 0;
-
-    R noisy[NU], clipped[NU];
 #pragma unroll
     for (int k = 0; k < NU; ++k) {
-        if (SYS == SCG_SYS_CARTPOLE) noisy[k] = h->normalized_action ? h->hover * action[k] : action[k];                      // cartpole.py:527-528
-        else noisy[k] = h->normalized_action ? ((R)1 + h->act_scale * action[k]) * h->hover : action[k];                       // quadrotor.py:772-773
+        if (SYS == SCG_SYS_CARTPOLE) cx.noisy[k] = h->normalized_action ? h->hover * action[k] : action[k];                   // cartpole.py:527-528
+        else cx.noisy[k] = h->normalized_action ? ((R)1 + h->act_scale * action[k]) * h->hover : action[k];                    // quadrotor.py:772-773
     }
     if (h->has_dist[SCG_MODE_ACTION])
-        apply_disturbances<R>(T.cfg, T.st.dist_off, T.N, n, SCG_MODE_ACTION, e.ctrl_step, pyb_step, noisy, NU, ns);
+        apply_disturbances<R>(T.cfg, T.st.dist_off, T.N, n, SCG_MODE_ACTION, e.ctrl_step, pyb_step, cx.noisy, NU, ns);
 #pragma unroll
     for (int k = 0; k < NU; ++k) {
-        R t = noisy[k];
+        R t = cx.noisy[k];
         t = t < h->act_low[k] ? h->act_low[k] : t;
         t = t > h->act_high[k] ? h->act_high[k] : t;
-        clipped[k] = t;
+        cx.clipped[k] = t;
     }
-    const bool has_dyn = h->has_dist[SCG_MODE_DYNAMICS] != 0;
-    R fd[3] = {(R)0, (R)0, (R)0};
-    if (has_dyn) {
+    cx.has_dyn = h->has_dist[SCG_MODE_DYNAMICS] != 0;
+    cx.fd[0] = cx.fd[1] = cx.fd[2] = (R)0;
+    if (cx.has_dyn) {
         const int ddim = (SYS == SCG_SYS_CARTPOLE) ? 2 : (SYS == SCG_SYS_QUAD1D) ? 1 : (SYS == SCG_SYS_QUAD2D) ? 2 : 3;
-        apply_disturbances<R>(T.cfg, T.st.dist_off, T.N, n, SCG_MODE_DYNAMICS, e.ctrl_step, pyb_step, fd, ddim, ns);
+        apply_disturbances<R>(T.cfg, T.st.dist_off, T.N, n, SCG_MODE_DYNAMICS, e.ctrl_step, pyb_step, cx.fd, ddim, ns);
     }
-    SCG_TICK(1);
+}
+
+template <int SYS, typename R>
+__device__ __forceinline__ void env_physics(const HotCfg<R>* h, EnvRegs<SYS, R>& e, const StepCtx<SYS, R>& cx, R* state) {
     if (SYS == SCG_SYS_CARTPOLE) {
-        Physics<SYS, R>::advance(h, e, clipped, fd, has_dyn);
+        Physics<SYS, R>::advance(h, e, cx.clipped, cx.fd, cx.has_dyn);
     } else {
-        R f[4]; quad_motor_forces<SYS, R>(h, clipped, f);
-        Physics<SYS, R>::advance(h, e, f, fd, has_dyn);
+        R f[4]; quad_motor_forces<SYS, R>(h, cx.clipped, f);
+        Physics<SYS, R>::advance(h, e, f, cx.fd, cx.has_dyn);
     }
     Physics<SYS, R>::state(e, state);
-    SCG_TICK(2);
+}
 
-    // ---- reward (quadrotor.py:819-862, cartpole.py:611-652) and info['mse'] (quadrotor.py:907-922, cartpole.py:685-695)
+// reward (quadrotor.py:819-862, cartpole.py:611-652) and info['mse'] (quadrotor.py:907-922, cartpole.py:685-695);
+// ctrl_step = the counter BEFORE this step's increment
+template <int SYS, typename R, typename GT>
+__device__ __forceinline__ void env_reward_mse(const HotCfg<R>* h, const GT* xg, const R* state, const R* noisy, const R* clipped, int ctrl_step,
+                                               R& rew_out, R& mse_out) {
+    constexpr int NX = SysDims<SYS>::NX, NU = SysDims<SYS>::NU;
     R rew, mse = (R)0;
-    {
-        const GT* g = goal_row<GT>(xg, h->L, h->task, NX, e.ctrl_step + 1);
-        R gk[NX];
+    const GT* g = goal_row<GT>(xg, h->L, h->task, NX, ctrl_step + 1);
+    R gk[NX];
 #pragma unroll
-        for (int k = 0; k < NX; ++k) gk[k] = (R)g[k];
-        if (h->cost == SCG_COST_RL_REWARD) {
-            R dist = (R)0;
-#pragma unroll
-            for (int k = 0; k < NX; ++k) {
-                R sk = state[k];
-                if (SYS == SCG_SYS_CARTPOLE && k == 2) sk = normalize_angle<R>(sk);                                  // cartpole.py:620
-                const R er = sk - gk[k];
-                dist += h->rew_state_w[k] * er * er;
-            }
-#pragma unroll
-            for (int k = 0; k < NU; ++k) {
-                const R ae = (SYS == SCG_SYS_CARTPOLE) ? noisy[k] : noisy[k] - h->u_goal[k];                          // cartpole.py:625 / quadrotor.py:829
-                dist += h->rew_act_w[k] * ae * ae;
-            }
-            rew = -dist;
-            if (h->rew_exponential) rew = Mth<R>::exp_(rew);
-        } else {
-            const int idx = (SYS == SCG_SYS_CARTPOLE) ? e.ctrl_step : e.ctrl_step + 1;                                // cartpole.py:648 / quadrotor.py:858
-            const GT* gq = goal_row<GT>(xg, h->L, h->task, NX, idx);
-            R l = (R)0;
-#pragma unroll
-            for (int k = 0; k < NX; ++k) { const R er = state[k] - (R)gq[k]; l += (R)0.5 * h->Qw[k] * er * er; }
-#pragma unroll
-            for (int k = 0; k < NU; ++k) { const R ae = clipped[k] - h->u_goal[k]; l += (R)0.5 * h->Rw[k] * ae * ae; }
-            rew = -l;
-        }
+    for (int k = 0; k < NX; ++k) gk[k] = (R)g[k];
+    if (h->cost == SCG_COST_RL_REWARD) {
+        R dist = (R)0;
 #pragma unroll
         for (int k = 0; k < NX; ++k) {
             R sk = state[k];
-            if (h->task == SCG_TASK_TRAJ_TRACKING) {
-                const bool is_angle = (SYS == SCG_SYS_CARTPOLE && k == 2) || (SYS == SCG_SYS_QUAD2D && k == 4) || (SYS == SCG_SYS_QUAD3D && k >= 6 && k < 9);
-                if (is_angle) sk = normalize_angle<R>(sk);
-            }
-            const R er = (sk - gk[k]) * h->mse_w[k];
-            mse += er * er;
+            if (SYS == SCG_SYS_CARTPOLE && k == 2) sk = normalize_angle<R>(sk);                                  // cartpole.py:620
+            const R er = sk - gk[k];
+            dist += h->rew_state_w[k] * er * er;
         }
+#pragma unroll
+        for (int k = 0; k < NU; ++k) {
+            const R ae = (SYS == SCG_SYS_CARTPOLE) ? noisy[k] : noisy[k] - h->u_goal[k];                          // cartpole.py:625 / quadrotor.py:829
+            dist += h->rew_act_w[k] * ae * ae;
+        }
+        rew = -dist;
+        if (h->rew_exponential) rew = Mth<R>::exp_(rew);
+    } else {
+        const int idx = (SYS == SCG_SYS_CARTPOLE) ? ctrl_step : ctrl_step + 1;                                    // cartpole.py:648 / quadrotor.py:858
+        const GT* gq = goal_row<GT>(xg, h->L, h->task, NX, idx);
+        R l = (R)0;
+#pragma unroll
+        for (int k = 0; k < NX; ++k) { const R er = state[k] - (R)gq[k]; l += (R)0.5 * h->Qw[k] * er * er; }
+#pragma unroll
+        for (int k = 0; k < NU; ++k) { const R ae = clipped[k] - h->u_goal[k]; l += (R)0.5 * h->Rw[k] * ae * ae; }
+        rew = -l;
     }
-    SCG_TICK(3);
-    // ---- done (quadrotor.py:864-894, cartpole.py:654-672)
-    int done = 0, goal_reached = 0, oob = 0;
+#pragma unroll
+    for (int k = 0; k < NX; ++k) {
+        R sk = state[k];
+        if (h->task == SCG_TASK_TRAJ_TRACKING) {
+            const bool is_angle = (SYS == SCG_SYS_CARTPOLE && k == 2) || (SYS == SCG_SYS_QUAD2D && k == 4) || (SYS == SCG_SYS_QUAD3D && k >= 6 && k < 9);
+            if (is_angle) sk = normalize_angle<R>(sk);
+        }
+        const R er = (sk - gk[k]) * h->mse_w[k];
+        mse += er * er;
+    }
+    rew_out = rew; mse_out = mse;
+}
+
+// done before the constraint / time-limit logic (quadrotor.py:864-894, cartpole.py:654-672)
+template <int SYS, typename R, typename GT>
+__device__ __forceinline__ int env_done(const HotCfg<R>* h, const GT* xg, const R* state, int& goal_reached, int& oob) {
+    constexpr int NX = SysDims<SYS>::NX;
+    int done = 0; goal_reached = 0; oob = 0;
     if (h->task == SCG_TASK_STABILIZATION) {
         R n2 = (R)0;
 #pragma unroll
@@ -800,58 +820,88 @@ __device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h,
         }
         done = oob;
     }
-    SCG_TICK(4);
-    // ---- after_step (benchmark_env.py:447-502)
-    e.ctrl_step += 1; e.total_steps += 1;
+    return done;
+}
+
+// constraint_violation (benchmark_env.py:468-485) for z = [state ; current_noisy_physical_action] already staged in `zbuf`
+// (constraints.py:166-171); `zbuf` is this env's column of a shared scratch [NX+NU][zstride] of doubles.
+__device__ __forceinline__ int env_constraints(const DevTables& T, const ConRow* __restrict__ rows, int n_con, int con_fast,
+                                               const double* __restrict__ zbuf, int zstride, double* cvals, float* cvals_f32) {
     int cviol = 0;
-    const int n_con = h->n_con;
-    if (n_con > 0) {
-        // z = [state ; current_noisy_physical_action] (constraints.py:166-171), indexed by column through the shared scratch
-#pragma unroll
-        for (int k = 0; k < NX; ++k) zbuf[k * zstride] = (double)state[k];
-#pragma unroll
-        for (int k = 0; k < NU; ++k) zbuf[(NX + k) * zstride] = (double)noisy[k];
-        if (h->con_fast) {
-            // violated <=> np.round(g, 8) > 0 (>= 0 if strict) <=> g*1e8 > 0.5 (>= -0.5): rint() rounds half to even
-            // (constraints.py:109,126-129); no stores inside this loop so the rows pipeline
+    if (con_fast) {
+        // violated <=> np.round(g, 8) > 0 (>= 0 if strict) <=> g*1e8 > 0.5 (>= -0.5): rint() rounds half to even
+        // (constraints.py:109,126-129); no stores inside this loop so the rows pipeline
 #pragma unroll 4
+        for (int r = 0; r < n_con; ++r) {
+            const ConRow row = rows[r];
+            double acc = __dmul_rn(row.val, zbuf[row.col * zstride]);
+            if (row.flags & 2) acc = fabs(acc);
+            const double t8 = __dsub_rn(acc, row.b) * 1e8;
+            cviol |= (row.flags & 1) ? (t8 >= -0.5) : (t8 > 0.5);
+        }
+        if (cvals || cvals_f32) {
             for (int r = 0; r < n_con; ++r) {
-                const ConRow row = h->rows[r];
+                const ConRow row = rows[r];
                 double acc = __dmul_rn(row.val, zbuf[row.col * zstride]);
                 if (row.flags & 2) acc = fabs(acc);
-                const double t8 = __dsub_rn(acc, row.b) * 1e8;
-                cviol |= (row.flags & 1) ? (t8 >= -0.5) : (t8 > 0.5);
-            }
-            if (cvals || cvals_f32) {
-                for (int r = 0; r < n_con; ++r) {
-                    const ConRow row = h->rows[r];
-                    double acc = __dmul_rn(row.val, zbuf[row.col * zstride]);
-                    if (row.flags & 2) acc = fabs(acc);
-                    const double g8 = rint(__dsub_rn(acc, row.b) * 1e8) / 1e8;   // np.round(g, 8)
-                    if (cvals) cvals[r] = g8;
-                    if (cvals_f32) cvals_f32[r] = (float)g8;
-                }
-            }
-        } else {
-            for (int r = 0; r < n_con; ++r) {
-                double acc = 0;
-                for (int p = T.con_ptr[r]; p < T.con_ptr[r + 1]; ++p) acc += T.con_val[p] * zbuf[T.con_col[p] * zstride];
-                if (T.con_kind[r] == SCG_CON_ABS) acc = fabs(acc);
-                const double gi = rint((acc - T.con_b[r]) * 1e8);
-                cviol |= T.con_strict[r] ? (gi >= 0.0) : (gi > 0.0);
-                if (cvals) cvals[r] = gi / 1e8;
-                if (cvals_f32) cvals_f32[r] = (float)(gi / 1e8);
+                const double g8 = rint(__dsub_rn(acc, row.b) * 1e8) / 1e8;   // np.round(g, 8)
+                if (cvals) cvals[r] = g8;
+                if (cvals_f32) cvals_f32[r] = (float)g8;
             }
         }
+    } else {
+        for (int r = 0; r < n_con; ++r) {
+            double acc = 0;
+            for (int p = T.con_ptr[r]; p < T.con_ptr[r + 1]; ++p) acc += T.con_val[p] * zbuf[T.con_col[p] * zstride];
+            if (T.con_kind[r] == SCG_CON_ABS) acc = fabs(acc);
+            const double gi = rint((acc - T.con_b[r]) * 1e8);
+            cviol |= T.con_strict[r] ? (gi >= 0.0) : (gi > 0.0);
+            if (cvals) cvals[r] = gi / 1e8;
+            if (cvals_f32) cvals_f32[r] = (float)(gi / 1e8);
+        }
+    }
+    return cviol;
+}
+
+// tail of after_step (benchmark_env.py:476-502); ctrl_step_after = the counter AFTER the increment
+template <typename R>
+__device__ __forceinline__ void env_finalize(const HotCfg<R>* h, int ctrl_step_after, int cviol, R& rew, int& done, int& truncated) {
+    if (h->n_con > 0) {
         if (cviol && h->done_on_violation) { done = 1; if (h->cost == SCG_COST_RL_REWARD && h->use_penalty) rew = (R)0; }
         if (h->cost == SCG_COST_RL_REWARD && h->use_penalty && cviol) {
             if (h->rew_exponential) rew = Mth<R>::exp_(Mth<R>::log_(rew) - h->penalty);
             else rew -= h->penalty;
         }
     }
-    SCG_TICK(5);
-    int truncated = 0;
-    if (e.ctrl_step >= h->ctrl_steps) { truncated = !done; done = 1; }
+    truncated = 0;
+    if (ctrl_step_after >= h->ctrl_steps) { truncated = !done; done = 1; }
+}
+
+// The whole step on one lane, WITHOUT auto-reset and WITHOUT building the observation (call make_obs next; `ns` is positioned
+// for the observation noise).  action[NU] is the raw controller action; on return `state` holds env.state.
+template <int SYS, typename R, typename GT>
+__device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h, const GT* xg, int n, EnvRegs<SYS, R>& e, const R* action, const double* noise_row,
+                                         double* __restrict__ zbuf, int zstride, R* state, R& rew_out, R& mse_out, StepInfo& info,
+                                         double* cvals, float* cvals_f32, NoiseSrc<R>& ns) {
+    constexpr int NX = SysDims<SYS>::NX, NU = SysDims<SYS>::NU;
+    StepCtx<SYS, R> cx;
+    env_pre<SYS, R>(T, h, n, e, action, noise_row, cx, ns);
+    env_physics<SYS, R>(h, e, cx, state);
+    R rew, mse;
+    env_reward_mse<SYS, R, GT>(h, xg, state, cx.noisy, cx.clipped, e.ctrl_step, rew, mse);
+    int goal_reached, oob;
+    int done = env_done<SYS, R, GT>(h, xg, state, goal_reached, oob);
+    e.ctrl_step += 1; e.total_steps += 1;
+    int cviol = 0;
+    if (h->n_con > 0) {
+#pragma unroll
+        for (int k = 0; k < NX; ++k) zbuf[k * zstride] = (double)state[k];
+#pragma unroll
+        for (int k = 0; k < NU; ++k) zbuf[(NX + k) * zstride] = (double)cx.noisy[k];
+        cviol = env_constraints(T, h->rows, h->n_con, h->con_fast, zbuf, zstride, cvals, cvals_f32);
+    }
+    int truncated;
+    env_finalize<R>(h, e.ctrl_step, cviol, rew, done, truncated);
     rew_out = rew; mse_out = mse;
     info.done = done; info.truncated = truncated; info.cviol = cviol; info.out_of_bounds = oob; info.goal_reached = goal_reached; info.current_step = e.ctrl_step;
 }

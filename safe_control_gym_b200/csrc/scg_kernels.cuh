@@ -373,18 +373,34 @@ __device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const
     MLP_TICK(7);
 }
 
+// named barriers (ids 1, 2) between the owner warp and the helper warps of the env-step section
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+#ifdef SCG_PROF
+#define PROF_T(v) long long v = clock64()
+#else
+#define PROF_T(v) do { } while (0)
+#endif
+
 template <int SYS, typename R, int HID, int E, int NT>
 __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams P) {
     constexpr int NX = SysDims<SYS>::NX, A = SysDims<SYS>::NU;
+    constexpr int NZ = NX + 2 * A;             // z scratch rows: state, noisy action, clipped action
+    // With >= 4 warps the env-step section is split: warp 0 = owners (sampling, action map, physics, done, finalize, reset),
+    // warp 1 = constraints, warp 2 = reward + mse, warp 3 = next observation.  Smaller CTAs keep everything on the owner lanes.
+    constexpr bool SPLIT = (NT >= 128) && (E <= 32);
     static_assert(NT / E >= A + 1, "layer 3 needs A+1 lane groups");
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ HotCfg<R> s_hot;
-    __shared__ double s_z[(NX + A) * E];
+    __shared__ double s_z[NZ * E];
     __shared__ float s_eps[A * E];
     __shared__ uint32_t s_tsteps0[E];
+    __shared__ int s_cstep[E];                 // ctrl_step BEFORE the increment of the step being processed
+    __shared__ int s_cviol[E];
+    __shared__ R s_rew[E], s_mse[E];
 
-    const scg_config* c = T.cfg;
     const int od = T.obs_dim, N = T.N, nc = T.n_con;
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * E;
@@ -412,6 +428,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
     const bool owner = tid < E;
     const int n = n0 + tid;
     const bool live = owner && n < N;
+    const int warp = tid >> 5, lane = tid & 31;
     EnvRegs<SYS, R> e;
     if (live) env_load<SYS, R>(T, n, e);
     if (owner) s_tsteps0[tid] = live ? e.total_steps : 0u;
@@ -428,19 +445,17 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
     for (int k = 0; k < A; ++k) { lsd[k] = s_blob[L.logstd + k]; sd[k] = expf(lsd[k]); inv2var[k] = 1.0f / (2.f * sd[k] * sd[k]); }
     const float log_sqrt_2pi = 0.91893853320467267f;
     const bool philox_eps = (P.eps == nullptr);
+    const bool obs_noise = h->has_dist[SCG_MODE_OBSERVATION] != 0;
     // obs write-out: element i = tid + j*NT of the [E][od] record maps to (env i / od, dim i % od); advance incrementally
     const int ow_k = tid % od, ow_e = tid / od, ow_dk = NT % od, ow_de = NT / od;
-
 #ifdef SCG_PROF
-    long long pacc[16]; for (int i = 0; i < 16; ++i) pacc[i] = 0;
-    long long pt[8];
+    long long pacc[8]; for (int i = 0; i < 8; ++i) pacc[i] = 0;
 #define PROF_ON (P.prof != nullptr && tid == 0)
 #endif
+
     for (int t = 0; t < P.T; ++t) {
         const size_t tn0 = (size_t)t * N + n0;
-#ifdef SCG_PROF
-        long long k0 = clock64();
-#endif
+        PROF_T(k0);
         // standard-normal draws of this step: table mode -> owner lanes issue the loads now (latency hidden by the MLP);
         // Philox mode -> the LAST lane group (idle during layer 3) generates them into shared memory, off the owners' critical path
         float z[A];
@@ -455,11 +470,10 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
             } else if (tid >= NT - E) {
                 const int ee = tid - (NT - E);
                 if (n0 + ee < N) {
-                    RngKey pk; pk.k0 = h->key0; pk.k1 = h->key1; pk.genv = h->genv0 + (uint32_t)(n0 + ee);
                     const uint32_t idx = s_tsteps0[ee] + (uint32_t)t;     // == that env's total_steps
 #pragma unroll
                     for (int k = 0; k < A; k += 2) {                      // one Philox block serves two action dims
-                        uint32_t x[4]; philox4x32_10((uint32_t)(k >> 1), idx, pk.genv, SCG_STREAM_POLICY, pk.k0, pk.k1, x);
+                        uint32_t x[4]; philox4x32_10((uint32_t)(k >> 1), idx, h->genv0 + (uint32_t)(n0 + ee), SCG_STREAM_POLICY, h->key0, h->key1, x);
                         s_eps[k * E + ee] = normal_from_words<float>(x[0], x[1]);
                         if (k + 1 < A) s_eps[(k + 1) * E + ee] = normal_from_words<float>(x[2], x[3]);
                     }
@@ -477,81 +491,123 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
                 if (k >= od) { k -= od; ee += 1; }
             }
         }
-#ifdef SCG_PROF
-        long long k1 = clock64();
-#endif
+        PROF_T(k1);
         mlp_forward<HID, E, NT, A>(s_blob, L, s_obs, s_h1, s_h2, s_out, od, P.activation);
-#ifdef SCG_PROF
-        long long k2 = clock64(), k3 = k2, k4 = k2, k5 = k2;
-#endif
+        PROF_T(k2);
 
-        // (b) owner lanes: sample, step the env, emit the record
+        // (b) env step.  Owner lanes: sample, action map, physics; then reward / constraints / next observation run on helper
+        // warps (SPLIT) while the owners evaluate termination; owners finalize, emit the record and auto-reset.
         int trunc = 0;
-        if (live) {
-            float act[A], logp = 0.f;
+        if (warp == 0) {
+            float act[A], logp = 0.f, val = 0.f;
+            R state[NX], rew = (R)0, mse = (R)0;
+            StepCtx<SYS, R> cx; NoiseSrc<R> ns; StepInfo info;
+            int done = 0, goal_reached = 0, oob = 0, cviol = 0, truncated = 0;
+            if (live) {
 #pragma unroll
-            for (int k = 0; k < A; ++k) {
-                const float zk = (philox_eps && !P.deterministic) ? s_eps[k * E + tid] : z[k];
-                const float mu = s_out[k * E + tid];
-                act[k] = fmaf(sd[k], zk, mu);                         // Normal.sample (ppo_utils.py:228)
-                const float d = act[k] - mu;
-                logp += -(d * d) * inv2var[k] - lsd[k] - log_sqrt_2pi;   // distributions.py:12-21
-            }
-            const float val = s_out[A * E + tid];
-            R action[A];
-#pragma unroll
-            for (int k = 0; k < A; ++k) action[k] = (R)act[k];
-            const double* nrow = (!h->philox && T.noise_table && T.D > 0)
-                                     ? T.noise_table + ((size_t)((P.noise_cursor + t) % T.Tn) * N + n) * T.D : nullptr;
-            R state[NX], rew, mse; StepInfo info; NoiseSrc<R> ns;
-            float* cvp = P.out.d_cvals ? P.out.d_cvals + (tn0 + tid) * nc : nullptr;
-#ifdef SCG_PROF
-            k3 = clock64();
-            env_step<SYS, R, R>(T, h, s_xg, n, e, action, nrow, s_z + tid, E, state, rew, mse, info, nullptr, cvp, ns, pt);
-            k4 = clock64();
-#else
-            env_step<SYS, R, R>(T, h, s_xg, n, e, action, nrow, s_z + tid, E, state, rew, mse, info, nullptr, cvp, ns);
-#endif
-            e.ep_ret += (float)rew; e.ep_len += 1.f; e.ep_cv += (float)info.cviol;
-            int obs_step = e.ctrl_step - 1; bool obs_reset = false;
-            if (info.done) {
-                if (info.truncated) {                                  // ppo.py:274-283: critic on the terminal observation
-                    trunc = 1;
-                    make_obs<SYS, R, R>(T, h, s_xg, state, n, e.ctrl_step - 1, false, ns, TileObsSink<E>{s_tobs, tid});
+                for (int k = 0; k < A; ++k) {
+                    const float zk = (philox_eps && !P.deterministic) ? s_eps[k * E + tid] : z[k];
+                    const float mu = s_out[k * E + tid];
+                    act[k] = fmaf(sd[k], zk, mu);                         // Normal.sample (ppo_utils.py:228)
+                    const float d = act[k] - mu;
+                    logp += -(d * d) * inv2var[k] - lsd[k] - log_sqrt_2pi;   // distributions.py:12-21
                 }
-                ep_count += 1; ep_ret_sum += e.ep_ret; ep_len_sum += e.ep_len; ep_cv_sum += e.ep_cv;
-                e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
-                env_reset<SYS, R>(T, h, n, e, state);                  // dummy_vec_env.py:33-38
-                ns = reset_noise<R>(T, h, n, e.episode);
-                obs_step = 0; obs_reset = true;
+                val = s_out[A * E + tid];
+                R action[A];
+#pragma unroll
+                for (int k = 0; k < A; ++k) action[k] = (R)act[k];
+                const double* nrow = (!h->philox && T.noise_table && T.D > 0)
+                                         ? T.noise_table + ((size_t)((P.noise_cursor + t) % T.Tn) * N + n) * T.D : nullptr;
+                env_pre<SYS, R>(T, h, n, e, action, nrow, cx, ns);
+                env_physics<SYS, R>(h, e, cx, state);
+                // publish z = [state; noisy action; clipped action] and the step counter for the helpers / the constraint rows
+#pragma unroll
+                for (int k = 0; k < NX; ++k) s_z[k * E + tid] = (double)state[k];
+#pragma unroll
+                for (int k = 0; k < A; ++k) { s_z[(NX + k) * E + tid] = (double)cx.noisy[k]; s_z[(NX + A + k) * E + tid] = (double)cx.clipped[k]; }
+                s_cstep[tid] = e.ctrl_step;
             }
-            make_obs<SYS, R, R>(T, h, s_xg, state, n, obs_step, obs_reset, ns, TileObsSink<E>{s_obs, tid});
+            PROF_T(k3);
+            if (SPLIT) {
+                named_bar_arrive(1, 128);                                  // helpers may start
+                if (live) done = env_done<SYS, R, R>(h, s_xg, state, goal_reached, oob);
+                named_bar_sync(2, 128);                                    // helpers are done
+                if (live) { rew = s_rew[tid]; mse = s_mse[tid]; cviol = s_cviol[tid]; }
+            } else if (live) {
+                env_reward_mse<SYS, R, R>(h, s_xg, state, cx.noisy, cx.clipped, e.ctrl_step, rew, mse);
+                done = env_done<SYS, R, R>(h, s_xg, state, goal_reached, oob);
+                if (nc > 0) cviol = env_constraints(T, h->rows, nc, h->con_fast, s_z + tid, E, nullptr, P.out.d_cvals ? P.out.d_cvals + (tn0 + tid) * nc : nullptr);
+            }
+            PROF_T(k4);
+            if (live) {
+                const int step_before = e.ctrl_step;
+                e.ctrl_step += 1; e.total_steps += 1;
+                env_finalize<R>(h, e.ctrl_step, cviol, rew, done, truncated);
+                info.done = done; info.truncated = truncated; info.cviol = cviol;
+                e.ep_ret += (float)rew; e.ep_len += 1.f; e.ep_cv += (float)cviol;
+                const bool helper_obs = SPLIT && !obs_noise;               // the helper already wrote the continuing observation
+                if (done) {
+                    if (truncated) {                                       // ppo.py:274-283: critic on the terminal observation
+                        trunc = 1;
+                        if (helper_obs) { for (int k = 0; k < od; ++k) s_tobs[tile_idx<E>(k, tid)] = s_obs[tile_idx<E>(k, tid)]; }
+                        else make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_tobs, tid});
+                    }
+                    ep_count += 1; ep_ret_sum += e.ep_ret; ep_len_sum += e.ep_len; ep_cv_sum += e.ep_cv;
+                    e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
+                    env_reset<SYS, R>(T, h, n, e, state);                  // dummy_vec_env.py:33-38
+                    ns = reset_noise<R>(T, h, n, e.episode);
+                    make_obs<SYS, R, R>(T, h, s_xg, state, n, 0, true, ns, TileObsSink<E>{s_obs, tid});
+                } else if (!helper_obs) {
+                    make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_obs, tid});
+                }
+                const size_t tn = tn0 + tid;
+                if (A == 2) *reinterpret_cast<float2*>(P.out.d_act + tn * A) = make_float2(act[0], act[1 % A]);
+                else if (A == 4) *reinterpret_cast<float4*>(P.out.d_act + tn * A) = make_float4(act[0], act[1 % A], act[2 % A], act[3 % A]);
+                else P.out.d_act[tn * A] = act[0];
+                P.out.d_rew[tn] = (float)rew;
+                P.out.d_mask[tn] = done ? 0.f : 1.f;
+                P.out.d_v[tn] = val;
+                P.out.d_logp[tn] = logp;
+                if (P.out.d_cviol) P.out.d_cviol[tn] = (float)cviol;
+                if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
+                if (!trunc) P.out.d_terminal_v[tn] = 0.f;
+            }
 #ifdef SCG_PROF
-            k5 = clock64();
+            if (PROF_ON) { long long k5 = clock64(); pacc[0] += k1 - k0; pacc[1] += k2 - k1; pacc[2] += k3 - k2; pacc[3] += k4 - k3; pacc[4] += k5 - k4; }
 #endif
-            const size_t tn = tn0 + tid;
-            if (A == 2) *reinterpret_cast<float2*>(P.out.d_act + tn * A) = make_float2(act[0], act[1 % A]);
-            else if (A == 4) *reinterpret_cast<float4*>(P.out.d_act + tn * A) = make_float4(act[0], act[1 % A], act[2 % A], act[3 % A]);
-            else P.out.d_act[tn * A] = act[0];
-            P.out.d_rew[tn] = (float)rew;
-            P.out.d_mask[tn] = info.done ? 0.f : 1.f;
-            P.out.d_v[tn] = val;
-            P.out.d_logp[tn] = logp;
-            if (P.out.d_cviol) P.out.d_cviol[tn] = (float)info.cviol;
-            if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
-            if (!trunc) P.out.d_terminal_v[tn] = 0.f;
+        } else if (SPLIT && warp <= 3) {
+            named_bar_sync(1, 128);                                        // z, ctrl_step published by the owners
+            const int ee = lane;
+            const bool hl = ee < E && n0 + ee < N;
+            if (hl) {
+                if (warp == 1) {                                           // constraints (benchmark_env.py:472-485)
+                    int cv = 0;
+                    if (nc > 0) cv = env_constraints(T, h->rows, nc, h->con_fast, s_z + ee, E, nullptr, P.out.d_cvals ? P.out.d_cvals + (tn0 + ee) * nc : nullptr);
+                    s_cviol[ee] = cv;
+                } else {
+                    R st[NX];
+#pragma unroll
+                    for (int k = 0; k < NX; ++k) st[k] = (R)s_z[k * E + ee];
+                    if (warp == 2) {                                       // reward + info['mse']
+                        R ny[A], cl[A], rw, ms;
+#pragma unroll
+                        for (int k = 0; k < A; ++k) { ny[k] = (R)s_z[(NX + k) * E + ee]; cl[k] = (R)s_z[(NX + A + k) * E + ee]; }
+                        env_reward_mse<SYS, R, R>(h, s_xg, st, ny, cl, s_cstep[ee], rw, ms);
+                        s_rew[ee] = rw; s_mse[ee] = ms;
+                    } else if (!obs_noise) {                               // next observation of the continuing episode
+                        NoiseSrc<R> nn; nn.row = nullptr; nn.philox = false; nn.slot = 0; nn.stream = 0; nn.idx = 0; nn.key.k0 = nn.key.k1 = nn.key.genv = 0;
+                        make_obs<SYS, R, R>(T, h, s_xg, st, n0 + ee, s_cstep[ee], false, nn, TileObsSink<E>{s_obs, ee});
+                    }
+                }
+            }
+            named_bar_arrive(2, 128);
         }
-#ifdef SCG_PROF
-        long long k6 = clock64();
-#endif
-        // (c) critic on the terminal observation of time-limit truncated envs (rare, CTA-uniform branch)
+        PROF_T(k6);
+        // (c) critic on the terminal observation of time-limit truncated envs (rare, CTA-uniform branch).
+        //     s_tobs aliases s_h2: written after layer 3 consumed h2, read by layer 1 of this pass, overwritten by its layer 2.
         const int any_trunc = __syncthreads_or(trunc);
 #ifdef SCG_PROF
-        if (PROF_ON) {
-            long long k7 = clock64();
-            pacc[0] += k1 - k0; pacc[1] += k2 - k1; pacc[2] += k3 - k2; pacc[3] += k4 - k3; pacc[4] += k5 - k4; pacc[5] += k6 - k5; pacc[6] += k7 - k6;
-            for (int i = 0; i < 5; ++i) pacc[8 + i] += pt[i + 1] - pt[i];
-        }
+        if (PROF_ON) pacc[5] += clock64() - k6;
 #endif
         if (any_trunc) {
             mlp_forward<HID, E, NT, A>(s_blob, L, s_tobs, s_h1, s_h2, s_out, od, P.activation);
@@ -560,7 +616,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
         }
     }
 #ifdef SCG_PROF
-    if (PROF_ON && blockIdx.x == 0) for (int i = 0; i < 16; ++i) P.prof[i] = pacc[i];
+    if (PROF_ON && blockIdx.x == 0) for (int i = 0; i < 8; ++i) P.prof[i] = pacc[i];
     long long g0 = clock64();
 #endif
     // ---- bootstrap value of the last observation, state write-back, GAE
@@ -606,7 +662,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
         }
     }
 #ifdef SCG_PROF
-    if (PROF_ON && blockIdx.x == 0) P.prof[15] = clock64() - g0;
+    if (PROF_ON && blockIdx.x == 0) P.prof[7] = clock64() - g0;
 #endif
 }
 

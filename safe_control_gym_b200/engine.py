@@ -159,15 +159,16 @@ class EngineHandle:
         obs_dim, act_dim, hid = dims
         f32 = torch.float32
         if out is None:
-            out = {
-                'obs': torch.empty(T, N, obs_dim, dtype=f32, device=dev), 'act': torch.empty(T, N, act_dim, dtype=f32, device=dev),
-                'rew': torch.empty(T, N, 1, dtype=f32, device=dev), 'mask': torch.empty(T, N, 1, dtype=f32, device=dev),
-                'v': torch.empty(T, N, 1, dtype=f32, device=dev), 'logp': torch.empty(T, N, 1, dtype=f32, device=dev),
-                'terminal_v': torch.empty(T, N, 1, dtype=f32, device=dev),
-            }
+            # the PPOBuffer keys that feed the update live back to back in ONE flat allocation ([key][T][N][width]): multi-GPU
+            # training exchanges it with a single all-gather, no packing copy (controllers/ppo/ppo.py: all_gather_rollout)
+            widths = [('obs', obs_dim), ('act', act_dim), ('rew', 1), ('mask', 1), ('v', 1), ('logp', 1), ('terminal_v', 1)]
             if 'ret' in want or 'adv' in want:
-                out['ret'] = torch.empty(T, N, 1, dtype=f32, device=dev)
-                out['adv'] = torch.empty(T, N, 1, dtype=f32, device=dev)
+                widths += [('ret', 1), ('adv', 1)]
+            flat = torch.empty(sum(w for _, w in widths) * T * N, dtype=f32, device=dev)
+            out, o = {'_flat': flat, '_layout': [(k, w) for k, w in widths], '_TN': (T, N)}, 0
+            for k, w in widths:
+                out[k] = flat[o:o + T * N * w].view(T, N, w)
+                o += T * N * w
             if 'cviol' in want:
                 out['cviol'] = torch.empty(T, N, 1, dtype=f32, device=dev)
             if 'cvals' in want and self.n_con > 0:

@@ -22,11 +22,14 @@ def _worker(rank, world, port, q):
     from safe_control_gym_b200.controllers.ppo.ppo import all_gather_rollout
     T, n = 5, 3
     g = torch.Generator().manual_seed(100 + rank)
-    out = {'obs': torch.randn(T, n, 12, generator=g), 'act': torch.randn(T, n, 2, generator=g), 'rew': torch.randn(T, n, 1, generator=g),
-           'mask': torch.ones(T, n, 1), 'v': torch.randn(T, n, 1, generator=g), 'logp': torch.randn(T, n, 1, generator=g),
-           'terminal_v': torch.zeros(T, n, 1), 'ret': torch.randn(T, n, 1, generator=g), 'adv': torch.randn(T, n, 1, generator=g)}
+    layout = [('obs', 12), ('act', 2), ('rew', 1), ('mask', 1), ('v', 1), ('logp', 1), ('terminal_v', 1), ('ret', 1), ('adv', 1)]
+    flat = torch.randn(sum(w for _, w in layout) * T * n, generator=g)
+    out, o = {'_flat': flat, '_layout': layout, '_TN': (T, n)}, 0
+    for k, w in layout:
+        out[k] = flat[o:o + T * n * w].view(T, n, w)
+        o += T * n * w
     res = all_gather_rollout(out)
-    q.put((rank, {k: v.numpy().copy() for k, v in res.items()}, {k: v.numpy().copy() for k, v in out.items()}))
+    q.put((rank, {k: v.numpy().copy() for k, v in res.items()}, {k: out[k].numpy().copy() for k, _ in layout}))
     dist.destroy_process_group()
 
 
@@ -42,10 +45,10 @@ def test_all_gather_of_the_rollout_record_gloo_world2():
         p.join(timeout=60)
     (r0, g0, l0), (r1, g1, l1) = got
     for k in l0:
-        assert g0[k].shape[0] == 2 * l0[k].shape[0]
-        np.testing.assert_array_equal(g0[k], g1[k])                       # every rank holds the identical gathered record
-        np.testing.assert_array_equal(g0[k][:5], l0[k])                   # rank-major: shard of rank 0 first, then rank 1
-        np.testing.assert_array_equal(g0[k][5:], l1[k])
+        assert g0[k].shape[:2] == (2, 15)
+        np.testing.assert_array_equal(g0[k], g1[k])                              # every rank holds the identical gathered record
+        np.testing.assert_array_equal(g0[k][0], l0[k].reshape(15, -1))            # [rank][T*n][w]
+        np.testing.assert_array_equal(g0[k][1], l1[k].reshape(15, -1))
 
 
 def test_sharded_rollouts_equal_slices_of_the_unsharded_rollout():

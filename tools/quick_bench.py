@@ -31,13 +31,16 @@ def run(name, N, T, hid, prec, epb, iters=5, **kw):
 if __name__ == '__main__':
     T = 200
     for prec in ('f64', 'f32'):
-        for epb in (32, 16):
+        for epb in (32, 16, 8):
             run('quadrotor_2D_track', 4096, T, 64, prec, epb)
-    run('quadrotor_2D_track', 32768, T, 64, 'f64', 32)
-    run('quadrotor_2D_track', 32768, T, 64, 'f32', 32)
+    for epb in (32, 16, 8):
+        run('quadrotor_2D_track', 32768, T, 64, 'f64', epb)
     run('cartpole', 4096, T, 64, 'f64', 32)
-    run('cartpole', 4096, T, 64, 'f32', 32)
-    run('cartpole_stab', 4096, T, 64, 'f64', 32)
-    run('quadrotor_3D_track', 8192, T, 64, 'f64', 32)
-    run('quadrotor_3D_track', 8192, T, 64, 'f32', 32)
+    run('cartpole', 4096, T, 64, 'f64', 16)
+    run('cartpole', 4096, T, 64, 'f64', 8)
+    run('cartpole_stab', 4096, T, 64, 'f64', 16)
+    for epb in (32, 16, 8):
+        run('quadrotor_3D_track', 8192, T, 64, 'f64', epb)
+    run('quadrotor_3D_track', 8192, T, 64, 'f32', 16)
     run('quadrotor_2D_track', 4096, T, 128, 'f64', 16)
+    run('quadrotor_2D_track', 4096, T, 128, 'f64', 8)
