@@ -293,12 +293,12 @@ static int dispatch_rollout(scg_env* e, const scg_rollout_args* a, const Rollout
 #else
     switch (a->hidden_dim) {
         case 32:
-            if (E == 0) E = 16;
+            if (E == 0) E = e->cfg.num_envs >= 16384 ? 16 : 32;
             if (E == 32) return launch_rollout<SYS, R, 32, 32, 256>(e, P, s);
             if (E == 16) return launch_rollout<SYS, R, 32, 16, 128>(e, P, s);
             break;
         case 64:
-            if (E == 0) E = 16;
+            if (E == 0) E = e->cfg.num_envs >= 16384 ? 16 : 32;   // many CTAs per SM at large N, one 8-warp CTA per SM otherwise
             if (E == 32) return launch_rollout<SYS, R, 64, 32, 256>(e, P, s);
             if (E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, s);
             if (E == 8) return launch_rollout<SYS, R, 64, 8, 64>(e, P, s);

@@ -639,34 +639,54 @@ __device__ __forceinline__ void env_reset(const DevTables& T, const HotCfg<R>* h
             }
     }
     const int n_inertial = (SYS == SCG_SYS_CARTPOLE) ? 3 : 4;
-    // inertial properties, additive randomisation (benchmark_env.py:267)
+    // additive randomisation (benchmark_env.py:267).  Philox: slot j = words 2(j&1), 2(j&1)+1 of block j>>1 -- one block per TWO slots.
+    auto draw = [&](int kind, double a, double b, uint32_t w0, uint32_t w1) -> double {
+        if (kind == SCG_RAND_UNIFORM) return a + (b - a) * u01_d(w0);
+        if (kind == SCG_RAND_NORMAL) return a + b * normal_from_words<double>(w0, w1);
+        return 0.0;
+    };
+    double inr[SCG_MAX_INERTIAL];
 #pragma unroll
-    for (int j = 0; j < SCG_MAX_INERTIAL; ++j) {
-        double v = h->inertial_nominal[j];
-        if (h->randomized_inertial && j < n_inertial) {
-            if (row) v += row[slot + j];
-            else if (philox && h->inertial_kind[j] != SCG_RAND_NONE) {
-                uint32_t w0, w1; rng_words(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j), w0, w1);
-                if (h->inertial_kind[j] == SCG_RAND_UNIFORM) v += h->inertial_a[j] + (h->inertial_b[j] - h->inertial_a[j]) * u01_d(w0);
-                else v += h->inertial_a[j] + h->inertial_b[j] * normal_from_words<double>(w0, w1);
+    for (int j = 0; j < SCG_MAX_INERTIAL; ++j) inr[j] = h->inertial_nominal[j];
+    if (h->randomized_inertial) {
+        if (row) {
+#pragma unroll
+            for (int j = 0; j < SCG_MAX_INERTIAL; ++j) if (j < n_inertial) inr[j] += row[slot + j];
+        } else if (philox) {
+#pragma unroll
+            for (int j = 0; j < SCG_MAX_INERTIAL; ++j) {
+                if (j < n_inertial && h->inertial_kind[j] != SCG_RAND_NONE) {
+                    uint32_t w0, w1; rng_words(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j), w0, w1);
+                    inr[j] += draw(h->inertial_kind[j], h->inertial_a[j], h->inertial_b[j], w0, w1);
+                }
             }
         }
-        e.inertial[j] = (R)v;
     }
+#pragma unroll
+    for (int j = 0; j < SCG_MAX_INERTIAL; ++j) e.inertial[j] = (R)inr[j];
     slot += SCG_MAX_INERTIAL;
     R init[NX];
+    if (h->randomized_init && !row && philox && (slot & 1) == 0) {
+        // common case: consecutive slot pairs share a Philox block (NX is even)
 #pragma unroll
-    for (int j = 0; j < NX; ++j) {
-        double v = h->init_nominal[j];
-        if (h->randomized_init) {
-            if (row) v += row[slot + j];
-            else if (philox && h->init_kind[j] != SCG_RAND_NONE) {
-                uint32_t w0, w1; rng_words(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j), w0, w1);
-                if (h->init_kind[j] == SCG_RAND_UNIFORM) v += h->init_a[j] + (h->init_b[j] - h->init_a[j]) * u01_d(w0);
-                else v += h->init_a[j] + h->init_b[j] * normal_from_words<double>(w0, w1);
-            }
+        for (int j = 0; j < NX; j += 2) {
+            uint32_t x[4]; philox4x32_10((uint32_t)((slot + j) >> 1), (uint32_t)k, key.genv, SCG_STREAM_EPISODE, key.k0, key.k1, x);
+            init[j] = (R)(h->init_nominal[j] + draw(h->init_kind[j], h->init_a[j], h->init_b[j], x[0], x[1]));
+            init[j + 1] = (R)(h->init_nominal[j + 1] + draw(h->init_kind[j + 1], h->init_a[j + 1], h->init_b[j + 1], x[2], x[3]));
         }
-        init[j] = (R)v;
+    } else {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+            double v = h->init_nominal[j];
+            if (h->randomized_init) {
+                if (row) v += row[slot + j];
+                else if (philox && h->init_kind[j] != SCG_RAND_NONE) {
+                    uint32_t w0, w1; rng_words(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j), w0, w1);
+                    v += draw(h->init_kind[j], h->init_a[j], h->init_b[j], w0, w1);
+                }
+            }
+            init[j] = (R)v;
+        }
     }
     e.episode = k + 1;
     Physics<SYS, R>::set_init(e, init);

@@ -86,6 +86,31 @@ __device__ __forceinline__ float tanh_fast(float x) {
     t = copysignf(t, x);
     return ax < 0.3f ? p : t;
 }
+// four tanh at once: 1/(e_i + 1) for four values from ONE reciprocal of their product (MUFU.RCP is the scarce pipe here:
+// 2 MUFU per tanh -> 1.25).  |x| is clamped to 10 so that the product of four (e^{2|x|} + 1) stays below 2^127.
+__device__ __forceinline__ void tanh_fast4(float& x0, float& x1, float& x2, float& x3) {
+    float x[4] = {x0, x1, x2, x3}, q[4], p[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float ax = fminf(fabsf(x[i]), 10.0f);
+        const float x2_ = x[i] * x[i];
+        float pp = fmaf(x2_, 0.021869488536155203f, -0.053968253968253971f);
+        pp = fmaf(x2_, pp, 0.13333333333333333f);
+        pp = fmaf(x2_, pp, -0.33333333333333333f);
+        p[i] = fmaf(x2_ * x[i], pp, x[i]);
+        q[i] = exp2f(ax * 2.8853900817779268f) + 1.0f;
+    }
+    const float q01 = q[0] * q[1], q23 = q[2] * q[3];
+    const float r = __fdividef(1.0f, q01 * q23);           // 1 / (q0 q1 q2 q3)
+    const float r01 = r * q23, r23 = r * q01;              // 1/(q0 q1), 1/(q2 q3)
+    const float inv[4] = {r01 * q[1], r01 * q[0], r23 * q[3], r23 * q[2]};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float t = copysignf(fmaf(-2.0f, inv[i], 1.0f), x[i]);
+        x[i] = fabsf(x[i]) < 0.3f ? p[i] : t;
+    }
+    x0 = x[0]; x1 = x[1]; x2 = x[2]; x3 = x[3];
+}
 template <int ACT> __device__ __forceinline__ float hidden_act(float x) {
     if (ACT == SCG_ACT_TANH) return tanh_fast(x);
     if (ACT == SCG_ACT_RELU) return fmaxf(x, 0.0f);
@@ -95,9 +120,7 @@ template <int ACT> __device__ __forceinline__ float hidden_act(float x) {
 template <int TU> __device__ __forceinline__ void apply_hidden_act(float (&acc)[4][TU], int act) {
     if (act == SCG_ACT_TANH) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < TU; ++j) acc[i][j] = tanh_fast(acc[i][j]);
+        for (int j = 0; j < TU; ++j) tanh_fast4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
     } else if (act == SCG_ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -289,21 +312,35 @@ __device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const
     long long mt = clock64();
 #endif
     float2 acc[4][TU];   // (even-k, odd-k) partial sums of env i x unit j
-    // one input pair: 4 envs x (k, k+1) activations, TU units x (k, k+1) weights -> 4*TU packed FMAs (FFMA2)
-    auto pair_step = [&](const float* __restrict__ a_chunk, const float* __restrict__ w_chunk) {
-        const float4 a01 = *reinterpret_cast<const float4*>(a_chunk);                 // envs 0,1 of the group
-        const float4 a23 = *reinterpret_cast<const float4*>(a_chunk + EG * 4);        // envs 2,3 (the other half)
-        const float2 av[4] = {make_float2(a01.x, a01.y), make_float2(a01.z, a01.w), make_float2(a23.x, a23.y), make_float2(a23.z, a23.w)};
-        float2 wv[TU];
+    // operands of one input pair: 4 envs x (k, k+1) activations, TU units x (k, k+1) weights
+    struct Ops { float4 a01, a23; float4 w[TU / 2]; };
+    auto load_ops = [&](Ops& o, const float* __restrict__ a_chunk, const float* __restrict__ w_chunk) {
+        o.a01 = *reinterpret_cast<const float4*>(a_chunk);                 // envs 0,1 of the group
+        o.a23 = *reinterpret_cast<const float4*>(a_chunk + EG * 4);        // envs 2,3 (the other half)
 #pragma unroll
-        for (int j = 0; j < TU; j += 2) {
-            const float4 w = *reinterpret_cast<const float4*>(w_chunk + 2 * j);
-            wv[j] = make_float2(w.x, w.y); wv[j + 1] = make_float2(w.z, w.w);
+        for (int j = 0; j < TU / 2; ++j) o.w[j] = *reinterpret_cast<const float4*>(w_chunk + 4 * j);
+    };
+    auto fma_ops = [&](const Ops& o) {                                     // 4*TU packed FMAs (FFMA2)
+        const float2 av[4] = {make_float2(o.a01.x, o.a01.y), make_float2(o.a01.z, o.a01.w), make_float2(o.a23.x, o.a23.y), make_float2(o.a23.z, o.a23.w)};
+#pragma unroll
+        for (int j = 0; j < TU / 2; ++j) {
+            const float2 w0 = make_float2(o.w[j].x, o.w[j].y), w1 = make_float2(o.w[j].z, o.w[j].w);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { acc[i][2 * j] = __ffma2_rn(av[i], w0, acc[i][2 * j]); acc[i][2 * j + 1] = __ffma2_rn(av[i], w1, acc[i][2 * j + 1]); }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < TU; ++j) acc[i][j] = __ffma2_rn(av[i], wv[j], acc[i][j]);
+    };
+    // two operand sets ping-pong so that the shared-memory latency of pair kp+1 hides behind the FMAs of pair kp
+    auto gemm = [&](const float* __restrict__ a, int a_stride, const float* __restrict__ w, int w_stride, int npair) {
+        Ops o0, o1;
+        load_ops(o0, a, w);
+#pragma unroll 2
+        for (int kp = 0; kp < npair; kp += 2) {
+            const bool has1 = kp + 1 < npair;
+            if (has1) load_ops(o1, a + (kp + 1) * a_stride, w + (kp + 1) * w_stride);
+            fma_ops(o0);
+            if (kp + 2 < npair) load_ops(o0, a + (kp + 2) * a_stride, w + (kp + 2) * w_stride);
+            if (has1) fma_ops(o1);
+        }
     };
     auto finish = [&](float* __restrict__ dst, int dst_unit0) {   // reduce pairs, activate, store pair-swizzled as the next layer's input
         float h[4][TU];
@@ -326,9 +363,7 @@ __device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const
         for (int j = 0; j < TU; ++j) { const float b = b1[j]; acc[0][j] = make_float2(b, 0.f); acc[1][j] = acc[0][j]; acc[2][j] = acc[0][j]; acc[3][j] = acc[0][j]; }
         const float* w = s_blob + L.w1t + u0 * 2;
         const float* a = s_in + eg * 4;
-        const int npair = obs_dim >> 1;
-#pragma unroll 2
-        for (int kp = 0; kp < npair; ++kp) pair_step(a + kp * (2 * EG * 4), w + kp * (2 * HID * 2));
+        gemm(a, 2 * EG * 4, w, 2 * HID * 2, obs_dim >> 1);
         MLP_TICK(0);
         finish(s_h1 + net * (HID / 2) * (2 * EG * 4), ul0);
         MLP_TICK(1);
@@ -342,8 +377,7 @@ __device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const
         for (int j = 0; j < TU; ++j) { const float b = b2[j]; acc[0][j] = make_float2(b, 0.f); acc[1][j] = acc[0][j]; acc[2][j] = acc[0][j]; acc[3][j] = acc[0][j]; }
         const float* w = s_blob + L.w2t + net * HID * HID + ul0 * 2;
         const float* a = s_h1 + net * (HID / 2) * (2 * EG * 4) + eg * 4;
-#pragma unroll 4
-        for (int kp = 0; kp < HID / 2; ++kp) pair_step(a + kp * (2 * EG * 4), w + kp * (HID * 2));
+        gemm(a, 2 * EG * 4, w, HID * 2, HID / 2);
         MLP_TICK(3);
         finish(s_h2 + net * (HID / 2) * (2 * EG * 4), ul0);
         MLP_TICK(4);
