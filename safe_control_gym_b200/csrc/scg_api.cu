@@ -335,8 +335,8 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
     P.policy = a->d_policy; P.eps = a->d_eps; P.noise_cursor = e->noise_cursor; P.out = *out; P.prof = nullptr;
 #ifdef SCG_PROF
     static long long* d_prof = nullptr;
-    if (!d_prof) cudaMalloc((void**)&d_prof, 16 * sizeof(long long));
-    cudaMemset(d_prof, 0, 16 * sizeof(long long));
+    if (!d_prof) cudaMalloc((void**)&d_prof, (16 + 2048) * sizeof(long long));
+    cudaMemset(d_prof, 0, (16 + 2048) * sizeof(long long));
     P.prof = d_prof;
 #endif
     cudaStream_t s = (cudaStream_t)stream;
@@ -355,11 +355,13 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
         fprintf(stderr, "[SCG_PROF] CTA0 cycles per step (T=%d):", a->T);
         for (int i = 0; i < 8; ++i) if (nm[i][0] != '-') fprintf(stderr, " %s=%.0f", nm[i], i == 7 ? (double)hp[i] : (double)hp[i] / a->T);
         fprintf(stderr, "\n");
-        long long mp[8]; cudaMemcpyFromSymbol(mp, g_mlp_prof, sizeof(mp)); long long z8[8] = {0}; cudaMemcpyToSymbol(g_mlp_prof, z8, sizeof(z8));
-        const char* mn[8] = {"L1", "L1epi", "bar1", "L2", "L2epi", "bar2", "L3", "bar3"};
-        fprintf(stderr, "[SCG_PROF] mlp_forward cycles per call (%d calls):", a->T + 1);
-        for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.0f", mn[i], (double)mp[i] / (a->T + 1));
-        fprintf(stderr, "\n");
+        {
+            std::vector<long long> ct(2048); cudaMemcpy(ct.data(), d_prof + 16, 2048 * sizeof(long long), cudaMemcpyDeviceToHost);
+            int G = (e->cfg.num_envs + 31) / 32; if (G > 1024) G = 1024;
+            long long mn = ct[0], mx = ct[0]; int imx = 0; double sum = 0;
+            for (int i = 0; i < G; ++i) { if (ct[i] < mn) mn = ct[i]; if (ct[i] > mx) { mx = ct[i]; imx = i; } sum += ct[i]; }
+            fprintf(stderr, "[SCG_PROF] per-CTA horizon cycles: min=%lld mean=%.0f max=%lld (cta %d, owner-lane-0 resets %lld vs cta0 %lld)\n", mn, sum / G, mx, imx, ct[1024 + imx], ct[1024]);
+        }
     }
 #endif
     e->launches += 1; e->noise_cursor += a->T;

@@ -616,36 +616,23 @@ __device__ __forceinline__ void make_obs(const DevTables& T, const HotCfg<R>* h,
     }
 }
 
-// reset() of one env (quadrotor.py:328-392, cartpole.py:266-352); the caller builds the observation with make_obs(at_reset)
+// Random draws of episode `k` of env `n` (a pure function of (n, k): host table row or Philox stream EPISODE), i.e. the inertial
+// properties and the initial state after the additive randomisation of benchmark_env.py:237-268 (quadrotor.py:346-372, cartpole.py:287-326).
+// Disturbance step offsets are NOT drawn here (see env_reset).
 template <int SYS, typename R>
-__device__ __forceinline__ void env_reset(const DevTables& T, const HotCfg<R>* h, int n, EnvRegs<SYS, R>& e, R* state) {
+__device__ __forceinline__ void reset_draw(const DevTables& T, const HotCfg<R>* h, int n, int k, double* inr /*[SCG_MAX_INERTIAL]*/, double* init /*[NX]*/) {
     constexpr int NX = SysDims<SYS>::NX;
-    const int k = e.episode;
     const bool philox = h->philox != 0;
     RngKey key; key.k0 = h->key0; key.k1 = h->key1; key.genv = h->genv0 + (uint32_t)n;
     const double* row = (!philox && T.ep_table) ? T.ep_table + ((size_t)(k % T.K) * T.N + n) * T.P : nullptr;
-    e.ctrl_step = 0;
-    int slot = 0;
-    if (h->n_off_draws > 0) {
-        // disturbance reset draws (benchmark_env.py:336-337, disturbances.py:102-106,148-151)
-        const scg_config* c = T.cfg;
-        for (int m = 0; m < 3; ++m)
-            for (int j = 0; j < c->n_dist[m]; ++j) {
-                const scg_disturbance* d = &c->dist[m][j];
-                if ((d->kind == SCG_DIST_IMPULSE || d->kind == SCG_DIST_STEP) && d->step_offset < 0) {
-                    int v = row ? (int)row[slot] : (philox ? rng_randint(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)slot, (uint32_t)h->ctrl_steps) : 0);
-                    T.st.dist_off[(size_t)(m * SCG_MAX_DIST + j) * T.N + n] = v; ++slot;
-                }
-            }
-    }
+    int slot = h->n_off_draws;
     const int n_inertial = (SYS == SCG_SYS_CARTPOLE) ? 3 : 4;
-    // additive randomisation (benchmark_env.py:267).  Philox: slot j = words 2(j&1), 2(j&1)+1 of block j>>1 -- one block per TWO slots.
+    // Philox: slot j = words 2(j&1), 2(j&1)+1 of block j>>1 -- one block per TWO slots.
     auto draw = [&](int kind, double a, double b, uint32_t w0, uint32_t w1) -> double {
         if (kind == SCG_RAND_UNIFORM) return a + (b - a) * u01_d(w0);
         if (kind == SCG_RAND_NORMAL) return a + b * normal_from_words<double>(w0, w1);
         return 0.0;
     };
-    double inr[SCG_MAX_INERTIAL];
 #pragma unroll
     for (int j = 0; j < SCG_MAX_INERTIAL; ++j) inr[j] = h->inertial_nominal[j];
     if (h->randomized_inertial) {
@@ -662,17 +649,14 @@ __device__ __forceinline__ void env_reset(const DevTables& T, const HotCfg<R>* h
             }
         }
     }
-#pragma unroll
-    for (int j = 0; j < SCG_MAX_INERTIAL; ++j) e.inertial[j] = (R)inr[j];
     slot += SCG_MAX_INERTIAL;
-    R init[NX];
     if (h->randomized_init && !row && philox && (slot & 1) == 0) {
         // common case: consecutive slot pairs share a Philox block (NX is even)
 #pragma unroll
         for (int j = 0; j < NX; j += 2) {
             uint32_t x[4]; philox4x32_10((uint32_t)((slot + j) >> 1), (uint32_t)k, key.genv, SCG_STREAM_EPISODE, key.k0, key.k1, x);
-            init[j] = (R)(h->init_nominal[j] + draw(h->init_kind[j], h->init_a[j], h->init_b[j], x[0], x[1]));
-            init[j + 1] = (R)(h->init_nominal[j + 1] + draw(h->init_kind[j + 1], h->init_a[j + 1], h->init_b[j + 1], x[2], x[3]));
+            init[j] = h->init_nominal[j] + draw(h->init_kind[j], h->init_a[j], h->init_b[j], x[0], x[1]);
+            init[j + 1] = h->init_nominal[j + 1] + draw(h->init_kind[j + 1], h->init_a[j + 1], h->init_b[j + 1], x[2], x[3]);
         }
     } else {
 #pragma unroll
@@ -685,11 +669,52 @@ __device__ __forceinline__ void env_reset(const DevTables& T, const HotCfg<R>* h
                     v += draw(h->init_kind[j], h->init_a[j], h->init_b[j], w0, w1);
                 }
             }
-            init[j] = (R)v;
+            init[j] = v;
         }
     }
+}
+
+// reset() of one env (quadrotor.py:328-392, cartpole.py:266-352); the caller builds the observation with make_obs(at_reset).
+// `cand` (nullable): pre-drawn values of THIS episode, [SCG_MAX_INERTIAL + NX] doubles with stride `cstride` (the fused collector's
+// helper warp draws them ahead of time, off the owners' critical path).
+template <int SYS, typename R>
+__device__ __forceinline__ void env_reset(const DevTables& T, const HotCfg<R>* h, int n, EnvRegs<SYS, R>& e, R* state,
+                                          const double* cand = nullptr, int cstride = 0) {
+    constexpr int NX = SysDims<SYS>::NX;
+    const int k = e.episode;
+    e.ctrl_step = 0;
+    if (h->n_off_draws > 0) {
+        // disturbance reset draws (benchmark_env.py:336-337, disturbances.py:102-106,148-151)
+        const scg_config* c = T.cfg;
+        const bool philox = h->philox != 0;
+        RngKey key; key.k0 = h->key0; key.k1 = h->key1; key.genv = h->genv0 + (uint32_t)n;
+        const double* row = (!philox && T.ep_table) ? T.ep_table + ((size_t)(k % T.K) * T.N + n) * T.P : nullptr;
+        int slot = 0;
+        for (int m = 0; m < 3; ++m)
+            for (int j = 0; j < c->n_dist[m]; ++j) {
+                const scg_disturbance* d = &c->dist[m][j];
+                if ((d->kind == SCG_DIST_IMPULSE || d->kind == SCG_DIST_STEP) && d->step_offset < 0) {
+                    int v = row ? (int)row[slot] : (philox ? rng_randint(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)slot, (uint32_t)h->ctrl_steps) : 0);
+                    T.st.dist_off[(size_t)(m * SCG_MAX_DIST + j) * T.N + n] = v; ++slot;
+                }
+            }
+    }
+    double inr[SCG_MAX_INERTIAL], init[NX];
+    if (cand) {
+#pragma unroll
+        for (int j = 0; j < SCG_MAX_INERTIAL; ++j) inr[j] = cand[j * cstride];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) init[j] = cand[(SCG_MAX_INERTIAL + j) * cstride];
+    } else {
+        reset_draw<SYS, R>(T, h, n, k, inr, init);
+    }
+#pragma unroll
+    for (int j = 0; j < SCG_MAX_INERTIAL; ++j) e.inertial[j] = (R)inr[j];
+    R initr[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) initr[j] = (R)init[j];
     e.episode = k + 1;
-    Physics<SYS, R>::set_init(e, init);
+    Physics<SYS, R>::set_init(e, initr);
     Physics<SYS, R>::state(e, state);
 }
 

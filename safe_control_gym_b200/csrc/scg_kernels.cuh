@@ -273,7 +273,7 @@ template <int HID, int E> struct RolloutSmem {
         BlobLayout L = blob_layout(obs_dim, act_dim, HID);
         blob = 0;
         obs = blob + L.total;
-        h1 = obs + obs_dim * E;
+        h1 = obs + 2 * obs_dim * E;          // two observation tiles (ping-pong): the decoupled critic still reads tile t while tile t+1 is built
         h2 = h1 + 2 * HID * E;
         tobs = h2;                       // aliases h2: see rollout_kernel (c)
         out = h2 + (2 * HID * E > obs_dim * E ? 2 * HID * E : obs_dim * E);
@@ -282,35 +282,31 @@ template <int HID, int E> struct RolloutSmem {
     }
 };
 
-// One fused actor+critic forward for the CTA's E envs.
-//   in  : s_in  pair-swizzled observation tile (tile_idx)
-//   out : s_out [A+1][E]       (A action means, then the value)
-// Layers 1 and 2 are register-tiled FP32 GEMMs: each thread owns a (4 envs x TU units) tile, weights and
-// activations stream from shared memory as 128-bit loads (weights broadcast across the env groups of a warp,
-// activations broadcast across its unit groups).
-#ifdef SCG_PROF
-__device__ long long g_mlp_prof[8];
-#define MLP_TICK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_mlp_prof[i] += clock64() - mt; mt = clock64(); } while (0)
-#else
-#define MLP_TICK(i) do { } while (0)
-#endif
+// named barriers: 1, 2 = owner warp <-> helper warps of the env-step section, 3 = the critic's thread group
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+template <int NTN, int BAR> __device__ __forceinline__ void group_sync() {
+    if (BAR == 0) __syncthreads(); else named_bar_sync(BAR, NTN);
+}
 
-template <int HID, int E, int NT, int A>
-__device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const BlobLayout L, const float* __restrict__ s_in, float* __restrict__ s_h1,
-                                         float* __restrict__ s_h2, float* __restrict__ s_out, int obs_dim, int act) {
+// Forward of ONE network (net 0 = actor with n_out = A outputs, net 1 = critic with 1 output) for the CTA's E envs by a group
+// of NTN threads (tl = index inside the group; BAR = 0: the group is the whole CTA or all groups run in lockstep -> __syncthreads,
+// otherwise the group's named barrier).
+//   s_in  : pair-swizzled observation tile (tile_idx)          s_h1n / s_h2n : this net's hidden tiles
+//   s_part: scratch [NTN/E][E] floats                           s_outn : [n_out][E]
+// Layers 1 and 2 are register-tiled FP32 GEMMs (4 envs x TU units per thread) out of shared memory with packed FFMA2;
+// layer 3 splits each dot product over the idle lane groups.
+template <int HID, int E, int NTN, int BAR>
+__device__ __forceinline__ void net_forward(int tl, int net, int n_out, int w3_row0, const float* __restrict__ s_blob, const BlobLayout L,
+                                            const float* __restrict__ s_in, float* __restrict__ s_h1n, float* __restrict__ s_h2n,
+                                            float* __restrict__ s_part, float* __restrict__ s_outn, int obs_dim, int act) {
     constexpr int EG = E / 4;              // env groups
-    constexpr int UG = NT / EG;            // unit groups
-    constexpr int TU = (2 * HID) / UG;     // units per thread
+    constexpr int UG = NTN / EG;           // unit groups
+    constexpr int TU = HID / UG;           // units per thread
     static_assert(TU == 2 || TU == 4, "unsupported tile");
-    static_assert(HID % TU == 0 && (2 * HID) % UG == 0, "tile must not straddle nets");
-    const int tid = threadIdx.x;
-    const int eg = tid % EG, ug = tid / EG;
-    const int u0 = ug * TU;
-    const int net = u0 / HID, ul0 = u0 % HID;
+    const int eg = tl % EG, ug = tl / EG;
+    const int ul0 = ug * TU;
 
-#ifdef SCG_PROF
-    long long mt = clock64();
-#endif
     float2 acc[4][TU];   // (even-k, odd-k) partial sums of env i x unit j
     // operands of one input pair: 4 envs x (k, k+1) activations, TU units x (k, k+1) weights
     struct Ops { float4 a01, a23; float4 w[TU / 2]; };
@@ -342,7 +338,11 @@ __device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const
             if (has1) fma_ops(o1);
         }
     };
-    auto finish = [&](float* __restrict__ dst, int dst_unit0) {   // reduce pairs, activate, store pair-swizzled as the next layer's input
+    auto init_acc = [&](const float* __restrict__ bias) {
+#pragma unroll
+        for (int j = 0; j < TU; ++j) { const float b = bias[j]; acc[0][j] = make_float2(b, 0.f); acc[1][j] = acc[0][j]; acc[2][j] = acc[0][j]; acc[3][j] = acc[0][j]; }
+    };
+    auto finish = [&](float* __restrict__ dst) {   // reduce pairs, activate, store pair-swizzled as the next layer's input
         float h[4][TU];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -351,65 +351,62 @@ __device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const
         apply_hidden_act<TU>(h, act);
 #pragma unroll
         for (int j = 0; j < TU; j += 2) {
-            float* d = dst + ((((dst_unit0 + j) >> 1) * 2) * EG + eg) * 4;
+            float* d = dst + ((((ul0 + j) >> 1) * 2) * EG + eg) * 4;
             *reinterpret_cast<float4*>(d) = make_float4(h[0][j], h[0][j + 1], h[1][j], h[1][j + 1]);
             *reinterpret_cast<float4*>(d + EG * 4) = make_float4(h[2][j], h[2][j + 1], h[3][j], h[3][j + 1]);
         }
     };
-    // ---- layer 1: [E x obs] . [obs x 2H]
+    // ---- layer 1: [E x obs] . [obs x H]      (W1P [kp][2H][2], this net's units start at net*H)
+    init_acc(s_blob + L.b1 + net * HID + ul0);
+    gemm(s_in + eg * 4, 2 * EG * 4, s_blob + L.w1t + (net * HID + ul0) * 2, 2 * HID * 2, obs_dim >> 1);
+    finish(s_h1n);
+    group_sync<NTN, BAR>();
+    // ---- layer 2: [E x H] . [H x H]          (W2P [net][kp][H][2])
+    init_acc(s_blob + L.b2 + net * HID + ul0);
+    gemm(s_h1n + eg * 4, 2 * EG * 4, s_blob + L.w2t + net * HID * HID + ul0 * 2, HID * 2, HID / 2);
+    finish(s_h2n);
+    group_sync<NTN, BAR>();
+    // ---- layer 3: n_out dot products per env, each split over KS lane groups, partial sums through shared memory
     {
-        const float* b1 = s_blob + L.b1 + u0;
-#pragma unroll
-        for (int j = 0; j < TU; ++j) { const float b = b1[j]; acc[0][j] = make_float2(b, 0.f); acc[1][j] = acc[0][j]; acc[2][j] = acc[0][j]; acc[3][j] = acc[0][j]; }
-        const float* w = s_blob + L.w1t + u0 * 2;
-        const float* a = s_in + eg * 4;
-        gemm(a, 2 * EG * 4, w, 2 * HID * 2, obs_dim >> 1);
-        MLP_TICK(0);
-        finish(s_h1 + net * (HID / 2) * (2 * EG * 4), ul0);
-        MLP_TICK(1);
-    }
-    __syncthreads();
-    MLP_TICK(2);
-    // ---- layer 2: per net [E x H] . [H x H]
-    {
-        const float* b2 = s_blob + L.b2 + u0;
-#pragma unroll
-        for (int j = 0; j < TU; ++j) { const float b = b2[j]; acc[0][j] = make_float2(b, 0.f); acc[1][j] = acc[0][j]; acc[2][j] = acc[0][j]; acc[3][j] = acc[0][j]; }
-        const float* w = s_blob + L.w2t + net * HID * HID + ul0 * 2;
-        const float* a = s_h1 + net * (HID / 2) * (2 * EG * 4) + eg * 4;
-        gemm(a, 2 * EG * 4, w, HID * 2, HID / 2);
-        MLP_TICK(3);
-        finish(s_h2 + net * (HID / 2) * (2 * EG * 4), ul0);
-        MLP_TICK(4);
-    }
-    __syncthreads();
-    MLP_TICK(5);
-    // ---- layer 3: A action means from the actor features, 1 value from the critic features
-    {
-        const int g = tid / E, e = tid % E;
-        if (g < A + 1) {
-            const float* w = s_blob + L.w3 + g * HID;
-            const float* hh = s_h2 + (g < A ? 0 : (HID / 2) * (2 * EG * 4)) + ((((e >> 1) & 1) * EG + (e >> 2)) << 2) + ((e & 1) << 1);
-            float2 s0 = make_float2(s_blob[L.b3 + g], 0.f), s1 = make_float2(0.f, 0.f);
+        constexpr int NG = NTN / E;                        // lane groups of E lanes
+        const int g = tl / E, e = tl % E;
+        const int ks_n = NG / n_out;                       // K-slices per output (>= 1)
+        const int o = g / ks_n, ks = g % ks_n;
+        if (o < n_out) {
+            const int kp0 = (HID / 2) * ks / ks_n, kp1 = (HID / 2) * (ks + 1) / ks_n;
+            const float* w = s_blob + L.w3 + (w3_row0 + o) * HID;
+            const float* hh = s_h2n + ((((e >> 1) & 1) * EG + (e >> 2)) << 2) + ((e & 1) << 1);
+            float2 s0 = make_float2(ks == 0 ? s_blob[L.b3 + w3_row0 + o] : 0.f, 0.f);
 #pragma unroll 4
-            for (int kp = 0; kp < HID / 2; kp += 2) {
-                const float4 wv = *reinterpret_cast<const float4*>(w + 2 * kp);
-                const float2 h0 = *reinterpret_cast<const float2*>(hh + kp * (2 * EG * 4));
-                const float2 h1 = *reinterpret_cast<const float2*>(hh + (kp + 1) * (2 * EG * 4));
-                s0 = __ffma2_rn(h0, make_float2(wv.x, wv.y), s0);
-                s1 = __ffma2_rn(h1, make_float2(wv.z, wv.w), s1);
+            for (int kp = kp0; kp < kp1; ++kp) {
+                const float2 wv = *reinterpret_cast<const float2*>(w + 2 * kp);
+                const float2 hv = *reinterpret_cast<const float2*>(hh + kp * (2 * EG * 4));
+                s0 = __ffma2_rn(hv, wv, s0);
             }
-            s_out[g * E + e] = (s0.x + s0.y) + (s1.x + s1.y);
+            s_part[g * E + e] = s0.x + s0.y;
+        }
+        group_sync<NTN, BAR>();
+        if (tl < n_out * E) {
+            const int oo = tl / E, ee = tl % E;
+            float v = 0.f;
+            for (int k = 0; k < ks_n; ++k) v += s_part[(oo * ks_n + k) * E + ee];
+            s_outn[oo * E + ee] = v;
         }
     }
-    MLP_TICK(6);
-    __syncthreads();
-    MLP_TICK(7);
+    group_sync<NTN, BAR>();
 }
 
-// named barriers (ids 1, 2) between the owner warp and the helper warps of the env-step section
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// Classic schedule: the lower half of the CTA computes the actor, the upper half the critic, in lockstep.
+//   out : s_out [A+1][E]  (A action means, then the value)
+template <int HID, int E, int NT, int A>
+__device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const BlobLayout L, const float* __restrict__ s_in, float* __restrict__ s_h1,
+                                         float* __restrict__ s_h2, float* __restrict__ s_part, float* __restrict__ s_out, int obs_dim, int act) {
+    constexpr int NTN = NT / 2;
+    constexpr int NETSZ = (HID / 2) * (2 * (E / 4) * 4);       // floats of one net's hidden tile
+    const int net = threadIdx.x / NTN, tl = threadIdx.x % NTN;
+    net_forward<HID, E, NTN, 0>(tl, net, net ? 1 : A, net ? A : 0, s_blob, L, s_in, s_h1 + net * NETSZ, s_h2 + net * NETSZ,
+                                s_part + net * NTN, s_out + (net ? A * E : 0), obs_dim, act);
+}
 
 #ifdef SCG_PROF
 #define PROF_T(v) long long v = clock64()
@@ -424,6 +421,14 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
     // With >= 4 warps the env-step section is split: warp 0 = owners (sampling, action map, physics, done, finalize, reset),
     // warp 1 = constraints, warp 2 = reward + mse, warp 3 = next observation.  Smaller CTAs keep everything on the owner lanes.
     constexpr bool SPLIT = (NT >= 128) && (E <= 32);
+    // Decoupled critic (8-warp CTAs): all warps compute the ACTOR (the only net on the critical path to the env step); the critic of
+    // the same observation then runs on warps 4-7 CONCURRENTLY with the env step of warps 0-3 and stores v[t] itself.
+#ifdef SCG_DECOUPLED_CRITIC   // measured on B200 (round 1): no faster than the lockstep schedule -> off by default
+    constexpr bool DECOUPLED = (NT == 256) && (HID / (NT / (E / 4)) >= 2);
+#else
+    constexpr bool DECOUPLED = false;
+#endif
+    constexpr int NETSZ = (HID / 2) * (2 * (E / 4) * 4);     // floats of one net's hidden tile
     static_assert(NT / E >= A + 1, "layer 3 needs A+1 lane groups");
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -434,6 +439,12 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
     __shared__ int s_cstep[E];                 // ctrl_step BEFORE the increment of the step being processed
     __shared__ int s_cviol[E];
     __shared__ R s_rew[E], s_mse[E];
+    __shared__ float s_part[2 * NT];
+    // reset candidates: the helper warp pre-draws the next two episodes of every env (slot = episode & 1)
+    constexpr int NC = SCG_MAX_INERTIAL + NX;
+    __shared__ double s_cand[2 * NC * E];
+    __shared__ int s_cand_ep[2 * E];           // episode index held by each candidate slot (-1 = empty)
+    __shared__ int s_epi[E];                   // next episode index of each env, published by its owner lane
 
     const int od = T.obs_dim, N = T.N, nc = T.n_con;
     const int tid = threadIdx.x;
@@ -459,13 +470,26 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
         tma_bulk_g2s(s_blob, P.policy, bytes, &s_bar);
     }
     // ---- meanwhile: owner lanes pull their env into registers, everyone fills the observation tile
-    const bool owner = tid < E;
-    const int n = n0 + tid;
-    const bool live = owner && n < N;
+    // roles: owner lanes sit in the LAST warp (the issue arbiter favours the highest warp id -- the env step is the critical
+    // path), helpers are the three warps below it, the decoupled critic is the lower half of the CTA
     const int warp = tid >> 5, lane = tid & 31;
+    int role = (NT / 32 - 1) - warp;                // 0 = owner warp, 1..3 = helper warps
+    int crit_tl = -1;                               // index inside the decoupled critic's thread group, or -1
+    if (DECOUPLED) {
+        // SM sub-partition = warp % 4.  The owner (warp 7) keeps sub-partition 3 free of GEMM warps: critic = warps 0,1,2,4,
+        // helpers = warp 5 (constraints), warp 6 (reward), warp 3 (next observation, the lightest; shares the owner's sub-partition)
+        const int cw = warp < 3 ? warp : (warp == 4 ? 3 : -1);
+        crit_tl = cw < 0 ? -1 : cw * 32 + lane;
+        role = warp == 7 ? 0 : warp == 5 ? 1 : warp == 6 ? 2 : warp == 3 ? 3 : 99;
+    }
+    const int ol = tid - (NT - 32);                 // owner lane index (env inside the CTA) when role == 0
+    const bool owner = ol >= 0 && ol < E;
+    const int n = n0 + ol;
+    const bool live = owner && n < N;
     EnvRegs<SYS, R> e;
     if (live) env_load<SYS, R>(T, n, e);
-    if (owner) s_tsteps0[tid] = live ? e.total_steps : 0u;
+    if (owner) { s_tsteps0[ol] = live ? e.total_steps : 0u; s_epi[ol] = live ? e.episode : 0; s_cand_ep[ol] = -1; s_cand_ep[E + ol] = -1; }
+    const bool use_cand = SPLIT && h->n_off_draws == 0;
     for (int i = tid; i < T.L * NX; i += NT) s_xg[i] = (R)T.x_goal[i];
     for (int i = tid; i < E * od; i += NT) {
         const int ee = i / od, k = i % od;
@@ -483,15 +507,20 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
     // obs write-out: element i = tid + j*NT of the [E][od] record maps to (env i / od, dim i % od); advance incrementally
     const int ow_k = tid % od, ow_e = tid / od, ow_dk = NT % od, ow_de = NT / od;
 #ifdef SCG_PROF
+    const long long cta_t0 = clock64();
     long long pacc[8]; for (int i = 0; i < 8; ++i) pacc[i] = 0;
-#define PROF_ON (P.prof != nullptr && tid == 0)
+#define PROF_ON (P.prof != nullptr && tid == NT - 32)
 #endif
 
+    int cur = 0;
+    const int OBS_TILE = od * E;
     for (int t = 0; t < P.T; ++t) {
         const size_t tn0 = (size_t)t * N + n0;
+        float* s_oc = s_obs + cur * OBS_TILE;            // observation of step t (policy input)
+        float* s_on = s_obs + (cur ^ 1) * OBS_TILE;      // observation of step t+1 (being built)
         PROF_T(k0);
         // standard-normal draws of this step: table mode -> owner lanes issue the loads now (latency hidden by the MLP);
-        // Philox mode -> the LAST lane group (idle during layer 3) generates them into shared memory, off the owners' critical path
+        // Philox mode -> the FIRST lane group generates them into shared memory, off the owners' critical path
         float z[A];
 #pragma unroll
         for (int k = 0; k < A; ++k) z[k] = 0.f;
@@ -499,10 +528,10 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
             if (!philox_eps) {
                 if (live) {
 #pragma unroll
-                    for (int k = 0; k < A; ++k) z[k] = __ldg(P.eps + (tn0 + tid) * A + k);
+                    for (int k = 0; k < A; ++k) z[k] = __ldg(P.eps + (tn0 + ol) * A + k);
                 }
-            } else if (tid >= NT - E) {
-                const int ee = tid - (NT - E);
+            } else if (tid < E) {
+                const int ee = tid;
                 if (n0 + ee < N) {
                     const uint32_t idx = s_tsteps0[ee] + (uint32_t)t;     // == that env's total_steps
 #pragma unroll
@@ -520,19 +549,20 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
             const int lim = (N - n0 < E ? N - n0 : E) * od;
             int k = ow_k, ee = ow_e;
             for (int i = tid; i < lim; i += NT) {
-                dst[i] = s_obs[tile_idx<E>(k, ee)];
+                dst[i] = s_oc[tile_idx<E>(k, ee)];
                 k += ow_dk; ee += ow_de;
                 if (k >= od) { k -= od; ee += 1; }
             }
         }
         PROF_T(k1);
-        mlp_forward<HID, E, NT, A>(s_blob, L, s_obs, s_h1, s_h2, s_out, od, P.activation);
+        if constexpr (DECOUPLED) net_forward<HID, E, NT, 0>(tid, 0, A, 0, s_blob, L, s_oc, s_h1, s_h2, s_part, s_out, od, P.activation);
+        else mlp_forward<HID, E, NT, A>(s_blob, L, s_oc, s_h1, s_h2, s_part, s_out, od, P.activation);
         PROF_T(k2);
 
         // (b) env step.  Owner lanes: sample, action map, physics; then reward / constraints / next observation run on helper
         // warps (SPLIT) while the owners evaluate termination; owners finalize, emit the record and auto-reset.
         int trunc = 0;
-        if (warp == 0) {
+        if (role == 0) {
             float act[A], logp = 0.f, val = 0.f;
             R state[NX], rew = (R)0, mse = (R)0;
             StepCtx<SYS, R> cx; NoiseSrc<R> ns; StepInfo info;
@@ -540,13 +570,13 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
             if (live) {
 #pragma unroll
                 for (int k = 0; k < A; ++k) {
-                    const float zk = (philox_eps && !P.deterministic) ? s_eps[k * E + tid] : z[k];
-                    const float mu = s_out[k * E + tid];
+                    const float zk = (philox_eps && !P.deterministic) ? s_eps[k * E + ol] : z[k];
+                    const float mu = s_out[k * E + ol];
                     act[k] = fmaf(sd[k], zk, mu);                         // Normal.sample (ppo_utils.py:228)
                     const float d = act[k] - mu;
                     logp += -(d * d) * inv2var[k] - lsd[k] - log_sqrt_2pi;   // distributions.py:12-21
                 }
-                val = s_out[A * E + tid];
+                if (!DECOUPLED) val = s_out[A * E + ol];
                 R action[A];
 #pragma unroll
                 for (int k = 0; k < A; ++k) action[k] = (R)act[k];
@@ -556,21 +586,21 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
                 env_physics<SYS, R>(h, e, cx, state);
                 // publish z = [state; noisy action; clipped action] and the step counter for the helpers / the constraint rows
 #pragma unroll
-                for (int k = 0; k < NX; ++k) s_z[k * E + tid] = (double)state[k];
+                for (int k = 0; k < NX; ++k) s_z[k * E + ol] = (double)state[k];
 #pragma unroll
-                for (int k = 0; k < A; ++k) { s_z[(NX + k) * E + tid] = (double)cx.noisy[k]; s_z[(NX + A + k) * E + tid] = (double)cx.clipped[k]; }
-                s_cstep[tid] = e.ctrl_step;
+                for (int k = 0; k < A; ++k) { s_z[(NX + k) * E + ol] = (double)cx.noisy[k]; s_z[(NX + A + k) * E + ol] = (double)cx.clipped[k]; }
+                s_cstep[ol] = e.ctrl_step;
             }
             PROF_T(k3);
             if (SPLIT) {
                 named_bar_arrive(1, 128);                                  // helpers may start
                 if (live) done = env_done<SYS, R, R>(h, s_xg, state, goal_reached, oob);
                 named_bar_sync(2, 128);                                    // helpers are done
-                if (live) { rew = s_rew[tid]; mse = s_mse[tid]; cviol = s_cviol[tid]; }
+                if (live) { rew = s_rew[ol]; mse = s_mse[ol]; cviol = s_cviol[ol]; }
             } else if (live) {
                 env_reward_mse<SYS, R, R>(h, s_xg, state, cx.noisy, cx.clipped, e.ctrl_step, rew, mse);
                 done = env_done<SYS, R, R>(h, s_xg, state, goal_reached, oob);
-                if (nc > 0) cviol = env_constraints(T, h->rows, nc, h->con_fast, s_z + tid, E, nullptr, P.out.d_cvals ? P.out.d_cvals + (tn0 + tid) * nc : nullptr);
+                if (nc > 0) cviol = env_constraints(T, h->rows, nc, h->con_fast, s_z + ol, E, nullptr, P.out.d_cvals ? P.out.d_cvals + (tn0 + ol) * nc : nullptr);
             }
             PROF_T(k4);
             if (live) {
@@ -583,24 +613,30 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
                 if (done) {
                     if (truncated) {                                       // ppo.py:274-283: critic on the terminal observation
                         trunc = 1;
-                        if (helper_obs) { for (int k = 0; k < od; ++k) s_tobs[tile_idx<E>(k, tid)] = s_obs[tile_idx<E>(k, tid)]; }
-                        else make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_tobs, tid});
+                        if (helper_obs) { for (int k = 0; k < od; ++k) s_tobs[tile_idx<E>(k, ol)] = s_on[tile_idx<E>(k, ol)]; }
+                        else make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_tobs, ol});
                     }
                     ep_count += 1; ep_ret_sum += e.ep_ret; ep_len_sum += e.ep_len; ep_cv_sum += e.ep_cv;
                     e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
-                    env_reset<SYS, R>(T, h, n, e, state);                  // dummy_vec_env.py:33-38
+                    {   // dummy_vec_env.py:33-38.  Take the pre-drawn episode if the helper already has it, draw inline otherwise.
+                        const int slot = e.episode & 1;
+                        const bool hit = use_cand && (*(volatile int*)&s_cand_ep[slot * E + ol] == e.episode);
+                        env_reset<SYS, R>(T, h, n, e, state, hit ? s_cand + slot * NC * E + ol : nullptr, E);
+                        __threadfence_block();                             // candidate fully read before the new index is published
+                        *(volatile int*)&s_epi[ol] = e.episode;
+                    }
                     ns = reset_noise<R>(T, h, n, e.episode);
-                    make_obs<SYS, R, R>(T, h, s_xg, state, n, 0, true, ns, TileObsSink<E>{s_obs, tid});
+                    make_obs<SYS, R, R>(T, h, s_xg, state, n, 0, true, ns, TileObsSink<E>{s_on, ol});
                 } else if (!helper_obs) {
-                    make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_obs, tid});
+                    make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_on, ol});
                 }
-                const size_t tn = tn0 + tid;
+                const size_t tn = tn0 + ol;
                 if (A == 2) *reinterpret_cast<float2*>(P.out.d_act + tn * A) = make_float2(act[0], act[1 % A]);
                 else if (A == 4) *reinterpret_cast<float4*>(P.out.d_act + tn * A) = make_float4(act[0], act[1 % A], act[2 % A], act[3 % A]);
                 else P.out.d_act[tn * A] = act[0];
                 P.out.d_rew[tn] = (float)rew;
                 P.out.d_mask[tn] = done ? 0.f : 1.f;
-                P.out.d_v[tn] = val;
+                if (!DECOUPLED) P.out.d_v[tn] = val;
                 P.out.d_logp[tn] = logp;
                 if (P.out.d_cviol) P.out.d_cviol[tn] = (float)cviol;
                 if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
@@ -609,12 +645,12 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
 #ifdef SCG_PROF
             if (PROF_ON) { long long k5 = clock64(); pacc[0] += k1 - k0; pacc[1] += k2 - k1; pacc[2] += k3 - k2; pacc[3] += k4 - k3; pacc[4] += k5 - k4; }
 #endif
-        } else if (SPLIT && warp <= 3) {
+        } else if (SPLIT && role <= 3) {
             named_bar_sync(1, 128);                                        // z, ctrl_step published by the owners
             const int ee = lane;
             const bool hl = ee < E && n0 + ee < N;
             if (hl) {
-                if (warp == 1) {                                           // constraints (benchmark_env.py:472-485)
+                if (role == 1) {                                           // constraints (benchmark_env.py:472-485)
                     int cv = 0;
                     if (nc > 0) cv = env_constraints(T, h->rows, nc, h->con_fast, s_z + ee, E, nullptr, P.out.d_cvals ? P.out.d_cvals + (tn0 + ee) * nc : nullptr);
                     s_cviol[ee] = cv;
@@ -622,7 +658,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
                     R st[NX];
 #pragma unroll
                     for (int k = 0; k < NX; ++k) st[k] = (R)s_z[k * E + ee];
-                    if (warp == 2) {                                       // reward + info['mse']
+                    if (role == 2) {                                       // reward + info['mse']
                         R ny[A], cl[A], rw, ms;
 #pragma unroll
                         for (int k = 0; k < A; ++k) { ny[k] = (R)s_z[(NX + k) * E + ee]; cl[k] = (R)s_z[(NX + A + k) * E + ee]; }
@@ -630,11 +666,37 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
                         s_rew[ee] = rw; s_mse[ee] = ms;
                     } else if (!obs_noise) {                               // next observation of the continuing episode
                         NoiseSrc<R> nn; nn.row = nullptr; nn.philox = false; nn.slot = 0; nn.stream = 0; nn.idx = 0; nn.key.k0 = nn.key.k1 = nn.key.genv = 0;
-                        make_obs<SYS, R, R>(T, h, s_xg, st, n0 + ee, s_cstep[ee], false, nn, TileObsSink<E>{s_obs, ee});
+                        make_obs<SYS, R, R>(T, h, s_xg, st, n0 + ee, s_cstep[ee], false, nn, TileObsSink<E>{s_on, ee});
                     }
                 }
             }
             named_bar_arrive(2, 128);
+            if (use_cand && role == 3 && hl) {
+                // off the critical path: keep the next two episodes of env ee pre-drawn (a pure function of (env, episode))
+                const int want = *(volatile int*)&s_epi[ee];
+#pragma unroll 1
+                for (int d = 0; d < 2; ++d) {
+                    const int ep = want + d, slot = ep & 1;
+                    if (*(volatile int*)&s_cand_ep[slot * E + ee] != ep) {
+                        double inr[SCG_MAX_INERTIAL], ini[NX];
+                        reset_draw<SYS, R>(T, h, n0 + ee, ep, inr, ini);
+                        double* cd = s_cand + slot * NC * E + ee;
+#pragma unroll
+                        for (int j = 0; j < SCG_MAX_INERTIAL; ++j) cd[j * E] = inr[j];
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) cd[(SCG_MAX_INERTIAL + j) * E] = ini[j];
+                        __threadfence_block();
+                        *(volatile int*)&s_cand_ep[slot * E + ee] = ep;
+                    }
+                }
+            }
+        } else if (DECOUPLED && crit_tl >= 0) {
+          if constexpr (DECOUPLED) {
+            // critic of observation t on four GEMM warps, concurrently with the env step above; it stores v[t] itself
+            const int tl = crit_tl;
+            net_forward<HID, E, NT / 2, 3>(tl, 1, 1, A, s_blob, L, s_oc, s_h1 + NETSZ, s_h2 + NETSZ, s_part + NT, s_out + A * E, od, P.activation);
+            if (tl < E && n0 + tl < N) P.out.d_v[tn0 + tl] = s_out[A * E + tl];
+          }
         }
         PROF_T(k6);
         // (c) critic on the terminal observation of time-limit truncated envs (rare, CTA-uniform branch).
@@ -644,25 +706,29 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
         if (PROF_ON) pacc[5] += clock64() - k6;
 #endif
         if (any_trunc) {
-            mlp_forward<HID, E, NT, A>(s_blob, L, s_tobs, s_h1, s_h2, s_out, od, P.activation);
-            if (live && trunc) P.out.d_terminal_v[tn0 + tid] = s_out[A * E + tid];
+            if constexpr (DECOUPLED) net_forward<HID, E, NT, 0>(tid, 1, 1, A, s_blob, L, s_tobs, s_h1 + NETSZ, s_h2 + NETSZ, s_part, s_out + A * E, od, P.activation);
+            else mlp_forward<HID, E, NT, A>(s_blob, L, s_tobs, s_h1, s_h2, s_part, s_out, od, P.activation);
+            if (live && trunc) P.out.d_terminal_v[tn0 + ol] = s_out[A * E + ol];
             __syncthreads();
         }
+        cur ^= 1;
     }
+    float* s_ol = s_obs + cur * OBS_TILE;                  // the observation after the last step
 #ifdef SCG_PROF
     if (PROF_ON && blockIdx.x == 0) for (int i = 0; i < 8; ++i) P.prof[i] = pacc[i];
     long long g0 = clock64();
 #endif
     // ---- bootstrap value of the last observation, state write-back, GAE
-    mlp_forward<HID, E, NT, A>(s_blob, L, s_obs, s_h1, s_h2, s_out, od, P.activation);
+    if constexpr (DECOUPLED) net_forward<HID, E, NT, 0>(tid, 1, 1, A, s_blob, L, s_ol, s_h1 + NETSZ, s_h2 + NETSZ, s_part, s_out + A * E, od, P.activation);
+    else mlp_forward<HID, E, NT, A>(s_blob, L, s_ol, s_h1, s_h2, s_part, s_out, od, P.activation);
     if (live) {
         env_store<SYS, R>(T, n, e);
         for (int k = 0; k < od; ++k) {
-            const float v = s_obs[tile_idx<E>(k, tid)];
+            const float v = s_ol[tile_idx<E>(k, ol)];
             T.st.cur_obs[(size_t)n * od + k] = v;
             if (P.out.d_last_obs) P.out.d_last_obs[(size_t)n * od + k] = v;
         }
-        const float lval = s_out[A * E + tid];
+        const float lval = s_out[A * E + ol];
         if (P.out.d_last_val) P.out.d_last_val[n] = lval;
         if (P.out.d_ep_count) { P.out.d_ep_count[n] = ep_count; P.out.d_ep_return_sum[n] = ep_ret_sum; P.out.d_ep_length_sum[n] = ep_len_sum; P.out.d_ep_cviol_sum[n] = ep_cv_sum; }
         if (P.out.d_ret && P.out.d_adv) {
@@ -697,6 +763,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
     }
 #ifdef SCG_PROF
     if (PROF_ON && blockIdx.x == 0) P.prof[7] = clock64() - g0;
+    if (PROF_ON && blockIdx.x < 1024) { P.prof[16 + blockIdx.x] = g0 - cta_t0; P.prof[16 + 1024 + blockIdx.x] = ep_count; }
 #endif
 }
 
