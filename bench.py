@@ -158,35 +158,37 @@ def run_ours(args):
     env_steps = world * N * T_HORIZON * args.steps
     value = env_steps / (total_ms * 1e-3)
 
-    # ---- end-to-end through the collector with HOST buffers: weights H2D, full PPOBuffer record D2H, every step
-    rec_keys = ('obs', 'act', 'rew', 'mask', 'v', 'logp', 'terminal_v', 'ret', 'adv')
-    host_params = [p.detach().cpu().pin_memory() for p in ac.parameters()]
-    host_flat = torch.empty(out['_flat'].shape, dtype=torch.float32).pin_memory()      # the whole record is one flat buffer
-    h2d_bytes = sum(p.numel() * 4 for p in host_params)
-    d2h_bytes = host_flat.numel() * 4
+    # ---- end-to-end through the collector with HOST buffers (engine.HostCollector): every step the policy parameters come from host
+    # memory (host pack -> one H2D) and the full PPOBuffer record goes back to pinned host memory (one D2H).  Two records in flight:
+    # the D2H of rollout k overlaps rollout k+1.  `e2e_serial` is the same with one record in flight (no overlap).
+    from safe_control_gym_b200.engine import HostCollector
+    ac_host = build_policy(env)
 
-    def e2e_step():
-        with torch.no_grad():
-            for p, hp in zip(ac.parameters(), host_params):
-                p.copy_(hp, non_blocking=True)
-        b_, d_ = pack_policy(ac, dev)
-        o = eng.rollout(b_, d_, T_HORIZON, use_gae=True, want=want, out=out)
-        host_flat.copy_(o['_flat'], non_blocking=True)
+    def e2e_rate(depth, n_steps):
+        hc = HostCollector(eng, dims, T_HORIZON, depth=depth, use_gae=True, want=want)
+        acc = 0.0
+        for _ in range(depth + 1):                     # warm-up (allocates the pinned buffers)
+            hc.submit(ac_host)
+            acc += float(hc.fetch()['rew'][0, 0, 0])
         torch.cuda.synchronize()
-        return float(host_flat[0])
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(n_steps):
+            hc.submit(ac_host)
+            if i >= depth - 1:
+                acc += float(hc.fetch()['rew'][-1, -1, 0])      # the host consumes every record
+        while hc.fetched < hc.submitted:
+            acc += float(hc.fetch()['rew'][-1, -1, 0])
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return world * N * T_HORIZON * n_steps / float(dt), hc.h2d_bytes, hc.d2h_bytes, acc
 
-    for _ in range(2):
-        e2e_step()
-    if world > 1:
-        dist.barrier()
-    e2e_steps = max(5, min(args.steps, 20))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * T_HORIZON * e2e_steps / float(e2e_s)
+    e2e_steps = max(8, min(args.steps, 32))
+    e2e_serial, h2d_bytes, d2h_bytes, _ = e2e_rate(1, e2e_steps)
+    e2e_value, _, _, _ = e2e_rate(2, e2e_steps)
     # the timed regions above last milliseconds: keep the same kernel running for ~2 s so that nvidia-smi (100 ms period)
     # records the clocks and throttle reasons UNDER THIS LOAD
     t_end = time.perf_counter() + 2.0
@@ -215,7 +217,10 @@ def run_ours(args):
                        'l2': 'flushed with a 256 MiB write before every timed step; per-step CUDA-event intervals summed'},
             'gpu_launches': int(launches),
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': int(d2h_bytes),
-                    'what': 'host policy weights -> GPU, fused rollout, full PPOBuffer record (obs, act, rew, mask, v, logp, terminal_v, ret, adv) -> pinned host'},
+                    'serial_value': e2e_serial, 'steps': e2e_steps,
+                    'what': 'engine.HostCollector: host policy parameters -> scg_policy_pack -> H2D, fused rollout, full PPOBuffer record '
+                            '(obs, act, rew, mask, v, logp, terminal_v, ret, adv) -> pinned host, consumed by the host every step; 2 records in flight '
+                            '(D2H of rollout k overlaps rollout k+1); serial_value = 1 record in flight'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                          'peak_source': peak_src, 'kernel': 'rollout_kernel<QUAD2D, double, 64, 32, 256>', 'kernel_ms': kern_s * 1e3,
                          'algorithmic_bytes_per_env_step': BYTES_PER_ENV_STEP,
@@ -295,7 +300,7 @@ def main():
     if res is not None:
         if int(os.environ.get('WORLD_SIZE', '1')) == 1 and not args.no_cpu_baseline:
             ncpu = os.cpu_count() or 8
-            n_env, reps = 32 * ncpu, 8             # bounded sample, ~10-20 s of CPU work on any core count
+            n_env, reps = 32 * ncpu, 20            # bounded sample, ~10-20 s of CPU work on any core count
             rate, secs, threads = oracle_rate(n_env, reps)
             res['cpu_baseline'] = {'value': rate, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
                                    'sample': f'{n_env} envs x {T_HORIZON} control steps x {reps} repeats ({secs:.1f} s), C oracle port of the reference path, OpenMP over envs'}

@@ -227,3 +227,89 @@ class EngineHandle:
             self.close()
         except Exception:
             pass
+
+
+def pack_policy_host(ac_or_params, dims, blob_out):
+    '''Host-side packer (C-ABI `scg_policy_pack`): parameters in host memory -> packed blob in (pinned) host memory.
+    `ac_or_params`: an MLPActorCritic on the CPU, or a dict {'actor_w': [3], 'actor_b': [3], 'logstd', 'critic_w': [3], 'critic_b': [3]}
+    of contiguous float32 CPU tensors.'''
+    if not isinstance(ac_or_params, dict):
+        a, c = ac_or_params.actor.pi_net.fcs, ac_or_params.critic.v_net.fcs
+        ac_or_params = {'actor_w': [l.weight for l in a], 'actor_b': [l.bias for l in a], 'logstd': ac_or_params.actor.logstd,
+                        'critic_w': [l.weight for l in c], 'critic_b': [l.bias for l in c]}
+    P = ac_or_params
+    obs_dim, act_dim, hid = dims
+
+    def arr(ts):
+        ts = [t.detach() for t in ts]
+        assert all(t.device.type == 'cpu' and t.dtype == torch.float32 and t.is_contiguous() for t in ts)
+        return (C.c_void_p * 3)(*[t.data_ptr() for t in ts]), ts
+
+    aw, k1 = arr(P['actor_w']); ab, k2 = arr(P['actor_b']); cw, k3 = arr(P['critic_w']); cb, k4 = arr(P['critic_b'])
+    ls = P['logstd'].detach()
+    assert blob_out.device.type == 'cpu' and blob_out.dtype == torch.float32 and blob_out.is_contiguous()
+    assert blob_out.numel() >= _abi.lib().scg_policy_blob_floats(obs_dim, act_dim, hid)
+    _abi.check(_abi.lib().scg_policy_pack(obs_dim, act_dim, hid, aw, ab, ls.data_ptr(), cw, cb, blob_out.data_ptr()))
+    return blob_out
+
+
+class HostCollector:
+    '''The fused collector for HOST-side consumers (the reference keeps policy parameters and the PPOBuffer in host memory,
+    ppo_utils.py:241-355): `submit(params)` packs the parameters on the host, copies the blob to the GPU, launches the fused rollout and
+    queues the device->host copy of the whole PPOBuffer record into pinned memory; `fetch()` returns the oldest record as numpy-backed
+    views.  `depth` records are in flight: the D2H copy of rollout k runs on a copy stream underneath rollout k+1.'''
+
+    def __init__(self, eng, dims, T, depth=2, **rollout_kw):
+        self.eng, self.dims, self.T, self.depth, self.kw = eng, dims, int(T), int(depth), rollout_kw
+        dev = eng.device
+        nblob = _abi.lib().scg_policy_blob_floats(*dims)
+        self.blob_host = [torch.zeros(nblob, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.blob_dev = [torch.zeros(nblob, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.out = [None] * depth
+        self.host = [None] * depth
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ev_done = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_copied = [torch.cuda.Event() for _ in range(depth)]
+        self.submitted = self.fetched = 0
+
+    @property
+    def h2d_bytes(self):
+        return self.blob_host[0].numel() * 4
+
+    @property
+    def d2h_bytes(self):
+        return self.host[0].numel() * 4 if self.host[0] is not None else 0
+
+    def submit(self, params):
+        if self.submitted - self.fetched >= self.depth:
+            raise RuntimeError('HostCollector: fetch() the oldest record before submitting another rollout')
+        s = self.submitted % self.depth
+        pack_policy_host(params, self.dims, self.blob_host[s])
+        cur = torch.cuda.current_stream(self.eng.device)
+        if self.submitted >= self.depth:
+            cur.wait_event(self.ev_copied[s])            # the record buffer is free once its previous D2H has finished
+        self.blob_dev[s].copy_(self.blob_host[s], non_blocking=True)
+        self.out[s] = self.eng.rollout(self.blob_dev[s], self.dims, self.T, out=self.out[s], **self.kw)
+        self.ev_done[s].record(cur)
+        flat = self.out[s]['_flat']
+        if self.host[s] is None:
+            self.host[s] = torch.empty(flat.shape, dtype=torch.float32).pin_memory()
+        self.copy_stream.wait_event(self.ev_done[s])
+        with torch.cuda.stream(self.copy_stream):
+            self.host[s].copy_(flat, non_blocking=True)
+            self.ev_copied[s].record(self.copy_stream)
+        self.submitted += 1
+
+    def fetch(self):
+        '''Blocks until the oldest in-flight record is in host memory; returns {key: numpy view [T][N][width]} (valid until the slot is reused).'''
+        if self.fetched >= self.submitted:
+            raise RuntimeError('HostCollector: nothing in flight')
+        s = self.fetched % self.depth
+        self.ev_copied[s].synchronize()
+        self.fetched += 1
+        T, N = self.out[s]['_TN']
+        res, o, h = {}, 0, self.host[s].numpy()
+        for k, w in self.out[s]['_layout']:
+            res[k] = h[o:o + T * N * w].reshape(T, N, w)
+            o += T * N * w
+        return res

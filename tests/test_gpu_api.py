@@ -164,3 +164,41 @@ def test_value_improves_on_cartpole_training():
         lens.append(np.mean(ctrl.env.length_queue) if len(ctrl.env.length_queue) else 0)
     assert lens[-1] > lens[1] * 1.2, lens
     ctrl.close()
+
+
+def test_host_collector_pipelined_records_equal_direct_rollouts():
+    '''engine.HostCollector (host parameters -> scg_policy_pack -> H2D -> fused rollout -> pinned host record, two records in flight)
+    returns bit-identical records to the same sequence of direct device rollouts.'''
+    from safe_control_gym_b200.controllers.ppo.ppo_utils import MLPActorCritic
+    from safe_control_gym_b200.engine import EngineHandle, HostCollector, pack_policy
+    env = H.make_env('quadrotor_2D_track')
+    N, T, K = 96, 40, 5
+    torch.manual_seed(3)
+    ac = MLPActorCritic(env.observation_space, env.action_space, hidden_dims=[64, 64], activation='tanh')
+    recs = []
+    for mode in ('direct', 'host'):
+        eng = EngineHandle(env, num_envs=N, auto_reset=True, rng_mode='philox', seed=21)
+        eng.reset()
+        got = []
+        if mode == 'direct':
+            blob, dims = pack_policy(ac.to(eng.device), eng.device)
+            ac.cpu()
+            for _ in range(K):
+                out = eng.rollout(blob, dims, T, use_gae=True, want=('ret', 'adv'))
+                got.append({k: out[k].cpu().numpy().copy() for k, _ in out['_layout']})
+        else:
+            hc = HostCollector(eng, (12, 2, 64), T, depth=2, use_gae=True, want=('ret', 'adv'))
+            for i in range(K):
+                hc.submit(ac)
+                if i >= 1:
+                    got.append({k: v.copy() for k, v in hc.fetch().items()})
+            got.append({k: v.copy() for k, v in hc.fetch().items()})
+            with pytest.raises(RuntimeError):
+                hc.fetch()
+            assert hc.h2d_bytes > 0 and hc.d2h_bytes == 4 * T * N * (12 + 2 + 7)
+        eng.close()
+        recs.append(got)
+    assert len(recs[0]) == len(recs[1]) == K
+    for a, b in zip(*recs):
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
