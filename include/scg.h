@@ -296,6 +296,51 @@ int  scg_state_bytes(const scg_env* env, size_t* bytes);
 int  scg_get_state(scg_env* env, void* h_blob, size_t bytes, void* stream);
 int  scg_set_state(scg_env* env, const void* h_blob, size_t bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused PPO update: PPOAgent.update, safe_control_gym/controllers/ppo/ppo_utils.py:82-146 --
+ * opt_epochs x num_mini_batch sequential minibatch steps, each = actor loss (clipped surrogate + entropy bonus, :56-69),
+ * KL gate `approx_kl <= 1.5 * target_kl` (:128), critic loss (:71-80), backward through both MLPs and two Adam steps
+ * (torch.optim.Adam defaults, :44-45) -- in ONE cooperative kernel launch.  Handle-free: runs on the current device.
+ *
+ * Training parameter blob ("train layout", floats; every section starts at a multiple of 4):
+ *   actor : W1[H][obs] b1[H] W2[H][H] b2[H] W3[A][H] b3[A] logstd[A]      (nn.Linear layout, ppo_utils.py:149-177)
+ *   critic: W1[H][obs] b1[H] W2[H][H] b2[H] W3[1][H] b3[1]                 (ppo_utils.py:180-194)
+ * scg_ppo_param_layout() returns the 13 section offsets + [13] = first critic float + [14] = total.
+ * ------------------------------------------------------------------------------------------- */
+#define SCG_PPO_KEY_OBS 0
+#define SCG_PPO_KEY_ACT 1
+#define SCG_PPO_KEY_LOGP 2
+#define SCG_PPO_KEY_ADV 3
+#define SCG_PPO_KEY_RET 4
+#define SCG_PPO_KEY_V 5
+typedef struct scg_ppo_args {
+    int32_t obs_dim, act_dim, hidden_dim, activation;
+    int32_t mini_batch_size, num_mini_batch, opt_epochs, use_clipped_value;   /* ppo.yaml:13-22 */
+    /* the record: row r of key k lives at d_key[k] + (r / block_rows) * block_stride[k] + (r % block_rows) * width(k)
+     * (one block = one rank's [T*n][width] slab of the all-gathered rollout record; a single-GPU record is one block) */
+    int64_t block_rows;
+    int64_t block_stride[6];
+    const float* d_key[6];         /* SCG_PPO_KEY_*: obs[.][obs_dim], act[.][act_dim], logp, adv (already normalised, ppo.py:300), ret, v */
+    const int32_t* d_perm;         /* [opt_epochs][perm_stride] row indices; minibatch i of epoch e = perm[e][i*mb .. (i+1)*mb) (ppo_utils.py:342-355) */
+    int64_t perm_stride;
+    double clip_param, target_kl, entropy_coef;
+    double actor_lr, critic_lr, beta1, beta2, adam_eps;
+    float* d_params;               /* train layout, updated in place */
+    float* d_exp_avg;              /* Adam first moments, train layout */
+    float* d_exp_avg_sq;           /* Adam second moments, train layout */
+    int64_t* d_adam_steps;         /* [2] optimizer step counts: actor (advances only when the KL gate passes), critic */
+    float* d_stats;                /* [8] += { sum policy_loss, sum value_loss, sum entropy_loss, sum approx_kl, actor steps taken, minibatches, 0, 0 } */
+    float* d_workspace;            /* scg_ppo_workspace_bytes() bytes of device scratch */
+    size_t workspace_bytes;
+    float* d_grad_out;             /* nullable: reduced gradient of the LAST minibatch in train layout (tests) */
+} scg_ppo_args;
+
+int    scg_ppo_param_layout(int32_t obs_dim, int32_t act_dim, int32_t hidden_dim, int32_t offsets_out[15]);
+size_t scg_ppo_workspace_bytes(const scg_ppo_args* args);
+int    scg_ppo_update(const scg_ppo_args* args, void* stream);
+/* train layout (device) -> packed rollout blob of scg_policy_pack() (device), one small launch */
+int    scg_policy_pack_device(int32_t obs_dim, int32_t act_dim, int32_t hidden_dim, const float* d_params, float* d_blob, void* stream);
+
 /* introspection used by the benchmark: how many kernels this handle launched so far */
 int  scg_launch_count(const scg_env* env, uint64_t* launches);
 

@@ -97,6 +97,21 @@ class scg_rollout_args(C.Structure):
     ]
 
 
+class scg_ppo_args(C.Structure):
+    _fields_ = [
+        ('obs_dim', C.c_int32), ('act_dim', C.c_int32), ('hidden_dim', C.c_int32), ('activation', C.c_int32),
+        ('mini_batch_size', C.c_int32), ('num_mini_batch', C.c_int32), ('opt_epochs', C.c_int32), ('use_clipped_value', C.c_int32),
+        ('block_rows', C.c_int64), ('block_stride', C.c_int64 * 6), ('d_key', C.c_void_p * 6),
+        ('d_perm', C.c_void_p), ('perm_stride', C.c_int64),
+        ('clip_param', C.c_double), ('target_kl', C.c_double), ('entropy_coef', C.c_double),
+        ('actor_lr', C.c_double), ('critic_lr', C.c_double), ('beta1', C.c_double), ('beta2', C.c_double), ('adam_eps', C.c_double),
+        ('d_params', C.c_void_p), ('d_exp_avg', C.c_void_p), ('d_exp_avg_sq', C.c_void_p), ('d_adam_steps', C.c_void_p),
+        ('d_stats', C.c_void_p), ('d_workspace', C.c_void_p), ('workspace_bytes', C.c_size_t), ('d_grad_out', C.c_void_p),
+    ]
+
+
+PPO_KEYS = ('obs', 'act', 'logp', 'adv', 'ret', 'v')      # SCG_PPO_KEY_*
+
 # every symbol include/scg.h declares: name -> (restype, argtypes)
 _VP = C.c_void_p
 _SYMBOLS = {
@@ -119,6 +134,10 @@ _SYMBOLS = {
     'scg_set_state': (C.c_int, [_VP, _VP, C.c_size_t, _VP]),
     'scg_launch_count': (C.c_int, [_VP, C.POINTER(C.c_uint64)]),
     'scg_philox_selftest': (C.c_int, [C.c_int32, _VP, _VP, _VP, C.c_int32]),
+    'scg_ppo_param_layout': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32 * 15)]),
+    'scg_ppo_workspace_bytes': (C.c_size_t, [C.POINTER(scg_ppo_args)]),
+    'scg_ppo_update': (C.c_int, [C.POINTER(scg_ppo_args), _VP]),
+    'scg_policy_pack_device': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP]),
 }
 
 LIB_NAME = os.environ.get('SCG_LIB_NAME', 'libscg_b200.so')   # SCG_LIB_NAME: developer builds (e.g. the -DSCG_PROF variant)

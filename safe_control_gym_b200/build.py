@@ -13,7 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['scg_api.cu', 'scg_kernels.cuh', 'scg_device.cuh']
+SOURCES = ['scg_api.cu', 'scg_ppo.cu', 'scg_kernels.cuh', 'scg_device.cuh']
+UNITS = ['scg_api.cu', 'scg_ppo.cu']          # translation units of libscg_b200.so
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-shared', '-Xcompiler', '-fPIC']
 
 
@@ -30,8 +31,8 @@ def build_cuda(force=False, prof=False, verbose=True):
     if not force and not _stale(out, deps):
         return out
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-DSCG_PROF'] if prof else []) + ['-I', os.path.join(ROOT, 'include'), '-o', out,
-                                                                     os.path.join(CSRC, 'scg_api.cu')]
+    cmd = ([nvcc] + NVCC_FLAGS + ['--threads', str(len(UNITS))] + (['-DSCG_PROF'] if prof else [])
+           + ['-I', os.path.join(ROOT, 'include'), '-o', out] + [os.path.join(CSRC, u) for u in UNITS])
     if verbose:
         print(' '.join(cmd), flush=True)
     subprocess.run(cmd, check=True)

@@ -104,7 +104,8 @@ class PPO:
         self.agent = PPOAgent(self.env.observation_space, self.env.action_space, hidden_dim=self.hidden_dim,
                               use_clipped_value=self.use_clipped_value, clip_param=self.clip_param, target_kl=self.target_kl,
                               entropy_coef=self.entropy_coef, actor_lr=self.actor_lr, critic_lr=self.critic_lr,
-                              opt_epochs=self.opt_epochs, mini_batch_size=self.mini_batch_size, activation=self.activation)
+                              opt_epochs=self.opt_epochs, mini_batch_size=self.mini_batch_size, activation=self.activation,
+                              fused_update=cfg.get('fused_update'))
         self.agent.to(self.device)
         self.obs_normalizer, self.reward_normalizer = BaseNormalizer(), BaseNormalizer()
         self.logger = _Logger(output_dir)
@@ -166,13 +167,19 @@ class PPO:
     def collect(self, T=None, deterministic=False, eps=None):
         '''The fused collector: one kernel launch for the whole horizon (replaces ppo.py:266-299).'''
         T = self.rollout_steps if T is None else T
-        blob, dims = pack_policy(self.agent.ac, self.device)
+        blob, dims = self._policy_blob()
         eng = self.env.unwrapped.engine
         out = eng.rollout(blob, dims, T, eps=eps, activation=self.activation, gamma=self.gamma, gae_lambda=self.gae_lambda,
                           use_gae=self.use_gae, deterministic=deterministic, out=self._rollout_out if eps is None else None)
         if eps is None:
             self._rollout_out = out
         return out
+
+    def _policy_blob(self):
+        '''Packed rollout blob: one pack kernel from the flat training vector (fused update) or the torch packer.'''
+        if self.agent.fused is not None:
+            return self.agent.fused.rollout_blob()
+        return pack_policy(self.agent.ac, self.device)
 
     def train_step(self):
         self.agent.train()
@@ -198,7 +205,7 @@ class PPO:
             self.eval_env = make_vec_envs(self.env_func, None, n_episodes, 1, self.seed * 111, rng_mode=self.env.unwrapped.rng_mode,
                                           device=self.device.index)
         self.eval_env.reset()
-        blob, dims = pack_policy(self.agent.ac, self.device)
+        blob, dims = self._policy_blob()
         T = int(self.eval_env.proto.CTRL_STEPS)
         out = self.eval_env.engine.rollout(blob, dims, T, activation=self.activation, deterministic=True, want=('cviol', 'mse', 'episode'))
         mask = out['mask'][..., 0]

@@ -60,8 +60,13 @@ class PPOAgent:
     '''Models, optimisers and the clipped-surrogate update (ppo_utils.py:16-146).'''
 
     def __init__(self, obs_space, act_space, hidden_dim=64, use_clipped_value=False, clip_param=0.2, target_kl=0.01,
-                 entropy_coef=0.01, actor_lr=0.0003, critic_lr=0.001, opt_epochs=10, mini_batch_size=64, activation='tanh', **kwargs):
+                 entropy_coef=0.01, actor_lr=0.0003, critic_lr=0.001, opt_epochs=10, mini_batch_size=64, activation='tanh',
+                 fused_update=None, **kwargs):
         self.obs_space, self.act_space = obs_space, act_space
+        self.actor_lr, self.critic_lr = actor_lr, critic_lr
+        # fused_update: None = use the fused sm_100a update kernel whenever the network shape is supported, True = require it,
+        # False = the step-by-step torch restatement of ppo_utils.py:82-146 (kept as the parity reference of the kernel)
+        self.fused_update, self.fused = fused_update, None
         self.use_clipped_value, self.clip_param, self.target_kl = use_clipped_value, clip_param, target_kl
         self.entropy_coef, self.opt_epochs, self.mini_batch_size, self.activation = entropy_coef, opt_epochs, mini_batch_size, activation
         self.ac = MLPActorCritic(obs_space, act_space, hidden_dims=[hidden_dim] * 2, activation=activation)
@@ -70,6 +75,15 @@ class PPOAgent:
 
     def to(self, device):
         self.ac.to(device)
+        device = torch.device(device)
+        obs_dim, act_dim = self.obs_space.shape[0], self.act_space.shape[0]
+        hid = self.ac.actor.pi_net.fcs[0].out_features
+        supported = device.type == 'cuda' and hid in (32, 64) and obs_dim <= 32 and act_dim <= 4
+        if self.fused_update and not supported:
+            raise NotImplementedError(f'fused PPO update: unsupported shape/device (hidden {hid}, obs {obs_dim}, act {act_dim}, {device})')
+        if supported and self.fused_update is not False:
+            from safe_control_gym_b200.engine import FusedPPOState
+            self.fused = FusedPPOState(self.ac, device)
 
     def train(self):
         self.ac.train()
@@ -77,13 +91,44 @@ class PPOAgent:
     def eval(self):
         self.ac.eval()
 
+    def _opt_groups(self):
+        names = {id(p): n for n, p in self.ac.named_parameters()}
+        return [(self.actor_opt, 0), (self.critic_opt, 1)], names
+
     def state_dict(self):
-        return {'ac': self.ac.state_dict(), 'actor_opt': self.actor_opt.state_dict(), 'critic_opt': self.critic_opt.state_dict()}
+        '''Checkpoint format of the reference (ppo_utils.py:47-54): torch.optim.Adam state dicts, also when the fused kernel owns the moments.'''
+        sd = {'ac': self.ac.state_dict(), 'actor_opt': self.actor_opt.state_dict(), 'critic_opt': self.critic_opt.state_dict()}
+        if self.fused is not None:
+            steps = self.fused.steps.tolist()
+            groups, names = self._opt_groups()
+            for opt, which in groups:
+                state = {}
+                if steps[which] > 0:
+                    for i, p in enumerate(opt.param_groups[0]['params']):
+                        n = names[id(p)]
+                        state[i] = {'step': torch.tensor(float(steps[which])), 'exp_avg': self.fused.views(self.fused.exp_avg, n).clone(),
+                                    'exp_avg_sq': self.fused.views(self.fused.exp_avg_sq, n).clone()}
+                sd['actor_opt' if which == 0 else 'critic_opt']['state'] = state
+        return sd
 
     def load_state_dict(self, sd):
-        self.ac.load_state_dict(sd['ac'])
+        self.ac.load_state_dict(sd['ac'])          # copy_ into the existing parameters: the flat training vector stays the storage
         self.actor_opt.load_state_dict(sd['actor_opt'])
         self.critic_opt.load_state_dict(sd['critic_opt'])
+        if self.fused is not None:
+            groups, names = self._opt_groups()
+            self.fused.exp_avg.zero_()
+            self.fused.exp_avg_sq.zero_()
+            steps = [0, 0]
+            for opt, which in groups:
+                st = sd['actor_opt' if which == 0 else 'critic_opt']['state']
+                for i, p in enumerate(opt.param_groups[0]['params']):
+                    if i in st:
+                        n = names[id(p)]
+                        self.fused.views(self.fused.exp_avg, n).copy_(st[i]['exp_avg'])
+                        self.fused.views(self.fused.exp_avg_sq, n).copy_(st[i]['exp_avg_sq'])
+                        steps[which] = int(st[i]['step'])
+            self.fused.steps.copy_(torch.tensor(steps, dtype=torch.int64))
 
     def compute_policy_loss(self, batch):
         dist, logp = self.ac.actor(batch['obs'], batch['act'])
@@ -103,7 +148,28 @@ class PPOAgent:
 
     def update(self, rollouts, device=None, generator=None):
         '''rollouts: dict of device tensors, [T][N][w] (one rank) or [G][T*n][w] views of the all-gathered record.
-        Minibatches are index-gathered on the GPU (two-level index, so the strided gathered views are never copied).'''
+        With the fused kernel (default on sm_100a) the whole opt_epochs x minibatch sequence is ONE launch (csrc/scg_ppo.cu);
+        `update_torch` is the step-by-step restatement of the reference and the kernel's parity reference.'''
+        if self.fused is None:
+            return self.update_torch(rollouts, device, generator)
+        flat = {k: v.reshape(v.shape[0], -1, v.shape[-1]) if v.dim() != 3 else v for k, v in rollouts.items()
+                if k in ('obs', 'act', 'logp', 'adv', 'ret', 'v')}
+        dev = flat['obs'].device
+        total = flat['obs'].shape[0] * flat['obs'].shape[1]
+        assert total // self.mini_batch_size != 0, 'num_mini_batch is 0'
+        perm = torch.stack([torch.randperm(total, device=dev, generator=generator) for _ in range(self.opt_epochs)]).to(torch.int32)
+        self.fused.stats.zero_()
+        group = self.actor_opt.param_groups[0]
+        n_mb = self.fused.update(flat, perm, self.mini_batch_size, activation=self.activation, clip_param=self.clip_param,
+                                 target_kl=self.target_kl, entropy_coef=self.entropy_coef, use_clipped_value=self.use_clipped_value,
+                                 actor_lr=group['lr'], critic_lr=self.critic_opt.param_groups[0]['lr'], betas=group['betas'], eps=group['eps'])
+        st = self.fused.stats.tolist()
+        n = self.opt_epochs * n_mb
+        return {'policy_loss': st[0] / n, 'value_loss': st[1] / n, 'entropy_loss': st[2] / n, 'approx_kl': st[3] / n,
+                'actor_steps': int(st[4]), 'minibatches': int(st[5])}
+
+    def update_torch(self, rollouts, device=None, generator=None):
+        '''Minibatches are index-gathered on the GPU (two-level index, so the strided gathered views are never copied).'''
         flat = {k: v.reshape(v.shape[0], -1, v.shape[-1]) if v.dim() == 3 else v for k, v in rollouts.items()
                 if k in ('obs', 'act', 'logp', 'adv', 'ret', 'v')}
         d0, d1 = flat['obs'].shape[0], flat['obs'].shape[1]

@@ -38,6 +38,8 @@ static thread_local std::string g_create_err;
 static int sys_nx(int s) { return s == SCG_SYS_CARTPOLE ? 4 : s == SCG_SYS_QUAD1D ? 2 : s == SCG_SYS_QUAD2D ? 6 : 12; }
 static int sys_nu(int s) { return s == SCG_SYS_CARTPOLE ? 1 : s == SCG_SYS_QUAD1D ? 1 : s == SCG_SYS_QUAD2D ? 2 : 4; }
 
+void scg_internal_set_error(const std::string& msg) { g_create_err = msg; }   // handle-free entry points (scg_ppo.cu)
+
 static int fail(scg_env* e, int code, const std::string& msg) {
     if (e) e->err = msg; else g_create_err = msg;
     return code;

@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
 }
 
 // Philox known-answer hook
-__global__ void philox_selftest_kernel(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int n) {
+static __global__ void philox_selftest_kernel(const uint32_t* ctr, const uint32_t* key, uint32_t* out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t o[4];

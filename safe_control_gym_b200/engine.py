@@ -313,3 +313,103 @@ class HostCollector:
             res[k] = h[o:o + T * N * w].reshape(T, N, w)
             o += T * N * w
         return res
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused PPO update (include/scg.h: scg_ppo_update; reference ppo_utils.py:82-146)
+TRAIN_SECTIONS = ('actor.pi_net.fcs.0.weight', 'actor.pi_net.fcs.0.bias', 'actor.pi_net.fcs.1.weight', 'actor.pi_net.fcs.1.bias',
+                  'actor.pi_net.fcs.2.weight', 'actor.pi_net.fcs.2.bias', 'actor.logstd',
+                  'critic.v_net.fcs.0.weight', 'critic.v_net.fcs.0.bias', 'critic.v_net.fcs.1.weight', 'critic.v_net.fcs.1.bias',
+                  'critic.v_net.fcs.2.weight', 'critic.v_net.fcs.2.bias')
+
+
+def ppo_train_layout(obs_dim, act_dim, hid):
+    '''{parameter name: float offset} of the flat training vector + 'critic0' (first critic float) + 'total' (C: scg_ppo_param_layout).'''
+    o = (C.c_int32 * 15)()
+    _abi.check(_abi.lib().scg_ppo_param_layout(obs_dim, act_dim, hid, C.byref(o)))
+    L = {name: int(o[i]) for i, name in enumerate(TRAIN_SECTIONS)}
+    L['critic0'], L['total'] = int(o[13]), int(o[14])
+    return L
+
+
+class FusedPPOState:
+    '''Flat training state of an MLPActorCritic on the GPU: parameters (the module's nn.Parameters become views into `params`),
+    Adam moments and step counts, in the train layout of include/scg.h.'''
+
+    def __init__(self, ac, device):
+        a, c = ac.actor.pi_net.fcs, ac.critic.v_net.fcs
+        if len(a) != 3 or len(c) != 3:
+            raise NotImplementedError('the fused PPO update supports two hidden layers (hidden_dims=[h, h])')
+        self.dims = (a[0].in_features, a[2].out_features, a[0].out_features)
+        self.device = torch.device(device)
+        self.layout = ppo_train_layout(*self.dims)
+        n = self.layout['total']
+        self.params = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.exp_avg = torch.zeros_like(self.params)
+        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.steps = torch.zeros(2, dtype=torch.int64, device=self.device)      # actor, critic optimizer step counts
+        self.stats = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self.workspace = None
+        self.named = dict(ac.named_parameters())
+        assert set(self.named) == set(TRAIN_SECTIONS), sorted(self.named)
+        with torch.no_grad():
+            for name in TRAIN_SECTIONS:
+                p, o = self.named[name], self.layout[name]
+                view = self.params[o:o + p.numel()].view(p.shape)
+                view.copy_(p.detach().to(self.device, torch.float32))
+                p.data = view                       # the module now reads / writes the flat vector
+        self.blob = torch.zeros(_abi.lib().scg_policy_blob_floats(*self.dims), dtype=torch.float32, device=self.device)
+
+    def views(self, flat, name):
+        p, o = self.named[name], self.layout[name]
+        return flat[o:o + p.numel()].view(p.shape)
+
+    def rollout_blob(self):
+        '''Packed policy blob for scg_rollout, refreshed from the training vector by one small kernel.'''
+        _abi.check(_abi.lib().scg_policy_pack_device(*self.dims, self.params.data_ptr(), self.blob.data_ptr(),
+                                                    torch.cuda.current_stream(self.device).cuda_stream))
+        return self.blob, self.dims
+
+    def update(self, batch, perm, mini_batch_size, activation='tanh', clip_param=0.2, target_kl=0.01, entropy_coef=0.01,
+               use_clipped_value=False, actor_lr=3e-4, critic_lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_out=None, num_mini_batch=None):
+        '''batch: {'obs','act','logp','adv','ret','v'} float32 device tensors [B][R][w] (stride(1) == w, stride(2) == 1; any block stride);
+        perm: int32 device tensor [opt_epochs][>= num_mini_batch * mini_batch_size] of row indices into the flattened [B*R] rows.
+        Returns the number of minibatches per epoch.  One kernel launch; results accumulate into self.stats.'''
+        a = _abi.scg_ppo_args()
+        a.obs_dim, a.act_dim, a.hidden_dim = self.dims
+        a.activation = _abi.ACTIVATIONS[activation]
+        widths = {'obs': self.dims[0], 'act': self.dims[1], 'logp': 1, 'adv': 1, 'ret': 1, 'v': 1}
+        B, R = batch['obs'].shape[0], batch['obs'].shape[1]
+        keep = []
+        for i, k in enumerate(_abi.PPO_KEYS):
+            t = batch[k]
+            if t.dtype != torch.float32 or t.device != self.device or tuple(t.shape) != (B, R, widths[k]):
+                raise ValueError(f'fused PPO update: bad record tensor {k}: {t.dtype} {tuple(t.shape)} {t.device}')
+            if (t.stride(2) != 1 and widths[k] > 1) or t.stride(1) != widths[k]:
+                t = t.contiguous()
+            keep.append(t)
+            a.d_key[i] = t.data_ptr()
+            a.block_stride[i] = t.stride(0)
+        a.block_rows = R
+        total = B * R
+        a.mini_batch_size = int(mini_batch_size)
+        a.num_mini_batch = total // int(mini_batch_size) if num_mini_batch is None else int(num_mini_batch)     # ppo_utils.py:93
+        if perm.dtype != torch.int32 or perm.dim() != 2 or not perm.is_contiguous() or perm.device != self.device:
+            raise ValueError('fused PPO update: perm must be a contiguous int32 device tensor [opt_epochs][rows]')
+        a.opt_epochs, a.perm_stride, a.d_perm = perm.shape[0], perm.shape[1], perm.data_ptr()
+        a.use_clipped_value = int(bool(use_clipped_value))
+        a.clip_param, a.target_kl, a.entropy_coef = float(clip_param), float(target_kl), float(entropy_coef)
+        a.actor_lr, a.critic_lr, a.beta1, a.beta2, a.adam_eps = float(actor_lr), float(critic_lr), float(betas[0]), float(betas[1]), float(eps)
+        a.d_params, a.d_exp_avg, a.d_exp_avg_sq = self.params.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        a.d_adam_steps, a.d_stats = self.steps.data_ptr(), self.stats.data_ptr()
+        a.d_grad_out = grad_out.data_ptr() if grad_out is not None else None
+        if a.num_mini_batch < 1:
+            raise AssertionError('num_mini_batch is 0')            # ppo_utils.py:94
+        need = _abi.lib().scg_ppo_workspace_bytes(C.byref(a))
+        if need == 0:
+            _abi.check(_abi.SCG_EINVAL)
+        if self.workspace is None or self.workspace.numel() * 4 < need:
+            self.workspace = torch.zeros((need + 3) // 4, dtype=torch.float32, device=self.device)     # pad floats are never written: keep them 0
+        a.d_workspace, a.workspace_bytes = self.workspace.data_ptr(), self.workspace.numel() * 4
+        _abi.check(_abi.lib().scg_ppo_update(C.byref(a), torch.cuda.current_stream(self.device).cuda_stream))
+        return a.num_mini_batch

@@ -25,14 +25,14 @@ def test_config_struct_layout_matches_the_header():
     '''sizeof(scg_config) is checked by scg_create (struct_size guard); here the ctypes mirror is checked against gcc.'''
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include "scg.h"\nint main(){printf("%zu %zu %zu %zu %zu", sizeof(scg_config), sizeof(scg_disturbance),' \
-          ' sizeof(scg_step_out), sizeof(scg_rollout_out), sizeof(scg_rollout_args));return 0;}\n'
+    src = '#include <stdio.h>\n#include "scg.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu", sizeof(scg_config), sizeof(scg_disturbance),' \
+          ' sizeof(scg_step_out), sizeof(scg_rollout_out), sizeof(scg_rollout_args), sizeof(scg_ppo_args));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, 'a.c'), 'w').write(src)
         subprocess.run(['gcc', '-I', os.path.join(H.ROOT, 'include'), os.path.join(d, 'a.c'), '-o', os.path.join(d, 'a')], check=True)
         sizes = [int(x) for x in subprocess.run([os.path.join(d, 'a')], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [C.sizeof(_abi.scg_config), C.sizeof(_abi.scg_disturbance), C.sizeof(_abi.scg_step_out),
-                     C.sizeof(_abi.scg_rollout_out), C.sizeof(_abi.scg_rollout_args)]
+                     C.sizeof(_abi.scg_rollout_out), C.sizeof(_abi.scg_rollout_args), C.sizeof(_abi.scg_ppo_args)]
 
 
 def test_policy_pack_layout_agrees_between_c_and_python():
@@ -51,6 +51,21 @@ def test_policy_pack_layout_agrees_between_c_and_python():
     pol = orc.OraclePolicy.from_state_dict(ac.state_dict(), 'tanh')
     ref, _ = H.policy_blob(pol, 'cpu')
     np.testing.assert_array_equal(blob.numpy(), ref.numpy())
+
+
+def test_ppo_train_layout_is_dense_nn_linear_order():
+    '''scg_ppo_param_layout: sections in the reference's parameter order, 4-float aligned, no overlap.'''
+    from safe_control_gym_b200.engine import TRAIN_SECTIONS, ppo_train_layout
+    obs_dim, act_dim, hid = 12, 2, 64
+    L = ppo_train_layout(obs_dim, act_dim, hid)
+    sizes = [hid * obs_dim, hid, hid * hid, hid, act_dim * hid, act_dim, act_dim, hid * obs_dim, hid, hid * hid, hid, hid, 1]
+    o = 0
+    for name, n in zip(TRAIN_SECTIONS, sizes):
+        assert L[name] == o and o % 4 == 0, name
+        o += (n + 3) // 4 * 4
+        if name == 'actor.logstd':
+            assert L['critic0'] == o
+    assert L['total'] == o
 
 
 def test_no_cpu_fallback_create_fails_loudly_without_a_gpu():
