@@ -250,7 +250,7 @@ typedef struct scg_rollout_args {
     int32_t activation;        /* SCG_ACT_* */
     int32_t use_gae;           /* ppo.yaml:11 */
     int32_t deterministic;     /* 1 = act() = mean (ppo_utils.py:233-238), logp of the mean */
-    int32_t envs_per_block;    /* 0 = library default */
+    int32_t envs_per_block;    /* 0 = library default; bits 0-15 = envs per CTA, bits 16-31 = threads per CTA (0 = 8 per env) */
     double gamma, gae_lambda;
     const float* d_policy;     /* packed policy blob, layout of scg_policy_pack() */
     const float* d_eps;        /* [T][N][act_dim] standard-normal draws, or NULL -> Philox */

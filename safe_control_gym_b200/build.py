@@ -25,13 +25,15 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_cuda(force=False, prof=False, verbose=True):
-    out = os.path.join(HERE, 'libscg_b200_prof.so' if prof else 'libscg_b200.so')
+def build_cuda(force=False, prof=False, verbose=True, dev=False):
+    '''prof: -DSCG_PROF phase counters (libscg_b200_prof.so); dev: hidden-64 rollout variants only, for quick kernel experiments
+    (libscg_b200_dev.so); select either at run time with SCG_LIB_NAME.'''
+    out = os.path.join(HERE, 'libscg_b200_prof.so' if prof else 'libscg_b200_dev.so' if dev else 'libscg_b200.so')
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(ROOT, 'include', 'scg.h')]
     if not force and not _stale(out, deps):
         return out
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = ([nvcc] + NVCC_FLAGS + ['--threads', str(len(UNITS))] + (['-DSCG_PROF'] if prof else [])
+    cmd = ([nvcc] + NVCC_FLAGS + ['--threads', str(len(UNITS))] + (['-DSCG_PROF'] if prof else []) + (['-DSCG_DEV_HID64_ONLY'] if dev else [])
            + ['-I', os.path.join(ROOT, 'include'), '-o', out] + [os.path.join(CSRC, u) for u in UNITS])
     if verbose:
         print(' '.join(cmd), flush=True)
@@ -47,7 +49,7 @@ def build_oracle(force=False):
 
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
-    build_cuda(force='--force' in argv, prof='--prof' in argv)
+    build_cuda(force='--force' in argv, prof='--prof' in argv, dev='--dev' in argv)
     build_oracle(force='--force' in argv)
 
 

@@ -287,29 +287,37 @@ static int launch_rollout(scg_env* e, const RolloutParams& P, cudaStream_t s) {
 // smaller CTAs and MORE of them per SM: the serial env-step section of one CTA then overlaps the MLP phase of its neighbours.
 template <int SYS, typename R>
 static int dispatch_rollout(scg_env* e, const scg_rollout_args* a, const RolloutParams& P, cudaStream_t s) {
-    int E = a->envs_per_block;
+    int E = a->envs_per_block & 0xffff;
+    const int NTq = (a->envs_per_block >> 16) & 0xffff;   // requested threads per CTA (0 = 8 per env)
 #ifdef SCG_PROF
+    if (a->hidden_dim == 64 && E == 16 && NTq == 256) return launch_rollout<SYS, R, 64, 16, 256>(e, P, s);
     if (a->hidden_dim == 64 && (E == 0 || E == 32)) return launch_rollout<SYS, R, 64, 32, 256>(e, P, s);
     if (a->hidden_dim == 64 && E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, s);
     return fail(e, SCG_EINVAL, "SCG_PROF build: only hidden 64 / E 32 or 16");
 #else
     switch (a->hidden_dim) {
+#ifndef SCG_DEV_HID64_ONLY
         case 32:
             if (E == 0) E = e->cfg.num_envs >= 16384 ? 16 : 32;
             if (E == 32) return launch_rollout<SYS, R, 32, 32, 256>(e, P, s);
             if (E == 16) return launch_rollout<SYS, R, 32, 16, 128>(e, P, s);
             break;
+#endif
         case 64:
             if (E == 0) E = e->cfg.num_envs >= 16384 ? 16 : 32;   // many CTAs per SM at large N, one 8-warp CTA per SM otherwise
+            if (E == 16 && NTq == 256) return launch_rollout<SYS, R, 64, 16, 256>(e, P, s);
+            if (E == 8 && NTq == 128) return launch_rollout<SYS, R, 64, 8, 128>(e, P, s);
             if (E == 32) return launch_rollout<SYS, R, 64, 32, 256>(e, P, s);
             if (E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, s);
             if (E == 8) return launch_rollout<SYS, R, 64, 8, 64>(e, P, s);
             break;
+#ifndef SCG_DEV_HID64_ONLY
         case 128:
             if (E == 0) E = 16;
             if (E == 16) return launch_rollout<SYS, R, 128, 16, 256>(e, P, s);
             if (E == 8) return launch_rollout<SYS, R, 128, 8, 128>(e, P, s);
             break;
+#endif
         default: return fail(e, SCG_EINVAL, "scg_rollout: hidden_dim must be 32, 64 or 128");
     }
     return fail(e, SCG_EINVAL, "scg_rollout: unsupported envs_per_block for this hidden_dim");
@@ -340,6 +348,7 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
     if (!d_prof) cudaMalloc((void**)&d_prof, (16 + 2048) * sizeof(long long));
     cudaMemset(d_prof, 0, (16 + 2048) * sizeof(long long));
     P.prof = d_prof;
+    { long long z[64] = {0}; cudaMemcpyToSymbol(scg_ticks, z, sizeof(z)); }
 #endif
     cudaStream_t s = (cudaStream_t)stream;
     const bool dbl = e->cfg.precision == SCG_PREC_F64;
@@ -357,6 +366,12 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
         fprintf(stderr, "[SCG_PROF] CTA0 cycles per step (T=%d):", a->T);
         for (int i = 0; i < 8; ++i) if (nm[i][0] != '-') fprintf(stderr, " %s=%.0f", nm[i], i == 7 ? (double)hp[i] : (double)hp[i] / a->T);
         fprintf(stderr, "\n");
+        {
+            long long tk[64]; cudaMemcpyFromSymbol(tk, scg_ticks, sizeof(tk));
+            fprintf(stderr, "[SCG_PROF] ticks/step:");
+            for (int i = 0; i < 25; ++i) fprintf(stderr, " %d:%.0f", i, (double)tk[i] / a->T);
+            fprintf(stderr, "\n");
+        }
         {
             std::vector<long long> ct(2048); cudaMemcpy(ct.data(), d_prof + 16, 2048 * sizeof(long long), cudaMemcpyDeviceToHost);
             int G = (e->cfg.num_envs + 31) / 32; if (G > 1024) G = 1024;

@@ -25,6 +25,16 @@
 
 #define SCG_PI 3.14159265358979323846
 
+// -DSCG_PROF developer builds: fine-grained cycle accounting of the owner warp's critical path (lane 0 of the last warp of CTA 0).
+// SCG_TK(i) adds the cycles since the previous tick to bucket i; each tick costs ~40 cycles itself.
+#ifdef SCG_PROF
+static __device__ long long scg_ticks[64];
+static __shared__ long long scg_tk_last;
+#define SCG_TK(i) do { if (threadIdx.x == blockDim.x - 32 && blockIdx.x == 0) { const long long c_ = clock64(); scg_ticks[i] += c_ - scg_tk_last; scg_tk_last = c_; } } while (0)
+#else
+#define SCG_TK(i) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // math wrappers
 // ---------------------------------------------------------------------------------------------
@@ -448,17 +458,20 @@ template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
         R fx = (R)0, fz = -h->gravity;                                 // gravity enters as the force m g
         if (has_dist) { fx += fd[0] * inv_m; fz += fd[1] * inv_m; }
         R x = e.ps[0], vx = e.ps[1], z = e.ps[2], vz = e.ps[3], th = e.ps[4], om = e.ps[5];
+        SCG_TK(3);
         R st, ct; Mth<R>::sincos_(th, &st, &ct);
         const R adt = alpha * dt, eps = adt * dt;
         R sd, cd, se, ce;
         Mth<R>::sincos_(om * dt, &sd, &cd);        // delta_0 = omega dt  (becomes delta_1 after the first eps rotation)
         Mth<R>::sincos_(eps, &se, &ce);
+        SCG_TK(4);
         for (int s = 0; s < h->steps; ++s) {
             vx += (st * tm + fx) * dt; vz += (ct * tm + fz) * dt; om += adt;
             x += vx * dt; z += vz * dt; th += om * dt;
             const R sd2 = sd * ce + cd * se; cd = cd * ce - sd * se; sd = sd2;        // delta += eps
             const R st2 = st * cd + ct * sd; ct = ct * cd - st * sd; st = st2;        // theta += delta
         }
+        SCG_TK(5);
         e.ps[0] = x; e.ps[1] = vx; e.ps[2] = z; e.ps[3] = vz; e.ps[4] = th; e.ps[5] = om;
     }
     static __device__ __forceinline__ void state(const EnvRegs<SCG_SYS_QUAD2D, R>& e, R* s) {
@@ -730,11 +743,6 @@ struct StepInfo {
     int done, truncated, cviol, out_of_bounds, goal_reached, current_step;
 };
 
-#ifdef SCG_PROF
-#define SCG_TICK(i) do { if (prof_t) prof_t[i] = clock64(); } while (0)
-#else
-#define SCG_TICK(i) do { } while (0)
-#endif
 
 // ---------------------------------------------------------------------------------------------
 // One control step, split into phases so that the fused collector can spread them over warps:
@@ -785,6 +793,7 @@ __device__ __forceinline__ void env_physics(const HotCfg<R>* h, EnvRegs<SYS, R>&
         Physics<SYS, R>::advance(h, e, cx.clipped, cx.fd, cx.has_dyn);
     } else {
         R f[4]; quad_motor_forces<SYS, R>(h, cx.clipped, f);
+        SCG_TK(2);
         Physics<SYS, R>::advance(h, e, f, cx.fd, cx.has_dyn);
     }
     Physics<SYS, R>::state(e, state);

@@ -357,15 +357,22 @@ __device__ __forceinline__ void net_forward(int tl, int net, int n_out, int w3_r
         }
     };
     // ---- layer 1: [E x obs] . [obs x H]      (W1P [kp][2H][2], this net's units start at net*H)
+    SCG_TK(14);
     init_acc(s_blob + L.b1 + net * HID + ul0);
     gemm(s_in + eg * 4, 2 * EG * 4, s_blob + L.w1t + (net * HID + ul0) * 2, 2 * HID * 2, obs_dim >> 1);
+    SCG_TK(15);
     finish(s_h1n);
+    SCG_TK(16);
     group_sync<NTN, BAR>();
+    SCG_TK(17);
     // ---- layer 2: [E x H] . [H x H]          (W2P [net][kp][H][2])
     init_acc(s_blob + L.b2 + net * HID + ul0);
     gemm(s_h1n + eg * 4, 2 * EG * 4, s_blob + L.w2t + net * HID * HID + ul0 * 2, HID * 2, HID / 2);
+    SCG_TK(18);
     finish(s_h2n);
+    SCG_TK(19);
     group_sync<NTN, BAR>();
+    SCG_TK(20);
     // ---- layer 3: n_out dot products per env, each split over KS lane groups, partial sums through shared memory
     {
         constexpr int NG = NTN / E;                        // lane groups of E lanes
@@ -393,7 +400,9 @@ __device__ __forceinline__ void net_forward(int tl, int net, int n_out, int w3_r
             s_outn[oo * E + ee] = v;
         }
     }
+    SCG_TK(21);
     group_sync<NTN, BAR>();
+    SCG_TK(22);
 }
 
 // Classic schedule: the lower half of the CTA computes the actor, the upper half the critic, in lockstep.
@@ -414,8 +423,13 @@ __device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const
 #define PROF_T(v) do { } while (0)
 #endif
 
+// CTAs per SM the register allocation is capped for: the 16-thread-per-env variants (E=16 x 256 threads, E=8 x 128 threads) halve
+// the per-step MLP latency of a CTA and rely on TWO (or more) co-resident CTAs per SM to fill the machine.
+__host__ __device__ constexpr int rollout_min_blocks(int HID, int E, int NT) {
+    return (NT / E >= 16 && HID <= 64) ? (NT == 256 ? 2 : 3) : 1;
+}
 template <int SYS, typename R, int HID, int E, int NT>
-__global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams P) {
+__global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_kernel(DevTables T, RolloutParams P) {
     constexpr int NX = SysDims<SYS>::NX, A = SysDims<SYS>::NU;
     constexpr int NZ = NX + 2 * A;             // z scratch rows: state, noisy action, clipped action
     // With >= 4 warps the env-step section is split: warp 0 = owners (sampling, action map, physics, done, finalize, reset),
@@ -508,6 +522,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
     const int ow_k = tid % od, ow_e = tid / od, ow_dk = NT % od, ow_de = NT / od;
 #ifdef SCG_PROF
     const long long cta_t0 = clock64();
+    if (tid == NT - 32) scg_tk_last = cta_t0;
     long long pacc[8]; for (int i = 0; i < 8; ++i) pacc[i] = 0;
 #define PROF_ON (P.prof != nullptr && tid == NT - 32)
 #endif
@@ -555,6 +570,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
             }
         }
         PROF_T(k1);
+        SCG_TK(13);
         if constexpr (DECOUPLED) net_forward<HID, E, NT, 0>(tid, 0, A, 0, s_blob, L, s_oc, s_h1, s_h2, s_part, s_out, od, P.activation);
         else mlp_forward<HID, E, NT, A>(s_blob, L, s_oc, s_h1, s_h2, s_part, s_out, od, P.activation);
         PROF_T(k2);
@@ -563,6 +579,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
         // warps (SPLIT) while the owners evaluate termination; owners finalize, emit the record and auto-reset.
         int trunc = 0;
         if (role == 0) {
+            SCG_TK(0);
             float act[A], logp = 0.f, val = 0.f;
             R state[NX], rew = (R)0, mse = (R)0;
             StepCtx<SYS, R> cx; NoiseSrc<R> ns; StepInfo info;
@@ -583,7 +600,9 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
                 const double* nrow = (!h->philox && T.noise_table && T.D > 0)
                                          ? T.noise_table + ((size_t)((P.noise_cursor + t) % T.Tn) * N + n) * T.D : nullptr;
                 env_pre<SYS, R>(T, h, n, e, action, nrow, cx, ns);
+                SCG_TK(1);
                 env_physics<SYS, R>(h, e, cx, state);
+                SCG_TK(6);
                 // publish z = [state; noisy action; clipped action] and the step counter for the helpers / the constraint rows
 #pragma unroll
                 for (int k = 0; k < NX; ++k) s_z[k * E + ol] = (double)state[k];
@@ -592,10 +611,13 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
                 s_cstep[ol] = e.ctrl_step;
             }
             PROF_T(k3);
+            SCG_TK(7);
             if (SPLIT) {
                 named_bar_arrive(1, 128);                                  // helpers may start
                 if (live) done = env_done<SYS, R, R>(h, s_xg, state, goal_reached, oob);
+                SCG_TK(8);
                 named_bar_sync(2, 128);                                    // helpers are done
+                SCG_TK(9);
                 if (live) { rew = s_rew[ol]; mse = s_mse[ol]; cviol = s_cviol[ol]; }
             } else if (live) {
                 env_reward_mse<SYS, R, R>(h, s_xg, state, cx.noisy, cx.clipped, e.ctrl_step, rew, mse);
@@ -607,6 +629,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
                 const int step_before = e.ctrl_step;
                 e.ctrl_step += 1; e.total_steps += 1;
                 env_finalize<R>(h, e.ctrl_step, cviol, rew, done, truncated);
+                SCG_TK(10);
                 info.done = done; info.truncated = truncated; info.cviol = cviol;
                 e.ep_ret += (float)rew; e.ep_len += 1.f; e.ep_cv += (float)cviol;
                 const bool helper_obs = SPLIT && !obs_noise;               // the helper already wrote the continuing observation
@@ -630,6 +653,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
                 } else if (!helper_obs) {
                     make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_on, ol});
                 }
+                SCG_TK(11);
                 const size_t tn = tn0 + ol;
                 if (A == 2) *reinterpret_cast<float2*>(P.out.d_act + tn * A) = make_float2(act[0], act[1 % A]);
                 else if (A == 4) *reinterpret_cast<float4*>(P.out.d_act + tn * A) = make_float4(act[0], act[1 % A], act[2 % A], act[3 % A]);
@@ -642,6 +666,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
                 if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
                 if (!trunc) P.out.d_terminal_v[tn] = 0.f;
             }
+            SCG_TK(12);
 #ifdef SCG_PROF
             if (PROF_ON) { long long k5 = clock64(); pacc[0] += k1 - k0; pacc[1] += k2 - k1; pacc[2] += k3 - k2; pacc[3] += k4 - k3; pacc[4] += k5 - k4; }
 #endif
@@ -698,6 +723,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
             if (tl < E && n0 + tl < N) P.out.d_v[tn0 + tl] = s_out[A * E + tl];
           }
         }
+        SCG_TK(23);
         PROF_T(k6);
         // (c) critic on the terminal observation of time-limit truncated envs (rare, CTA-uniform branch).
         //     s_tobs aliases s_h2: written after layer 3 consumed h2, read by layer 1 of this pass, overwritten by its layer 2.
@@ -712,6 +738,7 @@ __global__ void __launch_bounds__(NT) rollout_kernel(DevTables T, RolloutParams 
             __syncthreads();
         }
         cur ^= 1;
+        SCG_TK(24);
     }
     float* s_ol = s_obs + cur * OBS_TILE;                  // the observation after the last step
 #ifdef SCG_PROF
