@@ -271,7 +271,7 @@ int scg_step(scg_env* e, const float* d_act, const double* d_act_f64, const scg_
 extern "C++" {
 template <int SYS, typename R, int HID, int E, int NT>
 static int launch_rollout(scg_env* e, const RolloutParams& P, cudaStream_t s) {
-    const RolloutSmem<HID, E> S(e->obs_dim, e->nu, e->L * e->nx * (int)(sizeof(R) / 4));
+    const RolloutSmem<HID, E> S(e->obs_dim, e->nu, e->L * e->nx * (int)(sizeof(R) / 4), NT / 64);
     const size_t smem = (size_t)S.total_floats * sizeof(float);
     auto kern = rollout_kernel<SYS, R, HID, E, NT>;
     CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -290,7 +290,6 @@ static int dispatch_rollout(scg_env* e, const scg_rollout_args* a, const Rollout
     int E = a->envs_per_block & 0xffff;
     const int NTq = (a->envs_per_block >> 16) & 0xffff;   // requested threads per CTA (0 = 8 per env)
 #ifdef SCG_PROF
-    if (a->hidden_dim == 64 && E == 16 && NTq == 256) return launch_rollout<SYS, R, 64, 16, 256>(e, P, s);
     if (a->hidden_dim == 64 && (E == 0 || E == 32)) return launch_rollout<SYS, R, 64, 32, 256>(e, P, s);
     if (a->hidden_dim == 64 && E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, s);
     return fail(e, SCG_EINVAL, "SCG_PROF build: only hidden 64 / E 32 or 16");
@@ -305,8 +304,10 @@ static int dispatch_rollout(scg_env* e, const scg_rollout_args* a, const Rollout
 #endif
         case 64:
             if (E == 0) E = e->cfg.num_envs >= 16384 ? 16 : 32;   // many CTAs per SM at large N, one 8-warp CTA per SM otherwise
+#ifdef SCG_DEV_HID64_ONLY   // 16 threads per env, two CTAs per SM: measured slower than the 8-thread-per-env variants (round 1)
             if (E == 16 && NTq == 256) return launch_rollout<SYS, R, 64, 16, 256>(e, P, s);
             if (E == 8 && NTq == 128) return launch_rollout<SYS, R, 64, 8, 128>(e, P, s);
+#endif
             if (E == 32) return launch_rollout<SYS, R, 64, 32, 256>(e, P, s);
             if (E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, s);
             if (E == 8) return launch_rollout<SYS, R, 64, 8, 64>(e, P, s);

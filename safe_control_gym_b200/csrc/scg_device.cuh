@@ -177,12 +177,17 @@ struct DevTables {
 template <int SYS, typename R> struct EnvRegs {
     R ps[SysDims<SYS>::PS];
     R inertial[SCG_MAX_INERTIAL];
+    R inv[2];            // reciprocals of the inertial properties the integrator divides by (2D quadrotor: 1/M, 1/Iyy)
     int ctrl_step;
     int episode;
     uint32_t total_steps;
     float ep_ret, ep_len, ep_cv;
 };
 
+template <int SYS, typename R> __device__ __forceinline__ void env_derived(EnvRegs<SYS, R>& e) {
+    e.inv[0] = (R)1 / e.inertial[0];
+    e.inv[1] = (SYS == SCG_SYS_QUAD2D) ? (R)1 / e.inertial[2] : (R)0;
+}
 template <int SYS, typename R>
 __device__ __forceinline__ void env_load(const DevTables& T, int n, EnvRegs<SYS, R>& e) {
     const int N = T.N;
@@ -190,6 +195,7 @@ __device__ __forceinline__ void env_load(const DevTables& T, int n, EnvRegs<SYS,
     for (int j = 0; j < SysDims<SYS>::PS; ++j) e.ps[j] = (R)T.st.phys[(size_t)j * N + n];
 #pragma unroll
     for (int j = 0; j < SCG_MAX_INERTIAL; ++j) e.inertial[j] = (R)T.st.inertial[(size_t)j * N + n];
+    env_derived<SYS, R>(e);
     e.ctrl_step = T.st.ctrl_step[n]; e.episode = T.st.episode[n]; e.total_steps = T.st.total_steps[n];
     e.ep_ret = T.st.ep_acc[n]; e.ep_len = T.st.ep_acc[N + n]; e.ep_cv = T.st.ep_acc[2 * N + n];
 }
@@ -450,10 +456,10 @@ template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
     // sub-step (3 sincos per control step instead of one per sub-step).
     static __device__ __forceinline__ void advance(const HotCfg<R>* h, EnvRegs<SCG_SYS_QUAD2D, R>& e, const R f[4], const R* fd, bool has_dist) {
         const R dt = h->dt;
-        const R inv_m = (R)1 / e.inertial[0];
+        const R inv_m = e.inv[0];                                      // 1/M, 1/Iyy: per-episode constants (env_load / env_reset)
         const R thrust = f[0] + f[1] + f[2] + f[3];
         const R tau_y = h->arm * (-f[0] + f[1] + f[2] - f[3]);         // r x F with the prop offsets of cf2x.urdf:42-78
-        const R alpha = tau_y / e.inertial[2];
+        const R alpha = tau_y * e.inv[1];
         const R tm = thrust * inv_m;
         R fx = (R)0, fz = -h->gravity;                                 // gravity enters as the force m g
         if (has_dist) { fx += fd[0] * inv_m; fz += fd[1] * inv_m; }
@@ -462,11 +468,21 @@ template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
         R st, ct; Mth<R>::sincos_(th, &st, &ct);
         const R adt = alpha * dt, eps = adt * dt;
         R sd, cd, se, ce;
-        Mth<R>::sincos_(om * dt, &sd, &cd);        // delta_0 = omega dt  (becomes delta_1 after the first eps rotation)
-        Mth<R>::sincos_(eps, &se, &ce);
+        // delta_0 = omega dt (becomes delta_1 after the first eps rotation) and eps = alpha dt^2 are small: series, no range reduction
+        const R d0 = om * dt;
+        if (Mth<R>::abs_(d0) <= (R)SCG_SMALL_ANGLE && Mth<R>::abs_(eps) <= (R)SCG_SMALL_ANGLE) {
+            sincos_small<R>(d0, &sd, &cd);
+            sincos_small<R>(eps, &se, &ce);
+        } else {
+            Mth<R>::sincos_(d0, &sd, &cd);
+            Mth<R>::sincos_(eps, &se, &ce);
+        }
         SCG_TK(4);
-        for (int s = 0; s < h->steps; ++s) {
-            vx += (st * tm + fx) * dt; vz += (ct * tm + fz) * dt; om += adt;
+        const R tmdt = tm * dt, fxdt = fx * dt, fzdt = fz * dt;
+        const int steps = h->steps;
+#pragma unroll 4
+        for (int s = 0; s < steps; ++s) {
+            vx += st * tmdt + fxdt; vz += ct * tmdt + fzdt; om += adt;
             x += vx * dt; z += vz * dt; th += om * dt;
             const R sd2 = sd * ce + cd * se; cd = cd * ce - sd * se; sd = sd2;        // delta += eps
             const R st2 = st * cd + ct * sd; ct = ct * cd - st * sd; st = st2;        // theta += delta
@@ -723,6 +739,7 @@ __device__ __forceinline__ void env_reset(const DevTables& T, const HotCfg<R>* h
     }
 #pragma unroll
     for (int j = 0; j < SCG_MAX_INERTIAL; ++j) e.inertial[j] = (R)inr[j];
+    env_derived<SYS, R>(e);
     R initr[NX];
 #pragma unroll
     for (int j = 0; j < NX; ++j) initr[j] = (R)init[j];

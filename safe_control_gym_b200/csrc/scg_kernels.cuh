@@ -86,30 +86,30 @@ __device__ __forceinline__ float tanh_fast(float x) {
     t = copysignf(t, x);
     return ax < 0.3f ? p : t;
 }
-// four tanh at once: 1/(e_i + 1) for four values from ONE reciprocal of their product (MUFU.RCP is the scarce pipe here:
-// 2 MUFU per tanh -> 1.25).  |x| is clamped to 10 so that the product of four (e^{2|x|} + 1) stays below 2^127.
+// two tanh at once: odd rational minimax x P(x^2) / Q(x^2) (degrees 13 / 6) on |x| <= 7.905 (tanh rounds to +-1 in float beyond),
+// |rel err| < 5e-7.  Horner steps are packed FP32 ops (FFMA2 / FMUL2: one instruction per step for both values), one MUFU.RCP per
+// value, no exponential: 11 instructions per value against ~28 for the exp-based form.
+__device__ __forceinline__ float2 tanh_rat2(float2 v) {
+    const float lim = 7.90531110763549805f;
+    const float2 x = make_float2(fminf(fmaxf(v.x, -lim), lim), fminf(fmaxf(v.y, -lim), lim));
+    const float2 x2 = __fmul2_rn(x, x);
+#define SCG_C2(c) make_float2(c, c)
+    float2 p = __ffma2_rn(x2, SCG_C2(-2.76076847742355e-16f), SCG_C2(2.00018790482477e-13f));
+    p = __ffma2_rn(x2, p, SCG_C2(-8.60467152213735e-11f));
+    p = __ffma2_rn(x2, p, SCG_C2(5.12229709037114e-08f));
+    p = __ffma2_rn(x2, p, SCG_C2(1.48572235717979e-05f));
+    p = __ffma2_rn(x2, p, SCG_C2(6.37261928875436e-04f));
+    p = __ffma2_rn(x2, p, SCG_C2(4.89352455891786e-03f));
+    p = __fmul2_rn(p, x);
+    float2 q = __ffma2_rn(x2, SCG_C2(1.19825839466702e-06f), SCG_C2(1.18534705686654e-04f));
+    q = __ffma2_rn(x2, q, SCG_C2(2.26843463243900e-03f));
+    q = __ffma2_rn(x2, q, SCG_C2(4.89352518554385e-03f));
+#undef SCG_C2
+    return make_float2(__fdividef(p.x, q.x), __fdividef(p.y, q.y));
+}
 __device__ __forceinline__ void tanh_fast4(float& x0, float& x1, float& x2, float& x3) {
-    float x[4] = {x0, x1, x2, x3}, q[4], p[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float ax = fminf(fabsf(x[i]), 10.0f);
-        const float x2_ = x[i] * x[i];
-        float pp = fmaf(x2_, 0.021869488536155203f, -0.053968253968253971f);
-        pp = fmaf(x2_, pp, 0.13333333333333333f);
-        pp = fmaf(x2_, pp, -0.33333333333333333f);
-        p[i] = fmaf(x2_ * x[i], pp, x[i]);
-        q[i] = exp2f(ax * 2.8853900817779268f) + 1.0f;
-    }
-    const float q01 = q[0] * q[1], q23 = q[2] * q[3];
-    const float r = __fdividef(1.0f, q01 * q23);           // 1 / (q0 q1 q2 q3)
-    const float r01 = r * q23, r23 = r * q01;              // 1/(q0 q1), 1/(q2 q3)
-    const float inv[4] = {r01 * q[1], r01 * q[0], r23 * q[3], r23 * q[2]};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float t = copysignf(fmaf(-2.0f, inv[i], 1.0f), x[i]);
-        x[i] = fabsf(x[i]) < 0.3f ? p[i] : t;
-    }
-    x0 = x[0]; x1 = x[1]; x2 = x[2]; x3 = x[3];
+    const float2 a = tanh_rat2(make_float2(x0, x1)), b = tanh_rat2(make_float2(x2, x3));
+    x0 = a.x; x1 = a.y; x2 = b.x; x3 = b.y;
 }
 template <int ACT> __device__ __forceinline__ float hidden_act(float x) {
     if (ACT == SCG_ACT_TANH) return tanh_fast(x);
@@ -267,44 +267,49 @@ struct RolloutParams {
 
 // shared memory carve-up (floats), all offsets multiples of 4
 template <int HID, int E> struct RolloutSmem {
-    int blob, obs, tobs, h1, h2, out, xg, total_floats;
-    // xg_floats: size of the shared X_GOAL copy in float units (L * nx * sizeof(R) / 4)
-    __host__ __device__ RolloutSmem(int obs_dim, int act_dim, int xg_floats) {
+    int blob, obs, tobs, h1, out, xg, total_floats;
+    // xg_floats: size of the shared X_GOAL copy in float units (L * nx * sizeof(R) / 4); nw: GEMM warps per network
+    __host__ __device__ RolloutSmem(int obs_dim, int act_dim, int xg_floats, int nw) {
         BlobLayout L = blob_layout(obs_dim, act_dim, HID);
         blob = 0;
         obs = blob + L.total;
-        h1 = obs + 2 * obs_dim * E;          // two observation tiles (ping-pong): the decoupled critic still reads tile t while tile t+1 is built
-        h2 = h1 + 2 * HID * E;
-        tobs = h2;                       // aliases h2: see rollout_kernel (c)
-        out = h2 + (2 * HID * E > obs_dim * E ? 2 * HID * E : obs_dim * E);
-        xg = out + pad4i((act_dim + 1) * E);
+        h1 = obs + 2 * obs_dim * E;          // two observation tiles (ping-pong): tile t+1 is built while tile t is still the policy input
+        tobs = h1 + 2 * HID * E;             // terminal observations of time-limit truncated envs
+        out = tobs + obs_dim * E;
+        xg = out + pad4i(nw * (act_dim + 1) * E);   // per-warp partial sums of the output layer
         total_floats = xg + pad4i(xg_floats);
     }
 };
 
-// named barriers: 1, 2 = owner warp <-> helper warps of the env-step section, 3 = the critic's thread group
+// named barriers: 1, 2 = owner warp <-> helper warps of the env-step section
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-template <int NTN, int BAR> __device__ __forceinline__ void group_sync() {
-    if (BAR == 0) __syncthreads(); else named_bar_sync(BAR, NTN);
-}
 
 // Forward of ONE network (net 0 = actor with n_out = A outputs, net 1 = critic with 1 output) for the CTA's E envs by a group
-// of NTN threads (tl = index inside the group; BAR = 0: the group is the whole CTA or all groups run in lockstep -> __syncthreads,
-// otherwise the group's named barrier).
-//   s_in  : pair-swizzled observation tile (tile_idx)          s_h1n / s_h2n : this net's hidden tiles
-//   s_part: scratch [NTN/E][E] floats                           s_outn : [n_out][E]
-// Layers 1 and 2 are register-tiled FP32 GEMMs (4 envs x TU units per thread) out of shared memory with packed FFMA2;
-// layer 3 splits each dot product over the idle lane groups.
-template <int HID, int E, int NTN, int BAR>
+// of NTN threads (tl = index inside the group); both groups run in lockstep (__syncthreads).
+//   s_in  : pair-swizzled observation tile (tile_idx)          s_h1n : this net's hidden tile
+//   s_outp: [NTN/32 warps][A+1 outputs][E] per-warp partial sums of the output layer (see mlp_out)
+// Layers 1 and 2 are register-tiled FP32 GEMMs (4 envs x TU units per thread) out of shared memory with packed FFMA2.
+// Layer 3 is fused into the epilogue of layer 2: every thread multiplies its 4 x TU activations with the matching slice of the
+// output rows, the unit groups of a warp are summed with shuffles and the per-warp partial sums go to shared memory -- the second
+// hidden tile is never stored and the whole forward needs two barriers.
+template <int HID, int E, int NTN, int AMAX>
 __device__ __forceinline__ void net_forward(int tl, int net, int n_out, int w3_row0, const float* __restrict__ s_blob, const BlobLayout L,
-                                            const float* __restrict__ s_in, float* __restrict__ s_h1n, float* __restrict__ s_h2n,
-                                            float* __restrict__ s_part, float* __restrict__ s_outn, int obs_dim, int act) {
+                                            const float* __restrict__ s_in, float* __restrict__ s_h1n, float* __restrict__ s_outp,
+                                            int obs_dim, int act) {
     constexpr int EG = E / 4;              // env groups
     constexpr int UG = NTN / EG;           // unit groups
     constexpr int TU = HID / UG;           // units per thread
     static_assert(TU == 2 || TU == 4, "unsupported tile");
-    const int eg = tl % EG, ug = tl / EG;
+    // lane -> (env group, unit group).  Measured on B200 (tools/ubench/lds_patterns.cu): an LDS.128 takes 2 shared-memory wavefronts
+    // when every quad of 4 adjacent lanes touches at most 2 distinct 16-byte chunks and 4 otherwise.  Lane bit 0 therefore selects
+    // the unit group, bits 1.. the env group, the remaining high bits the unit group again: both the activation and the weight
+    // loads of the GEMM loops are on the 2-wavefront path.
+    constexpr int EGB = (EG == 16) ? 4 : (EG == 8) ? 3 : (EG == 4) ? 2 : (EG == 2) ? 1 : 0;
+    static_assert((1 << EGB) == EG && EG <= 16, "E must be 4, 8, 16, 32 or 64");
+    const int ln = tl & 31;
+    const int eg = (ln >> 1) & (EG - 1);
+    const int ug = (tl >> 5) * (32 / EG) + ((ln & 1) | ((ln >> (1 + EGB)) << 1));
     const int ul0 = ug * TU;
 
     float2 acc[4][TU];   // (even-k, odd-k) partial sums of env i x unit j
@@ -342,79 +347,86 @@ __device__ __forceinline__ void net_forward(int tl, int net, int n_out, int w3_r
 #pragma unroll
         for (int j = 0; j < TU; ++j) { const float b = bias[j]; acc[0][j] = make_float2(b, 0.f); acc[1][j] = acc[0][j]; acc[2][j] = acc[0][j]; acc[3][j] = acc[0][j]; }
     };
-    auto finish = [&](float* __restrict__ dst) {   // reduce pairs, activate, store pair-swizzled as the next layer's input
-        float h[4][TU];
+    float h[4][TU];
+    auto activate = [&]() {                        // reduce the (even, odd) pairs and apply the hidden activation
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < TU; ++j) h[i][j] = acc[i][j].x + acc[i][j].y;
         apply_hidden_act<TU>(h, act);
-#pragma unroll
-        for (int j = 0; j < TU; j += 2) {
-            float* d = dst + ((((ul0 + j) >> 1) * 2) * EG + eg) * 4;
-            *reinterpret_cast<float4*>(d) = make_float4(h[0][j], h[0][j + 1], h[1][j], h[1][j + 1]);
-            *reinterpret_cast<float4*>(d + EG * 4) = make_float4(h[2][j], h[2][j + 1], h[3][j], h[3][j + 1]);
-        }
     };
     // ---- layer 1: [E x obs] . [obs x H]      (W1P [kp][2H][2], this net's units start at net*H)
     SCG_TK(14);
     init_acc(s_blob + L.b1 + net * HID + ul0);
     gemm(s_in + eg * 4, 2 * EG * 4, s_blob + L.w1t + (net * HID + ul0) * 2, 2 * HID * 2, obs_dim >> 1);
     SCG_TK(15);
-    finish(s_h1n);
+    activate();
+#pragma unroll
+    for (int j = 0; j < TU; j += 2) {              // store pair-swizzled as the input of layer 2
+        float* d = s_h1n + ((((ul0 + j) >> 1) * 2) * EG + eg) * 4;
+        *reinterpret_cast<float4*>(d) = make_float4(h[0][j], h[0][j + 1], h[1][j], h[1][j + 1]);
+        *reinterpret_cast<float4*>(d + EG * 4) = make_float4(h[2][j], h[2][j + 1], h[3][j], h[3][j + 1]);
+    }
     SCG_TK(16);
-    group_sync<NTN, BAR>();
+    __syncthreads();
     SCG_TK(17);
     // ---- layer 2: [E x H] . [H x H]          (W2P [net][kp][H][2])
     init_acc(s_blob + L.b2 + net * HID + ul0);
     gemm(s_h1n + eg * 4, 2 * EG * 4, s_blob + L.w2t + net * HID * HID + ul0 * 2, HID * 2, HID / 2);
     SCG_TK(18);
-    finish(s_h2n);
+    activate();
     SCG_TK(19);
-    group_sync<NTN, BAR>();
-    SCG_TK(20);
-    // ---- layer 3: n_out dot products per env, each split over KS lane groups, partial sums through shared memory
+    // ---- layer 3 on the register tile: partial dot products over this thread's TU units, summed over the warp's unit groups
     {
-        constexpr int NG = NTN / E;                        // lane groups of E lanes
-        const int g = tl / E, e = tl % E;
-        const int ks_n = NG / n_out;                       // K-slices per output (>= 1)
-        const int o = g / ks_n, ks = g % ks_n;
-        if (o < n_out) {
-            const int kp0 = (HID / 2) * ks / ks_n, kp1 = (HID / 2) * (ks + 1) / ks_n;
-            const float* w = s_blob + L.w3 + (w3_row0 + o) * HID;
-            const float* hh = s_h2n + ((((e >> 1) & 1) * EG + (e >> 2)) << 2) + ((e & 1) << 1);
-            float2 s0 = make_float2(ks == 0 ? s_blob[L.b3 + w3_row0 + o] : 0.f, 0.f);
-#pragma unroll 4
-            for (int kp = kp0; kp < kp1; ++kp) {
-                const float2 wv = *reinterpret_cast<const float2*>(w + 2 * kp);
-                const float2 hv = *reinterpret_cast<const float2*>(hh + kp * (2 * EG * 4));
-                s0 = __ffma2_rn(hv, wv, s0);
+        float part[AMAX][4];
+#pragma unroll
+        for (int o = 0; o < AMAX; ++o) {
+            if (o < n_out) {                       // warp-uniform
+                const float* w3 = s_blob + L.w3 + (w3_row0 + o) * HID + ul0;
+                float w[TU];
+                if (TU == 4) { const float4 t = *reinterpret_cast<const float4*>(w3); w[0] = t.x; w[1] = t.y; w[2 % TU] = t.z; w[3 % TU] = t.w; }
+                else { const float2 t = *reinterpret_cast<const float2*>(w3); w[0] = t.x; w[1] = t.y; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float v = h[i][0] * w[0];
+#pragma unroll
+                    for (int j = 1; j < TU; ++j) v = fmaf(h[i][j], w[j], v);
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+#pragma unroll
+                    for (int b = 1 + EGB; b < 5; ++b) v += __shfl_xor_sync(0xffffffffu, v, 1 << b);
+                    part[o][i] = v;
+                }
             }
-            s_part[g * E + e] = s0.x + s0.y;
         }
-        group_sync<NTN, BAR>();
-        if (tl < n_out * E) {
-            const int oo = tl / E, ee = tl % E;
-            float v = 0.f;
-            for (int k = 0; k < ks_n; ++k) v += s_part[(oo * ks_n + k) * E + ee];
-            s_outn[oo * E + ee] = v;
+        if ((ln & 1) == 0 && (ln >> (1 + EGB)) == 0) {     // one lane per env group holds the warp's sums
+#pragma unroll
+            for (int o = 0; o < AMAX; ++o)
+                if (o < n_out)
+                    *reinterpret_cast<float4*>(s_outp + ((tl >> 5) * (AMAX + 1) + w3_row0 + o) * E + eg * 4) = make_float4(part[o][0], part[o][1], part[o][2], part[o][3]);
         }
     }
     SCG_TK(21);
-    group_sync<NTN, BAR>();
+    __syncthreads();
     SCG_TK(22);
 }
 
-// Classic schedule: the lower half of the CTA computes the actor, the upper half the critic, in lockstep.
-//   out : s_out [A+1][E]  (A action means, then the value)
+// The lower half of the CTA computes the actor, the upper half the critic, in lockstep.
+//   s_outp : [NT/64 warps][A+1][E] partial sums; read the outputs with mlp_out()
 template <int HID, int E, int NT, int A>
 __device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const BlobLayout L, const float* __restrict__ s_in, float* __restrict__ s_h1,
-                                         float* __restrict__ s_h2, float* __restrict__ s_part, float* __restrict__ s_out, int obs_dim, int act) {
+                                         float* __restrict__ s_outp, int obs_dim, int act) {
     constexpr int NTN = NT / 2;
     constexpr int NETSZ = (HID / 2) * (2 * (E / 4) * 4);       // floats of one net's hidden tile
     const int net = threadIdx.x / NTN, tl = threadIdx.x % NTN;
-    net_forward<HID, E, NTN, 0>(tl, net, net ? 1 : A, net ? A : 0, s_blob, L, s_in, s_h1 + net * NETSZ, s_h2 + net * NETSZ,
-                                s_part + net * NTN, s_out + (net ? A * E : 0), obs_dim, act);
+    net_forward<HID, E, NTN, A>(tl, net, net ? 1 : A, net ? A : 0, s_blob, L, s_in, s_h1 + net * NETSZ, s_outp, obs_dim, act);
+}
+// output o (0..A-1 action means, A = value) of env e: bias + the per-warp partial sums, in a fixed order
+template <int E, int NW, int A>
+__device__ __forceinline__ float mlp_out(const float* __restrict__ s_outp, const float* __restrict__ s_blob, const BlobLayout& L, int o, int e) {
+    float v = s_blob[L.b3 + o];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) v += s_outp[(w * (A + 1) + o) * E + e];
+    return v;
 }
 
 #ifdef SCG_PROF
@@ -435,15 +447,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     // With >= 4 warps the env-step section is split: warp 0 = owners (sampling, action map, physics, done, finalize, reset),
     // warp 1 = constraints, warp 2 = reward + mse, warp 3 = next observation.  Smaller CTAs keep everything on the owner lanes.
     constexpr bool SPLIT = (NT >= 128) && (E <= 32);
-    // Decoupled critic (8-warp CTAs): all warps compute the ACTOR (the only net on the critical path to the env step); the critic of
-    // the same observation then runs on warps 4-7 CONCURRENTLY with the env step of warps 0-3 and stores v[t] itself.
-#ifdef SCG_DECOUPLED_CRITIC   // measured on B200 (round 1): no faster than the lockstep schedule -> off by default
-    constexpr bool DECOUPLED = (NT == 256) && (HID / (NT / (E / 4)) >= 2);
-#else
-    constexpr bool DECOUPLED = false;
-#endif
-    constexpr int NETSZ = (HID / 2) * (2 * (E / 4) * 4);     // floats of one net's hidden tile
-    static_assert(NT / E >= A + 1, "layer 3 needs A+1 lane groups");
+    constexpr int NW = NT / 64;                // GEMM warps per network
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ HotCfg<R> s_hot;
@@ -453,23 +457,22 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     __shared__ int s_cstep[E];                 // ctrl_step BEFORE the increment of the step being processed
     __shared__ int s_cviol[E];
     __shared__ R s_rew[E], s_mse[E];
-    __shared__ float s_part[2 * NT];
     // reset candidates: the helper warp pre-draws the next two episodes of every env (slot = episode & 1)
     constexpr int NC = SCG_MAX_INERTIAL + NX;
     __shared__ double s_cand[2 * NC * E];
     __shared__ int s_cand_ep[2 * E];           // episode index held by each candidate slot (-1 = empty)
     __shared__ int s_epi[E];                   // next episode index of each env, published by its owner lane
+    __shared__ int s_flag[E], s_hit[E];        // FAST path: done / truncated bits of the step, "helper built the reset observation"
 
     const int od = T.obs_dim, N = T.N, nc = T.n_con;
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * E;
-    const RolloutSmem<HID, E> S(od, A, T.L * NX * (int)(sizeof(R) / 4));
+    const RolloutSmem<HID, E> S(od, A, T.L * NX * (int)(sizeof(R) / 4), NW);
     const BlobLayout L = blob_layout(od, A, HID);
     float* s_blob = smem + S.blob;
     float* s_obs = smem + S.obs;
     float* s_tobs = smem + S.tobs;
     float* s_h1 = smem + S.h1;
-    float* s_h2 = smem + S.h2;
     float* s_out = smem + S.out;
     R* s_xg = reinterpret_cast<R*>(smem + S.xg);      // X_GOAL [L][nx] in the integrator's precision
 
@@ -485,17 +488,9 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     }
     // ---- meanwhile: owner lanes pull their env into registers, everyone fills the observation tile
     // roles: owner lanes sit in the LAST warp (the issue arbiter favours the highest warp id -- the env step is the critical
-    // path), helpers are the three warps below it, the decoupled critic is the lower half of the CTA
+    // path), helpers are the three warps below it
     const int warp = tid >> 5, lane = tid & 31;
-    int role = (NT / 32 - 1) - warp;                // 0 = owner warp, 1..3 = helper warps
-    int crit_tl = -1;                               // index inside the decoupled critic's thread group, or -1
-    if (DECOUPLED) {
-        // SM sub-partition = warp % 4.  The owner (warp 7) keeps sub-partition 3 free of GEMM warps: critic = warps 0,1,2,4,
-        // helpers = warp 5 (constraints), warp 6 (reward), warp 3 (next observation, the lightest; shares the owner's sub-partition)
-        const int cw = warp < 3 ? warp : (warp == 4 ? 3 : -1);
-        crit_tl = cw < 0 ? -1 : cw * 32 + lane;
-        role = warp == 7 ? 0 : warp == 5 ? 1 : warp == 6 ? 2 : warp == 3 ? 3 : 99;
-    }
+    const int role = (NT / 32 - 1) - warp;          // 0 = owner warp, 1..3 = helper warps
     const int ol = tid - (NT - 32);                 // owner lane index (env inside the CTA) when role == 0
     const bool owner = ol >= 0 && ol < E;
     const int n = n0 + ol;
@@ -518,6 +513,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     const float log_sqrt_2pi = 0.91893853320467267f;
     const bool philox_eps = (P.eps == nullptr);
     const bool obs_noise = h->has_dist[SCG_MODE_OBSERVATION] != 0;
+    const bool fast_done = use_cand && !obs_noise && !h->done_on_violation;
     // obs write-out: element i = tid + j*NT of the [E][od] record maps to (env i / od, dim i % od); advance incrementally
     const int ow_k = tid % od, ow_e = tid / od, ow_dk = NT % od, ow_de = NT / od;
 #ifdef SCG_PROF
@@ -571,29 +567,30 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
         }
         PROF_T(k1);
         SCG_TK(13);
-        if constexpr (DECOUPLED) net_forward<HID, E, NT, 0>(tid, 0, A, 0, s_blob, L, s_oc, s_h1, s_h2, s_part, s_out, od, P.activation);
-        else mlp_forward<HID, E, NT, A>(s_blob, L, s_oc, s_h1, s_h2, s_part, s_out, od, P.activation);
+        mlp_forward<HID, E, NT, A>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
         PROF_T(k2);
 
-        // (b) env step.  Owner lanes: sample, action map, physics; then reward / constraints / next observation run on helper
-        // warps (SPLIT) while the owners evaluate termination; owners finalize, emit the record and auto-reset.
+        // (b) env step.  Owner lanes: sample, action map, physics, termination test; then reward / constraints / next observation
+        // run on helper warps (SPLIT); owners finalize, emit the record and auto-reset.  FAST path (no observation noise, no
+        // done_on_violation, pre-drawn reset candidates): the owner publishes done / truncated right after the physics, so the
+        // observation helper also builds the terminal and the RESET observation -- the owner only reloads its registers on a reset.
         int trunc = 0;
         if (role == 0) {
             SCG_TK(0);
             float act[A], logp = 0.f, val = 0.f;
             R state[NX], rew = (R)0, mse = (R)0;
-            StepCtx<SYS, R> cx; NoiseSrc<R> ns; StepInfo info;
-            int done = 0, goal_reached = 0, oob = 0, cviol = 0, truncated = 0;
+            StepCtx<SYS, R> cx; NoiseSrc<R> ns;
+            int done = 0, goal_reached = 0, oob = 0, cviol = 0, truncated = 0, fl = 0;
             if (live) {
 #pragma unroll
                 for (int k = 0; k < A; ++k) {
                     const float zk = (philox_eps && !P.deterministic) ? s_eps[k * E + ol] : z[k];
-                    const float mu = s_out[k * E + ol];
+                    const float mu = mlp_out<E, NW, A>(s_out, s_blob, L, k, ol);
                     act[k] = fmaf(sd[k], zk, mu);                         // Normal.sample (ppo_utils.py:228)
                     const float d = act[k] - mu;
                     logp += -(d * d) * inv2var[k] - lsd[k] - log_sqrt_2pi;   // distributions.py:12-21
                 }
-                if (!DECOUPLED) val = s_out[A * E + ol];
+                val = mlp_out<E, NW, A>(s_out, s_blob, L, A, ol);
                 R action[A];
 #pragma unroll
                 for (int k = 0; k < A; ++k) action[k] = (R)act[k];
@@ -609,12 +606,50 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
 #pragma unroll
                 for (int k = 0; k < A; ++k) { s_z[(NX + k) * E + ol] = (double)cx.noisy[k]; s_z[(NX + A + k) * E + ol] = (double)cx.clipped[k]; }
                 s_cstep[ol] = e.ctrl_step;
+                if (fast_done) {
+                    done = env_done<SYS, R, R>(h, s_xg, state, goal_reached, oob);
+                    fl = (e.ctrl_step + 1 >= h->ctrl_steps) ? (done ? 1 : 3) : done;   // bit 0 done, bit 1 truncated
+                    s_flag[ol] = fl;
+                }
             }
             PROF_T(k3);
             SCG_TK(7);
+            const size_t tn = tn0 + ol;
+            const int step_before = e.ctrl_step;
+            bool publish_epi = false;
+            auto store_policy_part = [&]() {                               // record entries that do not depend on the helpers
+                if (A == 2) *reinterpret_cast<float2*>(P.out.d_act + tn * A) = make_float2(act[0], act[1 % A]);
+                else if (A == 4) *reinterpret_cast<float4*>(P.out.d_act + tn * A) = make_float4(act[0], act[1 % A], act[2 % A], act[3 % A]);
+                else P.out.d_act[tn * A] = act[0];
+                P.out.d_v[tn] = val;
+                P.out.d_logp[tn] = logp;
+            };
+            auto auto_reset = [&](bool hit, bool write_obs) {              // dummy_vec_env.py:33-38
+                const int slot = e.episode & 1;
+                env_reset<SYS, R>(T, h, n, e, state, hit ? s_cand + slot * NC * E + ol : nullptr, E);
+                if (write_obs) {
+                    ns = reset_noise<R>(T, h, n, e.episode);
+                    make_obs<SYS, R, R>(T, h, s_xg, state, n, 0, true, ns, TileObsSink<E>{s_on, ol});
+                }
+            };
             if (SPLIT) {
                 named_bar_arrive(1, 128);                                  // helpers may start
-                if (live) done = env_done<SYS, R, R>(h, s_xg, state, goal_reached, oob);
+                if (live) {
+                    if (!fast_done) done = env_done<SYS, R, R>(h, s_xg, state, goal_reached, oob);
+                    else {
+                        // FAST: everything that does not need the helpers' results happens while they work
+                        store_policy_part();
+                        P.out.d_mask[tn] = (fl & 1) ? 0.f : 1.f;
+                        if (fl != 3) P.out.d_terminal_v[tn] = 0.f;
+                        if (fl & 1) {
+                            // take the pre-drawn episode if the helper has it (same test as the observation helper), draw inline otherwise;
+                            // the new episode index is published after the helpers are done (they still read the old one)
+                            const bool hit = *(volatile int*)&s_cand_ep[(e.episode & 1) * E + ol] == e.episode;
+                            auto_reset(hit, !hit);
+                            publish_epi = true;
+                        } else e.ctrl_step += 1;
+                    }
+                }
                 SCG_TK(8);
                 named_bar_sync(2, 128);                                    // helpers are done
                 SCG_TK(9);
@@ -626,52 +661,48 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
             }
             PROF_T(k4);
             if (live) {
-                const int step_before = e.ctrl_step;
-                e.ctrl_step += 1; e.total_steps += 1;
-                env_finalize<R>(h, e.ctrl_step, cviol, rew, done, truncated);
+                e.total_steps += 1;
+                env_finalize<R>(h, step_before + 1, cviol, rew, done, truncated);   // FAST: reproduces the done / truncated bits of `fl`
                 SCG_TK(10);
-                info.done = done; info.truncated = truncated; info.cviol = cviol;
                 e.ep_ret += (float)rew; e.ep_len += 1.f; e.ep_cv += (float)cviol;
-                const bool helper_obs = SPLIT && !obs_noise;               // the helper already wrote the continuing observation
                 if (done) {
-                    if (truncated) {                                       // ppo.py:274-283: critic on the terminal observation
-                        trunc = 1;
-                        if (helper_obs) { for (int k = 0; k < od; ++k) s_tobs[tile_idx<E>(k, ol)] = s_on[tile_idx<E>(k, ol)]; }
-                        else make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_tobs, ol});
-                    }
                     ep_count += 1; ep_ret_sum += e.ep_ret; ep_len_sum += e.ep_len; ep_cv_sum += e.ep_cv;
                     e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
-                    {   // dummy_vec_env.py:33-38.  Take the pre-drawn episode if the helper already has it, draw inline otherwise.
-                        const int slot = e.episode & 1;
-                        const bool hit = use_cand && (*(volatile int*)&s_cand_ep[slot * E + ol] == e.episode);
-                        env_reset<SYS, R>(T, h, n, e, state, hit ? s_cand + slot * NC * E + ol : nullptr, E);
+                }
+                if (fast_done) {
+                    trunc = truncated;
+                    if (publish_epi) *(volatile int*)&s_epi[ol] = e.episode;
+                } else {
+                    e.ctrl_step += 1;
+                    const bool helper_obs = SPLIT && !obs_noise;           // the helper already wrote the continuing observation
+                    if (done) {
+                        if (truncated) {                                   // ppo.py:274-283: critic on the terminal observation
+                            trunc = 1;
+                            if (helper_obs) { for (int k = 0; k < od; ++k) s_tobs[tile_idx<E>(k, ol)] = s_on[tile_idx<E>(k, ol)]; }
+                            else make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_tobs, ol});
+                        }
+                        const bool hit = use_cand && (*(volatile int*)&s_cand_ep[(e.episode & 1) * E + ol] == e.episode);
+                        auto_reset(hit, true);
                         __threadfence_block();                             // candidate fully read before the new index is published
                         *(volatile int*)&s_epi[ol] = e.episode;
+                    } else if (!helper_obs) {
+                        make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_on, ol});
                     }
-                    ns = reset_noise<R>(T, h, n, e.episode);
-                    make_obs<SYS, R, R>(T, h, s_xg, state, n, 0, true, ns, TileObsSink<E>{s_on, ol});
-                } else if (!helper_obs) {
-                    make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_on, ol});
+                    store_policy_part();
+                    P.out.d_mask[tn] = done ? 0.f : 1.f;
+                    if (!trunc) P.out.d_terminal_v[tn] = 0.f;
                 }
                 SCG_TK(11);
-                const size_t tn = tn0 + ol;
-                if (A == 2) *reinterpret_cast<float2*>(P.out.d_act + tn * A) = make_float2(act[0], act[1 % A]);
-                else if (A == 4) *reinterpret_cast<float4*>(P.out.d_act + tn * A) = make_float4(act[0], act[1 % A], act[2 % A], act[3 % A]);
-                else P.out.d_act[tn * A] = act[0];
                 P.out.d_rew[tn] = (float)rew;
-                P.out.d_mask[tn] = done ? 0.f : 1.f;
-                if (!DECOUPLED) P.out.d_v[tn] = val;
-                P.out.d_logp[tn] = logp;
                 if (P.out.d_cviol) P.out.d_cviol[tn] = (float)cviol;
                 if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
-                if (!trunc) P.out.d_terminal_v[tn] = 0.f;
             }
             SCG_TK(12);
 #ifdef SCG_PROF
             if (PROF_ON) { long long k5 = clock64(); pacc[0] += k1 - k0; pacc[1] += k2 - k1; pacc[2] += k3 - k2; pacc[3] += k4 - k3; pacc[4] += k5 - k4; }
 #endif
         } else if (SPLIT && role <= 3) {
-            named_bar_sync(1, 128);                                        // z, ctrl_step published by the owners
+            named_bar_sync(1, 128);                                        // z, ctrl_step (and the FAST done flags) published by the owners
             const int ee = lane;
             const bool hl = ee < E && n0 + ee < N;
             if (hl) {
@@ -689,9 +720,28 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                         for (int k = 0; k < A; ++k) { ny[k] = (R)s_z[(NX + k) * E + ee]; cl[k] = (R)s_z[(NX + A + k) * E + ee]; }
                         env_reward_mse<SYS, R, R>(h, s_xg, st, ny, cl, s_cstep[ee], rw, ms);
                         s_rew[ee] = rw; s_mse[ee] = ms;
-                    } else if (!obs_noise) {                               // next observation of the continuing episode
+                    } else if (!obs_noise) {                               // next observation
                         NoiseSrc<R> nn; nn.row = nullptr; nn.philox = false; nn.slot = 0; nn.stream = 0; nn.idx = 0; nn.key.k0 = nn.key.k1 = nn.key.genv = 0;
-                        make_obs<SYS, R, R>(T, h, s_xg, st, n0 + ee, s_cstep[ee], false, nn, TileObsSink<E>{s_on, ee});
+                        const int fl = fast_done ? s_flag[ee] : 0;
+                        if (!(fl & 1)) {                                   // continuing episode (or the slow path: the owner fixes up done envs)
+                            make_obs<SYS, R, R>(T, h, s_xg, st, n0 + ee, s_cstep[ee], false, nn, TileObsSink<E>{s_on, ee});
+                        } else {
+                            if (fl & 2) make_obs<SYS, R, R>(T, h, s_xg, st, n0 + ee, s_cstep[ee], false, nn, TileObsSink<E>{s_tobs, ee});   // terminal observation
+                            const int ep = *(volatile int*)&s_epi[ee], slot = ep & 1;          // the episode about to start
+                            int hit = 0;
+                            if (*(volatile int*)&s_cand_ep[slot * E + ee] == ep) {
+                                const double* cd = s_cand + slot * NC * E + ee;
+                                R initr[NX];
+#pragma unroll
+                                for (int j = 0; j < NX; ++j) initr[j] = (R)cd[(SCG_MAX_INERTIAL + j) * E];
+                                EnvRegs<SYS, R> tmp; R st0[NX];
+                                Physics<SYS, R>::set_init(tmp, initr);
+                                Physics<SYS, R>::state(tmp, st0);
+                                make_obs<SYS, R, R>(T, h, s_xg, st0, n0 + ee, 0, true, nn, TileObsSink<E>{s_on, ee});
+                                hit = 1;
+                            }
+                            s_hit[ee] = hit;
+                        }
                     }
                 }
             }
@@ -715,26 +765,17 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                     }
                 }
             }
-        } else if (DECOUPLED && crit_tl >= 0) {
-          if constexpr (DECOUPLED) {
-            // critic of observation t on four GEMM warps, concurrently with the env step above; it stores v[t] itself
-            const int tl = crit_tl;
-            net_forward<HID, E, NT / 2, 3>(tl, 1, 1, A, s_blob, L, s_oc, s_h1 + NETSZ, s_h2 + NETSZ, s_part + NT, s_out + A * E, od, P.activation);
-            if (tl < E && n0 + tl < N) P.out.d_v[tn0 + tl] = s_out[A * E + tl];
-          }
         }
         SCG_TK(23);
         PROF_T(k6);
         // (c) critic on the terminal observation of time-limit truncated envs (rare, CTA-uniform branch).
-        //     s_tobs aliases s_h2: written after layer 3 consumed h2, read by layer 1 of this pass, overwritten by its layer 2.
         const int any_trunc = __syncthreads_or(trunc);
 #ifdef SCG_PROF
         if (PROF_ON) pacc[5] += clock64() - k6;
 #endif
         if (any_trunc) {
-            if constexpr (DECOUPLED) net_forward<HID, E, NT, 0>(tid, 1, 1, A, s_blob, L, s_tobs, s_h1 + NETSZ, s_h2 + NETSZ, s_part, s_out + A * E, od, P.activation);
-            else mlp_forward<HID, E, NT, A>(s_blob, L, s_tobs, s_h1, s_h2, s_part, s_out, od, P.activation);
-            if (live && trunc) P.out.d_terminal_v[tn0 + ol] = s_out[A * E + ol];
+            mlp_forward<HID, E, NT, A>(s_blob, L, s_tobs, s_h1, s_out, od, P.activation);
+            if (live && trunc) P.out.d_terminal_v[tn0 + ol] = mlp_out<E, NW, A>(s_out, s_blob, L, A, ol);
             __syncthreads();
         }
         cur ^= 1;
@@ -746,8 +787,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     long long g0 = clock64();
 #endif
     // ---- bootstrap value of the last observation, state write-back, GAE
-    if constexpr (DECOUPLED) net_forward<HID, E, NT, 0>(tid, 1, 1, A, s_blob, L, s_ol, s_h1 + NETSZ, s_h2 + NETSZ, s_part, s_out + A * E, od, P.activation);
-    else mlp_forward<HID, E, NT, A>(s_blob, L, s_ol, s_h1, s_h2, s_part, s_out, od, P.activation);
+    mlp_forward<HID, E, NT, A>(s_blob, L, s_ol, s_h1, s_out, od, P.activation);
     if (live) {
         env_store<SYS, R>(T, n, e);
         for (int k = 0; k < od; ++k) {
@@ -755,7 +795,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
             T.st.cur_obs[(size_t)n * od + k] = v;
             if (P.out.d_last_obs) P.out.d_last_obs[(size_t)n * od + k] = v;
         }
-        const float lval = s_out[A * E + ol];
+        const float lval = mlp_out<E, NW, A>(s_out, s_blob, L, A, ol);
         if (P.out.d_last_val) P.out.d_last_val[n] = lval;
         if (P.out.d_ep_count) { P.out.d_ep_count[n] = ep_count; P.out.d_ep_return_sum[n] = ep_ret_sum; P.out.d_ep_length_sum[n] = ep_len_sum; P.out.d_ep_cviol_sum[n] = ep_cv_sum; }
         if (P.out.d_ret && P.out.d_adv) {
