@@ -645,61 +645,52 @@ __device__ __forceinline__ void make_obs(const DevTables& T, const HotCfg<R>* h,
     }
 }
 
+// One additive randomisation sample (benchmark_env.py:260-267) from two Philox words.  Cold code, deliberately out of line:
+// inlined per slot it used to be the largest part of the rollout kernel (float64 log / sqrt / cos per copy).
+static __device__ __noinline__ double rand_draw(int kind, double a, double b, uint32_t w0, uint32_t w1) {
+    if (kind == SCG_RAND_UNIFORM) return a + (b - a) * u01_d(w0);
+    if (kind == SCG_RAND_NORMAL) return a + b * normal_from_words<double>(w0, w1);
+    return 0.0;
+}
 // Random draws of episode `k` of env `n` (a pure function of (n, k): host table row or Philox stream EPISODE), i.e. the inertial
 // properties and the initial state after the additive randomisation of benchmark_env.py:237-268 (quadrotor.py:346-372, cartpole.py:287-326).
-// Disturbance step offsets are NOT drawn here (see env_reset).
+// Disturbance step offsets are NOT drawn here (see env_reset).  Draw slot j = words 2(j&1), 2(j&1)+1 of Philox block j>>1.
+// out[j * stride], j < SCG_MAX_INERTIAL: inertial properties; out[(init_row + i) * stride], i < NX: the initial state.
+// One compact out-of-line copy.
 template <int SYS, typename R>
-__device__ __forceinline__ void reset_draw(const DevTables& T, const HotCfg<R>* h, int n, int k, double* inr /*[SCG_MAX_INERTIAL]*/, double* init /*[NX]*/) {
+__device__ __noinline__ void reset_draw(const DevTables& T, const HotCfg<R>* h, int n, int k, double* out, int stride, int init_row) {
     constexpr int NX = SysDims<SYS>::NX;
     const bool philox = h->philox != 0;
-    RngKey key; key.k0 = h->key0; key.k1 = h->key1; key.genv = h->genv0 + (uint32_t)n;
+    const uint32_t genv = h->genv0 + (uint32_t)n;
     const double* row = (!philox && T.ep_table) ? T.ep_table + ((size_t)(k % T.K) * T.N + n) * T.P : nullptr;
-    int slot = h->n_off_draws;
+    const int slot0 = h->n_off_draws;
     const int n_inertial = (SYS == SCG_SYS_CARTPOLE) ? 3 : 4;
-    // Philox: slot j = words 2(j&1), 2(j&1)+1 of block j>>1 -- one block per TWO slots.
-    auto draw = [&](int kind, double a, double b, uint32_t w0, uint32_t w1) -> double {
-        if (kind == SCG_RAND_UNIFORM) return a + (b - a) * u01_d(w0);
-        if (kind == SCG_RAND_NORMAL) return a + b * normal_from_words<double>(w0, w1);
-        return 0.0;
-    };
-#pragma unroll
-    for (int j = 0; j < SCG_MAX_INERTIAL; ++j) inr[j] = h->inertial_nominal[j];
-    if (h->randomized_inertial) {
-        if (row) {
-#pragma unroll
-            for (int j = 0; j < SCG_MAX_INERTIAL; ++j) if (j < n_inertial) inr[j] += row[slot + j];
-        } else if (philox) {
-#pragma unroll
-            for (int j = 0; j < SCG_MAX_INERTIAL; ++j) {
-                if (j < n_inertial && h->inertial_kind[j] != SCG_RAND_NONE) {
-                    uint32_t w0, w1; rng_words(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j), w0, w1);
-                    inr[j] += draw(h->inertial_kind[j], h->inertial_a[j], h->inertial_b[j], w0, w1);
+    uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0; int have = -1;   // Philox block currently held
+#pragma unroll 1
+    for (int j = 0; j < SCG_MAX_INERTIAL + NX; ++j) {
+        const bool inertial = j < SCG_MAX_INERTIAL;
+        const int i = inertial ? j : j - SCG_MAX_INERTIAL;
+        double v = inertial ? h->inertial_nominal[i] : h->init_nominal[i];
+        const bool on = inertial ? (h->randomized_inertial && i < n_inertial) : (h->randomized_init != 0);
+        if (on) {
+            const int slot = slot0 + j;
+            if (row) v += row[slot];
+            else if (philox) {
+                const int kind = inertial ? h->inertial_kind[i] : h->init_kind[i];
+                if (kind != SCG_RAND_NONE) {
+                    if (have != (slot >> 1)) {
+                        have = slot >> 1;
+                        uint32_t x[4]; philox4x32_10((uint32_t)have, (uint32_t)k, genv, SCG_STREAM_EPISODE, h->key0, h->key1, x);
+                        x0 = x[0]; x1 = x[1]; x2 = x[2]; x3 = x[3];
+                    }
+                    const uint32_t w0 = (slot & 1) ? x2 : x0, w1 = (slot & 1) ? x3 : x1;
+                    const double a = inertial ? h->inertial_a[i] : h->init_a[i], b = inertial ? h->inertial_b[i] : h->init_b[i];
+                    if (kind == SCG_RAND_UNIFORM) v += a + (b - a) * u01_d(w0);
+                    else v += rand_draw(kind, a, b, w0, w1);
                 }
             }
         }
-    }
-    slot += SCG_MAX_INERTIAL;
-    if (h->randomized_init && !row && philox && (slot & 1) == 0) {
-        // common case: consecutive slot pairs share a Philox block (NX is even)
-#pragma unroll
-        for (int j = 0; j < NX; j += 2) {
-            uint32_t x[4]; philox4x32_10((uint32_t)((slot + j) >> 1), (uint32_t)k, key.genv, SCG_STREAM_EPISODE, key.k0, key.k1, x);
-            init[j] = h->init_nominal[j] + draw(h->init_kind[j], h->init_a[j], h->init_b[j], x[0], x[1]);
-            init[j + 1] = h->init_nominal[j + 1] + draw(h->init_kind[j + 1], h->init_a[j + 1], h->init_b[j + 1], x[2], x[3]);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < NX; ++j) {
-            double v = h->init_nominal[j];
-            if (h->randomized_init) {
-                if (row) v += row[slot + j];
-                else if (philox && h->init_kind[j] != SCG_RAND_NONE) {
-                    uint32_t w0, w1; rng_words(key, SCG_STREAM_EPISODE, (uint32_t)k, (uint32_t)(slot + j), w0, w1);
-                    v += draw(h->init_kind[j], h->init_a[j], h->init_b[j], w0, w1);
-                }
-            }
-            init[j] = v;
-        }
+        out[(inertial ? i : init_row + i) * stride] = v;
     }
 }
 
@@ -735,7 +726,12 @@ __device__ __forceinline__ void env_reset(const DevTables& T, const HotCfg<R>* h
 #pragma unroll
         for (int j = 0; j < NX; ++j) init[j] = cand[(SCG_MAX_INERTIAL + j) * cstride];
     } else {
-        reset_draw<SYS, R>(T, h, n, k, inr, init);
+        double tmp[SCG_MAX_INERTIAL + NX];
+        reset_draw<SYS, R>(T, h, n, k, tmp, 1, SCG_MAX_INERTIAL);
+#pragma unroll
+        for (int j = 0; j < SCG_MAX_INERTIAL; ++j) inr[j] = tmp[j];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) init[j] = tmp[SCG_MAX_INERTIAL + j];
     }
 #pragma unroll
     for (int j = 0; j < SCG_MAX_INERTIAL; ++j) e.inertial[j] = (R)inr[j];

@@ -157,6 +157,11 @@ template <int E> struct TileObsSink {   // env `e` of the CTA's pair-swizzled ob
     template <typename R> __device__ __forceinline__ void operator()(int k, R v) const { tile[tile_idx<E>(k, e)] = (float)v; }
 };
 
+struct PlainObsSink {       // column of a [k][stride] float array
+    float* col; int stride;
+    template <typename R> __device__ __forceinline__ void operator()(int k, R v) const { col[k * stride] = (float)v; }
+};
+
 // ---------------------------------------------------------------------------------------------
 // lane-per-env kernels (gym-style API)
 // ---------------------------------------------------------------------------------------------
@@ -267,7 +272,7 @@ struct RolloutParams {
 
 // shared memory carve-up (floats), all offsets multiples of 4
 template <int HID, int E> struct RolloutSmem {
-    int blob, obs, tobs, h1, out, xg, total_floats;
+    int blob, obs, tobs, cobs, h1, out, xg, total_floats;
     // xg_floats: size of the shared X_GOAL copy in float units (L * nx * sizeof(R) / 4); nw: GEMM warps per network
     __host__ __device__ RolloutSmem(int obs_dim, int act_dim, int xg_floats, int nw) {
         BlobLayout L = blob_layout(obs_dim, act_dim, HID);
@@ -275,7 +280,8 @@ template <int HID, int E> struct RolloutSmem {
         obs = blob + L.total;
         h1 = obs + 2 * obs_dim * E;          // two observation tiles (ping-pong): tile t+1 is built while tile t is still the policy input
         tobs = h1 + 2 * HID * E;             // terminal observations of time-limit truncated envs
-        out = tobs + obs_dim * E;
+        cobs = tobs + obs_dim * E;           // reset observations of the two candidate episodes
+        out = cobs + 2 * obs_dim * E;
         xg = out + pad4i(nw * (act_dim + 1) * E);   // per-warp partial sums of the output layer
         total_floats = xg + pad4i(xg_floats);
     }
@@ -451,18 +457,20 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ HotCfg<R> s_hot;
-    __shared__ double s_z[NZ * E];
-    __shared__ float s_eps[A * E];
+    __shared__ double s_z[2 * NZ * E];         // [state; noisy action; clipped action] of the last two steps (FAST: double-buffered)
+    __shared__ float s_eps[2 * A * E];
     __shared__ uint32_t s_tsteps0[E];
-    __shared__ int s_cstep[E];                 // ctrl_step BEFORE the increment of the step being processed
-    __shared__ int s_cviol[E];
-    __shared__ R s_rew[E], s_mse[E];
-    // reset candidates: the helper warp pre-draws the next two episodes of every env (slot = episode & 1)
-    constexpr int NC = SCG_MAX_INERTIAL + NX;
+    __shared__ int s_cstep[2 * E];             // ctrl_step BEFORE the increment, of the last two steps
+    __shared__ int s_flag[2 * E];              // bit 0 done, bit 1 truncated, of the last two steps
+    // reset candidates: a helper warp keeps the next two episodes of every env ready (slot = episode & 1):
+    // inertial properties, their reciprocals, the integrator state of the initial condition (+ its observation in s_cobs)
+    constexpr int PS = SysDims<SYS>::PS;
+    constexpr int NC = SCG_MAX_INERTIAL + 2 + PS;
     __shared__ double s_cand[2 * NC * E];
     __shared__ int s_cand_ep[2 * E];           // episode index held by each candidate slot (-1 = empty)
     __shared__ int s_epi[E];                   // next episode index of each env, published by its owner lane
-    __shared__ int s_flag[E], s_hit[E];        // FAST path: done / truncated bits of the step, "helper built the reset observation"
+    __shared__ float s_stat[6 * E];            // FAST: episode statistics kept by the record helpers, handed back at the end
+    __shared__ int s_epc[E];
 
     const int od = T.obs_dim, N = T.N, nc = T.n_con;
     const int tid = threadIdx.x;
@@ -472,6 +480,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     float* s_blob = smem + S.blob;
     float* s_obs = smem + S.obs;
     float* s_tobs = smem + S.tobs;
+    float* s_cobs = smem + S.cobs;                    // reset observations of the two candidate slots, [slot][k][E]
     float* s_h1 = smem + S.h1;
     float* s_out = smem + S.out;
     R* s_xg = reinterpret_cast<R*>(smem + S.xg);      // X_GOAL [L][nx] in the integrator's precision
@@ -513,9 +522,68 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     const float log_sqrt_2pi = 0.91893853320467267f;
     const bool philox_eps = (P.eps == nullptr);
     const bool obs_noise = h->has_dist[SCG_MODE_OBSERVATION] != 0;
-    const bool fast_done = use_cand && !obs_noise && !h->done_on_violation;
-    // obs write-out: element i = tid + j*NT of the [E][od] record maps to (env i / od, dim i % od); advance incrementally
-    const int ow_k = tid % od, ow_e = tid / od, ow_dk = NT % od, ow_de = NT / od;
+    const bool fast = use_cand && !obs_noise && !h->done_on_violation && !h->use_penalty;
+    const int OBS_TILE = od * E;
+    // ---- helper-warp work of the FAST schedule (lane ee = env ee of the CTA)
+    const int ee = lane;
+    const bool hl = SPLIT && role >= 1 && role <= 3 && ee < E && n0 + ee < N;
+    float h_a = 0.f, h_b = 0.f, h_sa = 0.f, h_sb = 0.f; int h_cnt = 0;   // role 2: ep return / length (+ sums), role 1: ep violations (+ sum)
+    if (hl && fast) {
+        if (role == 2) { h_a = T.st.ep_acc[n0 + ee]; h_b = T.st.ep_acc[N + n0 + ee]; }
+        if (role == 1) h_a = T.st.ep_acc[2 * N + n0 + ee];
+    }
+    // record entries of step tp that are not on the owners' critical path (reward, mse, constraint rows, episode statistics)
+    auto process_record = [&](int tp) {
+        const int bsel = tp & 1;
+        const double* zb = s_z + bsel * NZ * E + ee;
+        const size_t tnp = (size_t)tp * N + n0 + ee;
+        const int dn = s_flag[bsel * E + ee] & 1;
+        if (role == 1) {                                                   // constraints (benchmark_env.py:472-485)
+            int cv = 0;
+            if (nc > 0) cv = env_constraints(T, h->rows, nc, h->con_fast, zb, E, nullptr, P.out.d_cvals ? P.out.d_cvals + tnp * nc : nullptr);
+            if (P.out.d_cviol) P.out.d_cviol[tnp] = (float)cv;
+            h_a += (float)cv;
+            if (dn) { h_sa += h_a; h_a = 0.f; }
+        } else {                                                           // reward + info['mse']
+            R st[NX], ny[A], cl[A], rw, ms;
+#pragma unroll
+            for (int k = 0; k < NX; ++k) st[k] = (R)zb[k * E];
+#pragma unroll
+            for (int k = 0; k < A; ++k) { ny[k] = (R)zb[(NX + k) * E]; cl[k] = (R)zb[(NX + A + k) * E]; }
+            env_reward_mse<SYS, R, R>(h, s_xg, st, ny, cl, s_cstep[bsel * E + ee], rw, ms);
+            P.out.d_rew[tnp] = (float)rw;
+            if (P.out.d_mse) P.out.d_mse[tnp] = (float)ms;
+            h_a += (float)rw; h_b += 1.f;
+            if (dn) { h_cnt += 1; h_sa += h_a; h_sb += h_b; h_a = 0.f; h_b = 0.f; }
+        }
+    };
+    // keep the next two episodes of env ee ready (a pure function of (env, episode)); runs while the owners sample and integrate
+    auto prepare_candidates = [&]() {
+        const int want = *(volatile int*)&s_epi[ee];
+#pragma unroll 1
+        for (int d = 0; d < 2; ++d) {
+            const int ep = want + d, slot = ep & 1;
+            if (*(volatile int*)&s_cand_ep[slot * E + ee] != ep) {
+                double* cd = s_cand + slot * NC * E + ee;
+                reset_draw<SYS, R>(T, h, n0 + ee, ep, cd, E, SCG_MAX_INERTIAL + 2);   // inertial at rows 0..3, initial state from row 6
+                EnvRegs<SYS, R> tmp; R initr[NX], st0[NX];
+#pragma unroll
+                for (int j = 0; j < SCG_MAX_INERTIAL; ++j) tmp.inertial[j] = (R)cd[j * E];
+#pragma unroll
+                for (int j = 0; j < NX; ++j) initr[j] = (R)cd[(SCG_MAX_INERTIAL + 2 + j) * E];
+                env_derived<SYS, R>(tmp);
+                Physics<SYS, R>::set_init(tmp, initr);
+                Physics<SYS, R>::state(tmp, st0);
+                cd[SCG_MAX_INERTIAL * E] = (double)tmp.inv[0]; cd[(SCG_MAX_INERTIAL + 1) * E] = (double)tmp.inv[1];
+#pragma unroll
+                for (int j = 0; j < PS; ++j) cd[(SCG_MAX_INERTIAL + 2 + j) * E] = (double)tmp.ps[j];
+                NoiseSrc<R> nn; nn.row = nullptr; nn.philox = false; nn.slot = 0; nn.stream = 0; nn.idx = 0; nn.key.k0 = nn.key.k1 = nn.key.genv = 0;
+                make_obs<SYS, R, R>(T, h, s_xg, st0, n0 + ee, 0, true, nn, PlainObsSink{s_cobs + slot * OBS_TILE + ee, E});
+                __threadfence_block();
+                *(volatile int*)&s_cand_ep[slot * E + ee] = ep;
+            }
+        }
+    };
 #ifdef SCG_PROF
     const long long cta_t0 = clock64();
     if (tid == NT - 32) scg_tk_last = cta_t0;
@@ -523,252 +591,178 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
 #define PROF_ON (P.prof != nullptr && tid == NT - 32)
 #endif
 
+    // With idle warps next to the owner / helper warps (8-warp CTAs) the two jobs that only feed the record or the NEXT step --
+    // PPOBuffer.obs[t] <- observation tile, and the Philox normals of step t+1 -- run on those warps during the env phase.
+    constexpr int NIDLE = SPLIT ? NT - 128 : 0;
+    constexpr bool DEFER = NIDLE >= 32 && NIDLE >= E;
+    const bool gen_eps = !P.deterministic && philox_eps;
+    auto make_eps = [&](int tt) {                        // lanes tid < E: standard normals of step tt into s_eps[tt & 1]
+        if (tid < E && n0 + tid < N) {
+            const uint32_t idx = s_tsteps0[tid] + (uint32_t)tt;          // == that env's total_steps at step tt
+            float* dst = s_eps + (tt & 1) * A * E + tid;
+#pragma unroll
+            for (int k = 0; k < A; k += 2) {                              // one Philox block serves two action dims
+                uint32_t x[4]; philox4x32_10((uint32_t)(k >> 1), idx, h->genv0 + (uint32_t)(n0 + tid), SCG_STREAM_POLICY, h->key0, h->key1, x);
+                dst[k * E] = normal_from_words<float>(x[0], x[1]);
+                if (k + 1 < A) dst[(k + 1) * E] = normal_from_words<float>(x[2], x[3]);
+            }
+        }
+    };
+    auto write_obs_record = [&](int tt, const float* tile, int t0, int nthr) {   // threads t0 = 0..nthr-1 copy the [E][od] tile to obs[tt]
+        float* dst = P.out.d_obs + ((size_t)tt * N + n0) * od;
+        const int lim = (N - n0 < E ? N - n0 : E) * od;
+        int k = t0 % od, en = t0 / od;
+        const int dk = nthr % od, de = nthr / od;
+        for (int i = t0; i < lim; i += nthr) {
+            dst[i] = tile[tile_idx<E>(k, en)];
+            k += dk; en += de;
+            if (k >= od) { k -= od; en += 1; }
+        }
+    };
+    if (DEFER && gen_eps) make_eps(0);
+    __syncthreads();
+
     int cur = 0;
-    const int OBS_TILE = od * E;
     for (int t = 0; t < P.T; ++t) {
         const size_t tn0 = (size_t)t * N + n0;
         float* s_oc = s_obs + cur * OBS_TILE;            // observation of step t (policy input)
         float* s_on = s_obs + (cur ^ 1) * OBS_TILE;      // observation of step t+1 (being built)
         PROF_T(k0);
-        // standard-normal draws of this step: table mode -> owner lanes issue the loads now (latency hidden by the MLP);
-        // Philox mode -> the FIRST lane group generates them into shared memory, off the owners' critical path
+        // standard-normal draws of this step.  Table mode: the owner lanes issue the loads now (latency hidden by the MLP).
+        // Philox mode: s_eps[t & 1] -- generated by an idle warp during the env phase of step t-1 (DEFER), by the first lane
+        // group right here otherwise.
         float z[A];
 #pragma unroll
         for (int k = 0; k < A; ++k) z[k] = 0.f;
-        if (!P.deterministic) {
-            if (!philox_eps) {
-                if (live) {
+        if (!P.deterministic && !philox_eps && live) {
 #pragma unroll
-                    for (int k = 0; k < A; ++k) z[k] = __ldg(P.eps + (tn0 + ol) * A + k);
-                }
-            } else if (tid < E) {
-                const int ee = tid;
-                if (n0 + ee < N) {
-                    const uint32_t idx = s_tsteps0[ee] + (uint32_t)t;     // == that env's total_steps
-#pragma unroll
-                    for (int k = 0; k < A; k += 2) {                      // one Philox block serves two action dims
-                        uint32_t x[4]; philox4x32_10((uint32_t)(k >> 1), idx, h->genv0 + (uint32_t)(n0 + ee), SCG_STREAM_POLICY, h->key0, h->key1, x);
-                        s_eps[k * E + ee] = normal_from_words<float>(x[0], x[1]);
-                        if (k + 1 < A) s_eps[(k + 1) * E + ee] = normal_from_words<float>(x[2], x[3]);
-                    }
-                }
-            }
+            for (int k = 0; k < A; ++k) z[k] = __ldg(P.eps + (tn0 + ol) * A + k);
         }
-        // (a) PPOBuffer.obs[t] <- observation tile (coalesced), then the policy forward
-        {
-            float* dst = P.out.d_obs + tn0 * od;
-            const int lim = (N - n0 < E ? N - n0 : E) * od;
-            int k = ow_k, ee = ow_e;
-            for (int i = tid; i < lim; i += NT) {
-                dst[i] = s_oc[tile_idx<E>(k, ee)];
-                k += ow_dk; ee += ow_de;
-                if (k >= od) { k -= od; ee += 1; }
-            }
+        if (!DEFER) {
+            if (gen_eps) make_eps(t);
+            write_obs_record(t, s_oc, tid, NT);      // (a) PPOBuffer.obs[t] <- observation tile (coalesced)
         }
         PROF_T(k1);
         SCG_TK(13);
         mlp_forward<HID, E, NT, A>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
         PROF_T(k2);
 
-        // (b) env step.  Owner lanes: sample, action map, physics, termination test; then reward / constraints / next observation
-        // run on helper warps (SPLIT); owners finalize, emit the record and auto-reset.  FAST path (no observation noise, no
-        // done_on_violation, pre-drawn reset candidates): the owner publishes done / truncated right after the physics, so the
-        // observation helper also builds the terminal and the RESET observation -- the owner only reloads its registers on a reset.
+        // (b) env step.
+        // FAST schedule (helper warps available, pre-drawn reset candidates, no observation noise, no done_on_violation / constraint
+        // penalty): the owner lanes run ONLY the chain the next policy forward depends on -- sample, action map, physics, termination
+        // test, next observation, register reload on a reset -- and publish [state; actions], the step counter and the done bits in
+        // a double-buffered scratch.  Reward, info['mse'], the constraint rows and the episode statistics of step t are evaluated by
+        // two helper warps one step later, while the owners integrate step t+1: nobody waits for anybody inside the env phase.
+        // Otherwise (SERIAL): the owner lanes do everything themselves.
         int trunc = 0;
         if (role == 0) {
             SCG_TK(0);
             float act[A], logp = 0.f, val = 0.f;
-            R state[NX], rew = (R)0, mse = (R)0;
-            StepCtx<SYS, R> cx; NoiseSrc<R> ns;
-            int done = 0, goal_reached = 0, oob = 0, cviol = 0, truncated = 0, fl = 0;
             if (live) {
 #pragma unroll
                 for (int k = 0; k < A; ++k) {
-                    const float zk = (philox_eps && !P.deterministic) ? s_eps[k * E + ol] : z[k];
+                    const float zk = gen_eps ? s_eps[(t & 1) * A * E + k * E + ol] : z[k];
                     const float mu = mlp_out<E, NW, A>(s_out, s_blob, L, k, ol);
                     act[k] = fmaf(sd[k], zk, mu);                         // Normal.sample (ppo_utils.py:228)
                     const float d = act[k] - mu;
                     logp += -(d * d) * inv2var[k] - lsd[k] - log_sqrt_2pi;   // distributions.py:12-21
                 }
                 val = mlp_out<E, NW, A>(s_out, s_blob, L, A, ol);
-                R action[A];
+                R action[A], state[NX];
 #pragma unroll
                 for (int k = 0; k < A; ++k) action[k] = (R)act[k];
                 const double* nrow = (!h->philox && T.noise_table && T.D > 0)
                                          ? T.noise_table + ((size_t)((P.noise_cursor + t) % T.Tn) * N + n) * T.D : nullptr;
+                StepCtx<SYS, R> cx; NoiseSrc<R> ns;
                 env_pre<SYS, R>(T, h, n, e, action, nrow, cx, ns);
                 SCG_TK(1);
                 env_physics<SYS, R>(h, e, cx, state);
                 SCG_TK(6);
-                // publish z = [state; noisy action; clipped action] and the step counter for the helpers / the constraint rows
+                // z = [state; noisy action; clipped action] and the step counter of this step (constraints.py:166-171)
+                double* zb = s_z + (fast ? (t & 1) * NZ * E : 0) + ol;
 #pragma unroll
-                for (int k = 0; k < NX; ++k) s_z[k * E + ol] = (double)state[k];
+                for (int k = 0; k < NX; ++k) zb[k * E] = (double)state[k];
 #pragma unroll
-                for (int k = 0; k < A; ++k) { s_z[(NX + k) * E + ol] = (double)cx.noisy[k]; s_z[(NX + A + k) * E + ol] = (double)cx.clipped[k]; }
-                s_cstep[ol] = e.ctrl_step;
-                if (fast_done) {
-                    done = env_done<SYS, R, R>(h, s_xg, state, goal_reached, oob);
-                    fl = (e.ctrl_step + 1 >= h->ctrl_steps) ? (done ? 1 : 3) : done;   // bit 0 done, bit 1 truncated
-                    s_flag[ol] = fl;
+                for (int k = 0; k < A; ++k) { zb[(NX + k) * E] = (double)cx.noisy[k]; zb[(NX + A + k) * E] = (double)cx.clipped[k]; }
+                const int step_before = e.ctrl_step;
+                const size_t tn = tn0 + ol;
+                int goal_reached = 0, oob = 0, done = env_done<SYS, R, R>(h, s_xg, state, goal_reached, oob), truncated = 0;
+                SCG_TK(7);
+                if (fast) {
+                    const int fl = (step_before + 1 >= h->ctrl_steps) ? (done ? 1 : 3) : done;   // bit 0 done, bit 1 truncated (benchmark_env.py:497-502)
+                    s_cstep[(t & 1) * E + ol] = step_before;
+                    s_flag[(t & 1) * E + ol] = fl;
+                    done = fl & 1; truncated = fl >> 1;
+                    e.total_steps += 1;
+                    // observation of the transition: the next policy input unless the episode ended; the terminal observation if truncated
+                    if (fl != 1) make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{truncated ? s_tobs : s_on, ol});
+                    SCG_TK(8);
+                    if (done) {                                            // dummy_vec_env.py:33-38
+                        const int slot = e.episode & 1;
+                        if (*(volatile int*)&s_cand_ep[slot * E + ol] == e.episode) {
+                            // the helper has the whole episode start ready: inertial properties, reciprocals, integrator state, observation
+                            const double* cd = s_cand + slot * NC * E + ol;
+#pragma unroll
+                            for (int j = 0; j < SCG_MAX_INERTIAL; ++j) e.inertial[j] = (R)cd[j * E];
+                            e.inv[0] = (R)cd[SCG_MAX_INERTIAL * E]; e.inv[1] = (R)cd[(SCG_MAX_INERTIAL + 1) * E];
+#pragma unroll
+                            for (int j = 0; j < PS; ++j) e.ps[j] = (R)cd[(SCG_MAX_INERTIAL + 2 + j) * E];
+                            const float* co = s_cobs + slot * OBS_TILE + ol;
+                            for (int k = 0; k < od; ++k) s_on[tile_idx<E>(k, ol)] = co[k * E];
+                            e.ctrl_step = 0; e.episode += 1;
+                        } else {                                           // not drawn yet (first steps of a launch): draw inline
+                            env_reset<SYS, R>(T, h, n, e, state);
+                            make_obs<SYS, R, R>(T, h, s_xg, state, n, 0, true, ns, TileObsSink<E>{s_on, ol});
+                        }
+                        *(volatile int*)&s_epi[ol] = e.episode;
+                    } else e.ctrl_step += 1;
+                    SCG_TK(9);
+                } else {
+                    R rew, mse; int cviol = 0;
+                    env_reward_mse<SYS, R, R>(h, s_xg, state, cx.noisy, cx.clipped, step_before, rew, mse);
+                    if (nc > 0) cviol = env_constraints(T, h->rows, nc, h->con_fast, zb, E, nullptr, P.out.d_cvals ? P.out.d_cvals + tn * nc : nullptr);
+                    e.ctrl_step += 1; e.total_steps += 1;
+                    env_finalize<R>(h, e.ctrl_step, cviol, rew, done, truncated);
+                    e.ep_ret += (float)rew; e.ep_len += 1.f; e.ep_cv += (float)cviol;
+                    if (done) {
+                        if (truncated) make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_tobs, ol});
+                        ep_count += 1; ep_ret_sum += e.ep_ret; ep_len_sum += e.ep_len; ep_cv_sum += e.ep_cv;
+                        e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
+                        env_reset<SYS, R>(T, h, n, e, state);
+                        ns = reset_noise<R>(T, h, n, e.episode);
+                        make_obs<SYS, R, R>(T, h, s_xg, state, n, 0, true, ns, TileObsSink<E>{s_on, ol});
+                    } else {
+                        make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_on, ol});
+                    }
+                    P.out.d_rew[tn] = (float)rew;
+                    if (P.out.d_cviol) P.out.d_cviol[tn] = (float)cviol;
+                    if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
                 }
-            }
-            PROF_T(k3);
-            SCG_TK(7);
-            const size_t tn = tn0 + ol;
-            const int step_before = e.ctrl_step;
-            bool publish_epi = false;
-            auto store_policy_part = [&]() {                               // record entries that do not depend on the helpers
+                trunc = truncated;
                 if (A == 2) *reinterpret_cast<float2*>(P.out.d_act + tn * A) = make_float2(act[0], act[1 % A]);
                 else if (A == 4) *reinterpret_cast<float4*>(P.out.d_act + tn * A) = make_float4(act[0], act[1 % A], act[2 % A], act[3 % A]);
                 else P.out.d_act[tn * A] = act[0];
                 P.out.d_v[tn] = val;
                 P.out.d_logp[tn] = logp;
-            };
-            auto auto_reset = [&](bool hit, bool write_obs) {              // dummy_vec_env.py:33-38
-                const int slot = e.episode & 1;
-                env_reset<SYS, R>(T, h, n, e, state, hit ? s_cand + slot * NC * E + ol : nullptr, E);
-                if (write_obs) {
-                    ns = reset_noise<R>(T, h, n, e.episode);
-                    make_obs<SYS, R, R>(T, h, s_xg, state, n, 0, true, ns, TileObsSink<E>{s_on, ol});
-                }
-            };
-            if (SPLIT) {
-                named_bar_arrive(1, 128);                                  // helpers may start
-                if (live) {
-                    if (!fast_done) done = env_done<SYS, R, R>(h, s_xg, state, goal_reached, oob);
-                    else {
-                        // FAST: everything that does not need the helpers' results happens while they work
-                        store_policy_part();
-                        P.out.d_mask[tn] = (fl & 1) ? 0.f : 1.f;
-                        if (fl != 3) P.out.d_terminal_v[tn] = 0.f;
-                        if (fl & 1) {
-                            // take the pre-drawn episode if the helper has it (same test as the observation helper), draw inline otherwise;
-                            // the new episode index is published after the helpers are done (they still read the old one)
-                            const bool hit = *(volatile int*)&s_cand_ep[(e.episode & 1) * E + ol] == e.episode;
-                            auto_reset(hit, !hit);
-                            publish_epi = true;
-                        } else e.ctrl_step += 1;
-                    }
-                }
-                SCG_TK(8);
-                named_bar_sync(2, 128);                                    // helpers are done
-                SCG_TK(9);
-                if (live) { rew = s_rew[ol]; mse = s_mse[ol]; cviol = s_cviol[ol]; }
-            } else if (live) {
-                env_reward_mse<SYS, R, R>(h, s_xg, state, cx.noisy, cx.clipped, e.ctrl_step, rew, mse);
-                done = env_done<SYS, R, R>(h, s_xg, state, goal_reached, oob);
-                if (nc > 0) cviol = env_constraints(T, h->rows, nc, h->con_fast, s_z + ol, E, nullptr, P.out.d_cvals ? P.out.d_cvals + (tn0 + ol) * nc : nullptr);
-            }
-            PROF_T(k4);
-            if (live) {
-                e.total_steps += 1;
-                env_finalize<R>(h, step_before + 1, cviol, rew, done, truncated);   // FAST: reproduces the done / truncated bits of `fl`
-                SCG_TK(10);
-                e.ep_ret += (float)rew; e.ep_len += 1.f; e.ep_cv += (float)cviol;
-                if (done) {
-                    ep_count += 1; ep_ret_sum += e.ep_ret; ep_len_sum += e.ep_len; ep_cv_sum += e.ep_cv;
-                    e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
-                }
-                if (fast_done) {
-                    trunc = truncated;
-                    if (publish_epi) *(volatile int*)&s_epi[ol] = e.episode;
-                } else {
-                    e.ctrl_step += 1;
-                    const bool helper_obs = SPLIT && !obs_noise;           // the helper already wrote the continuing observation
-                    if (done) {
-                        if (truncated) {                                   // ppo.py:274-283: critic on the terminal observation
-                            trunc = 1;
-                            if (helper_obs) { for (int k = 0; k < od; ++k) s_tobs[tile_idx<E>(k, ol)] = s_on[tile_idx<E>(k, ol)]; }
-                            else make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_tobs, ol});
-                        }
-                        const bool hit = use_cand && (*(volatile int*)&s_cand_ep[(e.episode & 1) * E + ol] == e.episode);
-                        auto_reset(hit, true);
-                        __threadfence_block();                             // candidate fully read before the new index is published
-                        *(volatile int*)&s_epi[ol] = e.episode;
-                    } else if (!helper_obs) {
-                        make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_on, ol});
-                    }
-                    store_policy_part();
-                    P.out.d_mask[tn] = done ? 0.f : 1.f;
-                    if (!trunc) P.out.d_terminal_v[tn] = 0.f;
-                }
-                SCG_TK(11);
-                P.out.d_rew[tn] = (float)rew;
-                if (P.out.d_cviol) P.out.d_cviol[tn] = (float)cviol;
-                if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
+                P.out.d_mask[tn] = done ? 0.f : 1.f;
+                if (!truncated) P.out.d_terminal_v[tn] = 0.f;
             }
             SCG_TK(12);
 #ifdef SCG_PROF
-            if (PROF_ON) { long long k5 = clock64(); pacc[0] += k1 - k0; pacc[1] += k2 - k1; pacc[2] += k3 - k2; pacc[3] += k4 - k3; pacc[4] += k5 - k4; }
+            if (PROF_ON) { long long k5 = clock64(); pacc[0] += k1 - k0; pacc[1] += k2 - k1; pacc[2] += k5 - k2; }
 #endif
         } else if (SPLIT && role <= 3) {
-            named_bar_sync(1, 128);                                        // z, ctrl_step (and the FAST done flags) published by the owners
-            const int ee = lane;
-            const bool hl = ee < E && n0 + ee < N;
-            if (hl) {
-                if (role == 1) {                                           // constraints (benchmark_env.py:472-485)
-                    int cv = 0;
-                    if (nc > 0) cv = env_constraints(T, h->rows, nc, h->con_fast, s_z + ee, E, nullptr, P.out.d_cvals ? P.out.d_cvals + (tn0 + ee) * nc : nullptr);
-                    s_cviol[ee] = cv;
-                } else {
-                    R st[NX];
-#pragma unroll
-                    for (int k = 0; k < NX; ++k) st[k] = (R)s_z[k * E + ee];
-                    if (role == 2) {                                       // reward + info['mse']
-                        R ny[A], cl[A], rw, ms;
-#pragma unroll
-                        for (int k = 0; k < A; ++k) { ny[k] = (R)s_z[(NX + k) * E + ee]; cl[k] = (R)s_z[(NX + A + k) * E + ee]; }
-                        env_reward_mse<SYS, R, R>(h, s_xg, st, ny, cl, s_cstep[ee], rw, ms);
-                        s_rew[ee] = rw; s_mse[ee] = ms;
-                    } else if (!obs_noise) {                               // next observation
-                        NoiseSrc<R> nn; nn.row = nullptr; nn.philox = false; nn.slot = 0; nn.stream = 0; nn.idx = 0; nn.key.k0 = nn.key.k1 = nn.key.genv = 0;
-                        const int fl = fast_done ? s_flag[ee] : 0;
-                        if (!(fl & 1)) {                                   // continuing episode (or the slow path: the owner fixes up done envs)
-                            make_obs<SYS, R, R>(T, h, s_xg, st, n0 + ee, s_cstep[ee], false, nn, TileObsSink<E>{s_on, ee});
-                        } else {
-                            if (fl & 2) make_obs<SYS, R, R>(T, h, s_xg, st, n0 + ee, s_cstep[ee], false, nn, TileObsSink<E>{s_tobs, ee});   // terminal observation
-                            const int ep = *(volatile int*)&s_epi[ee], slot = ep & 1;          // the episode about to start
-                            int hit = 0;
-                            if (*(volatile int*)&s_cand_ep[slot * E + ee] == ep) {
-                                const double* cd = s_cand + slot * NC * E + ee;
-                                R initr[NX];
-#pragma unroll
-                                for (int j = 0; j < NX; ++j) initr[j] = (R)cd[(SCG_MAX_INERTIAL + j) * E];
-                                EnvRegs<SYS, R> tmp; R st0[NX];
-                                Physics<SYS, R>::set_init(tmp, initr);
-                                Physics<SYS, R>::state(tmp, st0);
-                                make_obs<SYS, R, R>(T, h, s_xg, st0, n0 + ee, 0, true, nn, TileObsSink<E>{s_on, ee});
-                                hit = 1;
-                            }
-                            s_hit[ee] = hit;
-                        }
-                    }
-                }
+            if (fast && hl) {
+                if (role == 3) prepare_candidates();
+                else if (t > 0) process_record(t - 1);
             }
-            named_bar_arrive(2, 128);
-            if (use_cand && role == 3 && hl) {
-                // off the critical path: keep the next two episodes of env ee pre-drawn (a pure function of (env, episode))
-                const int want = *(volatile int*)&s_epi[ee];
-#pragma unroll 1
-                for (int d = 0; d < 2; ++d) {
-                    const int ep = want + d, slot = ep & 1;
-                    if (*(volatile int*)&s_cand_ep[slot * E + ee] != ep) {
-                        double inr[SCG_MAX_INERTIAL], ini[NX];
-                        reset_draw<SYS, R>(T, h, n0 + ee, ep, inr, ini);
-                        double* cd = s_cand + slot * NC * E + ee;
-#pragma unroll
-                        for (int j = 0; j < SCG_MAX_INERTIAL; ++j) cd[j * E] = inr[j];
-#pragma unroll
-                        for (int j = 0; j < NX; ++j) cd[(SCG_MAX_INERTIAL + j) * E] = ini[j];
-                        __threadfence_block();
-                        *(volatile int*)&s_cand_ep[slot * E + ee] = ep;
-                    }
-                }
-            }
+        } else if (DEFER) {                                               // idle warps: record the policy input, draw the next normals
+            write_obs_record(t, s_oc, tid, NIDLE);
+            if (gen_eps && t + 1 < P.T) make_eps(t + 1);
         }
         SCG_TK(23);
         PROF_T(k6);
-        // (c) critic on the terminal observation of time-limit truncated envs (rare, CTA-uniform branch).
+        // (c) critic on the terminal observation of time-limit truncated envs (rare, CTA-uniform branch)
         const int any_trunc = __syncthreads_or(trunc);
 #ifdef SCG_PROF
         if (PROF_ON) pacc[5] += clock64() - k6;
@@ -786,9 +780,20 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     if (PROF_ON && blockIdx.x == 0) for (int i = 0; i < 8; ++i) P.prof[i] = pacc[i];
     long long g0 = clock64();
 #endif
-    // ---- bootstrap value of the last observation, state write-back, GAE
+    // ---- FAST: the record helpers still owe the last step; they hand the episode statistics back to the owner lanes
+    if (fast && hl && role != 3) {
+        process_record(P.T - 1);
+        if (role == 2) { s_stat[ee] = h_a; s_stat[E + ee] = h_b; s_stat[3 * E + ee] = h_sa; s_stat[4 * E + ee] = h_sb; s_epc[ee] = h_cnt; }
+        else { s_stat[2 * E + ee] = h_a; s_stat[5 * E + ee] = h_sa; }
+    }
+    // ---- bootstrap value of the last observation (its barriers also order the helpers' record stores before the GAE scan),
+    //      state write-back, GAE
     mlp_forward<HID, E, NT, A>(s_blob, L, s_ol, s_h1, s_out, od, P.activation);
     if (live) {
+        if (fast) {
+            e.ep_ret = s_stat[ol]; e.ep_len = s_stat[E + ol]; e.ep_cv = s_stat[2 * E + ol];
+            ep_ret_sum = s_stat[3 * E + ol]; ep_len_sum = s_stat[4 * E + ol]; ep_cv_sum = s_stat[5 * E + ol]; ep_count = s_epc[ol];
+        }
         env_store<SYS, R>(T, n, e);
         for (int k = 0; k < od; ++k) {
             const float v = s_ol[tile_idx<E>(k, ol)];
