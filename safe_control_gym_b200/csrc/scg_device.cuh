@@ -66,14 +66,17 @@ template <> struct Mth<float> {
     static __device__ __forceinline__ float pow_(float x, float y) { return powf(x, y); }
 };
 
-// normalization.py:8-10 (numpy floored modulo)
+// normalization.py:8-10 (numpy floored modulo).  The modulo is the identity on [0, 2pi): the fmod path is cold and out of line.
+template <typename R> __device__ __noinline__ R normalize_angle_slow(R y) {
+    const R two_pi = (R)(2.0 * SCG_PI);
+    y = Mth<R>::fmod_(y, two_pi);
+    if (y < (R)0) y += two_pi;
+    return y;
+}
 template <typename R> __device__ __forceinline__ R normalize_angle(R x) {
     const R two_pi = (R)(2.0 * SCG_PI);
     R y = x + (R)SCG_PI;
-    if (!(y >= (R)0 && y < two_pi)) {        // the floored modulo is the identity on [0, 2pi): skip fmod on the common path
-        y = Mth<R>::fmod_(y, two_pi);
-        if (y < (R)0) y += two_pi;
-    }
+    if (!(y >= (R)0 && y < two_pi)) y = normalize_angle_slow<R>(y);
     return y - (R)SCG_PI;
 }
 
@@ -449,6 +452,13 @@ template <typename R> struct Physics<SCG_SYS_QUAD1D, R> {
     }
 };
 
+// pitch as pybullet.getEulerFromQuaternion reports it for q = (0, sin(th/2), 0, cos(th/2)): asin(sin th), clamped at +-pi/2 when
+// |sin th| >= 0.99999.  Identical to th while |th| < ~1.5663, so only large angles come here (cold, out of line).
+template <typename R> __device__ __noinline__ R pitch_of_theta(R th) {
+    const R sarg = Mth<R>::sin_(th);
+    return (sarg <= (R)-0.99999) ? (R)(-0.5 * SCG_PI) : (sarg >= (R)0.99999) ? (R)(0.5 * SCG_PI) : Mth<R>::asin_(sarg);
+}
+
 template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
     // ps = x, vx, z, vz, theta, omega_y ; inertial = M, Ixx, Iyy, Izz
     // Within a control step thrust and torque are constant, so omega grows linearly and the per-sub-step angle increment
@@ -493,12 +503,7 @@ template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
     static __device__ __forceinline__ void state(const EnvRegs<SCG_SYS_QUAD2D, R>& e, R* s) {
         s[0] = e.ps[0]; s[1] = e.ps[1]; s[2] = e.ps[2]; s[3] = e.ps[3];
         R th = e.ps[4];
-        // pitch as pybullet.getEulerFromQuaternion reports it for q = (0, sin(th/2), 0, cos(th/2)): asin(sin th),
-        // clamped at +-pi/2 when |sin th| >= 0.99999.  Identical to th while |th| < ~1.5663.
-        if (Mth<R>::abs_(th) > (R)1.5) {
-            R sarg = Mth<R>::sin_(th);
-            th = (sarg <= (R)-0.99999) ? (R)(-0.5 * SCG_PI) : (sarg >= (R)0.99999) ? (R)(0.5 * SCG_PI) : Mth<R>::asin_(sarg);
-        }
+        if (Mth<R>::abs_(th) > (R)1.5) th = pitch_of_theta<R>(th);       // beyond the 85 deg bound: the episode is ending anyway
         s[4] = th; s[5] = e.ps[5];
     }
     static __device__ __forceinline__ void set_init(EnvRegs<SCG_SYS_QUAD2D, R>& e, const R* init) {
@@ -892,7 +897,7 @@ __device__ __forceinline__ int env_done(const HotCfg<R>* h, const GT* xg, const 
 
 // constraint_violation (benchmark_env.py:468-485) for z = [state ; current_noisy_physical_action] already staged in `zbuf`
 // (constraints.py:166-171); `zbuf` is this env's column of a shared scratch [NX+NU][zstride] of doubles.
-__device__ __forceinline__ int env_constraints(const DevTables& T, const ConRow* __restrict__ rows, int n_con, int con_fast,
+static __device__ __noinline__ int env_constraints(const DevTables& T, const ConRow* __restrict__ rows, int n_con, int con_fast,
                                                const double* __restrict__ zbuf, int zstride, double* cvals, float* cvals_f32) {
     int cviol = 0;
     if (con_fast) {

@@ -69,6 +69,10 @@ CASES = [
     ('quadrotor_2D_track', 128, 200, 64, {}),
     ('quadrotor_3D_track', 96, 200, 64, {}),
     ('quadrotor_2D_track', 40, 60, 128, dict(done_on_violation=True, use_constraint_penalty=True, constraint_penalty=0.5)),
+    # other CTA shapes of the fused collector (envs per CTA): 16 x 128 threads, 8 x 64 threads (owner lanes do everything)
+    ('quadrotor_2D_track', 72, 100, 64, {}, 16),
+    ('quadrotor_2D_track', 44, 100, 64, {}, 8),
+    ('cartpole_stab', 50, 64, 32, {}, 16),
 ]
 
 
@@ -98,7 +102,8 @@ def _compare_rollouts(o, g, N, T, obs_tol, state_tol):
 @pytest.mark.parametrize('prec', ['f64', 'f32'])
 @pytest.mark.parametrize('case', CASES, ids=[f'{c[0]}-h{c[3]}-{i}' for i, c in enumerate(CASES)])
 def test_fused_rollout_matches_oracle(case, prec):
-    name, N, T, hid, kw = case
+    name, N, T, hid, kw = case[:5]
+    epb = case[5] if len(case) > 5 else 0
     env = H.make_env(name, **kw)
     seed = 1000
     tab = H.episode_table(env, N, K=8, seed=seed)
@@ -114,7 +119,7 @@ def test_fused_rollout_matches_oracle(case, prec):
     eng.set_episode_table(tab)
     eng.reset()
     blob, dims = H.policy_blob(pol, eng.device)
-    gg = eng.rollout(blob, dims, T, eps=eps.to(eng.device), gamma=0.99, gae_lambda=0.95, use_gae=True,
+    gg = eng.rollout(blob, dims, T, eps=eps.to(eng.device), gamma=0.99, gae_lambda=0.95, use_gae=True, envs_per_block=epb,
                      want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode'))
     torch.cuda.synchronize()
     if prec == 'f64':
