@@ -94,7 +94,7 @@ def run_ours(args):
 
     import safe_control_gym_b200  # noqa: F401
     from safe_control_gym_b200 import configs
-    from safe_control_gym_b200.controllers.ppo.ppo import all_gather_rollout
+    from safe_control_gym_b200.controllers.ppo.ppo import PeerGatheredRollout, rollout_flat_numel
     from safe_control_gym_b200.engine import EngineHandle, pack_policy
     from safe_control_gym_b200.utils.registration import make
 
@@ -113,13 +113,16 @@ def run_ours(args):
     ac = build_policy(env).to(dev)
     blob, dims = pack_policy(ac, dev)
     want = ('ret', 'adv', 'cviol', 'last', 'episode')
-    out = eng.rollout(blob, dims, T_HORIZON, use_gae=True, want=want)
+    # N > 1: the rollout record is all-gathered INSIDE the collector kernel (peer stores over NVLink into every rank's gathered
+    # buffer, torch symmetric memory); the per-step collective is one barrier.  Falls back to the NCCL all-gather if P2P is unavailable.
+    pg = PeerGatheredRollout(rollout_flat_numel(dims[0], dims[1], T_HORIZON, N), dev) if world > 1 else None
+    out = eng.rollout(blob, dims, T_HORIZON, use_gae=True, want=want, **(pg.rollout_kwargs() if pg else {}))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
     def one_step():
         o = eng.rollout(blob, dims, T_HORIZON, use_gae=True, want=want, out=out)
         if world > 1:
-            all_gather_rollout(o)      # the single NCCL all-gather of the rollout buffer before the PPO update
+            pg.finish(o)               # gathered record complete on every rank (barrier; NCCL all-gather in the fallback)
         return o
 
     sampler = ClockSampler(local_rank)      # samples from the warm-up to the end of the end-to-end loop (the timed region alone is ~ms)
@@ -142,7 +145,7 @@ def run_ours(args):
         o = eng.rollout(blob, dims, T_HORIZON, use_gae=True, want=want, out=out)
         k.record()                     # kernel-only interval for the roofline
         if world > 1:
-            all_gather_rollout(o)
+            pg.finish(o)
         b.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -213,7 +216,9 @@ def run_ours(args):
             'data': 'synthetic (random-init 64-64 actor-critic, Philox-seeded initial states)',
             'config': {'workload': 'Quadrotor-2D trajectory tracking (quadrotor_2D_track.yaml), PPO 64-64 tanh actor-critic, fused rollout',
                        'envs_per_gpu': N, 'horizon': T_HORIZON, 'physics_substeps_per_step': 20, 'one_bench_step': 'one fused rollout launch',
-                       'parallelism': f'env-sharded x{world}' + (', one NCCL all-gather of the rollout record per step' if world > 1 else ''),
+                       'parallelism': f'env-sharded x{world}' + ('' if world == 1 else (
+                           ', rollout record all-gathered inside the collector kernel (NVLink peer stores, torch symmetric memory) + one barrier per step'
+                           if pg.fused else f', one NCCL all-gather of the rollout record per step (peer memory unavailable: {pg.why})')),
                        'l2': 'flushed with a 256 MiB write before every timed step; per-step CUDA-event intervals summed'},
             'gpu_launches': int(launches),
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': int(d2h_bytes),
@@ -263,9 +268,10 @@ def run_reference(args):
     if rank != 0:
         return None
     n = args.ref_envs
+    ncpu = os.cpu_count() or 1                 # torchrun exports OMP_NUM_THREADS=1: ask for every host thread explicitly
     for _ in range(args.warmup):
-        oracle_rate(n, 1)
-    rate, secs, threads = oracle_rate(n, args.steps)
+        oracle_rate(n, 1, threads=ncpu)
+    rate, secs, threads = oracle_rate(n, args.steps, threads=ncpu)
     return {
         'impl': 'reference', 'metric': 'env-steps/sec (4096 envs, 200-step horizon)', 'value': rate, 'unit': 'env-steps/s',
         'n_gpus': int(os.environ.get('WORLD_SIZE', '1')), 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': secs / args.steps * 1e3,

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SCG_ABI_VERSION 1
+#define SCG_ABI_VERSION 2
 
 #define SCG_MAX_NX 12          /* max state dim (Quadrotor-3D) */
 #define SCG_MAX_NU 4           /* max action dim */
@@ -220,6 +220,8 @@ typedef struct scg_step_out {
 } scg_step_out;
 
 /* Output buffers of the fused rollout, PPOBuffer scheme (ppo_utils.py:266-295): [T][N][.] float32. */
+#define SCG_MAX_PEERS 8
+
 typedef struct scg_rollout_out {
     float* d_obs;              /* [T][N][obs_dim] observation fed to the policy at step t */
     float* d_act;              /* [T][N][act_dim] */
@@ -254,6 +256,14 @@ typedef struct scg_rollout_args {
     double gamma, gae_lambda;
     const float* d_policy;     /* packed policy blob, layout of scg_policy_pack() */
     const float* d_eps;        /* [T][N][act_dim] standard-normal draws, or NULL -> Philox */
+    /* Fused rollout + all-gather over NVLink (the single collective of the path): every store to the PPOBuffer keys
+     * obs / act / rew / mask / v / logp / terminal_v / ret / adv is repeated at `pointer + peer_byte_offset[g]` for g < n_peers,
+     * i.e. into the same slot of each peer GPU's gathered buffer (peer-mapped memory, e.g. torch symmetric memory).  Those keys
+     * must then live in ONE allocation per GPU so that one offset per peer fits them all.  n_peers = 0: local stores only.  The
+     * caller orders the peers' reads after the kernel with its own barrier (stream-ordered). */
+    int32_t n_peers;
+    int32_t reserved0;
+    int64_t peer_byte_offset[SCG_MAX_PEERS];
 } scg_rollout_args;
 
 typedef struct scg_env scg_env;   /* opaque, one per (device, batch) */

@@ -74,6 +74,64 @@ def all_gather_rollout(out):
     return res
 
 
+def rollout_flat_numel(obs_dim, act_dim, T, n, with_ret_adv=True):
+    '''float32 elements of one rank's flat rollout record (the layout engine.rollout builds).'''
+    return (obs_dim + act_dim + 5 + (2 if with_ret_adv else 0)) * T * n
+
+
+class PeerGatheredRollout:
+    '''Fused rollout + all-gather: the gathered PPOBuffer record [G][flat] lives in peer-mapped memory (torch symmetric
+    memory over NVLink / NVSwitch); rank r's collector kernel writes every record entry into slot r of EVERY rank's copy while it
+    runs, so the only collective left is a barrier.  Falls back to the NCCL all-gather (all_gather_rollout) when symmetric memory
+    cannot be set up (no P2P access, old torch).
+
+        pg = PeerGatheredRollout(flat_numel, device)         # collective: every rank calls it
+        out = eng.rollout(..., **pg.rollout_kwargs())         # first call allocates the views on pg's slot
+        rec = pg.finish(out)                                  # barrier; per-key views [G][T*n][width] like all_gather_rollout
+    '''
+
+    def __init__(self, flat_numel, device, group=None):
+        import torch.distributed as dist
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.numel = int(flat_numel)
+        self.slot = ((self.numel * 4 + 127) // 128) * 32          # floats per slot, 128-byte aligned
+        self.fused, self.why = False, ''
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.buf = symm_mem.empty(self.world * self.slot, dtype=torch.float32, device=device)
+            self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+            ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+            mine = ptrs[self.rank]
+            self.offsets = [ptrs[g] - mine for g in range(self.world) if g != self.rank]
+            self.fused = True
+        except Exception as e:   # noqa: BLE001 -- any failure means "use the NCCL all-gather"
+            self.why = f'{type(e).__name__}: {e}'
+            self.buf = torch.empty(self.world * self.slot, dtype=torch.float32, device=device)
+            self.hdl, self.offsets = None, []
+        ok = torch.tensor([1 if self.fused else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)                # all ranks or none
+        if int(ok) == 0 and self.fused:
+            self.fused, self.offsets, self.why = False, [], 'a peer could not map symmetric memory'
+        self.local = self.buf[self.rank * self.slot: self.rank * self.slot + self.numel]
+
+    def rollout_kwargs(self):
+        return {'flat': self.local, 'peer_byte_offsets': self.offsets if self.fused else None}
+
+    def finish(self, out):
+        import torch.distributed as dist
+        if self.fused:
+            self.hdl.barrier(channel=0)                           # stream-ordered: every rank's kernel (and its peer stores) is done
+        else:
+            dist.all_gather_into_tensor(self.buf, self.buf[self.rank * self.slot:(self.rank + 1) * self.slot].clone())
+        g = self.buf.view(self.world, self.slot)
+        T, n = out['_TN']
+        res, o = {}, 0
+        for k, w in out['_layout']:
+            res[k] = g[:, o:o + T * n * w].view(self.world, T * n, w)
+            o += T * n * w
+        return res
+
+
 class PPO:
     '''Proximal policy optimisation on the fused collector.'''
 
@@ -169,8 +227,14 @@ class PPO:
         T = self.rollout_steps if T is None else T
         blob, dims = self._policy_blob()
         eng = self.env.unwrapped.engine
+        kw = {}
+        if self.world > 1 and eps is None and self._rollout_out is None:
+            # multi-GPU training: the record is written straight into every rank's gathered buffer (fused rollout + all-gather)
+            self._peer = PeerGatheredRollout(rollout_flat_numel(dims[0], dims[1], T, eng.N), self.device)
+            kw = self._peer.rollout_kwargs()
         out = eng.rollout(blob, dims, T, eps=eps, activation=self.activation, gamma=self.gamma, gae_lambda=self.gae_lambda,
-                          use_gae=self.use_gae, deterministic=deterministic, out=self._rollout_out if eps is None else None)
+                          use_gae=self.use_gae, deterministic=deterministic, out=self._rollout_out if eps is None else None,
+                          want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode'), **kw)
         if eps is None:
             self._rollout_out = out
         return out
@@ -188,7 +252,10 @@ class PPO:
         self.obs = out['last_obs']
         self.env.record_rollout(out)
         self.total_steps += self.rollout_batch_size * self.rollout_steps
-        batch = all_gather_rollout(out) if self.world > 1 else {k: v for k, v in out.items() if not k.startswith('_')}
+        if self.world > 1:
+            batch = self._peer.finish(out) if getattr(self, '_peer', None) is not None else all_gather_rollout(out)
+        else:
+            batch = {k: v for k, v in out.items() if not k.startswith('_')}
         adv = batch['adv']
         rollouts = dict(batch)
         rollouts['adv'] = (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-6)          # ppo.py:300 (numpy std, ddof=0)

@@ -344,6 +344,12 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
     P.T = a->T; P.activation = a->activation; P.use_gae = a->use_gae; P.deterministic = a->deterministic;
     P.gamma = (float)a->gamma; P.lam = (float)a->gae_lambda; P.gamma_d = a->gamma; P.lam_d = a->gae_lambda;
     P.policy = a->d_policy; P.eps = a->d_eps; P.noise_cursor = e->noise_cursor; P.out = *out; P.prof = nullptr;
+    if (a->n_peers < 0 || a->n_peers > SCG_MAX_PEERS) return fail(e, SCG_EINVAL, "scg_rollout: n_peers out of range");
+    P.n_peers = a->n_peers;
+    for (int g = 0; g < SCG_MAX_PEERS; ++g) {
+        P.peer_off[g] = g < a->n_peers ? a->peer_byte_offset[g] : 0;
+        if (P.peer_off[g] & 15) return fail(e, SCG_EINVAL, "scg_rollout: peer_byte_offset must be a multiple of 16");
+    }
 #ifdef SCG_PROF
     static long long* d_prof = nullptr;
     if (!d_prof) cudaMalloc((void**)&d_prof, (16 + 2048) * sizeof(long long));

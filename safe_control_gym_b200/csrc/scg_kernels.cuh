@@ -267,6 +267,8 @@ struct RolloutParams {
     const float* eps;    // [T][N][A] or null
     long long noise_cursor;
     scg_rollout_out out;
+    int n_peers;                 // fused all-gather: peer copies of the PPOBuffer keys (see scg_rollout_args)
+    long long peer_off[SCG_MAX_PEERS];
     long long* prof;     // SCG_PROF builds: per-phase cycle counters of CTA 0 (nullable)
 };
 
@@ -441,6 +443,13 @@ __device__ __forceinline__ float mlp_out(const float* __restrict__ s_outp, const
 #define PROF_T(v) do { } while (0)
 #endif
 
+// Record store that is repeated into the peers' gathered buffers (NVLink peer memory; plain posted writes, coalesced like the
+// local ones): the all-gather of the rollout record happens inside the collector, there is no separate collective to wait for.
+template <typename V> __device__ __forceinline__ void pstore(const RolloutParams& P, V* ptr, V v) {
+    *ptr = v;
+    for (int g = 0; g < P.n_peers; ++g) *reinterpret_cast<V*>(reinterpret_cast<char*>(ptr) + P.peer_off[g]) = v;
+}
+
 // CTAs per SM the register allocation is capped for: the 16-thread-per-env variants (E=16 x 256 threads, E=8 x 128 threads) halve
 // the per-step MLP latency of a CTA and rely on TWO (or more) co-resident CTAs per SM to fill the machine.
 __host__ __device__ constexpr int rollout_min_blocks(int HID, int E, int NT) {
@@ -469,6 +478,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     __shared__ double s_cand[2 * NC * E];
     __shared__ int s_cand_ep[2 * E];           // episode index held by each candidate slot (-1 = empty)
     __shared__ int s_epi[E];                   // next episode index of each env, published by its owner lane
+    __shared__ float s_rec[2 * (A + 2) * E];   // FAST: act, v, logp of the last two steps, stored to the record by a helper warp
     __shared__ float s_stat[6 * E];            // FAST: episode statistics kept by the record helpers, handed back at the end
     __shared__ int s_epc[E];
 
@@ -532,13 +542,30 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
         if (role == 2) { h_a = T.st.ep_acc[n0 + ee]; h_b = T.st.ep_acc[N + n0 + ee]; }
         if (role == 1) h_a = T.st.ep_acc[2 * N + n0 + ee];
     }
-    // record entries of step tp that are not on the owners' critical path (reward, mse, constraint rows, episode statistics)
+    auto store_policy_record = [&](size_t tn, const float* act, float val, float logp, int done, int truncated) {
+        if (A == 2) pstore(P, reinterpret_cast<float2*>(P.out.d_act + tn * A), make_float2(act[0], act[1 % A]));
+        else if (A == 4) pstore(P, reinterpret_cast<float4*>(P.out.d_act + tn * A), make_float4(act[0], act[1 % A], act[2 % A], act[3 % A]));
+        else pstore(P, P.out.d_act + tn * A, act[0]);
+        pstore(P, P.out.d_v + tn, val);
+        pstore(P, P.out.d_logp + tn, logp);
+        pstore(P, P.out.d_mask + tn, done ? 0.f : 1.f);
+        if (!truncated) pstore(P, P.out.d_terminal_v + tn, 0.f);       // truncated: the terminal-value pass stores critic(terminal obs)
+    };
+    // record entries of step tp that are not on the owners' critical path (reward, mse, constraint rows, episode statistics,
+    // and the stores of act / v / logp / mask / terminal_v the owner lane left in shared memory)
     auto process_record = [&](int tp) {
         const int bsel = tp & 1;
         const double* zb = s_z + bsel * NZ * E + ee;
         const size_t tnp = (size_t)tp * N + n0 + ee;
-        const int dn = s_flag[bsel * E + ee] & 1;
-        if (role == 1) {                                                   // constraints (benchmark_env.py:472-485)
+        const int fl = s_flag[bsel * E + ee], dn = fl & 1;
+        if (role == 1) {                                                   // constraints (benchmark_env.py:472-485) + policy part of the record
+            {
+                const float* rb = s_rec + bsel * (A + 2) * E + ee;
+                float act[A];
+#pragma unroll
+                for (int k = 0; k < A; ++k) act[k] = rb[k * E];
+                store_policy_record(tnp, act, rb[A * E], rb[(A + 1) * E], dn, fl >> 1);
+            }
             int cv = 0;
             if (nc > 0) cv = env_constraints(T, h->rows, nc, h->con_fast, zb, E, nullptr, P.out.d_cvals ? P.out.d_cvals + tnp * nc : nullptr);
             if (P.out.d_cviol) P.out.d_cviol[tnp] = (float)cv;
@@ -551,7 +578,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
 #pragma unroll
             for (int k = 0; k < A; ++k) { ny[k] = (R)zb[(NX + k) * E]; cl[k] = (R)zb[(NX + A + k) * E]; }
             env_reward_mse<SYS, R, R>(h, s_xg, st, ny, cl, s_cstep[bsel * E + ee], rw, ms);
-            P.out.d_rew[tnp] = (float)rw;
+            pstore(P, P.out.d_rew + tnp, (float)rw);
             if (P.out.d_mse) P.out.d_mse[tnp] = (float)ms;
             h_a += (float)rw; h_b += 1.f;
             if (dn) { h_cnt += 1; h_sa += h_a; h_sb += h_b; h_a = 0.f; h_b = 0.f; }
@@ -614,7 +641,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
         int k = t0 % od, en = t0 / od;
         const int dk = nthr % od, de = nthr / od;
         for (int i = t0; i < lim; i += nthr) {
-            dst[i] = tile[tile_idx<E>(k, en)];
+            pstore(P, dst + i, tile[tile_idx<E>(k, en)]);
             k += dk; en += de;
             if (k >= od) { k -= od; en += 1; }
         }
@@ -734,18 +761,20 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                     } else {
                         make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_on, ol});
                     }
-                    P.out.d_rew[tn] = (float)rew;
+                    pstore(P, P.out.d_rew + tn, (float)rew);
                     if (P.out.d_cviol) P.out.d_cviol[tn] = (float)cviol;
                     if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
                 }
                 trunc = truncated;
-                if (A == 2) *reinterpret_cast<float2*>(P.out.d_act + tn * A) = make_float2(act[0], act[1 % A]);
-                else if (A == 4) *reinterpret_cast<float4*>(P.out.d_act + tn * A) = make_float4(act[0], act[1 % A], act[2 % A], act[3 % A]);
-                else P.out.d_act[tn * A] = act[0];
-                P.out.d_v[tn] = val;
-                P.out.d_logp[tn] = logp;
-                P.out.d_mask[tn] = done ? 0.f : 1.f;
-                if (!truncated) P.out.d_terminal_v[tn] = 0.f;
+                if (fast) {
+                    // the record entries go through shared memory: a helper warp stores them (and their peer copies) one step later
+                    float* rb = s_rec + (t & 1) * (A + 2) * E + ol;
+#pragma unroll
+                    for (int k = 0; k < A; ++k) rb[k * E] = act[k];
+                    rb[A * E] = val; rb[(A + 1) * E] = logp;
+                } else {
+                    store_policy_record(tn, act, val, logp, done, truncated);
+                }
             }
             SCG_TK(12);
 #ifdef SCG_PROF
@@ -769,7 +798,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
 #endif
         if (any_trunc) {
             mlp_forward<HID, E, NT, A>(s_blob, L, s_tobs, s_h1, s_out, od, P.activation);
-            if (live && trunc) P.out.d_terminal_v[tn0 + ol] = mlp_out<E, NW, A>(s_out, s_blob, L, A, ol);
+            if (live && trunc) pstore(P, P.out.d_terminal_v + tn0 + ol, mlp_out<E, NW, A>(s_out, s_blob, L, A, ol));
             __syncthreads();
         }
         cur ^= 1;
@@ -822,12 +851,12 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                     if (j < cnt) {
                         const size_t tn = (size_t)(t1 - 1 - j) * N + n;
                         const float r = rr[j] + P.gamma * tv[j];
-                        P.out.d_rew[tn] = r;                               // rews += gamma * terminal_v, in place (ppo_utils.py:389)
+                        pstore(P, P.out.d_rew + tn, r);                     // rews += gamma * terminal_v, in place (ppo_utils.py:389)
                         const float m = mm[j], v = vv[j];
                         ret = r + P.gamma * m * ret;
                         if (!P.use_gae) adv = (double)(ret - v);
                         else { const float td = r + P.gamma * m * vnext - v; adv = adv * P.lam_d * P.gamma_d * (double)m + (double)td; }
-                        P.out.d_ret[tn] = ret; P.out.d_adv[tn] = (float)adv; vnext = v;
+                        pstore(P, P.out.d_ret + tn, ret); pstore(P, P.out.d_adv + tn, (float)adv); vnext = v;
                     }
                 }
             }

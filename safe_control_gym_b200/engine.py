@@ -153,8 +153,13 @@ class EngineHandle:
         return b
 
     def rollout(self, policy_blob, dims, T, eps=None, activation='tanh', gamma=0.99, gae_lambda=0.95, use_gae=False,
-                deterministic=False, envs_per_block=0, want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode'), out=None):
-        '''One fused launch: T steps of policy + env for all N envs.  Returns PPOBuffer-shaped torch.cuda tensors.'''
+                deterministic=False, envs_per_block=0, want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode'), out=None,
+                flat=None, peer_byte_offsets=None):
+        '''One fused launch: T steps of policy + env for all N envs.  Returns PPOBuffer-shaped torch.cuda tensors.
+
+        flat: optional caller-owned float32 buffer for the PPOBuffer keys (e.g. this rank's slot of a peer-mapped gathered buffer);
+        peer_byte_offsets: byte distances from that slot to the same slot in each peer GPU's gathered buffer -- the kernel then
+        repeats every record store there (fused rollout + all-gather over NVLink, see PeerGatheredRollout in controllers/ppo).'''
         dev, N = self.device, self.N
         obs_dim, act_dim, hid = dims
         f32 = torch.float32
@@ -164,7 +169,10 @@ class EngineHandle:
             widths = [('obs', obs_dim), ('act', act_dim), ('rew', 1), ('mask', 1), ('v', 1), ('logp', 1), ('terminal_v', 1)]
             if 'ret' in want or 'adv' in want:
                 widths += [('ret', 1), ('adv', 1)]
-            flat = torch.empty(sum(w for _, w in widths) * T * N, dtype=f32, device=dev)
+            numel = sum(w for _, w in widths) * T * N
+            if flat is None:
+                flat = torch.empty(numel, dtype=f32, device=dev)
+            assert flat.is_cuda and flat.dtype == f32 and flat.is_contiguous() and flat.numel() == numel, (flat.shape, numel)
             out, o = {'_flat': flat, '_layout': [(k, w) for k, w in widths], '_TN': (T, N)}, 0
             for k, w in widths:
                 out[k] = flat[o:o + T * N * w].view(T, N, w)
@@ -197,6 +205,14 @@ class EngineHandle:
             assert eps.dtype == torch.float32 and eps.is_cuda and tuple(eps.shape) == (T, N, act_dim), (eps.dtype, eps.shape)
             eps = eps.contiguous()
         args.d_eps = eps.data_ptr() if eps is not None else None
+        offs = list(peer_byte_offsets) if peer_byte_offsets is not None else out.get('_peer_byte_offsets', [])
+        if len(offs) > _abi.SCG_MAX_PEERS:
+            raise ValueError(f'at most {_abi.SCG_MAX_PEERS} peers')
+        args.n_peers = len(offs)
+        for g, v in enumerate(offs):
+            args.peer_byte_offset[g] = int(v)
+        if offs:
+            out['_peer_byte_offsets'] = offs
         _abi.check(self.lib.scg_rollout(self.h, C.byref(args), C.byref(ro), self._stream()), self.h)
         return out
 

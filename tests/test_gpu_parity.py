@@ -235,3 +235,31 @@ def test_state_checkpoint_roundtrip():
     b = [_np(eng.step(acts[t])['state_f64']).copy() for t in range(10, 20)]
     np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
     eng.close()
+
+
+def test_fused_peer_gather_writes_identical_copies():
+    '''Fused rollout + all-gather (scg_rollout_args.n_peers): every PPOBuffer store is repeated at pointer + peer offset.  On one
+    GPU the "peers" are two more slots of the same allocation; all copies must be bit-identical and equal to a plain rollout.'''
+    from safe_control_gym_b200.controllers.ppo.ppo import rollout_flat_numel
+    N, T, hid = 80, 60, 64
+    env = H.make_env('quadrotor_2D_track')
+    pol = H.random_policy(env.obs_dim, env.action_dim, hid, seed=0, activation='tanh')
+    numel = rollout_flat_numel(env.obs_dim, env.action_dim, T, N)
+    slot = ((numel * 4 + 127) // 128) * 32
+    outs = []
+    for peers in (0, 2):
+        eng = _engine(env, N, auto_reset=True, precision='f64', rng_mode='philox', seed=7)
+        eng.reset()
+        blob, dims = H.policy_blob(pol, eng.device)
+        buf = torch.zeros(3 * slot, dtype=torch.float32, device=eng.device)
+        offs = [slot * 4 * (g + 1) for g in range(peers)]
+        out = eng.rollout(blob, dims, T, use_gae=True, flat=buf[:numel], peer_byte_offsets=offs, want=('ret', 'adv'))
+        torch.cuda.synchronize()
+        outs.append(buf.clone())
+        if peers:
+            for g in range(peers):
+                assert torch.equal(buf[:numel], buf[slot * (g + 1): slot * (g + 1) + numel])
+        else:
+            assert float(buf[slot:].abs().max()) == 0.0
+        eng.close()
+    assert torch.equal(outs[0][:numel], outs[1][:numel])
