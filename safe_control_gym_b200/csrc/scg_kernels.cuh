@@ -533,6 +533,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     const bool philox_eps = (P.eps == nullptr);
     const bool obs_noise = h->has_dist[SCG_MODE_OBSERVATION] != 0;
     const bool fast = use_cand && !obs_noise && !h->done_on_violation && !h->use_penalty;
+    const bool relay = fast && P.n_peers > 0;   // the owner lanes leave act / v / logp to a helper warp when every store has peer copies
     const int OBS_TILE = od * E;
     // ---- helper-warp work of the FAST schedule (lane ee = env ee of the CTA)
     const int ee = lane;
@@ -559,7 +560,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
         const size_t tnp = (size_t)tp * N + n0 + ee;
         const int fl = s_flag[bsel * E + ee], dn = fl & 1;
         if (role == 1) {                                                   // constraints (benchmark_env.py:472-485) + policy part of the record
-            {
+            if (relay) {
                 const float* rb = s_rec + bsel * (A + 2) * E + ee;
                 float act[A];
 #pragma unroll
@@ -766,8 +767,8 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                     if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
                 }
                 trunc = truncated;
-                if (fast) {
-                    // the record entries go through shared memory: a helper warp stores them (and their peer copies) one step later
+                if (relay) {
+                    // multi-GPU: the record entries go through shared memory, a helper warp stores them and their peer copies one step later
                     float* rb = s_rec + (t & 1) * (A + 2) * E + ol;
 #pragma unroll
                     for (int k = 0; k < A; ++k) rb[k * E] = act[k];
