@@ -29,6 +29,15 @@ def _worker(rank, world, port, q):
         out[k] = flat[o:o + T * n * w].view(T, n, w)
         o += T * n * w
     res = all_gather_rollout(out)
+    # the peer-memory gatherer must fall back to the same collective where symmetric memory is unavailable (CPU / gloo)
+    from safe_control_gym_b200.controllers.ppo.ppo import PeerGatheredRollout, rollout_flat_numel
+    assert rollout_flat_numel(12, 2, T, n) == flat.numel()
+    pg = PeerGatheredRollout(flat.numel(), torch.device('cpu'))
+    assert not pg.fused and pg.rollout_kwargs()['peer_byte_offsets'] is None
+    pg.rollout_kwargs()['flat'].copy_(flat)                     # what the collector kernel would have written into the local slot
+    res2 = pg.finish(out)
+    for k in res:
+        assert torch.equal(res[k], res2[k]), k
     q.put((rank, {k: v.numpy().copy() for k, v in res.items()}, {k: out[k].numpy().copy() for k, _ in layout}))
     dist.destroy_process_group()
 
