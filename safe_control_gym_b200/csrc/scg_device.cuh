@@ -635,17 +635,19 @@ __device__ __forceinline__ void make_obs(const DevTables& T, const HotCfg<R>* h,
             sink(k, v);
         }
     }
-    if (h->obs_goal_horizon > 0) {
-        if (h->task == SCG_TASK_TRAJ_TRACKING) {
-            const int next_step = at_reset ? 1 : ctrl_step + 2;
-            for (int hh = 0; hh < h->obs_goal_horizon; ++hh) {
-                const GT* g = goal_row<GT>(xg, h->L, h->task, NX, next_step + hh);
+    // goal part: the row is read into registers BEFORE the first store -- sink and table may both be shared memory, and the
+    // compiler must otherwise keep every load behind the previous store (a serial LDS -> convert -> STS chain per element)
+    const int horizon = h->obs_goal_horizon;
+    if (horizon > 0) {
+        const bool tracking = h->task == SCG_TASK_TRAJ_TRACKING;
+        const int next_step = at_reset ? 1 : ctrl_step + 2, Lr = h->L;
+        for (int hh = 0; hh < (tracking ? horizon : 1); ++hh) {
+            const GT* g = tracking ? goal_row<GT>(xg, Lr, SCG_TASK_TRAJ_TRACKING, NX, next_step + hh) : xg;
+            GT gv[NX];
 #pragma unroll
-                for (int k = 0; k < NX; ++k) sink(NX * (1 + hh) + k, (R)g[k]);
-            }
-        } else {
+            for (int k = 0; k < NX; ++k) gv[k] = g[k];
 #pragma unroll
-            for (int k = 0; k < NX; ++k) sink(NX + k, (R)xg[k]);
+            for (int k = 0; k < NX; ++k) sink(NX * (1 + hh) + k, (R)gv[k]);
         }
     }
 }

@@ -736,7 +736,13 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
 #pragma unroll
                             for (int j = 0; j < PS; ++j) e.ps[j] = (R)cd[(SCG_MAX_INERTIAL + 2 + j) * E];
                             const float* co = s_cobs + slot * OBS_TILE + ol;
-                            for (int k = 0; k < od; ++k) s_on[tile_idx<E>(k, ol)] = co[k * E];
+                            for (int k = 0; k < od; k += 4) {               // loads first, then stores (both shared memory: no serial chain)
+                                float cv[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) cv[j] = (k + j < od) ? co[(k + j) * E] : 0.f;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) if (k + j < od) s_on[tile_idx<E>(k + j, ol)] = cv[j];
+                            }
                             e.ctrl_step = 0; e.episode += 1;
                         } else {                                           // not drawn yet (first steps of a launch): draw inline
                             env_reset<SYS, R>(T, h, n, e, state);
@@ -852,13 +858,31 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                     if (j < cnt) {
                         const size_t tn = (size_t)(t1 - 1 - j) * N + n;
                         const float r = rr[j] + P.gamma * tv[j];
-                        pstore(P, P.out.d_rew + tn, r);                     // rews += gamma * terminal_v, in place (ppo_utils.py:389)
+                        P.out.d_rew[tn] = r;                               // rews += gamma * terminal_v, in place (ppo_utils.py:389)
                         const float m = mm[j], v = vv[j];
                         ret = r + P.gamma * m * ret;
                         if (!P.use_gae) adv = (double)(ret - v);
                         else { const float td = r + P.gamma * m * vnext - v; adv = adv * P.lam_d * P.gamma_d * (double)m + (double)td; }
-                        pstore(P, P.out.d_ret + tn, ret); pstore(P, P.out.d_adv + tn, (float)adv); vnext = v;
+                        P.out.d_ret[tn] = ret; P.out.d_adv[tn] = (float)adv; vnext = v;
                     }
+                }
+            }
+        }
+    }
+    // fused all-gather: the scan above is one serial chain per env, so its three columns (rew, ret, adv) reach the peers afterwards,
+    // copied by the whole CTA (rows of E consecutive floats per step)
+    if (P.n_peers > 0 && P.out.d_ret && P.out.d_adv) {
+        __syncthreads();
+        const int cols = N - n0 < E ? N - n0 : E;
+        for (int i = tid; i < P.T * E; i += NT) {
+            const int tt = i / E, c = i % E;
+            if (c < cols) {
+                const size_t tn = (size_t)tt * N + n0 + c;
+                const float r = P.out.d_rew[tn], q = P.out.d_ret[tn], a = P.out.d_adv[tn];
+                for (int g = 0; g < P.n_peers; ++g) {
+                    *reinterpret_cast<float*>(reinterpret_cast<char*>(P.out.d_rew + tn) + P.peer_off[g]) = r;
+                    *reinterpret_cast<float*>(reinterpret_cast<char*>(P.out.d_ret + tn) + P.peer_off[g]) = q;
+                    *reinterpret_cast<float*>(reinterpret_cast<char*>(P.out.d_adv + tn) + P.peer_off[g]) = a;
                 }
             }
         }
