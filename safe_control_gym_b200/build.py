@@ -13,9 +13,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['scg_api.cu', 'scg_ppo.cu', 'scg_kernels.cuh', 'scg_device.cuh']
-UNITS = ['scg_api.cu', 'scg_ppo.cu']          # translation units of libscg_b200.so
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-shared', '-Xcompiler', '-fPIC']
+ROLLOUT_UNITS = [f'scg_rollout_{s}_{p}.cu' for s in ('quad3d', 'quad2d', 'cartpole') for p in ('f64', 'f32')]   # slowest first
+UNITS = ROLLOUT_UNITS + ['scg_api.cu', 'scg_ppo.cu']          # translation units of libscg_b200.so (compiled in parallel)
+SOURCES = UNITS + ['scg_kernels.cuh', 'scg_device.cuh', 'scg_rollout_launch.cuh']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-shared', '-Xcompiler', '-fPIC',
+              '--compress-mode=size']     # line tables make the fatbin large; the compressed image travels to the GPU box faster
 
 
 def _stale(target, deps):
@@ -33,7 +35,7 @@ def build_cuda(force=False, prof=False, verbose=True, dev=False):
     if not force and not _stale(out, deps):
         return out
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = ([nvcc] + NVCC_FLAGS + ['--threads', str(len(UNITS))] + (['-DSCG_PROF'] if prof else []) + (['-DSCG_DEV_HID64_ONLY'] if dev else [])
+    cmd = ([nvcc] + NVCC_FLAGS + ['--threads', str(min(len(UNITS), os.cpu_count() or 1))] + (['-DSCG_PROF'] if prof else []) + (['-DSCG_DEV_HID64_ONLY'] if dev else [])
            + ['-I', os.path.join(ROOT, 'include'), '-o', out] + [os.path.join(CSRC, u) for u in UNITS])
     if verbose:
         print(' '.join(cmd), flush=True)

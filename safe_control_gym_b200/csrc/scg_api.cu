@@ -13,6 +13,7 @@
 
 #include "scg.h"
 #include "scg_kernels.cuh"
+#include "scg_rollout_launch.cuh"
 
 struct scg_env {
     scg_config cfg;
@@ -268,64 +269,6 @@ int scg_step(scg_env* e, const float* d_act, const double* d_act_f64, const scg_
     return SCG_OK;
 }
 
-extern "C++" {
-template <int SYS, typename R, int HID, int E, int NT>
-static int launch_rollout(scg_env* e, const RolloutParams& P, cudaStream_t s) {
-    const RolloutSmem<HID, E> S(e->obs_dim, e->nu, e->L * e->nx * (int)(sizeof(R) / 4), NT / 64);
-    const size_t smem = (size_t)S.total_floats * sizeof(float);
-    auto kern = rollout_kernel<SYS, R, HID, E, NT>;
-    CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // the kernel lives out of shared memory (weights, tiles, tables): ask for the largest carve-out so several CTAs fit per SM
-    CUDA_TRY(e, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    const int G = (e->cfg.num_envs + E - 1) / E;
-    kern<<<G, NT, smem, s>>>(e->tab, P);
-    CUDA_TRY(e, cudaGetLastError());
-    return SCG_OK;
-}
-
-// envs_per_block -> (E, threads): a CTA always runs 8 threads per env (4x4 register tiles at hidden 64), so smaller E means
-// smaller CTAs and MORE of them per SM: the serial env-step section of one CTA then overlaps the MLP phase of its neighbours.
-template <int SYS, typename R>
-static int dispatch_rollout(scg_env* e, const scg_rollout_args* a, const RolloutParams& P, cudaStream_t s) {
-    int E = a->envs_per_block & 0xffff;
-    const int NTq = (a->envs_per_block >> 16) & 0xffff;   // requested threads per CTA (0 = 8 per env)
-#ifdef SCG_PROF
-    if (a->hidden_dim == 64 && (E == 0 || E == 32)) return launch_rollout<SYS, R, 64, 32, 256>(e, P, s);
-    if (a->hidden_dim == 64 && E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, s);
-    return fail(e, SCG_EINVAL, "SCG_PROF build: only hidden 64 / E 32 or 16");
-#else
-    switch (a->hidden_dim) {
-#ifndef SCG_DEV_HID64_ONLY
-        case 32:
-            if (E == 0) E = e->cfg.num_envs >= 16384 ? 16 : 32;
-            if (E == 32) return launch_rollout<SYS, R, 32, 32, 256>(e, P, s);
-            if (E == 16) return launch_rollout<SYS, R, 32, 16, 128>(e, P, s);
-            break;
-#endif
-        case 64:
-            if (E == 0) E = e->cfg.num_envs >= 16384 ? 16 : 32;   // many CTAs per SM at large N, one 8-warp CTA per SM otherwise
-#ifdef SCG_DEV_HID64_ONLY   // 16 threads per env, two CTAs per SM: measured slower than the 8-thread-per-env variants (round 1)
-            if (E == 16 && NTq == 256) return launch_rollout<SYS, R, 64, 16, 256>(e, P, s);
-            if (E == 8 && NTq == 128) return launch_rollout<SYS, R, 64, 8, 128>(e, P, s);
-#endif
-            if (E == 32) return launch_rollout<SYS, R, 64, 32, 256>(e, P, s);
-            if (E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, s);
-            if (E == 8) return launch_rollout<SYS, R, 64, 8, 64>(e, P, s);
-            break;
-#ifndef SCG_DEV_HID64_ONLY
-        case 128:
-            if (E == 0) E = 16;
-            if (E == 16) return launch_rollout<SYS, R, 128, 16, 256>(e, P, s);
-            if (E == 8) return launch_rollout<SYS, R, 128, 8, 128>(e, P, s);
-            break;
-#endif
-        default: return fail(e, SCG_EINVAL, "scg_rollout: hidden_dim must be 32, 64 or 128");
-    }
-    return fail(e, SCG_EINVAL, "scg_rollout: unsupported envs_per_block for this hidden_dim");
-#endif
-}
-}  // extern C++
-
 int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* out, void* stream) {
     int rc = check_ready(e, "scg_rollout"); if (rc) return rc;
     if (!a || !out) return fail(e, SCG_EINVAL, "scg_rollout: null argument");
@@ -350,44 +293,18 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
         P.peer_off[g] = g < a->n_peers ? a->peer_byte_offset[g] : 0;
         if (P.peer_off[g] & 15) return fail(e, SCG_EINVAL, "scg_rollout: peer_byte_offset must be a multiple of 16");
     }
-#ifdef SCG_PROF
-    static long long* d_prof = nullptr;
-    if (!d_prof) cudaMalloc((void**)&d_prof, (16 + 2048) * sizeof(long long));
-    cudaMemset(d_prof, 0, (16 + 2048) * sizeof(long long));
-    P.prof = d_prof;
-    { long long z[64] = {0}; cudaMemcpyToSymbol(scg_ticks, z, sizeof(z)); }
-#endif
     cudaStream_t s = (cudaStream_t)stream;
     const bool dbl = e->cfg.precision == SCG_PREC_F64;
+    RolloutLaunch rl{e->cfg.num_envs, e->obs_dim, e->nu, e->nx, e->L, e->tab};
+    RolloutLaunchResult r;
     switch (e->cfg.system) {
-        case SCG_SYS_CARTPOLE: rc = dbl ? dispatch_rollout<SCG_SYS_CARTPOLE, double>(e, a, P, s) : dispatch_rollout<SCG_SYS_CARTPOLE, float>(e, a, P, s); break;
-        case SCG_SYS_QUAD2D: rc = dbl ? dispatch_rollout<SCG_SYS_QUAD2D, double>(e, a, P, s) : dispatch_rollout<SCG_SYS_QUAD2D, float>(e, a, P, s); break;
-        case SCG_SYS_QUAD3D: rc = dbl ? dispatch_rollout<SCG_SYS_QUAD3D, double>(e, a, P, s) : dispatch_rollout<SCG_SYS_QUAD3D, float>(e, a, P, s); break;
+        case SCG_SYS_CARTPOLE: r = dbl ? scg_rollout_cartpole_f64(rl, a, P, s) : scg_rollout_cartpole_f32(rl, a, P, s); break;
+        case SCG_SYS_QUAD2D: r = dbl ? scg_rollout_quad2d_f64(rl, a, P, s) : scg_rollout_quad2d_f32(rl, a, P, s); break;
+        case SCG_SYS_QUAD3D: r = dbl ? scg_rollout_quad3d_f64(rl, a, P, s) : scg_rollout_quad3d_f32(rl, a, P, s); break;
         default: return fail(e, SCG_EINVAL, "scg_rollout: the fused collector supports cartpole, quadrotor 2D and 3D");
     }
-    if (rc) return rc;
-#ifdef SCG_PROF
-    {
-        long long hp[16]; cudaMemcpy(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost);
-        const char* nm[8] = {"eps+obs_write", "mlp", "sample+pre+physics", "helpers/done(wait)", "finalize+reset+stores", "end barrier", "-", "tail(mlp+gae)"};
-        fprintf(stderr, "[SCG_PROF] CTA0 cycles per step (T=%d):", a->T);
-        for (int i = 0; i < 8; ++i) if (nm[i][0] != '-') fprintf(stderr, " %s=%.0f", nm[i], i == 7 ? (double)hp[i] : (double)hp[i] / a->T);
-        fprintf(stderr, "\n");
-        {
-            long long tk[64]; cudaMemcpyFromSymbol(tk, scg_ticks, sizeof(tk));
-            fprintf(stderr, "[SCG_PROF] ticks/step:");
-            for (int i = 0; i < 25; ++i) fprintf(stderr, " %d:%.0f", i, (double)tk[i] / a->T);
-            fprintf(stderr, "\n");
-        }
-        {
-            std::vector<long long> ct(2048); cudaMemcpy(ct.data(), d_prof + 16, 2048 * sizeof(long long), cudaMemcpyDeviceToHost);
-            int G = (e->cfg.num_envs + 31) / 32; if (G > 1024) G = 1024;
-            long long mn = ct[0], mx = ct[0]; int imx = 0; double sum = 0;
-            for (int i = 0; i < G; ++i) { if (ct[i] < mn) mn = ct[i]; if (ct[i] > mx) { mx = ct[i]; imx = i; } sum += ct[i]; }
-            fprintf(stderr, "[SCG_PROF] per-CTA horizon cycles: min=%lld mean=%.0f max=%lld (cta %d, owner-lane-0 resets %lld vs cta0 %lld)\n", mn, sum / G, mx, imx, ct[1024 + imx], ct[1024]);
-        }
-    }
-#endif
+    if (r.code == SCG_ECUDA) return fail(e, SCG_ECUDA, std::string(r.msg) + ": " + cudaGetErrorString(r.cuda));
+    if (r.code != SCG_OK) return fail(e, r.code, r.msg);
     e->launches += 1; e->noise_cursor += a->T;
     return SCG_OK;
 }

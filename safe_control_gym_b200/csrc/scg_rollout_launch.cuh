@@ -1,0 +1,110 @@
+// scg_rollout_launch.cuh -- launch + variant dispatch of rollout_kernel, shared by the per-(system, precision) translation
+// units scg_rollout_*.cu.  The rollout kernel is by far the most expensive template to compile; one translation unit per
+// (system, precision) lets nvcc build them in parallel (build.py: --threads).  scg_api.cu only sees the entry points below.
+#pragma once
+#include <cstdio>
+#include <vector>
+#include "scg_kernels.cuh"
+
+struct RolloutLaunch {          // what a launch needs from the handle
+    int num_envs, obs_dim, nu, nx, L;
+    DevTables tab;
+};
+struct RolloutLaunchResult {    // code: SCG_OK / SCG_EINVAL (msg) / SCG_ECUDA (cuda, msg = failing call)
+    int code; cudaError_t cuda; const char* msg;
+};
+
+RolloutLaunchResult scg_rollout_cartpole_f64(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
+RolloutLaunchResult scg_rollout_cartpole_f32(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
+RolloutLaunchResult scg_rollout_quad2d_f64(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
+RolloutLaunchResult scg_rollout_quad2d_f32(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
+RolloutLaunchResult scg_rollout_quad3d_f64(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
+RolloutLaunchResult scg_rollout_quad3d_f32(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
+
+#ifdef SCG_ROLLOUT_IMPL   // defined by the scg_rollout_*.cu units only
+#define RL_CUDA(call) do { cudaError_t st_ = (call); if (st_ != cudaSuccess) return RolloutLaunchResult{SCG_ECUDA, st_, #call}; } while (0)
+
+template <int SYS, typename R, int HID, int E, int NT>
+static RolloutLaunchResult launch_rollout(const RolloutLaunch& e, RolloutParams P, const scg_rollout_args* a, cudaStream_t s) {
+    const RolloutSmem<HID, E> S(e.obs_dim, e.nu, e.L * e.nx * (int)(sizeof(R) / 4), NT / 64);
+    const size_t smem = (size_t)S.total_floats * sizeof(float);
+    auto kern = rollout_kernel<SYS, R, HID, E, NT>;
+    RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the kernel lives out of shared memory (weights, tiles, tables): ask for the largest carve-out so several CTAs fit per SM
+    RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    const int G = (e.num_envs + E - 1) / E;
+#ifdef SCG_PROF
+    static long long* d_prof = nullptr;
+    if (!d_prof) cudaMalloc((void**)&d_prof, (16 + 2048) * sizeof(long long));
+    cudaMemset(d_prof, 0, (16 + 2048) * sizeof(long long));
+    P.prof = d_prof;
+    { long long z[64] = {0}; cudaMemcpyToSymbol(scg_ticks, z, sizeof(z)); }
+#endif
+    kern<<<G, NT, smem, s>>>(e.tab, P);
+    RL_CUDA(cudaGetLastError());
+#ifdef SCG_PROF
+    {
+        long long hp[16]; cudaMemcpy(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost);
+        const char* nm[8] = {"eps+obs_write", "mlp", "env step (owner)", "-", "-", "end barrier", "-", "tail(mlp+gae)"};
+        fprintf(stderr, "[SCG_PROF] CTA0 cycles per step (T=%d):", a->T);
+        for (int i = 0; i < 8; ++i) if (nm[i][0] != '-') fprintf(stderr, " %s=%.0f", nm[i], i == 7 ? (double)hp[i] : (double)hp[i] / a->T);
+        fprintf(stderr, "\n");
+        long long tk[64]; cudaMemcpyFromSymbol(tk, scg_ticks, sizeof(tk));
+        fprintf(stderr, "[SCG_PROF] ticks/step:");
+        for (int i = 0; i < 25; ++i) fprintf(stderr, " %d:%.0f", i, (double)tk[i] / a->T);
+        fprintf(stderr, "\n");
+        std::vector<long long> ct(2048); cudaMemcpy(ct.data(), d_prof + 16, 2048 * sizeof(long long), cudaMemcpyDeviceToHost);
+        int GG = G > 1024 ? 1024 : G;
+        long long mn = ct[0], mx = ct[0]; double sum = 0;
+        for (int i = 0; i < GG; ++i) { if (ct[i] < mn) mn = ct[i]; if (ct[i] > mx) mx = ct[i]; sum += ct[i]; }
+        fprintf(stderr, "[SCG_PROF] per-CTA horizon cycles: min=%lld mean=%.0f max=%lld\n", mn, sum / GG, mx);
+    }
+#else
+    (void)a;
+#endif
+    return RolloutLaunchResult{SCG_OK, cudaSuccess, nullptr};
+}
+
+// envs_per_block -> (E, threads): a CTA runs 8 threads per env (4x4 register tiles at hidden 64).  Default: one 8-warp CTA of
+// 32 envs (owner warp, helper warps, idle GEMM warps: see rollout_kernel); 16 envs x 128 threads at very large batches.
+template <int SYS, typename R>
+static RolloutLaunchResult dispatch_rollout(const RolloutLaunch& e, const scg_rollout_args* a, const RolloutParams& P, cudaStream_t s) {
+    int E = a->envs_per_block & 0xffff;
+    const int NTq = (a->envs_per_block >> 16) & 0xffff;   // requested threads per CTA (0 = 8 per env)
+    (void)NTq;
+#ifdef SCG_PROF
+    if (a->hidden_dim == 64 && (E == 0 || E == 32)) return launch_rollout<SYS, R, 64, 32, 256>(e, P, a, s);
+    if (a->hidden_dim == 64 && E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, a, s);
+    return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "SCG_PROF build: only hidden 64 / E 32 or 16"};
+#else
+    switch (a->hidden_dim) {
+#ifndef SCG_DEV_HID64_ONLY
+        case 32:
+            if (E == 0) E = 32;
+            if (E == 32) return launch_rollout<SYS, R, 32, 32, 256>(e, P, a, s);
+            if (E == 16) return launch_rollout<SYS, R, 32, 16, 128>(e, P, a, s);
+            break;
+#endif
+        case 64:
+            if (E == 0) E = 32;
+#ifdef SCG_DEV_HID64_ONLY   // 16 threads per env, two CTAs per SM: measured slower than the 8-thread-per-env variants (round 1)
+            if (E == 16 && NTq == 256) return launch_rollout<SYS, R, 64, 16, 256>(e, P, a, s);
+            if (E == 8 && NTq == 128) return launch_rollout<SYS, R, 64, 8, 128>(e, P, a, s);
+#endif
+            if (E == 32) return launch_rollout<SYS, R, 64, 32, 256>(e, P, a, s);
+            if (E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, a, s);
+            if (E == 8) return launch_rollout<SYS, R, 64, 8, 64>(e, P, a, s);
+            break;
+#ifndef SCG_DEV_HID64_ONLY
+        case 128:
+            if (E == 0) E = 16;
+            if (E == 16) return launch_rollout<SYS, R, 128, 16, 256>(e, P, a, s);
+            if (E == 8) return launch_rollout<SYS, R, 128, 8, 128>(e, P, a, s);
+            break;
+#endif
+        default: return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: hidden_dim must be 32, 64 or 128"};
+    }
+    return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: unsupported envs_per_block for this hidden_dim"};
+#endif
+}
+#endif  // SCG_ROLLOUT_IMPL
