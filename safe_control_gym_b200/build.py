@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
-ROLLOUT_UNITS = [f'scg_rollout_{s}_{p}.cu' for s in ('quad3d', 'quad2d', 'cartpole') for p in ('f64', 'f32')]   # slowest first
+ROLLOUT_UNITS = [f'scg_rollout_{s}_{p}.cu' for s in ('quad3d', 'quad2d', 'cartpole', 'quad1d') for p in ('f64', 'f32')]   # slowest first
 UNITS = ROLLOUT_UNITS + ['scg_api.cu', 'scg_ppo.cu']          # translation units of libscg_b200.so (compiled in parallel)
 SOURCES = UNITS + ['scg_kernels.cuh', 'scg_device.cuh', 'scg_rollout_launch.cuh']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-shared', '-Xcompiler', '-fPIC',

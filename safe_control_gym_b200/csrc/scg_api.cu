@@ -299,9 +299,10 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
     RolloutLaunchResult r;
     switch (e->cfg.system) {
         case SCG_SYS_CARTPOLE: r = dbl ? scg_rollout_cartpole_f64(rl, a, P, s) : scg_rollout_cartpole_f32(rl, a, P, s); break;
+        case SCG_SYS_QUAD1D: r = dbl ? scg_rollout_quad1d_f64(rl, a, P, s) : scg_rollout_quad1d_f32(rl, a, P, s); break;
         case SCG_SYS_QUAD2D: r = dbl ? scg_rollout_quad2d_f64(rl, a, P, s) : scg_rollout_quad2d_f32(rl, a, P, s); break;
         case SCG_SYS_QUAD3D: r = dbl ? scg_rollout_quad3d_f64(rl, a, P, s) : scg_rollout_quad3d_f32(rl, a, P, s); break;
-        default: return fail(e, SCG_EINVAL, "scg_rollout: the fused collector supports cartpole, quadrotor 2D and 3D");
+        default: return fail(e, SCG_EINVAL, "scg_rollout: unknown system");
     }
     if (r.code == SCG_ECUDA) return fail(e, SCG_ECUDA, std::string(r.msg) + ": " + cudaGetErrorString(r.cuda));
     if (r.code != SCG_OK) return fail(e, r.code, r.msg);

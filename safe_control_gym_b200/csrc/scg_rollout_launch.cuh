@@ -16,6 +16,8 @@ struct RolloutLaunchResult {    // code: SCG_OK / SCG_EINVAL (msg) / SCG_ECUDA (
 
 RolloutLaunchResult scg_rollout_cartpole_f64(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
 RolloutLaunchResult scg_rollout_cartpole_f32(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
+RolloutLaunchResult scg_rollout_quad1d_f64(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
+RolloutLaunchResult scg_rollout_quad1d_f32(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
 RolloutLaunchResult scg_rollout_quad2d_f64(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
 RolloutLaunchResult scg_rollout_quad2d_f32(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
 RolloutLaunchResult scg_rollout_quad3d_f64(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);

@@ -73,6 +73,12 @@ CASES = [
     ('quadrotor_2D_track', 72, 100, 64, {}, 16),
     ('quadrotor_2D_track', 44, 100, 64, {}, 8),
     ('cartpole_stab', 50, 64, 32, {}, 16),
+    # 1-D quadrotor (quadrotor.py quad_type 1) through the fused collector
+    ('quadrotor', 48, 120, 64, dict(quad_type=1, randomized_init=True, task='traj_tracking', obs_goal_horizon=1, cost='rl_reward', ctrl_freq=50,
+                                    pyb_freq=1000, normalized_rl_action_space=True, done_on_out_of_bound=True,
+                                    task_info=dict(trajectory_type='figure8', num_cycles=1, trajectory_plane='xz',
+                                                   trajectory_position_offset=[0, 1], trajectory_scale=0.5),
+                                    init_state=dict(init_x=1.0, init_x_dot=0.0))),
 ]
 
 
