@@ -141,6 +141,7 @@ template <> struct SysDims<SCG_SYS_QUAD2D> { static constexpr int NX = 6, NU = 2
 template <> struct SysDims<SCG_SYS_QUAD3D> { static constexpr int NX = 12, NU = 4, PS = 13; }; // pos3, quat4, vel3, omega_world3
 
 #define SCG_PS_MAX 13
+#define SCG_NINV 4
 
 // Persistent per-env state, SoA in one device allocation ("state blob", checkpointable as one memcpy).
 struct DevState {
@@ -180,7 +181,7 @@ struct DevTables {
 template <int SYS, typename R> struct EnvRegs {
     R ps[SysDims<SYS>::PS];
     R inertial[SCG_MAX_INERTIAL];
-    R inv[2];            // reciprocals of the inertial properties the integrator divides by (2D quadrotor: 1/M, 1/Iyy)
+    R inv[SCG_NINV];     // reciprocals of the inertial properties the integrator divides by (2D: 1/M, 1/Iyy; 3D: 1/M, 1/Ixx, 1/Iyy, 1/Izz)
     int ctrl_step;
     int episode;
     uint32_t total_steps;
@@ -189,7 +190,9 @@ template <int SYS, typename R> struct EnvRegs {
 
 template <int SYS, typename R> __device__ __forceinline__ void env_derived(EnvRegs<SYS, R>& e) {
     e.inv[0] = (R)1 / e.inertial[0];
-    e.inv[1] = (SYS == SCG_SYS_QUAD2D) ? (R)1 / e.inertial[2] : (R)0;
+    e.inv[1] = (SYS == SCG_SYS_QUAD2D) ? (R)1 / e.inertial[2] : (SYS == SCG_SYS_QUAD3D) ? (R)1 / e.inertial[1] : (R)0;
+    e.inv[2] = (SYS == SCG_SYS_QUAD3D) ? (R)1 / e.inertial[2] : (R)0;
+    e.inv[3] = (SYS == SCG_SYS_QUAD3D) ? (R)1 / e.inertial[3] : (R)0;
 }
 template <int SYS, typename R>
 __device__ __forceinline__ void env_load(const DevTables& T, int n, EnvRegs<SYS, R>& e) {
@@ -516,9 +519,9 @@ template <typename R> struct Physics<SCG_SYS_QUAD3D, R> {
     // ps = pos[0..2], quat[3..6] (x,y,z,w), vel[7..9], omega_world[10..12]
     static __device__ void advance(const HotCfg<R>* h, EnvRegs<SCG_SYS_QUAD3D, R>& e, const R f[4], const R* fd, bool has_dist) {
         const R dt = h->dt;
-        const R m = e.inertial[0], inv_m = (R)1 / m;
+        const R inv_m = e.inv[0];                                      // per-episode reciprocals (env_load / reset candidates)
         const R J0 = e.inertial[1], J1 = e.inertial[2], J2 = e.inertial[3];
-        const R iJ0 = (R)1 / J0, iJ1 = (R)1 / J1, iJ2 = (R)1 / J2;
+        const R iJ0 = e.inv[1], iJ1 = e.inv[2], iJ2 = e.inv[3];
         const R a = h->arm;
         const R tm = (f[0] + f[1] + f[2] + f[3]) * inv_m;
         const R tbx = a * (f[0] + f[1] - f[2] - f[3]);
@@ -702,11 +705,8 @@ __device__ __noinline__ void reset_draw(const DevTables& T, const HotCfg<R>* h, 
 }
 
 // reset() of one env (quadrotor.py:328-392, cartpole.py:266-352); the caller builds the observation with make_obs(at_reset).
-// `cand` (nullable): pre-drawn values of THIS episode, [SCG_MAX_INERTIAL + NX] doubles with stride `cstride` (the fused collector's
-// helper warp draws them ahead of time, off the owners' critical path).
 template <int SYS, typename R>
-__device__ __forceinline__ void env_reset(const DevTables& T, const HotCfg<R>* h, int n, EnvRegs<SYS, R>& e, R* state,
-                                          const double* cand = nullptr, int cstride = 0) {
+__device__ __forceinline__ void env_reset(const DevTables& T, const HotCfg<R>* h, int n, EnvRegs<SYS, R>& e, R* state) {
     constexpr int NX = SysDims<SYS>::NX;
     const int k = e.episode;
     e.ctrl_step = 0;
@@ -727,12 +727,7 @@ __device__ __forceinline__ void env_reset(const DevTables& T, const HotCfg<R>* h
             }
     }
     double inr[SCG_MAX_INERTIAL], init[NX];
-    if (cand) {
-#pragma unroll
-        for (int j = 0; j < SCG_MAX_INERTIAL; ++j) inr[j] = cand[j * cstride];
-#pragma unroll
-        for (int j = 0; j < NX; ++j) init[j] = cand[(SCG_MAX_INERTIAL + j) * cstride];
-    } else {
+    {
         double tmp[SCG_MAX_INERTIAL + NX];
         reset_draw<SYS, R>(T, h, n, k, tmp, 1, SCG_MAX_INERTIAL);
 #pragma unroll

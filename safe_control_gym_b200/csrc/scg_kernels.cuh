@@ -3,12 +3,15 @@
 //   reset_kernel   : lane per env, (re-)initialises masked envs            (Quadrotor.reset / CartPole.reset)
 //   step_kernel    : lane per env, one control step with caller actions    (env.step / DummyVecEnv.step_wait)
 //   rollout_kernel : one CTA owns E envs for the whole horizon.  Per step: fused actor+critic MLP as
-//                    register-tiled FP32 GEMMs out of shared memory, Gaussian sampling, env step
-//                    (physics sub-steps, reward, done, constraints, disturbances), auto-reset, one coalesced
-//                    write of the PPOBuffer record, terminal-value pass on truncation, and after the horizon
-//                    the critic bootstrap + reverse GAE scan.  No host round trip inside the horizon.
-//                    (PPO.train_step collector, safe_control_gym/controllers/ppo/ppo.py:259-297)
+//                    register-tiled FP32 GEMMs out of shared memory (all warps), then the env step on the owner
+//                    lanes (Gaussian sampling, action map, physics sub-steps, termination, next observation,
+//                    auto-reset) while helper warps evaluate reward / constraints / statistics of the previous
+//                    step, prepare the next reset episodes and write the record; terminal-value pass on
+//                    truncation; after the horizon the critic bootstrap + reverse GAE scan.  No host round trip
+//                    inside the horizon; on several GPUs the record is stored into every peer's gathered buffer.
+//                    (PPO.train_step collector, safe_control_gym/controllers/ppo/ppo.py:259-297; DESIGN.md 4)
 #pragma once
+#include <type_traits>
 #include "scg_device.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -289,10 +292,6 @@ template <int HID, int E> struct RolloutSmem {
     }
 };
 
-// named barriers: 1, 2 = owner warp <-> helper warps of the env-step section
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-
 // Forward of ONE network (net 0 = actor with n_out = A outputs, net 1 = critic with 1 output) for the CTA's E envs by a group
 // of NTN threads (tl = index inside the group); both groups run in lockstep (__syncthreads).
 //   s_in  : pair-swizzled observation tile (tile_idx)          s_h1n : this net's hidden tile
@@ -351,6 +350,19 @@ __device__ __forceinline__ void net_forward(int tl, int net, int n_out, int w3_r
             if (has1) fma_ops(o1);
         }
     };
+    // the same with a compile-time trip count (fully unrolled: the short first layer is all prologue / epilogue otherwise)
+    auto gemm_fixed = [&](const float* __restrict__ a, int a_stride, const float* __restrict__ w, int w_stride, auto npair_c) {
+        constexpr int NP = decltype(npair_c)::value;
+        Ops o0, o1;
+        load_ops(o0, a, w);
+#pragma unroll
+        for (int kp = 0; kp < NP; kp += 2) {
+            if (kp + 1 < NP) load_ops(o1, a + (kp + 1) * a_stride, w + (kp + 1) * w_stride);
+            fma_ops(o0);
+            if (kp + 2 < NP) load_ops(o0, a + (kp + 2) * a_stride, w + (kp + 2) * w_stride);
+            if (kp + 1 < NP) fma_ops(o1);
+        }
+    };
     auto init_acc = [&](const float* __restrict__ bias) {
 #pragma unroll
         for (int j = 0; j < TU; ++j) { const float b = bias[j]; acc[0][j] = make_float2(b, 0.f); acc[1][j] = acc[0][j]; acc[2][j] = acc[0][j]; acc[3][j] = acc[0][j]; }
@@ -366,7 +378,14 @@ __device__ __forceinline__ void net_forward(int tl, int net, int n_out, int w3_r
     // ---- layer 1: [E x obs] . [obs x H]      (W1P [kp][2H][2], this net's units start at net*H)
     SCG_TK(14);
     init_acc(s_blob + L.b1 + net * HID + ul0);
-    gemm(s_in + eg * 4, 2 * EG * 4, s_blob + L.w1t + (net * HID + ul0) * 2, 2 * HID * 2, obs_dim >> 1);
+    {
+        const float* a1 = s_in + eg * 4; const float* w1 = s_blob + L.w1t + (net * HID + ul0) * 2;
+        const int np1 = obs_dim >> 1;
+        if (np1 == 6) gemm_fixed(a1, 2 * EG * 4, w1, 2 * HID * 2, std::integral_constant<int, 6>{});          // Quadrotor-2D tracking (obs 12)
+        else if (np1 == 12) gemm_fixed(a1, 2 * EG * 4, w1, 2 * HID * 2, std::integral_constant<int, 12>{});   // Quadrotor-3D tracking (obs 24)
+        else if (np1 == 2) gemm_fixed(a1, 2 * EG * 4, w1, 2 * HID * 2, std::integral_constant<int, 2>{});     // CartPole (obs 4)
+        else gemm(a1, 2 * EG * 4, w1, 2 * HID * 2, np1);
+    }
     SCG_TK(15);
     activate();
 #pragma unroll
@@ -474,7 +493,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     // reset candidates: a helper warp keeps the next two episodes of every env ready (slot = episode & 1):
     // inertial properties, their reciprocals, the integrator state of the initial condition (+ its observation in s_cobs)
     constexpr int PS = SysDims<SYS>::PS;
-    constexpr int NC = SCG_MAX_INERTIAL + 2 + PS;
+    constexpr int NC = SCG_MAX_INERTIAL + SCG_NINV + PS;
     __shared__ double s_cand[2 * NC * E];
     __shared__ int s_cand_ep[2 * E];           // episode index held by each candidate slot (-1 = empty)
     __shared__ int s_epi[E];                   // next episode index of each env, published by its owner lane
@@ -593,18 +612,19 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
             const int ep = want + d, slot = ep & 1;
             if (*(volatile int*)&s_cand_ep[slot * E + ee] != ep) {
                 double* cd = s_cand + slot * NC * E + ee;
-                reset_draw<SYS, R>(T, h, n0 + ee, ep, cd, E, SCG_MAX_INERTIAL + 2);   // inertial at rows 0..3, initial state from row 6
+                reset_draw<SYS, R>(T, h, n0 + ee, ep, cd, E, SCG_MAX_INERTIAL + SCG_NINV);   // inertial at rows 0..3, initial state after the reciprocals
                 EnvRegs<SYS, R> tmp; R initr[NX], st0[NX];
 #pragma unroll
                 for (int j = 0; j < SCG_MAX_INERTIAL; ++j) tmp.inertial[j] = (R)cd[j * E];
 #pragma unroll
-                for (int j = 0; j < NX; ++j) initr[j] = (R)cd[(SCG_MAX_INERTIAL + 2 + j) * E];
+                for (int j = 0; j < NX; ++j) initr[j] = (R)cd[(SCG_MAX_INERTIAL + SCG_NINV + j) * E];
                 env_derived<SYS, R>(tmp);
                 Physics<SYS, R>::set_init(tmp, initr);
                 Physics<SYS, R>::state(tmp, st0);
-                cd[SCG_MAX_INERTIAL * E] = (double)tmp.inv[0]; cd[(SCG_MAX_INERTIAL + 1) * E] = (double)tmp.inv[1];
 #pragma unroll
-                for (int j = 0; j < PS; ++j) cd[(SCG_MAX_INERTIAL + 2 + j) * E] = (double)tmp.ps[j];
+                for (int j = 0; j < SCG_NINV; ++j) cd[(SCG_MAX_INERTIAL + j) * E] = (double)tmp.inv[j];
+#pragma unroll
+                for (int j = 0; j < PS; ++j) cd[(SCG_MAX_INERTIAL + SCG_NINV + j) * E] = (double)tmp.ps[j];
                 NoiseSrc<R> nn; nn.row = nullptr; nn.philox = false; nn.slot = 0; nn.stream = 0; nn.idx = 0; nn.key.k0 = nn.key.k1 = nn.key.genv = 0;
                 make_obs<SYS, R, R>(T, h, s_xg, st0, n0 + ee, 0, true, nn, PlainObsSink{s_cobs + slot * OBS_TILE + ee, E});
                 __threadfence_block();
@@ -732,9 +752,10 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                             const double* cd = s_cand + slot * NC * E + ol;
 #pragma unroll
                             for (int j = 0; j < SCG_MAX_INERTIAL; ++j) e.inertial[j] = (R)cd[j * E];
-                            e.inv[0] = (R)cd[SCG_MAX_INERTIAL * E]; e.inv[1] = (R)cd[(SCG_MAX_INERTIAL + 1) * E];
 #pragma unroll
-                            for (int j = 0; j < PS; ++j) e.ps[j] = (R)cd[(SCG_MAX_INERTIAL + 2 + j) * E];
+                            for (int j = 0; j < SCG_NINV; ++j) e.inv[j] = (R)cd[(SCG_MAX_INERTIAL + j) * E];
+#pragma unroll
+                            for (int j = 0; j < PS; ++j) e.ps[j] = (R)cd[(SCG_MAX_INERTIAL + SCG_NINV + j) * E];
                             const float* co = s_cobs + slot * OBS_TILE + ol;
                             for (int k = 0; k < od; k += 4) {               // loads first, then stores (both shared memory: no serial chain)
                                 float cv[4];
