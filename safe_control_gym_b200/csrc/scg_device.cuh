@@ -575,7 +575,12 @@ template <typename R> struct Physics<SCG_SYS_QUAD3D, R> {
             const R n1 = cw * q[1] + ay * q[3] + az * q[0] - ax * q[2];
             const R n2 = cw * q[2] + az * q[3] + ax * q[1] - ay * q[0];
             const R n3 = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
-            const R inn = (R)1 / Mth<R>::sqrt_(n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3);
+            // renormalise like Bullet.  q was unit and the increment is a unit quaternion up to the series truncation, so
+            // |n|^2 = 1 + d with |d| tiny: 1/sqrt(1 + d) = 1 - d/2 + 3 d^2/8 - 5 d^3/16 (error < 1e-19 for |d| < 1e-5), no sqrt / divide
+            const R d = (n0 * n0 + n1 * n1 + n2 * n2 + n3 * n3) - (R)1;
+            R inn;
+            if (Mth<R>::abs_(d) < (R)1e-5) inn = (R)1 + d * ((R)-0.5 + d * ((R)0.375 - d * (R)0.3125));
+            else inn = (R)1 / Mth<R>::sqrt_((R)1 + d);
             q[0] = n0 * inn; q[1] = n1 * inn; q[2] = n2 * inn; q[3] = n3 * inn;
         }
         e.ps[0] = px; e.ps[1] = py; e.ps[2] = pz; e.ps[3] = q[0]; e.ps[4] = q[1]; e.ps[5] = q[2]; e.ps[6] = q[3];

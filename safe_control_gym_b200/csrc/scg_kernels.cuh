@@ -749,6 +749,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                         const int slot = e.episode & 1;
                         if (*(volatile int*)&s_cand_ep[slot * E + ol] == e.episode) {
                             // the helper has the whole episode start ready: inertial properties, reciprocals, integrator state, observation
+                            __threadfence_block();                         // acquire: no candidate load may move above the flag check
                             const double* cd = s_cand + slot * NC * E + ol;
 #pragma unroll
                             for (int j = 0; j < SCG_MAX_INERTIAL; ++j) e.inertial[j] = (R)cd[j * E];
