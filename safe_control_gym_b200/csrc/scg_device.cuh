@@ -281,6 +281,7 @@ template <typename R> struct HotCfg {
     int obs_goal_horizon, obs_wrap, philox, has_dist[3], n_con, con_fast, L;
     R dt, hover, act_scale, goal_tol, penalty, x_thr, th_thr;
     R gravity, kf, inv_nm_kf, pwm_c, pwm_s, inv_pwm_s, pwm_min, pwm_max, arm, km_over_kf, pole_w2;
+    R thr_lo, thr_hi, inv_nm;   // thrust per input at the PWM limits (with a margin), 1 / motors per input
     R act_low[SCG_MAX_NU], act_high[SCG_MAX_NU], u_goal[SCG_MAX_NU], rew_act_w[SCG_MAX_NU], Rw[SCG_MAX_NU];
     R rew_state_w[SCG_MAX_NX], mse_w[SCG_MAX_NX], Qw[SCG_MAX_NX];
     double state_low[SCG_MAX_NX], state_high[SCG_MAX_NX];   // float32-rounded bounds, compared in double like numpy does
@@ -311,6 +312,12 @@ __device__ __noinline__ void hot_load(const DevTables& T, HotCfg<R>* h) {
     h->pwm_c = (R)c->pwm2rpm_const; h->pwm_s = (R)c->pwm2rpm_scale; h->inv_pwm_s = (R)(1.0 / c->pwm2rpm_scale);
     h->pwm_min = (R)c->pwm_min; h->pwm_max = (R)c->pwm_max; h->arm = (R)c->arm; h->km_over_kf = (R)(c->km / c->kf);
     h->pole_w2 = (R)(c->pole_width * c->pole_width);
+    {
+        const double nmkf = (double)(4 / NU) * c->kf;
+        const double rlo = c->pwm2rpm_scale * c->pwm_min + c->pwm2rpm_const, rhi = c->pwm2rpm_scale * c->pwm_max + c->pwm2rpm_const;
+        h->thr_lo = (R)(rlo * rlo * nmkf * (1.0 + 1e-6)); h->thr_hi = (R)(rhi * rhi * nmkf * (1.0 - 1e-6));
+        h->inv_nm = (R)(1.0 / (double)(4 / NU));
+    }
     for (int k = 0; k < SCG_MAX_NU; ++k) {
         h->act_low[k] = (R)c->act_low[k]; h->act_high[k] = (R)c->act_high[k]; h->u_goal[k] = (R)c->u_goal[k];
         h->rew_act_w[k] = (R)c->rew_act_weight[k]; h->Rw[k] = (R)c->R[k];
@@ -360,14 +367,25 @@ template <int SYS, typename R>
 __device__ __forceinline__ void quad_motor_forces(const HotCfg<R>* h, const R* thrust, R f[4]) {
     constexpr int NU = SysDims<SYS>::NU;
     R mf[NU];
+    // cmd2pwm -> clip -> pwm2rpm -> kf rpm^2 is the identity thrust/n_motor (up to a few ulp) while the PWM stays strictly inside its
+    // bounds -- always, unless the command sits on the action bounds, which are those PWM limits in thrust units.  The square root is
+    // only taken in that boundary case (warp-uniformly rare): thr_lo / thr_hi are the thrusts of the PWM limits with a 1e-6 margin.
+    bool inside = true;
 #pragma unroll
-    for (int k = 0; k < NU; ++k) {
-        R t = thrust[k] < (R)0 ? (R)0 : thrust[k];
-        R pwm = (Mth<R>::sqrt_(t * h->inv_nm_kf) - h->pwm_c) * h->inv_pwm_s;
-        pwm = pwm < h->pwm_min ? h->pwm_min : pwm;
-        pwm = pwm > h->pwm_max ? h->pwm_max : pwm;
-        R rpm = h->pwm_s * pwm + h->pwm_c;
-        mf[k] = rpm * rpm * h->kf;
+    for (int k = 0; k < NU; ++k) inside = inside && thrust[k] > h->thr_lo && thrust[k] < h->thr_hi;
+    if (inside) {
+#pragma unroll
+        for (int k = 0; k < NU; ++k) mf[k] = thrust[k] * h->inv_nm;
+    } else {
+#pragma unroll
+        for (int k = 0; k < NU; ++k) {
+            R t = thrust[k] < (R)0 ? (R)0 : thrust[k];
+            R pwm = (Mth<R>::sqrt_(t * h->inv_nm_kf) - h->pwm_c) * h->inv_pwm_s;
+            pwm = pwm < h->pwm_min ? h->pwm_min : pwm;
+            pwm = pwm > h->pwm_max ? h->pwm_max : pwm;
+            R rpm = h->pwm_s * pwm + h->pwm_c;
+            mf[k] = rpm * rpm * h->kf;
+        }
     }
     if (NU == 1) { f[0] = f[1] = f[2] = f[3] = mf[0]; }
     else if (NU == 2) { f[0] = mf[0]; f[1] = mf[1 % NU]; f[2] = mf[1 % NU]; f[3] = mf[0]; }   // quadrotor_utils.py:39
