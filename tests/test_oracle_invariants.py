@@ -112,3 +112,40 @@ def test_cartpole_energy_drift_is_small_without_input():
     for _ in range(100):
         out = o.step(np.zeros((1, 1)))
     assert abs(energy(out['state'][0]) - e0) / abs(e0) < 5e-3
+
+
+def test_3d_integrator_converges_to_the_reference_symbolic_model():
+    '''As pyb_freq -> inf the 3-D oracle (quaternion exponential map, world-frame angular velocity, gyroscopic term) converges at
+    first order to an RK integration of the reference's symbolic 3-D model -- Z-Y-X Euler angles, body rates, Euler-rate kinematics
+    (quadrotor.py:533-562) -- evaluated with the URDF lever arm 0.028 (cf2x.urdf:42-78) instead of L/sqrt(2).'''
+    from scipy.integrate import solve_ivp
+    m, g, arm = 0.027, 9.8, 0.028
+    J = np.array([1.4e-5, 1.4e-5, 2.17e-5])
+    gamma = 7.94e-12 / 3.16e-10
+    f = np.array([0.0672, 0.0660, 0.0655, 0.0668])                  # unequal motor thrusts: roll, pitch and yaw torques
+
+    def rhs(t, x):
+        phi, th, psi = x[6:9]
+        w = x[9:12]
+        cph, sph, cth, sth, cps, sps = np.cos(phi), np.sin(phi), np.cos(th), np.sin(th), np.cos(psi), np.sin(psi)
+        Rob = np.array([[cps * cth, cps * sth * sph - sps * cph, cps * sth * cph + sps * sph],
+                        [sps * cth, sps * sth * sph + cps * cph, sps * sth * cph - cps * sph],
+                        [-sth, cth * sph, cth * cph]])                  # RotZ(psi) RotY(theta) RotX(phi) (transformations.py:173-187)
+        acc = Rob @ np.array([0, 0, f.sum()]) / m - np.array([0, 0, g])
+        Mb = np.array([arm * (f[0] + f[1] - f[2] - f[3]), arm * (-f[0] + f[1] + f[2] - f[3]), gamma * (-f[0] + f[1] - f[2] + f[3])])
+        wdot = (Mb - np.cross(w, J * w)) / J
+        W = np.array([[1, sph * np.tan(th), cph * np.tan(th)], [0, cph, -sph], [0, sph / cth, cph / cth]])
+        ang = W @ w
+        return [x[1], acc[0], x[3], acc[1], x[5], acc[2], ang[0], ang[1], ang[2], wdot[0], wdot[1], wdot[2]]
+    s0 = np.zeros(12); s0[4] = 1.0; s0[6:9] = [0.08, -0.05, 0.3]        # zero initial rates (quadrotor.py:379 passes p,q,r as WORLD rates)
+    ref = solve_ivp(rhs, (0, 0.2), s0, rtol=1e-12, atol=1e-14).y[:, -1]
+    errs = []
+    for pyb in (500, 1000, 2000, 4000):
+        env = _quad(3, pyb_freq=pyb)
+        o = H.make_oracle(env, 1, auto_reset=False)
+        o.set_env_state(0, s0)
+        for _ in range(10):
+            out = o.step(f.reshape(1, 4))
+        errs.append(np.abs(out['state'][0] - ref).max())
+    ratios = np.asarray(errs[:-1]) / np.asarray(errs[1:])
+    assert errs[-1] < 2e-3 and np.all(ratios > 1.7) and np.all(ratios < 2.3), (errs, ratios)     # O(dt)
