@@ -80,3 +80,26 @@ def test_no_cpu_fallback_create_fails_loudly_without_a_gpu():
     h = C.c_void_p()
     assert _abi.lib().scg_create(C.byref(cfg), C.byref(h)) == _abi.SCG_EINVAL
     assert b'not divisible' in _abi.lib().scg_last_error(None)
+
+
+def test_fused_collector_variants_fit_the_sm():
+    '''Resource usage of every rollout_kernel instantiation in the built library (cuobjdump, no GPU needed): registers within the
+    256-thread budget of one SM (64 K registers => <= 255 per thread for one CTA, and the 8-warp default must keep one CTA resident),
+    static shared memory below the 48 KB static limit, sm_100a code present.'''
+    import re
+    import shutil
+    import subprocess
+    from safe_control_gym_b200 import _abi
+    if shutil.which('cuobjdump') is None:
+        import pytest
+        pytest.skip('cuobjdump not on PATH')
+    txt = subprocess.run(['cuobjdump', '--dump-resource-usage', _abi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert 'sm_100a' in txt
+    rows = re.findall(r'Function (_Z14rollout_kernel\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+)', txt)
+    assert len(rows) >= 8 * 7, len(rows)          # 4 systems x 2 precisions x 7 (hidden, envs-per-CTA) variants
+    for name, reg, stack, shared in rows:
+        m = re.search(r'ILi(\d)E([df])Li(\d+)ELi(\d+)ELi(\d+)E', name)
+        nt = int(m.group(5))
+        assert int(reg) <= 255 and int(reg) * nt <= 65536, (name, reg)
+        assert int(shared) <= 48 * 1024, (name, shared)
+        assert int(stack) <= 1024, (name, stack)
