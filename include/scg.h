@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SCG_ABI_VERSION 2
+#define SCG_ABI_VERSION 3
 
 #define SCG_MAX_NX 12          /* max state dim (Quadrotor-3D) */
 #define SCG_MAX_NU 4           /* max action dim */
@@ -264,6 +264,11 @@ typedef struct scg_rollout_args {
     int32_t n_peers;
     int32_t reserved0;
     int64_t peer_byte_offset[SCG_MAX_PEERS];
+    /* NVSwitch multicast variant of the same gather: if non-zero, `pointer + multicast_byte_offset` is the multicast mapping of the
+     * gathered buffer (one `multimem.st` lands in EVERY rank's copy, this rank's included), and it replaces the n_peers unicast
+     * copies: one extra store per record entry instead of n_peers.  The plain local store is still issued (the kernel reads its own
+     * record back for the GAE scan through the unicast address). */
+    int64_t multicast_byte_offset;
 } scg_rollout_args;
 
 typedef struct scg_env scg_env;   /* opaque, one per (device, batch) */

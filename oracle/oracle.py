@@ -114,6 +114,7 @@ class Oracle:
             raise ValueError('scg_oracle_create failed (config size mismatch?)')
         self.N = cfg.num_envs
         xg = np.ascontiguousarray(np.atleast_2d(x_goal), dtype=np.float64)
+        self.x_goal = xg
         self.lib.scg_oracle_set_reference(self.h, _p(xg), C.c_int(xg.shape[0]))
         if constraints_csr is not None:
             kind, strict, ptr, col, val, b = constraints_csr

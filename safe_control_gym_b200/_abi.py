@@ -8,7 +8,7 @@ raises if `libscg_b200.so` is missing or cannot be loaded.
 import ctypes as C
 import os
 
-SCG_ABI_VERSION = 2
+SCG_ABI_VERSION = 3
 SCG_MAX_PEERS = 8
 SCG_MAX_NX = 12
 SCG_MAX_NU = 4
@@ -96,6 +96,7 @@ class scg_rollout_args(C.Structure):
         ('gamma', C.c_double), ('gae_lambda', C.c_double),
         ('d_policy', C.c_void_p), ('d_eps', C.c_void_p),
         ('n_peers', C.c_int32), ('reserved0', C.c_int32), ('peer_byte_offset', C.c_int64 * SCG_MAX_PEERS),
+        ('multicast_byte_offset', C.c_int64),
     ]
 
 

@@ -81,6 +81,32 @@ CARTPOLE_STAB = dict(
 )
 
 
+# BASELINE.json config 2: "CartPole stabilization, 4096 batched envs, random-MLP policy rollout" = the packaged cartpole.yaml defaults
+# (ctrl 50 / pyb 50, init state uniform +-0.05 per component cartpole.py:92-113, obs 4, act 1; SURVEY.md 8d "C2").
+CARTPOLE_C2 = dict(ctrl_freq=50, pyb_freq=50, randomized_init=True, task='stabilization', cost='rl_reward', obs_goal_horizon=0,
+                   normalized_rl_action_space=False, done_on_out_of_bound=True)
+
+# BASELINE.json config 4: "Quadrotor-3D lemniscate tracking with parametric mass/inertia disturbances + constraint eval": the 3-D
+# tracking YAML verbatim + additive zero-mean inertial randomisation (masses stay physical) + white-noise force on the dynamics
+# (SURVEY.md 8d "C4").  `honor_randomization_info` keeps these ranges instead of the class defaults (quadrotor.py:208,233 quirk).
+QUADROTOR_3D_TRACK_C4 = dict(
+    QUADROTOR_3D_TRACK, randomized_inertial_prop=True, honor_randomization_info=True,
+    inertial_prop_randomization_info=dict(M=_uniform(-0.005, 0.005), Ixx=_uniform(-1e-6, 1e-6), Iyy=_uniform(-1e-6, 1e-6),
+                                          Izz=_uniform(-1e-6, 1e-6)),
+    disturbances=dict(dynamics=[dict(disturbance_func='white_noise', std=0.01)]),
+)
+
+# name -> (env id, task config).  c2/c3/c4 are the BASELINE.json configs bench.py --config selects.
+BENCH_CONFIGS = {
+    'c2': ('cartpole', 'cartpole_c2', 4096),
+    'c3': ('quadrotor', 'quadrotor_2D_track', 4096),
+    'c4': ('quadrotor', 'quadrotor_3D_track_c4', 8192),
+}
+
+
 def get(name):
-    return deepcopy({'quadrotor_2D_track': QUADROTOR_2D_TRACK, 'quadrotor_3D_track': QUADROTOR_3D_TRACK,
-                     'cartpole_stab': CARTPOLE_STAB}[name])
+    cfg = deepcopy({'quadrotor_2D_track': QUADROTOR_2D_TRACK, 'quadrotor_3D_track': QUADROTOR_3D_TRACK,
+                    'cartpole_stab': CARTPOLE_STAB, 'cartpole_c2': CARTPOLE_C2, 'quadrotor_3D_track_c4': QUADROTOR_3D_TRACK_C4}[name])
+    if name == 'quadrotor_3D_track_c4':      # initial-state ranges: keep the reference quirk (class defaults win, quadrotor.py:208)
+        cfg['init_state_randomization_info'] = None
+    return cfg

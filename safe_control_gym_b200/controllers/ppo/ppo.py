@@ -95,27 +95,60 @@ class PeerGatheredRollout:
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         self.numel = int(flat_numel)
         self.slot = ((self.numel * 4 + 127) // 128) * 32          # floats per slot, 128-byte aligned
-        self.fused, self.why = False, ''
+        self.fused, self.why, self.buf, self.hdl, self.offsets, self.mc_offset = False, '', None, None, [], None
+        symm_mem = None
+
+        def agree(ok):                                            # all ranks or none, BEFORE the next collective is entered
+            t = torch.tensor([1 if ok else 0], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return int(t) == 1
+        # step 1 (local, cannot hang): import + allocation.  A rank that fails here must not leave the others inside rendezvous().
         try:
             import torch.distributed._symmetric_memory as symm_mem
             self.buf = symm_mem.empty(self.world * self.slot, dtype=torch.float32, device=device)
-            self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
-            ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-            mine = ptrs[self.rank]
-            self.offsets = [ptrs[g] - mine for g in range(self.world) if g != self.rank]
-            self.fused = True
+            local_ok = True
         except Exception as e:   # noqa: BLE001 -- any failure means "use the NCCL all-gather"
-            self.why = f'{type(e).__name__}: {e}'
-            self.buf = torch.empty(self.world * self.slot, dtype=torch.float32, device=device)
-            self.hdl, self.offsets = None, []
-        ok = torch.tensor([1 if self.fused else 0], device=device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)                # all ranks or none
-        if int(ok) == 0 and self.fused:
-            self.fused, self.offsets, self.why = False, [], 'a peer could not map symmetric memory'
+            self.why, local_ok = f'{type(e).__name__}: {e}', False
+        if agree(local_ok):
+            # step 2 (collective): every rank enters the rendezvous
+            try:
+                self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+                ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+                mine = ptrs[self.rank]
+                self.offsets = [ptrs[g] - mine for g in range(self.world) if g != self.rank]
+                mc = int(getattr(self.hdl, 'multicast_ptr', 0) or 0)
+                self.mc_offset = (mc - mine) if mc else None      # NVSwitch multicast mapping of the same buffer (multimem.st)
+                rdv_ok = True
+            except Exception as e:   # noqa: BLE001
+                self.why, rdv_ok = f'{type(e).__name__}: {e}', False
+            self.fused = agree(rdv_ok)
+            if not self.fused and not self.why:
+                self.why = 'a peer could not map symmetric memory'
+        elif not self.why:
+            self.why = 'a peer could not allocate symmetric memory'
+        if not self.fused:
+            self.hdl, self.offsets, self.mc_offset = None, [], None
+            if self.buf is None:
+                self.buf = torch.empty(self.world * self.slot, dtype=torch.float32, device=device)
+        # multicast needs every rank to have the mapping
+        if self.fused and not agree(self.mc_offset is not None):
+            self.mc_offset = None
         self.local = self.buf[self.rank * self.slot: self.rank * self.slot + self.numel]
+        self._began = False
 
     def rollout_kwargs(self):
-        return {'flat': self.local, 'peer_byte_offsets': self.offsets if self.fused else None}
+        kw = {'flat': self.local, 'peer_byte_offsets': self.offsets if self.fused else None}
+        if self.fused and self.mc_offset is not None and os.environ.get('SCG_NO_MULTICAST') != '1':
+            kw['multicast_byte_offset'] = self.mc_offset
+        return kw
+
+    def begin(self):
+        '''Call BEFORE launching a rollout into the gathered buffer: a stream-ordered barrier after which no rank is still reading
+        the previous record (its PPO update has finished on every rank), so the peers' stores of the next rollout cannot race with
+        a slower rank's update (write-after-read across GPUs).'''
+        if self.fused:
+            self.hdl.barrier(channel=1)
+        self._began = True
 
     def finish(self, out):
         import torch.distributed as dist
@@ -170,7 +203,9 @@ class PPO:
         self._perm_gen = torch.Generator(device=self.device)
         self._perm_gen.manual_seed(int(seed) + 12345)      # identical on every rank
         self.total_steps = 0
-        self._rollout_out = None
+        self._rollout_out, self._peers, self._peer = {}, {}, None     # cached record buffers / gathered buffers, keyed on the horizon
+        self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        self.precision = precision
 
     # ------------------------------------------------------------------------------------------
     def reset(self):
@@ -188,31 +223,84 @@ class PPO:
         self.logger.close()
 
     def save(self, path):
-        os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
-        state = {'agent': self.agent.state_dict(), 'obs_normalizer': {}, 'reward_normalizer': {}}
+        '''Checkpoint in the reference's format (ppo.py:112-131).  Multi-rank runs: every rank's env shard (engine state blob + its
+        observations) is gathered to rank 0, which writes the file; `load` hands each rank its own slice back.'''
+        import random
+        state = {'agent': self.agent.state_dict(), 'obs_normalizer': self.obs_normalizer.state_dict(),
+                 'reward_normalizer': self.reward_normalizer.state_dict()}
         if self.training:
-            state.update({'total_steps': self.total_steps, 'obs': self.obs.detach().cpu().numpy(),
-                          'random_state': {'torch': torch.get_rng_state(), 'perm': self._perm_gen.get_state()},
-                          'env_random_state': self.env.get_env_random_state()})
-        torch.save(state, path)
+            shard = {'obs': self.obs.detach().cpu().numpy(), 'env_random_state': self.env.get_env_random_state()}
+            shards = [shard]
+            if self.world > 1:
+                import torch.distributed as dist
+                shards = [None] * self.world if self.rank == 0 else None
+                dist.gather_object(shard, shards, dst=0)
+            if self.rank == 0:
+                state.update({'total_steps': self.total_steps,
+                              'obs': np.concatenate([sh['obs'] for sh in shards], 0),
+                              # the reference's get_random_state() keys (utils/utils.py:109-123) + the minibatch permutation generator
+                              'random_state': {'random': random.getstate(), 'numpy': np.random.get_state(), 'torch': torch.get_rng_state(),
+                                               'perm': self._perm_gen.get_state()},
+                              'env_random_state': [st for sh in shards for st in sh['env_random_state']]})
+        if self.rank == 0:
+            os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
+            torch.save(state, path)
 
     def load(self, path):
+        import random
         state = torch.load(path, weights_only=False, map_location=self.device)
         self.agent.load_state_dict(state['agent'])
+        self.obs_normalizer.load_state_dict(state.get('obs_normalizer', {}))
+        self.reward_normalizer.load_state_dict(state.get('reward_normalizer', {}))
         if self.training and 'env_random_state' in state and isinstance(state['env_random_state'][0], dict):
             self.total_steps = state['total_steps']
-            self.obs = torch.as_tensor(state['obs'], dtype=torch.float32, device=self.device)
-            self._perm_gen.set_state(state['random_state']['perm'].cpu())
-            self.env.set_env_random_state(state['env_random_state'])
+            ers = state['env_random_state']
+            if len(ers) != self.world:
+                raise ValueError(f'checkpoint holds {len(ers)} env shards, this run has {self.world} ranks')
+            n = self.local_batch
+            obs = np.asarray(state['obs'])
+            if obs.shape[0] != n * self.world:
+                raise ValueError('checkpoint batch size does not match rollout_batch_size')
+            self.obs = torch.as_tensor(obs[self.rank * n:(self.rank + 1) * n], dtype=torch.float32, device=self.device)
+            rs = state['random_state']
+            if 'random' in rs:
+                random.setstate(rs['random'])
+            if 'numpy' in rs:
+                np.random.set_state(rs['numpy'])
+            if 'torch' in rs:
+                torch.set_rng_state(rs['torch'].cpu())
+            if 'perm' in rs:
+                self._perm_gen.set_state(rs['perm'].cpu())
+            self.env.set_env_random_state([ers[self.rank]])
+            self.logger.load(self.total_steps)
 
     def learn(self, env=None, **kwargs):
+        '''Training loop with the reference's checkpoint / evaluation / logging cadence (ppo.py:150-191).'''
+        if self.num_checkpoints > 0:
+            step_interval = np.linspace(0, self.max_env_steps, self.num_checkpoints)
+            interval_save = np.zeros_like(step_interval, dtype=bool)
         while self.total_steps < self.max_env_steps:
             results = self.train_step()
             if self.total_steps >= self.max_env_steps or (self.save_interval and self.total_steps % self.save_interval == 0):
+                self.save(self.checkpoint_path)                       # latest / final checkpoint (collective when world > 1)
+                self.save(os.path.join(self.output_dir, 'checkpoints', f'model_{self.total_steps}.pt'))
                 if self.rank == 0:
-                    self.save(self.checkpoint_path)
+                    self.logger.info(f'Checkpoint | {self.checkpoint_path}')
+            if self.num_checkpoints > 0:
+                interval_id = int(np.argmin(np.abs(np.array(step_interval) - self.total_steps)))
+                if not interval_save[interval_id]:                    # intermediate checkpoint
+                    self.save(os.path.join(self.output_dir, 'checkpoints', f'model_{self.total_steps}.pt'))
+                    interval_save[interval_id] = True
             if self.eval_interval and self.total_steps % self.eval_interval == 0:
-                results['eval'] = self.run(n_episodes=self.eval_batch_size)
+                ev = self.run(n_episodes=self.eval_batch_size)
+                results['eval'] = ev
+                if self.rank == 0:
+                    self.logger.info('Eval | ep_lengths {:.2f} +/- {:.2f} | ep_return {:.3f} +/- {:.3f}'.format(
+                        ev['ep_lengths'].mean(), ev['ep_lengths'].std(), ev['ep_returns'].mean(), ev['ep_returns'].std()))
+                score = float(ev['ep_returns'].mean())
+                if self.eval_save_best and getattr(self, 'eval_best_score', -np.inf) < score:
+                    self.eval_best_score = score
+                    self.save(os.path.join(self.output_dir, 'model_best.pt'))
             if self.log_interval and self.total_steps % self.log_interval == 0:
                 self.log_step(results)
 
@@ -228,15 +316,20 @@ class PPO:
         blob, dims = self._policy_blob()
         eng = self.env.unwrapped.engine
         kw = {}
-        if self.world > 1 and eps is None and self._rollout_out is None:
-            # multi-GPU training: the record is written straight into every rank's gathered buffer (fused rollout + all-gather)
-            self._peer = PeerGatheredRollout(rollout_flat_numel(dims[0], dims[1], T, eng.N), self.device)
-            kw = self._peer.rollout_kwargs()
+        cached = self._rollout_out.get(T) if eps is None else None
+        if self.world > 1 and eps is None:
+            if T not in self._peers:
+                # multi-GPU training: the record is written straight into every rank's gathered buffer (fused rollout + all-gather)
+                self._peers[T] = PeerGatheredRollout(rollout_flat_numel(dims[0], dims[1], T, eng.N), self.device)
+            self._peer = self._peers[T]
+            if cached is None:
+                kw = self._peer.rollout_kwargs()
+            self._peer.begin()      # every rank's previous update has consumed the gathered buffer before anyone overwrites it
         out = eng.rollout(blob, dims, T, eps=eps, activation=self.activation, gamma=self.gamma, gae_lambda=self.gae_lambda,
-                          use_gae=self.use_gae, deterministic=deterministic, out=self._rollout_out if eps is None else None,
+                          use_gae=self.use_gae, deterministic=deterministic, out=cached,
                           want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode'), **kw)
         if eps is None:
-            self._rollout_out = out
+            self._rollout_out[T] = out
         return out
 
     def _policy_blob(self):
@@ -250,17 +343,21 @@ class PPO:
         start = time.time()
         out = self.collect()
         self.obs = out['last_obs']
-        self.env.record_rollout(out)
         self.total_steps += self.rollout_batch_size * self.rollout_steps
         if self.world > 1:
-            batch = self._peer.finish(out) if getattr(self, '_peer', None) is not None else all_gather_rollout(out)
+            batch = self._peer.finish(out) if self._peer is not None else all_gather_rollout(out)
         else:
             batch = {k: v for k, v in out.items() if not k.startswith('_')}
         adv = batch['adv']
         rollouts = dict(batch)
+        self._ev[0].record()
         rollouts['adv'] = (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-6)          # ppo.py:300 (numpy std, ddof=0)
-        results = self.agent.update(rollouts, self.device, generator=self._perm_gen)
-        results.update({'step': self.total_steps, 'elapsed_time': time.time() - start})
+        results = self.agent.update(rollouts, self.device, generator=self._perm_gen, defer_stats=True)
+        self._ev[1].record()
+        # host-side readbacks only after the update has been launched: the episode statistics of the rollout and the loss sums
+        self.env.record_rollout(out)
+        results = self.agent.finish_update(results)
+        results.update({'step': self.total_steps, 'elapsed_time': time.time() - start, 'update_ms': self._ev[0].elapsed_time(self._ev[1])})
         return results
 
     def run(self, env=None, render=False, n_episodes=10, verbose=False):
@@ -270,7 +367,7 @@ class PPO:
             if self.eval_env is not None:
                 self.eval_env.close()
             self.eval_env = make_vec_envs(self.env_func, None, n_episodes, 1, self.seed * 111, rng_mode=self.env.unwrapped.rng_mode,
-                                          device=self.device.index)
+                                          device=self.device.index, precision=self.precision)
         self.eval_env.reset()
         blob, dims = self._policy_blob()
         T = int(self.eval_env.proto.CTRL_STEPS)

@@ -146,12 +146,12 @@ class PPOAgent:
             return 0.5 * torch.max((v_cur - batch['ret']).pow(2), (v_old_clipped - batch['ret']).pow(2)).mean()
         return 0.5 * (v_cur - batch['ret']).pow(2).mean()
 
-    def update(self, rollouts, device=None, generator=None):
+    def update(self, rollouts, device=None, generator=None, defer_stats=False):
         '''rollouts: dict of device tensors, [T][N][w] (one rank) or [G][T*n][w] views of the all-gathered record.
         With the fused kernel (default on sm_100a) the whole opt_epochs x minibatch sequence is ONE launch (csrc/scg_ppo.cu);
         `update_torch` is the step-by-step restatement of the reference and the kernel's parity reference.'''
         if self.fused is None:
-            return self.update_torch(rollouts, device, generator)
+            return self.update_torch(rollouts, device, generator)           # (finish_update passes plain dicts through)
         flat = {k: v.reshape(v.shape[0], -1, v.shape[-1]) if v.dim() != 3 else v for k, v in rollouts.items()
                 if k in ('obs', 'act', 'logp', 'adv', 'ret', 'v')}
         dev = flat['obs'].device
@@ -163,8 +163,16 @@ class PPOAgent:
         n_mb = self.fused.update(flat, perm, self.mini_batch_size, activation=self.activation, clip_param=self.clip_param,
                                  target_kl=self.target_kl, entropy_coef=self.entropy_coef, use_clipped_value=self.use_clipped_value,
                                  actor_lr=group['lr'], critic_lr=self.critic_opt.param_groups[0]['lr'], betas=group['betas'], eps=group['eps'])
+        pending = {'_pending_fused_stats': self.opt_epochs * n_mb}
+        return pending if defer_stats else self.finish_update(pending)
+
+    def finish_update(self, results):
+        '''Reads the loss sums of a fused update back (one host sync).  Separate from `update` so that the caller can queue more device
+        work first.'''
+        if '_pending_fused_stats' not in results:
+            return results
+        n = results['_pending_fused_stats']
         st = self.fused.stats.tolist()
-        n = self.opt_epochs * n_mb
         return {'policy_loss': st[0] / n, 'value_loss': st[1] / n, 'entropy_loss': st[2] / n, 'approx_kl': st[3] / n,
                 'actor_steps': int(st[4]), 'minibatches': int(st[5])}
 

@@ -293,6 +293,8 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
         P.peer_off[g] = g < a->n_peers ? a->peer_byte_offset[g] : 0;
         if (P.peer_off[g] & 15) return fail(e, SCG_EINVAL, "scg_rollout: peer_byte_offset must be a multiple of 16");
     }
+    if (a->multicast_byte_offset & 15) return fail(e, SCG_EINVAL, "scg_rollout: multicast_byte_offset must be a multiple of 16");
+    P.mc_off = a->multicast_byte_offset;
     cudaStream_t s = (cudaStream_t)stream;
     const bool dbl = e->cfg.precision == SCG_PREC_F64;
     RolloutLaunch rl{e->cfg.num_envs, e->obs_dim, e->nu, e->nx, e->L, e->tab};

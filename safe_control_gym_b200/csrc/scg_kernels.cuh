@@ -272,6 +272,7 @@ struct RolloutParams {
     scg_rollout_out out;
     int n_peers;                 // fused all-gather: peer copies of the PPOBuffer keys (see scg_rollout_args)
     long long peer_off[SCG_MAX_PEERS];
+    long long mc_off;            // != 0: NVSwitch multicast mapping of the gathered buffer (multimem.st), replaces the unicast peer copies
     long long* prof;     // SCG_PROF builds: per-phase cycle counters of CTA 0 (nullable)
 };
 
@@ -464,9 +465,19 @@ __device__ __forceinline__ float mlp_out(const float* __restrict__ s_outp, const
 
 // Record store that is repeated into the peers' gathered buffers (NVLink peer memory; plain posted writes, coalesced like the
 // local ones): the all-gather of the rollout record happens inside the collector, there is no separate collective to wait for.
+// With an NVSwitch multicast mapping of the gathered buffer (P.mc_off), ONE `multimem.st` lands in every rank's copy instead of
+// n_peers unicast stores: the replication happens in the switch, not in this SM's LSU.
+__device__ __forceinline__ void multimem_st(float* p, float v) { asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void multimem_st(float2* p, float2 v) {
+    asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void multimem_st(float4* p, float4 v) {
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 template <typename V> __device__ __forceinline__ void pstore(const RolloutParams& P, V* ptr, V v) {
     *ptr = v;
-    for (int g = 0; g < P.n_peers; ++g) *reinterpret_cast<V*>(reinterpret_cast<char*>(ptr) + P.peer_off[g]) = v;
+    if (P.mc_off) multimem_st(reinterpret_cast<V*>(reinterpret_cast<char*>(ptr) + P.mc_off), v);
+    else for (int g = 0; g < P.n_peers; ++g) *reinterpret_cast<V*>(reinterpret_cast<char*>(ptr) + P.peer_off[g]) = v;
 }
 
 // CTAs per SM the register allocation is capped for: the 16-thread-per-env variants (E=16 x 256 threads, E=8 x 128 threads) halve
@@ -552,7 +563,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     const bool philox_eps = (P.eps == nullptr);
     const bool obs_noise = h->has_dist[SCG_MODE_OBSERVATION] != 0;
     const bool fast = use_cand && !obs_noise && !h->done_on_violation && !h->use_penalty;
-    const bool relay = fast && P.n_peers > 0;   // the owner lanes leave act / v / logp to a helper warp when every store has peer copies
+    const bool relay = fast && (P.n_peers > 0 || P.mc_off != 0);   // the owner lanes leave act / v / logp to a helper warp when every store has peer copies
     const int OBS_TILE = od * E;
     // ---- helper-warp work of the FAST schedule (lane ee = env ee of the CTA)
     const int ee = lane;
@@ -880,12 +891,14 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                     if (j < cnt) {
                         const size_t tn = (size_t)(t1 - 1 - j) * N + n;
                         const float r = rr[j] + P.gamma * tv[j];
-                        P.out.d_rew[tn] = r;                               // rews += gamma * terminal_v, in place (ppo_utils.py:389)
+                        if (P.mc_off) pstore(P, P.out.d_rew + tn, r); else P.out.d_rew[tn] = r;   // rews += gamma * terminal_v, in place (ppo_utils.py:389)
                         const float m = mm[j], v = vv[j];
                         ret = r + P.gamma * m * ret;
                         if (!P.use_gae) adv = (double)(ret - v);
                         else { const float td = r + P.gamma * m * vnext - v; adv = adv * P.lam_d * P.gamma_d * (double)m + (double)td; }
-                        P.out.d_ret[tn] = ret; P.out.d_adv[tn] = (float)adv; vnext = v;
+                        if (P.mc_off) { pstore(P, P.out.d_ret + tn, ret); pstore(P, P.out.d_adv + tn, (float)adv); }   // one multicast store each: no tail copy
+                        else { P.out.d_ret[tn] = ret; P.out.d_adv[tn] = (float)adv; }
+                        vnext = v;
                     }
                 }
             }
@@ -893,7 +906,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     }
     // fused all-gather: the scan above is one serial chain per env, so its three columns (rew, ret, adv) reach the peers afterwards,
     // copied by the whole CTA (rows of E consecutive floats per step)
-    if (P.n_peers > 0 && P.out.d_ret && P.out.d_adv) {
+    if (P.n_peers > 0 && !P.mc_off && P.out.d_ret && P.out.d_adv) {
         __syncthreads();
         const int cols = N - n0 < E ? N - n0 : E;
         for (int i = tid; i < P.T * E; i += NT) {

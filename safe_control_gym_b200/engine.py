@@ -154,12 +154,14 @@ class EngineHandle:
 
     def rollout(self, policy_blob, dims, T, eps=None, activation='tanh', gamma=0.99, gae_lambda=0.95, use_gae=False,
                 deterministic=False, envs_per_block=0, want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode'), out=None,
-                flat=None, peer_byte_offsets=None):
+                flat=None, peer_byte_offsets=None, multicast_byte_offset=None):
         '''One fused launch: T steps of policy + env for all N envs.  Returns PPOBuffer-shaped torch.cuda tensors.
 
         flat: optional caller-owned float32 buffer for the PPOBuffer keys (e.g. this rank's slot of a peer-mapped gathered buffer);
         peer_byte_offsets: byte distances from that slot to the same slot in each peer GPU's gathered buffer -- the kernel then
-        repeats every record store there (fused rollout + all-gather over NVLink, see PeerGatheredRollout in controllers/ppo).'''
+        repeats every record store there (fused rollout + all-gather over NVLink, see PeerGatheredRollout in controllers/ppo);
+        multicast_byte_offset: byte distance from that slot to the NVSwitch multicast mapping of the gathered buffer -- one
+        `multimem.st` per record entry then replaces the per-peer copies.'''
         dev, N = self.device, self.N
         obs_dim, act_dim, hid = dims
         f32 = torch.float32
@@ -213,6 +215,10 @@ class EngineHandle:
             args.peer_byte_offset[g] = int(v)
         if offs:
             out['_peer_byte_offsets'] = offs
+        mc = multicast_byte_offset if multicast_byte_offset is not None else out.get('_multicast_byte_offset', 0)
+        args.multicast_byte_offset = int(mc or 0)
+        if mc:
+            out['_multicast_byte_offset'] = int(mc)
         _abi.check(self.lib.scg_rollout(self.h, C.byref(args), C.byref(ro), self._stream()), self.h)
         return out
 

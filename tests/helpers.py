@@ -80,3 +80,75 @@ def policy_blob(pol, device):
                              out.ctypes.data_as(C.c_void_p))
     assert rc == 0
     return torch.from_numpy(out).to(device), (pol.obs_dim, pol.act_dim, pol.hidden)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# strict rollout comparison with FORK PROOFS
+def _termination_margin(cfg, x_goal, state, cvals_row):
+    '''Distance of one env.state (oracle, float64) to the nearest termination threshold of `_get_done`
+    (quadrotor.py:864-894, cartpole.py:654-672) / done_on_violation (benchmark_env.py:476-481).'''
+    from safe_control_gym_b200 import _abi
+    m = []
+    if cfg.task == _abi.SCG_TASK_STABILIZATION:
+        nx = len(state)
+        m.append(abs(float(np.linalg.norm(state - np.asarray(x_goal).reshape(-1)[:nx])) - cfg.goal_tolerance))
+    if cfg.done_on_out_of_bound:
+        if cfg.system == _abi.SCG_SYS_CARTPOLE:
+            m += [abs(abs(state[0]) - cfg.x_threshold), abs(abs(state[2]) - cfg.theta_threshold)]
+        else:
+            mask = {_abi.SCG_SYS_QUAD1D: [1, 0], _abi.SCG_SYS_QUAD2D: [1, 0, 1, 0, 1, 0],
+                    _abi.SCG_SYS_QUAD3D: [1, 0, 1, 0, 1, 0, 1, 1, 1, 0, 0, 0]}[cfg.system]
+            for k, on in enumerate(mask):
+                if on:
+                    m += [abs(state[k] - cfg.state_low[k]), abs(state[k] - cfg.state_high[k])]
+    if cfg.done_on_violation and cvals_row is not None:
+        m.append(float(np.abs(cvals_row).min()))
+    return min(m) if m else np.inf
+
+
+def compare_rollouts(o, g, cfg, x_goal, N, T, obs_tol, max_fork_frac=0.02, keys_extra=()):
+    '''o: oracle record (numpy, produced with trace=True), g: engine record (torch or numpy).  Every key is compared per env up
+    to the first `mask` mismatch.  A mismatch ("fork") is only accepted with a PROOF that it is a float tie at a termination
+    threshold: at the fork step the oracle's env.state must lie within the already observed oracle-vs-kernel trajectory
+    deviation of that env (x10, + float32 record quantisation) of the threshold that fired; anything else fails the test.
+    ret / adv / episode statistics are compared on the un-forked envs.  Returns the list of proven forks.'''
+    tonp = lambda t: t.detach().cpu().numpy() if hasattr(t, 'detach') else np.asarray(t)
+    gm, om = tonp(g['mask'])[..., 0], o['mask'][..., 0]
+    mism = gm != om
+    first_bad = np.where(mism.any(0), mism.argmax(0), T)            # [N]
+    forked = np.nonzero(first_bad < T)[0]
+    nx = o['state_trace'].shape[-1]
+    go, oo = tonp(g['obs']), o['obs']
+    proofs = []
+    for i in forked:
+        ts = int(first_bad[i])
+        dev = float(np.abs(go[:ts + 1, i, :nx] - oo[:ts + 1, i, :nx]).max())
+        tol = min(10.0 * dev + 2e-6, 1e-3)
+        cv = o['cvals'][ts, i] if 'cvals' in o else None
+        margin = _termination_margin(cfg, x_goal, o['state_trace'][ts, i], cv)
+        assert margin <= tol, (f'env {i} forked at step {ts} (oracle done={1 - om[ts, i]:.0f}, kernel done={1 - gm[ts, i]:.0f}) but the oracle state is '
+                               f'{margin:.3e} away from the nearest termination threshold (trajectory deviation so far {dev:.3e}): not a float tie')
+        proofs.append((int(i), ts, margin, dev))
+    assert len(forked) <= max(1, int(max_fork_frac * N)), f'{len(forked)} of {N} envs forked (all proven ties, but too many): {proofs[:8]}'
+    valid = np.arange(T)[:, None] < first_bad[None, :]                # [T][N] steps strictly before the fork
+    tols = [('obs', obs_tol), ('act', obs_tol), ('rew', obs_tol), ('v', 5e-5), ('logp', 2e-4), ('terminal_v', 5e-5), ('cviol', 0), ('mse', obs_tol)]
+    tols += [(k, obs_tol) for k in keys_extra]
+    for k, tol in tols:
+        if k not in g or k not in o:
+            continue
+        a, b = tonp(g[k]), o[k]
+        d = np.abs(a - b) / (1.0 + np.abs(b))
+        d = d.reshape(T, N, -1).max(-1)
+        assert d[valid].max() <= tol, (k, float(d[valid].max()), np.unravel_index(np.argmax(np.where(valid, d, 0)), d.shape))
+    full = first_bad == T
+    for k in ('ret', 'adv'):
+        if k in g and k in o:
+            np.testing.assert_allclose(tonp(g[k])[:, full], o[k][:, full], rtol=2e-4, atol=2e-4, err_msg=k)
+    if 'ep_count' in g:
+        np.testing.assert_array_equal(tonp(g['ep_count'])[full], o['ep_count'][full])
+        np.testing.assert_allclose(tonp(g['ep_return_sum'])[full], o['ep_return_sum'][full], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(tonp(g['ep_length_sum'])[full], o['ep_length_sum'][full], rtol=0, atol=0)
+        np.testing.assert_allclose(tonp(g['ep_cviol_sum'])[full], o['ep_cviol_sum'][full], rtol=0, atol=0)
+    if 'last_obs' in g:
+        np.testing.assert_allclose(tonp(g['last_obs'])[full], o['last_obs'][full], rtol=obs_tol * 10, atol=obs_tol * 10)
+    return proofs

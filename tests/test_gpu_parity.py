@@ -82,27 +82,10 @@ CASES = [
 ]
 
 
-def _compare_rollouts(o, g, N, T, obs_tol, state_tol):
-    '''o: oracle dict (numpy), g: engine dict (torch).  Compares per env up to the first `mask` mismatch (a float tie at a
-    termination threshold legitimately forks the trajectories); such forks must be rare.'''
-    gm, om = _np(g['mask'])[..., 0], o['mask'][..., 0]
-    mism = gm != om
-    first_bad = np.where(mism.any(0), mism.argmax(0), T)            # [N]
-    assert (first_bad < T).sum() <= max(1, int(0.02 * N)), f'{(first_bad < T).sum()} of {N} envs forked'
-    valid = np.arange(T)[:, None] < first_bad[None, :]                # [T][N] steps strictly before the fork
-    for k, tol in (('obs', obs_tol), ('act', obs_tol), ('rew', obs_tol), ('v', 5e-5), ('logp', 2e-4), ('terminal_v', 5e-5),
-                   ('cviol', 0), ('mse', obs_tol)):
-        a, b = _np(g[k]), o[k]
-        d = np.abs(a - b) / (1.0 + np.abs(b))
-        d = d.reshape(T, N, -1).max(-1)
-        assert d[valid].max() <= tol, (k, float(d[valid].max()))
-    full = first_bad == T
-    for k in ('ret', 'adv'):
-        a, b = _np(g[k])[:, full], o[k][:, full]
-        np.testing.assert_allclose(a, b, rtol=2e-4, atol=2e-4, err_msg=k)
-    np.testing.assert_array_equal(_np(g['ep_count'])[full], o['ep_count'][full])
-    np.testing.assert_allclose(_np(g['ep_return_sum'])[full], o['ep_return_sum'][full], rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(_np(g['last_obs'])[full], o['last_obs'][full], rtol=obs_tol * 10, atol=obs_tol * 10)
+def _compare_rollouts(o, g, N, T, obs_tol, state_tol, oracle=None):
+    '''o: oracle dict (numpy, trace=True), g: engine dict (torch).  Per env up to the first `mask` mismatch; every mismatch needs a
+    proof that it is a float tie at a termination threshold (helpers.compare_rollouts).'''
+    return H.compare_rollouts(o, g, oracle.cfg, oracle.x_goal, N, T, obs_tol)
 
 
 @pytest.mark.parametrize('prec', ['f64', 'f32'])
@@ -119,7 +102,7 @@ def test_fused_rollout_matches_oracle(case, prec):
     o = H.make_oracle(env, N, auto_reset=True, precision=prec)
     o.set_episode_table(tab)
     o.reset()
-    oo = o.rollout(pol, T, eps=eps.numpy(), gamma=0.99, gae_lambda=0.95, use_gae=True)
+    oo = o.rollout(pol, T, eps=eps.numpy(), gamma=0.99, gae_lambda=0.95, use_gae=True, trace=True)
     # engine
     eng = _engine(env, N, auto_reset=True, precision=prec)
     eng.set_episode_table(tab)
@@ -129,9 +112,9 @@ def test_fused_rollout_matches_oracle(case, prec):
                      want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode'))
     torch.cuda.synchronize()
     if prec == 'f64':
-        _compare_rollouts(oo, gg, N, T, obs_tol=2e-5, state_tol=1e-8)
+        _compare_rollouts(oo, gg, N, T, obs_tol=2e-5, state_tol=1e-8, oracle=o)
     else:
-        _compare_rollouts(oo, gg, N, T, obs_tol=1e-4, state_tol=1e-4)   # north-star tolerance
+        _compare_rollouts(oo, gg, N, T, obs_tol=1e-4, state_tol=1e-4, oracle=o)   # north-star tolerance
     assert eng.launch_count() == 2   # reset + ONE fused rollout launch for the whole horizon
     eng.close()
 
@@ -208,12 +191,12 @@ def test_philox_mode_statistics_and_oracle_agreement():
     pol = H.random_policy(env.obs_dim, env.action_dim, hid, seed=2)
     o = H.make_oracle(env, N, auto_reset=True, rng_mode='philox', seed=77)
     o.reset()
-    oo = o.rollout(pol, T, eps=None)
+    oo = o.rollout(pol, T, eps=None, trace=True)
     eng = _engine(env, N, auto_reset=True, rng_mode='philox', seed=77)
     eng.reset()
     blob, dims = H.policy_blob(pol, eng.device)
     gg = eng.rollout(blob, dims, T, eps=None)
-    _compare_rollouts(oo, gg, N, T, obs_tol=5e-5, state_tol=1e-6)
+    _compare_rollouts(oo, gg, N, T, obs_tol=5e-5, state_tol=1e-6, oracle=o)
     eng.close()
 
 
