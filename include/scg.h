@@ -219,6 +219,11 @@ typedef struct scg_step_out {
     double*  d_terminal_state_f64; /* [N][nx] state before the auto-reset */
 } scg_step_out;
 
+/* policy-MLP engines of the fused collector */
+#define SCG_MLP_AUTO 0         /* library default */
+#define SCG_MLP_FFMA2 1        /* CUDA cores: register-tiled FP32 GEMMs with packed FFMA2 */
+#define SCG_MLP_TCGEN05 2      /* 5th-gen tensor cores: tcgen05.mma kind::tf32, 3xTF32 hi/lo split, FP32 accumulators in tensor memory */
+
 /* Output buffers of the fused rollout, PPOBuffer scheme (ppo_utils.py:266-295): [T][N][.] float32. */
 #define SCG_MAX_PEERS 8
 
@@ -262,7 +267,7 @@ typedef struct scg_rollout_args {
      * must then live in ONE allocation per GPU so that one offset per peer fits them all.  n_peers = 0: local stores only.  The
      * caller orders the peers' reads after the kernel with its own barrier (stream-ordered). */
     int32_t n_peers;
-    int32_t reserved0;
+    int32_t mlp_engine;        /* SCG_MLP_*: which units run the policy MLP of the fused collector */
     int64_t peer_byte_offset[SCG_MAX_PEERS];
     /* NVSwitch multicast variant of the same gather: if non-zero, `pointer + multicast_byte_offset` is the multicast mapping of the
      * gathered buffer (one `multimem.st` lands in EVERY rank's copy, this rank's included), and it replaces the n_peers unicast

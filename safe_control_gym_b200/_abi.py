@@ -31,6 +31,8 @@ SCG_MODE_ACTION, SCG_MODE_DYNAMICS, SCG_MODE_OBSERVATION = 0, 1, 2
 SCG_RAND_NONE, SCG_RAND_UNIFORM, SCG_RAND_NORMAL = 0, 1, 2
 SCG_ACT_TANH, SCG_ACT_RELU, SCG_ACT_LEAKY_RELU = 0, 1, 2
 SCG_CON_LINEAR, SCG_CON_ABS = 0, 1
+SCG_MLP_AUTO, SCG_MLP_FFMA2, SCG_MLP_TCGEN05 = 0, 1, 2
+MLP_ENGINES = {'auto': SCG_MLP_AUTO, 'ffma2': SCG_MLP_FFMA2, 'tcgen05': SCG_MLP_TCGEN05}
 
 ACTIVATIONS = {'tanh': SCG_ACT_TANH, 'relu': SCG_ACT_RELU, 'leaky_relu': SCG_ACT_LEAKY_RELU}
 
@@ -95,7 +97,7 @@ class scg_rollout_args(C.Structure):
         ('activation', C.c_int32), ('use_gae', C.c_int32), ('deterministic', C.c_int32), ('envs_per_block', C.c_int32),
         ('gamma', C.c_double), ('gae_lambda', C.c_double),
         ('d_policy', C.c_void_p), ('d_eps', C.c_void_p),
-        ('n_peers', C.c_int32), ('reserved0', C.c_int32), ('peer_byte_offset', C.c_int64 * SCG_MAX_PEERS),
+        ('n_peers', C.c_int32), ('mlp_engine', C.c_int32), ('peer_byte_offset', C.c_int64 * SCG_MAX_PEERS),
         ('multicast_byte_offset', C.c_int64),
     ]
 

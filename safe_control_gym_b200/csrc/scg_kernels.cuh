@@ -563,7 +563,10 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     const bool philox_eps = (P.eps == nullptr);
     const bool obs_noise = h->has_dist[SCG_MODE_OBSERVATION] != 0;
     const bool fast = use_cand && !obs_noise && !h->done_on_violation && !h->use_penalty;
-    const bool relay = fast && (P.n_peers > 0 || P.mc_off != 0);   // the owner lanes leave act / v / logp to a helper warp when every store has peer copies
+#ifndef SCG_RELAY_ALWAYS
+#define SCG_RELAY_ALWAYS 0
+#endif
+    const bool relay = fast && (P.n_peers > 0 || P.mc_off != 0 || SCG_RELAY_ALWAYS);   // the owner lanes leave act / v / logp to a helper warp when every store has peer copies
     const int OBS_TILE = od * E;
     // ---- helper-warp work of the FAST schedule (lane ee = env ee of the CTA)
     const int ee = lane;

@@ -23,7 +23,11 @@ RolloutLaunchResult scg_rollout_quad2d_f32(const RolloutLaunch&, const scg_rollo
 RolloutLaunchResult scg_rollout_quad3d_f64(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
 RolloutLaunchResult scg_rollout_quad3d_f32(const RolloutLaunch&, const scg_rollout_args*, RolloutParams, cudaStream_t);
 
+#ifndef SCG_TC_DEFAULT
+#define SCG_TC_DEFAULT 0      // 1: hidden-64 rollouts use the tensor-core collector unless the caller asks for the CUDA-core one
+#endif
 #ifdef SCG_ROLLOUT_IMPL   // defined by the scg_rollout_*.cu units only
+#include "scg_rollout_tc.cuh"
 #define RL_CUDA(call) do { cudaError_t st_ = (call); if (st_ != cudaSuccess) return RolloutLaunchResult{SCG_ECUDA, st_, #call}; } while (0)
 
 template <int SYS, typename R, int HID, int E, int NT>
@@ -67,6 +71,22 @@ static RolloutLaunchResult launch_rollout(const RolloutLaunch& e, RolloutParams 
     return RolloutLaunchResult{SCG_OK, cudaSuccess, nullptr};
 }
 
+// tensor-core collector (tcgen05 / TMEM, 3xTF32): 32 envs x 256 threads, hidden 64
+template <int SYS, typename R, int HID>
+static RolloutLaunchResult launch_rollout_tc(const RolloutLaunch& e, RolloutParams P, cudaStream_t s) {
+    const tc::Smem<HID> S(e.obs_dim, e.nu, e.L * e.nx * (int)(sizeof(R) / 4));
+    const size_t smem = (size_t)S.total_floats * sizeof(float);
+    auto kern = rollout_tc_kernel<SYS, R, HID>;
+    cudaFuncAttributes fa;
+    RL_CUDA(cudaFuncGetAttributes(&fa, kern));
+    if (smem + fa.sharedSizeBytes > 227 * 1024) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: the tensor-core collector does not fit this configuration in shared memory"};
+    RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int G = (e.num_envs + tc::E - 1) / tc::E;
+    kern<<<G, tc::NT, smem, s>>>(e.tab, P);
+    RL_CUDA(cudaGetLastError());
+    return RolloutLaunchResult{SCG_OK, cudaSuccess, nullptr};
+}
+
 // envs_per_block -> (E, threads): a CTA runs 8 threads per env (4x4 register tiles at hidden 64).  Default: one 8-warp CTA of
 // 32 envs (owner warp, helper warps, idle GEMM warps: see rollout_kernel); 16 envs x 128 threads at very large batches.
 template <int SYS, typename R>
@@ -74,6 +94,17 @@ static RolloutLaunchResult dispatch_rollout(const RolloutLaunch& e, const scg_ro
     int E = a->envs_per_block & 0xffff;
     const int NTq = (a->envs_per_block >> 16) & 0xffff;   // requested threads per CTA (0 = 8 per env)
     (void)NTq;
+#ifndef SCG_PROF
+    // mlp_engine: 0 = library default, 1 = CUDA cores (FFMA2), 2 = tensor cores (tcgen05, 3xTF32; hidden 64, 32 envs per CTA)
+    if (a->mlp_engine == SCG_MLP_TCGEN05 || (a->mlp_engine == SCG_MLP_AUTO && SCG_TC_DEFAULT && a->hidden_dim == 64 && (E == 0 || E == 32))) {
+        if (a->hidden_dim != 64) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: the tensor-core collector is available for hidden_dim 64"};
+        if (e.obs_dim > 32 && a->mlp_engine == SCG_MLP_TCGEN05) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: tensor-core collector: observation too wide"};
+        if (e.obs_dim <= 32) {
+            RolloutLaunchResult r = launch_rollout_tc<SYS, R, 64>(e, P, s);
+            if (r.code == SCG_OK || a->mlp_engine == SCG_MLP_TCGEN05) return r;
+        }
+    }
+#endif
 #ifdef SCG_PROF
     if (a->hidden_dim == 64 && (E == 0 || E == 32)) return launch_rollout<SYS, R, 64, 32, 256>(e, P, a, s);
     if (a->hidden_dim == 64 && E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, a, s);

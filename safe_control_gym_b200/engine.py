@@ -5,6 +5,7 @@ allocated here and handed to the C-ABI as a raw pointer; results are returned as
 '''
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -154,7 +155,7 @@ class EngineHandle:
 
     def rollout(self, policy_blob, dims, T, eps=None, activation='tanh', gamma=0.99, gae_lambda=0.95, use_gae=False,
                 deterministic=False, envs_per_block=0, want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode'), out=None,
-                flat=None, peer_byte_offsets=None, multicast_byte_offset=None):
+                flat=None, peer_byte_offsets=None, multicast_byte_offset=None, mlp_engine=None):
         '''One fused launch: T steps of policy + env for all N envs.  Returns PPOBuffer-shaped torch.cuda tensors.
 
         flat: optional caller-owned float32 buffer for the PPOBuffer keys (e.g. this rank's slot of a peer-mapped gathered buffer);
@@ -203,6 +204,8 @@ class EngineHandle:
         args.use_gae, args.deterministic, args.envs_per_block = int(bool(use_gae)), int(bool(deterministic)), int(envs_per_block)
         args.gamma, args.gae_lambda = float(gamma), float(gae_lambda)
         args.d_policy = policy_blob.data_ptr()
+        eng_name = mlp_engine if mlp_engine is not None else os.environ.get('SCG_MLP_ENGINE', 'auto')
+        args.mlp_engine = _abi.MLP_ENGINES[eng_name]
         if eps is not None:
             assert eps.dtype == torch.float32 and eps.is_cuda and tuple(eps.shape) == (T, N, act_dim), (eps.dtype, eps.shape)
             eps = eps.contiguous()

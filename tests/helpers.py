@@ -106,12 +106,15 @@ def _termination_margin(cfg, x_goal, state, cvals_row):
     return min(m) if m else np.inf
 
 
-def compare_rollouts(o, g, cfg, x_goal, N, T, obs_tol, max_fork_frac=0.02, keys_extra=()):
+def compare_rollouts(o, g, cfg, x_goal, N, T, obs_tol, max_fork_frac=0.02, keys_extra=(), early=None):
     '''o: oracle record (numpy, produced with trace=True), g: engine record (torch or numpy).  Every key is compared per env up
     to the first `mask` mismatch.  A mismatch ("fork") is only accepted with a PROOF that it is a float tie at a termination
     threshold: at the fork step the oracle's env.state must lie within the already observed oracle-vs-kernel trajectory
     deviation of that env (x10, + float32 record quantisation) of the threshold that fired; anything else fails the test.
-    ret / adv / episode statistics are compared on the un-forked envs.  Returns the list of proven forks.'''
+    ret / adv / episode statistics are compared on the un-forked envs.  `early` = (steps, tol): a tighter bound on the first steps of the
+    horizon -- the float32 policy's rounding differences are amplified by the closed loop over the horizon, so the full-horizon bound
+    (the north-star rtol 1e-4) alone would not tell amplified rounding from a small systematic error.  Returns the proven forks and
+    the largest relative deviation per key.'''
     tonp = lambda t: t.detach().cpu().numpy() if hasattr(t, 'detach') else np.asarray(t)
     gm, om = tonp(g['mask'])[..., 0], o['mask'][..., 0]
     mism = gm != om
@@ -131,15 +134,33 @@ def compare_rollouts(o, g, cfg, x_goal, N, T, obs_tol, max_fork_frac=0.02, keys_
         proofs.append((int(i), ts, margin, dev))
     assert len(forked) <= max(1, int(max_fork_frac * N)), f'{len(forked)} of {N} envs forked (all proven ties, but too many): {proofs[:8]}'
     valid = np.arange(T)[:, None] < first_bad[None, :]                # [T][N] steps strictly before the fork
-    tols = [('obs', obs_tol), ('act', obs_tol), ('rew', obs_tol), ('v', 5e-5), ('logp', 2e-4), ('terminal_v', 5e-5), ('cviol', 0), ('mse', obs_tol)]
+    tols = [('obs', obs_tol), ('act', obs_tol), ('rew', obs_tol), ('v', 5e-5), ('logp', 2e-4), ('terminal_v', 5e-5), ('mse', obs_tol)]
     tols += [(k, obs_tol) for k in keys_extra]
+    worst = {}
     for k, tol in tols:
         if k not in g or k not in o:
             continue
         a, b = tonp(g[k]), o[k]
         d = np.abs(a - b) / (1.0 + np.abs(b))
         d = d.reshape(T, N, -1).max(-1)
-        assert d[valid].max() <= tol, (k, float(d[valid].max()), np.unravel_index(np.argmax(np.where(valid, d, 0)), d.shape))
+        worst[k] = float(d[valid].max()) if valid.any() else 0.0
+        assert worst[k] <= tol, (k, worst[k], np.unravel_index(np.argmax(np.where(valid, d, 0)), d.shape))
+        if early is not None and k in ('obs', 'act', 'rew', 'mse') + tuple(keys_extra):
+            ve = valid[:early[0]]
+            worst[k + '_early'] = float(d[:early[0]][ve].max())
+            assert worst[k + '_early'] <= early[1], (k, 'first steps', worst[k + '_early'])
+    # constraint_violation is a threshold function of the state too: a mismatch needs the same kind of proof -- the oracle's
+    # constraint value nearest to zero must be within the trajectory deviation (values are rounded to 8 decimals, constraints.py:109)
+    cv_tie = np.zeros(N, bool)
+    if 'cviol' in g and 'cviol' in o:
+        cm = (tonp(g['cviol'])[..., 0] != o['cviol'][..., 0]) & valid
+        for t, i in zip(*np.nonzero(cm)):
+            dev = float(np.abs(go[:t + 2, i, :nx] - oo[:t + 2, i, :nx]).max())
+            margin = float(np.abs(o['cvals'][t, i]).min()) if 'cvals' in o else np.inf
+            assert margin <= min(10.0 * dev + 2e-6, 1e-3), f'cviol of env {i} differs at step {t} but the nearest constraint value is {margin:.3e} (deviation {dev:.3e})'
+            cv_tie[i] = True
+        assert cv_tie.sum() <= max(1, int(max_fork_frac * N)), f'{cv_tie.sum()} envs with constraint-violation ties'
+        worst['cviol_ties'] = int(cv_tie.sum())
     full = first_bad == T
     for k in ('ret', 'adv'):
         if k in g and k in o:
@@ -148,7 +169,7 @@ def compare_rollouts(o, g, cfg, x_goal, N, T, obs_tol, max_fork_frac=0.02, keys_
         np.testing.assert_array_equal(tonp(g['ep_count'])[full], o['ep_count'][full])
         np.testing.assert_allclose(tonp(g['ep_return_sum'])[full], o['ep_return_sum'][full], rtol=1e-4, atol=1e-4)
         np.testing.assert_allclose(tonp(g['ep_length_sum'])[full], o['ep_length_sum'][full], rtol=0, atol=0)
-        np.testing.assert_allclose(tonp(g['ep_cviol_sum'])[full], o['ep_cviol_sum'][full], rtol=0, atol=0)
+        np.testing.assert_allclose(tonp(g['ep_cviol_sum'])[full & ~cv_tie], o['ep_cviol_sum'][full & ~cv_tie], rtol=0, atol=0)
     if 'last_obs' in g:
         np.testing.assert_allclose(tonp(g['last_obs'])[full], o['last_obs'][full], rtol=obs_tol * 10, atol=obs_tol * 10)
-    return proofs
+    return proofs, worst

@@ -22,7 +22,8 @@ torch = pytest.importorskip('torch')
 BENCH_SEED = 1337      # bench.py: EngineHandle(..., rng_mode='philox', seed=1337)
 
 
-def _run_pair(name, N, T, hid, prec, *, seed=BENCH_SEED, epb=0, want_cvals=False, use_gae=True, policy_seed=0, env_kw=None, offset=0):
+def _run_pair(name, N, T, hid, prec, *, seed=BENCH_SEED, epb=0, want_cvals=False, use_gae=True, policy_seed=0, env_kw=None, offset=0,
+              engine='ffma2'):
     from safe_control_gym_b200.engine import EngineHandle
     env = H.make_env(name, **(env_kw or {}))
     pol = H.random_policy(env.obs_dim, env.action_dim, hid, seed=policy_seed, activation='tanh')
@@ -33,53 +34,62 @@ def _run_pair(name, N, T, hid, prec, *, seed=BENCH_SEED, epb=0, want_cvals=False
     eng.reset()
     blob, dims = H.policy_blob(pol, eng.device)
     want = ('ret', 'adv', 'cviol', 'mse', 'last', 'episode') + (('cvals',) if want_cvals else ())
-    gg = eng.rollout(blob, dims, T, eps=None, gamma=0.99, gae_lambda=0.95, use_gae=use_gae, envs_per_block=epb, want=want)
+    gg = eng.rollout(blob, dims, T, eps=None, gamma=0.99, gae_lambda=0.95, use_gae=use_gae, envs_per_block=epb, want=want, mlp_engine=engine)
     torch.cuda.synchronize()
     assert eng.launch_count() == 2          # reset + ONE fused launch for the whole horizon
     return o, oo, eng, gg
 
 
 def _check(o, oo, eng, gg, N, T, prec, extra=()):
-    tol = 2e-5 if prec == 'f64' else 1e-4            # f32 state: the north-star tolerance rtol 1e-4 over 200 steps
-    proofs = H.compare_rollouts(oo, gg, o.cfg, o.x_goal, N, T, obs_tol=tol, max_fork_frac=0.002, keys_extra=extra)
+    # BASELINE.json north_star: rtol 1e-4 over the 200-step horizon (the float32 policy's rounding differences are amplified by the
+    # closed loop: the worst of 819 200 samples sits at ~5e-5 in f64 mode); the first 25 steps must agree much tighter
+    early = (25, 5e-6 if prec == 'f64' else 3e-5)
+    proofs, worst = H.compare_rollouts(oo, gg, o.cfg, o.x_goal, N, T, obs_tol=1e-4, max_fork_frac=0.002, keys_extra=extra, early=early)
+    print('largest relative deviation per key:', {k: f'{v:.2e}' for k, v in worst.items()})
     done_frac = 1.0 - float(oo['mask'].mean())
     assert done_frac > 0.0                           # resets happened inside the horizon
     print(f'forks (all proven float ties at a termination threshold): {len(proofs)} of {N}: {proofs[:4]}')
     eng.close()
 
 
+ENGINES = ['ffma2', 'tcgen05']      # CUDA-core and tensor-core (3xTF32) policy MLP: both must meet the same bar
+
+
+@pytest.mark.parametrize('engine', ENGINES)
 @pytest.mark.parametrize('prec', ['f64', 'f32'])
-def test_c3_exactly_as_bench_runs_it(prec):
+def test_c3_exactly_as_bench_runs_it(prec, engine):
     '''bench.py default: quadrotor_2D_track, 4096 envs, T = 200, Philox seed 1337, hidden 64, default CTA shape.'''
     N, T = 4096, 200
-    o, oo, eng, gg = _run_pair('quadrotor_2D_track', N, T, 64, prec)
+    o, oo, eng, gg = _run_pair('quadrotor_2D_track', N, T, 64, prec, engine=engine)
     _check(o, oo, eng, gg, N, T, prec)
 
 
+@pytest.mark.parametrize('engine', ENGINES)
 @pytest.mark.parametrize('prec', ['f64', 'f32'])
-def test_c2_cartpole_4096(prec):
+def test_c2_cartpole_4096(prec, engine):
     N, T = 4096, 200
-    o, oo, eng, gg = _run_pair('cartpole_c2', N, T, 64, prec)
+    o, oo, eng, gg = _run_pair('cartpole_c2', N, T, 64, prec, engine=engine)
     _check(o, oo, eng, gg, N, T, prec)
 
 
+@pytest.mark.parametrize('engine', ENGINES)
 @pytest.mark.parametrize('prec', ['f64', 'f32'])
-def test_c4_as_baseline_states_it(prec):
+def test_c4_as_baseline_states_it(prec, engine):
     '''Quadrotor-3D figure-8, 8192 envs, in-kernel (Philox) inertial randomisation + white-noise dynamics + 32 constraint rows, fused
     collector, constraint values compared.'''
     N, T = 8192, 200
-    o, oo, eng, gg = _run_pair('quadrotor_3D_track_c4', N, T, 64, prec, want_cvals=True)
+    o, oo, eng, gg = _run_pair('quadrotor_3D_track_c4', N, T, 64, prec, want_cvals=True, engine=engine)
     assert o.n_con == 32 and gg['cvals'].shape == (T, N, 32)
     # the randomisation took effect: masses differ between envs (read back from the oracle through a reset observation is not
     # possible, so look at the thrust-to-acceleration spread instead: constraint values of the input rows are policy-only)
     _check(o, oo, eng, gg, N, T, prec, extra=('cvals',))
 
 
-@pytest.mark.parametrize('N,epb', [(4096 + 13, 0), (1000, 16), (37, 8)])
-def test_partial_last_cta(N, epb):
+@pytest.mark.parametrize('N,epb,engine', [(4096 + 13, 0, 'ffma2'), (1000, 16, 'ffma2'), (37, 8, 'ffma2'), (4096 + 13, 0, 'tcgen05'), (37, 0, 'tcgen05')])
+def test_partial_last_cta(N, epb, engine):
     '''N not a multiple of the CTA's env tile: the last CTA runs with dead lanes; env indices beyond the tile boundary.'''
     T = 120
-    o, oo, eng, gg = _run_pair('quadrotor_2D_track', N, T, 64, 'f64', epb=epb, seed=99)
+    o, oo, eng, gg = _run_pair('quadrotor_2D_track', N, T, 64, 'f64', epb=epb, seed=99, engine=engine)
     _check(o, oo, eng, gg, N, T, 'f64')
 
 
@@ -109,3 +119,29 @@ def test_sharded_ranks_reproduce_slices_of_the_single_batch():
             assert torch.equal(gs[k], gf[k][:, r * n:(r + 1) * n]), k
         sh.close()
     full.close()
+
+
+@pytest.mark.parametrize('name', ['quadrotor_2D_track', 'quadrotor_3D_track', 'cartpole_c2'])
+def test_tensor_core_policy_forward_matches_torch_fp32(name):
+    '''3xTF32 on tcgen05 against a plain float32 torch forward of the same 64-64 tanh actor-critic (deterministic rollout: act = mean,
+    v = value), rtol 1e-5 -- the policy parity bar of SURVEY.md 8c.'''
+    from safe_control_gym_b200.engine import EngineHandle
+    env = H.make_env(name)
+    N, T = 96, 30
+    pol = H.random_policy(env.obs_dim, env.action_dim, 64, seed=11)
+    eng = EngineHandle(env, num_envs=N, auto_reset=True, rng_mode='philox', seed=4)
+    eng.reset()
+    blob, dims = H.policy_blob(pol, eng.device)
+    out = eng.rollout(blob, dims, T, deterministic=True, mlp_engine='tcgen05')
+    obs = out['obs'].cpu()
+
+    def mlp(w, b, x):
+        for i in range(3):
+            x = torch.nn.functional.linear(x, torch.from_numpy(w[i]), torch.from_numpy(b[i]))
+            if i < 2:
+                x = torch.tanh(x)
+        return x
+    mean, val = mlp(pol.aw, pol.ab, obs), mlp(pol.cw, pol.cb, obs)
+    np.testing.assert_allclose(out['act'].cpu().numpy(), mean.numpy(), rtol=1e-5, atol=3e-6)
+    np.testing.assert_allclose(out['v'].cpu().numpy(), val.numpy(), rtol=1e-5, atol=3e-6)
+    eng.close()

@@ -85,7 +85,7 @@ CASES = [
 def _compare_rollouts(o, g, N, T, obs_tol, state_tol, oracle=None):
     '''o: oracle dict (numpy, trace=True), g: engine dict (torch).  Per env up to the first `mask` mismatch; every mismatch needs a
     proof that it is a float tie at a termination threshold (helpers.compare_rollouts).'''
-    return H.compare_rollouts(o, g, oracle.cfg, oracle.x_goal, N, T, obs_tol)
+    return H.compare_rollouts(o, g, oracle.cfg, oracle.x_goal, N, T, obs_tol)[0]
 
 
 @pytest.mark.parametrize('prec', ['f64', 'f32'])
