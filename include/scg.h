@@ -110,6 +110,8 @@ extern "C" {
 /* constraint row kinds */
 #define SCG_CON_LINEAR 0       /* g = a.z - b           (constraints.py:274) */
 #define SCG_CON_ABS 1          /* g = |a.z| - b         (SymmetricStateConstraint, constraints.py:445-447) */
+#define SCG_CON_QUAD 2         /* g = sum_ij q_ij z_i z_j - b  (QuadraticConstraint x'F'PFx - b, constraints.py:222); every non-zero of the
+                                * row carries the PAIR of z indices as col = i | (j << 8) */
 
 typedef struct scg_disturbance {
     int32_t kind;              /* SCG_DIST_* */
@@ -247,6 +249,10 @@ typedef struct scg_rollout_out {
     float*   d_ep_length_sum;  /* [N] nullable */
     float*   d_ep_cviol_sum;   /* [N] nullable */
     int32_t* d_ep_count;       /* [N] nullable */
+    /* with obs / reward normalisation (scg_rollout_args.d_norm): what the running normalisers of the controller must be updated with
+     * after the rollout (normalization.py:106-113,148-159) */
+    float* d_obs_raw;          /* [T][N][obs_dim] nullable: the UN-normalised observation env.step returned at step t (reset obs where done) */
+    float* d_rew_raw;          /* [T][N] nullable: the UN-normalised reward */
 } scg_rollout_out;
 
 /* Arguments of the fused rollout. */
@@ -274,6 +280,13 @@ typedef struct scg_rollout_args {
      * copies: one extra store per record entry instead of n_peers.  The plain local store is still issued (the kernel reads its own
      * record back for the GAE scan through the unicast address). */
     int64_t multicast_byte_offset;
+    /* Observation / reward normalisers of the controller (MeanStdNormalizer / RewardStdNormalizer, math_and_models/normalization.py:88-159;
+     * applied in ppo.py:270-271) with statistics FROZEN for the duration of the rollout (the controller updates them once per rollout
+     * from d_obs_raw / d_rew_raw).  d_norm = NULL: off.  Layout (float64): mean[obs_dim], inv_std[obs_dim] = 1/sqrt(var + eps),
+     * clip_obs, obs_on (0/1), rew_scale = 1/sqrt(var_ret + eps), clip_rew, rew_on (0/1).  The terminal observation fed to the critic
+     * stays un-normalised, as in the reference (ppo.py:279-282). */
+    const double* d_norm;
+    const float* d_obs0;       /* [N][obs_dim] nullable: policy input of step 0 (default: the observation the engine carried over) */
 } scg_rollout_args;
 
 typedef struct scg_env scg_env;   /* opaque, one per (device, batch) */

@@ -60,7 +60,7 @@ class _Policy(C.Structure):
 class _RolloutOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('obs', 'act', 'rew', 'mask', 'v', 'logp', 'terminal_v', 'ret', 'adv', 'cviol', 'cvals', 'mse',
                                          'last_obs', 'last_val', 'ep_return_sum', 'ep_length_sum', 'ep_cviol_sum', 'ep_count',
-                                         'state_trace')]
+                                         'state_trace', 'replay_obs', 'replay_act', 'replay_mask', 'next_obs', 'norm', 'obs0', 'obs_raw', 'rew_raw')]
 
 
 class OraclePolicy:
@@ -173,7 +173,9 @@ class Oracle:
             raise RuntimeError('[ERROR] You must call env.reset() at least once before using env.step().')
         return o
 
-    def rollout(self, policy, T, eps=None, deterministic=False, gamma=0.99, gae_lambda=0.95, use_gae=False, trace=False):
+    def rollout(self, policy, T, eps=None, deterministic=False, gamma=0.99, gae_lambda=0.95, use_gae=False, trace=False, replay=None, norm=None, obs0=None):
+        '''replay = {'obs', 'act', 'mask'} (float32 [T][N][.] arrays of another collector's record): teacher-forced one-step predictions,
+        see oracle_rollout_out in scg_oracle.c.'''
         N, od, A, nc = self.N, self.obs_dim, self.nu, self.n_con
         f = np.float32
         o = {
@@ -187,9 +189,23 @@ class Oracle:
             o['cvals'] = np.empty((T, N, nc), f)
         if trace:
             o['state_trace'] = np.empty((T, N, self.nx), np.float64)
+        keep = []
+        if norm is not None:
+            o['obs_raw'] = np.empty((T, N, od), f)
+            o['rew_raw'] = np.empty((T, N, 1), f)
+        if replay is not None:
+            o['next_obs'] = np.empty((T, N, od), f)
+            for k in ('obs', 'act', 'mask'):
+                keep.append(np.ascontiguousarray(replay[k], dtype=np.float32).reshape(T, N, -1))
         ro = _RolloutOut()
         for k, v in o.items():
             setattr(ro, k, v.ctypes.data)
+        if replay is not None:
+            ro.replay_obs, ro.replay_act, ro.replay_mask = keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data
+        if norm is not None:
+            keep.append(np.ascontiguousarray(norm, dtype=np.float64)); ro.norm = keep[-1].ctypes.data
+        if obs0 is not None:
+            keep.append(np.ascontiguousarray(obs0, dtype=np.float32)); ro.obs0 = keep[-1].ctypes.data
         e = None if eps is None else np.ascontiguousarray(eps, dtype=np.float32).reshape(T, N, A)
         ps = policy.c_struct()
         rc = self.lib.scg_oracle_rollout(self.h, C.byref(ps), _p(e), C.c_int(T), C.c_int(int(deterministic)), C.c_double(gamma),

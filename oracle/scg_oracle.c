@@ -518,6 +518,12 @@ static int eval_constraints(const scg_oracle* o, const oenv* e, double* g_out) {
     for (int r = 0; r < rows; ++r) {
         double acc = 0;
         for (int p = o->row_ptr[r]; p < o->row_ptr[r + 1]; ++p) {
+            if (o->row_kind[r] == SCG_CON_QUAD) {      /* x'F'PFx (CO:222): the non-zero carries the pair of z indices */
+                int c0 = o->col[p] & 0xff, c1 = o->col[p] >> 8;
+                double z0 = c0 < nx ? e->state[c0] : e->noisy_act[c0 - nx], z1 = c1 < nx ? e->state[c1] : e->noisy_act[c1 - nx];
+                acc += o->val[p] * z0 * z1;
+                continue;
+            }
             int cidx = o->col[p];
             double z = cidx < nx ? e->state[cidx] : e->noisy_act[cidx - nx];
             acc += o->val[p] * z;
@@ -736,6 +742,25 @@ void scg_oracle_set_env_state(scg_oracle* o, int i, const double* state, const d
     make_obs(o, e, e->ctrl_step == 0, &ns, e->obs);
 }
 
+/* Overwrites the physical state of env i with an OBSERVED env.state (the inverse of extract_state): used by the teacher-forced
+ * replay below.  Counters, episode index and the per-episode inertial properties are left alone. */
+static void inject_observed_state(scg_oracle* o, int i, const double* st) {
+    oenv* e = &o->envs[i]; const scg_config* c = &o->cfg;
+    if (c->system == SCG_SYS_CARTPOLE) { e->q[0] = st[0]; e->qd[0] = st[1]; e->q[1] = st[2]; e->qd[1] = st[3]; }
+    else if (c->system == SCG_SYS_QUAD1D) { e->pos[2] = st[0]; e->vel[2] = st[1]; }
+    else if (c->system == SCG_SYS_QUAD2D) {
+        double rpy[3] = {0, st[4], 0};
+        e->pos[0] = st[0]; e->vel[0] = st[1]; e->pos[1] = 0; e->vel[1] = 0; e->pos[2] = st[2]; e->vel[2] = st[3];
+        quat_from_rpy(rpy, e->quat); e->omega[0] = 0; e->omega[1] = st[5]; e->omega[2] = 0;
+    } else {
+        double rpy[3] = {st[6], st[7], st[8]}, R[9];
+        e->pos[0] = st[0]; e->vel[0] = st[1]; e->pos[1] = st[2]; e->vel[1] = st[3]; e->pos[2] = st[4]; e->vel[2] = st[5];
+        quat_from_rpy(rpy, e->quat); rot_from_quat(e->quat, R);
+        for (int r = 0; r < 3; ++r) e->omega[r] = R[3 * r + 0] * st[9] + R[3 * r + 1] * st[10] + R[3 * r + 2] * st[11];   /* omega_world = R . body rates */
+    }
+    extract_state(o, e);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* policy: MLPActorCritic (PU:149-238, neural_networks.py:18-54, distributions.py:9-33), float32 */
 /* ------------------------------------------------------------------------------------------ */
@@ -766,6 +791,18 @@ typedef struct {
     float *obs, *act, *rew, *mask, *v, *logp, *terminal_v, *ret, *adv, *cviol, *cvals, *mse, *last_obs, *last_val;
     float *ep_return_sum, *ep_length_sum, *ep_cviol_sum; int32_t* ep_count;
     double* state_trace;   /* [T][N][nx] env.state after each step before auto-reset (debug) */
+    /* TEACHER-FORCED REPLAY of somebody else's record (the CUDA collector's): before every step the env's physical state is
+     * overwritten with the state part of replay_obs[t] and the env is stepped with replay_act[t]; an episode ends when
+     * replay_mask[t] says so.  Every output of this struct is then the oracle's answer to the RECORD's own inputs of that step --
+     * one-step predictions, free of the closed-loop amplification of float32 rounding differences.  `act` holds mean + sd * eps
+     * (what the sampler should have produced for the recorded observation); `next_obs` the observation after the step
+     * (terminal observation when done; compare with replay_obs[t + 1] where the record did not reset). */
+    const float *replay_obs, *replay_act, *replay_mask;
+    float* next_obs;       /* [T][N][obs_dim] */
+    /* frozen observation / reward normalisers (normalization.py:88-159 as applied in PPO:270-271; layout of scg_rollout_args.d_norm) */
+    const double* norm;
+    const float* obs0;     /* [N][obs_dim] policy input of step 0 (nullable) */
+    float *obs_raw, *rew_raw;
 } oracle_rollout_out;
 
 /* PPO.train_step collector loop (PPO:259-297) + compute_returns_and_advantages (PU:374-400) */
@@ -776,13 +813,23 @@ int scg_oracle_rollout(scg_oracle* o, const oracle_policy* p, const float* eps /
     for (int i = 0; i < N; ++i) if (!o->envs[i].initial_reset) return SCG_ESTATE;
     if (out->ep_count) for (int i = 0; i < N; ++i) { out->ep_count[i] = 0; out->ep_return_sum[i] = 0; out->ep_length_sum[i] = 0; out->ep_cviol_sum[i] = 0; }
     const float log_sqrt_2pi = (float)log(sqrt(2 * PI_D));
+    const double* nm = out->norm;
+    const int norm_obs = nm && nm[2 * od + 1] != 0.0, norm_rew = nm && nm[2 * od + 4] != 0.0;
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < N; ++i) {
         oenv* e = &o->envs[i];
         const uint32_t genv = (uint32_t)(c->env_index_offset + i);
+        if (out->obs0) for (int k = 0; k < od; ++k) e->obs[k] = (double)out->obs0[(size_t)i * od + k];
         for (int t = 0; t < T; ++t) {
             size_t tn = (size_t)t * N + i;
             float obs_f[SCG_MAX_OBS], mean[SCG_MAX_NU], val, act[SCG_MAX_NU];
+            const int replay = out->replay_obs != NULL;
+            if (replay) {
+                double st[SCG_MAX_NX];
+                for (int k = 0; k < nx; ++k) st[k] = (double)out->replay_obs[tn * od + k];
+                inject_observed_state(o, i, st);
+                for (int k = 0; k < od; ++k) e->obs[k] = (double)out->replay_obs[tn * od + k];
+            }
             for (int k = 0; k < od; ++k) obs_f[k] = (float)e->obs[k];        /* torch.FloatTensor(obs) PPO:268 */
             mlp_forward(p->aw, p->ab, od, p->hidden, A, p->activation, obs_f, mean);
             mlp_forward(p->cw, p->cb, od, p->hidden, 1, p->activation, obs_f, &val);
@@ -795,14 +842,17 @@ int scg_oracle_rollout(scg_oracle* o, const oracle_policy* p, const float* eps /
                 float d = act[k] - mean[k];
                 logp += -(d * d) / (2 * sd * sd) - p->logstd[k] - log_sqrt_2pi; /* distributions.py:12-21 */
             }
-            double actd[SCG_MAX_NU]; for (int k = 0; k < A; ++k) actd[k] = (double)act[k];
+            double actd[SCG_MAX_NU]; for (int k = 0; k < A; ++k) actd[k] = replay ? (double)out->replay_act[tn * A + k] : (double)act[k];
             const double* nrow = (c->rng_mode == SCG_RNG_TABLE && o->noise_table && o->D > 0)
                                  ? o->noise_table + ((size_t)((o->noise_cursor + t) % o->Tn) * N + i) * o->D : NULL;
             double nobs[SCG_MAX_OBS], cv[SCG_MAX_CON_ROWS]; step_info inf;
             env_step(o, i, actd, nrow, nobs, &inf, cv);
             if (out->state_trace) memcpy(out->state_trace + tn * nx, e->state, sizeof(double) * nx);
+            if (out->next_obs) for (int k = 0; k < od; ++k) out->next_obs[tn * od + k] = (float)nobs[k];
             e->ep_return += inf.rew; e->ep_length += 1; e->ep_cviol += inf.cviol;
             float term_v = 0;
+            const int own_done = inf.done;
+            if (replay) inf.done = out->replay_mask[tn] == 0.f;            /* follow the record's episode boundaries */
             if (inf.done) {
                 if (inf.truncated) {                                          /* PPO:274-283 */
                     float tobs[SCG_MAX_OBS]; for (int k = 0; k < od; ++k) tobs[k] = (float)nobs[k];
@@ -812,9 +862,19 @@ int scg_oracle_rollout(scg_oracle* o, const oracle_policy* p, const float* eps /
                 e->ep_return = 0; e->ep_length = 0; e->ep_cviol = 0;
                 env_reset(o, i);                                              /* VE:33-38 */
             } else memcpy(e->obs, nobs, sizeof(double) * od);
+            /* PPO:270-271: next_obs = obs_normalizer(next_obs); rew = reward_normalizer(rew, done) -- statistics frozen for the rollout */
+            if (out->obs_raw) for (int k = 0; k < od; ++k) out->obs_raw[tn * od + k] = (float)e->obs[k];
+            if (norm_obs) for (int k = 0; k < od; ++k) {
+                double y = ((double)(float)e->obs[k] - nm[k]) * nm[od + k];
+                y = y < -nm[2 * od] ? -nm[2 * od] : y; y = y > nm[2 * od] ? nm[2 * od] : y;
+                e->obs[k] = (double)(float)y;
+            }
+            if (out->rew_raw) out->rew_raw[tn] = (float)inf.rew;
+            float rew_rec = (float)inf.rew;
+            if (norm_rew) { double y = (double)rew_rec * nm[2 * od + 2]; y = y < -nm[2 * od + 3] ? -nm[2 * od + 3] : y; y = y > nm[2 * od + 3] ? nm[2 * od + 3] : y; rew_rec = (float)y; }
             for (int k = 0; k < od; ++k) out->obs[tn * od + k] = obs_f[k];
             for (int k = 0; k < A; ++k) out->act[tn * A + k] = act[k];
-            out->rew[tn] = (float)inf.rew; out->mask[tn] = inf.done ? 0.f : 1.f; out->v[tn] = val; out->logp[tn] = logp; out->terminal_v[tn] = term_v;
+            out->rew[tn] = rew_rec; out->mask[tn] = (replay ? own_done : inf.done) ? 0.f : 1.f; out->v[tn] = val; out->logp[tn] = logp; out->terminal_v[tn] = term_v;
             if (out->cviol) out->cviol[tn] = (float)inf.cviol;
             if (out->cvals && nc > 0) for (int k = 0; k < nc; ++k) out->cvals[tn * nc + k] = (float)cv[k];
             if (out->mse) out->mse[tn] = (float)inf.mse;

@@ -30,7 +30,7 @@ SCG_DIST_IMPULSE, SCG_DIST_STEP, SCG_DIST_UNIFORM, SCG_DIST_WHITE, SCG_DIST_PERI
 SCG_MODE_ACTION, SCG_MODE_DYNAMICS, SCG_MODE_OBSERVATION = 0, 1, 2
 SCG_RAND_NONE, SCG_RAND_UNIFORM, SCG_RAND_NORMAL = 0, 1, 2
 SCG_ACT_TANH, SCG_ACT_RELU, SCG_ACT_LEAKY_RELU = 0, 1, 2
-SCG_CON_LINEAR, SCG_CON_ABS = 0, 1
+SCG_CON_LINEAR, SCG_CON_ABS, SCG_CON_QUAD = 0, 1, 2
 SCG_MLP_AUTO, SCG_MLP_FFMA2, SCG_MLP_TCGEN05 = 0, 1, 2
 MLP_ENGINES = {'auto': SCG_MLP_AUTO, 'ffma2': SCG_MLP_FFMA2, 'tcgen05': SCG_MLP_TCGEN05}
 
@@ -88,7 +88,7 @@ class scg_step_out(C.Structure):
 class scg_rollout_out(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         'd_obs', 'd_act', 'd_rew', 'd_mask', 'd_v', 'd_logp', 'd_terminal_v', 'd_ret', 'd_adv', 'd_cviol', 'd_cvals', 'd_mse',
-        'd_last_obs', 'd_last_val', 'd_ep_return_sum', 'd_ep_length_sum', 'd_ep_cviol_sum', 'd_ep_count')]
+        'd_last_obs', 'd_last_val', 'd_ep_return_sum', 'd_ep_length_sum', 'd_ep_cviol_sum', 'd_ep_count', 'd_obs_raw', 'd_rew_raw')]
 
 
 class scg_rollout_args(C.Structure):
@@ -98,7 +98,7 @@ class scg_rollout_args(C.Structure):
         ('gamma', C.c_double), ('gae_lambda', C.c_double),
         ('d_policy', C.c_void_p), ('d_eps', C.c_void_p),
         ('n_peers', C.c_int32), ('mlp_engine', C.c_int32), ('peer_byte_offset', C.c_int64 * SCG_MAX_PEERS),
-        ('multicast_byte_offset', C.c_int64),
+        ('multicast_byte_offset', C.c_int64), ('d_norm', C.c_void_p), ('d_obs0', C.c_void_p),
     ]
 
 

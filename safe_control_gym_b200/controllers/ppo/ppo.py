@@ -22,7 +22,7 @@ from safe_control_gym_b200.controllers.ppo.ppo_utils import PPOAgent
 from safe_control_gym_b200.engine import pack_policy
 from safe_control_gym_b200.envs.env_wrappers.record_episode_statistics import VecRecordEpisodeStatistics
 from safe_control_gym_b200.envs.env_wrappers.vectorized_env import make_vec_envs
-from safe_control_gym_b200.math_and_models.normalization import BaseNormalizer
+from safe_control_gym_b200.math_and_models.normalization import BaseNormalizer, MeanStdNormalizer, RewardStdNormalizer
 
 # defaults of safe_control_gym/controllers/ppo/ppo.yaml:1-39
 DEFAULT_CONFIG = dict(
@@ -176,9 +176,6 @@ class PPO:
             self.__dict__[k] = v
         self.env_func, self.training = env_func, training
         self.checkpoint_path, self.output_dir, self.seed = checkpoint_path, output_dir, seed
-        if self.norm_obs or self.norm_reward:
-            raise NotImplementedError('running obs/reward normalisers reduce over the whole batch every step '
-                                      '(normalization.py:106-113,148-159) and are not available in the fused collector')
         import torch.distributed as dist
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
@@ -198,7 +195,13 @@ class PPO:
                               opt_epochs=self.opt_epochs, mini_batch_size=self.mini_batch_size, activation=self.activation,
                               fused_update=cfg.get('fused_update'))
         self.agent.to(self.device)
+        # pre-/post-processing (ppo.py:70-75).  Inside the fused collector the statistics are frozen for one rollout and updated after it
+        # from the raw streams the kernel records (math_and_models/normalization.py)
         self.obs_normalizer, self.reward_normalizer = BaseNormalizer(), BaseNormalizer()
+        if self.norm_obs:
+            self.obs_normalizer = MeanStdNormalizer(shape=self.env.observation_space.shape, clip=self.clip_obs, epsilon=1e-8, device=self.device)
+        if self.norm_reward:
+            self.reward_normalizer = RewardStdNormalizer(gamma=self.gamma, clip=self.clip_reward, epsilon=1e-8, device=self.device)
         self.logger = _Logger(output_dir)
         self._perm_gen = torch.Generator(device=self.device)
         self._perm_gen.manual_seed(int(seed) + 12345)      # identical on every rank
@@ -214,7 +217,7 @@ class PPO:
             self.env.add_tracker('constraint_violation', 0, mode='queue')
             self.total_steps = 0
             obs, _ = self.env.reset()
-            self.obs = obs
+            self.obs = self.obs_normalizer(obs).to(torch.float32) if self.norm_obs else obs      # ppo.py:96-97
 
     def close(self):
         self.env.close()
@@ -325,12 +328,47 @@ class PPO:
             if cached is None:
                 kw = self._peer.rollout_kwargs()
             self._peer.begin()      # every rank's previous update has consumed the gathered buffer before anyone overwrites it
+        want = ('ret', 'adv', 'cviol', 'mse', 'last', 'episode')
+        if self.norm_obs or self.norm_reward:
+            want += ('raw',)
+            kw.update(norm=self._norm_blob(), obs0=self.obs.contiguous() if self.norm_obs else None)
         out = eng.rollout(blob, dims, T, eps=eps, activation=self.activation, gamma=self.gamma, gae_lambda=self.gae_lambda,
-                          use_gae=self.use_gae, deterministic=deterministic, out=cached,
-                          want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode'), **kw)
+                          use_gae=self.use_gae, deterministic=deterministic, out=cached, want=want, **kw)
         if eps is None:
             self._rollout_out[T] = out
         return out
+
+    def _norm_blob(self):
+        '''Frozen normaliser statistics in the layout of scg_rollout_args.d_norm.'''
+        od = self.env.observation_space.shape[0]
+        b = torch.zeros(2 * od + 5, dtype=torch.float64, device=self.device)
+        if self.norm_obs:
+            rms = self.obs_normalizer.rms
+            b[:od] = rms.mean
+            b[od:2 * od] = 1.0 / torch.sqrt(rms.var + self.obs_normalizer.epsilon)
+            b[2 * od], b[2 * od + 1] = float(self.obs_normalizer.clip), 1.0
+        if self.norm_reward:
+            b[2 * od + 2], b[2 * od + 3], b[2 * od + 4] = self.reward_normalizer.scale(), float(self.reward_normalizer.clip), 1.0
+        return b
+
+    def _update_normalizers(self, out):
+        '''Once per rollout (the reference: once per step, ppo.py:270-271): merge the raw streams of the rollout into the statistics.'''
+        if self.norm_obs and not self.obs_normalizer.read_only:
+            raw = out['obs_raw'].reshape(-1, out['obs_raw'].shape[-1])
+            if self.world > 1:
+                import torch.distributed as dist
+                n = torch.tensor([raw.shape[0]], dtype=torch.float64, device=self.device)
+                s1, s2 = raw.double().sum(0), raw.double().square().sum(0)
+                for t in (n, s1, s2):
+                    dist.all_reduce(t)
+                mean = s1 / n
+                self.obs_normalizer.rms.update_from_moments(mean, s2 / n - mean.square(), float(n))
+            else:
+                self.obs_normalizer.rms.update(raw)
+        if self.norm_reward and not self.reward_normalizer.read_only:
+            if self.world > 1:
+                raise NotImplementedError('norm_reward with several ranks: the running-return statistics are per-env and not reduced yet')
+            self.reward_normalizer.update_from_rollout(out['rew_raw'][..., 0], 1.0 - out['mask'][..., 0])
 
     def _policy_blob(self):
         '''Packed rollout blob: one pack kernel from the flat training vector (fused update) or the torch packer.'''
@@ -344,6 +382,9 @@ class PPO:
         out = self.collect()
         self.obs = out['last_obs']
         self.total_steps += self.rollout_batch_size * self.rollout_steps
+        if self.norm_obs or self.norm_reward:
+            self.obs_normalizer.unset_read_only()
+            self._update_normalizers(out)
         if self.world > 1:
             batch = self._peer.finish(out) if self._peer is not None else all_gather_rollout(out)
         else:
@@ -368,10 +409,15 @@ class PPO:
                 self.eval_env.close()
             self.eval_env = make_vec_envs(self.env_func, None, n_episodes, 1, self.seed * 111, rng_mode=self.env.unwrapped.rng_mode,
                                           device=self.device.index, precision=self.precision)
-        self.eval_env.reset()
+        obs, _ = self.eval_env.reset()
         blob, dims = self._policy_blob()
         T = int(self.eval_env.proto.CTRL_STEPS)
-        out = self.eval_env.engine.rollout(blob, dims, T, activation=self.activation, deterministic=True, want=('cviol', 'mse', 'episode'))
+        kw = {}
+        if self.norm_obs:              # ppo.py:218,229: frozen statistics during evaluation
+            self.obs_normalizer.set_read_only()
+            kw = dict(norm=self._norm_blob(), obs0=self.obs_normalizer.normalize(obs).to(torch.float32).contiguous())
+            kw['norm'][2 * dims[0] + 4] = 0.0       # evaluation reports raw rewards
+        out = self.eval_env.engine.rollout(blob, dims, T, activation=self.activation, deterministic=True, want=('cviol', 'mse', 'episode'), **kw)
         mask = out['mask'][..., 0]
         first_done = torch.where((mask == 0).any(0), (mask == 0).float().argmax(0), torch.full((n_episodes,), T - 1, device=self.device))
         steps = torch.arange(T, device=self.device)[:, None]

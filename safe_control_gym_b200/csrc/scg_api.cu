@@ -190,8 +190,13 @@ int scg_set_constraints(scg_env* e, int32_t n_rows, const int32_t* kind, const i
     if (!kind || !strict || !row_ptr || !col || !val || !b) return fail(e, SCG_EINVAL, "scg_set_constraints: null argument");
     const int nnz = row_ptr[n_rows];
     if (nnz < 0 || nnz > SCG_MAX_CON_NNZ) return fail(e, SCG_EINVAL, "scg_set_constraints: too many non-zeros");
-    for (int i = 0; i < nnz; ++i)
-        if (col[i] < 0 || col[i] >= e->nx + e->nu) return fail(e, SCG_EINVAL, "scg_set_constraints: column index out of range");
+    for (int r = 0; r < n_rows; ++r) {
+        if (kind[r] < SCG_CON_LINEAR || kind[r] > SCG_CON_QUAD) return fail(e, SCG_EINVAL, "scg_set_constraints: unknown row kind");
+        for (int i = row_ptr[r]; i < row_ptr[r + 1]; ++i) {
+            const int c0 = kind[r] == SCG_CON_QUAD ? (col[i] & 0xff) : col[i], c1 = kind[r] == SCG_CON_QUAD ? (col[i] >> 8) : 0;
+            if (c0 < 0 || c0 >= e->nx + e->nu || c1 < 0 || c1 >= e->nx + e->nu) return fail(e, SCG_EINVAL, "scg_set_constraints: column index out of range");
+        }
+    }
     CUDA_TRY(e, upload(&e->d_con_kind, kind, (size_t)n_rows));
     CUDA_TRY(e, upload(&e->d_con_strict, strict, (size_t)n_rows));
     CUDA_TRY(e, upload(&e->d_con_ptr, row_ptr, (size_t)n_rows + 1));
@@ -295,6 +300,7 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
     }
     if (a->multicast_byte_offset & 15) return fail(e, SCG_EINVAL, "scg_rollout: multicast_byte_offset must be a multiple of 16");
     P.mc_off = a->multicast_byte_offset;
+    P.norm = a->d_norm; P.obs0 = a->d_obs0;
     cudaStream_t s = (cudaStream_t)stream;
     const bool dbl = e->cfg.precision == SCG_PREC_F64;
     RolloutLaunch rl{e->cfg.num_envs, e->obs_dim, e->nu, e->nx, e->L, e->tab};

@@ -333,7 +333,7 @@ __device__ __noinline__ void hot_load(const DevTables& T, HotCfg<R>* h) {
     h->n_con = T.n_con; h->con_fast = 1;
     for (int r = 0; r < T.n_con; ++r) {
         const int p0 = T.con_ptr[r], p1 = T.con_ptr[r + 1];
-        if (p1 - p0 > 1) h->con_fast = 0;
+        if (p1 - p0 > 1 || T.con_kind[r] == SCG_CON_QUAD) h->con_fast = 0;
         ConRow row; row.col = p1 > p0 ? T.con_col[p0] : 0; row.val = p1 > p0 ? T.con_val[p0] : 0.0; row.b = T.con_b[r];
         row.flags = (T.con_strict[r] ? 1 : 0) | (T.con_kind[r] == SCG_CON_ABS ? 2 : 0);
         h->rows[r] = row;
@@ -944,7 +944,11 @@ static __device__ __noinline__ int env_constraints(const DevTables& T, const Con
     } else {
         for (int r = 0; r < n_con; ++r) {
             double acc = 0;
-            for (int p = T.con_ptr[r]; p < T.con_ptr[r + 1]; ++p) acc += T.con_val[p] * zbuf[T.con_col[p] * zstride];
+            if (T.con_kind[r] == SCG_CON_QUAD) {       // x' F' P F x (constraints.py:222): every non-zero carries a pair of z indices
+                for (int p = T.con_ptr[r]; p < T.con_ptr[r + 1]; ++p) { const int cc = T.con_col[p]; acc += T.con_val[p] * zbuf[(cc & 0xff) * zstride] * zbuf[(cc >> 8) * zstride]; }
+            } else {
+                for (int p = T.con_ptr[r]; p < T.con_ptr[r + 1]; ++p) acc += T.con_val[p] * zbuf[T.con_col[p] * zstride];
+            }
             if (T.con_kind[r] == SCG_CON_ABS) acc = fabs(acc);
             const double gi = rint((acc - T.con_b[r]) * 1e8);
             cviol |= T.con_strict[r] ? (gi >= 0.0) : (gi > 0.0);

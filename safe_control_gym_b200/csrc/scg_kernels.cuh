@@ -272,6 +272,8 @@ struct RolloutParams {
     scg_rollout_out out;
     int n_peers;                 // fused all-gather: peer copies of the PPOBuffer keys (see scg_rollout_args)
     long long peer_off[SCG_MAX_PEERS];
+    const double* norm;          // frozen obs / reward normaliser statistics (scg_rollout_args.d_norm), nullable
+    const float* obs0;           // policy input of step 0, nullable
     long long mc_off;            // != 0: NVSwitch multicast mapping of the gathered buffer (multimem.st), replaces the unicast peer copies
     long long* prof;     // SCG_PROF builds: per-phase cycle counters of CTA 0 (nullable)
 };
@@ -457,6 +459,21 @@ __device__ __forceinline__ float mlp_out(const float* __restrict__ s_outp, const
     return v;
 }
 
+// frozen normaliser statistics in shared memory (MeanStdNormalizer / RewardStdNormalizer, normalization.py:88-159)
+struct NormState { double mean[SCG_MAX_OBS], inv[SCG_MAX_OBS], clip_obs, rew_scale, clip_rew; int obs_on, rew_on; };
+__device__ __forceinline__ void norm_load(NormState* s, const double* g, int od, int tid, int nthreads) {
+    for (int i = tid; i < od; i += nthreads) { s->mean[i] = g[i]; s->inv[i] = g[od + i]; }
+    if (tid == 0) { s->clip_obs = g[2 * od]; s->obs_on = g[2 * od + 1] != 0.0; s->rew_scale = g[2 * od + 2]; s->clip_rew = g[2 * od + 3]; s->rew_on = g[2 * od + 4] != 0.0; }
+}
+__device__ __forceinline__ float norm_obs_value(const NormState* s, int k, float x) {     // np.clip((x - mean) / sqrt(var + eps), -clip, clip)
+    const double y = ((double)x - s->mean[k]) * s->inv[k];
+    return (float)fmin(fmax(y, -s->clip_obs), s->clip_obs);
+}
+__device__ __forceinline__ float norm_rew_value(const NormState* s, float r) {            // np.clip(x / sqrt(var + eps), -clip, clip)
+    const double y = (double)r * s->rew_scale;
+    return (float)fmin(fmax(y, -s->clip_rew), s->clip_rew);
+}
+
 #ifdef SCG_PROF
 #define PROF_T(v) long long v = clock64()
 #else
@@ -511,6 +528,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     __shared__ float s_rec[2 * (A + 2) * E];   // FAST: act, v, logp of the last two steps, stored to the record by a helper warp
     __shared__ float s_stat[6 * E];            // FAST: episode statistics kept by the record helpers, handed back at the end
     __shared__ int s_epc[E];
+    __shared__ NormState s_norm;
 
     const int od = T.obs_dim, N = T.N, nc = T.n_con;
     const int tid = threadIdx.x;
@@ -549,10 +567,13 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     if (owner) { s_tsteps0[ol] = live ? e.total_steps : 0u; s_epi[ol] = live ? e.episode : 0; s_cand_ep[ol] = -1; s_cand_ep[E + ol] = -1; }
     const bool use_cand = SPLIT && h->n_off_draws == 0;
     for (int i = tid; i < T.L * NX; i += NT) s_xg[i] = (R)T.x_goal[i];
+    const float* obs_src = P.obs0 ? P.obs0 : T.st.cur_obs;
     for (int i = tid; i < E * od; i += NT) {
         const int ee = i / od, k = i % od;
-        s_obs[tile_idx<E>(k, ee)] = (n0 + ee < N) ? T.st.cur_obs[(size_t)(n0 + ee) * od + k] : 0.f;
+        s_obs[tile_idx<E>(k, ee)] = (n0 + ee < N) ? obs_src[(size_t)(n0 + ee) * od + k] : 0.f;
     }
+    if (P.norm) norm_load(&s_norm, P.norm, od, tid, NT);
+    const bool norm_obs = P.norm != nullptr && P.norm[2 * od + 1] != 0.0, norm_rew = P.norm != nullptr && P.norm[2 * od + 4] != 0.0;
     float ep_ret_sum = 0.f, ep_len_sum = 0.f, ep_cv_sum = 0.f; int ep_count = 0;
     mbar_wait(&s_bar, 0);
     __syncthreads();
@@ -612,7 +633,8 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
 #pragma unroll
             for (int k = 0; k < A; ++k) { ny[k] = (R)zb[(NX + k) * E]; cl[k] = (R)zb[(NX + A + k) * E]; }
             env_reward_mse<SYS, R, R>(h, s_xg, st, ny, cl, s_cstep[bsel * E + ee], rw, ms);
-            pstore(P, P.out.d_rew + tnp, (float)rw);
+            if (P.out.d_rew_raw) P.out.d_rew_raw[tnp] = (float)rw;
+            pstore(P, P.out.d_rew + tnp, norm_rew ? norm_rew_value(&s_norm, (float)rw) : (float)rw);
             if (P.out.d_mse) P.out.d_mse[tnp] = (float)ms;
             h_a += (float)rw; h_b += 1.f;
             if (dn) { h_cnt += 1; h_sa += h_a; h_sb += h_b; h_a = 0.f; h_b = 0.f; }
@@ -804,9 +826,19 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                     } else {
                         make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_on, ol});
                     }
-                    pstore(P, P.out.d_rew + tn, (float)rew);
+                    if (P.out.d_rew_raw) P.out.d_rew_raw[tn] = (float)rew;
+                    pstore(P, P.out.d_rew + tn, norm_rew ? norm_rew_value(&s_norm, (float)rew) : (float)rew);
                     if (P.out.d_cviol) P.out.d_cviol[tn] = (float)cviol;
                     if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
+                }
+                if (norm_obs || P.out.d_obs_raw) {       // the observation env.step returned: raw copy for the statistics update, normalised in place
+                    float* raw = P.out.d_obs_raw ? P.out.d_obs_raw + tn * od : nullptr;
+                    for (int k = 0; k < od; ++k) {
+                        const int i = tile_idx<E>(k, ol);
+                        const float x = s_on[i];
+                        if (raw) raw[k] = x;
+                        if (norm_obs) s_on[i] = norm_obs_value(&s_norm, k, x);
+                    }
                 }
                 trunc = truncated;
                 if (relay) {

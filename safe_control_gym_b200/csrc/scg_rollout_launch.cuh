@@ -74,7 +74,7 @@ static RolloutLaunchResult launch_rollout(const RolloutLaunch& e, RolloutParams 
 // tensor-core collector (tcgen05 / TMEM, 3xTF32): 32 envs x 256 threads, hidden 64
 template <int SYS, typename R, int HID>
 static RolloutLaunchResult launch_rollout_tc(const RolloutLaunch& e, RolloutParams P, cudaStream_t s) {
-    const tc::Smem<HID> S(e.obs_dim, e.nu, e.L * e.nx * (int)(sizeof(R) / 4));
+    const typename tc::Variant<HID>::Plan S(e.obs_dim, e.nu, e.L * e.nx * (int)(sizeof(R) / 4));
     const size_t smem = (size_t)S.total_floats * sizeof(float);
     auto kern = rollout_tc_kernel<SYS, R, HID>;
     cudaFuncAttributes fa;
@@ -82,8 +82,20 @@ static RolloutLaunchResult launch_rollout_tc(const RolloutLaunch& e, RolloutPara
     if (smem + fa.sharedSizeBytes > 227 * 1024) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: the tensor-core collector does not fit this configuration in shared memory"};
     RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int G = (e.num_envs + tc::E - 1) / tc::E;
+#ifdef SCG_TC_PROF
+    { long long z[16] = {0}; cudaMemcpyToSymbol(tc_ticks, z, sizeof(z)); }
+#endif
     kern<<<G, tc::NT, smem, s>>>(e.tab, P);
     RL_CUDA(cudaGetLastError());
+#ifdef SCG_TC_PROF
+    {
+        long long tk[16]; cudaMemcpyFromSymbol(tk, tc_ticks, sizeof(tk));
+        const char* nm[11] = {"L1 issue", "L1 wait", "E1", "E1 fence+sync", "L2 issue", "L2 wait", "E2", "E2 sync", "owner env", "owner->barrier", "env phase (warp 0)"};
+        fprintf(stderr, "[SCG_TC_PROF] cycles / forward (T=%d, ~T+1 forwards):", P.T);
+        for (int i = 0; i < 11; ++i) fprintf(stderr, " %s=%.0f", nm[i], (double)tk[i] / P.T);
+        fprintf(stderr, "\n");
+    }
+#endif
     return RolloutLaunchResult{SCG_OK, cudaSuccess, nullptr};
 }
 
@@ -96,11 +108,15 @@ static RolloutLaunchResult dispatch_rollout(const RolloutLaunch& e, const scg_ro
     (void)NTq;
 #ifndef SCG_PROF
     // mlp_engine: 0 = library default, 1 = CUDA cores (FFMA2), 2 = tensor cores (tcgen05, 3xTF32; hidden 64, 32 envs per CTA)
-    if (a->mlp_engine == SCG_MLP_TCGEN05 || (a->mlp_engine == SCG_MLP_AUTO && SCG_TC_DEFAULT && a->hidden_dim == 64 && (E == 0 || E == 32))) {
-        if (a->hidden_dim != 64) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: the tensor-core collector is available for hidden_dim 64"};
+    // library default (SCG_MLP_AUTO): tensor cores for hidden 128 (where they win by a wide margin), CUDA cores for hidden 32 / 64
+    // (measured: DESIGN.md 4); a configuration that does not fit the tensor-core kernel's shared-memory plan falls back to FFMA2
+    const bool want_tc = a->mlp_engine == SCG_MLP_TCGEN05 ||
+                         (a->mlp_engine == SCG_MLP_AUTO && (E == 0 || E == 32) && (a->hidden_dim == 128 || (SCG_TC_DEFAULT && a->hidden_dim == 64)));
+    if (want_tc) {
+        if (a->hidden_dim != 64 && a->hidden_dim != 128) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: the tensor-core collector is available for hidden_dim 64 and 128"};
         if (e.obs_dim > 32 && a->mlp_engine == SCG_MLP_TCGEN05) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: tensor-core collector: observation too wide"};
         if (e.obs_dim <= 32) {
-            RolloutLaunchResult r = launch_rollout_tc<SYS, R, 64>(e, P, s);
+            RolloutLaunchResult r = a->hidden_dim == 64 ? launch_rollout_tc<SYS, R, 64>(e, P, s) : launch_rollout_tc<SYS, R, 128>(e, P, s);
             if (r.code == SCG_OK || a->mlp_engine == SCG_MLP_TCGEN05) return r;
         }
     }

@@ -18,7 +18,20 @@
 //
 // The weights arrive in the SAME packed blob as for rollout_kernel (one TMA bulk copy); each CTA converts them once per launch.
 #pragma once
+#include <cuda_fp16.h>
+#include <type_traits>
 #include "scg_kernels.cuh"
+
+#ifdef SCG_TC_PROF
+static __device__ long long tc_ticks[16];
+#define TC_TICK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long c_ = clock64(); tc_ticks[i] += c_ - tk_; tk_ = c_; } } while (0)
+#define TC_TICK0() long long tk_ = clock64()
+#define TC_OWN(i, a, b) do { if (threadIdx.x == tc::NT - 32 && blockIdx.x == 0) tc_ticks[i] += (b) - (a); } while (0)
+#else
+#define TC_TICK(i) do { } while (0)
+#define TC_TICK0() do { } while (0)
+#define TC_OWN(i, a, b) do { } while (0)
+#endif
 
 namespace tc {
 
@@ -99,7 +112,7 @@ struct TcObsSink {
 // shared-memory plan (float offsets; every section a multiple of 4 floats = 16 bytes)
 template <int HID> struct Smem {
     int blob, small, w1, w2, h1, obs, tobs, cobs, out, xg, total_floats;
-    int OBSP, w1_floats, w2_floats, h1_floats, obs_floats, small_floats;
+    int OBSP, w1_floats, w2_floats, h1_floats, obs_floats, small_floats, slot_floats, tiles_floats;
     __host__ __device__ Smem(int obs_dim, int act_dim, int xg_floats) {
         const BlobLayout L = blob_layout(obs_dim, act_dim, HID);
         OBSP = pad8(obs_dim);
@@ -112,7 +125,7 @@ template <int HID> struct Smem {
         const int act_tiles = 4 * h1_floats + 6 * obs_floats;       // H1 {net 0,1} x {hi,lo}; obs {cur,next,terminal} x {hi,lo}
         blob = 0;
         const int region0 = L.total > act_tiles ? L.total : act_tiles;
-        h1 = 0; obs = 4 * h1_floats; tobs = obs + 4 * obs_floats;
+        h1 = 0; obs = 4 * h1_floats; tobs = obs + 4 * obs_floats; slot_floats = 2 * obs_floats; tiles_floats = act_tiles;
         small = pad4i(region0);
         w1 = small + pad4i(small_floats);
         w2 = w1 + 2 * w1_floats;
@@ -148,9 +161,10 @@ struct Ctx {
 // per-warp partial sums of the output layer are then readable with mlp_out<E, 4, A>(ctx.s_out, ...).
 template <int HID, int A>
 __device__ __noinline__ void forward(const Ctx& c /* in shared memory */, uint32_t obs_s, uint32_t obs_lo_bytes, int act, uint32_t& fwd) {
-    static_assert(HID == 64, "the tensor-core collector is instantiated for hidden 64 (hidden 128: see DESIGN.md)");
+    static_assert(HID == 64, "3xTF32 forward of the hidden-64 collector (hidden 128: forward128)");
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const uint32_t parity = fwd & 1u;
+    TC_TICK0();
     // ---- layer 1: one elected thread issues the MMAs (3 independent pass chains, K = obsp)
     if (w == 0) {
       if (l == 0) {
@@ -173,8 +187,10 @@ __device__ __noinline__ void forward(const Ctx& c /* in shared memory */, uint32
       }
       __syncwarp();       // the other lanes of the issuing warp wait here instead of competing with the elected lane for issue slots
     }
+    TC_TICK(0);
     mbar_wait_bounded(c.bar, parity);
     tc_fence_after();
+    TC_TICK(1);
     {   // ---- epilogue 1: row u = 32 (w & 3) + l of the fused tile (actor units 0..63, critic 64..127), envs [16 (w >> 2), +16)
         const int u = 32 * (w & 3) + l, h = w >> 2, net = u >> 6, unit = u & 63;
         const uint32_t ta = c.tmem + ((uint32_t)(32 * (w & 3)) << 16) + D1_COL + 16 * h;
@@ -193,9 +209,11 @@ __device__ __noinline__ void forward(const Ctx& c /* in shared memory */, uint32
             hi[i] = hv; lo[i] = x[j] - hv;
         }
     }
+    TC_TICK(2);
     fence_proxy_async();          // the activation tile was written through the generic proxy, the tensor core reads it through the async proxy
     tc_fence_before();
     __syncthreads();
+    TC_TICK(3);
     // ---- layer 2: 2 nets x 3 passes = 6 independent chains, K = 64
     if (w == 0) {
       if (l == 0) {
@@ -222,8 +240,10 @@ __device__ __noinline__ void forward(const Ctx& c /* in shared memory */, uint32
       }
       __syncwarp();
     }
+    TC_TICK(4);
     mbar_wait_bounded(c.bar + 1, parity);
     tc_fence_after();
+    TC_TICK(5);
     {   // ---- epilogue 2 (+ fused output layer): warps 0-3 actor, 4-7 critic; M = 64 accumulators live in lanes 0-15 of each TMEM
         //      quadrant (row = 16 q + lane): lane l < 16 takes envs 0..15 of unit 16 q + l, lane l + 16 envs 16..31 of the same unit
         const int net = w >> 2, q = w & 3, unit = 16 * q + (l & 15);
@@ -274,10 +294,253 @@ __device__ __noinline__ void forward(const Ctx& c /* in shared memory */, uint32
             }
         }
     }
+    TC_TICK(6);
     tc_fence_before();
     __syncthreads();
+    TC_TICK(7);
     fwd += 1;
 }
+
+// =============================================================================================
+// hidden 128 (the width of every quadrotor checkpoint the reference ships): FP16 operands with a SCALED low part.
+//   x = hi + lo' * 2^-11,  hi = fp16(x), lo' = fp16((x - hi) * 2^11)   (22 significant bits, like the TF32 hi/lo pair, and lo' stays
+//   a normal fp16 number); D = acc0 + acc1 * 2^-11 with acc0 = Whi.Hhi and acc1 = Whi.Hlo' + Wlo'.Hhi in two tensor-memory accumulators.
+//   `kind::f16` MMAs contract K = 16 per instruction -- half the instructions of the TF32 form (the tensor pipe needs ~65 cycles
+//   per tcgen05.mma at N = 32 whatever its size, tools/ubench/mlp_tc2.cu) -- and both nets' weights (2 x 128 x 128, hi and lo') fit
+//   in shared memory as 128 KB, which the TF32 copies (256 KB) would not.
+//   layer 1  D1_net[128 x 32] = W1_net[128 x OBSP16] . obs^T     layer 2  D2_net[128 x 32] = W2_net[128 x 128] . H1_net^T    (M128 N32 K16)
+// =============================================================================================
+constexpr float LO_SCALE = 2048.0f, LO_UNSCALE = 1.0f / 2048.0f;
+__host__ __device__ constexpr int pad16(int x) { return (x + 15) & ~15; }
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {     // D=F32 [4,6)=1, A=F16 [7,10)=0, B=F16 [10,13)=0, K-major both
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// half index of element (row, k) in a B tile (33 rows of 16 bytes per K-chunk of 8 halves) / in an A tile with M rows
+__device__ __forceinline__ int bh_idx(int k, int n) { return (k >> 3) * (LBO_B / 2) + n * 8 + (k & 7); }
+__device__ __forceinline__ int ah_idx(int m, int k, int M) { return ((k >> 3) * M + m) * 8 + (k & 7); }
+__host__ __device__ constexpr int bh_tile_floats(int K) { return (K / 8) * (LBO_B / 4); }     // size of one fp16 B tile in float units
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn((x - __half2float(hi)) * LO_SCALE);
+}
+
+struct Smem128 {
+    int small, w1, w2, h1, obs, tobs, cobs, out, total_floats;
+    int OBSP, w1_floats, w2_floats, h1_floats, obs_tile_floats, slot_floats, small_floats, tiles_floats;
+    __host__ __device__ Smem128(int obs_dim, int act_dim, int /*xg_floats: X_GOAL stays in global memory*/ = 0) {
+        constexpr int HID = 128;
+        OBSP = pad16(obs_dim);
+        w1_floats = 128 * OBSP / 2;                  // one fp16 copy of one net's layer-1 A tile [128 rows][OBSP]
+        w2_floats = HID * HID / 2;
+        h1_floats = bh_tile_floats(HID);
+        obs_tile_floats = bh_tile_floats(OBSP);
+        slot_floats = pad4i(obs_dim * E) + 2 * obs_tile_floats;       // plain float32 copy [k][E] + hi + lo' operand tiles
+        small_floats = pad4i(2 * HID) * 2 + pad4i((act_dim + 1) * HID) + pad4i(act_dim + 1) + pad4i(act_dim);
+        h1 = 0; obs = 4 * h1_floats; tobs = obs + 2 * slot_floats; tiles_floats = obs + 3 * slot_floats;
+        small = tiles_floats;
+        w1 = small + pad4i(small_floats);
+        w2 = w1 + 4 * w1_floats;
+        cobs = w2 + 4 * w2_floats;
+        out = cobs + 2 * obs_dim * E;
+        total_floats = out + pad4i(4 * (act_dim + 1) * E);
+    }
+};
+
+struct Sink128 {       // observation element (k, env): exact float32 copy + fp16 hi / scaled lo operands
+    float* plain; __half* hi; __half* lo; int e;
+    template <typename R> __device__ __forceinline__ void operator()(int k, R v) const {
+        const float x = (float)v;
+        plain[k * E + e] = x;
+        __half a, b; split_f16(x, a, b);
+        const int i = bh_idx(k, e);
+        hi[i] = a; lo[i] = b;
+    }
+};
+
+constexpr int D1H_COL = 0;         // + net * 64 + acc * 32
+constexpr int D2H_COL = 128;
+
+struct Ctx128 {
+    uint32_t tmem;
+    uint32_t w1_s[2][2], w2_s[2][2], h1_s[2][2];    // [net][hi/lo]
+    __half* h1_p[2][2];
+    const float* small; SmallLayout SL;
+    float* s_out;
+    uint64_t* bar;
+    int obsp, od;
+};
+
+template <int A>
+__device__ __noinline__ void forward128(const Ctx128& c /* in shared memory */, uint32_t obs_hi_s, uint32_t obs_lo_s, int act, uint32_t& fwd) {
+    constexpr int HID = 128;
+    const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+    const uint32_t parity = fwd & 1u;
+    constexpr uint32_t I = idesc_f16(128, E);
+    constexpr uint32_t LBO_A = 128 * 16;
+    TC_TICK0();
+    if (w == 0) {
+      if (l == 0) {
+        tc_fence_after();
+        const int ksteps = c.obsp >> 4;
+        const uint32_t tm = c.tmem;
+        const uint64_t dB[2] = {make_desc(obs_hi_s, LBO_B, SBO), make_desc(obs_lo_s, LBO_B, SBO)};
+#pragma unroll
+        for (int net = 0; net < 2; ++net) {
+            const uint64_t dA[2] = {make_desc(c.w1_s[net][0], LBO_A, SBO), make_desc(c.w1_s[net][1], LBO_A, SBO)};
+#pragma unroll 1
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t ka = (uint64_t)((ks * 2 * LBO_A) >> 4), kb = (uint64_t)((ks * 2 * LBO_B) >> 4);
+                mma_f16(tm + D1H_COL + net * 64, dA[0] + ka, dB[0] + kb, I, ks > 0);             // hi . hi
+                mma_f16(tm + D1H_COL + net * 64 + 32, dA[0] + ka, dB[1] + kb, I, ks > 0);        // hi . lo'
+                mma_f16(tm + D1H_COL + net * 64 + 32, dA[1] + ka, dB[0] + kb, I, 1u);            // lo' . hi
+            }
+        }
+        mma_commit(c.bar);
+      }
+      __syncwarp();
+    }
+    TC_TICK(0);
+    mbar_wait_bounded(c.bar, parity);
+    tc_fence_after();
+    TC_TICK(1);
+    const int net = w >> 2, q = w & 3, u = 32 * q + l;          // this thread's unit (a TMEM lane) of net `net`
+    {   // ---- epilogue 1: 32 envs of one unit, two halves of 16 to bound the register use
+        const float b = c.small[c.SL.b1 + net * HID + u];
+        __half* hi = c.h1_p[net][0]; __half* lo = c.h1_p[net][1];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const uint32_t ta = c.tmem + ((uint32_t)(32 * q) << 16) + D1H_COL + net * 64 + 16 * hh;
+            float x[16], y[16];
+            tmem_ld16(ta, x); tmem_ld16(ta + 32, y);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = fmaf(y[j], LO_UNSCALE, x[j]) + b;
+            act16<0>(x, act);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                __half a, bb; split_f16(x[j], a, bb);
+                const int i = bh_idx(u, 16 * hh + j);
+                hi[i] = a; lo[i] = bb;
+            }
+        }
+    }
+    TC_TICK(2);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    TC_TICK(3);
+    if (w == 0) {
+      if (l == 0) {
+        tc_fence_after();
+        const uint32_t tm = c.tmem;
+        uint64_t dA[2][2], dB[2][2];
+#pragma unroll
+        for (int n2 = 0; n2 < 2; ++n2)
+#pragma unroll
+            for (int p = 0; p < 2; ++p) { dA[n2][p] = make_desc(c.w2_s[n2][p], LBO_A, SBO); dB[n2][p] = make_desc(c.h1_s[n2][p], LBO_B, SBO); }
+#pragma unroll
+        for (int ks = 0; ks < HID / 16; ++ks) {
+            constexpr uint64_t one = 1;
+            const uint64_t ka = one * ((ks * 2 * LBO_A) >> 4), kb = one * ((ks * 2 * LBO_B) >> 4);
+#pragma unroll
+            for (int n2 = 0; n2 < 2; ++n2) {
+                mma_f16(tm + D2H_COL + n2 * 64, dA[n2][0] + ka, dB[n2][0] + kb, I, ks > 0);
+                mma_f16(tm + D2H_COL + n2 * 64 + 32, dA[n2][0] + ka, dB[n2][1] + kb, I, ks > 0);
+                mma_f16(tm + D2H_COL + n2 * 64 + 32, dA[n2][1] + ka, dB[n2][0] + kb, I, 1u);
+            }
+        }
+        mma_commit(c.bar + 1);
+      }
+      __syncwarp();
+    }
+    TC_TICK(4);
+    mbar_wait_bounded(c.bar + 1, parity);
+    tc_fence_after();
+    TC_TICK(5);
+    {   // ---- epilogue 2 + fused output layer: reduce-scatter over the 32 units of the quadrant (all five lane bits); lane l ends with env l
+        const float b = c.small[c.SL.b2 + net * HID + u];
+        float x[32];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const uint32_t ta = c.tmem + ((uint32_t)(32 * q) << 16) + D2H_COL + net * 64 + 16 * hh;
+            float a0[16], a1[16];
+            tmem_ld16(ta, a0); tmem_ld16(ta + 32, a1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a0[j] = fmaf(a1[j], LO_UNSCALE, a0[j]) + b;
+            act16<0>(a0, act);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[16 * hh + j] = a0[j];
+        }
+        const int n_out = net ? 1 : A, row0 = net ? A : 0;
+#pragma unroll
+        for (int o = 0; o < A; ++o) {
+            if (o < n_out) {
+                const float w3 = c.small[c.SL.w3 + (row0 + o) * HID + u];
+                float p16[16], p8[8], p4[4], p2[2];
+                {
+                    const bool up = (l & 16) != 0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float a0 = x[j] * w3, a1 = x[j + 16] * w3;
+                        const float r = __shfl_xor_sync(0xffffffffu, up ? a0 : a1, 16);
+                        p16[j] = (up ? a1 : a0) + r;
+                    }
+                }
+                {
+                    const bool up = (l & 8) != 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const float r = __shfl_xor_sync(0xffffffffu, up ? p16[j] : p16[j + 8], 8); p8[j] = (up ? p16[j + 8] : p16[j]) + r; }
+                }
+                {
+                    const bool up = (l & 4) != 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float r = __shfl_xor_sync(0xffffffffu, up ? p8[j] : p8[j + 4], 4); p4[j] = (up ? p8[j + 4] : p8[j]) + r; }
+                }
+                {
+                    const bool up = (l & 2) != 0;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) { const float r = __shfl_xor_sync(0xffffffffu, up ? p4[j] : p4[j + 2], 2); p2[j] = (up ? p4[j + 2] : p4[j]) + r; }
+                }
+                const bool up = (l & 1) != 0;
+                const float r = __shfl_xor_sync(0xffffffffu, up ? p2[0] : p2[1], 1);
+                c.s_out[(q * (A + 1) + row0 + o) * E + l] = (up ? p2[1] : p2[0]) + r;
+            }
+        }
+    }
+    TC_TICK(6);
+    tc_fence_before();
+    __syncthreads();
+    TC_TICK(7);
+    fwd += 1;
+}
+
+// ---- per-width dispatch used by the collector body --------------------------------------------------------------------------
+template <int HID> struct Variant;
+template <> struct Variant<64> {
+    using Plan = Smem<64>; using CtxT = Ctx;
+    static __device__ __forceinline__ TcObsSink sink(float* slot, const Plan& S, int, int e) { return TcObsSink{slot, slot + S.obs_floats, e}; }
+    static __device__ __forceinline__ float val(const float* slot, const Plan& S, int k, int en) { const int i = b_idx(k, en); return slot[i] + slot[S.obs_floats + i]; }
+    template <int A> static __device__ __forceinline__ void fwd(const CtxT& c, float* slot, const Plan& S, int act, uint32_t& f) {
+        forward<64, A>(c, smem_u32(slot), (uint32_t)S.obs_floats * 4u, act, f);
+    }
+};
+template <> struct Variant<128> {
+    using Plan = Smem128; using CtxT = Ctx128;
+    static __device__ __forceinline__ Sink128 sink(float* slot, const Plan& S, int od, int e) {
+        __half* hi = reinterpret_cast<__half*>(slot + pad4i(od * E));
+        return Sink128{slot, hi, hi + 2 * S.obs_tile_floats, e};
+    }
+    static __device__ __forceinline__ float val(const float* slot, const Plan&, int k, int en) { return slot[k * E + en]; }
+    template <int A> static __device__ __forceinline__ void fwd(const CtxT& c, float* slot, const Plan& S, int act, uint32_t& f) {
+        const uint32_t hi = smem_u32(slot) + (uint32_t)pad4i(c.od * E) * 4u;
+        forward128<A>(c, hi, hi + (uint32_t)S.obs_tile_floats * 4u, act, f);
+    }
+};
 
 }  // namespace tc
 
@@ -294,7 +557,9 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
     __shared__ __align__(8) uint64_t s_bar;          // TMA staging of the blob
     __shared__ __align__(8) uint64_t s_mbar[2];      // layer-1 / layer-2 accumulators ready
     __shared__ uint32_t s_tmem;
-    __shared__ tc::Ctx s_ctx;
+    using V = tc::Variant<HID>;
+    using XG = std::conditional_t<HID == 64, R, double>;      // X_GOAL: shared copy in the integrator's precision (hidden 64) / global table (hidden 128)
+    __shared__ typename V::CtxT s_ctx;
     __shared__ HotCfg<R> s_hot;
     __shared__ double s_z[2 * NZ * E];
     __shared__ float s_eps[2 * A * E];
@@ -309,32 +574,34 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
     __shared__ float s_rec[2 * (A + 2) * E];
     __shared__ float s_stat[6 * E];
     __shared__ int s_epc[E];
+    __shared__ NormState s_norm;
 
     const int od = T.obs_dim, N = T.N, nc = T.n_con;
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * E;
-    const tc::Smem<HID> S(od, A, T.L * NX * (int)(sizeof(R) / 4));
+    const typename V::Plan S(od, A, T.L * NX * (int)(sizeof(R) / 4));
     const BlobLayout L = blob_layout(od, A, HID);
     const tc::SmallLayout SL = tc::small_layout(A, HID);
-    float* s_blob = smem + S.blob;
     float* s_small = smem + S.small;
     float* s_cobs = smem + S.cobs;
     float* s_out = smem + S.out;
-    R* s_xg = reinterpret_cast<R*>(smem + S.xg);
-    const int OBSF = S.obs_floats;                     // floats of one copy of an observation tile
-    // observation tiles: [cur | next] ping-pong, each hi then lo; terminal tile hi then lo
+    const XG* s_xg;
+    // observation slots: [cur | next] ping-pong + terminal; a slot holds the operand tiles (hi / lo) of one observation of the 32 envs
+    const int SLOT = S.slot_floats;
     float* s_obs = smem + S.obs;
     float* s_tobs = smem + S.tobs;
 
-    // ---- stage the packed policy (TMA bulk copy), allocate tensor memory, load the hot constants
+    // ---- stage the packed policy (hidden 64: TMA bulk copy into shared memory), allocate tensor memory, load the hot constants
     if (tid == 0) { mbar_init(&s_bar, 1); mbar_init(&s_mbar[0], 1); mbar_init(&s_mbar[1], 1); fence_mbar_init(); }
     if (tid == 32) hot_load<SYS, R>(T, &s_hot);
     const HotCfg<R>* h = &s_hot;
     __syncthreads();
-    if (tid == 0) {
-        const uint32_t bytes = (uint32_t)L.total * 4u;
-        mbar_expect_tx(&s_bar, bytes);
-        tma_bulk_g2s(s_blob, P.policy, bytes, &s_bar);
+    if constexpr (HID == 64) {
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)L.total * 4u;
+            mbar_expect_tx(&s_bar, bytes);
+            tma_bulk_g2s(smem + S.blob, P.policy, bytes, &s_bar);
+        }
     }
     const int warp = tid >> 5, lane = tid & 31;
     if (warp == 1) {
@@ -350,12 +617,15 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
     if (live) env_load<SYS, R>(T, n, e);
     if (owner) { s_tsteps0[ol] = live ? e.total_steps : 0u; s_epi[ol] = live ? e.episode : 0; s_cand_ep[ol] = -1; s_cand_ep[E + ol] = -1; }
     const bool use_cand = h->n_off_draws == 0;
-    for (int i = tid; i < T.L * NX; i += NT) s_xg[i] = (R)T.x_goal[i];
     float ep_ret_sum = 0.f, ep_len_sum = 0.f, ep_cv_sum = 0.f; int ep_count = 0;
-    mbar_wait(&s_bar, 0);
-    __syncthreads();
-    // ---- convert the blob: biases / output rows / logstd as they are, W1 and W2 as hi / lo A tiles (K-major canonical layout)
-    {
+    if constexpr (HID == 64) {
+        R* xg = reinterpret_cast<R*>(smem + S.xg);
+        for (int i = tid; i < T.L * NX; i += NT) xg[i] = (R)T.x_goal[i];
+        s_xg = xg;
+        const float* s_blob = smem + S.blob;
+        mbar_wait(&s_bar, 0);
+        __syncthreads();
+        // ---- convert the blob: biases / output rows / logstd as they are, W1 and W2 as TF32 hi / lo A tiles (K-major canonical layout)
         for (int i = tid; i < 2 * HID; i += NT) { s_small[SL.b1 + i] = s_blob[L.b1 + i]; s_small[SL.b2 + i] = s_blob[L.b2 + i]; }
         for (int i = tid; i < (A + 1) * HID; i += NT) s_small[SL.w3 + i] = s_blob[L.w3 + i];
         if (tid < 4) { s_small[SL.b3 + tid] = tid < A + 1 ? s_blob[L.b3 + tid] : 0.f; s_small[SL.logstd + tid] = tid < A ? s_blob[L.logstd + tid] : 0.f; }
@@ -378,16 +648,44 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
                 w2h[j] = hv; w2l[j] = x - hv;
             }
         }
+        __syncthreads();      // the blob is dead from here on: the activation tiles alias it
+    } else {
+        // hidden 128: the packed blob (147 KB) does not fit next to its converted copy -- convert straight from global memory (L2)
+        s_xg = T.x_goal;
+        const float* __restrict__ g = P.policy;
+        for (int i = tid; i < 2 * HID; i += NT) { s_small[SL.b1 + i] = __ldg(g + L.b1 + i); s_small[SL.b2 + i] = __ldg(g + L.b2 + i); }
+        for (int i = tid; i < (A + 1) * HID; i += NT) s_small[SL.w3 + i] = __ldg(g + L.w3 + i);
+        if (tid < 4) { s_small[SL.b3 + tid] = tid < A + 1 ? __ldg(g + L.b3 + tid) : 0.f; s_small[SL.logstd + tid] = tid < A ? __ldg(g + L.logstd + tid) : 0.f; }
+        if (tid == 4 && A + 1 > 4) s_small[SL.b3 + 4] = __ldg(g + L.b3 + 4);
+        for (int net = 0; net < 2; ++net) {
+            __half* w1h = reinterpret_cast<__half*>(smem + S.w1 + net * 2 * S.w1_floats); __half* w1l = w1h + 2 * S.w1_floats;
+            for (int i = tid; i < HID * S.OBSP; i += NT) {
+                const int m = i % HID, k = i / HID;
+                const float x = k < od ? __ldg(g + L.w1t + ((k >> 1) * 2 * HID + net * HID + m) * 2 + (k & 1)) : 0.f;
+                __half a, b; tc::split_f16(x, a, b);
+                const int j = tc::ah_idx(m, k, HID);
+                w1h[j] = a; w1l[j] = b;
+            }
+            __half* w2h = reinterpret_cast<__half*>(smem + S.w2 + net * 2 * S.w2_floats); __half* w2l = w2h + 2 * S.w2_floats;
+            for (int i = tid; i < HID * HID; i += NT) {          // consecutive threads read consecutive floats of W2P [k/2][H][2]
+                const int par = i & 1, u = (i >> 1) % HID, kp = (i >> 1) / HID, k = 2 * kp + par;
+                const float x = __ldg(g + L.w2t + net * HID * HID + i);
+                __half a, b; tc::split_f16(x, a, b);
+                const int j = tc::ah_idx(u, k, HID);
+                w2h[j] = a; w2l[j] = b;
+            }
+        }
     }
-    __syncthreads();      // the blob is dead from here on: the activation tiles alias it
-    for (int i = tid; i < 4 * S.h1_floats + 6 * OBSF; i += NT) smem[S.h1 + i] = 0.f;     // zero: padded K columns and dead env rows stay 0
+    for (int i = tid; i < S.tiles_floats; i += NT) smem[S.h1 + i] = 0.f;     // zero: padded K columns and dead env rows stay 0
     __syncthreads();
+    const float* obs_src = P.obs0 ? P.obs0 : T.st.cur_obs;
     for (int i = tid; i < E * od; i += NT) {
         const int ee = i / od, k = i % od;
-        const float x = (n0 + ee < N) ? T.st.cur_obs[(size_t)(n0 + ee) * od + k] : 0.f;
-        const float hv = tc::tf32_hi(x);
-        s_obs[tc::b_idx(k, ee)] = hv; s_obs[OBSF + tc::b_idx(k, ee)] = x - hv;
+        const float x = (n0 + ee < N) ? obs_src[(size_t)(n0 + ee) * od + k] : 0.f;
+        V::sink(s_obs, S, od, ee)(k, x);
     }
+    if (P.norm) norm_load(&s_norm, P.norm, od, tid, NT);
+    const bool norm_obs = P.norm != nullptr && P.norm[2 * od + 1] != 0.0, norm_rew = P.norm != nullptr && P.norm[2 * od + 4] != 0.0;
     float sd[A], lsd[A], inv2var[A];
 #pragma unroll
     for (int k = 0; k < A; ++k) { lsd[k] = s_small[SL.logstd + k]; sd[k] = expf(lsd[k]); inv2var[k] = 1.0f / (2.f * sd[k] * sd[k]); }
@@ -409,22 +707,27 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
     __syncthreads();
     tc::tc_fence_after();
     if (tid == 0) {
-        tc::Ctx& cx_tc = s_ctx;
+        typename V::CtxT& cx_tc = s_ctx;
         cx_tc.tmem = s_tmem;
         const uint32_t w1s = smem_u32(smem + S.w1), w2s = smem_u32(smem + S.w2), h1s = smem_u32(smem + S.h1);
-        cx_tc.w1_s[0] = w1s; cx_tc.w1_s[1] = w1s + S.w1_floats * 4;
+        if constexpr (HID == 64) {
+            cx_tc.w1_s[0] = w1s; cx_tc.w1_s[1] = w1s + S.w1_floats * 4;
+        } else {
+            for (int net = 0; net < 2; ++net)
+                for (int p = 0; p < 2; ++p) cx_tc.w1_s[net][p] = w1s + (net * 2 + p) * S.w1_floats * 4;
+            cx_tc.od = od;
+        }
         for (int net = 0; net < 2; ++net)
             for (int p = 0; p < 2; ++p) {
                 cx_tc.w2_s[net][p] = w2s + (net * 2 + p) * S.w2_floats * 4;
                 cx_tc.h1_s[net][p] = h1s + (net * 2 + p) * S.h1_floats * 4;
-                cx_tc.h1_p[net][p] = smem + S.h1 + (net * 2 + p) * S.h1_floats;
+                cx_tc.h1_p[net][p] = reinterpret_cast<std::remove_reference_t<decltype(cx_tc.h1_p[0][0])>>(smem + S.h1 + (net * 2 + p) * S.h1_floats);
             }
         cx_tc.small = s_small; cx_tc.SL = SL; cx_tc.s_out = s_out; cx_tc.bar = s_mbar; cx_tc.obsp = S.OBSP;
     }
-    const tc::Ctx& cx_tc = s_ctx;     // published by the barrier below (before the first forward)
+    const typename V::CtxT& cx_tc = s_ctx;     // published by the barrier below (before the first forward)
     uint32_t fwd = 0;
-    const uint32_t obs_lo_bytes = (uint32_t)OBSF * 4u;
-    auto tile_val = [&](const float* tile, int k, int en) { const int i = tc::b_idx(k, en); return tile[i] + tile[OBSF + i]; };   // hi + lo = the float32 value, exactly
+    auto tile_val = [&](const float* slot, int k, int en) { return V::val(slot, S, k, en); };   // the float32 observation, exactly
 
     auto store_policy_record = [&](size_t tn, const float* act, float val, float logp, int done, int truncated) {
         if (A == 2) pstore(P, reinterpret_cast<float2*>(P.out.d_act + tn * A), make_float2(act[0], act[1 % A]));
@@ -459,8 +762,9 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
             for (int k = 0; k < NX; ++k) st[k] = (R)zb[k * E];
 #pragma unroll
             for (int k = 0; k < A; ++k) { ny[k] = (R)zb[(NX + k) * E]; cl[k] = (R)zb[(NX + A + k) * E]; }
-            env_reward_mse<SYS, R, R>(h, s_xg, st, ny, cl, s_cstep[bsel * E + ee], rw, ms);
-            pstore(P, P.out.d_rew + tnp, (float)rw);
+            env_reward_mse<SYS, R, XG>(h, s_xg, st, ny, cl, s_cstep[bsel * E + ee], rw, ms);
+            if (P.out.d_rew_raw) P.out.d_rew_raw[tnp] = (float)rw;
+            pstore(P, P.out.d_rew + tnp, norm_rew ? norm_rew_value(&s_norm, (float)rw) : (float)rw);
             if (P.out.d_mse) P.out.d_mse[tnp] = (float)ms;
             h_a += (float)rw; h_b += 1.f;
             if (dn) { h_cnt += 1; h_sa += h_a; h_sb += h_b; h_a = 0.f; h_b = 0.f; }
@@ -487,7 +791,7 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
 #pragma unroll
                 for (int j = 0; j < PS; ++j) cd[(SCG_MAX_INERTIAL + SCG_NINV + j) * E] = (double)tmp.ps[j];
                 NoiseSrc<R> nn; nn.row = nullptr; nn.philox = false; nn.slot = 0; nn.stream = 0; nn.idx = 0; nn.key.k0 = nn.key.k1 = nn.key.genv = 0;
-                make_obs<SYS, R, R>(T, h, s_xg, st0, n0 + ee, 0, true, nn, PlainObsSink{s_cobs + slot * OBS_TILE + ee, E});
+                make_obs<SYS, R, XG>(T, h, s_xg, st0, n0 + ee, 0, true, nn, PlainObsSink{s_cobs + slot * OBS_TILE + ee, E});
                 __threadfence_block();
                 *(volatile int*)&s_cand_ep[slot * E + ee] = ep;
             }
@@ -525,8 +829,8 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
     int cur = 0;
     for (int t = 0; t < P.T; ++t) {
         const size_t tn0 = (size_t)t * N + n0;
-        float* s_oc = s_obs + cur * 2 * OBSF;
-        float* s_on = s_obs + (cur ^ 1) * 2 * OBSF;
+        float* s_oc = s_obs + cur * SLOT;
+        float* s_on = s_obs + (cur ^ 1) * SLOT;
         float z[A];
 #pragma unroll
         for (int k = 0; k < A; ++k) z[k] = 0.f;
@@ -534,9 +838,12 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
 #pragma unroll
             for (int k = 0; k < A; ++k) z[k] = __ldg(P.eps + (tn0 + ol) * A + k);
         }
-        tc::forward<HID, A>(cx_tc, smem_u32(s_oc), obs_lo_bytes, P.activation, fwd);
+        V::template fwd<A>(cx_tc, s_oc, S, P.activation, fwd);
 
         int trunc = 0;
+#ifdef SCG_TC_PROF
+        const long long own0 = clock64();
+#endif
         if (role == 0) {
             float act[A], logp = 0.f, val = 0.f;
             if (live) {
@@ -564,16 +871,16 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
                 for (int k = 0; k < A; ++k) { zb[(NX + k) * E] = (double)cx.noisy[k]; zb[(NX + A + k) * E] = (double)cx.clipped[k]; }
                 const int step_before = e.ctrl_step;
                 const size_t tn = tn0 + ol;
-                int goal_reached = 0, oob = 0, done = env_done<SYS, R, R>(h, s_xg, state, goal_reached, oob), truncated = 0;
-                const tc::TcObsSink sink_next{s_on, s_on + OBSF, ol}, sink_term{s_tobs, s_tobs + OBSF, ol};
+                int goal_reached = 0, oob = 0, done = env_done<SYS, R, XG>(h, s_xg, state, goal_reached, oob), truncated = 0;
+                const auto sink_next = V::sink(s_on, S, od, ol), sink_term = V::sink(s_tobs, S, od, ol);
                 if (fast) {
                     const int fl = (step_before + 1 >= h->ctrl_steps) ? (done ? 1 : 3) : done;
                     s_cstep[(t & 1) * E + ol] = step_before;
                     s_flag[(t & 1) * E + ol] = fl;
                     done = fl & 1; truncated = fl >> 1;
                     e.total_steps += 1;
-                    if (fl != 1) { if (truncated) make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, sink_term);
-                                   else make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, sink_next); }
+                    if (fl != 1) { if (truncated) make_obs<SYS, R, XG>(T, h, s_xg, state, n, step_before, false, ns, sink_term);
+                                   else make_obs<SYS, R, XG>(T, h, s_xg, state, n, step_before, false, ns, sink_next); }
                     if (done) {
                         const int slot = e.episode & 1;
                         if (*(volatile int*)&s_cand_ep[slot * E + ol] == e.episode) {
@@ -596,30 +903,39 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
                             e.ctrl_step = 0; e.episode += 1;
                         } else {
                             env_reset<SYS, R>(T, h, n, e, state);
-                            make_obs<SYS, R, R>(T, h, s_xg, state, n, 0, true, ns, sink_next);
+                            make_obs<SYS, R, XG>(T, h, s_xg, state, n, 0, true, ns, sink_next);
                         }
                         *(volatile int*)&s_epi[ol] = e.episode;
                     } else e.ctrl_step += 1;
                 } else {
                     R rew, mse; int cviol = 0;
-                    env_reward_mse<SYS, R, R>(h, s_xg, state, cx.noisy, cx.clipped, step_before, rew, mse);
+                    env_reward_mse<SYS, R, XG>(h, s_xg, state, cx.noisy, cx.clipped, step_before, rew, mse);
                     if (nc > 0) cviol = env_constraints(T, h->rows, nc, h->con_fast, zb, E, nullptr, P.out.d_cvals ? P.out.d_cvals + tn * nc : nullptr);
                     e.ctrl_step += 1; e.total_steps += 1;
                     env_finalize<R>(h, e.ctrl_step, cviol, rew, done, truncated);
                     e.ep_ret += (float)rew; e.ep_len += 1.f; e.ep_cv += (float)cviol;
                     if (done) {
-                        if (truncated) make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, sink_term);
+                        if (truncated) make_obs<SYS, R, XG>(T, h, s_xg, state, n, step_before, false, ns, sink_term);
                         ep_count += 1; ep_ret_sum += e.ep_ret; ep_len_sum += e.ep_len; ep_cv_sum += e.ep_cv;
                         e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
                         env_reset<SYS, R>(T, h, n, e, state);
                         ns = reset_noise<R>(T, h, n, e.episode);
-                        make_obs<SYS, R, R>(T, h, s_xg, state, n, 0, true, ns, sink_next);
+                        make_obs<SYS, R, XG>(T, h, s_xg, state, n, 0, true, ns, sink_next);
                     } else {
-                        make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, sink_next);
+                        make_obs<SYS, R, XG>(T, h, s_xg, state, n, step_before, false, ns, sink_next);
                     }
-                    pstore(P, P.out.d_rew + tn, (float)rew);
+                    if (P.out.d_rew_raw) P.out.d_rew_raw[tn] = (float)rew;
+                    pstore(P, P.out.d_rew + tn, norm_rew ? norm_rew_value(&s_norm, (float)rew) : (float)rew);
                     if (P.out.d_cviol) P.out.d_cviol[tn] = (float)cviol;
                     if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
+                }
+                if (norm_obs || P.out.d_obs_raw) {       // the observation env.step returned: raw copy for the statistics update, normalised in place
+                    float* raw = P.out.d_obs_raw ? P.out.d_obs_raw + tn * od : nullptr;
+                    for (int k = 0; k < od; ++k) {
+                        const float x = tile_val(s_on, k, ol);
+                        if (raw) raw[k] = x;
+                        if (norm_obs) sink_next(k, norm_obs_value(&s_norm, k, x));
+                    }
                 }
                 trunc = truncated;
                 if (relay) {
@@ -641,21 +957,29 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
             write_obs_record(t, s_oc, tid, NIDLE);
             if (gen_eps && t + 1 < P.T) make_eps(t + 1);
         }
+#ifdef SCG_TC_PROF
+        const long long own1 = clock64();
+        TC_OWN(8, own0, own1);
+#endif
         const int any_trunc = __syncthreads_or(trunc);
+#ifdef SCG_TC_PROF
+        TC_OWN(9, own1, clock64());
+        if (threadIdx.x == 0 && blockIdx.x == 0) tc_ticks[10] += clock64() - own0;     // whole env phase seen by warp 0
+#endif
         if (any_trunc) {
-            tc::forward<HID, A>(cx_tc, smem_u32(s_tobs), obs_lo_bytes, P.activation, fwd);
+            V::template fwd<A>(cx_tc, s_tobs, S, P.activation, fwd);
             if (live && trunc) pstore(P, P.out.d_terminal_v + tn0 + ol, mlp_out<E, NW, A>(s_out, s_small, BlobLayout{0, 0, 0, 0, 0, SL.b3, 0, 0}, A, ol));
             __syncthreads();
         }
         cur ^= 1;
     }
-    float* s_ol = s_obs + cur * 2 * OBSF;
+    float* s_ol = s_obs + cur * SLOT;
     if (fast && hl && role != 3) {
         process_record(P.T - 1);
         if (role == 2) { s_stat[ee] = h_a; s_stat[E + ee] = h_b; s_stat[3 * E + ee] = h_sa; s_stat[4 * E + ee] = h_sb; s_epc[ee] = h_cnt; }
         else { s_stat[2 * E + ee] = h_a; s_stat[5 * E + ee] = h_sa; }
     }
-    tc::forward<HID, A>(cx_tc, smem_u32(s_ol), obs_lo_bytes, P.activation, fwd);
+    V::template fwd<A>(cx_tc, s_ol, S, P.activation, fwd);
     if (live) {
         if (fast) {
             e.ep_ret = s_stat[ol]; e.ep_len = s_stat[E + ol]; e.ep_cv = s_stat[2 * E + ol];

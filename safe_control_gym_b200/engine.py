@@ -155,7 +155,7 @@ class EngineHandle:
 
     def rollout(self, policy_blob, dims, T, eps=None, activation='tanh', gamma=0.99, gae_lambda=0.95, use_gae=False,
                 deterministic=False, envs_per_block=0, want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode'), out=None,
-                flat=None, peer_byte_offsets=None, multicast_byte_offset=None, mlp_engine=None):
+                flat=None, peer_byte_offsets=None, multicast_byte_offset=None, mlp_engine=None, norm=None, obs0=None):
         '''One fused launch: T steps of policy + env for all N envs.  Returns PPOBuffer-shaped torch.cuda tensors.
 
         flat: optional caller-owned float32 buffer for the PPOBuffer keys (e.g. this rank's slot of a peer-mapped gathered buffer);
@@ -189,6 +189,9 @@ class EngineHandle:
             if 'last' in want:
                 out['last_obs'] = torch.empty(N, obs_dim, dtype=f32, device=dev)
                 out['last_val'] = torch.empty(N, 1, dtype=f32, device=dev)
+            if 'raw' in want:          # un-normalised observation / reward streams for the controller's running normalisers
+                out['obs_raw'] = torch.empty(T, N, obs_dim, dtype=f32, device=dev)
+                out['rew_raw'] = torch.empty(T, N, 1, dtype=f32, device=dev)
             if 'episode' in want:
                 out['ep_return_sum'] = torch.empty(N, dtype=f32, device=dev)
                 out['ep_length_sum'] = torch.empty(N, dtype=f32, device=dev)
@@ -196,7 +199,7 @@ class EngineHandle:
                 out['ep_count'] = torch.empty(N, dtype=torch.int32, device=dev)
         ro = _abi.scg_rollout_out()
         for name in ('obs', 'act', 'rew', 'mask', 'v', 'logp', 'terminal_v', 'ret', 'adv', 'cviol', 'cvals', 'mse', 'last_obs', 'last_val',
-                     'ep_return_sum', 'ep_length_sum', 'ep_cviol_sum', 'ep_count'):
+                     'ep_return_sum', 'ep_length_sum', 'ep_cviol_sum', 'ep_count', 'obs_raw', 'rew_raw'):
             setattr(ro, 'd_' + name, out[name].data_ptr() if name in out else None)
         args = _abi.scg_rollout_args()
         args.T, args.obs_dim, args.act_dim, args.hidden_dim = int(T), int(obs_dim), int(act_dim), int(hid)
@@ -210,6 +213,14 @@ class EngineHandle:
             assert eps.dtype == torch.float32 and eps.is_cuda and tuple(eps.shape) == (T, N, act_dim), (eps.dtype, eps.shape)
             eps = eps.contiguous()
         args.d_eps = eps.data_ptr() if eps is not None else None
+        if norm is not None:
+            assert norm.dtype == torch.float64 and norm.is_cuda and norm.numel() == 2 * obs_dim + 5, (norm.dtype, norm.shape)
+            norm = norm.contiguous()
+        args.d_norm = norm.data_ptr() if norm is not None else None
+        if obs0 is not None:
+            assert obs0.dtype == torch.float32 and obs0.is_cuda and tuple(obs0.shape) == (N, obs_dim), (obs0.dtype, obs0.shape)
+            obs0 = obs0.contiguous()
+        args.d_obs0 = obs0.data_ptr() if obs0 is not None else None
         offs = list(peer_byte_offsets) if peer_byte_offsets is not None else out.get('_peer_byte_offsets', [])
         if len(offs) > _abi.SCG_MAX_PEERS:
             raise ValueError(f'at most {_abi.SCG_MAX_PEERS} peers')
@@ -278,15 +289,42 @@ def pack_policy_host(ac_or_params, dims, blob_out):
     return blob_out
 
 
+def bind_to_gpu_numa_node(device_index):
+    '''Pins the calling process to the CPUs of the NUMA node its GPU hangs off (sysfs), so that pinned host buffers allocated afterwards
+    are node-local (first touch) and the D2H DMA of the rollout record does not cross the socket interconnect.  One process per GPU
+    (torchrun) otherwise floats over both sockets and eight concurrent record copies collapse (SCALE_r01: 8-GPU e2e below 4-GPU).
+    Returns the node index, or None when the topology cannot be read (nothing is changed then).'''
+    try:
+        pci = torch.cuda.get_device_properties(device_index)
+        bus_id = f'{pci.pci_domain_id:04x}:{pci.pci_bus_id:02x}:{pci.pci_device_id:02x}.0'
+        with open(f'/sys/bus/pci/devices/{bus_id}/numa_node') as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:   # noqa: BLE001 -- best effort: containers often hide sysfs
+        return None
+
+
 class HostCollector:
     '''The fused collector for HOST-side consumers (the reference keeps policy parameters and the PPOBuffer in host memory,
     ppo_utils.py:241-355): `submit(params)` packs the parameters on the host, copies the blob to the GPU, launches the fused rollout and
     queues the device->host copy of the whole PPOBuffer record into pinned memory; `fetch()` returns the oldest record as numpy-backed
     views.  `depth` records are in flight: the D2H copy of rollout k runs on a copy stream underneath rollout k+1.'''
 
-    def __init__(self, eng, dims, T, depth=2, **rollout_kw):
+    def __init__(self, eng, dims, T, depth=2, numa_bind=True, **rollout_kw):
         self.eng, self.dims, self.T, self.depth, self.kw = eng, dims, int(T), int(depth), rollout_kw
         dev = eng.device
+        self.numa_node = bind_to_gpu_numa_node(eng.device_index) if numa_bind else None
         nblob = _abi.lib().scg_policy_blob_floats(*dims)
         self.blob_host = [torch.zeros(nblob, dtype=torch.float32).pin_memory() for _ in range(depth)]
         self.blob_dev = [torch.zeros(nblob, dtype=torch.float32, device=dev) for _ in range(depth)]

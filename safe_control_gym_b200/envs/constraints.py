@@ -1,7 +1,7 @@
 '''Constraint specifications for the CUDA engine.
 
 Host-side mirror of safe_control_gym/envs/constraints.py: the same YAML `constraint_form`s and class
-names, but a constraint here is a *description* -- rows of `g(z) = a.z - b <= 0` over z = [state; input]
+names, but a constraint here is a *description* -- rows of `g(z) = a.z - b <= 0` (or `|a.z| - b`, or the quadratic form `z'Qz - b`) over z = [state; input]
 -- that is uploaded once (scg_set_constraints) and evaluated every step inside the kernels with the
 reference's numerics: A, b cast to float32 (constraints.py:267-268), values rounded to 8 decimals
 (constraints.py:109), violated when `g > 0` (`>=` if strict, constraints.py:126-129), input constraints
@@ -193,7 +193,8 @@ class SymmetricStateConstraint(BoundedConstraint):
 
 
 class QuadraticConstraint(Constraint):
-    '''x' P x <= b (constraints.py:181-231): accepted for API parity, not evaluable by the engine.'''
+    '''x' P x <= b (constraints.py:181-231).  Engine view: ONE row of kind SCG_CON_QUAD over z = [state; input] whose non-zeros are the
+    entries of Q = F' P F, each carrying its pair of z indices.'''
 
     def __init__(self, env, P, b, constrained_variable, strict=False, active_dims=None, tolerance=None, decimals=8):
         super().__init__(env, constrained_variable, strict=strict, active_dims=active_dims, tolerance=tolerance, decimals=decimals)
@@ -206,7 +207,12 @@ class QuadraticConstraint(Constraint):
         self.check_tolerance_shape()
 
     def rows(self):
-        raise NotImplementedError('quadratic_constraint is not supported by the CUDA engine (linear / bounded / default / abs_bound are)')
+        Q = self.constraint_filter.T @ np.asarray(self.P, dtype=np.float64) @ self.constraint_filter
+        off = self._z_offset()
+        cols = {}
+        for i, j in zip(*np.nonzero(Q)):
+            cols[int(off + i) | (int(off + j) << 8)] = float(Q[i, j])
+        return [(_abi.SCG_CON_QUAD, bool(self.strict), cols, float(self.b))]
 
 
 class ConstraintList:

@@ -106,7 +106,7 @@ def _termination_margin(cfg, x_goal, state, cvals_row):
     return min(m) if m else np.inf
 
 
-def compare_rollouts(o, g, cfg, x_goal, N, T, obs_tol, max_fork_frac=0.02, keys_extra=(), early=None):
+def compare_rollouts(o, g, cfg, x_goal, N, T, obs_tol, max_fork_frac=0.02, keys_extra=(), early=None, horizon_check=True):
     '''o: oracle record (numpy, produced with trace=True), g: engine record (torch or numpy).  Every key is compared per env up
     to the first `mask` mismatch.  A mismatch ("fork") is only accepted with a PROOF that it is a float tie at a termination
     threshold: at the fork step the oracle's env.state must lie within the already observed oracle-vs-kernel trajectory
@@ -144,7 +144,12 @@ def compare_rollouts(o, g, cfg, x_goal, N, T, obs_tol, max_fork_frac=0.02, keys_
         d = np.abs(a - b) / (1.0 + np.abs(b))
         d = d.reshape(T, N, -1).max(-1)
         worst[k] = float(d[valid].max()) if valid.any() else 0.0
-        assert worst[k] <= tol, (k, worst[k], np.unravel_index(np.argmax(np.where(valid, d, 0)), d.shape))
+        if horizon_check:
+            # over the whole horizon the closed loop amplifies the float32 policy's rounding differences: all but a handful of the T x N
+            # samples must be inside `tol`, and even the worst chaotic env inside 10 x tol
+            n_out = int((d[valid] > tol).sum())
+            worst[k + '_over_tol'] = n_out
+            assert n_out <= max(2, int(2e-5 * valid.sum())) and worst[k] <= 10 * tol, (k, worst[k], n_out, np.unravel_index(np.argmax(np.where(valid, d, 0)), d.shape))
         if early is not None and k in ('obs', 'act', 'rew', 'mse') + tuple(keys_extra):
             ve = valid[:early[0]]
             worst[k + '_early'] = float(d[:early[0]][ve].max())
@@ -162,6 +167,8 @@ def compare_rollouts(o, g, cfg, x_goal, N, T, obs_tol, max_fork_frac=0.02, keys_
         assert cv_tie.sum() <= max(1, int(max_fork_frac * N)), f'{cv_tie.sum()} envs with constraint-violation ties'
         worst['cviol_ties'] = int(cv_tie.sum())
     full = first_bad == T
+    if not horizon_check:
+        return proofs, worst
     for k in ('ret', 'adv'):
         if k in g and k in o:
             np.testing.assert_allclose(tonp(g[k])[:, full], o[k][:, full], rtol=2e-4, atol=2e-4, err_msg=k)
@@ -173,3 +180,56 @@ def compare_rollouts(o, g, cfg, x_goal, N, T, obs_tol, max_fork_frac=0.02, keys_
     if 'last_obs' in g:
         np.testing.assert_allclose(tonp(g['last_obs'])[full], o['last_obs'][full], rtol=obs_tol * 10, atol=obs_tol * 10)
     return proofs, worst
+
+
+def compare_replay(oracle, policy, g, N, T, tol=2e-5, gamma=0.99, gae_lambda=0.95, use_gae=True, max_tie_frac=0.002):
+    '''TEACHER-FORCED parity: `oracle` (a fresh, reset Oracle of the same configuration) replays the engine's record `g` -- before every
+    step its env state is overwritten with the record's observation and it is stepped with the record's action -- and every output
+    of every one of the T x N transitions is compared with the oracle's one-step answer: sampled action (mean + sd * Philox normal),
+    value, log-probability, next observation, reward, mse, constraint values and flags, done flag, and the GAE columns.  Unlike a
+    trajectory comparison this bound does not grow with the horizon (no closed-loop amplification of the float32 policy's rounding
+    differences), so it is tight at the full benchmark size.  done / constraint-violation mismatches need a tie proof.'''
+    tonp = lambda t: t.detach().cpu().numpy() if hasattr(t, 'detach') else np.asarray(t)
+    rec = {k: tonp(g[k]) for k in ('obs', 'act', 'mask')}
+    p = oracle.rollout(policy, T, eps=None, gamma=gamma, gae_lambda=gae_lambda, use_gae=use_gae, replay=rec)
+    cfg, nx = oracle.cfg, oracle.nx
+    worst = {}
+
+    def rel(a, b):
+        return np.abs(a - b) / (1.0 + np.abs(b))
+    for k, t_ in (('act', 3e-5), ('v', 1e-5), ('logp', 1e-4), ('rew', tol), ('mse', tol), ('cvals', tol)):
+        if k in g and k in p:
+            d = rel(tonp(g[k]), p[k])
+            worst[k] = float(d.max())
+            assert worst[k] <= t_, (k, worst[k], np.unravel_index(np.argmax(d), d.shape))
+    gm, pm = rec['mask'][..., 0], p['mask'][..., 0]
+    # next observation: record obs[t + 1] against the prediction, wherever the record did not reset
+    cont = gm[:-1] == 1
+    d = rel(rec['obs'][1:], p['next_obs'][:-1]).max(-1)
+    worst['next_obs'] = float(d[cont].max())
+    assert worst['next_obs'] <= tol, ('next_obs', worst['next_obs'], np.unravel_index(np.argmax(np.where(cont, d, 0)), d.shape))
+    # done flags: a mismatch is only accepted as a tie at a termination threshold (the predicted state sits on it)
+    ties = 0
+    for t, i in zip(*np.nonzero(gm != pm)):
+        cv = p['cvals'][t, i] if 'cvals' in p else None
+        margin = _termination_margin(cfg, oracle.x_goal, p['next_obs'][t, i, :nx].astype(np.float64), cv)
+        assert margin <= 20 * tol, f'done flag of env {i} differs at step {t}; the predicted state is {margin:.3e} away from the nearest threshold'
+        ties += 1
+    if 'cviol' in g:
+        for t, i in zip(*np.nonzero(tonp(g['cviol'])[..., 0] != p['cviol'][..., 0])):
+            margin = float(np.abs(p['cvals'][t, i]).min())
+            assert margin <= 20 * tol, f'cviol of env {i} differs at step {t}; nearest constraint value {margin:.3e}'
+            ties += 1
+    assert ties <= max(2, int(max_tie_frac * N * T / 50)), f'{ties} threshold ties'
+    worst['ties'] = ties
+    # terminal values (critic on the terminal observation of truncated envs) where both sides agree on done
+    same = gm == pm
+    d = rel(tonp(g['terminal_v'])[..., 0], p['terminal_v'][..., 0])
+    worst['terminal_v'] = float(d[same].max())
+    assert worst['terminal_v'] <= 5e-5, ('terminal_v', worst['terminal_v'])
+    if 'ret' in g and ties == 0:
+        for k in ('ret', 'adv'):
+            d = rel(tonp(g[k]), p[k])
+            worst[k] = float(d.max())
+            assert worst[k] <= 2e-4, (k, worst[k])
+    return worst

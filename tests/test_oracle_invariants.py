@@ -149,3 +149,25 @@ def test_3d_integrator_converges_to_the_reference_symbolic_model():
         errs.append(np.abs(out['state'][0] - ref).max())
     ratios = np.asarray(errs[:-1]) / np.asarray(errs[1:])
     assert errs[-1] < 2e-3 and np.all(ratios > 1.7) and np.all(ratios < 2.3), (errs, ratios)     # O(dt)
+
+
+def test_quadratic_constraint_rows_match_numpy():
+    '''QuadraticConstraint (constraints.py:181-231): the oracle's CSR evaluation of z'Qz - b against the reference formula
+    np.round(x.T @ F.T @ P @ F @ x - b, 8) evaluated with numpy on the oracle's own states.'''
+    rng = np.random.default_rng(0)
+    P6 = rng.normal(size=(6, 6)); P6 = P6 @ P6.T
+    P4 = np.eye(4) + 0.2
+    cons = [dict(constraint_form='quadratic_constraint', constrained_variable='state', P=P6.tolist(), b=3.0),
+            dict(constraint_form='quadratic_constraint', constrained_variable='input_and_state', active_dims=[0, 2, 6, 7], P=P4.tolist(), b=2.0)]
+    env = H.make_env('quadrotor_2D_track', constraints=cons)
+    N = 16
+    o = H.make_oracle(env, N, auto_reset=False)
+    o.set_episode_table(H.episode_table(env, N, K=2, seed=1))
+    o.reset()
+    for t in range(20):
+        act = rng.uniform(-1, 1, size=(N, 2))
+        s = o.step(act)
+        x = s['state']
+        g0 = np.round(np.einsum('ni,ij,nj->n', x, P6, x) - 3.0, 8)
+        np.testing.assert_allclose(s['cvals'][:, 0], g0, rtol=0, atol=2e-8)
+        assert ((s['cvals'] > 0).any(1) == (s['cviol'] > 0)).all()
