@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <string>
 
 #include "scg.h"
@@ -152,7 +153,31 @@ __device__ __forceinline__ void dense_forward(const float* __restrict__ W, int w
     }
 }
 
+// train-layout index -> offset in the CTA's padded shared-memory parameter copy (-1: layout padding, nothing to store)
 template <int HID, int MS>
+__device__ __forceinline__ int train_to_smem(int p, const TrainLayout& L, const PpoSmem<HID, MS>& S, int obs, int A) {
+    constexpr int W2S = HID + 4;
+    const int net = p >= L.critic0;
+    const int base = net * S.net_floats;
+    const int w1 = net ? L.c_w1 : L.a_w1, b1 = net ? L.c_b1 : L.a_b1, w2 = net ? L.c_w2 : L.a_w2, b2 = net ? L.c_b2 : L.a_b2;
+    const int w3 = net ? L.c_w3 : L.a_w3, b3 = net ? L.c_b3 : L.a_b3, nout = net ? 1 : A;
+    if (p >= w1 && p < w1 + HID * obs) { const int i = p - w1; return base + S.o_w1 + (i / obs) * S.w1s + (i % obs); }
+    if (p >= b1 && p < b1 + HID) return base + S.o_b1 + (p - b1);
+    if (p >= w2 && p < w2 + HID * HID) { const int i = p - w2; return base + S.o_w2 + (i / HID) * W2S + (i % HID); }
+    if (p >= b2 && p < b2 + HID) return base + S.o_b2 + (p - b2);
+    if (p >= w3 && p < w3 + nout * HID) return base + S.o_w3 + (p - w3);
+    if (p >= b3 && p < b3 + nout) return base + S.o_b3 + (p - b3);
+    if (!net && p >= L.a_ls && p < L.a_ls + A) return S.o_ls + (p - L.a_ls);
+    return -1;
+}
+
+// CLUSTER = false: one cooperative grid, partial gradients through global memory, two grid barriers per minibatch (large minibatches).
+// CLUSTER = true : ONE thread-block cluster works on the minibatch (ppo.yaml's default minibatch of 64 = 8 CTAs x 8 samples): partial
+//                  gradients stay in shared memory, every CTA reduces its slice of the parameter vector over the cluster through
+//                  distributed shared memory, keeps that slice's Adam moments and master weights in REGISTERS for the whole launch and
+//                  stores the updated weights straight into every CTA's shared-memory copy -- no global round trip, no parameter
+//                  reload, two cluster barriers per minibatch instead of two grid barriers + ~5 L2 round trips.
+template <int HID, int MS, bool CLUSTER>
 __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
     constexpr int MSP = MS + 4;
     constexpr int W2S = HID + 4;
@@ -171,8 +196,10 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
     const PpoSmem<HID, MS> S(P.obs);
     const TrainLayout L = train_layout(P.obs, P.act, HID);
     cg::grid_group grid = cg::this_grid();
+    cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, net = tid / PPO_NETT, t = tid % PPO_NETT;
-    const int G = gridDim.x, cta = blockIdx.x;
+    const int G = gridDim.x, cta = blockIdx.x;            // CLUSTER: the grid is exactly one cluster
+    float* gbuf = smem + S.total;                          // CLUSTER: this CTA's partial gradient (train layout) + loss sums, read by the peers
     const int obs = P.obs, A = P.act, act = P.activation, mb = P.mb;
     const int nout = net == 0 ? A : 1;
     const int n_chunks = (mb + MS - 1) / MS;
@@ -231,6 +258,19 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
     __syncthreads();
     load_params();
 
+    // CLUSTER: this CTA owns parameters [p0, p1); thread tid owns p0 + tid + 256 j.  Master weights and Adam moments live in registers.
+    constexpr int NPT = 8;                                 // >= ceil(ceil(total / cluster size) / 256) for every supported shape (checked on the host)
+    float own_x[NPT], own_m[NPT], own_v[NPT]; int own_off[NPT];
+    const int c_per = (((L.total + G - 1) / G) + 3) & ~3;
+    const int c_p0 = cta * c_per, c_p1 = min(L.total, c_p0 + c_per);
+    if constexpr (CLUSTER) {
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            const int p = c_p0 + tid + PPO_NT * j;
+            own_x[j] = own_m[j] = own_v[j] = 0.f; own_off[j] = -1;
+            if (p < c_p1) { own_x[j] = __ldcg(P.params + p); own_m[j] = __ldcg(P.m + p); own_v[j] = __ldcg(P.v + p); own_off[j] = train_to_smem<HID, MS>(p, L, S, obs, A); }
+        }
+    }
     long long step_a = P.steps[0], step_c = P.steps[1];   // optimizer step counts: every CTA tracks them identically
     // thread 0: beta1 ** step, beta2 ** step of the actor / critic optimizers, advanced by one multiplication per step
     double bpow[4] = {1.0, 1.0, 1.0, 1.0};
@@ -478,7 +518,7 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
 
             // ---- publish this CTA's partial gradient (train layout) and loss sums
             {
-                float* w = P.ws + (size_t)cta * P.ws_pitch;
+                float* w = CLUSTER ? gbuf : P.ws + (size_t)cta * P.ws_pitch;
 #pragma unroll
                 for (int j = 0; j < UT2; ++j)
 #pragma unroll
@@ -494,8 +534,8 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                     __stcg(w + L.total + 0, st_pl); __stcg(w + L.total + 1, st_vl); __stcg(w + L.total + 2, st_kl);
                 }
             }
-            __threadfence();
-            if (G > 1) grid.sync(); else __syncthreads();
+            if constexpr (CLUSTER) cluster.sync();
+            else { __threadfence(); if (G > 1) grid.sync(); else __syncthreads(); }
 
             // ---- reduce over CTAs (fixed order) + KL gate + Adam on this CTA's slice
             {
@@ -504,8 +544,13 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                     float pl = 0.f, vl = 0.f, kl = 0.f;
                     const int Gu = n_chunks < G ? n_chunks : G;       // CTAs that had work
                     for (int c2 = tid; c2 < Gu; c2 += 32) {
-                        const float* w = P.ws + (size_t)c2 * P.ws_pitch + L.total;
-                        pl += __ldcg(w + 0); vl += __ldcg(w + 1); kl += __ldcg(w + 2);
+                        if constexpr (CLUSTER) {
+                            const float* w = cluster.map_shared_rank(gbuf, c2) + L.total;
+                            pl += w[0]; vl += w[1]; kl += w[2];
+                        } else {
+                            const float* w = P.ws + (size_t)c2 * P.ws_pitch + L.total;
+                            pl += __ldcg(w + 0); vl += __ldcg(w + 1); kl += __ldcg(w + 2);
+                        }
                     }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {                // fixed tree: identical in every CTA
@@ -532,11 +577,48 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                 __syncthreads();
                 const bool apply_actor = s_gate[0] != 0.0;
                 const int Gu = n_chunks < G ? n_chunks : G;
-                const int per = (((L.total + G - 1) / G) + 3) & ~3;
-                const int p0 = cta * per, p1 = min(L.total, p0 + per);
                 const float b2f = (float)P.beta2, w1f = (float)(1.0 - P.beta1), w2f = (float)(1.0 - P.beta2);
                 const float epsf = (float)P.eps;
                 const bool want_grad = P.grad_out && ep == P.epochs - 1 && mi == P.n_mb - 1;
+                auto adam = [&](float& mm, float& vv, float& xx, float gg, float step_size, float bc2s) {
+                    mm = fmaf(w1f, gg - mm, mm);                           // exp_avg.lerp_(grad, 1 - beta1)
+                    vv = fmaf(w2f * gg, gg, b2f * vv);                     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+                    const float denom = sqrtf(vv) / bc2s + epsf;
+                    xx = xx - step_size * (mm / denom);                    // param.addcdiv_(exp_avg, denom, value=-step_size)
+                };
+                if constexpr (CLUSTER) {
+                    const float* peer[8];
+#pragma unroll
+                    for (int c2 = 0; c2 < 8; ++c2) peer[c2] = cluster.map_shared_rank(gbuf, c2 < G ? c2 : 0);
+                    float g[NPT];
+#pragma unroll
+                    for (int j = 0; j < NPT; ++j) {                        // all the remote loads first (latency overlaps), fixed summation order
+                        const int p = c_p0 + tid + PPO_NT * j;
+                        float acc = 0.f;
+                        if (p < c_p1) {
+#pragma unroll
+                            for (int c2 = 0; c2 < 8; ++c2) if (c2 < Gu) acc += peer[c2][p];
+                        }
+                        g[j] = acc;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NPT; ++j) {
+                        const int p = c_p0 + tid + PPO_NT * j;
+                        if (p >= c_p1) continue;
+                        float gg = g[j];
+                        if (p >= L.a_ls && p < L.a_ls + A) gg += -(float)P.ent_coef;      // d(entropy_coef * entropy_loss)/d logstd
+                        if (want_grad) P.grad_out[p] = gg;
+                        const bool actor = p < L.critic0;
+                        if (actor && !apply_actor) continue;
+                        adam(own_m[j], own_v[j], own_x[j], gg, (float)(actor ? s_gate[1] : s_gate[3]), (float)(actor ? s_gate[2] : s_gate[4]));
+                        if (own_off[j] >= 0) {
+#pragma unroll
+                            for (int c2 = 0; c2 < 8; ++c2) if (c2 < G) cluster.map_shared_rank(smem, c2)[own_off[j]] = own_x[j];
+                        }
+                    }
+                } else {
+                const int per = (((L.total + G - 1) / G) + 3) & ~3;
+                const int p0 = cta * per, p1 = min(L.total, p0 + per);
                 const float4* __restrict__ ws4 = reinterpret_cast<const float4*>(P.ws);
                 float4* __restrict__ m4p = reinterpret_cast<float4*>(P.m);
                 float4* __restrict__ v4p = reinterpret_cast<float4*>(P.v);
@@ -559,21 +641,23 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                     if (want_grad) reinterpret_cast<float4*>(P.grad_out)[q] = g;
                     if (actor && !apply_actor) continue;
                     const float step_size = (float)(actor ? s_gate[1] : s_gate[3]), bc2s = (float)(actor ? s_gate[2] : s_gate[4]);
-                    auto adam = [&](float& mm, float& vv, float& xx, float gg) {
-                        mm = fmaf(w1f, gg - mm, mm);                           // exp_avg.lerp_(grad, 1 - beta1)
-                        vv = fmaf(w2f * gg, gg, b2f * vv);                     // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-                        const float denom = sqrtf(vv) / bc2s + epsf;
-                        xx = xx - step_size * (mm / denom);                    // param.addcdiv_(exp_avg, denom, value=-step_size)
-                    };
-                    adam(m.x, v.x, x.x, g.x); adam(m.y, v.y, x.y, g.y); adam(m.z, v.z, x.z, g.z); adam(m.w, v.w, x.w, g.w);
+                    adam(m.x, v.x, x.x, g.x, step_size, bc2s); adam(m.y, v.y, x.y, g.y, step_size, bc2s);
+                    adam(m.z, v.z, x.z, g.z, step_size, bc2s); adam(m.w, v.w, x.w, g.w, step_size, bc2s);
                     __stcg(m4p + q, m); __stcg(v4p + q, v); __stcg(x4p + q, x);
+                }
                 }
                 step_a += apply_actor ? 1 : 0;
                 step_c += 1;
             }
-            __threadfence();
-            if (G > 1) grid.sync(); else __syncthreads();
-            load_params();
+            if constexpr (CLUSTER) cluster.sync();          // every CTA's shared-memory weights are up to date (remote stores), gbuf may be overwritten
+            else { __threadfence(); if (G > 1) grid.sync(); else __syncthreads(); load_params(); }
+        }
+    }
+    if constexpr (CLUSTER) {                                // the slice owners write weights and moments back once per launch
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            const int p = c_p0 + tid + PPO_NT * j;
+            if (p < c_p1) { P.params[p] = own_x[j]; P.m[p] = own_m[j]; P.v[p] = own_v[j]; }
         }
     }
     if (cta == 0 && tid == 0) {
@@ -623,11 +707,35 @@ template <int HID, int MS>
 int ppo_launch(const scg_ppo_args* a, PpoParams& P, int G, cudaStream_t st) {
     const PpoSmem<HID, MS> S(a->obs_dim);
     const size_t smem = sizeof(float) * S.total;
-    cudaError_t e = cudaFuncSetAttribute(ppo_update_kernel<HID, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppo_update_kernel<HID, MS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return ppo_fail(SCG_ECUDA, std::string("scg_ppo_update: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     void* kargs[] = {(void*)&P};
-    e = cudaLaunchCooperativeKernel((void*)ppo_update_kernel<HID, MS>, dim3(G), dim3(PPO_NT), kargs, smem, st);
+    e = cudaLaunchCooperativeKernel((void*)ppo_update_kernel<HID, MS, false>, dim3(G), dim3(PPO_NT), kargs, smem, st);
     if (e != cudaSuccess) return ppo_fail(SCG_ECUDA, std::string("scg_ppo_update: launch: ") + cudaGetErrorString(e));
+    return SCG_OK;
+}
+
+// small minibatches: ONE thread-block cluster of C CTAs (C = 1, 2, 4 or 8), MS samples per CTA and chunk
+constexpr int PPO_CLUSTER_MAX_MB = 256;
+template <int HID, int MS>
+int ppo_launch_cluster(const scg_ppo_args* a, PpoParams& P, cudaStream_t st) {
+    const PpoSmem<HID, MS> S(a->obs_dim);
+    const TrainLayout L = train_layout(a->obs_dim, a->act_dim, HID);
+    const int chunks = (a->mini_batch_size + MS - 1) / MS;
+    int C = 1; while (C < 8 && C < chunks) C *= 2;
+    if ((((L.total + C - 1) / C) + 3) / 4 * 4 > 8 * PPO_NT) C = 8;       // the slice of a CTA must fit NPT registers per thread
+    const size_t smem = sizeof(float) * ((size_t)S.total + L.total + PPO_NSTAT);
+    auto kern = ppo_update_kernel<HID, MS, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return ppo_fail(SCG_ECUDA, std::string("scg_ppo_update: cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(C); cfg.blockDim = dim3(PPO_NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, P);
+    if (e != cudaSuccess) return ppo_fail(SCG_ECUDA, std::string("scg_ppo_update: cluster launch: ") + cudaGetErrorString(e));
     return SCG_OK;
 }
 
@@ -696,6 +804,10 @@ int scg_ppo_update(const scg_ppo_args* a, void* stream) {
     P.params = a->d_params; P.m = a->d_exp_avg; P.v = a->d_exp_avg_sq; P.steps = (long long*)a->d_adam_steps;
     P.stats = a->d_stats; P.ws = a->d_workspace; P.ws_pitch = L.total + PPO_NSTAT; P.grad_out = a->d_grad_out;
     cudaStream_t st = (cudaStream_t)stream;
+    if (a->mini_batch_size <= PPO_CLUSTER_MAX_MB && !getenv("SCG_PPO_NO_CLUSTER")) {
+        if (a->hidden_dim == 64) return ppo_launch_cluster<64, 8>(a, P, st);
+        return ppo_launch_cluster<32, 16>(a, P, st);
+    }
     if (a->hidden_dim == 64) return ppo_launch<64, 64>(a, P, G, st);
     return ppo_launch<32, 64>(a, P, G, st);
 }

@@ -111,7 +111,7 @@ def test_hidden_128_collector(name, N, engine):
     '''hidden 128 = the width of every quadrotor checkpoint the reference ships (tensor cores: fp16 hi + scaled lo operands).'''
     T = 200
     o, oo, eng, gg = _run_pair(name, N, T, 128, 'f64', policy_seed=3, engine=engine)
-    _check(o, oo, eng, gg, N, T, 'f64', pol=_run_pair.last[0], fresh=_run_pair.last[1])
+    _check(o, oo, eng, gg, N, T, 'f64', stable=not name.startswith('cartpole'), pol=_run_pair.last[0], fresh=_run_pair.last[1])
 
 
 def test_sharded_ranks_reproduce_slices_of_the_single_batch():
