@@ -224,7 +224,9 @@ typedef struct scg_step_out {
 /* policy-MLP engines of the fused collector */
 #define SCG_MLP_AUTO 0         /* library default */
 #define SCG_MLP_FFMA2 1        /* CUDA cores: register-tiled FP32 GEMMs with packed FFMA2 */
-#define SCG_MLP_TCGEN05 2      /* 5th-gen tensor cores: tcgen05.mma kind::tf32, 3xTF32 hi/lo split, FP32 accumulators in tensor memory */
+#define SCG_MLP_TCGEN05 2      /* 5th-gen tensor cores: tcgen05.mma kind::f16 on fp16 hi + scaled-lo operands (22 significant bits), FP32 accumulators in
+                                * tensor memory; hidden 128: two M128 tiles per layer, hidden 64: actor + critic fused into one width-128 net */
+#define SCG_MLP_TCGEN05_TF32 3 /* hidden 64 only: tcgen05.mma kind::tf32, 3xTF32 hi/lo split (twice the MMAs of the fp16 form; kept for comparison) */
 
 /* Output buffers of the fused rollout, PPOBuffer scheme (ppo_utils.py:266-295): [T][N][.] float32. */
 #define SCG_MAX_PEERS 8

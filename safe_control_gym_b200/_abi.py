@@ -31,8 +31,8 @@ SCG_MODE_ACTION, SCG_MODE_DYNAMICS, SCG_MODE_OBSERVATION = 0, 1, 2
 SCG_RAND_NONE, SCG_RAND_UNIFORM, SCG_RAND_NORMAL = 0, 1, 2
 SCG_ACT_TANH, SCG_ACT_RELU, SCG_ACT_LEAKY_RELU = 0, 1, 2
 SCG_CON_LINEAR, SCG_CON_ABS, SCG_CON_QUAD = 0, 1, 2
-SCG_MLP_AUTO, SCG_MLP_FFMA2, SCG_MLP_TCGEN05 = 0, 1, 2
-MLP_ENGINES = {'auto': SCG_MLP_AUTO, 'ffma2': SCG_MLP_FFMA2, 'tcgen05': SCG_MLP_TCGEN05}
+SCG_MLP_AUTO, SCG_MLP_FFMA2, SCG_MLP_TCGEN05, SCG_MLP_TCGEN05_TF32 = 0, 1, 2, 3
+MLP_ENGINES = {'auto': SCG_MLP_AUTO, 'ffma2': SCG_MLP_FFMA2, 'tcgen05': SCG_MLP_TCGEN05, 'tcgen05_tf32': SCG_MLP_TCGEN05_TF32}
 
 ACTIVATIONS = {'tanh': SCG_ACT_TANH, 'relu': SCG_ACT_RELU, 'leaky_relu': SCG_ACT_LEAKY_RELU}
 

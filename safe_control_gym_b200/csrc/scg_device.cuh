@@ -690,12 +690,14 @@ static __device__ __noinline__ double rand_draw(int kind, double a, double b, ui
 // Disturbance step offsets are NOT drawn here (see env_reset).  Draw slot j = words 2(j&1), 2(j&1)+1 of Philox block j>>1.
 // out[j * stride], j < SCG_MAX_INERTIAL: inertial properties; out[(init_row + i) * stride], i < NX: the initial state.
 // One compact out-of-line copy.
+// `staged_row`: the table row of (n, k) already staged in shared memory (TMA bulk copy issued by the caller), or nullptr.
 template <int SYS, typename R>
-__device__ __noinline__ void reset_draw(const DevTables& T, const HotCfg<R>* h, int n, int k, double* out, int stride, int init_row) {
+__device__ __noinline__ void reset_draw(const DevTables& T, const HotCfg<R>* h, int n, int k, double* out, int stride, int init_row,
+                                        const double* staged_row = nullptr) {
     constexpr int NX = SysDims<SYS>::NX;
     const bool philox = h->philox != 0;
     const uint32_t genv = h->genv0 + (uint32_t)n;
-    const double* row = (!philox && T.ep_table) ? T.ep_table + ((size_t)(k % T.K) * T.N + n) * T.P : nullptr;
+    const double* row = staged_row ? staged_row : (!philox && T.ep_table) ? T.ep_table + ((size_t)(k % T.K) * T.N + n) * T.P : nullptr;
     const int slot0 = h->n_off_draws;
     const int n_inertial = (SYS == SCG_SYS_CARTPOLE) ? 3 : 4;
     uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0; int have = -1;   // Philox block currently held

@@ -529,6 +529,10 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     __shared__ float s_stat[6 * E];            // FAST: episode statistics kept by the record helpers, handed back at the end
     __shared__ int s_epc[E];
     __shared__ NormState s_norm;
+    // table mode: per-env rows of the [K][N][P] episode table, staged by TMA bulk copies (one mbarrier per env and candidate slot)
+    constexpr int PROW = SCG_MAX_INERTIAL + NX;
+    __shared__ __align__(16) double s_row[SPLIT ? 2 * E * PROW : 2];
+    __shared__ __align__(8) uint64_t s_rowbar[SPLIT ? 2 * E : 1];
 
     const int od = T.obs_dim, N = T.N, nc = T.n_con;
     const int tid = threadIdx.x;
@@ -544,7 +548,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     R* s_xg = reinterpret_cast<R*>(smem + S.xg);      // X_GOAL [L][nx] in the integrator's precision
 
     // ---- stage the packed policy into shared memory with one TMA bulk copy
-    if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&s_bar, 1); if (SPLIT) for (int i = 0; i < 2 * E; ++i) mbar_init(&s_rowbar[i], 1); fence_mbar_init(); }
     if (tid == 32) hot_load<SYS, R>(T, &s_hot);
     const HotCfg<R>* h = &s_hot;
     __syncthreads();
@@ -641,14 +645,31 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
         }
     };
     // keep the next two episodes of env ee ready (a pure function of (env, episode)); runs while the owners sample and integrate
+    // table mode: the env's row of episode `ep` is fetched with a TMA bulk copy (cp.async.bulk + mbarrier) into s_row[slot][ee]; both
+    // candidate slots are issued before the first wait, so the second copy overlaps the first candidate's arithmetic
+    const bool tma_rows = SPLIT && !h->philox && T.ep_table != nullptr && T.P == PROW && (T.P & 1) == 0;
+    uint32_t row_phase = 0;                    // bit `slot`: parity of that slot's mbarrier (helper lanes only)
     auto prepare_candidates = [&]() {
         const int want = *(volatile int*)&s_epi[ee];
+        bool need[2];
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            const int ep = want + d, slot = ep & 1;
+            need[d] = *(volatile int*)&s_cand_ep[slot * E + ee] != ep;
+            if (need[d] && tma_rows) {
+                const uint32_t bytes = (uint32_t)PROW * 8u;
+                mbar_expect_tx(&s_rowbar[slot * E + ee], bytes);
+                tma_bulk_g2s(s_row + (slot * E + ee) * PROW, T.ep_table + ((size_t)(ep % T.K) * T.N + n0 + ee) * T.P, bytes, &s_rowbar[slot * E + ee]);
+            }
+        }
 #pragma unroll 1
         for (int d = 0; d < 2; ++d) {
             const int ep = want + d, slot = ep & 1;
-            if (*(volatile int*)&s_cand_ep[slot * E + ee] != ep) {
+            if (need[d]) {
                 double* cd = s_cand + slot * NC * E + ee;
-                reset_draw<SYS, R>(T, h, n0 + ee, ep, cd, E, SCG_MAX_INERTIAL + SCG_NINV);   // inertial at rows 0..3, initial state after the reciprocals
+                const double* staged = nullptr;
+                if (tma_rows) { mbar_wait(&s_rowbar[slot * E + ee], (row_phase >> slot) & 1u); row_phase ^= 1u << slot; staged = s_row + (slot * E + ee) * PROW; }
+                reset_draw<SYS, R>(T, h, n0 + ee, ep, cd, E, SCG_MAX_INERTIAL + SCG_NINV, staged);   // inertial at rows 0..3, initial state after the reciprocals
                 EnvRegs<SYS, R> tmp; R initr[NX], st0[NX];
 #pragma unroll
                 for (int j = 0; j < SCG_MAX_INERTIAL; ++j) tmp.inertial[j] = (R)cd[j * E];

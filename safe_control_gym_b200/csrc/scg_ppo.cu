@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 
@@ -25,6 +26,13 @@
 #include "scg_kernels.cuh"
 
 namespace cg = cooperative_groups;
+
+// -DSCG_PPO_PROF: per-phase cycle accounting of CTA 0 / thread 0 (printed by the kernel at its end)
+#ifdef SCG_PPO_PROF
+#define PP_T(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long c_ = clock64(); pp_acc[i] += c_ - pp_last; pp_last = c_; } } while (0)
+#else
+#define PP_T(i) do { } while (0)
+#endif
 
 void scg_internal_set_error(const std::string& msg);   // scg_api.cu (message returned by scg_last_error(NULL))
 
@@ -34,6 +42,7 @@ constexpr int PPO_NT = 256;     // threads per CTA: 128 per network
 constexpr int PPO_NETT = 128;
 constexpr int PPO_MAXA = 4;     // act_dim <= 4 on this path
 constexpr int PPO_NSTAT = 8;
+constexpr int PPO_CLUSTER_NPT = 6;   // parameters per thread a CTA of the cluster kernel owns (registers: weight, two Adam moments, smem offset)
 
 struct TrainLayout {
     int a_w1, a_b1, a_w2, a_b2, a_w3, a_b3, a_ls;
@@ -255,11 +264,12 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
     };
     // one-time zero fill of the padding the staging loop never touches (W1 columns >= obs, W2 pad columns, W3 rows >= n_out)
     for (int i = tid; i < 2 * S.net_floats; i += PPO_NT) smem[i] = 0.0f;
+    if constexpr (CLUSTER) for (int i = tid; i < L.total + PPO_NSTAT; i += PPO_NT) gbuf[i] = 0.0f;     // layout padding is never published: keep it 0
     __syncthreads();
     load_params();
 
     // CLUSTER: this CTA owns parameters [p0, p1); thread tid owns p0 + tid + 256 j.  Master weights and Adam moments live in registers.
-    constexpr int NPT = 8;                                 // >= ceil(ceil(total / cluster size) / 256) for every supported shape (checked on the host)
+    constexpr int NPT = PPO_CLUSTER_NPT;                   // >= ceil(ceil(total / cluster size) / 256): checked on the host, which falls back to the grid kernel otherwise
     float own_x[NPT], own_m[NPT], own_v[NPT]; int own_off[NPT];
     const int c_per = (((L.total + G - 1) / G) + 3) & ~3;
     const int c_p0 = cta * c_per, c_p1 = min(L.total, c_p0 + c_per);
@@ -271,6 +281,10 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
             if (p < c_p1) { own_x[j] = __ldcg(P.params + p); own_m[j] = __ldcg(P.m + p); own_v[j] = __ldcg(P.v + p); own_off[j] = train_to_smem<HID, MS>(p, L, S, obs, A); }
         }
     }
+#ifdef SCG_PPO_PROF
+    long long pp_acc[16]; for (int i = 0; i < 16; ++i) pp_acc[i] = 0;
+    long long pp_last = clock64();
+#endif
     long long step_a = P.steps[0], step_c = P.steps[1];   // optimizer step counts: every CTA tracks them identically
     // thread 0: beta1 ** step, beta2 ** step of the actor / critic optimizers, advanced by one multiplication per step
     double bpow[4] = {1.0, 1.0, 1.0, 1.0};
@@ -306,6 +320,7 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                     sIdx[i] = r >= 0 ? (int)(r % P.block_rows) : 0;
                 }
                 __syncthreads();
+                PP_T(0);
                 for (int i = tid; i < MS * S.obsp; i += PPO_NT) {
                     const int s = i / S.obsp, k = i % S.obsp, r = sRow[s];
                     float v = 0.f;
@@ -321,6 +336,7 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                     sSc[q * MSP + s] = r >= 0 ? __ldg(P.key[2 + q] + r * P.block_stride[2 + q] + sIdx[s]) : 0.f;
                 }
                 __syncthreads();
+                PP_T(1);
                 // ---- forward (neural_networks.py:49-54)
                 dense_forward<HID, MS, UT, TUN>(sp + S.o_w1, S.w1s, sp + S.o_b1, sX, S.obsp, sH1, tu, ts, act);
                 __syncthreads();
@@ -335,6 +351,7 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                     sD[o * MSP + s] = a;
                 }
                 __syncthreads();
+                PP_T(2);
                 // ---- losses and d(loss)/d(network outputs)
                 float r_pl = 0.f, r_kl = 0.f, r_vl = 0.f, r_ls[PPO_MAXA] = {0.f, 0.f, 0.f, 0.f};
                 if (t < MS) {
@@ -403,6 +420,7 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                         for (int d = 0; d < PPO_MAXA; ++d) gls[d] += sRed[w * 8 + 4 + d];
                     }
                 }
+                PP_T(3);
                 // ---- backward, layer 3: dW3[o][k] += sum_s dout[o][s] h2[k][s]; db3[o] += sum_s dout[o][s]
 #pragma unroll
                 for (int i = 0; i < NW3; ++i) {
@@ -444,6 +462,7 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                     }
                 }
                 __syncthreads();
+                PP_T(4);
                 // ---- dW2[u][k] += sum_s dz2[u][s] h1[k][s]   (u = tu2 + TUN2*j, k = tk + TKN*i)
 #pragma unroll 2
                 for (int s = 0; s < MS; s += 4) {
@@ -468,6 +487,7 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                     gb2 += a;
                 }
                 __syncthreads();
+                PP_T(5);
                 // ---- dz1 = (W2^T dz2) * act'(h1), in place over h1   (k = UT*tu + j contiguous, 4 samples)
                 {
                     float acc[UT][4];
@@ -492,6 +512,7 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                     }
                 }
                 __syncthreads();
+                PP_T(6);
                 // ---- dW1[u][k] += sum_s dz1[u][s] x[k][s]; db1
 #pragma unroll
                 for (int i = 0; i < NW1; ++i) {
@@ -514,28 +535,32 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                     gb1 += a;
                 }
                 __syncthreads();
+                PP_T(7);
             }   // chunks
 
             // ---- publish this CTA's partial gradient (train layout) and loss sums
             {
                 float* w = CLUSTER ? gbuf : P.ws + (size_t)cta * P.ws_pitch;
+                auto put = [](float* dst, float val) { if constexpr (CLUSTER) *dst = val; else __stcg(dst, val); };   // shared vs global (L2) destination
 #pragma unroll
                 for (int j = 0; j < UT2; ++j)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) __stcg(w + g_w2 + (tu2 + TUN2 * j) * HID + (tk + TKN * i), gW2[j][i]);
+                    for (int i = 0; i < 4; ++i) put(w + g_w2 + (tu2 + TUN2 * j) * HID + (tk + TKN * i), gW2[j][i]);
 #pragma unroll
-                for (int i = 0; i < NW1; ++i) { const int idx = t + PPO_NETT * i; if (idx < HID * obs) __stcg(w + g_w1 + idx, gW1[i]); }
+                for (int i = 0; i < NW1; ++i) { const int idx = t + PPO_NETT * i; if (idx < HID * obs) put(w + g_w1 + idx, gW1[i]); }
 #pragma unroll
-                for (int i = 0; i < NW3; ++i) { const int idx = t + PPO_NETT * i; if (idx < nout * HID) __stcg(w + g_w3 + idx, gW3[i]); }
-                if (t < HID) { __stcg(w + g_b1 + t, gb1); __stcg(w + g_b2 + t, gb2); }
-                if (t < nout) __stcg(w + g_b3 + t, gb3);
+                for (int i = 0; i < NW3; ++i) { const int idx = t + PPO_NETT * i; if (idx < nout * HID) put(w + g_w3 + idx, gW3[i]); }
+                if (t < HID) { put(w + g_b1 + t, gb1); put(w + g_b2 + t, gb2); }
+                if (t < nout) put(w + g_b3 + t, gb3);
                 if (tid == 0) {
-                    for (int d = 0; d < A; ++d) __stcg(w + L.a_ls + d, gls[d]);
-                    __stcg(w + L.total + 0, st_pl); __stcg(w + L.total + 1, st_vl); __stcg(w + L.total + 2, st_kl);
+                    for (int d = 0; d < A; ++d) put(w + L.a_ls + d, gls[d]);
+                    put(w + L.total + 0, st_pl); put(w + L.total + 1, st_vl); put(w + L.total + 2, st_kl);
                 }
             }
+            PP_T(8);
             if constexpr (CLUSTER) cluster.sync();
             else { __threadfence(); if (G > 1) grid.sync(); else __syncthreads(); }
+            PP_T(9);
 
             // ---- reduce over CTAs (fixed order) + KL gate + Adam on this CTA's slice
             {
@@ -587,9 +612,6 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                     xx = xx - step_size * (mm / denom);                    // param.addcdiv_(exp_avg, denom, value=-step_size)
                 };
                 if constexpr (CLUSTER) {
-                    const float* peer[8];
-#pragma unroll
-                    for (int c2 = 0; c2 < 8; ++c2) peer[c2] = cluster.map_shared_rank(gbuf, c2 < G ? c2 : 0);
                     float g[NPT];
 #pragma unroll
                     for (int j = 0; j < NPT; ++j) {                        // all the remote loads first (latency overlaps), fixed summation order
@@ -597,7 +619,7 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                         float acc = 0.f;
                         if (p < c_p1) {
 #pragma unroll
-                            for (int c2 = 0; c2 < 8; ++c2) if (c2 < Gu) acc += peer[c2][p];
+                            for (int c2 = 0; c2 < 8; ++c2) if (c2 < Gu) acc += cluster.map_shared_rank(gbuf, c2)[p];
                         }
                         g[j] = acc;
                     }
@@ -649,8 +671,10 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                 step_a += apply_actor ? 1 : 0;
                 step_c += 1;
             }
+            PP_T(10);
             if constexpr (CLUSTER) cluster.sync();          // every CTA's shared-memory weights are up to date (remote stores), gbuf may be overwritten
             else { __threadfence(); if (G > 1) grid.sync(); else __syncthreads(); load_params(); }
+            PP_T(11);
         }
     }
     if constexpr (CLUSTER) {                                // the slice owners write weights and moments back once per launch
@@ -660,6 +684,13 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
             if (p < c_p1) { P.params[p] = own_x[j]; P.m[p] = own_m[j]; P.v[p] = own_v[j]; }
         }
     }
+#ifdef SCG_PPO_PROF
+    if (cta == 0 && tid == 0) {
+        const double n = (double)P.epochs * P.n_mb;
+        printf("[SCG_PPO_PROF] cycles / minibatch (MS=%d cluster=%d G=%d): idx=%.0f gather=%.0f fwd=%.0f loss=%.0f dW3+dz2=%.0f dW2=%.0f dz1=%.0f dW1=%.0f publish=%.0f sync1=%.0f reduce+adam=%.0f sync2(+reload)=%.0f\n",
+               MS, (int)CLUSTER, G, pp_acc[0] / n, pp_acc[1] / n, pp_acc[2] / n, pp_acc[3] / n, pp_acc[4] / n, pp_acc[5] / n, pp_acc[6] / n, pp_acc[7] / n, pp_acc[8] / n, pp_acc[9] / n, pp_acc[10] / n, pp_acc[11] / n);
+    }
+#endif
     if (cta == 0 && tid == 0) {
         P.steps[0] = step_a; P.steps[1] = step_c;
         for (int i = 0; i < 6; ++i) P.stats[i] += stat[i];
@@ -723,7 +754,8 @@ int ppo_launch_cluster(const scg_ppo_args* a, PpoParams& P, cudaStream_t st) {
     const TrainLayout L = train_layout(a->obs_dim, a->act_dim, HID);
     const int chunks = (a->mini_batch_size + MS - 1) / MS;
     int C = 1; while (C < 8 && C < chunks) C *= 2;
-    if ((((L.total + C - 1) / C) + 3) / 4 * 4 > 8 * PPO_NT) C = 8;       // the slice of a CTA must fit NPT registers per thread
+    if ((((L.total + C - 1) / C) + 3) / 4 * 4 > PPO_CLUSTER_NPT * PPO_NT) C = 8;       // the slice of a CTA must fit NPT registers per thread
+    if ((((L.total + C - 1) / C) + 3) / 4 * 4 > PPO_CLUSTER_NPT * PPO_NT) return -100;  // does not fit: the caller uses the grid kernel
     const size_t smem = sizeof(float) * ((size_t)S.total + L.total + PPO_NSTAT);
     auto kern = ppo_update_kernel<HID, MS, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -805,8 +837,8 @@ int scg_ppo_update(const scg_ppo_args* a, void* stream) {
     P.stats = a->d_stats; P.ws = a->d_workspace; P.ws_pitch = L.total + PPO_NSTAT; P.grad_out = a->d_grad_out;
     cudaStream_t st = (cudaStream_t)stream;
     if (a->mini_batch_size <= PPO_CLUSTER_MAX_MB && !getenv("SCG_PPO_NO_CLUSTER")) {
-        if (a->hidden_dim == 64) return ppo_launch_cluster<64, 8>(a, P, st);
-        return ppo_launch_cluster<32, 16>(a, P, st);
+        const int rc2 = a->hidden_dim == 64 ? ppo_launch_cluster<64, 8>(a, P, st) : ppo_launch_cluster<32, 16>(a, P, st);
+        if (rc2 != -100) return rc2;
     }
     if (a->hidden_dim == 64) return ppo_launch<64, 64>(a, P, G, st);
     return ppo_launch<32, 64>(a, P, G, st);

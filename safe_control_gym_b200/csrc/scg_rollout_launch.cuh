@@ -3,6 +3,7 @@
 // (system, precision) lets nvcc build them in parallel (build.py: --threads).  scg_api.cu only sees the entry points below.
 #pragma once
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "scg_kernels.cuh"
 
@@ -110,14 +111,18 @@ static RolloutLaunchResult dispatch_rollout(const RolloutLaunch& e, const scg_ro
     // mlp_engine: 0 = library default, 1 = CUDA cores (FFMA2), 2 = tensor cores (tcgen05, 3xTF32; hidden 64, 32 envs per CTA)
     // library default (SCG_MLP_AUTO): tensor cores for hidden 128 (where they win by a wide margin), CUDA cores for hidden 32 / 64
     // (measured: DESIGN.md 4); a configuration that does not fit the tensor-core kernel's shared-memory plan falls back to FFMA2
-    const bool want_tc = a->mlp_engine == SCG_MLP_TCGEN05 ||
+    const bool force_tc = a->mlp_engine == SCG_MLP_TCGEN05 || a->mlp_engine == SCG_MLP_TCGEN05_TF32;
+    const bool want_tc = force_tc ||
                          (a->mlp_engine == SCG_MLP_AUTO && (E == 0 || E == 32) && (a->hidden_dim == 128 || (SCG_TC_DEFAULT && a->hidden_dim == 64)));
     if (want_tc) {
         if (a->hidden_dim != 64 && a->hidden_dim != 128) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: the tensor-core collector is available for hidden_dim 64 and 128"};
-        if (e.obs_dim > 32 && a->mlp_engine == SCG_MLP_TCGEN05) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: tensor-core collector: observation too wide"};
+        if (e.obs_dim > 32 && force_tc) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: tensor-core collector: observation too wide"};
         if (e.obs_dim <= 32) {
-            RolloutLaunchResult r = a->hidden_dim == 64 ? launch_rollout_tc<SYS, R, 64>(e, P, s) : launch_rollout_tc<SYS, R, 128>(e, P, s);
-            if (r.code == SCG_OK || a->mlp_engine == SCG_MLP_TCGEN05) return r;
+            // hidden 64: fp16 fused-net form (half the MMAs of 3xTF32); SCG_MLP_TCGEN05_TF32 selects the TF32 form
+            const bool tf32_64 = a->mlp_engine == SCG_MLP_TCGEN05_TF32;
+            RolloutLaunchResult r = a->hidden_dim == 128 ? launch_rollout_tc<SYS, R, 128>(e, P, s)
+                                    : tf32_64 ? launch_rollout_tc<SYS, R, 64>(e, P, s) : launch_rollout_tc<SYS, R, tc::HID64F>(e, P, s);
+            if (r.code == SCG_OK || force_tc) return r;
         }
     }
 #endif

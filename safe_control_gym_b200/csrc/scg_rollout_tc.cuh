@@ -374,8 +374,11 @@ struct Ctx128 {
     int obsp, od;
 };
 
-template <int A>
-__device__ __noinline__ void forward128(const Ctx128& c /* in shared memory */, uint32_t obs_hi_s, uint32_t obs_lo_s, int act, uint32_t& fwd) {
+// NETS = 2: hidden 128, actor and critic are two M128 tiles.  NETS = 1: hidden 64, actor and critic FUSED into one width-128 net --
+// layer 1 [W1_actor; W1_critic] (they share the observation), layer 2 the block-diagonal diag(W2_actor, W2_critic) over the stacked
+// hidden vector (same number of MMAs as two M64 tiles, half the MMAs of the TF32 form); rows 0..63 actor units, 64..127 critic units.
+template <int A, int NETS>
+__device__ __noinline__ void forward_f16(const Ctx128& c /* in shared memory */, uint32_t obs_hi_s, uint32_t obs_lo_s, int act, uint32_t& fwd) {
     constexpr int HID = 128;
     const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
     const uint32_t parity = fwd & 1u;
@@ -389,7 +392,7 @@ __device__ __noinline__ void forward128(const Ctx128& c /* in shared memory */, 
         const uint32_t tm = c.tmem;
         const uint64_t dB[2] = {make_desc(obs_hi_s, LBO_B, SBO), make_desc(obs_lo_s, LBO_B, SBO)};
 #pragma unroll
-        for (int net = 0; net < 2; ++net) {
+        for (int net = 0; net < NETS; ++net) {
             const uint64_t dA[2] = {make_desc(c.w1_s[net][0], LBO_A, SBO), make_desc(c.w1_s[net][1], LBO_A, SBO)};
 #pragma unroll 1
             for (int ks = 0; ks < ksteps; ++ks) {
@@ -407,13 +410,17 @@ __device__ __noinline__ void forward128(const Ctx128& c /* in shared memory */, 
     mbar_wait_bounded(c.bar, parity);
     tc_fence_after();
     TC_TICK(1);
-    const int net = w >> 2, q = w & 3, u = 32 * q + l;          // this thread's unit (a TMEM lane) of net `net`
-    {   // ---- epilogue 1: 32 envs of one unit, two halves of 16 to bound the register use
+    // NETS = 2: warp w serves net w >> 2, all 32 envs of its unit.  NETS = 1: both warps of a quadrant serve the fused net, 16 envs each.
+    const int net = NETS == 2 ? (w >> 2) : 0, q = w & 3, u = 32 * q + l;          // this thread's unit (a TMEM lane)
+    constexpr int NH = NETS == 2 ? 2 : 1;                                           // halves of 16 envs per thread
+    const int h0 = NETS == 2 ? 0 : (w >> 2);
+    {   // ---- epilogue 1
         const float b = c.small[c.SL.b1 + net * HID + u];
         __half* hi = c.h1_p[net][0]; __half* lo = c.h1_p[net][1];
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const uint32_t ta = c.tmem + ((uint32_t)(32 * q) << 16) + D1H_COL + net * 64 + 16 * hh;
+        for (int hh = 0; hh < NH; ++hh) {
+            const int eh = h0 + hh;
+            const uint32_t ta = c.tmem + ((uint32_t)(32 * q) << 16) + D1H_COL + net * 64 + 16 * eh;
             float x[16], y[16];
             tmem_ld16(ta, x); tmem_ld16(ta + 32, y);
             tmem_ld_wait();
@@ -423,7 +430,7 @@ __device__ __noinline__ void forward128(const Ctx128& c /* in shared memory */, 
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 __half a, bb; split_f16(x[j], a, bb);
-                const int i = bh_idx(u, 16 * hh + j);
+                const int i = bh_idx(u, 16 * eh + j);
                 hi[i] = a; lo[i] = bb;
             }
         }
@@ -439,7 +446,7 @@ __device__ __noinline__ void forward128(const Ctx128& c /* in shared memory */, 
         const uint32_t tm = c.tmem;
         uint64_t dA[2][2], dB[2][2];
 #pragma unroll
-        for (int n2 = 0; n2 < 2; ++n2)
+        for (int n2 = 0; n2 < NETS; ++n2)
 #pragma unroll
             for (int p = 0; p < 2; ++p) { dA[n2][p] = make_desc(c.w2_s[n2][p], LBO_A, SBO); dB[n2][p] = make_desc(c.h1_s[n2][p], LBO_B, SBO); }
 #pragma unroll
@@ -447,7 +454,7 @@ __device__ __noinline__ void forward128(const Ctx128& c /* in shared memory */, 
             constexpr uint64_t one = 1;
             const uint64_t ka = one * ((ks * 2 * LBO_A) >> 4), kb = one * ((ks * 2 * LBO_B) >> 4);
 #pragma unroll
-            for (int n2 = 0; n2 < 2; ++n2) {
+            for (int n2 = 0; n2 < NETS; ++n2) {
                 mma_f16(tm + D2H_COL + n2 * 64, dA[n2][0] + ka, dB[n2][0] + kb, I, ks > 0);
                 mma_f16(tm + D2H_COL + n2 * 64 + 32, dA[n2][0] + ka, dB[n2][1] + kb, I, ks > 0);
                 mma_f16(tm + D2H_COL + n2 * 64 + 32, dA[n2][1] + ka, dB[n2][0] + kb, I, 1u);
@@ -461,7 +468,7 @@ __device__ __noinline__ void forward128(const Ctx128& c /* in shared memory */, 
     mbar_wait_bounded(c.bar + 1, parity);
     tc_fence_after();
     TC_TICK(5);
-    {   // ---- epilogue 2 + fused output layer: reduce-scatter over the 32 units of the quadrant (all five lane bits); lane l ends with env l
+    if constexpr (NETS == 2) {   // ---- epilogue 2 + fused output layer: reduce-scatter over the 32 units of the quadrant (all five lane bits); lane l ends with env l
         const float b = c.small[c.SL.b2 + net * HID + u];
         float x[32];
 #pragma unroll
@@ -511,6 +518,47 @@ __device__ __noinline__ void forward128(const Ctx128& c /* in shared memory */, 
                 c.s_out[(q * (A + 1) + row0 + o) * E + l] = (up ? p2[1] : p2[0]) + r;
             }
         }
+    } else {   // ---- fused width-128 net (hidden 64): quadrants 0, 1 hold actor units, 2, 3 critic units; 16 envs per thread
+        constexpr int H = 64;
+        const int eh = w >> 2, cr = q >> 1, unit = u & 63;             // env half, critic?, unit inside its net
+        const uint32_t ta = c.tmem + ((uint32_t)(32 * q) << 16) + D2H_COL + 16 * eh;
+        float x[16], a1[16];
+        tmem_ld16(ta, x); tmem_ld16(ta + 32, a1);
+        tmem_ld_wait();
+        const float b = c.small[c.SL.b2 + u];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = fmaf(a1[j], LO_UNSCALE, x[j]) + b;
+        act16<0>(x, act);
+        // the quadrant's nets' output rows; every quadrant also writes zeros for the other net's outputs (mlp_out sums all four)
+#pragma unroll
+        for (int o = 0; o < A + 1; ++o) {
+            const bool mine = (o == A) == (cr != 0);                   // warp-uniform
+            float res = 0.f;
+            if (mine) {
+                const float w3 = c.small[c.SL.w3 + o * H + unit];
+                float p8[8], p4[4], p2[2];
+                {
+                    const bool up = (l & 16) != 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const float r = __shfl_xor_sync(0xffffffffu, (up ? x[j] : x[j + 8]) * w3, 16); p8[j] = (up ? x[j + 8] : x[j]) * w3 + r; }
+                }
+                {
+                    const bool up = (l & 8) != 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float r = __shfl_xor_sync(0xffffffffu, up ? p8[j] : p8[j + 4], 8); p4[j] = (up ? p8[j + 4] : p8[j]) + r; }
+                }
+                {
+                    const bool up = (l & 4) != 0;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) { const float r = __shfl_xor_sync(0xffffffffu, up ? p4[j] : p4[j + 2], 4); p2[j] = (up ? p4[j + 2] : p4[j]) + r; }
+                }
+                const bool up = (l & 2) != 0;
+                const float r = __shfl_xor_sync(0xffffffffu, up ? p2[0] : p2[1], 2);
+                res = (up ? p2[1] : p2[0]) + r;
+                res += __shfl_xor_sync(0xffffffffu, res, 1);           // lanes 2e, 2e + 1 hold the two halves of env e's sum
+            }
+            if ((l & 1) == 0) c.s_out[(q * (A + 1) + o) * E + 16 * eh + (l >> 1)] = res;
+        }
     }
     TC_TICK(6);
     tc_fence_before();
@@ -529,6 +577,40 @@ template <> struct Variant<64> {
         forward<64, A>(c, smem_u32(slot), (uint32_t)S.obs_floats * 4u, act, f);
     }
 };
+constexpr int HID64F = 1064;       // variant tag: hidden 64 as ONE fused width-128 net with fp16 operands (forward_f16<A, 1>)
+struct Smem64F {
+    int small, w1, w2, h1, obs, tobs, cobs, out, xg, total_floats;
+    int OBSP, w1_floats, w2_floats, h1_floats, obs_tile_floats, slot_floats, small_floats, tiles_floats;
+    __host__ __device__ Smem64F(int obs_dim, int act_dim, int xg_floats) {
+        OBSP = pad16(obs_dim);
+        w1_floats = 128 * OBSP / 2;                  // one fp16 copy of the fused layer-1 A tile [128 rows][OBSP]
+        w2_floats = 128 * 128 / 2;                   // one fp16 copy of diag(W2_actor, W2_critic)
+        h1_floats = bh_tile_floats(128);
+        obs_tile_floats = bh_tile_floats(OBSP);
+        slot_floats = pad4i(obs_dim * E) + 2 * obs_tile_floats;
+        small_floats = pad4i(2 * 64) * 2 + pad4i((act_dim + 1) * 64) + pad4i(act_dim + 1) + pad4i(act_dim);
+        h1 = 0; obs = 2 * h1_floats; tobs = obs + 2 * slot_floats; tiles_floats = obs + 3 * slot_floats;
+        small = tiles_floats;
+        w1 = small + pad4i(small_floats);
+        w2 = w1 + 2 * w1_floats;
+        cobs = w2 + 2 * w2_floats;
+        out = cobs + 2 * obs_dim * E;
+        xg = out + pad4i(4 * (act_dim + 1) * E);
+        total_floats = xg + pad4i(xg_floats);
+    }
+};
+template <> struct Variant<HID64F> {
+    using Plan = Smem64F; using CtxT = Ctx128;
+    static __device__ __forceinline__ Sink128 sink(float* slot, const Plan& S, int od, int e) {
+        __half* hi = reinterpret_cast<__half*>(slot + pad4i(od * E));
+        return Sink128{slot, hi, hi + 2 * S.obs_tile_floats, e};
+    }
+    static __device__ __forceinline__ float val(const float* slot, const Plan&, int k, int en) { return slot[k * E + en]; }
+    template <int A> static __device__ __forceinline__ void fwd(const CtxT& c, float* slot, const Plan& S, int act, uint32_t& f) {
+        const uint32_t hi = smem_u32(slot) + (uint32_t)pad4i(c.od * E) * 4u;
+        forward_f16<A, 1>(c, hi, hi + (uint32_t)S.obs_tile_floats * 4u, act, f);
+    }
+};
 template <> struct Variant<128> {
     using Plan = Smem128; using CtxT = Ctx128;
     static __device__ __forceinline__ Sink128 sink(float* slot, const Plan& S, int od, int e) {
@@ -538,7 +620,7 @@ template <> struct Variant<128> {
     static __device__ __forceinline__ float val(const float* slot, const Plan&, int k, int en) { return slot[k * E + en]; }
     template <int A> static __device__ __forceinline__ void fwd(const CtxT& c, float* slot, const Plan& S, int act, uint32_t& f) {
         const uint32_t hi = smem_u32(slot) + (uint32_t)pad4i(c.od * E) * 4u;
-        forward128<A>(c, hi, hi + (uint32_t)S.obs_tile_floats * 4u, act, f);
+        forward_f16<A, 2>(c, hi, hi + (uint32_t)S.obs_tile_floats * 4u, act, f);
     }
 };
 
@@ -558,7 +640,8 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
     __shared__ __align__(8) uint64_t s_mbar[2];      // layer-1 / layer-2 accumulators ready
     __shared__ uint32_t s_tmem;
     using V = tc::Variant<HID>;
-    using XG = std::conditional_t<HID == 64, R, double>;      // X_GOAL: shared copy in the integrator's precision (hidden 64) / global table (hidden 128)
+    constexpr int HIDN = (HID == tc::HID64F) ? 64 : HID;      // network width (HID is the variant tag)
+    using XG = std::conditional_t<HID == 128, double, R>;      // X_GOAL: shared copy in the integrator's precision (hidden 64) / global table (hidden 128)
     __shared__ typename V::CtxT s_ctx;
     __shared__ HotCfg<R> s_hot;
     __shared__ double s_z[2 * NZ * E];
@@ -580,8 +663,8 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * E;
     const typename V::Plan S(od, A, T.L * NX * (int)(sizeof(R) / 4));
-    const BlobLayout L = blob_layout(od, A, HID);
-    const tc::SmallLayout SL = tc::small_layout(A, HID);
+    const BlobLayout L = blob_layout(od, A, HIDN);
+    const tc::SmallLayout SL = tc::small_layout(A, HIDN);
     float* s_small = smem + S.small;
     float* s_cobs = smem + S.cobs;
     float* s_out = smem + S.out;
@@ -649,6 +732,32 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
             }
         }
         __syncthreads();      // the blob is dead from here on: the activation tiles alias it
+    } else if constexpr (HID == tc::HID64F) {
+        // hidden 64, fp16 operands, actor + critic fused into one width-128 net: [W1_actor; W1_critic] and diag(W2_actor, W2_critic)
+        R* xg = reinterpret_cast<R*>(smem + S.xg);
+        for (int i = tid; i < T.L * NX; i += NT) xg[i] = (R)T.x_goal[i];
+        s_xg = xg;
+        const float* __restrict__ g = P.policy;
+        for (int i = tid; i < 2 * 64; i += NT) { s_small[SL.b1 + i] = __ldg(g + L.b1 + i); s_small[SL.b2 + i] = __ldg(g + L.b2 + i); }
+        for (int i = tid; i < (A + 1) * 64; i += NT) s_small[SL.w3 + i] = __ldg(g + L.w3 + i);
+        if (tid < 4) { s_small[SL.b3 + tid] = tid < A + 1 ? __ldg(g + L.b3 + tid) : 0.f; s_small[SL.logstd + tid] = tid < A ? __ldg(g + L.logstd + tid) : 0.f; }
+        if (tid == 4 && A + 1 > 4) s_small[SL.b3 + 4] = __ldg(g + L.b3 + 4);
+        for (int i = tid; i < 2 * (S.w1_floats + S.w2_floats); i += NT) smem[S.w1 + i] = 0.f;     // padded K columns and the off-diagonal blocks
+        __syncthreads();
+        __half* w1h = reinterpret_cast<__half*>(smem + S.w1); __half* w1l = w1h + 2 * S.w1_floats;
+        for (int i = tid; i < 128 * od; i += NT) {             // W1P [k/2][2H][2]: consecutive threads read consecutive floats
+            const int par = i & 1, m = (i >> 1) % 128, k = 2 * ((i >> 1) / 128) + par;
+            __half a, b; tc::split_f16(__ldg(g + L.w1t + i), a, b);
+            const int j = tc::ah_idx(m, k, 128);
+            w1h[j] = a; w1l[j] = b;
+        }
+        __half* w2h = reinterpret_cast<__half*>(smem + S.w2); __half* w2l = w2h + 2 * S.w2_floats;
+        for (int i = tid; i < 2 * 64 * 64; i += NT) {          // W2P [net][k/2][H][2]
+            const int net = i / (64 * 64), r = i % (64 * 64), par = r & 1, u = (r >> 1) % 64, k = 2 * ((r >> 1) / 64) + par;
+            __half a, b; tc::split_f16(__ldg(g + L.w2t + i), a, b);
+            const int j = tc::ah_idx(net * 64 + u, net * 64 + k, 128);
+            w2h[j] = a; w2l[j] = b;
+        }
     } else {
         // hidden 128: the packed blob (147 KB) does not fit next to its converted copy -- convert straight from global memory (L2)
         s_xg = T.x_goal;
@@ -717,6 +826,7 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
                 for (int p = 0; p < 2; ++p) cx_tc.w1_s[net][p] = w1s + (net * 2 + p) * S.w1_floats * 4;
             cx_tc.od = od;
         }
+        // (the fused hidden-64 variant only uses net 0 of the [net][hi/lo] tables: its single tiles sit at the same offsets)
         for (int net = 0; net < 2; ++net)
             for (int p = 0; p < 2; ++p) {
                 cx_tc.w2_s[net][p] = w2s + (net * 2 + p) * S.w2_floats * 4;

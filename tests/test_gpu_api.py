@@ -202,3 +202,35 @@ def test_host_collector_pipelined_records_equal_direct_rollouts():
     for a, b in zip(*recs):
         for k in a:
             np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+
+
+def test_ppo_run_matches_an_oracle_deterministic_rollout(tmp_path):
+    '''PPO.run (ppo.py:210-257: deterministic actions, first episode of each eval env) as one fused rollout against the same evaluation
+    done by the oracle: returns, lengths, constraint violations and mean squared error per episode.'''
+    from functools import partial
+
+    from oracle import oracle as orc
+    from safe_control_gym_b200 import configs
+    from safe_control_gym_b200.utils.registration import make
+    task = {k: v for k, v in configs.get('quadrotor_2D_track').items() if k != 'seed'}
+    env_func = partial(make, 'quadrotor', **task)
+    ctrl = make('ppo', env_func, training=True, output_dir=str(tmp_path), seed=7, rollout_batch_size=64, rollout_steps=20, mini_batch_size=256,
+                opt_epochs=1, hidden_dim=64)
+    ctrl.reset()
+    ctrl.train_step()
+    n_ep = 24
+    ev = ctrl.run(n_episodes=n_ep)
+    env = H.make_env('quadrotor_2D_track')
+    T = int(env.CTRL_STEPS)
+    pol = orc.OraclePolicy.from_state_dict({k: v.detach().cpu() for k, v in ctrl.agent.ac.state_dict().items()}, 'tanh')
+    o = H.make_oracle(env, n_ep, auto_reset=True, rng_mode='philox', seed=ctrl.seed * 111)
+    o.reset()
+    oo = o.rollout(pol, T, deterministic=True)
+    mask = oo['mask'][..., 0]
+    first_done = np.where((mask == 0).any(0), (mask == 0).argmax(0), T - 1)
+    live = (np.arange(T)[:, None] <= first_done[None, :]).astype(np.float64)
+    np.testing.assert_array_equal(ev['ep_lengths'], first_done + 1)
+    np.testing.assert_allclose(ev['ep_returns'], (oo['rew'][..., 0] * live).sum(0), rtol=2e-4, atol=1e-4)
+    np.testing.assert_allclose(ev['constraint_violation'], (oo['cviol'][..., 0] * live).sum(0), rtol=0, atol=0)
+    np.testing.assert_allclose(ev['mse'], (oo['mse'][..., 0] * live).sum(0) / (first_done + 1), rtol=2e-4, atol=1e-5)
+    ctrl.close()

@@ -64,7 +64,7 @@ def _check(o, oo, eng, gg, N, T, prec, extra=(), stable=True, pol=None, fresh=No
     eng.close()
 
 
-ENGINES = ['ffma2', 'tcgen05']      # CUDA-core and tensor-core (3xTF32) policy MLP: both must meet the same bar
+ENGINES = ['ffma2', 'tcgen05', 'tcgen05_tf32']      # CUDA-core and tensor-core (3xTF32) policy MLP: both must meet the same bar
 
 
 @pytest.mark.parametrize('engine', ENGINES)
