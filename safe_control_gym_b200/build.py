@@ -1,4 +1,4 @@
-'''In-tree build of the CUDA library (sm_100a) and of the CPU oracle used by the tests.
+'''In-tree build of the CUDA library (sm_100a).  (The CPU oracle of the test-suite builds itself: oracle/oracle.py.)
 
     python -m safe_control_gym_b200.build [--force] [--prof]
 
@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 ROLLOUT_UNITS = [f'scg_rollout_{s}_{p}.cu' for s in ('quad3d', 'quad2d', 'cartpole', 'quad1d') for p in ('f64', 'f32')]   # slowest first
 UNITS = ROLLOUT_UNITS + ['scg_api.cu', 'scg_ppo.cu']          # translation units of libscg_b200.so (compiled in parallel)
-SOURCES = UNITS + ['scg_kernels.cuh', 'scg_device.cuh', 'scg_rollout_launch.cuh']
+SOURCES = UNITS + ['scg_kernels.cuh', 'scg_device.cuh', 'scg_rollout_launch.cuh', 'scg_rollout_tc.cuh']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-shared', '-Xcompiler', '-fPIC',
               '--compress-mode=size']     # line tables make the fatbin large; the compressed image travels to the GPU box faster
 
@@ -43,16 +43,9 @@ def build_cuda(force=False, prof=False, verbose=True, dev=False):
     return out
 
 
-def build_oracle(force=False):
-    sys.path.insert(0, ROOT)
-    from oracle import oracle as orc
-    return orc.build(force=force)
-
-
 def main(argv=None):
     argv = sys.argv[1:] if argv is None else argv
     build_cuda(force='--force' in argv, prof='--prof' in argv, dev='--dev' in argv)
-    build_oracle(force='--force' in argv)
 
 
 if __name__ == '__main__':

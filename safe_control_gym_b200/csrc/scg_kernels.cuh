@@ -474,6 +474,20 @@ __device__ __forceinline__ float norm_rew_value(const NormState* s, float r) {  
     return (float)fmin(fmax(y, -s->clip_rew), s->clip_rew);
 }
 
+// Out of line on purpose: the collectors' owner path is register-starved (Quadrotor-3D: 255 registers); inlined, the disabled normaliser
+// code alone cost +8 % on C4.  A call is only made when normalisation / raw recording is requested (kernel-parameter test).
+static __device__ __noinline__ float norm_rew_apply(const NormState* s, float r) { return s->rew_on ? norm_rew_value(s, r) : r; }
+// observation of env `ol` in a pair-swizzled tile: raw copy to `raw` (nullable), normalised in place
+template <int E> static __device__ __noinline__ void norm_obs_pass(float* tile, int ol, int od, float* raw, const NormState* s, bool have_norm) {
+    const bool on = have_norm && s->obs_on;
+    for (int k = 0; k < od; ++k) {
+        const int i = ((((k >> 1) * 2 + ((ol >> 1) & 1)) * (E / 4) + (ol >> 2)) << 2) + ((ol & 1) << 1) + (k & 1);     // tile_idx<E>(k, ol)
+        const float x = tile[i];
+        if (raw) raw[k] = x;
+        if (on) tile[i] = norm_obs_value(s, k, x);
+    }
+}
+
 #ifdef SCG_PROF
 #define PROF_T(v) long long v = clock64()
 #else
@@ -495,6 +509,17 @@ template <typename V> __device__ __forceinline__ void pstore(const RolloutParams
     *ptr = v;
     if (P.mc_off) multimem_st(reinterpret_cast<V*>(reinterpret_cast<char*>(ptr) + P.mc_off), v);
     else for (int g = 0; g < P.n_peers; ++g) *reinterpret_cast<V*>(reinterpret_cast<char*>(ptr) + P.peer_off[g]) = v;
+}
+
+// One row of the episode table (global) -> shared memory with a TMA bulk copy; the calling lane waits for it.  The mbarrier word is
+// re-armed for every copy and its phase parity lives next to it (bar[1]), so the collector keeps no state in registers.
+static __device__ __noinline__ const double* stage_table_row(double* dst, const double* src, int bytes, uint64_t* bar) {
+    const uint32_t parity = (uint32_t)(bar[1] & 1u);
+    mbar_expect_tx(bar, (uint32_t)bytes);
+    tma_bulk_g2s(dst, src, (uint32_t)bytes, bar);
+    mbar_wait(bar, parity);
+    bar[1] = parity ^ 1u;
+    return dst;
 }
 
 // CTAs per SM the register allocation is capped for: the 16-thread-per-env variants (E=16 x 256 threads, E=8 x 128 threads) halve
@@ -532,7 +557,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     // table mode: per-env rows of the [K][N][P] episode table, staged by TMA bulk copies (one mbarrier per env and candidate slot)
     constexpr int PROW = SCG_MAX_INERTIAL + NX;
     __shared__ __align__(16) double s_row[SPLIT ? 2 * E * PROW : 2];
-    __shared__ __align__(8) uint64_t s_rowbar[SPLIT ? 2 * E : 1];
+    __shared__ __align__(8) uint64_t s_rowbar[SPLIT ? 2 * (2 * E) : 2];     // (mbarrier, parity) pairs
 
     const int od = T.obs_dim, N = T.N, nc = T.n_con;
     const int tid = threadIdx.x;
@@ -548,7 +573,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     R* s_xg = reinterpret_cast<R*>(smem + S.xg);      // X_GOAL [L][nx] in the integrator's precision
 
     // ---- stage the packed policy into shared memory with one TMA bulk copy
-    if (tid == 0) { mbar_init(&s_bar, 1); if (SPLIT) for (int i = 0; i < 2 * E; ++i) mbar_init(&s_rowbar[i], 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&s_bar, 1); if (SPLIT) for (int i = 0; i < 2 * E; ++i) { mbar_init(&s_rowbar[2 * i], 1); s_rowbar[2 * i + 1] = 0; } fence_mbar_init(); }
     if (tid == 32) hot_load<SYS, R>(T, &s_hot);
     const HotCfg<R>* h = &s_hot;
     __syncthreads();
@@ -577,7 +602,8 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
         s_obs[tile_idx<E>(k, ee)] = (n0 + ee < N) ? obs_src[(size_t)(n0 + ee) * od + k] : 0.f;
     }
     if (P.norm) norm_load(&s_norm, P.norm, od, tid, NT);
-    const bool norm_obs = P.norm != nullptr && P.norm[2 * od + 1] != 0.0, norm_rew = P.norm != nullptr && P.norm[2 * od + 4] != 0.0;
+    // (the normaliser switches are read from s_norm / the kernel parameters where they are needed: a flag kept in a register across the
+    //  horizon loop costs the register-starved 3-D instantiations spills -- measured +10 % on C4)
     float ep_ret_sum = 0.f, ep_len_sum = 0.f, ep_cv_sum = 0.f; int ep_count = 0;
     mbar_wait(&s_bar, 0);
     __syncthreads();
@@ -638,37 +664,27 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
             for (int k = 0; k < A; ++k) { ny[k] = (R)zb[(NX + k) * E]; cl[k] = (R)zb[(NX + A + k) * E]; }
             env_reward_mse<SYS, R, R>(h, s_xg, st, ny, cl, s_cstep[bsel * E + ee], rw, ms);
             if (P.out.d_rew_raw) P.out.d_rew_raw[tnp] = (float)rw;
-            pstore(P, P.out.d_rew + tnp, norm_rew ? norm_rew_value(&s_norm, (float)rw) : (float)rw);
+            pstore(P, P.out.d_rew + tnp, P.norm ? norm_rew_apply(&s_norm, (float)rw) : (float)rw);
             if (P.out.d_mse) P.out.d_mse[tnp] = (float)ms;
             h_a += (float)rw; h_b += 1.f;
             if (dn) { h_cnt += 1; h_sa += h_a; h_sb += h_b; h_a = 0.f; h_b = 0.f; }
         }
     };
     // keep the next two episodes of env ee ready (a pure function of (env, episode)); runs while the owners sample and integrate
-    // table mode: the env's row of episode `ep` is fetched with a TMA bulk copy (cp.async.bulk + mbarrier) into s_row[slot][ee]; both
-    // candidate slots are issued before the first wait, so the second copy overlaps the first candidate's arithmetic
-    const bool tma_rows = SPLIT && !h->philox && T.ep_table != nullptr && T.P == PROW && (T.P & 1) == 0;
-    uint32_t row_phase = 0;                    // bit `slot`: parity of that slot's mbarrier (helper lanes only)
+    // table mode: the env's row of episode `ep` of the [K][N][P] table is staged with a TMA bulk copy (cp.async.bulk + mbarrier) by the
+    // out-of-line stage_table_row(): one mbarrier per (candidate slot, env), its parity kept in shared memory
     auto prepare_candidates = [&]() {
         const int want = *(volatile int*)&s_epi[ee];
-        bool need[2];
-#pragma unroll
-        for (int d = 0; d < 2; ++d) {
-            const int ep = want + d, slot = ep & 1;
-            need[d] = *(volatile int*)&s_cand_ep[slot * E + ee] != ep;
-            if (need[d] && tma_rows) {
-                const uint32_t bytes = (uint32_t)PROW * 8u;
-                mbar_expect_tx(&s_rowbar[slot * E + ee], bytes);
-                tma_bulk_g2s(s_row + (slot * E + ee) * PROW, T.ep_table + ((size_t)(ep % T.K) * T.N + n0 + ee) * T.P, bytes, &s_rowbar[slot * E + ee]);
-            }
-        }
 #pragma unroll 1
         for (int d = 0; d < 2; ++d) {
             const int ep = want + d, slot = ep & 1;
-            if (need[d]) {
+            if (*(volatile int*)&s_cand_ep[slot * E + ee] != ep) {
                 double* cd = s_cand + slot * NC * E + ee;
                 const double* staged = nullptr;
-                if (tma_rows) { mbar_wait(&s_rowbar[slot * E + ee], (row_phase >> slot) & 1u); row_phase ^= 1u << slot; staged = s_row + (slot * E + ee) * PROW; }
+#ifndef SCG_NO_TMA_ROWS
+                if (SPLIT && !h->philox && T.ep_table != nullptr && T.P == PROW && (T.P & 1) == 0)
+                    staged = stage_table_row(s_row + (slot * E + ee) * PROW, T.ep_table + ((size_t)(ep % T.K) * T.N + n0 + ee) * T.P, PROW * 8, &s_rowbar[2 * (slot * E + ee)]);
+#endif
                 reset_draw<SYS, R>(T, h, n0 + ee, ep, cd, E, SCG_MAX_INERTIAL + SCG_NINV, staged);   // inertial at rows 0..3, initial state after the reciprocals
                 EnvRegs<SYS, R> tmp; R initr[NX], st0[NX];
 #pragma unroll
@@ -848,19 +864,12 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                         make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_on, ol});
                     }
                     if (P.out.d_rew_raw) P.out.d_rew_raw[tn] = (float)rew;
-                    pstore(P, P.out.d_rew + tn, norm_rew ? norm_rew_value(&s_norm, (float)rew) : (float)rew);
+                    pstore(P, P.out.d_rew + tn, P.norm ? norm_rew_apply(&s_norm, (float)rew) : (float)rew);
                     if (P.out.d_cviol) P.out.d_cviol[tn] = (float)cviol;
                     if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
                 }
-                if (norm_obs || P.out.d_obs_raw) {       // the observation env.step returned: raw copy for the statistics update, normalised in place
-                    float* raw = P.out.d_obs_raw ? P.out.d_obs_raw + tn * od : nullptr;
-                    for (int k = 0; k < od; ++k) {
-                        const int i = tile_idx<E>(k, ol);
-                        const float x = s_on[i];
-                        if (raw) raw[k] = x;
-                        if (norm_obs) s_on[i] = norm_obs_value(&s_norm, k, x);
-                    }
-                }
+                if (P.norm || P.out.d_obs_raw)           // the observation env.step returned: raw copy for the statistics update, normalised in place
+                    norm_obs_pass<E>(s_on, ol, od, P.out.d_obs_raw ? P.out.d_obs_raw + tn * od : nullptr, &s_norm, P.norm != nullptr);
                 trunc = truncated;
                 if (relay) {
                     // multi-GPU: the record entries go through shared memory, a helper warp stores them and their peer copies one step later

@@ -42,7 +42,7 @@ constexpr int PPO_NT = 256;     // threads per CTA: 128 per network
 constexpr int PPO_NETT = 128;
 constexpr int PPO_MAXA = 4;     // act_dim <= 4 on this path
 constexpr int PPO_NSTAT = 8;
-constexpr int PPO_CLUSTER_NPT = 6;   // parameters per thread a CTA of the cluster kernel owns (registers: weight, two Adam moments, smem offset)
+constexpr int PPO_CLUSTER_NPT = 2;   // float4 parameter groups per thread a CTA of the cluster kernel owns (registers: weights, two Adam moments)
 
 struct TrainLayout {
     int a_w1, a_b1, a_w2, a_b2, a_w3, a_b3, a_ls;
@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
     const int obs = P.obs, A = P.act, act = P.activation, mb = P.mb;
     const int nout = net == 0 ? A : 1;
     const int n_chunks = (mb + MS - 1) / MS;
+    const unsigned obs_magic = (unsigned)((0x100000000ull + (unsigned)obs - 1) / (unsigned)obs);     // ceil(2^32 / obs)
     float* sp = smem + net * S.net_floats;           // this net's parameters
     float* sX = smem + S.o_x;
     float* sH1 = smem + S.o_h1 + net * HID * MSP;
@@ -268,17 +269,28 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
     __syncthreads();
     load_params();
 
-    // CLUSTER: this CTA owns parameters [p0, p1); thread tid owns p0 + tid + 256 j.  Master weights and Adam moments live in registers.
-    constexpr int NPT = PPO_CLUSTER_NPT;                   // >= ceil(ceil(total / cluster size) / 256): checked on the host, which falls back to the grid kernel otherwise
-    float own_x[NPT], own_m[NPT], own_v[NPT]; int own_off[NPT];
-    const int c_per = (((L.total + G - 1) / G) + 3) & ~3;
-    const int c_p0 = cta * c_per, c_p1 = min(L.total, c_p0 + c_per);
+    // CLUSTER: this CTA owns the float4 groups [q0, q1) of the parameter vector; thread tid owns q0 + tid + 256 j.  Master weights and
+    // Adam moments of those groups live in registers for the whole launch.
+    constexpr int NPT = PPO_CLUSTER_NPT;                   // float4 groups per thread: checked on the host (grid kernel otherwise)
+    float4 own_x[NPT], own_m[NPT], own_v[NPT]; int own_off[NPT];     // own_off: shared-memory offset of the group (-1: none, -2: not contiguous)
+    const int c_nq = (L.total + 3) / 4, c_perq = (c_nq + G - 1) / G;
+    const int c_q0 = cta * c_perq, c_q1 = min(c_nq, c_q0 + c_perq);
     if constexpr (CLUSTER) {
 #pragma unroll
         for (int j = 0; j < NPT; ++j) {
-            const int p = c_p0 + tid + PPO_NT * j;
-            own_x[j] = own_m[j] = own_v[j] = 0.f; own_off[j] = -1;
-            if (p < c_p1) { own_x[j] = __ldcg(P.params + p); own_m[j] = __ldcg(P.m + p); own_v[j] = __ldcg(P.v + p); own_off[j] = train_to_smem<HID, MS>(p, L, S, obs, A); }
+            const int q = c_q0 + tid + PPO_NT * j;
+            own_x[j] = own_m[j] = own_v[j] = make_float4(0.f, 0.f, 0.f, 0.f); own_off[j] = -1;
+            if (q < c_q1) {
+                own_x[j] = __ldcg(reinterpret_cast<const float4*>(P.params) + q);
+                own_m[j] = __ldcg(reinterpret_cast<const float4*>(P.m) + q);
+                own_v[j] = __ldcg(reinterpret_cast<const float4*>(P.v) + q);
+                int o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o[i] = train_to_smem<HID, MS>(4 * q + i, L, S, obs, A);
+                const bool contig = o[0] >= 0 && (o[0] & 3) == 0 && o[1] == o[0] + 1 && o[2] == o[0] + 2 && o[3] == o[0] + 3;
+                const bool none = o[0] < 0 && o[1] < 0 && o[2] < 0 && o[3] < 0;
+                own_off[j] = contig ? o[0] : none ? -1 : -2;
+            }
         }
     }
 #ifdef SCG_PPO_PROF
@@ -518,7 +530,7 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                 for (int i = 0; i < NW1; ++i) {
                     const int idx = t + PPO_NETT * i;
                     if (idx < HID * obs) {
-                        const int u = idx / obs, k = idx % obs;
+                        const int u = (int)__umulhi((unsigned)idx, obs_magic), k = idx - u * obs;      // idx / obs, idx % obs (idx < 2^16)
                         float a = 0.f;
 #pragma unroll 4
                         for (int s = 0; s < MS; s += 4) {
@@ -612,30 +624,38 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
                     xx = xx - step_size * (mm / denom);                    // param.addcdiv_(exp_avg, denom, value=-step_size)
                 };
                 if constexpr (CLUSTER) {
-                    float g[NPT];
-#pragma unroll
-                    for (int j = 0; j < NPT; ++j) {                        // all the remote loads first (latency overlaps), fixed summation order
-                        const int p = c_p0 + tid + PPO_NT * j;
-                        float acc = 0.f;
-                        if (p < c_p1) {
-#pragma unroll
-                            for (int c2 = 0; c2 < 8; ++c2) if (c2 < Gu) acc += cluster.map_shared_rank(gbuf, c2)[p];
-                        }
-                        g[j] = acc;
-                    }
 #pragma unroll
                     for (int j = 0; j < NPT; ++j) {
-                        const int p = c_p0 + tid + PPO_NT * j;
-                        if (p >= c_p1) continue;
-                        float gg = g[j];
-                        if (p >= L.a_ls && p < L.a_ls + A) gg += -(float)P.ent_coef;      // d(entropy_coef * entropy_loss)/d logstd
-                        if (want_grad) P.grad_out[p] = gg;
+                        const int q = c_q0 + tid + PPO_NT * j;
+                        if (q >= c_q1) continue;
+                        // the 8 remote (distributed shared memory) loads are independent: issue them together, then sum in a fixed order
+                        float4 w[8];
+#pragma unroll
+                        for (int c2 = 0; c2 < 8; ++c2)
+                            w[c2] = c2 < Gu ? *(reinterpret_cast<const float4*>(cluster.map_shared_rank(gbuf, c2)) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 g = w[0];
+#pragma unroll
+                        for (int c2 = 1; c2 < 8; ++c2) { g.x += w[c2].x; g.y += w[c2].y; g.z += w[c2].z; g.w += w[c2].w; }
+                        const int p = 4 * q;
+                        if (p == L.a_ls) {                                   // d(entropy_coef * entropy_loss)/d logstd = -entropy_coef
+                            const float e = -(float)P.ent_coef;
+                            g.x += e; if (A > 1) g.y += e; if (A > 2) g.z += e; if (A > 3) g.w += e;
+                        }
+                        if (want_grad) reinterpret_cast<float4*>(P.grad_out)[q] = g;
                         const bool actor = p < L.critic0;
                         if (actor && !apply_actor) continue;
-                        adam(own_m[j], own_v[j], own_x[j], gg, (float)(actor ? s_gate[1] : s_gate[3]), (float)(actor ? s_gate[2] : s_gate[4]));
-                        if (own_off[j] >= 0) {
+                        const float step_size = (float)(actor ? s_gate[1] : s_gate[3]), bc2s = (float)(actor ? s_gate[2] : s_gate[4]);
+                        adam(own_m[j].x, own_v[j].x, own_x[j].x, g.x, step_size, bc2s); adam(own_m[j].y, own_v[j].y, own_x[j].y, g.y, step_size, bc2s);
+                        adam(own_m[j].z, own_v[j].z, own_x[j].z, g.z, step_size, bc2s); adam(own_m[j].w, own_v[j].w, own_x[j].w, g.w, step_size, bc2s);
+                        if (own_off[j] >= 0) {                               // the group is contiguous in the padded shared layout: one 16-byte store per CTA
 #pragma unroll
-                            for (int c2 = 0; c2 < 8; ++c2) if (c2 < G) cluster.map_shared_rank(smem, c2)[own_off[j]] = own_x[j];
+                            for (int c2 = 0; c2 < 8; ++c2) if (c2 < G) *reinterpret_cast<float4*>(cluster.map_shared_rank(smem, c2) + own_off[j]) = own_x[j];
+                        } else if (own_off[j] == -2) {                       // straddles a row / section boundary: element by element
+                            const float xs[4] = {own_x[j].x, own_x[j].y, own_x[j].z, own_x[j].w};
+                            for (int i = 0; i < 4; ++i) {
+                                const int o = train_to_smem<HID, MS>(p + i, L, S, obs, A);
+                                if (o >= 0) for (int c2 = 0; c2 < G; ++c2) cluster.map_shared_rank(smem, c2)[o] = xs[i];
+                            }
                         }
                     }
                 } else {
@@ -680,8 +700,8 @@ __global__ void __launch_bounds__(PPO_NT, 1) ppo_update_kernel(PpoParams P) {
     if constexpr (CLUSTER) {                                // the slice owners write weights and moments back once per launch
 #pragma unroll
         for (int j = 0; j < NPT; ++j) {
-            const int p = c_p0 + tid + PPO_NT * j;
-            if (p < c_p1) { P.params[p] = own_x[j]; P.m[p] = own_m[j]; P.v[p] = own_v[j]; }
+            const int q = c_q0 + tid + PPO_NT * j;
+            if (q < c_q1) { reinterpret_cast<float4*>(P.params)[q] = own_x[j]; reinterpret_cast<float4*>(P.m)[q] = own_m[j]; reinterpret_cast<float4*>(P.v)[q] = own_v[j]; }
         }
     }
 #ifdef SCG_PPO_PROF
@@ -754,8 +774,9 @@ int ppo_launch_cluster(const scg_ppo_args* a, PpoParams& P, cudaStream_t st) {
     const TrainLayout L = train_layout(a->obs_dim, a->act_dim, HID);
     const int chunks = (a->mini_batch_size + MS - 1) / MS;
     int C = 1; while (C < 8 && C < chunks) C *= 2;
-    if ((((L.total + C - 1) / C) + 3) / 4 * 4 > PPO_CLUSTER_NPT * PPO_NT) C = 8;       // the slice of a CTA must fit NPT registers per thread
-    if ((((L.total + C - 1) / C) + 3) / 4 * 4 > PPO_CLUSTER_NPT * PPO_NT) return -100;  // does not fit: the caller uses the grid kernel
+    const int nq = (L.total + 3) / 4;
+    if ((nq + C - 1) / C > PPO_CLUSTER_NPT * PPO_NT) C = 8;                  // the slice of a CTA must fit NPT float4 groups per thread
+    if ((nq + C - 1) / C > PPO_CLUSTER_NPT * PPO_NT) return -100;            // does not fit: the caller uses the grid kernel
     const size_t smem = sizeof(float) * ((size_t)S.total + L.total + PPO_NSTAT);
     auto kern = ppo_update_kernel<HID, MS, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -567,7 +567,7 @@ __device__ __noinline__ void forward_f16(const Ctx128& c /* in shared memory */,
     fwd += 1;
 }
 
-// ---- per-width dispatch used by the collector body --------------------------------------------------------------------------
+// ---- per-width dispatch used by the collector body (forward declaration of the out-of-line normaliser pass below) --------------------------------------------------------------------------
 template <int HID> struct Variant;
 template <> struct Variant<64> {
     using Plan = Smem<64>; using CtxT = Ctx;
@@ -623,6 +623,18 @@ template <> struct Variant<128> {
         forward_f16<A, 2>(c, hi, hi + (uint32_t)S.obs_tile_floats * 4u, act, f);
     }
 };
+
+// out of line for the same reason as norm_obs_pass<E> of the FFMA2 collector
+template <int HID> static __device__ __noinline__ void norm_obs_pass(float* slot, const typename Variant<HID>::Plan& S, int od, int ol, float* raw,
+                                                                     const NormState* s, bool have_norm) {
+    const bool on = have_norm && s->obs_on;
+    const auto sink = Variant<HID>::sink(slot, S, od, ol);
+    for (int k = 0; k < od; ++k) {
+        const float x = Variant<HID>::val(slot, S, k, ol);
+        if (raw) raw[k] = x;
+        if (on) sink(k, norm_obs_value(s, k, x));
+    }
+}
 
 }  // namespace tc
 
@@ -794,7 +806,6 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
         V::sink(s_obs, S, od, ee)(k, x);
     }
     if (P.norm) norm_load(&s_norm, P.norm, od, tid, NT);
-    const bool norm_obs = P.norm != nullptr && P.norm[2 * od + 1] != 0.0, norm_rew = P.norm != nullptr && P.norm[2 * od + 4] != 0.0;
     float sd[A], lsd[A], inv2var[A];
 #pragma unroll
     for (int k = 0; k < A; ++k) { lsd[k] = s_small[SL.logstd + k]; sd[k] = expf(lsd[k]); inv2var[k] = 1.0f / (2.f * sd[k] * sd[k]); }
@@ -874,7 +885,7 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
             for (int k = 0; k < A; ++k) { ny[k] = (R)zb[(NX + k) * E]; cl[k] = (R)zb[(NX + A + k) * E]; }
             env_reward_mse<SYS, R, XG>(h, s_xg, st, ny, cl, s_cstep[bsel * E + ee], rw, ms);
             if (P.out.d_rew_raw) P.out.d_rew_raw[tnp] = (float)rw;
-            pstore(P, P.out.d_rew + tnp, norm_rew ? norm_rew_value(&s_norm, (float)rw) : (float)rw);
+            pstore(P, P.out.d_rew + tnp, P.norm ? norm_rew_apply(&s_norm, (float)rw) : (float)rw);
             if (P.out.d_mse) P.out.d_mse[tnp] = (float)ms;
             h_a += (float)rw; h_b += 1.f;
             if (dn) { h_cnt += 1; h_sa += h_a; h_sb += h_b; h_a = 0.f; h_b = 0.f; }
@@ -1035,18 +1046,12 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
                         make_obs<SYS, R, XG>(T, h, s_xg, state, n, step_before, false, ns, sink_next);
                     }
                     if (P.out.d_rew_raw) P.out.d_rew_raw[tn] = (float)rew;
-                    pstore(P, P.out.d_rew + tn, norm_rew ? norm_rew_value(&s_norm, (float)rew) : (float)rew);
+                    pstore(P, P.out.d_rew + tn, P.norm ? norm_rew_apply(&s_norm, (float)rew) : (float)rew);
                     if (P.out.d_cviol) P.out.d_cviol[tn] = (float)cviol;
                     if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
                 }
-                if (norm_obs || P.out.d_obs_raw) {       // the observation env.step returned: raw copy for the statistics update, normalised in place
-                    float* raw = P.out.d_obs_raw ? P.out.d_obs_raw + tn * od : nullptr;
-                    for (int k = 0; k < od; ++k) {
-                        const float x = tile_val(s_on, k, ol);
-                        if (raw) raw[k] = x;
-                        if (norm_obs) sink_next(k, norm_obs_value(&s_norm, k, x));
-                    }
-                }
+                if (P.norm || P.out.d_obs_raw)           // the observation env.step returned: raw copy for the statistics update, normalised in place
+                    tc::norm_obs_pass<HID>(s_on, S, od, ol, P.out.d_obs_raw ? P.out.d_obs_raw + tn * od : nullptr, &s_norm, P.norm != nullptr);
                 trunc = truncated;
                 if (relay) {
                     float* rb = s_rec + (t & 1) * (A + 2) * E + ol;

@@ -59,7 +59,7 @@ def _check(o, oo, eng, gg, N, T, prec, extra=(), stable=True, pol=None, fresh=No
     done_frac = 1.0 - float(oo['mask'].mean())
     assert done_frac > 0.0                           # resets happened inside the horizon
     if fresh is not None:
-        w = H.compare_replay(fresh, pol, gg, N, T, tol=2e-5 if prec == 'f64' else 1e-4)
+        w = H.compare_replay(fresh, pol, gg, N, T, tol=2e-5 if prec == 'f64' else 2e-4)      # f32 state arithmetic: one-step error ~1e-6 .. 1e-4 (cvals near zero)
         print('teacher-forced replay: largest relative deviation per key:', {k: f'{v:.2e}' if isinstance(v, float) else v for k, v in w.items()})
     eng.close()
 
