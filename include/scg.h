@@ -230,6 +230,7 @@ typedef struct scg_step_out {
 
 /* Output buffers of the fused rollout, PPOBuffer scheme (ppo_utils.py:266-295): [T][N][.] float32. */
 #define SCG_MAX_PEERS 8
+#define SCG_MAX_SAFETY 16        /* constraint models of a safety layer (SafeExplorer) */
 
 typedef struct scg_rollout_out {
     float* d_obs;              /* [T][N][obs_dim] observation fed to the policy at step t */
@@ -253,6 +254,7 @@ typedef struct scg_rollout_out {
     int32_t* d_ep_count;       /* [N] nullable */
     /* with obs / reward normalisation (scg_rollout_args.d_norm): what the running normalisers of the controller must be updated with
      * after the rollout (normalization.py:106-113,148-159) */
+    float* d_c;                /* [T][N][safety_constraints] nullable: the constraint values fed to the safety layer at step t (SafePPOBuffer 'c') */
     float* d_obs_raw;          /* [T][N][obs_dim] nullable: the UN-normalised observation env.step returned at step t (reset obs where done) */
     float* d_rew_raw;          /* [T][N] nullable: the UN-normalised reward */
 } scg_rollout_out;
@@ -289,6 +291,16 @@ typedef struct scg_rollout_args {
      * stays un-normalised, as in the reference (ppo.py:279-282). */
     const double* d_norm;
     const float* d_obs0;       /* [N][obs_dim] nullable: policy input of step 0 (default: the observation the engine carried over) */
+    /* Safety layer of the SafeExplorer collector (safe_control_gym/controllers/safe_explorer/safe_explorer_utils.py:15-176, applied inside the
+     * actor: safe_ppo_utils.py:88-104): one constraint model per state-constraint row i < safety_constraints, each an MLP
+     * obs -> relu(hidden) -> act_dim; the mean action is projected  mu_safe = mu - lambda* g_i*(obs),
+     * lambda_i = relu((g_i . mu + c_i + slack_i) / (g_i . g_i + 1e-8)), i* = argmax lambda (Dalal et al. 2018, eq. 5-6), c = the first
+     * `safety_constraints` constraint values of the current state; sampling and log-prob use mu_safe.  0 = no safety layer.
+     * d_safety: per model { W1[hidden][obs_dim], b1[hidden], W2[act_dim][hidden], b2[act_dim] } (nn.Linear layout), models back to back. */
+    int32_t safety_constraints;
+    int32_t safety_hidden;
+    const float* d_safety;
+    double safety_slack[SCG_MAX_SAFETY];
 } scg_rollout_args;
 
 typedef struct scg_env scg_env;   /* opaque, one per (device, batch) */

@@ -60,7 +60,8 @@ class _Policy(C.Structure):
 class _RolloutOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('obs', 'act', 'rew', 'mask', 'v', 'logp', 'terminal_v', 'ret', 'adv', 'cviol', 'cvals', 'mse',
                                          'last_obs', 'last_val', 'ep_return_sum', 'ep_length_sum', 'ep_cviol_sum', 'ep_count',
-                                         'state_trace', 'replay_obs', 'replay_act', 'replay_mask', 'next_obs', 'norm', 'obs0', 'obs_raw', 'rew_raw')]
+                                         'state_trace', 'replay_obs', 'replay_act', 'replay_mask', 'next_obs', 'norm', 'obs0', 'obs_raw', 'rew_raw')] + \
+        [('safety_C', C.c_int), ('safety_H', C.c_int), ('safety', C.c_void_p), ('safety_slack', C.c_void_p), ('c', C.c_void_p)]
 
 
 class OraclePolicy:
@@ -173,7 +174,7 @@ class Oracle:
             raise RuntimeError('[ERROR] You must call env.reset() at least once before using env.step().')
         return o
 
-    def rollout(self, policy, T, eps=None, deterministic=False, gamma=0.99, gae_lambda=0.95, use_gae=False, trace=False, replay=None, norm=None, obs0=None):
+    def rollout(self, policy, T, eps=None, deterministic=False, gamma=0.99, gae_lambda=0.95, use_gae=False, trace=False, replay=None, norm=None, obs0=None, safety=None):
         '''replay = {'obs', 'act', 'mask'} (float32 [T][N][.] arrays of another collector's record): teacher-forced one-step predictions,
         see oracle_rollout_out in scg_oracle.c.'''
         N, od, A, nc = self.N, self.obs_dim, self.nu, self.n_con
@@ -190,6 +191,8 @@ class Oracle:
         if trace:
             o['state_trace'] = np.empty((T, N, self.nx), np.float64)
         keep = []
+        if safety is not None:          # {'blob': float32 [C * per], 'C', 'H', 'slack': [C]}
+            o['c'] = np.empty((T, N, safety['C']), f)
         if norm is not None:
             o['obs_raw'] = np.empty((T, N, od), f)
             o['rew_raw'] = np.empty((T, N, 1), f)
@@ -206,6 +209,11 @@ class Oracle:
             keep.append(np.ascontiguousarray(norm, dtype=np.float64)); ro.norm = keep[-1].ctypes.data
         if obs0 is not None:
             keep.append(np.ascontiguousarray(obs0, dtype=np.float32)); ro.obs0 = keep[-1].ctypes.data
+        if safety is not None:
+            keep.append(np.ascontiguousarray(safety['blob'], dtype=np.float32)); ro.safety = keep[-1].ctypes.data
+            sl = np.zeros(16); sl[:safety['C']] = safety['slack']
+            keep.append(sl); ro.safety_slack = keep[-1].ctypes.data
+            ro.safety_C, ro.safety_H = int(safety['C']), int(safety['H'])
         e = None if eps is None else np.ascontiguousarray(eps, dtype=np.float32).reshape(T, N, A)
         ps = policy.c_struct()
         rc = self.lib.scg_oracle_rollout(self.h, C.byref(ps), _p(e), C.c_int(T), C.c_int(int(deterministic)), C.c_double(gamma),

@@ -803,6 +803,11 @@ typedef struct {
     const double* norm;
     const float* obs0;     /* [N][obs_dim] policy input of step 0 (nullable) */
     float *obs_raw, *rew_raw;
+    /* SafeExplorer safety layer (safe_explorer_utils.py:15-176; layout of scg_rollout_args.d_safety) */
+    int safety_C, safety_H;
+    const float* safety;
+    const double* safety_slack;
+    float* c;              /* [T][N][safety_C] constraint values fed to the safety layer */
 } oracle_rollout_out;
 
 /* PPO.train_step collector loop (PPO:259-297) + compute_returns_and_advantages (PU:374-400) */
@@ -833,6 +838,32 @@ int scg_oracle_rollout(scg_oracle* o, const oracle_policy* p, const float* eps /
             for (int k = 0; k < od; ++k) obs_f[k] = (float)e->obs[k];        /* torch.FloatTensor(obs) PPO:268 */
             mlp_forward(p->aw, p->ab, od, p->hidden, A, p->activation, obs_f, mean);
             mlp_forward(p->cw, p->cb, od, p->hidden, 1, p->activation, obs_f, &val);
+            if (out->safety_C > 0) {
+                /* c = info['constraint_values'][:C] of the current state (safe_ppo.py:123,344); mu_safe = mu - lambda* g_i* (safe_explorer_utils.py:120-176) */
+                double cv[SCG_MAX_CON_ROWS];
+                eval_constraints(o, e, cv);
+                const int C = out->safety_C, H = out->safety_H, per = H * od + H + A * H + A;
+                float best = -1.0f, gbest[SCG_MAX_NU] = {0};
+                for (int ci = 0; ci < C; ++ci) {
+                    const float* w1 = out->safety + (size_t)ci * per; const float* b1 = w1 + H * od; const float* w2 = b1 + H; const float* b2 = w2 + A * H;
+                    float g[SCG_MAX_NU];
+                    for (int a = 0; a < A; ++a) g[a] = b2[a];
+                    for (int j = 0; j < H; ++j) {
+                        float hj = b1[j];
+                        for (int k = 0; k < od; ++k) hj += w1[j * od + k] * obs_f[k];
+                        hj = hj > 0 ? hj : 0;
+                        for (int a = 0; a < A; ++a) g[a] += w2[a * H + j] * hj;
+                    }
+                    const float cf = (float)cv[ci];
+                    if (out->c) out->c[tn * C + ci] = cf;
+                    float num = 0, den = 0;
+                    for (int a = 0; a < A; ++a) { num += g[a] * mean[a]; den += g[a] * g[a]; }
+                    num = (num + cf) + (float)out->safety_slack[ci];
+                    float m = num / (den + 1e-8f); m = m > 0 ? m : 0;
+                    if (m > best) { best = m; for (int a = 0; a < A; ++a) gbest[a] = g[a]; }
+                }
+                for (int a = 0; a < A; ++a) mean[a] = mean[a] - best * gbest[a];
+            }
             float logp = 0;
             for (int k = 0; k < A; ++k) {
                 float sd = expf(p->logstd[k]);

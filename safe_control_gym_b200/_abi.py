@@ -10,6 +10,7 @@ import os
 
 SCG_ABI_VERSION = 3
 SCG_MAX_PEERS = 8
+SCG_MAX_SAFETY = 16
 SCG_MAX_NX = 12
 SCG_MAX_NU = 4
 SCG_MAX_OBS = 48
@@ -88,7 +89,7 @@ class scg_step_out(C.Structure):
 class scg_rollout_out(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         'd_obs', 'd_act', 'd_rew', 'd_mask', 'd_v', 'd_logp', 'd_terminal_v', 'd_ret', 'd_adv', 'd_cviol', 'd_cvals', 'd_mse',
-        'd_last_obs', 'd_last_val', 'd_ep_return_sum', 'd_ep_length_sum', 'd_ep_cviol_sum', 'd_ep_count', 'd_obs_raw', 'd_rew_raw')]
+        'd_last_obs', 'd_last_val', 'd_ep_return_sum', 'd_ep_length_sum', 'd_ep_cviol_sum', 'd_ep_count', 'd_c', 'd_obs_raw', 'd_rew_raw')]
 
 
 class scg_rollout_args(C.Structure):
@@ -99,6 +100,7 @@ class scg_rollout_args(C.Structure):
         ('d_policy', C.c_void_p), ('d_eps', C.c_void_p),
         ('n_peers', C.c_int32), ('mlp_engine', C.c_int32), ('peer_byte_offset', C.c_int64 * SCG_MAX_PEERS),
         ('multicast_byte_offset', C.c_int64), ('d_norm', C.c_void_p), ('d_obs0', C.c_void_p),
+        ('safety_constraints', C.c_int32), ('safety_hidden', C.c_int32), ('d_safety', C.c_void_p), ('safety_slack', C.c_double * SCG_MAX_SAFETY),
     ]
 
 

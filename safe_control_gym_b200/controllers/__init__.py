@@ -1,7 +1,11 @@
-'''Register controllers (safe_control_gym/controllers/__init__.py:29-31): only `ppo` is on the hot path.'''
+'''Register controllers (safe_control_gym/controllers/__init__.py:29-47): `ppo` (the hot path) and its sibling collector `safe_explorer_ppo`.'''
 
 from safe_control_gym_b200.utils.registration import register
 
 register(idx='ppo',
          entry_point='safe_control_gym_b200.controllers.ppo.ppo:PPO',
          config_entry_point='safe_control_gym_b200.controllers.ppo.ppo:DEFAULT_CONFIG')
+
+register(idx='safe_explorer_ppo',
+         entry_point='safe_control_gym_b200.controllers.safe_explorer.safe_ppo:SafeExplorerPPO',
+         config_entry_point='safe_control_gym_b200.controllers.safe_explorer.safe_ppo:DEFAULT_CONFIG')

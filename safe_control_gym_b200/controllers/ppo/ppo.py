@@ -318,7 +318,7 @@ class PPO:
         T = self.rollout_steps if T is None else T
         blob, dims = self._policy_blob()
         eng = self.env.unwrapped.engine
-        kw = {}
+        kw = self._collector_kwargs()
         cached = self._rollout_out.get(T) if eps is None else None
         if self.world > 1 and eps is None:
             if T not in self._peers:
@@ -326,7 +326,7 @@ class PPO:
                 self._peers[T] = PeerGatheredRollout(rollout_flat_numel(dims[0], dims[1], T, eng.N), self.device)
             self._peer = self._peers[T]
             if cached is None:
-                kw = self._peer.rollout_kwargs()
+                kw.update(self._peer.rollout_kwargs())
             self._peer.begin()      # every rank's previous update has consumed the gathered buffer before anyone overwrites it
         want = ('ret', 'adv', 'cviol', 'mse', 'last', 'episode')
         if self.norm_obs or self.norm_reward:
@@ -337,6 +337,10 @@ class PPO:
         if eps is None:
             self._rollout_out[T] = out
         return out
+
+    def _collector_kwargs(self):
+        '''Extra `engine.rollout` arguments of a sibling collector (SafeExplorerPPO: the safety layer).'''
+        return {}
 
     def _norm_blob(self):
         '''Frozen normaliser statistics in the layout of scg_rollout_args.d_norm.'''
@@ -412,10 +416,10 @@ class PPO:
         obs, _ = self.eval_env.reset()
         blob, dims = self._policy_blob()
         T = int(self.eval_env.proto.CTRL_STEPS)
-        kw = {}
+        kw = self._collector_kwargs()
         if self.norm_obs:              # ppo.py:218,229: frozen statistics during evaluation
             self.obs_normalizer.set_read_only()
-            kw = dict(norm=self._norm_blob(), obs0=self.obs_normalizer.normalize(obs).to(torch.float32).contiguous())
+            kw.update(norm=self._norm_blob(), obs0=self.obs_normalizer.normalize(obs).to(torch.float32).contiguous())
             kw['norm'][2 * dims[0] + 4] = 0.0       # evaluation reports raw rewards
         out = self.eval_env.engine.rollout(blob, dims, T, activation=self.activation, deterministic=True, want=('cviol', 'mse', 'episode'), **kw)
         mask = out['mask'][..., 0]

@@ -30,6 +30,7 @@ struct scg_env {
     DevTables tab;
     long long noise_cursor = 0;
     bool did_reset = false;
+    bool con_single = true;      // every constraint row has exactly one non-zero (bounds): the in-kernel fast path
     uint64_t launches = 0;
     std::string err;
 };
@@ -204,6 +205,8 @@ int scg_set_constraints(scg_env* e, int32_t n_rows, const int32_t* kind, const i
     CUDA_TRY(e, upload(&e->d_con_val, val, (size_t)(nnz > 0 ? nnz : 1)));
     CUDA_TRY(e, upload(&e->d_con_b, b, (size_t)n_rows));
     e->n_con = n_rows;
+    e->con_single = true;
+    for (int r = 0; r < n_rows; ++r) if (row_ptr[r + 1] - row_ptr[r] != 1 || kind[r] == SCG_CON_QUAD) e->con_single = false;
     e->tab.n_con = n_rows; e->tab.con_kind = e->d_con_kind; e->tab.con_strict = e->d_con_strict; e->tab.con_ptr = e->d_con_ptr;
     e->tab.con_col = e->d_con_col; e->tab.con_val = e->d_con_val; e->tab.con_b = e->d_con_b;
     return SCG_OK;
@@ -301,6 +304,12 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
     if (a->multicast_byte_offset & 15) return fail(e, SCG_EINVAL, "scg_rollout: multicast_byte_offset must be a multiple of 16");
     P.mc_off = a->multicast_byte_offset;
     P.norm = a->d_norm; P.obs0 = a->d_obs0;
+    if (a->safety_constraints < 0 || a->safety_constraints > SCG_MAX_SAFETY || (a->safety_constraints > 0 && (!a->d_safety || a->safety_hidden < 1 || a->safety_hidden > 256)))
+        return fail(e, SCG_EINVAL, "scg_rollout: bad safety layer (safety_constraints in [0, 16], safety_hidden in [1, 256], d_safety non-null)");
+    if (a->safety_constraints > e->n_con) return fail(e, SCG_EINVAL, "scg_rollout: safety_constraints exceeds the number of constraint rows of the env");
+    if (a->safety_constraints > 0 && !e->con_single) return fail(e, SCG_EINVAL, "scg_rollout: the safety layer needs single-variable (bound) constraint rows");
+    P.safety_C = a->safety_constraints; P.safety_H = a->safety_hidden; P.safety = a->d_safety;
+    for (int i = 0; i < SCG_MAX_SAFETY; ++i) P.safety_slack[i] = (float)a->safety_slack[i];
     cudaStream_t s = (cudaStream_t)stream;
     const bool dbl = e->cfg.precision == SCG_PREC_F64;
     RolloutLaunch rl{e->cfg.num_envs, e->obs_dim, e->nu, e->nx, e->L, e->tab};

@@ -272,6 +272,9 @@ struct RolloutParams {
     scg_rollout_out out;
     int n_peers;                 // fused all-gather: peer copies of the PPOBuffer keys (see scg_rollout_args)
     long long peer_off[SCG_MAX_PEERS];
+    int safety_C, safety_H;      // SafeExplorer safety layer: constraint models (0 = none), hidden width
+    const float* safety;         // [C] x { W1[H][obs], b1[H], W2[A][H], b2[A] }
+    float safety_slack[SCG_MAX_SAFETY];
     const double* norm;          // frozen obs / reward normaliser statistics (scg_rollout_args.d_norm), nullable
     const float* obs0;           // policy input of step 0, nullable
     long long mc_off;            // != 0: NVSwitch multicast mapping of the gathered buffer (multimem.st), replaces the unicast peer copies
@@ -474,6 +477,54 @@ __device__ __forceinline__ float norm_rew_value(const NormState* s, float r) {  
     return (float)fmin(fmax(y, -s->clip_rew), s->clip_rew);
 }
 
+// ---------------------------------------------------------------------------------------------
+// SafeExplorer safety layer (safe_explorer_utils.py:15-176).  All three pieces are out of line: they only run when a safety layer is given.
+// ---------------------------------------------------------------------------------------------
+// g_i(obs) of every constraint model for the CTA's E envs: thread (e = tid % E, group = tid / E) handles models group, group + NT/E, ...
+// s_g[(i * A + a) * E + e].  obs comes from a pair-swizzled tile (tile_idx<E>).
+template <int E, int A> static __device__ __noinline__ void safety_models(const float* __restrict__ blob, int C, int H, int od, const float* tile,
+                                                                          float* s_g, int tid, int nthreads) {
+    const int e = tid % E, per = H * od + H + A * H + A;
+    for (int i = tid / E; i < C; i += nthreads / E) {
+        const float* w1 = blob + (size_t)i * per; const float* b1 = w1 + H * od; const float* w2 = b1 + H; const float* b2 = w2 + A * H;
+        float g[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) g[a] = __ldg(b2 + a);
+        for (int j = 0; j < H; ++j) {
+            float hj = __ldg(b1 + j);
+            for (int k = 0; k < od; ++k)
+                hj = fmaf(__ldg(w1 + j * od + k), tile[((((k >> 1) * 2 + ((e >> 1) & 1)) * (E / 4) + (e >> 2)) << 2) + ((e & 1) << 1) + (k & 1)], hj);
+            hj = fmaxf(hj, 0.0f);                                  // MLP default activation: relu (neural_networks.py:25)
+#pragma unroll
+            for (int a = 0; a < A; ++a) g[a] = fmaf(__ldg(w2 + a * H + j), hj, g[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < A; ++a) s_g[(i * A + a) * E + e] = g[a];
+    }
+}
+// Owner lane: c_i = np.round(a_i z - b_i, 8) of the CURRENT state for the first C (single-variable) constraint rows (float32 like
+// torch.FloatTensor(c)), recorded as SafePPOBuffer 'c', then mu <- mu - lambda* g_i* (get_safe_action, safe_explorer_utils.py:120-176) in
+// float32 like the reference's torch code.  `st` / `mu` are caller-local arrays that only exist inside the safety branch.
+template <int NX, int E, int A> static __device__ __noinline__ void safety_apply(const double* st, const ConRow* rows, int C, const float* s_g, const float* slack,
+                                                                                 int e, float* mu, float* c_rec) {
+    float best = -1.0f; int bi = 0;
+    for (int i = 0; i < C; ++i) {
+        const ConRow row = rows[i];
+        double acc = __dmul_rn(row.val, st[row.col < NX ? row.col : 0]);
+        if (row.flags & 2) acc = fabs(acc);
+        const float ci = (float)(rint(__dsub_rn(acc, row.b) * 1e8) / 1e8);
+        if (c_rec) c_rec[i] = ci;
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int a = 0; a < A; ++a) { const float g = s_g[(i * A + a) * E + e]; num = fmaf(g, mu[a], num); den = fmaf(g, g, den); }
+        num = (num + ci) + slack[i];
+        const float m = fmaxf(num / (den + 1e-8f), 0.0f);
+        if (m > best) { best = m; bi = i; }                       // topk(..., 1): the first maximum
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) mu[a] = mu[a] - best * s_g[(bi * A + a) * E + e];
+}
+
 // Out of line on purpose: the collectors' owner path is register-starved (Quadrotor-3D: 255 registers); inlined, the disabled normaliser
 // code alone cost +8 % on C4.  A call is only made when normalisation / raw recording is requested (kernel-parameter test).
 static __device__ __noinline__ float norm_rew_apply(const NormState* s, float r) { return s->rew_on ? norm_rew_value(s, r) : r; }
@@ -527,7 +578,8 @@ static __device__ __noinline__ const double* stage_table_row(double* dst, const 
 __host__ __device__ constexpr int rollout_min_blocks(int HID, int E, int NT) {
     return (NT / E >= 16 && HID <= 64) ? (NT == 256 ? 2 : 3) : 1;
 }
-template <int SYS, typename R, int HID, int E, int NT>
+// SAFE: the SafeExplorer variant (safety layer between actor and env); a separate instantiation so that the default collector carries none of its code
+template <int SYS, typename R, int HID, int E, int NT, bool SAFE = false>
 __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_kernel(DevTables T, RolloutParams P) {
     constexpr int NX = SysDims<SYS>::NX, A = SysDims<SYS>::NU;
     constexpr int NZ = NX + 2 * A;             // z scratch rows: state, noisy action, clipped action
@@ -554,6 +606,8 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     __shared__ float s_stat[6 * E];            // FAST: episode statistics kept by the record helpers, handed back at the end
     __shared__ int s_epc[E];
     __shared__ NormState s_norm;
+    __shared__ float s_g[SAFE ? SCG_MAX_SAFETY * A * E : 1];       // safety layer: g_i(obs) of the current step
+    __shared__ float s_slack[SAFE ? SCG_MAX_SAFETY : 1];
     // table mode: per-env rows of the [K][N][P] episode table, staged by TMA bulk copies (one mbarrier per env and candidate slot)
     constexpr int PROW = SCG_MAX_INERTIAL + NX;
     __shared__ __align__(16) double s_row[SPLIT ? 2 * E * PROW : 2];
@@ -602,6 +656,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
         s_obs[tile_idx<E>(k, ee)] = (n0 + ee < N) ? obs_src[(size_t)(n0 + ee) * od + k] : 0.f;
     }
     if (P.norm) norm_load(&s_norm, P.norm, od, tid, NT);
+    if constexpr (SAFE) { if (tid < SCG_MAX_SAFETY) s_slack[tid] = P.safety_slack[tid]; }
     // (the normaliser switches are read from s_norm / the kernel parameters where they are needed: a flag kept in a register across the
     //  horizon loop costs the register-starved 3-D instantiations spills -- measured +10 % on C4)
     float ep_ret_sum = 0.f, ep_len_sum = 0.f, ep_cv_sum = 0.f; int ep_count = 0;
@@ -766,6 +821,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
         PROF_T(k1);
         SCG_TK(13);
         mlp_forward<HID, E, NT, A>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
+        if constexpr (SAFE) { safety_models<E, A>(P.safety, P.safety_C, P.safety_H, od, s_oc, s_g, tid, NT); __syncthreads(); }
         PROF_T(k2);
 
         // (b) env step.
@@ -780,12 +836,25 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
             SCG_TK(0);
             float act[A], logp = 0.f, val = 0.f;
             if (live) {
+                float mu[A];
+#pragma unroll
+                for (int k = 0; k < A; ++k) mu[k] = mlp_out<E, NW, A>(s_out, s_blob, L, k, ol);
+                if constexpr (SAFE) {                                        // SafeExplorer: project the mean action (safe_ppo_utils.py:88-104)
+                    R stc[NX]; double std_[NX]; float m2[A];
+                    Physics<SYS, R>::state(e, stc);
+#pragma unroll
+                    for (int k = 0; k < NX; ++k) std_[k] = (double)stc[k];
+#pragma unroll
+                    for (int k = 0; k < A; ++k) m2[k] = mu[k];
+                    safety_apply<NX, E, A>(std_, h->rows, P.safety_C, s_g, s_slack, ol, m2, P.out.d_c ? P.out.d_c + (tn0 + ol) * P.safety_C : nullptr);
+#pragma unroll
+                    for (int k = 0; k < A; ++k) mu[k] = m2[k];
+                }
 #pragma unroll
                 for (int k = 0; k < A; ++k) {
                     const float zk = gen_eps ? s_eps[(t & 1) * A * E + k * E + ol] : z[k];
-                    const float mu = mlp_out<E, NW, A>(s_out, s_blob, L, k, ol);
-                    act[k] = fmaf(sd[k], zk, mu);                         // Normal.sample (ppo_utils.py:228)
-                    const float d = act[k] - mu;
+                    act[k] = fmaf(sd[k], zk, mu[k]);                      // Normal.sample (ppo_utils.py:228)
+                    const float d = act[k] - mu[k];
                     logp += -(d * d) * inv2var[k] - lsd[k] - log_sqrt_2pi;   // distributions.py:12-21
                 }
                 val = mlp_out<E, NW, A>(s_out, s_blob, L, A, ol);

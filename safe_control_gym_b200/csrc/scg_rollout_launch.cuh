@@ -31,11 +31,11 @@ RolloutLaunchResult scg_rollout_quad3d_f32(const RolloutLaunch&, const scg_rollo
 #include "scg_rollout_tc.cuh"
 #define RL_CUDA(call) do { cudaError_t st_ = (call); if (st_ != cudaSuccess) return RolloutLaunchResult{SCG_ECUDA, st_, #call}; } while (0)
 
-template <int SYS, typename R, int HID, int E, int NT>
+template <int SYS, typename R, int HID, int E, int NT, bool SAFE = false>
 static RolloutLaunchResult launch_rollout(const RolloutLaunch& e, RolloutParams P, const scg_rollout_args* a, cudaStream_t s) {
     const RolloutSmem<HID, E> S(e.obs_dim, e.nu, e.L * e.nx * (int)(sizeof(R) / 4), NT / 64);
     const size_t smem = (size_t)S.total_floats * sizeof(float);
-    auto kern = rollout_kernel<SYS, R, HID, E, NT>;
+    auto kern = rollout_kernel<SYS, R, HID, E, NT, SAFE>;
     RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // the kernel lives out of shared memory (weights, tiles, tables): ask for the largest carve-out so several CTAs fit per SM
     RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -108,6 +108,10 @@ static RolloutLaunchResult dispatch_rollout(const RolloutLaunch& e, const scg_ro
     const int NTq = (a->envs_per_block >> 16) & 0xffff;   // requested threads per CTA (0 = 8 per env)
     (void)NTq;
 #ifndef SCG_PROF
+    if (a->safety_constraints > 0) {      // SafeExplorer collector: CUDA-core MLP, 32 envs per CTA, hidden 64 (the reference's default width)
+        if (a->hidden_dim != 64 || !(E == 0 || E == 32)) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: the safety-layer collector is built for hidden_dim 64, 32 envs per CTA"};
+        return launch_rollout<SYS, R, 64, 32, 256, true>(e, P, a, s);
+    }
     // mlp_engine: 0 = library default, 1 = CUDA cores (FFMA2), 2 = tensor cores (tcgen05, 3xTF32; hidden 64, 32 envs per CTA)
     // library default (SCG_MLP_AUTO): tensor cores for hidden 128 (where they win by a wide margin), CUDA cores for hidden 32 / 64
     // (measured: DESIGN.md 4); a configuration that does not fit the tensor-core kernel's shared-memory plan falls back to FFMA2

@@ -155,7 +155,7 @@ class EngineHandle:
 
     def rollout(self, policy_blob, dims, T, eps=None, activation='tanh', gamma=0.99, gae_lambda=0.95, use_gae=False,
                 deterministic=False, envs_per_block=0, want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode'), out=None,
-                flat=None, peer_byte_offsets=None, multicast_byte_offset=None, mlp_engine=None, norm=None, obs0=None):
+                flat=None, peer_byte_offsets=None, multicast_byte_offset=None, mlp_engine=None, norm=None, obs0=None, safety=None):
         '''One fused launch: T steps of policy + env for all N envs.  Returns PPOBuffer-shaped torch.cuda tensors.
 
         flat: optional caller-owned float32 buffer for the PPOBuffer keys (e.g. this rank's slot of a peer-mapped gathered buffer);
@@ -189,6 +189,8 @@ class EngineHandle:
             if 'last' in want:
                 out['last_obs'] = torch.empty(N, obs_dim, dtype=f32, device=dev)
                 out['last_val'] = torch.empty(N, 1, dtype=f32, device=dev)
+            if safety is not None:     # SafePPOBuffer 'c': the constraint values the safety layer saw at every step
+                out['c'] = torch.empty(T, N, int(safety['C']), dtype=f32, device=dev)
             if 'raw' in want:          # un-normalised observation / reward streams for the controller's running normalisers
                 out['obs_raw'] = torch.empty(T, N, obs_dim, dtype=f32, device=dev)
                 out['rew_raw'] = torch.empty(T, N, 1, dtype=f32, device=dev)
@@ -199,7 +201,7 @@ class EngineHandle:
                 out['ep_count'] = torch.empty(N, dtype=torch.int32, device=dev)
         ro = _abi.scg_rollout_out()
         for name in ('obs', 'act', 'rew', 'mask', 'v', 'logp', 'terminal_v', 'ret', 'adv', 'cviol', 'cvals', 'mse', 'last_obs', 'last_val',
-                     'ep_return_sum', 'ep_length_sum', 'ep_cviol_sum', 'ep_count', 'obs_raw', 'rew_raw'):
+                     'ep_return_sum', 'ep_length_sum', 'ep_cviol_sum', 'ep_count', 'obs_raw', 'rew_raw', 'c'):
             setattr(ro, 'd_' + name, out[name].data_ptr() if name in out else None)
         args = _abi.scg_rollout_args()
         args.T, args.obs_dim, args.act_dim, args.hidden_dim = int(T), int(obs_dim), int(act_dim), int(hid)
@@ -221,6 +223,13 @@ class EngineHandle:
             assert obs0.dtype == torch.float32 and obs0.is_cuda and tuple(obs0.shape) == (N, obs_dim), (obs0.dtype, obs0.shape)
             obs0 = obs0.contiguous()
         args.d_obs0 = obs0.data_ptr() if obs0 is not None else None
+        if safety is not None:
+            blob_s = safety['blob']
+            Cn, Hn = int(safety['C']), int(safety['H'])
+            assert blob_s.dtype == torch.float32 and blob_s.is_cuda and blob_s.is_contiguous() and blob_s.numel() == Cn * (Hn * obs_dim + Hn + act_dim * Hn + act_dim)
+            args.safety_constraints, args.safety_hidden, args.d_safety = Cn, Hn, blob_s.data_ptr()
+            for i, v in enumerate(safety['slack']):
+                args.safety_slack[i] = float(v)
         offs = list(peer_byte_offsets) if peer_byte_offsets is not None else out.get('_peer_byte_offsets', [])
         if len(offs) > _abi.SCG_MAX_PEERS:
             raise ValueError(f'at most {_abi.SCG_MAX_PEERS} peers')

@@ -182,7 +182,7 @@ def compare_rollouts(o, g, cfg, x_goal, N, T, obs_tol, max_fork_frac=0.02, keys_
     return proofs, worst
 
 
-def compare_replay(oracle, policy, g, N, T, tol=2e-5, gamma=0.99, gae_lambda=0.95, use_gae=True, max_tie_frac=0.002):
+def compare_replay(oracle, policy, g, N, T, tol=2e-5, gamma=0.99, gae_lambda=0.95, use_gae=True, max_tie_frac=0.002, **oracle_kw):
     '''TEACHER-FORCED parity: `oracle` (a fresh, reset Oracle of the same configuration) replays the engine's record `g` -- before every
     step its env state is overwritten with the record's observation and it is stepped with the record's action -- and every output
     of every one of the T x N transitions is compared with the oracle's one-step answer: sampled action (mean + sd * Philox normal),
@@ -191,13 +191,13 @@ def compare_replay(oracle, policy, g, N, T, tol=2e-5, gamma=0.99, gae_lambda=0.9
     differences), so it is tight at the full benchmark size.  done / constraint-violation mismatches need a tie proof.'''
     tonp = lambda t: t.detach().cpu().numpy() if hasattr(t, 'detach') else np.asarray(t)
     rec = {k: tonp(g[k]) for k in ('obs', 'act', 'mask')}
-    p = oracle.rollout(policy, T, eps=None, gamma=gamma, gae_lambda=gae_lambda, use_gae=use_gae, replay=rec)
+    p = oracle.rollout(policy, T, eps=None, gamma=gamma, gae_lambda=gae_lambda, use_gae=use_gae, replay=rec, **oracle_kw)
     cfg, nx = oracle.cfg, oracle.nx
     worst = {}
 
     def rel(a, b):
         return np.abs(a - b) / (1.0 + np.abs(b))
-    for k, t_ in (('act', 3e-5), ('v', 1e-5), ('logp', 1e-4), ('rew', tol), ('mse', tol), ('cvals', tol)):
+    for k, t_ in (('act', 3e-5), ('v', 1e-5), ('logp', 1e-4), ('rew', tol), ('mse', tol), ('cvals', tol), ('c', tol)):
         if k in g and k in p:
             d = rel(tonp(g[k]), p[k])
             worst[k] = float(d.max())

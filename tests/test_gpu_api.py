@@ -234,3 +234,41 @@ def test_ppo_run_matches_an_oracle_deterministic_rollout(tmp_path):
     np.testing.assert_allclose(ev['constraint_violation'], (oo['cviol'][..., 0] * live).sum(0), rtol=0, atol=0)
     np.testing.assert_allclose(ev['mse'], (oo['mse'][..., 0] * live).sum(0) / (first_done + 1), rtol=2e-4, atol=1e-5)
     ctrl.close()
+
+
+def test_batched_experiment_metrics_match_the_oracle(tmp_path):
+    '''BaseExperiment.run_evaluation + MetricExtractor (base_experiment.py:49-165,380-492) on the fused collector: every metric against the
+    same evaluation done step by step by the oracle.'''
+    from functools import partial
+
+    from oracle import oracle as orc
+    from safe_control_gym_b200 import configs
+    from safe_control_gym_b200.experiments.base_experiment import BaseExperiment, MetricExtractor
+    from safe_control_gym_b200.utils.registration import make
+    task = {k: v for k, v in configs.get('quadrotor_2D_track').items() if k != 'seed'}
+    ctrl = make('ppo', partial(make, 'quadrotor', **task), training=True, output_dir=str(tmp_path), seed=3, rollout_batch_size=64, rollout_steps=20,
+                mini_batch_size=256, opt_epochs=1)
+    ctrl.reset()
+    ctrl.train_step()
+    n_ep = 32
+    exp = BaseExperiment(ctrl)
+    data, metrics = exp.run_evaluation(n_episodes=n_ep)
+    env = H.make_env('quadrotor_2D_track')
+    T = int(env.CTRL_STEPS)
+    pol = orc.OraclePolicy.from_state_dict({k: v.detach().cpu() for k, v in ctrl.agent.ac.state_dict().items()}, 'tanh')
+    o = H.make_oracle(env, n_ep, auto_reset=True, rng_mode='philox', seed=ctrl.seed * 111)
+    o.reset()
+    oo = o.rollout(pol, T, deterministic=True)
+    mask = oo['mask'][..., 0]
+    first = np.where((mask == 0).any(0), (mask == 0).argmax(0), T - 1)
+    ref = {'length': [np.ones(f + 1) for f in first], 'reward': [oo['rew'][:f + 1, i, 0].astype(np.float64) for i, f in enumerate(first)],
+           'mse': [oo['mse'][:f + 1, i, 0].astype(np.float64) for i, f in enumerate(first)],
+           'constraint_violation': [oo['cviol'][:f + 1, i, 0].astype(np.float64) for i, f in enumerate(first)]}
+    mref = MetricExtractor().compute_metrics(ref)
+    for k in ('average_length', 'failure_rate', 'average_constraint_violation'):
+        assert metrics[k] == mref[k], k
+    for k in ('average_return', 'average_rmse', 'rmse_std', 'worst_case_rmse_at_0.5'):
+        np.testing.assert_allclose(metrics[k], mref[k], rtol=2e-4, atol=1e-6, err_msg=k)
+    assert len(data['obs']) == n_ep and data['obs'][0].shape[1] == 12
+    exp.close()
+    ctrl.close()

@@ -115,3 +115,24 @@ def test_trajectory_generators():
     with pytest.raises(ValueError, match='Trajectory type'):
         H.make_env('quadrotor', task='traj_tracking', task_info={'trajectory_type': 'spiral', 'num_cycles': 1, 'trajectory_plane': 'xz',
                                                                    'trajectory_position_offset': [0, 0], 'trajectory_scale': 1})
+
+
+def test_metric_extractor_on_reference_style_and_batched_data():
+    '''MetricExtractor (base_experiment.py:380-492): the same numbers from the reference's layout (lists of per-step info dicts) and from the
+    batched harness' per-episode arrays; compute_cvar as performance_metrics.py:6-33.'''
+    from safe_control_gym_b200.experiments.base_experiment import MetricExtractor, compute_cvar
+    rng = np.random.default_rng(0)
+    lens = [5, 9, 3, 7]
+    eps = [{'rew': rng.random(L), 'mse': rng.random(L), 'cv': (rng.random(L) < 0.3).astype(float)} for L in lens]
+    batched = {'length': [np.ones(L, dtype=np.int64) for L in lens], 'reward': [e['rew'] for e in eps], 'mse': [e['mse'] for e in eps],
+               'constraint_violation': [e['cv'] for e in eps]}
+    ref_style = {'length': [np.ones(L) for L in lens], 'reward': [e['rew'] for e in eps],
+                 'info': [[{'mse': e['mse'][t], 'constraint_violation': e['cv'][t]} for t in range(L)] for e, L in zip(eps, lens)]}
+    ma, mb = MetricExtractor().compute_metrics(batched), MetricExtractor().compute_metrics(ref_style)
+    for k in ma:
+        np.testing.assert_allclose(np.asarray(ma[k], dtype=float), np.asarray(mb[k], dtype=float), rtol=1e-12)
+    rmse = np.array([np.sqrt(e['mse'].mean()) for e in eps])
+    np.testing.assert_allclose(ma['average_rmse'], rmse.mean())
+    np.testing.assert_allclose(ma['worst_case_rmse_at_0.5'], np.sort(rmse)[-2:].mean())
+    np.testing.assert_allclose(ma['failure_rate'], np.mean([float(e['cv'].any()) for e in eps]))
+    assert compute_cvar(np.arange(10.0), 0.3) == 1.0
