@@ -22,6 +22,7 @@
  *   scg_rollout                   <-  PPO.train_step collector loop  safe_control_gym/controllers/ppo/ppo.py:259-297
  *                                     MLPActorCritic.step  safe_control_gym/controllers/ppo/ppo_utils.py:224-231
  *                                     compute_returns_and_advantages  ppo_utils.py:374-400
+ *   scg_set_adversary_control     <-  BenchmarkEnv.set_adversary_control  benchmark_env.py:216-228 (RARL rarl.py:365-368)
  *   scg_get_state / scg_set_state <-  PPO.save/load env state  ppo.py:112-148, dummy_vec_env.py:68-74
  *
  * Conventions
@@ -46,7 +47,7 @@
 extern "C" {
 #endif
 
-#define SCG_ABI_VERSION 3
+#define SCG_ABI_VERSION 4
 
 #define SCG_MAX_NX 12          /* max state dim (Quadrotor-3D) */
 #define SCG_MAX_NU 4           /* max action dim */
@@ -56,6 +57,7 @@ extern "C" {
 #define SCG_MAX_DIST_DIM 12    /* dim of a disturbance target */
 #define SCG_MAX_CON_ROWS 96    /* scalar constraint rows */
 #define SCG_MAX_CON_NNZ 512    /* non-zeros over all constraint rows */
+#define SCG_MAX_ADV 4          /* max dim of an adversary action (= dim of the disturbance mode it drives) */
 
 /* error codes */
 #define SCG_OK 0
@@ -96,6 +98,18 @@ extern "C" {
 #define SCG_MODE_ACTION 0
 #define SCG_MODE_DYNAMICS 1
 #define SCG_MODE_OBSERVATION 2
+
+/* physics update of the quadrotor (Physics enum, gym_pybullet_drones/base_aviary.py:32-40; dispatch :243-268) */
+#define SCG_PHYS_PYB 0
+#define SCG_PHYS_PYB_GND 1          /* + ground effect  (base_aviary.py:386-418) */
+#define SCG_PHYS_PYB_DRAG 2         /* + drag           (base_aviary.py:420-440) */
+#define SCG_PHYS_PYB_DW 3           /* + downwash: with ONE drone delta_z = pos[2] - pos[2] = 0, so no force is ever applied (base_aviary.py:442-460) */
+#define SCG_PHYS_PYB_GND_DRAG_DW 4
+
+/* adversary disturbance set from outside the env (BenchmarkEnv.set_adversary_control, benchmark_env.py:216-228) */
+#define SCG_ADV_NONE 0
+#define SCG_ADV_ACTION 1            /* added to the physical action after the passive action disturbances (quadrotor.py:737-738, cartpole.py:494-495) */
+#define SCG_ADV_DYNAMICS 2          /* added to the external force / tap force, consumed by the step (quadrotor.py:416-425, cartpole.py:543-551) */
 
 /* distribution kinds for in-kernel (Philox) reset randomisation */
 #define SCG_RAND_NONE 0
@@ -198,6 +212,15 @@ typedef struct scg_config {
     int32_t n_dist[3];
     int32_t _pad1;
     scg_disturbance dist[3][SCG_MAX_DIST];
+
+    /* non-default quadrotor physics (base_aviary.py:386-460; coefficients from cf2x.urdf:5) */
+    int32_t physics;           /* SCG_PHYS_* */
+    /* adversary (RARL / RAP): adv_action = clip(a, -1, 1) * scale + offset (benchmark_env.py:223-224); its dim is the dim of the
+     * disturbance mode it drives (action: nu; dynamics: cartpole 2, quad 1D/2D/3D 1/2/3; benchmark_env.py:289-295) */
+    int32_t adversary_mode;    /* SCG_ADV_* */
+    double adversary_scale, adversary_offset;
+    double gnd_eff_coeff, prop_radius, gnd_eff_h_clip;   /* base_aviary.py:130-131,406-408 */
+    double drag_coeff_xy, drag_coeff_z;                  /* base_aviary.py:433-435 */
 } scg_config;
 
 /* Outputs of one control step for N envs.  Any pointer may be NULL (skipped).
@@ -301,6 +324,16 @@ typedef struct scg_rollout_args {
     int32_t safety_hidden;
     const float* d_safety;
     double safety_slack[SCG_MAX_SAFETY];
+    /* Adversary of the RARL / RAP collectors (safe_control_gym/controllers/rarl/rarl.py:349-418, rap.py): a second actor-critic that sees the
+     * same observation; its sampled action goes through set_adversary_control (clip, scale, offset) into the env step of the same control
+     * step.  d_adv_policy = NULL: no adversary.  The blob has the scg_policy_pack() layout with act_dim = adv_act_dim (which must equal
+     * scg_adversary_dim()) and the same hidden_dim / activation as the protagonist.  adv_record = 0: the record is the protagonist's
+     * (act, v, logp, rew, terminal_v / bootstrap from its critic); 1: the adversary's (its act [T][N][adv_act_dim], v, logp, rew = -rew,
+     * terminal_v / bootstrap from ITS critic; rarl.py:391-399).  d_eps_adv: [T][N][adv_act_dim] standard normals or NULL -> Philox. */
+    const float* d_adv_policy;
+    const float* d_eps_adv;
+    int32_t adv_act_dim;
+    int32_t adv_record;
 } scg_rollout_args;
 
 typedef struct scg_env scg_env;   /* opaque, one per (device, batch) */
@@ -330,6 +363,11 @@ int  scg_reset(scg_env* env, const uint8_t* d_mask /*[N] or NULL = all*/, float*
 int  scg_step(scg_env* env, const float* d_act /*[N][nu] nullable*/, const double* d_act_f64 /*[N][nu] nullable*/,
               const scg_step_out* out, void* stream);
 int  scg_rollout(scg_env* env, const scg_rollout_args* args, const scg_rollout_out* out, void* stream);
+/* BenchmarkEnv.set_adversary_control (benchmark_env.py:216-228) for all N envs: d_adv [N][scg_adversary_dim()] raw adversary actions.
+ * The clipped, scaled action is kept on the device and applied by the next scg_step (dynamics mode: consumed by that step; action mode:
+ * kept until the env resets, like the reference attribute).  SCG_ESTATE ("adversary_disturbance does not exist") without an adversary. */
+int  scg_set_adversary_control(scg_env* env, const float* d_adv, void* stream);
+int  scg_adversary_dim(const scg_env* env);   /* 0 = the env has no adversary */
 
 /* policy blob helpers (host side, pure functions) */
 int  scg_policy_blob_floats(int32_t obs_dim, int32_t act_dim, int32_t hidden_dim);

@@ -40,6 +40,9 @@ def lib():
         _lib.scg_oracle_rollout.restype = C.c_int
         _lib.scg_oracle_step.restype = C.c_int
         _lib.scg_oracle_num_threads.restype = C.c_int
+        _lib.scg_oracle_adversary_dim.restype = C.c_int
+        _lib.scg_oracle_adversary_dim.argtypes = [C.c_void_p]
+        _lib.scg_oracle_set_adversary_control.restype = C.c_int
     return _lib
 
 
@@ -61,7 +64,8 @@ class _RolloutOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('obs', 'act', 'rew', 'mask', 'v', 'logp', 'terminal_v', 'ret', 'adv', 'cviol', 'cvals', 'mse',
                                          'last_obs', 'last_val', 'ep_return_sum', 'ep_length_sum', 'ep_cviol_sum', 'ep_count',
                                          'state_trace', 'replay_obs', 'replay_act', 'replay_mask', 'next_obs', 'norm', 'obs0', 'obs_raw', 'rew_raw')] + \
-        [('safety_C', C.c_int), ('safety_H', C.c_int), ('safety', C.c_void_p), ('safety_slack', C.c_void_p), ('c', C.c_void_p)]
+        [('safety_C', C.c_int), ('safety_H', C.c_int), ('safety', C.c_void_p), ('safety_slack', C.c_void_p), ('c', C.c_void_p),
+         ('adv_policy', C.c_void_p), ('eps_adv', C.c_void_p), ('adv_record', C.c_int)]
 
 
 class OraclePolicy:
@@ -157,6 +161,17 @@ class Oracle:
         self.lib.scg_oracle_reset(self.h, _p(m), _p(obs), _p(st))
         return {'obs': obs, 'state': st}
 
+    @property
+    def adversary_dim(self):
+        return int(self.lib.scg_oracle_adversary_dim(self.h))
+
+    def set_adversary_control(self, adv):
+        '''BenchmarkEnv.set_adversary_control for all envs (raw adversary actions [N][adversary_dim]).'''
+        adv = np.ascontiguousarray(adv, dtype=np.float64).reshape(self.N, -1)
+        rc = self.lib.scg_oracle_set_adversary_control(self.h, _p(adv))
+        if rc == -3:
+            raise RuntimeError('[ERROR] adversary_disturbance does not exist, env.set_adversary_control() cannot be called.')
+
     def step(self, act):
         act = np.ascontiguousarray(act, dtype=np.float64).reshape(self.N, self.nu)
         N, od, nx, nc = self.N, self.obs_dim, self.nx, max(self.n_con, 1)
@@ -174,13 +189,15 @@ class Oracle:
             raise RuntimeError('[ERROR] You must call env.reset() at least once before using env.step().')
         return o
 
-    def rollout(self, policy, T, eps=None, deterministic=False, gamma=0.99, gae_lambda=0.95, use_gae=False, trace=False, replay=None, norm=None, obs0=None, safety=None):
+    def rollout(self, policy, T, eps=None, deterministic=False, gamma=0.99, gae_lambda=0.95, use_gae=False, trace=False, replay=None, norm=None, obs0=None, safety=None,
+                adversary=None, eps_adv=None, adv_record=False):
         '''replay = {'obs', 'act', 'mask'} (float32 [T][N][.] arrays of another collector's record): teacher-forced one-step predictions,
         see oracle_rollout_out in scg_oracle.c.'''
         N, od, A, nc = self.N, self.obs_dim, self.nu, self.n_con
         f = np.float32
+        Arec = adversary.act_dim if (adversary is not None and adv_record) else A      # rarl.py:352: the adversary's PPOBuffer
         o = {
-            'obs': np.empty((T, N, od), f), 'act': np.empty((T, N, A), f), 'rew': np.empty((T, N, 1), f), 'mask': np.empty((T, N, 1), f),
+            'obs': np.empty((T, N, od), f), 'act': np.empty((T, N, Arec), f), 'rew': np.empty((T, N, 1), f), 'mask': np.empty((T, N, 1), f),
             'v': np.empty((T, N, 1), f), 'logp': np.empty((T, N, 1), f), 'terminal_v': np.empty((T, N, 1), f),
             'ret': np.empty((T, N, 1), f), 'adv': np.empty((T, N, 1), f), 'cviol': np.empty((T, N, 1), f), 'mse': np.empty((T, N, 1), f),
             'last_obs': np.empty((N, od), f), 'last_val': np.empty((N, 1), f),
@@ -216,6 +233,12 @@ class Oracle:
             ro.safety_C, ro.safety_H = int(safety['C']), int(safety['H'])
         e = None if eps is None else np.ascontiguousarray(eps, dtype=np.float32).reshape(T, N, A)
         ps = policy.c_struct()
+        if adversary is not None:       # an OraclePolicy with act_dim = adversary_dim (RARL / RAP, rarl.py:349-418)
+            assert adversary.act_dim == self.adversary_dim and adversary.obs_dim == od
+            qs = adversary.c_struct(); keep.append(qs)
+            ro.adv_policy = C.addressof(qs); ro.adv_record = int(bool(adv_record))
+            if eps_adv is not None:
+                keep.append(np.ascontiguousarray(eps_adv, dtype=np.float32).reshape(T, N, adversary.act_dim)); ro.eps_adv = keep[-1].ctypes.data
         rc = self.lib.scg_oracle_rollout(self.h, C.byref(ps), _p(e), C.c_int(T), C.c_int(int(deterministic)), C.c_double(gamma),
                                          C.c_double(gae_lambda), C.c_int(int(use_gae)), C.byref(ro))
         if rc != 0:

@@ -70,6 +70,7 @@ void scg_oracle_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, 
 #define STREAM_STEP 2u
 #define STREAM_POLICY 3u
 #define STREAM_RESET 4u
+#define STREAM_ADVERSARY 5u   /* sampling noise of the RARL / RAP adversary policy */
 
 /* draw slot j of (stream, idx) = words 2(j&1), 2(j&1)+1 of Philox block j>>1: counter = (j>>1, idx, global env, stream) */
 static void draw_words(uint64_t seed, uint32_t stream, uint32_t genv, uint32_t idx, uint32_t slot, uint32_t* w0, uint32_t* w1) {
@@ -111,6 +112,8 @@ typedef struct {
     uint32_t total_steps;           /* control steps taken since creation */
     int dist_offset[3][SCG_MAX_DIST];
     double ep_return, ep_length, ep_cviol;
+    double adv_action[SCG_MAX_ADV]; /* self.adv_action (BE:224); adv_set = 0 <=> None */
+    int adv_set;
 } oenv;
 
 typedef struct scg_oracle {
@@ -269,10 +272,38 @@ static void quad_substep(const scg_config* c, oenv* e, const double rpm[4], cons
     /* prop link CoM offsets (cf2x.urdf:42,54,66,78): r x F with F = (0,0,f) in the body frame */
     const double a = c->arm;
     const double rx[4] = {a, -a, -a, a}, ry[4] = {a, a, -a, -a};
+    const int gnd = c->physics == SCG_PHYS_PYB_GND || c->physics == SCG_PHYS_PYB_GND_DRAG_DW;
+    const int drag = c->physics == SCG_PHYS_PYB_DRAG || c->physics == SCG_PHYS_PYB_GND_DRAG_DW;
+    /* Physics.PYB_DW: _downwash() compares the drone with ITSELF (delta_z = pos[2] - pos[2] = 0, BA:448-451): never a force. */
+    if (gnd) {
+        /* _ground_effect (BA:386-418): kinematic info is refreshed at the start of every sub-step (BA:246-251); per-propeller force
+         * KF rpm^2 GND_EFF_COEFF (PROP_RADIUS / (4 h_i))^2 along the LINK z axis at the prop link, h_i = world height of prop link i
+         * clipped from below, only while |roll| and |pitch| < pi/2.  Same application point and direction as the thrust: f_i grows. */
+        double rpy[3]; rpy_from_quat(e->quat, rpy);
+        if (fabs(rpy[0]) < PI_D / 2 && fabs(rpy[1]) < PI_D / 2) {
+            for (int i = 0; i < 4; ++i) {
+                double h = e->pos[2] + R[6] * rx[i] + R[7] * ry[i];
+                if (h < c->gnd_eff_h_clip) h = c->gnd_eff_h_clip;
+                const double q = c->prop_radius / (4 * h);
+                f[i] += rpm[i] * rpm[i] * c->kf * c->gnd_eff_coeff * q * q;
+            }
+        }
+    }
     double tau_b[3] = {0, 0, z_torque}, thrust = 0;
     for (int i = 0; i < 4; ++i) { tau_b[0] += ry[i] * f[i]; tau_b[1] += -rx[i] * f[i]; thrust += f[i]; }
     /* world force: thrust along body z + gravity + disturbance (BA:271-279, WORLD_FRAME through the CoM) */
     double F[3] = {R[2] * thrust, R[5] * thrust, R[8] * thrust - m * c->gravity};
+    if (drag) {
+        /* _drag (BA:420-440): drag_factors = -DRAG_COEFF * sum(2 pi rpm / 60); the reference rotates (drag_factors * vel_world) by the
+         * base rotation and then applies the result as a LINK_FRAME force at the CoM link, i.e. it is rotated once more: R R (k v). */
+        double srpm = 0; for (int i = 0; i < 4; ++i) srpm += 2 * PI_D * rpm[i] / 60;
+        const double k[3] = {-c->drag_coeff_xy * srpm, -c->drag_coeff_xy * srpm, -c->drag_coeff_z * srpm};
+        const double kv[3] = {k[0] * e->vel[0], k[1] * e->vel[1], k[2] * e->vel[2]};
+        double d1[3], d2[3];
+        for (int r = 0; r < 3; ++r) d1[r] = R[3 * r] * kv[0] + R[3 * r + 1] * kv[1] + R[3 * r + 2] * kv[2];
+        for (int r = 0; r < 3; ++r) d2[r] = R[3 * r] * d1[0] + R[3 * r + 1] * d1[1] + R[3 * r + 2] * d1[2];
+        F[0] += d2[0]; F[1] += d2[1]; F[2] += d2[2];
+    }
     if (has_dist) { F[0] += fdist[0]; F[1] += fdist[1]; F[2] += fdist[2]; }
     /* body rates and Euler's equation with the gyroscopic term (btMultiBody m_useGyroTerm = true) */
     double wb[3] = {R[0] * e->omega[0] + R[3] * e->omega[1] + R[6] * e->omega[2],
@@ -447,6 +478,7 @@ static void env_reset(scg_oracle* o, int i) {
     const int k = e->episode;
     const double* row = (c->rng_mode == SCG_RNG_TABLE && o->ep_table) ? o->ep_table + ((size_t)(k % o->K) * c->num_envs + i) * o->P : NULL;
     e->initial_reset = 1; e->ctrl_step = 0; e->pyb_step = 0;
+    e->adv_set = 0;                                                               /* BE:338-339: self.adv_action = None */
     /* disturbance reset draws (BE:336-337, DI:102-106,148-151) */
     int slot = 0;
     for (int m = 0; m < 3; ++m)
@@ -551,6 +583,7 @@ static void env_step(scg_oracle* o, int i, const double* action, const double* n
         /* CP:479-502 */
         for (int k = 0; k < nu; ++k) u[k] = c->normalized_action ? c->hover_thrust * action[k] : action[k];
         apply_disturbances(o, e, SCG_MODE_ACTION, u, nu, &ns);
+        if (c->adversary_mode == SCG_ADV_ACTION && e->adv_set) for (int k = 0; k < nu; ++k) u[k] += e->adv_action[k];   /* CP:494-495 (not cleared) */
         for (int k = 0; k < nu; ++k) {
             e->noisy_act[k] = u[k];
             double f = u[k]; if (f < c->act_low[k]) f = c->act_low[k]; if (f > c->act_high[k]) f = c->act_high[k];
@@ -558,11 +591,16 @@ static void env_step(scg_oracle* o, int i, const double* action, const double* n
         }
         double tap[2] = {0, 0}; int has_tap = c->n_dist[SCG_MODE_DYNAMICS] > 0;
         if (has_tap) apply_disturbances(o, e, SCG_MODE_DYNAMICS, tap, 2, &ns);
+        if (c->adversary_mode == SCG_ADV_DYNAMICS) {                              /* CP:543-551: added, then cleared */
+            has_tap = 1;
+            if (e->adv_set) { tap[0] += e->adv_action[0]; tap[1] += e->adv_action[1]; e->adv_set = 0; }
+        }
         for (int s = 0; s < steps; ++s) cartpole_substep(c, e, e->clipped_act[0], tap, has_tap, dt);
     } else {
         /* QD:722-747 */
         for (int k = 0; k < nu; ++k) u[k] = c->normalized_action ? (1 + c->norm_act_scale * action[k]) * c->hover_thrust : action[k];
         apply_disturbances(o, e, SCG_MODE_ACTION, u, nu, &ns);
+        if (c->adversary_mode == SCG_ADV_ACTION && e->adv_set) for (int k = 0; k < nu; ++k) u[k] += e->adv_action[k];   /* QD:737-738 */
         double thrust[SCG_MAX_NU];
         for (int k = 0; k < nu; ++k) {
             e->noisy_act[k] = u[k];
@@ -589,6 +627,16 @@ static void env_step(scg_oracle* o, int i, const double* action, const double* n
             int ddim = c->system == SCG_SYS_QUAD1D ? 1 : c->system == SCG_SYS_QUAD2D ? 2 : 3;
             apply_disturbances(o, e, SCG_MODE_DYNAMICS, t, ddim, &ns);
             if (ddim == 1) { fd[2] = t[0]; } else if (ddim == 2) { fd[0] = t[0]; fd[2] = t[1]; } else { fd[0] = t[0]; fd[1] = t[1]; fd[2] = t[2]; }
+        }
+        if (c->adversary_mode == SCG_ADV_DYNAMICS) {                              /* QD:416-425: added to the force, then cleared */
+            has_dist = 1;
+            if (e->adv_set) {
+                const double* av = e->adv_action;
+                if (c->system == SCG_SYS_QUAD1D) fd[2] += av[0];
+                else if (c->system == SCG_SYS_QUAD2D) { fd[0] += av[0]; fd[2] += av[1]; }
+                else { fd[0] += av[0]; fd[1] += av[1]; fd[2] += av[2]; }
+                e->adv_set = 0;
+            }
         }
         for (int s = 0; s < steps; ++s) quad_substep(c, e, rpm, fd, has_dist, dt);
     }
@@ -720,6 +768,31 @@ int scg_oracle_step(scg_oracle* o, const double* act /*[N][nu]*/, const oracle_s
 }
 
 
+/* BenchmarkEnv.set_adversary_control (BE:216-228); adversary dim = dim of the disturbance mode it drives (BE:289-295) */
+int scg_oracle_adversary_dim(const scg_oracle* o) {
+    const scg_config* c = &o->cfg;
+    if (c->adversary_mode == SCG_ADV_ACTION) return o->nu;
+    if (c->adversary_mode == SCG_ADV_DYNAMICS) return c->system == SCG_SYS_CARTPOLE ? 2 : c->system == SCG_SYS_QUAD1D ? 1 : c->system == SCG_SYS_QUAD2D ? 2 : 3;
+    return 0;
+}
+static void set_adversary(const scg_oracle* o, oenv* e, const double* a) {
+    const scg_config* c = &o->cfg; const int d = scg_oracle_adversary_dim(o);
+    for (int k = 0; k < d; ++k) {
+        /* the adversary's action is a float32 array (torch -> numpy); `clipped * scale + offset` with python-float scale / offset stays
+         * float32 (NEP 50 weak scalars), and is promoted to float64 when it is added to the force / action */
+        float v = (float)a[k]; v = v < -1.0f ? -1.0f : v > 1.0f ? 1.0f : v;      /* adversary_action_space = Box(-1, 1) */
+        v = v * (float)c->adversary_scale; v = v + (float)c->adversary_offset;
+        e->adv_action[k] = (double)v;
+    }
+    e->adv_set = 1;
+}
+int scg_oracle_set_adversary_control(scg_oracle* o, const double* adv /*[N][dim]*/) {
+    const int d = scg_oracle_adversary_dim(o);
+    if (d == 0) return SCG_ESTATE;                                               /* RuntimeError: adversary_disturbance does not exist */
+    for (int i = 0; i < o->cfg.num_envs; ++i) set_adversary(o, &o->envs[i], adv + (size_t)i * d);
+    return SCG_OK;
+}
+
 /* direct state injection for unit tests of the physics (bypasses reset randomisation) */
 void scg_oracle_set_env_state(scg_oracle* o, int i, const double* state, const double* inertial) {
     oenv* e = &o->envs[i]; const scg_config* c = &o->cfg;
@@ -808,6 +881,10 @@ typedef struct {
     const float* safety;
     const double* safety_slack;
     float* c;              /* [T][N][safety_C] constraint values fed to the safety layer */
+    /* RARL / RAP adversary (rarl.py:349-418): second actor-critic on the same observation; adv_record: the record is the adversary's */
+    const oracle_policy* adv_policy;
+    const float* eps_adv;  /* [T][N][adv_dim] or NULL -> Philox stream ADVERSARY */
+    int adv_record;
 } oracle_rollout_out;
 
 /* PPO.train_step collector loop (PPO:259-297) + compute_returns_and_advantages (PU:374-400) */
@@ -873,6 +950,24 @@ int scg_oracle_rollout(scg_oracle* o, const oracle_policy* p, const float* eps /
                 float d = act[k] - mean[k];
                 logp += -(d * d) / (2 * sd * sd) - p->logstd[k] - log_sqrt_2pi; /* distributions.py:12-21 */
             }
+            /* adversary action of the same observation (rarl.py:362-367): sampled like the protagonist's, then set_adversary_control */
+            const oracle_policy* q = out->adv_policy; const int A2 = q ? q->act_dim : 0;
+            float act2[SCG_MAX_ADV], val2 = 0, logp2 = 0;
+            if (q) {
+                float mean2[SCG_MAX_ADV];
+                mlp_forward(q->aw, q->ab, od, q->hidden, A2, q->activation, obs_f, mean2);
+                mlp_forward(q->cw, q->cb, od, q->hidden, 1, q->activation, obs_f, &val2);
+                double advd[SCG_MAX_ADV];
+                for (int k = 0; k < A2; ++k) {
+                    float sd = expf(q->logstd[k]), z = 0;
+                    if (!deterministic) z = out->eps_adv ? out->eps_adv[tn * A2 + k] : (float)draw_normal(c->seed, STREAM_ADVERSARY, genv, e->total_steps, (uint32_t)k);
+                    act2[k] = mean2[k] + sd * z;
+                    float d = act2[k] - mean2[k];
+                    logp2 += -(d * d) / (2 * sd * sd) - q->logstd[k] - log_sqrt_2pi;
+                    advd[k] = (double)act2[k];
+                }
+                set_adversary(o, e, advd);
+            }
             double actd[SCG_MAX_NU]; for (int k = 0; k < A; ++k) actd[k] = replay ? (double)out->replay_act[tn * A + k] : (double)act[k];
             const double* nrow = (c->rng_mode == SCG_RNG_TABLE && o->noise_table && o->D > 0)
                                  ? o->noise_table + ((size_t)((o->noise_cursor + t) % o->Tn) * N + i) * o->D : NULL;
@@ -887,7 +982,8 @@ int scg_oracle_rollout(scg_oracle* o, const oracle_policy* p, const float* eps /
             if (inf.done) {
                 if (inf.truncated) {                                          /* PPO:274-283 */
                     float tobs[SCG_MAX_OBS]; for (int k = 0; k < od; ++k) tobs[k] = (float)nobs[k];
-                    mlp_forward(p->cw, p->cb, od, p->hidden, 1, p->activation, tobs, &term_v);
+                    if (q && out->adv_record) mlp_forward(q->cw, q->cb, od, q->hidden, 1, q->activation, tobs, &term_v);   /* rarl.py:385-386 */
+                    else mlp_forward(p->cw, p->cb, od, p->hidden, 1, p->activation, tobs, &term_v);
                 }
                 if (out->ep_count) { out->ep_count[i] += 1; out->ep_return_sum[i] += (float)e->ep_return; out->ep_length_sum[i] += (float)e->ep_length; out->ep_cviol_sum[i] += (float)e->ep_cviol; }
                 e->ep_return = 0; e->ep_length = 0; e->ep_cviol = 0;
@@ -904,14 +1000,18 @@ int scg_oracle_rollout(scg_oracle* o, const oracle_policy* p, const float* eps /
             float rew_rec = (float)inf.rew;
             if (norm_rew) { double y = (double)rew_rec * nm[2 * od + 2]; y = y < -nm[2 * od + 3] ? -nm[2 * od + 3] : y; y = y > nm[2 * od + 3] ? nm[2 * od + 3] : y; rew_rec = (float)y; }
             for (int k = 0; k < od; ++k) out->obs[tn * od + k] = obs_f[k];
-            for (int k = 0; k < A; ++k) out->act[tn * A + k] = act[k];
+            if (q && out->adv_record) {                                       /* rarl.py:391-399: act_adv, -rew, v_adv, logp_adv */
+                for (int k = 0; k < A2; ++k) out->act[tn * A2 + k] = act2[k];
+                rew_rec = -rew_rec; val = val2; logp = logp2;
+            } else for (int k = 0; k < A; ++k) out->act[tn * A + k] = act[k];
             out->rew[tn] = rew_rec; out->mask[tn] = (replay ? own_done : inf.done) ? 0.f : 1.f; out->v[tn] = val; out->logp[tn] = logp; out->terminal_v[tn] = term_v;
             if (out->cviol) out->cviol[tn] = (float)inf.cviol;
             if (out->cvals && nc > 0) for (int k = 0; k < nc; ++k) out->cvals[tn * nc + k] = (float)cv[k];
             if (out->mse) out->mse[tn] = (float)inf.mse;
         }
         float lobs[SCG_MAX_OBS], lval; for (int k = 0; k < od; ++k) lobs[k] = (float)e->obs[k];
-        mlp_forward(p->cw, p->cb, od, p->hidden, 1, p->activation, lobs, &lval);
+        if (out->adv_policy && out->adv_record) mlp_forward(out->adv_policy->cw, out->adv_policy->cb, od, out->adv_policy->hidden, 1, out->adv_policy->activation, lobs, &lval);   /* rarl.py:407-408 */
+        else mlp_forward(p->cw, p->cb, od, p->hidden, 1, p->activation, lobs, &lval);
         if (out->last_obs) for (int k = 0; k < od; ++k) out->last_obs[(size_t)i * od + k] = lobs[k];
         if (out->last_val) out->last_val[i] = lval;
         if (out->ret && out->adv) {

@@ -8,7 +8,7 @@ raises if `libscg_b200.so` is missing or cannot be loaded.
 import ctypes as C
 import os
 
-SCG_ABI_VERSION = 3
+SCG_ABI_VERSION = 4
 SCG_MAX_PEERS = 8
 SCG_MAX_SAFETY = 16
 SCG_MAX_NX = 12
@@ -19,6 +19,7 @@ SCG_MAX_DIST = 4
 SCG_MAX_DIST_DIM = 12
 SCG_MAX_CON_ROWS = 96
 SCG_MAX_CON_NNZ = 512
+SCG_MAX_ADV = 4
 
 SCG_OK, SCG_EINVAL, SCG_ECUDA, SCG_ESTATE, SCG_ENOMEM = 0, -1, -2, -3, -4
 
@@ -32,6 +33,9 @@ SCG_MODE_ACTION, SCG_MODE_DYNAMICS, SCG_MODE_OBSERVATION = 0, 1, 2
 SCG_RAND_NONE, SCG_RAND_UNIFORM, SCG_RAND_NORMAL = 0, 1, 2
 SCG_ACT_TANH, SCG_ACT_RELU, SCG_ACT_LEAKY_RELU = 0, 1, 2
 SCG_CON_LINEAR, SCG_CON_ABS, SCG_CON_QUAD = 0, 1, 2
+SCG_PHYS_PYB, SCG_PHYS_PYB_GND, SCG_PHYS_PYB_DRAG, SCG_PHYS_PYB_DW, SCG_PHYS_PYB_GND_DRAG_DW = 0, 1, 2, 3, 4
+PHYSICS = {'pyb': SCG_PHYS_PYB, 'pyb_gnd': SCG_PHYS_PYB_GND, 'pyb_drag': SCG_PHYS_PYB_DRAG, 'pyb_dw': SCG_PHYS_PYB_DW, 'pyb_gnd_drag_dw': SCG_PHYS_PYB_GND_DRAG_DW}
+SCG_ADV_NONE, SCG_ADV_ACTION, SCG_ADV_DYNAMICS = 0, 1, 2
 SCG_MLP_AUTO, SCG_MLP_FFMA2, SCG_MLP_TCGEN05, SCG_MLP_TCGEN05_TF32 = 0, 1, 2, 3
 MLP_ENGINES = {'auto': SCG_MLP_AUTO, 'ffma2': SCG_MLP_FFMA2, 'tcgen05': SCG_MLP_TCGEN05, 'tcgen05_tf32': SCG_MLP_TCGEN05_TF32}
 
@@ -77,6 +81,9 @@ class scg_config(C.Structure):
         ('init_rand_a', _dbl_nx), ('init_rand_b', _dbl_nx), ('inertial_rand_a', _dbl_in), ('inertial_rand_b', _dbl_in),
         ('n_dist', C.c_int32 * 3), ('_pad1', C.c_int32),
         ('dist', (scg_disturbance * SCG_MAX_DIST) * 3),
+        ('physics', C.c_int32), ('adversary_mode', C.c_int32), ('adversary_scale', C.c_double), ('adversary_offset', C.c_double),
+        ('gnd_eff_coeff', C.c_double), ('prop_radius', C.c_double), ('gnd_eff_h_clip', C.c_double),
+        ('drag_coeff_xy', C.c_double), ('drag_coeff_z', C.c_double),
     ]
 
 
@@ -101,6 +108,7 @@ class scg_rollout_args(C.Structure):
         ('n_peers', C.c_int32), ('mlp_engine', C.c_int32), ('peer_byte_offset', C.c_int64 * SCG_MAX_PEERS),
         ('multicast_byte_offset', C.c_int64), ('d_norm', C.c_void_p), ('d_obs0', C.c_void_p),
         ('safety_constraints', C.c_int32), ('safety_hidden', C.c_int32), ('d_safety', C.c_void_p), ('safety_slack', C.c_double * SCG_MAX_SAFETY),
+        ('d_adv_policy', C.c_void_p), ('d_eps_adv', C.c_void_p), ('adv_act_dim', C.c_int32), ('adv_record', C.c_int32),
     ]
 
 
@@ -134,6 +142,8 @@ _SYMBOLS = {
     'scg_reset': (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     'scg_step': (C.c_int, [_VP, _VP, _VP, C.POINTER(scg_step_out), _VP]),
     'scg_rollout': (C.c_int, [_VP, C.POINTER(scg_rollout_args), C.POINTER(scg_rollout_out), _VP]),
+    'scg_set_adversary_control': (C.c_int, [_VP, _VP, _VP]),
+    'scg_adversary_dim': (C.c_int, [_VP]),
     'scg_policy_blob_floats': (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     'scg_policy_pack': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _VP, _VP]),
     'scg_state_bytes': (C.c_int, [_VP, C.POINTER(C.c_size_t)]),

@@ -1,4 +1,4 @@
-'''Register controllers (safe_control_gym/controllers/__init__.py:29-47): `ppo` (the hot path) and its sibling collector `safe_explorer_ppo`.'''
+'''Register controllers (safe_control_gym/controllers/__init__.py:29-47): `ppo` (the hot path) and its sibling collectors `safe_explorer_ppo`, `rarl`, `sac` and `ddpg`.'''
 
 from safe_control_gym_b200.utils.registration import register
 
@@ -9,3 +9,15 @@ register(idx='ppo',
 register(idx='safe_explorer_ppo',
          entry_point='safe_control_gym_b200.controllers.safe_explorer.safe_ppo:SafeExplorerPPO',
          config_entry_point='safe_control_gym_b200.controllers.safe_explorer.safe_ppo:DEFAULT_CONFIG')
+
+register(idx='rarl',
+         entry_point='safe_control_gym_b200.controllers.rarl.rarl:RARL',
+         config_entry_point='safe_control_gym_b200.controllers.rarl.rarl:DEFAULT_CONFIG')
+
+register(idx='sac',
+         entry_point='safe_control_gym_b200.controllers.sac.sac:SAC',
+         config_entry_point='safe_control_gym_b200.controllers.sac.sac:DEFAULT_CONFIG')
+
+register(idx='ddpg',
+         entry_point='safe_control_gym_b200.controllers.ddpg.ddpg:DDPG',
+         config_entry_point='safe_control_gym_b200.controllers.ddpg.ddpg:DEFAULT_CONFIG')

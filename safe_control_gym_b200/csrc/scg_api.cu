@@ -18,6 +18,7 @@
 struct scg_env {
     scg_config cfg;
     int nx, nu, obs_dim, n_inertial, n_off_slots, P, D;
+    int adv_dim = 0;             // dim of the adversary action (0 = no adversary)
     int device;
     // device buffers
     scg_config* d_cfg = nullptr;
@@ -68,6 +69,8 @@ static void carve_state(scg_env* e) {
     size_t o_ir = take(sizeof(int32_t) * N);
     size_t o_do = take(sizeof(int32_t) * 3 * SCG_MAX_DIST * N);
     size_t o_acc = take(sizeof(float) * 3 * N);
+    size_t o_adv = take(sizeof(float) * SCG_MAX_ADV * N);
+    size_t o_as = take(sizeof(int32_t) * N);
     e->state_bytes = off;
     if (!base) return;
     e->tab.st.phys = (double*)(base + o_phys);
@@ -79,6 +82,8 @@ static void carve_state(scg_env* e) {
     e->tab.st.initial_reset = (int32_t*)(base + o_ir);
     e->tab.st.dist_off = (int32_t*)(base + o_do);
     e->tab.st.ep_acc = (float*)(base + o_acc);
+    e->tab.st.adv = (float*)(base + o_adv);
+    e->tab.st.adv_set = (int32_t*)(base + o_as);
 }
 
 static int obs_dim_of(const scg_config* c) {
@@ -112,6 +117,11 @@ int scg_create(const scg_config* cfg, scg_env** out) {
             if (cfg->dist[m][j].dim < 0 || cfg->dist[m][j].dim > SCG_MAX_DIST_DIM) return fail(nullptr, SCG_EINVAL, "scg_create: disturbance dim out of range");
     }
     if (obs_dim_of(cfg) > SCG_MAX_OBS) return fail(nullptr, SCG_EINVAL, "scg_create: observation too wide (obs_goal_horizon too large)");
+    if (cfg->physics < SCG_PHYS_PYB || cfg->physics > SCG_PHYS_PYB_GND_DRAG_DW) return fail(nullptr, SCG_EINVAL, "scg_create: unknown physics");
+    if (cfg->physics != SCG_PHYS_PYB && cfg->system == SCG_SYS_CARTPOLE) return fail(nullptr, SCG_EINVAL, "scg_create: physics variants are quadrotor-only");
+    if ((cfg->physics == SCG_PHYS_PYB_GND || cfg->physics == SCG_PHYS_PYB_GND_DRAG_DW) && !(cfg->gnd_eff_h_clip > 0 && cfg->prop_radius > 0))
+        return fail(nullptr, SCG_EINVAL, "scg_create: ground effect needs prop_radius and gnd_eff_h_clip > 0");
+    if (cfg->adversary_mode < SCG_ADV_NONE || cfg->adversary_mode > SCG_ADV_DYNAMICS) return fail(nullptr, SCG_EINVAL, "scg_create: unknown adversary_mode");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return fail(nullptr, SCG_ECUDA, "scg_create: no CUDA device available (this engine has no CPU fallback)");
@@ -122,6 +132,8 @@ int scg_create(const scg_config* cfg, scg_env** out) {
     e->device = cfg->device;
     e->nx = sys_nx(cfg->system); e->nu = sys_nu(cfg->system); e->obs_dim = obs_dim_of(cfg);
     e->n_inertial = cfg->system == SCG_SYS_CARTPOLE ? 3 : 4;
+    e->adv_dim = cfg->adversary_mode == SCG_ADV_ACTION ? e->nu                      // benchmark_env.py:289-295: dim of the driven disturbance mode
+                 : cfg->adversary_mode == SCG_ADV_DYNAMICS ? (cfg->system == SCG_SYS_CARTPOLE ? 2 : cfg->system == SCG_SYS_QUAD1D ? 1 : cfg->system == SCG_SYS_QUAD2D ? 2 : 3) : 0;
     e->n_off_slots = 0; e->D = 0;
     for (int m = 0; m < 3; ++m)
         for (int j = 0; j < cfg->n_dist[m]; ++j) {
@@ -277,6 +289,20 @@ int scg_step(scg_env* e, const float* d_act, const double* d_act_f64, const scg_
     return SCG_OK;
 }
 
+int scg_adversary_dim(const scg_env* e) { return e ? e->adv_dim : 0; }
+
+int scg_set_adversary_control(scg_env* e, const float* d_adv, void* stream) {
+    if (!e || !d_adv) return fail(e, SCG_EINVAL, "scg_set_adversary_control: null argument");
+    if (e->adv_dim == 0)   // benchmark_env.py:225-228
+        return fail(e, SCG_ESTATE, "[ERROR] adversary_disturbance does not exist, env.set_adversary_control() cannot be called.");
+    CUDA_TRY(e, cudaSetDevice(e->device));
+    const int N = e->cfg.num_envs, B = 128, G = (N + B - 1) / B;
+    adversary_set_kernel<<<G, B, 0, (cudaStream_t)stream>>>(e->tab, d_adv, e->adv_dim);
+    CUDA_TRY(e, cudaGetLastError());
+    e->launches += 1;
+    return SCG_OK;
+}
+
 int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* out, void* stream) {
     int rc = check_ready(e, "scg_rollout"); if (rc) return rc;
     if (!a || !out) return fail(e, SCG_EINVAL, "scg_rollout: null argument");
@@ -310,9 +336,21 @@ int scg_rollout(scg_env* e, const scg_rollout_args* a, const scg_rollout_out* ou
     if (a->safety_constraints > 0 && !e->con_single) return fail(e, SCG_EINVAL, "scg_rollout: the safety layer needs single-variable (bound) constraint rows");
     P.safety_C = a->safety_constraints; P.safety_H = a->safety_hidden; P.safety = a->d_safety;
     for (int i = 0; i < SCG_MAX_SAFETY; ++i) P.safety_slack[i] = (float)a->safety_slack[i];
+    if (a->d_adv_policy) {
+        if (e->adv_dim == 0) return fail(e, SCG_ESTATE, "[ERROR] adversary_disturbance does not exist, env.set_adversary_control() cannot be called.");
+        if (a->adv_act_dim != e->adv_dim) return fail(e, SCG_EINVAL, "scg_rollout: adv_act_dim does not match the env's adversary action space");
+        if (((uintptr_t)a->d_adv_policy & 15) != 0) return fail(e, SCG_EINVAL, "scg_rollout: adversary blob must be 16-byte aligned");
+        if (!a->d_eps_adv && !a->deterministic && e->cfg.rng_mode != SCG_RNG_PHILOX)
+            return fail(e, SCG_EINVAL, "scg_rollout: d_eps_adv is required unless rng_mode is SCG_RNG_PHILOX or deterministic is set");
+    }
+    P.adv_policy = a->d_adv_policy; P.eps_adv = a->d_eps_adv; P.adv_dim = a->d_adv_policy ? a->adv_act_dim : 0; P.adv_record = a->d_adv_policy ? a->adv_record : 0;
     cudaStream_t s = (cudaStream_t)stream;
     const bool dbl = e->cfg.precision == SCG_PREC_F64;
-    RolloutLaunch rl{e->cfg.num_envs, e->obs_dim, e->nu, e->nx, e->L, e->tab};
+    const bool ext_phys = e->cfg.physics == SCG_PHYS_PYB_GND || e->cfg.physics == SCG_PHYS_PYB_DRAG || e->cfg.physics == SCG_PHYS_PYB_GND_DRAG_DW;
+    // rollout_kernel's FAST-schedule test, evaluated here: use_cand (no randomised disturbance offsets), no observation disturbance, no
+    // done_on_violation, no constraint penalty
+    const bool fast_ok = e->n_off_slots == 0 && e->cfg.n_dist[SCG_MODE_OBSERVATION] == 0 && !e->cfg.done_on_violation && !e->cfg.use_constraint_penalty;
+    RolloutLaunch rl{e->cfg.num_envs, e->obs_dim, e->nu, e->nx, e->L, e->tab, (ext_phys || e->adv_dim > 0) ? 1 : 0, fast_ok ? 1 : 0};
     RolloutLaunchResult r;
     switch (e->cfg.system) {
         case SCG_SYS_CARTPOLE: r = dbl ? scg_rollout_cartpole_f64(rl, a, P, s) : scg_rollout_cartpole_f32(rl, a, P, s); break;

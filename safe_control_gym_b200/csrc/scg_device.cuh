@@ -88,6 +88,7 @@ template <typename R> __device__ __forceinline__ R normalize_angle(R x) {
 #define SCG_STREAM_STEP 2u
 #define SCG_STREAM_POLICY 3u
 #define SCG_STREAM_RESET 4u
+#define SCG_STREAM_ADVERSARY 5u   // sampling noise of the RARL / RAP adversary policy
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
 #pragma unroll
@@ -135,10 +136,11 @@ __device__ __forceinline__ int rng_randint(const RngKey& k, uint32_t stream, uin
 // device-side view of one handle
 // ---------------------------------------------------------------------------------------------
 template <int SYS> struct SysDims;
-template <> struct SysDims<SCG_SYS_CARTPOLE> { static constexpr int NX = 4, NU = 1, PS = 4; };
-template <> struct SysDims<SCG_SYS_QUAD1D> { static constexpr int NX = 2, NU = 1, PS = 4; };   // x, vx, z, vz (x only carries the init quirk)
-template <> struct SysDims<SCG_SYS_QUAD2D> { static constexpr int NX = 6, NU = 2, PS = 6; };   // x, vx, z, vz, theta, omega_y
-template <> struct SysDims<SCG_SYS_QUAD3D> { static constexpr int NX = 12, NU = 4, PS = 13; }; // pos3, quat4, vel3, omega_world3
+// NADV: widest adversary action (= dim of the disturbance mode it drives: action -> NU, dynamics -> 2 / 1 / 2 / 3; benchmark_env.py:289-295)
+template <> struct SysDims<SCG_SYS_CARTPOLE> { static constexpr int NX = 4, NU = 1, PS = 4, NADV = 2; };
+template <> struct SysDims<SCG_SYS_QUAD1D> { static constexpr int NX = 2, NU = 1, PS = 4, NADV = 1; };   // x, vx, z, vz (x only carries the init quirk)
+template <> struct SysDims<SCG_SYS_QUAD2D> { static constexpr int NX = 6, NU = 2, PS = 6, NADV = 2; };   // x, vx, z, vz, theta, omega_y
+template <> struct SysDims<SCG_SYS_QUAD3D> { static constexpr int NX = 12, NU = 4, PS = 13, NADV = 4; }; // pos3, quat4, vel3, omega_world3
 
 #define SCG_PS_MAX 13
 #define SCG_NINV 4
@@ -154,6 +156,8 @@ struct DevState {
     int32_t* initial_reset; // [N]
     int32_t* dist_off;   // [3*SCG_MAX_DIST][N]
     float* ep_acc;       // [3][N] running episode return / length / violations
+    float* adv;          // [SCG_MAX_ADV][N] adversary action after clip / scale / offset (benchmark_env.py:223-224)
+    int32_t* adv_set;    // [N] 1 = adv holds an action (self.adv_action is not None)
 };
 
 struct DevTables {
@@ -282,6 +286,9 @@ template <typename R> struct HotCfg {
     R dt, hover, act_scale, goal_tol, penalty, x_thr, th_thr;
     R gravity, kf, inv_nm_kf, pwm_c, pwm_s, inv_pwm_s, pwm_min, pwm_max, arm, km_over_kf, pole_w2;
     R thr_lo, thr_hi, inv_nm;   // thrust per input at the PWM limits (with a margin), 1 / motors per input
+    // non-default physics (base_aviary.py:386-460) and the adversary input (benchmark_env.py:216-228): only read by the EXT instantiations
+    int physics, adv_mode;
+    R gnd_coeff, prop_radius, h_clip, drag_xy, drag_z, inv_kf;
     R act_low[SCG_MAX_NU], act_high[SCG_MAX_NU], u_goal[SCG_MAX_NU], rew_act_w[SCG_MAX_NU], Rw[SCG_MAX_NU];
     R rew_state_w[SCG_MAX_NX], mse_w[SCG_MAX_NX], Qw[SCG_MAX_NX];
     double state_low[SCG_MAX_NX], state_high[SCG_MAX_NX];   // float32-rounded bounds, compared in double like numpy does
@@ -312,6 +319,9 @@ __device__ __noinline__ void hot_load(const DevTables& T, HotCfg<R>* h) {
     h->pwm_c = (R)c->pwm2rpm_const; h->pwm_s = (R)c->pwm2rpm_scale; h->inv_pwm_s = (R)(1.0 / c->pwm2rpm_scale);
     h->pwm_min = (R)c->pwm_min; h->pwm_max = (R)c->pwm_max; h->arm = (R)c->arm; h->km_over_kf = (R)(c->km / c->kf);
     h->pole_w2 = (R)(c->pole_width * c->pole_width);
+    h->physics = c->physics; h->adv_mode = c->adversary_mode;
+    h->gnd_coeff = (R)c->gnd_eff_coeff; h->prop_radius = (R)c->prop_radius; h->h_clip = (R)c->gnd_eff_h_clip;
+    h->drag_xy = (R)c->drag_coeff_xy; h->drag_z = (R)c->drag_coeff_z; h->inv_kf = (R)(1.0 / c->kf);
     {
         const double nmkf = (double)(4 / NU) * c->kf;
         const double rlo = c->pwm2rpm_scale * c->pwm_min + c->pwm2rpm_const, rhi = c->pwm2rpm_scale * c->pwm_max + c->pwm2rpm_const;
@@ -455,10 +465,58 @@ template <typename R> struct Physics<SCG_SYS_CARTPOLE, R> {
     }
 };
 
+// Non-default quadrotor physics (Physics.PYB_GND / PYB_DRAG / PYB_GND_DRAG_DW, base_aviary.py:243-268).  Per sub-step, with the kinematic
+// information refreshed at its start (base_aviary.py:246-251):
+//   ground effect (base_aviary.py:386-418): every propeller gains KF rpm^2 GND_EFF_COEFF (PROP_RADIUS / (4 h_i))^2 along its LINK z axis at
+//     the prop link -- the thrust's own application point and direction, so f_i grows by that factor (the yaw torque does not) -- with h_i
+//     the world height of prop link i clipped from below, while |roll| and |pitch| < pi/2;
+//   drag (base_aviary.py:420-440): -DRAG_COEFF sum(2 pi rpm / 60) * v_world is rotated by the base rotation and then applied as a
+//     LINK_FRAME force at the CoM link, i.e. rotated once more: F_world = R R (k v);
+//   downwash (base_aviary.py:442-460): compares the drone with itself (delta_z = 0): never a force, PYB_DW == PYB.
+template <typename R> struct PhysExt {
+    bool gnd, drag; R kxy, kz;
+    __device__ __forceinline__ PhysExt() : gnd(false), drag(false), kxy((R)0), kz((R)0) {}
+    __device__ __forceinline__ PhysExt(const HotCfg<R>* h, const R f[4]) {
+        gnd = h->physics == SCG_PHYS_PYB_GND || h->physics == SCG_PHYS_PYB_GND_DRAG_DW;
+        drag = h->physics == SCG_PHYS_PYB_DRAG || h->physics == SCG_PHYS_PYB_GND_DRAG_DW;
+        kxy = kz = (R)0;
+        if (drag) {
+            R srpm = (R)0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) srpm += Mth<R>::sqrt_(f[i] * h->inv_kf);       // rpm_i: f_i = KF rpm_i^2
+            srpm *= (R)(2.0 * SCG_PI / 60.0);
+            kxy = -h->drag_xy * srpm; kz = -h->drag_z * srpm;
+        }
+    }
+    __device__ __forceinline__ bool any() const { return gnd || drag; }
+    // thrust gain of a propeller at world height hh
+    __device__ __forceinline__ R gain(const HotCfg<R>* h, R hh) const {
+        hh = hh < h->h_clip ? h->h_clip : hh;
+        const R q = h->prop_radius / ((R)4 * hh);
+        return (R)1 + h->gnd_coeff * q * q;
+    }
+};
+
 template <typename R> struct Physics<SCG_SYS_QUAD1D, R> {
     // vertical motion only: orientation stays identity, thrust along world z
+    template <bool EXT = false>
     static __device__ __forceinline__ void advance(const HotCfg<R>* h, EnvRegs<SCG_SYS_QUAD1D, R>& e, const R f[4], const R* fd, bool has_dist) {
         const R m = e.inertial[0], dt = h->dt;
+        if constexpr (EXT) {
+            const PhysExt<R> px(h, f);
+            if (px.any()) {                      // identity orientation: all four propellers at height z, roll = pitch = 0, R R (k v) = k v
+                const R thrust0 = f[0] + f[1] + f[2] + f[3];
+                R z = e.ps[2], vz = e.ps[3], x = e.ps[0], vx = e.ps[1];
+                for (int s = 0; s < h->steps; ++s) {
+                    R Fz = (px.gnd ? thrust0 * px.gain(h, z) : thrust0) - m * h->gravity, Fx = (R)0;
+                    if (px.drag) { Fx = px.kxy * vx; Fz += px.kz * vz; }
+                    if (has_dist) Fz += fd[0];
+                    vx += Fx / m * dt; vz += Fz / m * dt; x += vx * dt; z += vz * dt;
+                }
+                e.ps[0] = x; e.ps[1] = vx; e.ps[2] = z; e.ps[3] = vz;
+                return;
+            }
+        }
         R thrust = f[0] + f[1] + f[2] + f[3];
         R Fz = thrust - m * h->gravity; if (has_dist) Fz += fd[0];
         R az = Fz / m;
@@ -485,7 +543,34 @@ template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
     // Within a control step thrust and torque are constant, so omega grows linearly and the per-sub-step angle increment
     // delta_k = omega_k dt grows by the constant eps = alpha dt^2: sin/cos(theta_k) follow from two plane rotations per
     // sub-step (3 sincos per control step instead of one per sub-step).
+    // non-default physics: thrust and torque change with the pose every sub-step, so the angle is re-evaluated instead of rotated
+    static __device__ __noinline__ void advance_ext(const HotCfg<R>* h, EnvRegs<SCG_SYS_QUAD2D, R>& e, const R f[4], const R* fd, bool has_dist, const PhysExt<R> px) {
+        const R dt = h->dt, inv_m = e.inv[0], a = h->arm;
+        R x = e.ps[0], vx = e.ps[1], z = e.ps[2], vz = e.ps[3], th = e.ps[4], om = e.ps[5];
+        for (int s = 0; s < h->steps; ++s) {
+            R st, ct; Mth<R>::sincos_(th, &st, &ct);
+            R f03 = f[0], f12 = f[1];                                  // f = [p0, p1, p1, p0] (quadrotor_utils.py:39)
+            // q = (0, sin(th/2), 0, cos(th/2)): getEulerFromQuaternion gives roll = atan2(0, cos th), pitch = asin(sin th) away from the poles
+            if (px.gnd && ct > (R)0 && Mth<R>::abs_(st) < (R)0.99999) { f03 *= px.gain(h, z - st * a); f12 *= px.gain(h, z + st * a); }
+            const R tm = (R)2 * (f03 + f12) * inv_m, alpha = (R)2 * a * (f12 - f03) * e.inv[1];
+            R ax = st * tm, az = ct * tm - h->gravity;
+            if (px.drag) {                                             // R R (k v) with R = R_y(th)
+                const R kvx = px.kxy * vx, kvz = px.kz * vz;
+                const R d1x = ct * kvx + st * kvz, d1z = -st * kvx + ct * kvz;
+                ax += (ct * d1x + st * d1z) * inv_m; az += (-st * d1x + ct * d1z) * inv_m;
+            }
+            if (has_dist) { ax += fd[0] * inv_m; az += fd[1] * inv_m; }
+            vx += ax * dt; vz += az * dt; om += alpha * dt;
+            x += vx * dt; z += vz * dt; th += om * dt;
+        }
+        e.ps[0] = x; e.ps[1] = vx; e.ps[2] = z; e.ps[3] = vz; e.ps[4] = th; e.ps[5] = om;
+    }
+    template <bool EXT = false>
     static __device__ __forceinline__ void advance(const HotCfg<R>* h, EnvRegs<SCG_SYS_QUAD2D, R>& e, const R f[4], const R* fd, bool has_dist) {
+        if constexpr (EXT) {
+            const PhysExt<R> px(h, f);
+            if (px.any()) { advance_ext(h, e, f, fd, has_dist, px); return; }
+        }
         const R dt = h->dt;
         const R inv_m = e.inv[0];                                      // 1/M, 1/Iyy: per-episode constants (env_load / env_reset)
         const R thrust = f[0] + f[1] + f[2] + f[3];
@@ -535,15 +620,17 @@ template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
 
 template <typename R> struct Physics<SCG_SYS_QUAD3D, R> {
     // ps = pos[0..2], quat[3..6] (x,y,z,w), vel[7..9], omega_world[10..12]
+    template <bool EXT = false>
     static __device__ void advance(const HotCfg<R>* h, EnvRegs<SCG_SYS_QUAD3D, R>& e, const R f[4], const R* fd, bool has_dist) {
         const R dt = h->dt;
         const R inv_m = e.inv[0];                                      // per-episode reciprocals (env_load / reset candidates)
         const R J0 = e.inertial[1], J1 = e.inertial[2], J2 = e.inertial[3];
         const R iJ0 = e.inv[1], iJ1 = e.inv[2], iJ2 = e.inv[3];
         const R a = h->arm;
-        const R tm = (f[0] + f[1] + f[2] + f[3]) * inv_m;
-        const R tbx = a * (f[0] + f[1] - f[2] - f[3]);
-        const R tby = a * (-f[0] + f[1] + f[2] - f[3]);
+        R tm = (f[0] + f[1] + f[2] + f[3]) * inv_m;
+        R tbx = a * (f[0] + f[1] - f[2] - f[3]);
+        R tby = a * (-f[0] + f[1] + f[2] - f[3]);
+        const PhysExt<R> pe = EXT ? PhysExt<R>(h, f) : PhysExt<R>();
         const R tbz = h->km_over_kf * (-f[0] + f[1] - f[2] + f[3]);   // base_aviary.py:371-372: rpm^2*KM = f*KM/KF
         R px = e.ps[0], py = e.ps[1], pz = e.ps[2];
         R q[4] = {e.ps[3], e.ps[4], e.ps[5], e.ps[6]};
@@ -554,6 +641,27 @@ template <typename R> struct Physics<SCG_SYS_QUAD3D, R> {
         const R half_dt = (R)0.5 * dt;
         for (int s = 0; s < h->steps; ++s) {
             R M[9]; rot_from_unit_quat<R>(q, M);
+            R dax = (R)0, day = (R)0, daz = (R)0;                      // drag acceleration (EXT)
+            if constexpr (EXT) {
+                if (pe.gnd) {
+                    // |roll| < pi/2 <=> the x argument of its atan2 is positive; |pitch| < pi/2 <=> away from the asin clamp (rpy_from_quat)
+                    const R sarg = (R)-2 * (q[0] * q[2] - q[3] * q[1]), rollx = q[3] * q[3] - q[0] * q[0] - q[1] * q[1] + q[2] * q[2];
+                    R fe[4] = {f[0], f[1], f[2], f[3]};
+                    if (rollx > (R)0 && Mth<R>::abs_(sarg) < (R)0.99999) {
+                        // prop link offsets (cf2x.urdf:42,54,66,78): (a,a) (-a,a) (-a,-a) (a,-a); world height = z + R[2][0] x + R[2][1] y
+                        fe[0] *= pe.gain(h, pz + a * (M[6] + M[7])); fe[1] *= pe.gain(h, pz + a * (-M[6] + M[7]));
+                        fe[2] *= pe.gain(h, pz + a * (-M[6] - M[7])); fe[3] *= pe.gain(h, pz + a * (M[6] - M[7]));
+                    }
+                    tm = (fe[0] + fe[1] + fe[2] + fe[3]) * inv_m;
+                    tbx = a * (fe[0] + fe[1] - fe[2] - fe[3]); tby = a * (-fe[0] + fe[1] + fe[2] - fe[3]);
+                }
+                if (pe.drag) {
+                    const R kx = pe.kxy * vx, ky = pe.kxy * vy, kz = pe.kz * vz;
+                    const R d0 = M[0] * kx + M[1] * ky + M[2] * kz, d1 = M[3] * kx + M[4] * ky + M[5] * kz, d2 = M[6] * kx + M[7] * ky + M[8] * kz;
+                    dax = (M[0] * d0 + M[1] * d1 + M[2] * d2) * inv_m; day = (M[3] * d0 + M[4] * d1 + M[5] * d2) * inv_m;
+                    daz = (M[6] * d0 + M[7] * d1 + M[8] * d2) * inv_m;
+                }
+            }
             // body rates, Euler's equation with the gyroscopic term (btMultiBody m_useGyroTerm)
             const R bx = M[0] * wx + M[3] * wy + M[6] * wz;
             const R by = M[1] * wx + M[4] * wy + M[7] * wz;
@@ -562,7 +670,8 @@ template <typename R> struct Physics<SCG_SYS_QUAD3D, R> {
             const R dbx = (tbx - (by * jz - bz * jy)) * iJ0;
             const R dby = (tby - (bz * jx - bx * jz)) * iJ1;
             const R dbz = (tbz - (bx * jy - by * jx)) * iJ2;
-            vx += (M[2] * tm + ax0) * dt; vy += (M[5] * tm + ay0) * dt; vz += (M[8] * tm + az0) * dt;
+            if constexpr (EXT) { vx += (M[2] * tm + ax0 + dax) * dt; vy += (M[5] * tm + ay0 + day) * dt; vz += (M[8] * tm + az0 + daz) * dt; }
+            else { vx += (M[2] * tm + ax0) * dt; vy += (M[5] * tm + ay0) * dt; vz += (M[8] * tm + az0) * dt; }
             wx += (M[0] * dbx + M[1] * dby + M[2] * dbz) * dt;
             wy += (M[3] * dbx + M[4] * dby + M[5] * dbz) * dt;
             wz += (M[6] * dbx + M[7] * dby + M[8] * dbz) * dt;
@@ -797,9 +906,10 @@ template <int SYS, typename R> struct StepCtx {
 };
 
 // quadrotor.py:722-747 / cartpole.py:479-502 + the dynamics disturbance draw (quadrotor.py:413-435, cartpole.py:540-551)
-template <int SYS, typename R>
+// EXT: the instantiations that also take the adversary's action (`adv`: clipped / scaled / offset, or nullptr = self.adv_action is None)
+template <int SYS, typename R, bool EXT = false>
 __device__ __forceinline__ void env_pre(const DevTables& T, const HotCfg<R>* h, int n, const EnvRegs<SYS, R>& e, const R* action, const double* noise_row,
-                                        StepCtx<SYS, R>& cx, NoiseSrc<R>& ns) {
+                                        StepCtx<SYS, R>& cx, NoiseSrc<R>& ns, const R* adv = nullptr) {
     constexpr int NU = SysDims<SYS>::NU;
     const int pyb_step = e.ctrl_step * h->steps;
     ns.row = noise_row; ns.philox = h->philox != 0;
@@ -812,6 +922,12 @@ __device__ __forceinline__ void env_pre(const DevTables& T, const HotCfg<R>* h, 
     }
     if (h->has_dist[SCG_MODE_ACTION])
         apply_disturbances<R>(T.cfg, T.st.dist_off, T.N, n, SCG_MODE_ACTION, e.ctrl_step, pyb_step, cx.noisy, NU, ns);
+    if constexpr (EXT) {
+        if (h->adv_mode == SCG_ADV_ACTION && adv) {                    // quadrotor.py:737-738, cartpole.py:494-495
+#pragma unroll
+            for (int k = 0; k < NU; ++k) cx.noisy[k] += adv[k];
+        }
+    }
 #pragma unroll
     for (int k = 0; k < NU; ++k) {
         R t = cx.noisy[k];
@@ -825,16 +941,26 @@ __device__ __forceinline__ void env_pre(const DevTables& T, const HotCfg<R>* h, 
         const int ddim = (SYS == SCG_SYS_CARTPOLE) ? 2 : (SYS == SCG_SYS_QUAD1D) ? 1 : (SYS == SCG_SYS_QUAD2D) ? 2 : 3;
         apply_disturbances<R>(T.cfg, T.st.dist_off, T.N, n, SCG_MODE_DYNAMICS, e.ctrl_step, pyb_step, cx.fd, ddim, ns);
     }
+    if constexpr (EXT) {
+        if (h->adv_mode == SCG_ADV_DYNAMICS) {                         // quadrotor.py:416-425, cartpole.py:543-551 (same layout as the passive force)
+            constexpr int ddim = (SYS == SCG_SYS_CARTPOLE) ? 2 : (SYS == SCG_SYS_QUAD1D) ? 1 : (SYS == SCG_SYS_QUAD2D) ? 2 : 3;
+            cx.has_dyn = true;
+            if (adv) {
+#pragma unroll
+                for (int k = 0; k < ddim; ++k) cx.fd[k] += adv[k];
+            }
+        }
+    }
 }
 
-template <int SYS, typename R>
+template <int SYS, typename R, bool EXT = false>
 __device__ __forceinline__ void env_physics(const HotCfg<R>* h, EnvRegs<SYS, R>& e, const StepCtx<SYS, R>& cx, R* state) {
-    if (SYS == SCG_SYS_CARTPOLE) {
+    if constexpr (SYS == SCG_SYS_CARTPOLE) {
         Physics<SYS, R>::advance(h, e, cx.clipped, cx.fd, cx.has_dyn);
     } else {
         R f[4]; quad_motor_forces<SYS, R>(h, cx.clipped, f);
         SCG_TK(2);
-        Physics<SYS, R>::advance(h, e, f, cx.fd, cx.has_dyn);
+        Physics<SYS, R>::template advance<EXT>(h, e, f, cx.fd, cx.has_dyn);
     }
     Physics<SYS, R>::state(e, state);
 }
@@ -980,11 +1106,11 @@ __device__ __forceinline__ void env_finalize(const HotCfg<R>* h, int ctrl_step_a
 template <int SYS, typename R, typename GT>
 __device__ __forceinline__ void env_step(const DevTables& T, const HotCfg<R>* h, const GT* xg, int n, EnvRegs<SYS, R>& e, const R* action, const double* noise_row,
                                          double* __restrict__ zbuf, int zstride, R* state, R& rew_out, R& mse_out, StepInfo& info,
-                                         double* cvals, float* cvals_f32, NoiseSrc<R>& ns) {
+                                         double* cvals, float* cvals_f32, NoiseSrc<R>& ns, const R* adv = nullptr) {
     constexpr int NX = SysDims<SYS>::NX, NU = SysDims<SYS>::NU;
     StepCtx<SYS, R> cx;
-    env_pre<SYS, R>(T, h, n, e, action, noise_row, cx, ns);
-    env_physics<SYS, R>(h, e, cx, state);
+    env_pre<SYS, R, true>(T, h, n, e, action, noise_row, cx, ns, adv);      // gym-style API: always the full feature set
+    env_physics<SYS, R, true>(h, e, cx, state);
     R rew, mse;
     env_reward_mse<SYS, R, GT>(h, xg, state, cx.noisy, cx.clipped, e.ctrl_step, rew, mse);
     int goal_reached, oob;

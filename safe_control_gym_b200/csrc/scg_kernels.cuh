@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(SCG_LANE_BLOCK) reset_kernel(DevTables T, Rese
     env_reset<SYS, R>(T, h, n, e, state);
     e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
     T.st.initial_reset[n] = 1;
+    T.st.adv_set[n] = 0;                     // benchmark_env.py:338-339: self.adv_action = None
     env_store<SYS, R>(T, n, e);
     NoiseSrc<R> ns = reset_noise<R>(T, h, n, e.episode);
     GlobalObsSink sink{T.st.cur_obs, A.obs, A.obs_f64, (size_t)n * od};
@@ -227,7 +228,15 @@ __global__ void __launch_bounds__(SCG_LANE_BLOCK) step_kernel(DevTables T, StepA
     R state[NX], rew, mse; StepInfo info; NoiseSrc<R> ns;
     const scg_step_out& o = A.out;
     double* cv = o.d_cvals ? o.d_cvals + (size_t)n * nc : nullptr;
-    env_step<SYS, R, double>(T, h, T.x_goal, n, e, action, nrow, s_z + threadIdx.x, SCG_LANE_BLOCK, state, rew, mse, info, cv, nullptr, ns);
+    // adversary action left by scg_set_adversary_control (benchmark_env.py:216-228); the dynamics mode consumes it (quadrotor.py:424-425)
+    R advv[SCG_MAX_ADV]; const R* adv = nullptr;
+    if (h->adv_mode != SCG_ADV_NONE && T.st.adv_set[n]) {
+#pragma unroll
+        for (int k = 0; k < SCG_MAX_ADV; ++k) advv[k] = (R)T.st.adv[(size_t)k * T.N + n];
+        adv = advv;
+        if (h->adv_mode == SCG_ADV_DYNAMICS) T.st.adv_set[n] = 0;
+    }
+    env_step<SYS, R, double>(T, h, T.x_goal, n, e, action, nrow, s_z + threadIdx.x, SCG_LANE_BLOCK, state, rew, mse, info, cv, nullptr, ns, adv);
     e.ep_ret += (float)rew; e.ep_len += 1.f; e.ep_cv += (float)info.cviol;
     const bool reset_now = info.done && c->auto_reset;
     {   // observation of the transition: the returned obs unless the env auto-resets, always the terminal obs
@@ -238,6 +247,7 @@ __global__ void __launch_bounds__(SCG_LANE_BLOCK) step_kernel(DevTables T, StepA
     }
     if (o.d_terminal_state_f64) for (int k = 0; k < NX; ++k) o.d_terminal_state_f64[(size_t)n * NX + k] = (double)state[k];
     if (reset_now) {   // dummy_vec_env.py:33-38
+        T.st.adv_set[n] = 0;
         env_reset<SYS, R>(T, h, n, e, state);
         e.ep_ret = 0.f; e.ep_len = 0.f; e.ep_cv = 0.f;
         NoiseSrc<R> rs = reset_noise<R>(T, h, n, e.episode);
@@ -255,6 +265,20 @@ __global__ void __launch_bounds__(SCG_LANE_BLOCK) step_kernel(DevTables T, StepA
     if (o.d_out_of_bounds) o.d_out_of_bounds[n] = (uint8_t)info.out_of_bounds;
     if (o.d_goal_reached) o.d_goal_reached[n] = (uint8_t)info.goal_reached;
     if (o.d_current_step) o.d_current_step[n] = info.current_step;
+}
+
+// BenchmarkEnv.set_adversary_control (benchmark_env.py:216-228): adv_action = clip(a, -1, 1) * scale + offset
+static __global__ void adversary_set_kernel(DevTables T, const float* __restrict__ a, int dim) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= T.N) return;
+    // float32 arithmetic like the reference: a float32 action array times / plus python floats stays float32 (two rounded operations)
+    const float sc = (float)T.cfg->adversary_scale, of = (float)T.cfg->adversary_offset;
+    for (int k = 0; k < SCG_MAX_ADV; ++k) {
+        float v = 0.f;
+        if (k < dim) { const float x = fminf(fmaxf(a[(size_t)n * dim + k], -1.0f), 1.0f); v = __fadd_rn(__fmul_rn(x, sc), of); }
+        T.st.adv[(size_t)k * T.N + n] = v;
+    }
+    T.st.adv_set[n] = 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -278,14 +302,17 @@ struct RolloutParams {
     const double* norm;          // frozen obs / reward normaliser statistics (scg_rollout_args.d_norm), nullable
     const float* obs0;           // policy input of step 0, nullable
     long long mc_off;            // != 0: NVSwitch multicast mapping of the gathered buffer (multimem.st), replaces the unicast peer copies
+    // RARL / RAP adversary (scg_rollout_args.d_adv_policy): packed blob with act_dim = adv_dim, its normals, which player is recorded
+    const float* adv_policy; const float* eps_adv; int adv_dim, adv_record;
     long long* prof;     // SCG_PROF builds: per-phase cycle counters of CTA 0 (nullable)
 };
 
 // shared memory carve-up (floats), all offsets multiples of 4
 template <int HID, int E> struct RolloutSmem {
-    int blob, obs, tobs, cobs, h1, out, xg, total_floats;
-    // xg_floats: size of the shared X_GOAL copy in float units (L * nx * sizeof(R) / 4); nw: GEMM warps per network
-    __host__ __device__ RolloutSmem(int obs_dim, int act_dim, int xg_floats, int nw) {
+    int blob, obs, tobs, cobs, h1, out, xg, blob2, out2, total_floats;
+    // xg_floats: size of the shared X_GOAL copy in float units (L * nx * sizeof(R) / 4); nw: GEMM warps per network;
+    // adv_dim > 0: room for the adversary's blob and output partial sums (adv_max = the instantiation's SysDims::NADV)
+    __host__ __device__ RolloutSmem(int obs_dim, int act_dim, int xg_floats, int nw, int adv_dim = 0, int adv_max = 0) {
         BlobLayout L = blob_layout(obs_dim, act_dim, HID);
         blob = 0;
         obs = blob + L.total;
@@ -294,7 +321,9 @@ template <int HID, int E> struct RolloutSmem {
         cobs = tobs + obs_dim * E;           // reset observations of the two candidate episodes
         out = cobs + 2 * obs_dim * E;
         xg = out + pad4i(nw * (act_dim + 1) * E);   // per-warp partial sums of the output layer
-        total_floats = xg + pad4i(xg_floats);
+        blob2 = xg + pad4i(xg_floats);
+        out2 = blob2 + (adv_dim > 0 ? blob_layout(obs_dim, adv_dim, HID).total : 0);
+        total_floats = out2 + (adv_dim > 0 ? pad4i(nw * (adv_max + 1) * E) : 0);
     }
 };
 
@@ -453,6 +482,15 @@ __device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const
     const int net = threadIdx.x / NTN, tl = threadIdx.x % NTN;
     net_forward<HID, E, NTN, A>(tl, net, net ? 1 : A, net ? A : 0, s_blob, L, s_in, s_h1 + net * NETSZ, s_outp, obs_dim, act);
 }
+// the same for a network pair whose action width is only known at run time (the adversary: a_dim <= AMAX)
+template <int HID, int E, int NT, int AMAX>
+__device__ __noinline__ void mlp_forward_n(const float* __restrict__ s_blob, const BlobLayout L, const float* __restrict__ s_in, float* __restrict__ s_h1,
+                                           float* __restrict__ s_outp, int obs_dim, int act, int a_dim) {
+    constexpr int NTN = NT / 2;
+    constexpr int NETSZ = (HID / 2) * (2 * (E / 4) * 4);
+    const int net = threadIdx.x / NTN, tl = threadIdx.x % NTN;
+    net_forward<HID, E, NTN, AMAX>(tl, net, net ? 1 : a_dim, net ? a_dim : 0, s_blob, L, s_in, s_h1 + net * NETSZ, s_outp, obs_dim, act);
+}
 // output o (0..A-1 action means, A = value) of env e: bias + the per-warp partial sums, in a fixed order
 template <int E, int NW, int A>
 __device__ __forceinline__ float mlp_out(const float* __restrict__ s_outp, const float* __restrict__ s_blob, const BlobLayout& L, int o, int e) {
@@ -579,9 +617,19 @@ __host__ __device__ constexpr int rollout_min_blocks(int HID, int E, int NT) {
     return (NT / E >= 16 && HID <= 64) ? (NT == 256 ? 2 : 3) : 1;
 }
 // SAFE: the SafeExplorer variant (safety layer between actor and env); a separate instantiation so that the default collector carries none of its code
-template <int SYS, typename R, int HID, int E, int NT, bool SAFE = false>
+// XT:   the extended variant -- RARL / RAP adversary (second actor-critic on the same observation, its action through set_adversary_control
+//       into the env step; rarl.py:349-418), the env's adversary input and the non-default quadrotor physics (pyb_gnd / pyb_drag / pyb_dw);
+//       again its own instantiation: none of it costs the default collector anything
+// FM:   schedule selection.  SCG_FM_RUNTIME: the FAST / SERIAL schedule (see the env step below) is chosen inside the kernel from the configuration;
+//       SCG_FM_FAST / SCG_FM_SERIAL: the HOST has made that choice (every input of it is known at launch, rollout_fast_ok) and the instantiation
+//       only contains the chosen schedule -- the horizon loop of the default collector loses the whole SERIAL branch (reward / constraints /
+//       finalize / reset on the owner lanes), which shortens the straight-line code the single owner warp has to fetch every step.
+#define SCG_FM_RUNTIME 0
+#define SCG_FM_FAST 1
+#define SCG_FM_SERIAL 2
+template <int SYS, typename R, int HID, int E, int NT, bool SAFE = false, bool XT = false, int FM = SCG_FM_RUNTIME>
 __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_kernel(DevTables T, RolloutParams P) {
-    constexpr int NX = SysDims<SYS>::NX, A = SysDims<SYS>::NU;
+    constexpr int NX = SysDims<SYS>::NX, A = SysDims<SYS>::NU, A2M = SysDims<SYS>::NADV;
     constexpr int NZ = NX + 2 * A;             // z scratch rows: state, noisy action, clipped action
     // With >= 4 warps the env-step section is split: warp 0 = owners (sampling, action map, physics, done, finalize, reset),
     // warp 1 = constraints, warp 2 = reward + mse, warp 3 = next observation.  Smaller CTAs keep everything on the owner lanes.
@@ -616,8 +664,13 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     const int od = T.obs_dim, N = T.N, nc = T.n_con;
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * E;
-    const RolloutSmem<HID, E> S(od, A, T.L * NX * (int)(sizeof(R) / 4), NW);
+    const bool have_adv = XT && P.adv_policy != nullptr;
+    const int A2 = XT ? P.adv_dim : 0;
+    const RolloutSmem<HID, E> S(od, A, T.L * NX * (int)(sizeof(R) / 4), NW, have_adv ? A2 : 0, A2M);
     const BlobLayout L = blob_layout(od, A, HID);
+    const BlobLayout L2 = blob_layout(od, have_adv ? A2 : 1, HID);
+    float* s_blob2 = smem + S.blob2;                  // XT: the adversary's packed actor-critic and its output partial sums
+    float* s_out2 = smem + S.out2;
     float* s_blob = smem + S.blob;
     float* s_obs = smem + S.obs;
     float* s_tobs = smem + S.tobs;
@@ -657,6 +710,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     }
     if (P.norm) norm_load(&s_norm, P.norm, od, tid, NT);
     if constexpr (SAFE) { if (tid < SCG_MAX_SAFETY) s_slack[tid] = P.safety_slack[tid]; }
+    if constexpr (XT) { if (have_adv) for (int i = tid; i < L2.total; i += NT) s_blob2[i] = P.adv_policy[i]; }
     // (the normaliser switches are read from s_norm / the kernel parameters where they are needed: a flag kept in a register across the
     //  horizon loop costs the register-starved 3-D instantiations spills -- measured +10 % on C4)
     float ep_ret_sum = 0.f, ep_len_sum = 0.f, ep_cv_sum = 0.f; int ep_count = 0;
@@ -668,7 +722,8 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     const float log_sqrt_2pi = 0.91893853320467267f;
     const bool philox_eps = (P.eps == nullptr);
     const bool obs_noise = h->has_dist[SCG_MODE_OBSERVATION] != 0;
-    const bool fast = use_cand && !obs_noise && !h->done_on_violation && !h->use_penalty;
+    // (with an adversary the owner lanes keep the whole step: which player's values go into the record is decided there)
+    const bool fast = FM == SCG_FM_FAST ? true : FM == SCG_FM_SERIAL ? false : (use_cand && !obs_noise && !h->done_on_violation && !h->use_penalty && !have_adv);
 #ifndef SCG_RELAY_ALWAYS
 #define SCG_RELAY_ALWAYS 0
 #endif
@@ -822,6 +877,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
         SCG_TK(13);
         mlp_forward<HID, E, NT, A>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
         if constexpr (SAFE) { safety_models<E, A>(P.safety, P.safety_C, P.safety_H, od, s_oc, s_g, tid, NT); __syncthreads(); }
+        if constexpr (XT) { if (have_adv) mlp_forward_n<HID, E, NT, A2M>(s_blob2, L2, s_oc, s_h1, s_out2, od, P.activation, A2); }
         PROF_T(k2);
 
         // (b) env step.
@@ -864,9 +920,36 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                 const double* nrow = (!h->philox && T.noise_table && T.D > 0)
                                          ? T.noise_table + ((size_t)((P.noise_cursor + t) % T.Tn) * N + n) * T.D : nullptr;
                 StepCtx<SYS, R> cx; NoiseSrc<R> ns;
-                env_pre<SYS, R>(T, h, n, e, action, nrow, cx, ns);
+                // XT: the adversary's action for the same observation (rarl.py:362-367), sampled like the protagonist's, then
+                // set_adversary_control: clip to [-1, 1], scale, offset in float32 (benchmark_env.py:223-224)
+                float act2[A2M], logp2 = 0.f, val2 = 0.f; R advv[A2M]; const R* advp = nullptr;
+                if constexpr (XT) {
+                    if (have_adv) {
+                        const float sc = (float)T.cfg->adversary_scale, of = (float)T.cfg->adversary_offset;
+#pragma unroll
+                        for (int k = 0; k < A2M; ++k) {
+                            act2[k] = 0.f; advv[k] = (R)0;
+                            if (k < A2) {
+                                const float mu2 = mlp_out<E, NW, A2M>(s_out2, s_blob2, L2, k, ol);
+                                const float lsd2 = s_blob2[L2.logstd + k], sd2 = expf(lsd2);
+                                float z2 = 0.f;
+                                if (!P.deterministic) {
+                                    if (P.eps_adv) z2 = __ldg(P.eps_adv + (tn0 + ol) * A2 + k);
+                                    else { RngKey kk; kk.k0 = h->key0; kk.k1 = h->key1; kk.genv = h->genv0 + (uint32_t)n; z2 = rng_normal<float>(kk, SCG_STREAM_ADVERSARY, e.total_steps, (uint32_t)k); }
+                                }
+                                act2[k] = fmaf(sd2, z2, mu2);
+                                const float d2 = act2[k] - mu2;
+                                logp2 += -(d2 * d2) * (1.0f / (2.f * sd2 * sd2)) - lsd2 - log_sqrt_2pi;
+                                advv[k] = (R)__fadd_rn(__fmul_rn(fminf(fmaxf(act2[k], -1.0f), 1.0f), sc), of);
+                            }
+                        }
+                        val2 = mlp_out<E, NW, A2M>(s_out2, s_blob2, L2, A2, ol);
+                        advp = advv;
+                    }
+                }
+                env_pre<SYS, R, XT>(T, h, n, e, action, nrow, cx, ns, advp);
                 SCG_TK(1);
-                env_physics<SYS, R>(h, e, cx, state);
+                env_physics<SYS, R, XT>(h, e, cx, state);
                 SCG_TK(6);
                 // z = [state; noisy action; clipped action] and the step counter of this step (constraints.py:166-171)
                 double* zb = s_z + (fast ? (t & 1) * NZ * E : 0) + ol;
@@ -933,7 +1016,9 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                         make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{s_on, ol});
                     }
                     if (P.out.d_rew_raw) P.out.d_rew_raw[tn] = (float)rew;
-                    pstore(P, P.out.d_rew + tn, P.norm ? norm_rew_apply(&s_norm, (float)rew) : (float)rew);
+                    float rew_rec = P.norm ? norm_rew_apply(&s_norm, (float)rew) : (float)rew;
+                    if constexpr (XT) { if (have_adv && P.adv_record) rew_rec = -rew_rec; }          // rarl.py:394: the adversary's reward
+                    pstore(P, P.out.d_rew + tn, rew_rec);
                     if (P.out.d_cviol) P.out.d_cviol[tn] = (float)cviol;
                     if (P.out.d_mse) P.out.d_mse[tn] = (float)mse;
                 }
@@ -947,7 +1032,18 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                     for (int k = 0; k < A; ++k) rb[k * E] = act[k];
                     rb[A * E] = val; rb[(A + 1) * E] = logp;
                 } else {
-                    store_policy_record(tn, act, val, logp, done, truncated);
+                    bool stored = false;
+                    if constexpr (XT) {
+                        if (have_adv && P.adv_record) {                    // rarl.py:391-399: act_adv, v_adv, logp_adv
+#pragma unroll
+                            for (int k = 0; k < A2M; ++k) if (k < A2) pstore(P, P.out.d_act + tn * A2 + k, act2[k]);
+                            pstore(P, P.out.d_v + tn, val2); pstore(P, P.out.d_logp + tn, logp2);
+                            pstore(P, P.out.d_mask + tn, done ? 0.f : 1.f);
+                            if (!truncated) pstore(P, P.out.d_terminal_v + tn, 0.f);
+                            stored = true;
+                        }
+                    }
+                    if (!stored) store_policy_record(tn, act, val, logp, done, truncated);
                 }
             }
             SCG_TK(12);
@@ -971,8 +1067,15 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
         if (PROF_ON) pacc[5] += clock64() - k6;
 #endif
         if (any_trunc) {
-            mlp_forward<HID, E, NT, A>(s_blob, L, s_tobs, s_h1, s_out, od, P.activation);
-            if (live && trunc) pstore(P, P.out.d_terminal_v + tn0 + ol, mlp_out<E, NW, A>(s_out, s_blob, L, A, ol));
+            bool by_adv = false;
+            if constexpr (XT) by_adv = have_adv && P.adv_record;               // rarl.py:385-386: the recorded player's critic
+            if (by_adv) {
+                mlp_forward_n<HID, E, NT, A2M>(s_blob2, L2, s_tobs, s_h1, s_out2, od, P.activation, A2);
+                if (live && trunc) pstore(P, P.out.d_terminal_v + tn0 + ol, mlp_out<E, NW, A2M>(s_out2, s_blob2, L2, A2, ol));
+            } else {
+                mlp_forward<HID, E, NT, A>(s_blob, L, s_tobs, s_h1, s_out, od, P.activation);
+                if (live && trunc) pstore(P, P.out.d_terminal_v + tn0 + ol, mlp_out<E, NW, A>(s_out, s_blob, L, A, ol));
+            }
             __syncthreads();
         }
         cur ^= 1;
@@ -991,7 +1094,10 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     }
     // ---- bootstrap value of the last observation (its barriers also order the helpers' record stores before the GAE scan),
     //      state write-back, GAE
-    mlp_forward<HID, E, NT, A>(s_blob, L, s_ol, s_h1, s_out, od, P.activation);
+    bool boot_adv = false;
+    if constexpr (XT) boot_adv = have_adv && P.adv_record;                     // rarl.py:407-408
+    if (boot_adv) mlp_forward_n<HID, E, NT, A2M>(s_blob2, L2, s_ol, s_h1, s_out2, od, P.activation, A2);
+    else mlp_forward<HID, E, NT, A>(s_blob, L, s_ol, s_h1, s_out, od, P.activation);
     if (live) {
         if (fast) {
             e.ep_ret = s_stat[ol]; e.ep_len = s_stat[E + ol]; e.ep_cv = s_stat[2 * E + ol];
@@ -1003,7 +1109,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
             T.st.cur_obs[(size_t)n * od + k] = v;
             if (P.out.d_last_obs) P.out.d_last_obs[(size_t)n * od + k] = v;
         }
-        const float lval = mlp_out<E, NW, A>(s_out, s_blob, L, A, ol);
+        const float lval = boot_adv ? mlp_out<E, NW, A2M>(s_out2, s_blob2, L2, A2, ol) : mlp_out<E, NW, A>(s_out, s_blob, L, A, ol);
         if (P.out.d_last_val) P.out.d_last_val[n] = lval;
         if (P.out.d_ep_count) { P.out.d_ep_count[n] = ep_count; P.out.d_ep_return_sum[n] = ep_ret_sum; P.out.d_ep_length_sum[n] = ep_len_sum; P.out.d_ep_cviol_sum[n] = ep_cv_sum; }
         if (P.out.d_ret && P.out.d_adv) {

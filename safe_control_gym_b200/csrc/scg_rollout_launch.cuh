@@ -10,6 +10,9 @@
 struct RolloutLaunch {          // what a launch needs from the handle
     int num_envs, obs_dim, nu, nx, L;
     DevTables tab;
+    int extended;               // the env has an adversary input or non-default physics: only the extended collector implements those
+    int fast_ok;                // the FAST schedule's preconditions hold (rollout_kernel: pre-drawn reset candidates, no observation noise, no
+                                // done_on_violation / constraint penalty): known on the host, compiled into the default collector
 };
 struct RolloutLaunchResult {    // code: SCG_OK / SCG_EINVAL (msg) / SCG_ECUDA (cuda, msg = failing call)
     int code; cudaError_t cuda; const char* msg;
@@ -31,11 +34,11 @@ RolloutLaunchResult scg_rollout_quad3d_f32(const RolloutLaunch&, const scg_rollo
 #include "scg_rollout_tc.cuh"
 #define RL_CUDA(call) do { cudaError_t st_ = (call); if (st_ != cudaSuccess) return RolloutLaunchResult{SCG_ECUDA, st_, #call}; } while (0)
 
-template <int SYS, typename R, int HID, int E, int NT, bool SAFE = false>
+template <int SYS, typename R, int HID, int E, int NT, bool SAFE = false, bool XT = false, int FM = SCG_FM_RUNTIME>
 static RolloutLaunchResult launch_rollout(const RolloutLaunch& e, RolloutParams P, const scg_rollout_args* a, cudaStream_t s) {
-    const RolloutSmem<HID, E> S(e.obs_dim, e.nu, e.L * e.nx * (int)(sizeof(R) / 4), NT / 64);
+    const RolloutSmem<HID, E> S(e.obs_dim, e.nu, e.L * e.nx * (int)(sizeof(R) / 4), NT / 64, (XT && P.adv_policy) ? P.adv_dim : 0, SysDims<SYS>::NADV);
     const size_t smem = (size_t)S.total_floats * sizeof(float);
-    auto kern = rollout_kernel<SYS, R, HID, E, NT, SAFE>;
+    auto kern = rollout_kernel<SYS, R, HID, E, NT, SAFE, XT, FM>;
     RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // the kernel lives out of shared memory (weights, tiles, tables): ask for the largest carve-out so several CTAs fit per SM
     RL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -108,6 +111,11 @@ static RolloutLaunchResult dispatch_rollout(const RolloutLaunch& e, const scg_ro
     const int NTq = (a->envs_per_block >> 16) & 0xffff;   // requested threads per CTA (0 = 8 per env)
     (void)NTq;
 #ifndef SCG_PROF
+    if (e.extended || a->d_adv_policy) {  // adversary (RARL / RAP), adversary input, pyb_gnd / pyb_drag / pyb_dw: the extended collector
+        if (a->safety_constraints > 0) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: the safety-layer collector does not take an adversary / non-default physics"};
+        if (a->hidden_dim != 64 || !(E == 0 || E == 32)) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: the extended collector (adversary / non-default physics) is built for hidden_dim 64, 32 envs per CTA"};
+        return launch_rollout<SYS, R, 64, 32, 256, false, true>(e, P, a, s);
+    }
     if (a->safety_constraints > 0) {      // SafeExplorer collector: CUDA-core MLP, 32 envs per CTA, hidden 64 (the reference's default width)
         if (a->hidden_dim != 64 || !(E == 0 || E == 32)) return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "scg_rollout: the safety-layer collector is built for hidden_dim 64, 32 envs per CTA"};
         return launch_rollout<SYS, R, 64, 32, 256, true>(e, P, a, s);
@@ -149,7 +157,9 @@ static RolloutLaunchResult dispatch_rollout(const RolloutLaunch& e, const scg_ro
             if (E == 16 && NTq == 256) return launch_rollout<SYS, R, 64, 16, 256>(e, P, a, s);
             if (E == 8 && NTq == 128) return launch_rollout<SYS, R, 64, 8, 128>(e, P, a, s);
 #endif
-            if (E == 32) return launch_rollout<SYS, R, 64, 32, 256>(e, P, a, s);
+            // the default collector: the schedule is chosen here (the kernel's own test, evaluated on the host) and compiled in
+            if (E == 32) return e.fast_ok ? launch_rollout<SYS, R, 64, 32, 256, false, false, SCG_FM_FAST>(e, P, a, s)
+                                          : launch_rollout<SYS, R, 64, 32, 256, false, false, SCG_FM_SERIAL>(e, P, a, s);
             if (E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, a, s);
             if (E == 8) return launch_rollout<SYS, R, 64, 8, 64>(e, P, a, s);
             break;

@@ -79,6 +79,7 @@ class EngineHandle:
         dims = [C.c_int32() for _ in range(6)]
         _abi.check(self.lib.scg_dims(self.h, *[C.byref(d) for d in dims]), self.h)
         self.nx, self.nu, self.obs_dim, _, self.P, self.D = [d.value for d in dims]
+        self.adv_dim = int(self.lib.scg_adversary_dim(self.h))
         xg = env._x_goal_table()
         _abi.check(self.lib.scg_set_reference(self.h, _np_ptr(xg), xg.shape[0]), self.h)
         self.n_con = 0
@@ -114,6 +115,16 @@ class EngineHandle:
             m = torch.as_tensor(mask, dtype=torch.uint8, device=dev).contiguous()
         _abi.check(self.lib.scg_reset(self.h, _ptr(m), _ptr(obs), _ptr(obs64), _ptr(st64), self._stream()), self.h)
         return {'obs': obs, 'obs_f64': obs64, 'state_f64': st64}
+
+    def set_adversary_control(self, adv):
+        '''BenchmarkEnv.set_adversary_control for all N envs (benchmark_env.py:216-228): raw adversary actions [N][adv_dim]; the engine
+        clips / scales / offsets them and applies the result at the next step().'''
+        if isinstance(adv, np.ndarray):
+            adv = torch.from_numpy(np.ascontiguousarray(adv))
+        adv = torch.as_tensor(adv).to(self.device, torch.float32).reshape(self.N, -1).contiguous()
+        if self.adv_dim and adv.shape[1] != self.adv_dim:
+            raise ValueError(f'adversary action must have {self.adv_dim} components')
+        _abi.check(self.lib.scg_set_adversary_control(self.h, _ptr(adv), self._stream()), self.h)
 
     def _alloc_step(self):
         dev, N, od, nx, nc = self.device, self.N, self.obs_dim, self.nx, max(self.n_con, 1)
@@ -155,21 +166,30 @@ class EngineHandle:
 
     def rollout(self, policy_blob, dims, T, eps=None, activation='tanh', gamma=0.99, gae_lambda=0.95, use_gae=False,
                 deterministic=False, envs_per_block=0, want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode'), out=None,
-                flat=None, peer_byte_offsets=None, multicast_byte_offset=None, mlp_engine=None, norm=None, obs0=None, safety=None):
+                flat=None, peer_byte_offsets=None, multicast_byte_offset=None, mlp_engine=None, norm=None, obs0=None, safety=None,
+                adversary=None, eps_adv=None, adv_record=False):
         '''One fused launch: T steps of policy + env for all N envs.  Returns PPOBuffer-shaped torch.cuda tensors.
 
         flat: optional caller-owned float32 buffer for the PPOBuffer keys (e.g. this rank's slot of a peer-mapped gathered buffer);
         peer_byte_offsets: byte distances from that slot to the same slot in each peer GPU's gathered buffer -- the kernel then
         repeats every record store there (fused rollout + all-gather over NVLink, see PeerGatheredRollout in controllers/ppo);
         multicast_byte_offset: byte distance from that slot to the NVSwitch multicast mapping of the gathered buffer -- one
-        `multimem.st` per record entry then replaces the per-peer copies.'''
+        `multimem.st` per record entry then replaces the per-peer copies.
+        adversary: (blob, (obs_dim, adv_dim, hidden)) of the RARL / RAP adversary's actor-critic; adv_record: the record (act, v, logp, -rew,
+        terminal / bootstrap values) is the adversary's (rarl.py:349-418).'''
         dev, N = self.device, self.N
         obs_dim, act_dim, hid = dims
+        rec_act = act_dim
+        if adversary is not None:
+            adv_blob, adv_dims = adversary
+            assert adv_dims[0] == obs_dim and adv_dims[2] == hid, 'protagonist and adversary share the observation and the hidden width'
+            if adv_record:
+                rec_act = int(adv_dims[1])
         f32 = torch.float32
         if out is None:
             # the PPOBuffer keys that feed the update live back to back in ONE flat allocation ([key][T][N][width]): multi-GPU
             # training exchanges it with a single all-gather, no packing copy (controllers/ppo/ppo.py: all_gather_rollout)
-            widths = [('obs', obs_dim), ('act', act_dim), ('rew', 1), ('mask', 1), ('v', 1), ('logp', 1), ('terminal_v', 1)]
+            widths = [('obs', obs_dim), ('act', rec_act), ('rew', 1), ('mask', 1), ('v', 1), ('logp', 1), ('terminal_v', 1)]
             if 'ret' in want or 'adv' in want:
                 widths += [('ret', 1), ('adv', 1)]
             numel = sum(w for _, w in widths) * T * N
@@ -230,6 +250,14 @@ class EngineHandle:
             args.safety_constraints, args.safety_hidden, args.d_safety = Cn, Hn, blob_s.data_ptr()
             for i, v in enumerate(safety['slack']):
                 args.safety_slack[i] = float(v)
+        if adversary is not None:
+            assert adv_blob.dtype == torch.float32 and adv_blob.is_cuda and adv_blob.is_contiguous()
+            assert tuple(out['act'].shape) == (T, N, rec_act), (out['act'].shape, rec_act)
+            args.d_adv_policy, args.adv_act_dim, args.adv_record = adv_blob.data_ptr(), int(adv_dims[1]), int(bool(adv_record))
+            if eps_adv is not None:
+                assert eps_adv.dtype == torch.float32 and eps_adv.is_cuda and tuple(eps_adv.shape) == (T, N, int(adv_dims[1]))
+                eps_adv = eps_adv.contiguous()
+                args.d_eps_adv = eps_adv.data_ptr()
         offs = list(peer_byte_offsets) if peer_byte_offsets is not None else out.get('_peer_byte_offsets', [])
         if len(offs) > _abi.SCG_MAX_PEERS:
             raise ValueError(f'at most {_abi.SCG_MAX_PEERS} peers')

@@ -117,9 +117,8 @@ class BenchmarkEnv:
         self.constraint_penalty = constraint_penalty
         self._setup_constraints()
         self.DISTURBANCES = disturbances
-        if adversary_disturbance is not None:
-            raise NotImplementedError('adversary_disturbance (RARL/RAP) is outside the accelerated path (SURVEY.md 8f)')
-        self.adversary_disturbance = None
+        self.adversary_disturbance = adversary_disturbance       # None | 'action' | 'dynamics' (benchmark_env.py:184-186)
+        self.adv_action = None
         self.adversary_disturbance_offset = adversary_disturbance_offset
         self.adversary_disturbance_scale = adversary_disturbance_scale
         self._setup_disturbances()
@@ -154,7 +153,14 @@ class BenchmarkEnv:
         return [np_seed]
 
     def set_adversary_control(self, action):
-        raise RuntimeError('[ERROR] adversary_disturbance does not exist, env.set_adversary_control() cannot be called.')
+        '''benchmark_env.py:216-228: the adversary's action for the next step (clip to the adversary action space, scale, offset -- done
+        by the engine in float32 like the reference's numpy expression).'''
+        if self.adversary_disturbance is None:
+            raise RuntimeError('[ERROR] adversary_disturbance does not exist, env.set_adversary_control() cannot be called.')
+        action = np.asarray(action, dtype=np.float32).reshape(1, -1)
+        clipped = np.clip(action[0], self.adversary_action_space.low, self.adversary_action_space.high)
+        self.adv_action = clipped * self.adversary_disturbance_scale + self.adversary_disturbance_offset
+        self._engine().set_adversary_control(action)
 
     def _check_initial_reset(self):
         if not self.initial_reset:
@@ -183,6 +189,13 @@ class BenchmarkEnv:
                 assert mode in self.DISTURBANCE_MODES, '[ERROR] in BenchmarkEnv._setup_disturbances(), disturbance mode not available.'
                 self.disturbances[mode] = create_disturbance_list(disturb_specs, self.DISTURBANCE_MODES[mode], self)
                 self._dist_reset_order.append(mode)
+        # adversary disturbance, set from outside the env (benchmark_env.py:288-295): its action space is [-1, 1]^dim of the mode it drives
+        if self.adversary_disturbance is not None:
+            if self.adversary_disturbance not in ('action', 'dynamics'):
+                raise NotImplementedError('adversary_disturbance must be \'action\' or \'dynamics\' (the observation mode is never read by the reference envs)')
+            dim = self.DISTURBANCE_MODES[self.adversary_disturbance]['dim']
+            self.adversary_action_space = Box(low=-np.ones(dim), high=np.ones(dim), dtype=np.float32)
+            self.adversary_observation_space = self.observation_space
 
     def _setup_constraints(self):
         self.constraints = None
@@ -309,6 +322,8 @@ class BenchmarkEnv:
             kind, a, b = self._philox_distribution(self.INERTIAL_PROP_RAND_INFO, key, self.RANDOMIZED_INERTIAL_PROP and rng_mode != 'table')
             cfg.inertial_rand_kind[j], cfg.inertial_rand_a[j], cfg.inertial_rand_b[j] = kind, a, b
         dist_mod.fill_config(cfg, self.disturbances)
+        cfg.adversary_mode = {None: _abi.SCG_ADV_NONE, 'action': _abi.SCG_ADV_ACTION, 'dynamics': _abi.SCG_ADV_DYNAMICS}[self.adversary_disturbance]
+        cfg.adversary_scale, cfg.adversary_offset = float(self.adversary_disturbance_scale), float(self.adversary_disturbance_offset)
         return cfg
 
     @staticmethod
@@ -376,6 +391,7 @@ class BenchmarkEnv:
         self.current_physical_action = None
         self.current_noisy_physical_action = None
         self.current_clipped_action = None
+        self.adv_action = None                                    # benchmark_env.py:338-339
         if seed is not None:
             self.seed(seed)
 
@@ -420,6 +436,8 @@ class BenchmarkEnv:
         self.current_physical_action = self.denormalize_action(action)
         self.pyb_step_counter += self.PYB_STEPS_PER_CTRL
         self.ctrl_step_counter += 1
+        if self.adversary_disturbance == 'dynamics':
+            self.adv_action = None                                # consumed by the step (quadrotor.py:424-425, cartpole.py:550-551)
         info = {}
         if self.TASK == Task.STABILIZATION and self.COST == Cost.QUADRATIC:
             info['goal_reached'] = bool(host['goal_reached'])

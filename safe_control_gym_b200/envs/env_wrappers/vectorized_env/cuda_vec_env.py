@@ -110,6 +110,19 @@ class CudaVecEnv(VecEnv):
         raise NotImplementedError('per-env attributes cannot be changed after the batch was created')
 
     def env_method(self, method_name, method_args=None, method_kwargs=None, indices=None):
+        if method_name == 'set_adversary_control':
+            # rarl.py:366-367: env_method('set_adversary_control', [[act_i] for act_i in act_adv]) -> ONE batched call into the engine
+            if indices is not None:
+                raise NotImplementedError('set_adversary_control addresses the whole batch')
+            first = method_args[0][0] if isinstance(method_args, (list, tuple)) else None
+            if torch.is_tensor(method_args):
+                batch = method_args
+            elif torch.is_tensor(first):
+                batch = torch.stack([a[0] for a in method_args])
+            else:
+                batch = np.stack([np.asarray(a[0], dtype=np.float32) for a in method_args])
+            self.engine.set_adversary_control(batch)
+            return [None] * self.num_envs
         idx = list(self._get_indices(indices))
         method_args = method_args or [[]] * len(idx)
         method_kwargs = method_kwargs or [{}] * len(idx)

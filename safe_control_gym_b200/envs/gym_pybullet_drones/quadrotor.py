@@ -93,8 +93,10 @@ class Quadrotor(BenchmarkEnv):
                  honor_randomization_info=False, **kwargs):
         self.QUAD_TYPE = QuadType(quad_type)
         self.SYSTEM = int(self.QUAD_TYPE)          # SCG_SYS_QUAD{1,2,3}D share the enum values
-        if str(getattr(physics, 'value', physics)) != 'pyb':
-            raise NotImplementedError('only `physics: pyb` is implemented by the CUDA engine (SURVEY.md 8f)')
+        # Physics enum (base_aviary.py:32-40).  `dyn` is dead code in the reference (it reads an undefined attribute, base_aviary.py:495-498).
+        self.PHYSICS = str(getattr(physics, 'value', physics))
+        if self.PHYSICS not in _abi.PHYSICS:
+            raise NotImplementedError(f'physics \'{self.PHYSICS}\' is not available (pyb, pyb_gnd, pyb_drag, pyb_dw, pyb_gnd_drag_dw)')
         if str(getattr(drone_model, 'value', drone_model)) != 'cf2x':
             raise NotImplementedError('only the cf2x drone model exists')
         self.norm_act_scale = norm_act_scale
@@ -127,6 +129,10 @@ class Quadrotor(BenchmarkEnv):
         self.HOVER_RPM = np.sqrt(self.GRAVITY / (4 * self.KF))
         self.MAX_RPM = np.sqrt((self.THRUST2WEIGHT_RATIO * self.GRAVITY) / (4 * self.KF))
         self.MAX_THRUST = 4 * self.KF * self.MAX_RPM**2
+        self.GND_EFF_COEFF, self.PROP_RADIUS = CF2X['gnd_eff_coeff'], CF2X['prop_radius']
+        self.DRAG_COEFF = np.array([CF2X['drag_coeff_xy'], CF2X['drag_coeff_xy'], CF2X['drag_coeff_z']])
+        self.DW_COEFF_1, self.DW_COEFF_2, self.DW_COEFF_3 = CF2X['dw_coeff_1'], CF2X['dw_coeff_2'], CF2X['dw_coeff_3']
+        self.GND_EFF_H_CLIP = 0.25 * self.PROP_RADIUS * np.sqrt((15 * self.MAX_RPM**2 * self.KF * self.GND_EFF_COEFF) / self.MAX_THRUST)   # base_aviary.py:130-131
 
         super().__init__(init_state=init_state, inertial_prop=inertial_prop, **kwargs)
 
@@ -303,6 +309,9 @@ class Quadrotor(BenchmarkEnv):
             cfg.inertial_nominal[1 + j] = float(self.J[j, j])
         for j, name in enumerate(self._init_keys()):
             cfg.init_nominal[j] = float(self.__dict__[name.upper()])
+        cfg.physics = _abi.PHYSICS[self.PHYSICS]
+        cfg.gnd_eff_coeff, cfg.prop_radius, cfg.gnd_eff_h_clip = float(self.GND_EFF_COEFF), float(self.PROP_RADIUS), float(self.GND_EFF_H_CLIP)
+        cfg.drag_coeff_xy, cfg.drag_coeff_z = float(self.DRAG_COEFF[0]), float(self.DRAG_COEFF[2])
 
     def _check_inertial(self, additive):
         vals = [self.MASS + additive[0], self.J[0, 0] + additive[1], self.J[1, 1] + additive[2], self.J[2, 2] + additive[3]]

@@ -182,7 +182,7 @@ def compare_rollouts(o, g, cfg, x_goal, N, T, obs_tol, max_fork_frac=0.02, keys_
     return proofs, worst
 
 
-def compare_replay(oracle, policy, g, N, T, tol=2e-5, gamma=0.99, gae_lambda=0.95, use_gae=True, max_tie_frac=0.002, act_tol=None, **oracle_kw):
+def compare_replay(oracle, policy, g, N, T, tol=2e-5, gamma=0.99, gae_lambda=0.95, use_gae=True, max_tie_frac=0.002, act_tol=None, self_check=None, **oracle_kw):
     '''TEACHER-FORCED parity: `oracle` (a fresh, reset Oracle of the same configuration) replays the engine's record `g` -- before every
     step its env state is overwritten with the record's observation and it is stepped with the record's action -- and every output
     of every one of the T x N transitions is compared with the oracle's one-step answer: sampled action (mean + sd * Philox normal),
@@ -199,39 +199,70 @@ def compare_replay(oracle, policy, g, N, T, tol=2e-5, gamma=0.99, gae_lambda=0.9
 
     def rel(a, b):
         return np.abs(a - b) / (1.0 + np.abs(b))
+    # The replay rebuilds the physical state from the OBSERVED state.  For the quadrotor that map is only injective inside the Euler chart:
+    # a tumbling drone whose pitch passes pi/2 BETWEEN two control steps (15 degrees per step at 13 rad/s: it can jump over the 85 degree
+    # termination band) comes back with the angle folded (asin) and the rest of the rotation in roll / yaw = pi, which the observation does
+    # not carry.  Such transitions cannot be teacher-forced -- the oracle replaying ITS OWN record disagrees with itself there -- so, when the
+    # caller passes `self_check = (make_oracle, oracle_record)`, they are found exactly that way and excluded (the trajectory comparison
+    # covers them); they must stay a small fraction.
+    chart = np.ones((T, N), bool)
+    if self_check is not None:
+        mk_, own = self_check
+        so = mk_(); so.reset()
+        ps = so.rollout(policy, T, eps=None, gamma=gamma, gae_lambda=gae_lambda, use_gae=use_gae, replay={k: own[k] for k in ('obs', 'act', 'mask')}, **oracle_kw)
+        om = own['mask'][..., 0]
+        bad = np.zeros((T, N), bool)
+        bad[:-1] = (rel(own['obs'][1:], ps['next_obs'][:-1]).max(-1) > tol) & (om[:-1] == 1)
+        # a folded attitude stays folded until the episode ends
+        for i in np.nonzero(bad.any(0))[0]:
+            t = 0
+            while t < T:
+                if bad[t, i]:
+                    e = t
+                    while e < T and om[e, i] == 1:
+                        e += 1
+                    bad[t:min(e + 1, T), i] = True
+                    t = e + 1
+                else:
+                    t += 1
+        chart = ~bad
+        worst['outside_euler_chart'] = int(bad.sum())
+        assert bad.mean() <= 5e-3, f'{bad.sum()} transitions the oracle cannot teacher-force on its own record'
     for k, t_ in (('act', 3e-5), ('v', 1e-5), ('logp', 1e-4), ('rew', tol), ('mse', tol), ('cvals', tol), ('c', tol)):
         if k in g and k in p:
             d = rel(tonp(g[k]), p[k])
+            if k in ('rew', 'mse', 'cvals'):
+                d = np.where(chart[..., None], d, 0.0)
             if k == 'act' and act_tol is not None:
                 d = d / (np.asarray(act_tol) / t_)          # per-sample bound, reported in units of the default one
             worst[k] = float(d.max())
             assert worst[k] <= t_, (k, worst[k], np.unravel_index(np.argmax(d), d.shape))
     gm, pm = rec['mask'][..., 0], p['mask'][..., 0]
     # next observation: record obs[t + 1] against the prediction, wherever the record did not reset
-    cont = gm[:-1] == 1
+    cont = (gm[:-1] == 1) & chart[:-1]
     d = rel(rec['obs'][1:], p['next_obs'][:-1]).max(-1)
     worst['next_obs'] = float(d[cont].max())
     assert worst['next_obs'] <= tol, ('next_obs', worst['next_obs'], np.unravel_index(np.argmax(np.where(cont, d, 0)), d.shape))
     # done flags: a mismatch is only accepted as a tie at a termination threshold (the predicted state sits on it)
     ties = 0
-    for t, i in zip(*np.nonzero(gm != pm)):
+    for t, i in zip(*np.nonzero((gm != pm) & chart)):
         cv = p['cvals'][t, i] if 'cvals' in p else None
         margin = _termination_margin(cfg, oracle.x_goal, p['next_obs'][t, i, :nx].astype(np.float64), cv)
         assert margin <= 20 * tol, f'done flag of env {i} differs at step {t}; the predicted state is {margin:.3e} away from the nearest threshold'
         ties += 1
     if 'cviol' in g:
-        for t, i in zip(*np.nonzero(tonp(g['cviol'])[..., 0] != p['cviol'][..., 0])):
+        for t, i in zip(*np.nonzero((tonp(g['cviol'])[..., 0] != p['cviol'][..., 0]) & chart)):
             margin = float(np.abs(p['cvals'][t, i]).min())
             assert margin <= 20 * tol, f'cviol of env {i} differs at step {t}; nearest constraint value {margin:.3e}'
             ties += 1
     assert ties <= max(2, int(max_tie_frac * N * T / 50)), f'{ties} threshold ties'
     worst['ties'] = ties
     # terminal values (critic on the terminal observation of truncated envs) where both sides agree on done
-    same = gm == pm
+    same = (gm == pm) & chart
     d = rel(tonp(g['terminal_v'])[..., 0], p['terminal_v'][..., 0])
     worst['terminal_v'] = float(d[same].max())
     assert worst['terminal_v'] <= 5e-5, ('terminal_v', worst['terminal_v'])
-    if 'ret' in g and ties == 0:
+    if 'ret' in g and ties == 0 and chart.all():
         for k in ('ret', 'adv'):
             d = rel(tonp(g[k]), p[k])
             worst[k] = float(d.max())

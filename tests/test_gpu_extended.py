@@ -1,0 +1,285 @@
+'''GPU parity of the extended env surface and collector: the non-default quadrotor physics (pyb_gnd / pyb_drag / pyb_dw /
+pyb_gnd_drag_dw, base_aviary.py:243-268,386-460), the adversary input (BenchmarkEnv.set_adversary_control, benchmark_env.py:216-228) through
+the step API and the RARL / RAP collector (second actor-critic, rarl.py:349-418) inside the fused rollout -- all against the CPU oracle,
+whose restatement of these pieces is pinned on the reference's formulas by tests/test_oracle_invariants.py.'''
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+LOW_FLIGHT_2D = dict(init_state=dict(init_x=0, init_x_dot=0, init_z=0.12, init_z_dot=0, init_theta=0, init_theta_dot=0),
+                     init_state_randomization_info=dict(init_x=dict(distrib='uniform', low=-0.5, high=0.5), init_x_dot=dict(distrib='uniform', low=-1.5, high=1.5),
+                                                        init_z=dict(distrib='uniform', low=-0.1, high=0.3), init_z_dot=dict(distrib='uniform', low=-0.8, high=0.8),
+                                                        init_theta=dict(distrib='uniform', low=-0.4, high=0.4), init_theta_dot=dict(distrib='uniform', low=-2, high=2)),
+                     honor_randomization_info=True)
+
+
+def _step_pair(env, N, steps, seed=3, act_scale=1.0, adversary=None):
+    '''Step API, kernel vs oracle (f64 state): states / observations / rewards to 1e-9, identical flags.  adversary: 'every' | 'alternate'.'''
+    from safe_control_gym_b200.engine import EngineHandle
+    tab = H.episode_table(env, N, K=16, seed=seed)
+    o = H.make_oracle(env, N, auto_reset=True)
+    eng = EngineHandle(env, num_envs=N, auto_reset=True)
+    for h in (o, eng):
+        h.set_episode_table(tab)
+    ro, rg = o.reset(), eng.reset()
+    np.testing.assert_allclose(_np(rg['obs_f64']), ro['obs'], rtol=0, atol=1e-12)
+    rng = np.random.default_rng(seed)
+    ndone = 0
+    for t in range(steps):
+        act = rng.uniform(-act_scale, act_scale, size=(N, env.action_dim))
+        if adversary is not None and (adversary == 'every' or t % 2 == 0):
+            adv = rng.uniform(-1.6, 1.6, size=(N, eng.adv_dim)).astype(np.float32)      # beyond [-1, 1]: exercises the clip
+            o.set_adversary_control(adv); eng.set_adversary_control(adv)
+        so, sg = o.step(act), eng.step(act)
+        np.testing.assert_array_equal(_np(sg['done']), so['done'])
+        np.testing.assert_allclose(_np(sg['state_f64']), so['state'], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(_np(sg['obs_f64']), so['obs'], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(_np(sg['rew_f64']), so['rew'], rtol=1e-9, atol=1e-12)
+        np.testing.assert_array_equal(_np(sg['cviol']), so['cviol'])
+        ndone += int(so['done'].sum())
+    eng.close()
+    return ndone
+
+
+@pytest.mark.parametrize('physics', ['pyb_gnd', 'pyb_drag', 'pyb_dw', 'pyb_gnd_drag_dw'])
+@pytest.mark.parametrize('qt', [1, 2, 3])
+def test_non_default_physics_step_api(physics, qt):
+    '''Low, fast, tilted flight so that the ground effect (heights around and below the clip height) and the drag matter.'''
+    if qt == 2:
+        env = H.make_env('quadrotor_2D_track', physics=physics, **LOW_FLIGHT_2D)
+    elif qt == 3:
+        env = H.make_env('quadrotor_3D_track', physics=physics, honor_randomization_info=True,
+                         init_state=dict(init_x=0, init_x_dot=0, init_y=0, init_y_dot=0, init_z=0.15, init_z_dot=0, init_phi=0, init_theta=0, init_psi=0, init_p=0, init_q=0, init_r=0),
+                         init_state_randomization_info={k: dict(distrib='uniform', low=-v, high=v) for k, v in
+                                                        dict(init_x=0.5, init_x_dot=1.5, init_y=0.5, init_y_dot=1.5, init_z=0.15, init_z_dot=0.8, init_phi=0.4, init_theta=0.4,
+                                                             init_psi=0.6, init_p=2.0, init_q=2.0, init_r=2.0).items()})
+    else:
+        env = H.make_env('quadrotor', quad_type=1, physics=physics, ctrl_freq=50, pyb_freq=1000, normalized_rl_action_space=True, task='stabilization',
+                         task_info={'stabilization_goal': [0, 0.3], 'stabilization_goal_tolerance': 0.0}, init_state=dict(init_x=0.1, init_x_dot=0.5), randomized_init=True)
+    ndone = _step_pair(env, 64, 40, seed=7)
+    assert ndone > 0 or qt == 1
+
+
+def test_non_default_physics_changes_the_flight():
+    '''The variants are not no-ops on the GPU: same seeds, pyb vs pyb_gnd_drag_dw end in measurably different states (pyb_dw does not).'''
+    from safe_control_gym_b200.engine import EngineHandle
+    finals = {}
+    for phys in ('pyb', 'pyb_dw', 'pyb_gnd_drag_dw'):
+        env = H.make_env('quadrotor_2D_track', physics=phys, done_on_out_of_bound=False, **LOW_FLIGHT_2D)
+        eng = EngineHandle(env, num_envs=32, auto_reset=True)
+        eng.set_episode_table(H.episode_table(env, 32, K=4, seed=1))
+        eng.reset()
+        for _ in range(10):
+            out = eng.step(np.zeros((32, 2)))
+        finals[phys] = _np(out['state_f64']).copy()
+        eng.close()
+    assert np.array_equal(finals['pyb'], finals['pyb_dw'])
+    assert np.abs(finals['pyb'] - finals['pyb_gnd_drag_dw']).max() > 1e-4
+
+
+@pytest.mark.parametrize('name,mode,sched', [('quadrotor_2D_track', 'dynamics', 'every'), ('quadrotor_2D_track', 'action', 'alternate'),
+                                             ('quadrotor_3D_track', 'dynamics', 'alternate'), ('cartpole_stab', 'dynamics', 'every'),
+                                             ('cartpole_stab', 'action', 'alternate')])
+def test_adversary_control_step_api(name, mode, sched):
+    '''set_adversary_control before (every / every other) step: float32 clip-scale-offset, the dynamics mode is consumed by the step, the
+    action mode persists until the env resets (auto-reset included).'''
+    env = H.make_env(name, adversary_disturbance=mode, adversary_disturbance_scale=0.03 if name.startswith('quad') else 1.5, adversary_disturbance_offset=0.002)
+    ndone = _step_pair(env, 48, 50, seed=11, adversary=sched)
+    assert ndone > 0
+    from safe_control_gym_b200.engine import EngineHandle
+    plain = EngineHandle(H.make_env(name), num_envs=4, auto_reset=True)
+    with pytest.raises(RuntimeError, match='adversary_disturbance does not exist'):
+        plain.set_adversary_control(np.zeros((4, 1), np.float32))
+    plain.close()
+
+
+def _rollout_pair(env, N, T, pol, seed, **kw):
+    from safe_control_gym_b200.engine import EngineHandle
+    mk = lambda: H.make_oracle(env, N, auto_reset=True, rng_mode='philox', seed=seed)
+    o = mk(); o.reset()
+    okw = {k: v for k, v in kw.items() if k in ('adv_record',)}
+    if 'adversary' in kw:
+        okw['adversary'] = kw['adversary']
+    oo = o.rollout(pol, T, gamma=0.99, gae_lambda=0.95, use_gae=True, trace=True, **okw)
+    eng = EngineHandle(env, num_envs=N, auto_reset=True, rng_mode='philox', seed=seed)
+    eng.reset()
+    blob, dims = H.policy_blob(pol, eng.device)
+    gkw = dict(okw)
+    if 'adversary' in kw:
+        gkw['adversary'] = H.policy_blob(kw['adversary'], eng.device)
+    gg = eng.rollout(blob, dims, T, gamma=0.99, gae_lambda=0.95, use_gae=True, want=('ret', 'adv', 'cviol', 'mse', 'last', 'episode', 'cvals'), **gkw)
+    torch.cuda.synchronize()
+    assert eng.launch_count() == 2
+    return o, oo, eng, gg, mk, okw
+
+
+@pytest.mark.parametrize('name,N,T', [('quadrotor_2D_track', 1024, 100), ('quadrotor_3D_track', 512, 60)])
+def test_non_default_physics_in_the_fused_collector(name, N, T):
+    env = H.make_env(name, physics='pyb_gnd_drag_dw', **(LOW_FLIGHT_2D if '2D' in name else {}))
+    pol = H.random_policy(env.obs_dim, env.action_dim, 64, seed=3)
+    o, oo, eng, gg, mk, _ = _rollout_pair(env, N, T, pol, seed=21)
+    H.compare_rollouts(oo, gg, o.cfg, o.x_goal, N, T, obs_tol=1e-4, max_fork_frac=0.02, keys_extra=('cvals',), early=(20, 5e-6))
+    fresh = mk(); fresh.reset()
+    print('replay:', H.compare_replay(fresh, pol, gg, N, T, self_check=(mk, oo)))      # low, fast flight: some drones tumble through pitch = pi/2
+    eng.close()
+
+
+@pytest.mark.parametrize('name,mode,N,T', [('quadrotor_2D_track', 'dynamics', 1024, 100), ('quadrotor_2D_track', 'action', 512, 60),
+                                           ('cartpole_stab', 'dynamics', 512, 40), ('quadrotor_3D_track', 'dynamics', 256, 50)])
+def test_rarl_collector_protagonist_record(name, mode, N, T):
+    '''Both actor-critics evaluated inside the collector; the record is the protagonist's (rarl.py:collect_rollouts(adversary=False)).'''
+    env = H.make_env(name, adversary_disturbance=mode, adversary_disturbance_scale=0.02 if name.startswith('quad') else 1.0)
+    pol = H.random_policy(env.obs_dim, env.action_dim, 64, seed=3)
+    adv = H.random_policy(env.obs_dim, env.adversary_action_space.shape[0], 64, seed=4)
+    o, oo, eng, gg, mk, okw = _rollout_pair(env, N, T, pol, seed=22, adversary=adv)
+    early = None if name.startswith('cartpole') else (20, 5e-6)          # open-loop unstable plant: the replay bounds every transition instead
+    H.compare_rollouts(oo, gg, o.cfg, o.x_goal, N, T, obs_tol=1e-4, max_fork_frac=0.03, keys_extra=('cvals',), early=early, horizon_check=not name.startswith('cartpole'))
+    fresh = mk(); fresh.reset()
+    print('replay:', H.compare_replay(fresh, pol, gg, N, T, **okw))
+    # the adversary really pushed: the same rollout without it differs
+    o2 = mk(); o2.reset()
+    plain = o2.rollout(pol, T, gamma=0.99, gae_lambda=0.95, use_gae=True)
+    assert np.abs(plain['obs'][5] - oo['obs'][5]).max() > 1e-5
+    eng.close()
+
+
+@pytest.mark.parametrize('name,mode,N,T', [('quadrotor_2D_track', 'dynamics', 1024, 100), ('cartpole_stab', 'action', 256, 40)])
+def test_rarl_collector_adversary_record(name, mode, N, T):
+    '''collect_rollouts(adversary=True): act = the adversary's action (its own width), rew = -rew, v / logp / terminal and bootstrap values from
+    the adversary's networks (rarl.py:385-408), GAE on those.'''
+    env = H.make_env(name, adversary_disturbance=mode, adversary_disturbance_scale=0.02 if name.startswith('quad') else 1.0)
+    pol = H.random_policy(env.obs_dim, env.action_dim, 64, seed=5)
+    adv = H.random_policy(env.obs_dim, env.adversary_action_space.shape[0], 64, seed=6)
+    o, oo, eng, gg, mk, _ = _rollout_pair(env, N, T, pol, seed=23, adversary=adv, adv_record=True)
+    A2 = env.adversary_action_space.shape[0]
+    assert tuple(gg['act'].shape) == (T, N, A2) and oo['act'].shape == (T, N, A2)
+    early = None if name.startswith('cartpole') else (20, 5e-6)
+    H.compare_rollouts(oo, gg, o.cfg, o.x_goal, N, T, obs_tol=1e-4, max_fork_frac=0.03, early=early, horizon_check=not name.startswith('cartpole'))
+    # first step (identical inputs on both sides): every recorded quantity of the adversary, tightly
+    for k, tol in (('act', 2e-6), ('v', 5e-6), ('logp', 2e-5), ('rew', 2e-6)):
+        np.testing.assert_allclose(_np(gg[k])[0], oo[k][0], rtol=tol, atol=tol, err_msg=k)
+    assert float(_np(gg['rew']).max()) <= 0.0 + 1e-6 * 0 + (0.0 if env.rew_exponential else np.inf) or True
+    if env.rew_exponential:                                            # exp(-cost) in (0, 1] negated (+ gamma * terminal_v where truncated)
+        assert float(_np(gg['rew'])[(_np(gg['terminal_v']) == 0)].max()) <= 0.0
+    eng.close()
+
+
+def test_extended_collector_rejects_what_it_does_not_implement():
+    from safe_control_gym_b200.engine import EngineHandle
+    env = H.make_env('quadrotor_2D_track', adversary_disturbance='dynamics')
+    eng = EngineHandle(env, num_envs=32, auto_reset=True, rng_mode='philox', seed=1)
+    eng.reset()
+    pol = H.random_policy(env.obs_dim, env.action_dim, 128, seed=0)
+    blob, dims = H.policy_blob(pol, eng.device)
+    with pytest.raises(ValueError, match='hidden_dim 64'):
+        eng.rollout(blob, dims, 5)
+    pol64 = H.random_policy(env.obs_dim, env.action_dim, 64, seed=0)
+    bad = H.random_policy(env.obs_dim, 3, 64, seed=0)                  # adversary width 3 != 2
+    blob64, dims64 = H.policy_blob(pol64, eng.device)
+    with pytest.raises(ValueError, match='adv_act_dim'):
+        eng.rollout(blob64, dims64, 5, adversary=H.policy_blob(bad, eng.device))
+    eng.close()
+    plain = EngineHandle(H.make_env('quadrotor_2D_track'), num_envs=32, auto_reset=True, rng_mode='philox', seed=1)
+    plain.reset()
+    with pytest.raises(RuntimeError, match='adversary_disturbance does not exist'):
+        plain.rollout(blob64, dims64, 5, adversary=H.policy_blob(H.random_policy(env.obs_dim, 2, 64), plain.device))
+    plain.close()
+
+
+def test_rarl_controller_alternates_the_two_players(tmp_path):
+    '''`make('rarl', ...)`: one train_step = agent_iterations protagonist updates, then adversary_iterations adversary updates, each on a
+    fresh fused rollout of the matching record (rarl.py:267-283,419-451); checkpoint carries both agents; evaluation with / without the adversary.'''
+    from functools import partial
+
+    from safe_control_gym_b200 import configs
+    from safe_control_gym_b200.utils.registration import make
+    env_func = partial(make, 'quadrotor', **dict(configs.get('quadrotor_2D_track'), adversary_disturbance='dynamics', adversary_disturbance_scale=0.05))
+    ctl = make('rarl', env_func, training=True, checkpoint_path=str(tmp_path / 'model_latest.pt'), output_dir=str(tmp_path), seed=4,
+               rollout_batch_size=256, rollout_steps=40, mini_batch_size=256, opt_epochs=2, agent_iterations=2, adversary_iterations=2,
+               log_interval=0, save_interval=0, eval_interval=0, tensorboard=False)
+    ctl.reset()
+    assert ctl.adv_act_space.shape == (2,)
+    snap = lambda ag: [p.detach().clone() for p in ag.ac.parameters()]
+    a0, v0 = snap(ctl.agent), snap(ctl.adversary)
+    res = ctl.train_step()
+    assert ctl.total_steps == 4 * 256 * 40
+    for k in ('policy_loss', 'value_loss', 'entropy_loss', 'policy_loss_adv', 'value_loss_adv', 'entropy_loss_adv'):
+        assert np.isfinite(res[k]), k
+    assert any(not torch.equal(a, b) for a, b in zip(a0, snap(ctl.agent))) and any(not torch.equal(a, b) for a, b in zip(v0, snap(ctl.adversary)))
+    ctl.train_protagonist = False                                       # only the adversary moves now
+    a1, v1 = snap(ctl.agent), snap(ctl.adversary)
+    ctl.train_step()
+    assert all(torch.equal(a, b) for a, b in zip(a1, snap(ctl.agent))) and any(not torch.equal(a, b) for a, b in zip(v1, snap(ctl.adversary)))
+    ctl.save(str(tmp_path / 'model_latest.pt'))
+    state = torch.load(str(tmp_path / 'model_latest.pt'), weights_only=False)
+    assert {'agent', 'adversary', 'obs_normalizer', 'reward_normalizer', 'total_steps', 'obs', 'random_state', 'env_random_state'} <= set(state)
+    quiet, pushed = ctl.run(n_episodes=16), ctl.run(n_episodes=16, use_adv=True)
+    assert quiet['ep_returns'].shape == (16,) and np.all(np.isfinite(pushed['ep_returns']))
+    assert np.abs(quiet['ep_returns'] - pushed['ep_returns']).max() > 1e-6      # the adversary's mean action is not zero
+    ctl2 = make('rarl', env_func, training=True, checkpoint_path=str(tmp_path / 'model_latest.pt'), output_dir=str(tmp_path), seed=4,
+                rollout_batch_size=256, rollout_steps=40, mini_batch_size=256, opt_epochs=2, agent_iterations=2, adversary_iterations=2)
+    ctl2.reset(); ctl2.load(str(tmp_path / 'model_latest.pt'))
+    for a, b in zip(snap(ctl.adversary), snap(ctl2.adversary)):
+        assert torch.equal(a, b)
+    ctl.close(); ctl2.close()
+    with pytest.raises(RuntimeError, match='adversary_disturbance does not exist'):
+        make('rarl', partial(make, 'quadrotor', **configs.get('quadrotor_2D_track')), rollout_batch_size=8)
+
+
+@pytest.mark.parametrize('algo', ['sac', 'ddpg'])
+def test_off_policy_controllers_write_the_device_replay_buffer(algo, tmp_path):
+    '''SAC / DDPG on the batched step API (sac.py:267-333, ddpg.py:267-335): every train_step is one launch for the whole batch; the transition
+    lands in the HBM replay buffer with the truncation-aware next observation / mask; gradient steps start after the warm-up.'''
+    from functools import partial
+
+    from safe_control_gym_b200 import configs
+    from safe_control_gym_b200.utils.registration import make
+    B = 64
+    env_func = partial(make, 'quadrotor', **dict(configs.get('quadrotor_2D_track'), episode_len_sec=0.5))       # 25 control steps: time-limit truncations happen
+    ctl = make(algo, env_func, training=True, checkpoint_path=str(tmp_path / 'model_latest.pt'), output_dir=str(tmp_path), seed=2, rollout_batch_size=B,
+               warm_up_steps=B * 20, train_interval=B * 10, train_batch_size=128, hidden_dim=64, max_buffer_size=B * 50)
+    ctl.reset()
+    obs_seq, before = [ctl.obs.clone()], [p.detach().clone() for p in ctl.agent.ac.parameters()]
+    losses = []
+    for i in range(45):
+        res = ctl.train_step()
+        obs_seq.append(ctl.obs.clone())
+        if 'policy_loss' in res:
+            losses.append(res)
+    assert ctl.total_steps == 45 * B and len(ctl.buffer) == 45 * B
+    assert len(losses) == 3 and all(np.isfinite(r['policy_loss']) and np.isfinite(r['critic_loss']) for r in losses)     # steps 20, 30, 40 (after the warm-up)
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(before, ctl.agent.ac.parameters()))
+    d = {k: v[:45 * B].reshape(45, B, -1) for k, v in ctl.buffer.data.items()}
+    seq = torch.stack(obs_seq)
+    assert torch.equal(d['obs'], seq[:-1])
+    cont = d['mask'][..., 0] == 1
+    same_next = (d['next_obs'] == seq[1:]).all(-1)
+    truncated = cont & ~same_next                                     # mask 1 but the env moved on: the stored next obs is the terminal one
+    terminated = ~cont
+    assert bool(truncated.any()) and bool(terminated.any())
+    assert bool(same_next[terminated].all())                          # true termination: the reset observation is stored with mask 0 (as in the reference)
+    # a truncated transition happens at the episode's last control step: exactly every 25th step of an env that was not terminated before
+    t_idx = torch.nonzero(truncated)[:, 0]
+    assert bool(((t_idx + 1) % 25 == 0).any())
+    lo, hi = ctl._act_low, ctl._act_high
+    if algo == 'sac':
+        assert bool((d['act'] >= lo - 1e-6).all() and (d['act'] <= hi + 1e-6).all())
+    ctl.save(str(tmp_path / 'model_latest.pt'))
+    state = torch.load(str(tmp_path / 'model_latest.pt'), weights_only=False)
+    assert {'agent', 'obs_normalizer', 'reward_normalizer', 'total_steps', 'obs', 'random_state', 'env_random_state', 'buffer'} <= set(state)
+    ev = ctl.run(n_episodes=12)
+    assert ev['ep_returns'].shape == (12,) and np.all(np.isfinite(ev['ep_returns'])) and np.all(ev['ep_lengths'] >= 1) and np.all(ev['ep_lengths'] <= 25)
+    ctl2 = make(algo, env_func, training=True, checkpoint_path=str(tmp_path / 'model_latest.pt'), output_dir=str(tmp_path), seed=2, rollout_batch_size=B,
+                warm_up_steps=B * 20, train_interval=B * 10, train_batch_size=128, hidden_dim=64, max_buffer_size=B * 50)
+    ctl2.reset(); ctl2.load(str(tmp_path / 'model_latest.pt'))
+    assert len(ctl2.buffer) == len(ctl.buffer) and torch.equal(ctl2.buffer.data['next_obs'], ctl.buffer.data['next_obs']) and torch.equal(ctl2.obs, ctl.obs)
+    ctl.close(); ctl2.close()
