@@ -373,6 +373,32 @@ template <typename R> __device__ __forceinline__ void sincos_small(R x, R* s, R*
 // physics
 // ---------------------------------------------------------------------------------------------
 // quadrotor.py:722-747 + quadrotor_utils.py:16-60: clipped thrust command(s) -> per-motor thrust kf*rpm^2
+// Cold paths of the collector's owner warp are kept OUT OF LINE (SCG_COLD_OUTLINE): that warp is bound by the fetch of its straight-line code
+// (24 % of its stall samples), and ptxas lays a rarely taken block out in source order, in the middle of the hot path.  Values travel by value
+// (small structs), never by reference: an address-taken register array would move to local memory for its whole lifetime.
+#ifndef SCG_COLD_OUTLINE
+#define SCG_COLD_OUTLINE 1
+#endif
+#if SCG_COLD_OUTLINE
+#define SCG_COLD __noinline__
+#else
+#define SCG_COLD __forceinline__
+#endif
+template <typename R, int NU> struct MotorF { R v[NU]; };
+// full cmd2pwm -> clip -> pwm2rpm -> kf rpm^2 chain (quadrotor_utils.py:16-60): only needed when a command sits on the PWM limits
+template <typename R, int NU> static __device__ SCG_COLD MotorF<R, NU> quad_motor_forces_clipped(const HotCfg<R>* h, MotorF<R, NU> thr) {
+    MotorF<R, NU> o;
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+        R t = thr.v[k] < (R)0 ? (R)0 : thr.v[k];
+        R pwm = (Mth<R>::sqrt_(t * h->inv_nm_kf) - h->pwm_c) * h->inv_pwm_s;
+        pwm = pwm < h->pwm_min ? h->pwm_min : pwm;
+        pwm = pwm > h->pwm_max ? h->pwm_max : pwm;
+        R rpm = h->pwm_s * pwm + h->pwm_c;
+        o.v[k] = rpm * rpm * h->kf;
+    }
+    return o;
+}
 template <int SYS, typename R>
 __device__ __forceinline__ void quad_motor_forces(const HotCfg<R>* h, const R* thrust, R f[4]) {
     constexpr int NU = SysDims<SYS>::NU;
@@ -387,15 +413,12 @@ __device__ __forceinline__ void quad_motor_forces(const HotCfg<R>* h, const R* t
 #pragma unroll
         for (int k = 0; k < NU; ++k) mf[k] = thrust[k] * h->inv_nm;
     } else {
+        MotorF<R, NU> t;
 #pragma unroll
-        for (int k = 0; k < NU; ++k) {
-            R t = thrust[k] < (R)0 ? (R)0 : thrust[k];
-            R pwm = (Mth<R>::sqrt_(t * h->inv_nm_kf) - h->pwm_c) * h->inv_pwm_s;
-            pwm = pwm < h->pwm_min ? h->pwm_min : pwm;
-            pwm = pwm > h->pwm_max ? h->pwm_max : pwm;
-            R rpm = h->pwm_s * pwm + h->pwm_c;
-            mf[k] = rpm * rpm * h->kf;
-        }
+        for (int k = 0; k < NU; ++k) t.v[k] = thrust[k];
+        t = quad_motor_forces_clipped<R, NU>(h, t);
+#pragma unroll
+        for (int k = 0; k < NU; ++k) mf[k] = t.v[k];
     }
     if (NU == 1) { f[0] = f[1] = f[2] = f[3] = mf[0]; }
     else if (NU == 2) { f[0] = mf[0]; f[1] = mf[1 % NU]; f[2] = mf[1 % NU]; f[3] = mf[0]; }   // quadrotor_utils.py:39
@@ -538,6 +561,13 @@ template <typename R> __device__ __noinline__ R pitch_of_theta(R th) {
     return (sarg <= (R)-0.99999) ? (R)(-0.5 * SCG_PI) : (sarg >= (R)0.99999) ? (R)(0.5 * SCG_PI) : Mth<R>::asin_(sarg);
 }
 
+template <typename R> struct SinCos2 { R sd, cd, se, ce; };
+template <typename R> static __device__ SCG_COLD SinCos2<R> sincos_pair_exact(R d0, R eps) {     // large per-sub-step angle increments: exact evaluation
+    SinCos2<R> o;
+    Mth<R>::sincos_(d0, &o.sd, &o.cd);
+    Mth<R>::sincos_(eps, &o.se, &o.ce);
+    return o;
+}
 template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
     // ps = x, vx, z, vz, theta, omega_y ; inertial = M, Ixx, Iyy, Izz
     // Within a control step thrust and torque are constant, so omega grows linearly and the per-sub-step angle increment
@@ -590,8 +620,8 @@ template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
             sincos_small<R>(d0, &sd, &cd);
             sincos_small<R>(eps, &se, &ce);
         } else {
-            Mth<R>::sincos_(d0, &sd, &cd);
-            Mth<R>::sincos_(eps, &se, &ce);
+            const SinCos2<R> sc = sincos_pair_exact<R>(d0, eps);
+            sd = sc.sd; cd = sc.cd; se = sc.se; ce = sc.ce;
         }
         SCG_TK(4);
         const R tmdt = tm * dt, fxdt = fx * dt, fzdt = fz * dt;
@@ -750,11 +780,12 @@ template <typename GT> __device__ __forceinline__ const GT* goal_row(const GT* x
 
 // _get_observation + extend_obs (quadrotor.py:777-817, cartpole.py:585-609, benchmark_env.py:422-445).
 // The observation is handed element by element to `sink(k, value)` (global buffers or the CTA's shared tile).
-template <int SYS, typename R, typename GT, typename Sink>
+// NOISE = false: the caller knows that no observation disturbance is configured (the collector's FAST schedule), the branch is compiled out.
+template <int SYS, typename R, typename GT, bool NOISE = true, typename Sink>
 __device__ __forceinline__ void make_obs(const DevTables& T, const HotCfg<R>* h, const GT* xg, const R* state, int n, int ctrl_step, bool at_reset,
                                          NoiseSrc<R>& ns, Sink sink) {
     constexpr int NX = SysDims<SYS>::NX;
-    if (h->has_dist[SCG_MODE_OBSERVATION]) {
+    if (NOISE && h->has_dist[SCG_MODE_OBSERVATION]) {
         R o[NX];
 #pragma unroll
         for (int k = 0; k < NX; ++k) o[k] = state[k];
@@ -1015,6 +1046,15 @@ __device__ __forceinline__ void env_reward_mse(const HotCfg<R>* h, const GT* xg,
     rew_out = rew; mse_out = mse;
 }
 
+// np.linalg.norm(state - goal) < tol (quadrotor.py:868, cartpole.py:659) without a square root on the common path: the squares decide unless
+// they are within rounding of each other, and only then the root is taken (out of line)
+template <typename R> static __device__ SCG_COLD bool goal_norm_below_exact(R n2, R tol) { return Mth<R>::sqrt_(n2) < tol; }
+template <typename R> __device__ __forceinline__ bool goal_norm_below(R n2, R tol) {
+    const R t2 = tol * tol, eps = (R)(sizeof(R) == 8 ? 1e-12 : 1e-5);
+    if (tol <= (R)0 || n2 > t2 * ((R)1 + eps)) return false;
+    if (n2 < t2 * ((R)1 - eps)) return true;
+    return goal_norm_below_exact<R>(n2, tol);
+}
 // done before the constraint / time-limit logic (quadrotor.py:864-894, cartpole.py:654-672)
 template <int SYS, typename R, typename GT>
 __device__ __forceinline__ int env_done(const HotCfg<R>* h, const GT* xg, const R* state, int& goal_reached, int& oob) {
@@ -1024,7 +1064,7 @@ __device__ __forceinline__ int env_done(const HotCfg<R>* h, const GT* xg, const 
         R n2 = (R)0;
 #pragma unroll
         for (int k = 0; k < NX; ++k) { const R er = state[k] - (R)xg[k]; n2 += er * er; }
-        goal_reached = Mth<R>::sqrt_(n2) < h->goal_tol;
+        goal_reached = goal_norm_below<R>(n2, h->goal_tol);
         done = goal_reached;
     }
     if (!done && h->done_on_oob) {

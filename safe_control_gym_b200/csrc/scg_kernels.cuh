@@ -70,6 +70,16 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// CTA-scope release / acquire on a shared-memory flag (reset candidates: helper warp -> owner lanes).  __threadfence_block() is fence.sc.cta
+// (MEMBAR.SC.CTA: it waits for the warp's outstanding GLOBAL record stores as well) -- on the owner lanes' critical path in every step in which
+// an episode ends.  The acquire load compiles to a plain LDS (a warp's shared-memory accesses are already ordered), the release to
+// MEMBAR.ALL.CTA + STS on the helper, off the critical path.
+__device__ __forceinline__ int lds_acquire(const int* p) {
+    int v; asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory"); return v;
+}
+__device__ __forceinline__ void sts_release(int* p, int v) {
+    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -482,6 +492,17 @@ __device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const
     const int net = threadIdx.x / NTN, tl = threadIdx.x % NTN;
     net_forward<HID, E, NTN, A>(tl, net, net ? 1 : A, net ? A : 0, s_blob, L, s_in, s_h1 + net * NETSZ, s_outp, obs_dim, act);
 }
+// The forward of the horizon loop, inlined: the call costs ~600 cycles per step (far jump, callee-saved registers through the stack, return) on
+// the path every warp waits for.  Measured (gpurun_out/r2_ab19.log): -1.2 % on C3, -3.8 % on C2; the register-starved Quadrotor-3D collector is
+// 0.7 % FASTER with the call (the inlined body competes with the integrator state for registers), so it keeps it.
+template <int HID, int E, int NT, int A>
+__device__ __forceinline__ void mlp_forward_inl(const float* __restrict__ s_blob, const BlobLayout L, const float* __restrict__ s_in, float* __restrict__ s_h1,
+                                                float* __restrict__ s_outp, int obs_dim, int act) {
+    constexpr int NTN = NT / 2;
+    constexpr int NETSZ = (HID / 2) * (2 * (E / 4) * 4);
+    const int net = threadIdx.x / NTN, tl = threadIdx.x % NTN;
+    net_forward<HID, E, NTN, A>(tl, net, net ? 1 : A, net ? A : 0, s_blob, L, s_in, s_h1 + net * NETSZ, s_outp, obs_dim, act);
+}
 // the same for a network pair whose action width is only known at run time (the adversary: a_dim <= AMAX)
 template <int HID, int E, int NT, int AMAX>
 __device__ __noinline__ void mlp_forward_n(const float* __restrict__ s_blob, const BlobLayout L, const float* __restrict__ s_in, float* __restrict__ s_h1,
@@ -587,12 +608,15 @@ template <int E> static __device__ __noinline__ void norm_obs_pass(float* tile, 
 // local ones): the all-gather of the rollout record happens inside the collector, there is no separate collective to wait for.
 // With an NVSwitch multicast mapping of the gathered buffer (P.mc_off), ONE `multimem.st` lands in every rank's copy instead of
 // n_peers unicast stores: the replication happens in the switch, not in this SM's LSU.
-__device__ __forceinline__ void multimem_st(float* p, float v) { asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+// (no "memory" clobber on purpose: a clobber inside one arm of pstore's branch is a compiler barrier for EVERY record store -- it undid the
+//  "all loads, then all stores" batching of the record writers and of the GAE scan and cost the single-GPU collector 360 cycles per step on the
+//  owner lanes, measured with the SCG_PROF ticks.  The multicast store has no consumer inside the kernel, so its order is free.)
+__device__ __forceinline__ void multimem_st(float* p, float v) { asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v)); }
 __device__ __forceinline__ void multimem_st(float2* p, float2 v) {
-    asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+    asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y));
 }
 __device__ __forceinline__ void multimem_st(float4* p, float4 v) {
-    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
 }
 template <typename V> __device__ __forceinline__ void pstore(const RolloutParams& P, V* ptr, V v) {
     *ptr = v;
@@ -616,6 +640,17 @@ static __device__ __noinline__ const double* stage_table_row(double* dst, const 
 __host__ __device__ constexpr int rollout_min_blocks(int HID, int E, int NT) {
     return (NT / E >= 16 && HID <= 64) ? (NT == 256 ? 2 : 3) : 1;
 }
+// FAST schedule, episode end before the helper warp has the next episode's start ready (only the first steps of a launch): draw it on the
+// owner lane.  Out of line and by value -- this block is ~10 KB of code that would otherwise sit in the middle of the owner warp's hot path.
+template <int SYS, typename R, int E> static __device__ SCG_COLD EnvRegs<SYS, R> reset_on_owner_lane(const DevTables& T, const HotCfg<R>* h, const R* s_xg, int n,
+                                                                                                 EnvRegs<SYS, R> e, float* s_on, int ol) {
+    R state[SysDims<SYS>::NX];
+    env_reset<SYS, R>(T, h, n, e, state);
+    NoiseSrc<R> nn; nn.row = nullptr; nn.philox = false; nn.slot = 0; nn.stream = 0; nn.idx = 0; nn.key.k0 = nn.key.k1 = nn.key.genv = 0;
+    make_obs<SYS, R, R, false>(T, h, s_xg, state, n, 0, true, nn, TileObsSink<E>{s_on, ol});
+    return e;
+}
+
 // SAFE: the SafeExplorer variant (safety layer between actor and env); a separate instantiation so that the default collector carries none of its code
 // XT:   the extended variant -- RARL / RAP adversary (second actor-critic on the same observation, its action through set_adversary_control
 //       into the env step; rarl.py:349-418), the env's adversary input and the non-default quadrotor physics (pyb_gnd / pyb_drag / pyb_dw);
@@ -725,7 +760,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     // (with an adversary the owner lanes keep the whole step: which player's values go into the record is decided there)
     const bool fast = FM == SCG_FM_FAST ? true : FM == SCG_FM_SERIAL ? false : (use_cand && !obs_noise && !h->done_on_violation && !h->use_penalty && !have_adv);
 #ifndef SCG_RELAY_ALWAYS
-#define SCG_RELAY_ALWAYS 0
+#define SCG_RELAY_ALWAYS 1      // measured (gpurun_out/r2_cold_ab.log): -0.8 % on C3, -3.2 % on the Quadrotor-3D collector, -0.9 % on C2
 #endif
     const bool relay = fast && (P.n_peers > 0 || P.mc_off != 0 || SCG_RELAY_ALWAYS);   // the owner lanes leave act / v / logp to a helper warp when every store has peer copies
     const int OBS_TILE = od * E;
@@ -810,8 +845,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                 for (int j = 0; j < PS; ++j) cd[(SCG_MAX_INERTIAL + SCG_NINV + j) * E] = (double)tmp.ps[j];
                 NoiseSrc<R> nn; nn.row = nullptr; nn.philox = false; nn.slot = 0; nn.stream = 0; nn.idx = 0; nn.key.k0 = nn.key.k1 = nn.key.genv = 0;
                 make_obs<SYS, R, R>(T, h, s_xg, st0, n0 + ee, 0, true, nn, PlainObsSink{s_cobs + slot * OBS_TILE + ee, E});
-                __threadfence_block();
-                *(volatile int*)&s_cand_ep[slot * E + ee] = ep;
+                sts_release(&s_cand_ep[slot * E + ee], ep);
             }
         }
     };
@@ -875,7 +909,8 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
         }
         PROF_T(k1);
         SCG_TK(13);
-        mlp_forward<HID, E, NT, A>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
+        if constexpr (SYS != SCG_SYS_QUAD3D && FM != SCG_FM_RUNTIME) mlp_forward_inl<HID, E, NT, A>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
+        else mlp_forward<HID, E, NT, A>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
         if constexpr (SAFE) { safety_models<E, A>(P.safety, P.safety_C, P.safety_H, od, s_oc, s_g, tid, NT); __syncthreads(); }
         if constexpr (XT) { if (have_adv) mlp_forward_n<HID, E, NT, A2M>(s_blob2, L2, s_oc, s_h1, s_out2, od, P.activation, A2); }
         PROF_T(k2);
@@ -968,13 +1003,12 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                     done = fl & 1; truncated = fl >> 1;
                     e.total_steps += 1;
                     // observation of the transition: the next policy input unless the episode ended; the terminal observation if truncated
-                    if (fl != 1) make_obs<SYS, R, R>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{truncated ? s_tobs : s_on, ol});
+                    if (fl != 1) make_obs<SYS, R, R, false>(T, h, s_xg, state, n, step_before, false, ns, TileObsSink<E>{truncated ? s_tobs : s_on, ol});   // FAST: no observation noise
                     SCG_TK(8);
                     if (done) {                                            // dummy_vec_env.py:33-38
                         const int slot = e.episode & 1;
-                        if (*(volatile int*)&s_cand_ep[slot * E + ol] == e.episode) {
+                        if (lds_acquire(&s_cand_ep[slot * E + ol]) == e.episode) {     // acquire: no candidate load may move above the flag check
                             // the helper has the whole episode start ready: inertial properties, reciprocals, integrator state, observation
-                            __threadfence_block();                         // acquire: no candidate load may move above the flag check
                             const double* cd = s_cand + slot * NC * E + ol;
 #pragma unroll
                             for (int j = 0; j < SCG_MAX_INERTIAL; ++j) e.inertial[j] = (R)cd[j * E];
@@ -991,9 +1025,8 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                                 for (int j = 0; j < 4; ++j) if (k + j < od) s_on[tile_idx<E>(k + j, ol)] = cv[j];
                             }
                             e.ctrl_step = 0; e.episode += 1;
-                        } else {                                           // not drawn yet (first steps of a launch): draw inline
-                            env_reset<SYS, R>(T, h, n, e, state);
-                            make_obs<SYS, R, R>(T, h, s_xg, state, n, 0, true, ns, TileObsSink<E>{s_on, ol});
+                        } else {                                           // not drawn yet (first steps of a launch): draw on this lane
+                            e = reset_on_owner_lane<SYS, R, E>(T, h, s_xg, n, e, s_on, ol);
                         }
                         *(volatile int*)&s_epi[ol] = e.episode;
                     } else e.ctrl_step += 1;
@@ -1061,6 +1094,10 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
         }
         SCG_TK(23);
         PROF_T(k6);
+#ifdef SCG_PROF
+        // time every warp spends in its env-phase job (lane 0 of each warp of CTA 0): who does the end-of-step barrier wait for?
+        if (P.prof != nullptr && blockIdx.x == 0 && lane == 0) atomicAdd((unsigned long long*)&P.prof[8 + warp], (unsigned long long)(k6 - k2));
+#endif
         // (c) critic on the terminal observation of time-limit truncated envs (rare, CTA-uniform branch)
         const int any_trunc = __syncthreads_or(trunc);
 #ifdef SCG_PROF

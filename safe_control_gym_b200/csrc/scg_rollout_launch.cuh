@@ -59,6 +59,9 @@ static RolloutLaunchResult launch_rollout(const RolloutLaunch& e, RolloutParams 
         fprintf(stderr, "[SCG_PROF] CTA0 cycles per step (T=%d):", a->T);
         for (int i = 0; i < 8; ++i) if (nm[i][0] != '-') fprintf(stderr, " %s=%.0f", nm[i], i == 7 ? (double)hp[i] : (double)hp[i] / a->T);
         fprintf(stderr, "\n");
+        fprintf(stderr, "[SCG_PROF] env-phase cycles per step by warp (7 = owner, 6 = role 1 constraints + policy record, 5 = role 2 reward / mse, 4 = role 3 reset candidates, 0-3 = obs record + normals):");
+        for (int i = 0; i < 8; ++i) fprintf(stderr, " w%d=%.0f", i, (double)hp[8 + i] / a->T);
+        fprintf(stderr, "\n");
         long long tk[64]; cudaMemcpyFromSymbol(tk, scg_ticks, sizeof(tk));
         fprintf(stderr, "[SCG_PROF] ticks/step:");
         for (int i = 0; i < 25; ++i) fprintf(stderr, " %d:%.0f", i, (double)tk[i] / a->T);

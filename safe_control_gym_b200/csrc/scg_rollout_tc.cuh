@@ -913,8 +913,7 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
                 for (int j = 0; j < PS; ++j) cd[(SCG_MAX_INERTIAL + SCG_NINV + j) * E] = (double)tmp.ps[j];
                 NoiseSrc<R> nn; nn.row = nullptr; nn.philox = false; nn.slot = 0; nn.stream = 0; nn.idx = 0; nn.key.k0 = nn.key.k1 = nn.key.genv = 0;
                 make_obs<SYS, R, XG>(T, h, s_xg, st0, n0 + ee, 0, true, nn, PlainObsSink{s_cobs + slot * OBS_TILE + ee, E});
-                __threadfence_block();
-                *(volatile int*)&s_cand_ep[slot * E + ee] = ep;
+                sts_release(&s_cand_ep[slot * E + ee], ep);
             }
         }
     };
@@ -1004,8 +1003,7 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
                                    else make_obs<SYS, R, XG>(T, h, s_xg, state, n, step_before, false, ns, sink_next); }
                     if (done) {
                         const int slot = e.episode & 1;
-                        if (*(volatile int*)&s_cand_ep[slot * E + ol] == e.episode) {
-                            __threadfence_block();
+                        if (lds_acquire(&s_cand_ep[slot * E + ol]) == e.episode) {
                             const double* cd = s_cand + slot * NC * E + ol;
 #pragma unroll
                             for (int j = 0; j < SCG_MAX_INERTIAL; ++j) e.inertial[j] = (R)cd[j * E];
