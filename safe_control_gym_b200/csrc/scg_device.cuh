@@ -137,9 +137,12 @@ __device__ __forceinline__ int rng_randint(const RngKey& k, uint32_t stream, uin
 // ---------------------------------------------------------------------------------------------
 template <int SYS> struct SysDims;
 // NADV: widest adversary action (= dim of the disturbance mode it drives: action -> NU, dynamics -> 2 / 1 / 2 / 3; benchmark_env.py:289-295)
-template <> struct SysDims<SCG_SYS_CARTPOLE> { static constexpr int NX = 4, NU = 1, PS = 4, NADV = 2; };
+#ifndef SCG_CP_CARRY
+#define SCG_CP_CARRY 0      // measured (gpurun_out/r2_ab25.log): carrying sin / cos theta in the cart-pole state is 3.8 % SLOWER on C2 than one exact sincos per control step
+#endif
+template <> struct SysDims<SCG_SYS_CARTPOLE> { static constexpr int NX = 4, NU = 1, PS = SCG_CP_CARRY ? 6 : 4, NADV = 2; };   // x, xdot, theta, thetadot, sin theta, cos theta
 template <> struct SysDims<SCG_SYS_QUAD1D> { static constexpr int NX = 2, NU = 1, PS = 4, NADV = 1; };   // x, vx, z, vz (x only carries the init quirk)
-template <> struct SysDims<SCG_SYS_QUAD2D> { static constexpr int NX = 6, NU = 2, PS = 6, NADV = 2; };   // x, vx, z, vz, theta, omega_y
+template <> struct SysDims<SCG_SYS_QUAD2D> { static constexpr int NX = 6, NU = 2, PS = 8, NADV = 2; };   // x, vx, z, vz, theta, omega_y, sin theta, cos theta
 template <> struct SysDims<SCG_SYS_QUAD3D> { static constexpr int NX = 12, NU = 4, PS = 13, NADV = 4; }; // pos3, quat4, vel3, omega_world3
 
 #define SCG_PS_MAX 13
@@ -452,14 +455,28 @@ template <typename R> __device__ __forceinline__ void rot_from_unit_quat(const R
 // semi-implicit Euler per sub-step -- velocities with the accelerations at the current pose, then poses with the NEW velocities.
 template <int SYS, typename R> struct Physics;
 
+template <typename R> struct SinCos2 { R sd, cd, se, ce; };
+template <typename R> static __device__ SCG_COLD SinCos2<R> sincos_pair_exact(R d0, R eps) {     // large per-sub-step angle increments: exact evaluation
+    SinCos2<R> o;
+    Mth<R>::sincos_(d0, &o.sd, &o.cd);
+    Mth<R>::sincos_(eps, &o.se, &o.ce);
+    return o;
+}
+
 template <typename R> struct Physics<SCG_SYS_CARTPOLE, R> {
-    // ps = x, xdot, theta, thetadot ; inertial = pole_length, cart_mass, pole_mass
+    // ps = x, xdot, theta, thetadot, sin theta, cos theta ; inertial = pole_length, cart_mass, pole_mass
+    // (sin theta, cos theta) are carried in the state and rotated by every sub-step's angle increment (see Physics<QUAD2D>): no sincos(theta)
+    // per control step on the owner lanes' critical path
     static __device__ __forceinline__ void advance(const HotCfg<R>* h, EnvRegs<SCG_SYS_CARTPOLE, R>& e, const R* force, const R* tap, bool has_tap) {
         const R l = e.inertial[0], M = e.inertial[1], m = e.inertial[2], g = h->gravity, dt = h->dt;
         const R Ic = m * (R)(1.0 / 12.0) * (((R)2 * l) * ((R)2 * l) + h->pole_w2);   // box inertia PyBullet recomputes (cartpole.py:301-304,318-322)
         const R a11 = M + m, a22 = Ic + m * l * l, ml = m * l, mgl = m * g * l;
         R x = e.ps[0], xd = e.ps[1], th = e.ps[2], thd = e.ps[3];
+#if SCG_CP_CARRY
+        R st = e.ps[4], ct = e.ps[5];
+#else
         R st, ct; Mth<R>::sincos_(th, &st, &ct);
+#endif
         const int steps = h->steps;
         for (int s = 0; s < steps; ++s) {
             R Qx = force[0], Qth = (R)0;
@@ -471,20 +488,28 @@ template <typename R> struct Physics<SCG_SYS_CARTPOLE, R> {
             xd += xdd * dt; thd += thdd * dt;
             x += xd * dt;
             const R dth = thd * dt; th += dth;
-            if (s + 1 < steps) {   // sin/cos of the new angle: rotate by the (small) increment, exact re-evaluation otherwise
-                if (Mth<R>::abs_(dth) <= (R)SCG_SMALL_ANGLE) {
-                    R sd, cd; sincos_small<R>(dth, &sd, &cd);
-                    const R s2 = st * cd + ct * sd; ct = ct * cd - st * sd; st = s2;
-                } else Mth<R>::sincos_(th, &st, &ct);
-            }
+            // sin/cos of the new angle: rotate by the (small) increment, exact re-evaluation otherwise
+            if (!SCG_CP_CARRY && s + 1 >= steps) break;
+            if (Mth<R>::abs_(dth) <= (R)SCG_SMALL_ANGLE) {
+                R sd, cd; sincos_small<R>(dth, &sd, &cd);
+                const R s2 = st * cd + ct * sd; ct = ct * cd - st * sd; st = s2;
+            } else { const SinCos2<R> sc = sincos_pair_exact<R>(th, (R)0); st = sc.sd; ct = sc.cd; }
         }
         e.ps[0] = x; e.ps[1] = xd; e.ps[2] = th; e.ps[3] = thd;
+#if SCG_CP_CARRY
+        const R nrm = (R)1.5 - (R)0.5 * (st * st + ct * ct);           // back onto the unit circle
+        e.ps[4] = st * nrm; e.ps[5] = ct * nrm;
+#endif
     }
     static __device__ __forceinline__ void state(const EnvRegs<SCG_SYS_CARTPOLE, R>& e, R* s) {
         s[0] = e.ps[0]; s[1] = e.ps[1]; s[2] = e.ps[2]; s[3] = e.ps[3];
     }
     static __device__ __forceinline__ void set_init(EnvRegs<SCG_SYS_CARTPOLE, R>& e, const R* init) {
         e.ps[0] = init[0]; e.ps[1] = init[1]; e.ps[2] = init[2]; e.ps[3] = init[3];
+#if SCG_CP_CARRY
+        R s0, c0; Mth<R>::sincos_(init[2], &s0, &c0);
+        e.ps[4] = s0; e.ps[5] = c0;
+#endif
     }
 };
 
@@ -561,21 +586,20 @@ template <typename R> __device__ __noinline__ R pitch_of_theta(R th) {
     return (sarg <= (R)-0.99999) ? (R)(-0.5 * SCG_PI) : (sarg >= (R)0.99999) ? (R)(0.5 * SCG_PI) : Mth<R>::asin_(sarg);
 }
 
-template <typename R> struct SinCos2 { R sd, cd, se, ce; };
-template <typename R> static __device__ SCG_COLD SinCos2<R> sincos_pair_exact(R d0, R eps) {     // large per-sub-step angle increments: exact evaluation
-    SinCos2<R> o;
-    Mth<R>::sincos_(d0, &o.sd, &o.cd);
-    Mth<R>::sincos_(eps, &o.se, &o.ce);
-    return o;
-}
 template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
-    // ps = x, vx, z, vz, theta, omega_y ; inertial = M, Ixx, Iyy, Izz
+    // ps = x, vx, z, vz, theta, omega_y, sin theta, cos theta ; inertial = M, Ixx, Iyy, Izz
     // Within a control step thrust and torque are constant, so omega grows linearly and the per-sub-step angle increment
     // delta_k = omega_k dt grows by the constant eps = alpha dt^2: sin/cos(theta_k) follow from two plane rotations per
-    // sub-step (3 sincos per control step instead of one per sub-step).
+    // sub-step.  (sin theta, cos theta) are part of the integrator state: they are rotated along with theta and carried from one control
+    // step to the next (one Newton step per control step keeps them on the unit circle), so no sine / cosine is evaluated inside an
+    // episode at all -- the exact sincos(theta) per control step was ~250 cycles of the owner lanes' critical path.  The phase error of the
+    // rotation recurrence grows by < 1.2e-16 per sub-step: < 6e-13 over a 250-step episode, three orders below the parity tolerance (1e-9).
     // non-default physics: thrust and torque change with the pose every sub-step, so the angle is re-evaluated instead of rotated
-    static __device__ __noinline__ void advance_ext(const HotCfg<R>* h, EnvRegs<SCG_SYS_QUAD2D, R>& e, const R f[4], const R* fd, bool has_dist, const PhysExt<R> px) {
+    // (out of line and BY VALUE: a reference to the register-resident env would pin it in local memory for the whole kernel)
+    static __device__ __noinline__ EnvRegs<SCG_SYS_QUAD2D, R> advance_ext(const HotCfg<R>* h, EnvRegs<SCG_SYS_QUAD2D, R> e, const R f0, const R f1, const R fdx, const R fdz,
+                                                                          bool has_dist, const PhysExt<R> px) {
         const R dt = h->dt, inv_m = e.inv[0], a = h->arm;
+        const R f[2] = {f0, f1}, fd[2] = {fdx, fdz};
         R x = e.ps[0], vx = e.ps[1], z = e.ps[2], vz = e.ps[3], th = e.ps[4], om = e.ps[5];
         for (int s = 0; s < h->steps; ++s) {
             R st, ct; Mth<R>::sincos_(th, &st, &ct);
@@ -594,12 +618,15 @@ template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
             x += vx * dt; z += vz * dt; th += om * dt;
         }
         e.ps[0] = x; e.ps[1] = vx; e.ps[2] = z; e.ps[3] = vz; e.ps[4] = th; e.ps[5] = om;
+        R sf, cf; Mth<R>::sincos_(th, &sf, &cf);
+        e.ps[6] = sf; e.ps[7] = cf;
+        return e;
     }
     template <bool EXT = false>
     static __device__ __forceinline__ void advance(const HotCfg<R>* h, EnvRegs<SCG_SYS_QUAD2D, R>& e, const R f[4], const R* fd, bool has_dist) {
         if constexpr (EXT) {
             const PhysExt<R> px(h, f);
-            if (px.any()) { advance_ext(h, e, f, fd, has_dist, px); return; }
+            if (px.any()) { e = advance_ext(h, e, f[0], f[1], has_dist ? fd[0] : (R)0, has_dist ? fd[1] : (R)0, has_dist, px); return; }
         }
         const R dt = h->dt;
         const R inv_m = e.inv[0];                                      // 1/M, 1/Iyy: per-episode constants (env_load / env_reset)
@@ -611,7 +638,7 @@ template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
         if (has_dist) { fx += fd[0] * inv_m; fz += fd[1] * inv_m; }
         R x = e.ps[0], vx = e.ps[1], z = e.ps[2], vz = e.ps[3], th = e.ps[4], om = e.ps[5];
         SCG_TK(3);
-        R st, ct; Mth<R>::sincos_(th, &st, &ct);
+        R st = e.ps[6], ct = e.ps[7];
         const R adt = alpha * dt, eps = adt * dt;
         R sd, cd, se, ce;
         // delta_0 = omega dt (becomes delta_1 after the first eps rotation) and eps = alpha dt^2 are small: series, no range reduction
@@ -626,6 +653,29 @@ template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
         SCG_TK(4);
         const R tmdt = tm * dt, fxdt = fx * dt, fzdt = fz * dt;
         const int steps = h->steps;
+#ifndef SCG_Q2D_SUMS
+#define SCG_Q2D_SUMS 1
+#endif
+#if SCG_Q2D_SUMS
+        // The owner lanes' FP64 work is THROUGHPUT bound: one warp issues a double-precision operation every ~4 cycles (measured with the
+        // phase ticks: the 16-operation sub-step takes 57 cycles, a blocked variant with shorter dependent chains but 17 operations per
+        // sub-step was 20 % SLOWER).  So the sub-step only keeps what it cannot avoid -- the two plane rotations (8 operations) and four
+        // additions -- and velocities, positions, angle and rate follow in closed form from the running sums of symplectic Euler:
+        //   S1_j = sum_{k<j} s_k,  P = sum_{j<=n} S1_j:   v_n = v_0 + dt (tm S1_n + n f),   x_n = x_0 + dt (n v_0 + dt (tm P + f n (n + 1) / 2)).
+        {
+            R S1s = (R)0, S1c = (R)0, Ps = (R)0, Pc = (R)0;
+#pragma unroll 4
+            for (int s = 0; s < steps; ++s) {
+                S1s += st; S1c += ct; Ps += S1s; Pc += S1c;
+                const R sd2 = sd * ce + cd * se; cd = cd * ce - sd * se; sd = sd2;        // delta += eps
+                const R st2 = st * cd + ct * sd; ct = ct * cd - st * sd; st = st2;        // theta += delta
+            }
+            const R n = (R)steps, t2 = (R)0.5 * n * (n + (R)1);
+            x += dt * (n * vx + dt * (tm * Ps + fx * t2)); z += dt * (n * vz + dt * (tm * Pc + fz * t2));
+            vx += dt * (tm * S1s + n * fx); vz += dt * (tm * S1c + n * fz);
+            th += dt * (n * om + adt * t2); om += n * adt;
+        }
+#else
 #pragma unroll 4
         for (int s = 0; s < steps; ++s) {
             vx += st * tmdt + fxdt; vz += ct * tmdt + fzdt; om += adt;
@@ -633,8 +683,10 @@ template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
             const R sd2 = sd * ce + cd * se; cd = cd * ce - sd * se; sd = sd2;        // delta += eps
             const R st2 = st * cd + ct * sd; ct = ct * cd - st * sd; st = st2;        // theta += delta
         }
+#endif
         SCG_TK(5);
-        e.ps[0] = x; e.ps[1] = vx; e.ps[2] = z; e.ps[3] = vz; e.ps[4] = th; e.ps[5] = om;
+        const R nrm = (R)1.5 - (R)0.5 * (st * st + ct * ct);           // back onto the unit circle (|1 - norm| is O(1e-15) per control step)
+        e.ps[0] = x; e.ps[1] = vx; e.ps[2] = z; e.ps[3] = vz; e.ps[4] = th; e.ps[5] = om; e.ps[6] = st * nrm; e.ps[7] = ct * nrm;
     }
     static __device__ __forceinline__ void state(const EnvRegs<SCG_SYS_QUAD2D, R>& e, R* s) {
         s[0] = e.ps[0]; s[1] = e.ps[1]; s[2] = e.ps[2]; s[3] = e.ps[3];
@@ -645,6 +697,8 @@ template <typename R> struct Physics<SCG_SYS_QUAD2D, R> {
     static __device__ __forceinline__ void set_init(EnvRegs<SCG_SYS_QUAD2D, R>& e, const R* init) {
 #pragma unroll
         for (int j = 0; j < 6; ++j) e.ps[j] = init[j];                 // quadrotor.py:373-377
+        R s0, c0; Mth<R>::sincos_(init[4], &s0, &c0);
+        e.ps[6] = s0; e.ps[7] = c0;
     }
 };
 

@@ -345,7 +345,9 @@ template <int HID, int E> struct RolloutSmem {
 // Layer 3 is fused into the epilogue of layer 2: every thread multiplies its 4 x TU activations with the matching slice of the
 // output rows, the unit groups of a warp are summed with shuffles and the per-warp partial sums go to shared memory -- the second
 // hidden tile is never stored and the whole forward needs two barriers.
-template <int HID, int E, int NTN, int AMAX>
+// NP1: the input-pair count (obs_dim / 2) whose first layer is fully unrolled in this instantiation (0 = none): one per system -- every unrolled
+// copy lengthens the code all eight warps fetch each step, and only one of them is ever executed
+template <int HID, int E, int NTN, int AMAX, int NP1 = 0>
 __device__ __forceinline__ void net_forward(int tl, int net, int n_out, int w3_row0, const float* __restrict__ s_blob, const BlobLayout L,
                                             const float* __restrict__ s_in, float* __restrict__ s_h1n, float* __restrict__ s_outp,
                                             int obs_dim, int act) {
@@ -426,9 +428,8 @@ __device__ __forceinline__ void net_forward(int tl, int net, int n_out, int w3_r
     {
         const float* a1 = s_in + eg * 4; const float* w1 = s_blob + L.w1t + (net * HID + ul0) * 2;
         const int np1 = obs_dim >> 1;
-        if (np1 == 6) gemm_fixed(a1, 2 * EG * 4, w1, 2 * HID * 2, std::integral_constant<int, 6>{});          // Quadrotor-2D tracking (obs 12)
-        else if (np1 == 12) gemm_fixed(a1, 2 * EG * 4, w1, 2 * HID * 2, std::integral_constant<int, 12>{});   // Quadrotor-3D tracking (obs 24)
-        else if (np1 == 2) gemm_fixed(a1, 2 * EG * 4, w1, 2 * HID * 2, std::integral_constant<int, 2>{});     // CartPole (obs 4)
+        // fully unrolled for the system's usual width: Quadrotor-2D tracking (obs 12: 6 pairs), Quadrotor-3D tracking (obs 24: 12), CartPole (obs 4: 2)
+        if (NP1 > 0 && np1 == NP1) gemm_fixed(a1, 2 * EG * 4, w1, 2 * HID * 2, std::integral_constant<int, (NP1 > 0 ? NP1 : 2)>{});
         else gemm(a1, 2 * EG * 4, w1, 2 * HID * 2, np1);
     }
     SCG_TK(15);
@@ -484,24 +485,24 @@ __device__ __forceinline__ void net_forward(int tl, int net, int n_out, int w3_r
 
 // The lower half of the CTA computes the actor, the upper half the critic, in lockstep.
 //   s_outp : [NT/64 warps][A+1][E] partial sums; read the outputs with mlp_out()
-template <int HID, int E, int NT, int A>
+template <int HID, int E, int NT, int A, int NP1 = 0>
 __device__ __noinline__ void mlp_forward(const float* __restrict__ s_blob, const BlobLayout L, const float* __restrict__ s_in, float* __restrict__ s_h1,
                                          float* __restrict__ s_outp, int obs_dim, int act) {
     constexpr int NTN = NT / 2;
     constexpr int NETSZ = (HID / 2) * (2 * (E / 4) * 4);       // floats of one net's hidden tile
     const int net = threadIdx.x / NTN, tl = threadIdx.x % NTN;
-    net_forward<HID, E, NTN, A>(tl, net, net ? 1 : A, net ? A : 0, s_blob, L, s_in, s_h1 + net * NETSZ, s_outp, obs_dim, act);
+    net_forward<HID, E, NTN, A, NP1>(tl, net, net ? 1 : A, net ? A : 0, s_blob, L, s_in, s_h1 + net * NETSZ, s_outp, obs_dim, act);
 }
 // The forward of the horizon loop, inlined: the call costs ~600 cycles per step (far jump, callee-saved registers through the stack, return) on
 // the path every warp waits for.  Measured (gpurun_out/r2_ab19.log): -1.2 % on C3, -3.8 % on C2; the register-starved Quadrotor-3D collector is
 // 0.7 % FASTER with the call (the inlined body competes with the integrator state for registers), so it keeps it.
-template <int HID, int E, int NT, int A>
+template <int HID, int E, int NT, int A, int NP1 = 0>
 __device__ __forceinline__ void mlp_forward_inl(const float* __restrict__ s_blob, const BlobLayout L, const float* __restrict__ s_in, float* __restrict__ s_h1,
                                                 float* __restrict__ s_outp, int obs_dim, int act) {
     constexpr int NTN = NT / 2;
     constexpr int NETSZ = (HID / 2) * (2 * (E / 4) * 4);
     const int net = threadIdx.x / NTN, tl = threadIdx.x % NTN;
-    net_forward<HID, E, NTN, A>(tl, net, net ? 1 : A, net ? A : 0, s_blob, L, s_in, s_h1 + net * NETSZ, s_outp, obs_dim, act);
+    net_forward<HID, E, NTN, A, NP1>(tl, net, net ? 1 : A, net ? A : 0, s_blob, L, s_in, s_h1 + net * NETSZ, s_outp, obs_dim, act);
 }
 // the same for a network pair whose action width is only known at run time (the adversary: a_dim <= AMAX)
 template <int HID, int E, int NT, int AMAX>
@@ -621,7 +622,12 @@ __device__ __forceinline__ void multimem_st(float4* p, float4 v) {
 template <typename V> __device__ __forceinline__ void pstore(const RolloutParams& P, V* ptr, V v) {
     *ptr = v;
     if (P.mc_off) multimem_st(reinterpret_cast<V*>(reinterpret_cast<char*>(ptr) + P.mc_off), v);
-    else for (int g = 0; g < P.n_peers; ++g) *reinterpret_cast<V*>(reinterpret_cast<char*>(ptr) + P.peer_off[g]) = v;
+    else {
+        // not unrolled on purpose: pstore is inlined at every record store, and the unrolled peer loops were 30 KB of the horizon loop's code
+        // (instruction fetch is what the single-GPU collector is short of); the unicast path is the fallback of the multicast one anyway
+#pragma unroll 1
+        for (int g = 0; g < P.n_peers; ++g) *reinterpret_cast<V*>(reinterpret_cast<char*>(ptr) + P.peer_off[g]) = v;
+    }
 }
 
 // One row of the episode table (global) -> shared memory with a TMA bulk copy; the calling lane waits for it.  The mbarrier word is
@@ -665,6 +671,7 @@ template <int SYS, typename R, int E> static __device__ SCG_COLD EnvRegs<SYS, R>
 template <int SYS, typename R, int HID, int E, int NT, bool SAFE = false, bool XT = false, int FM = SCG_FM_RUNTIME>
 __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_kernel(DevTables T, RolloutParams P) {
     constexpr int NX = SysDims<SYS>::NX, A = SysDims<SYS>::NU, A2M = SysDims<SYS>::NADV;
+    constexpr int NP1 = SYS == SCG_SYS_CARTPOLE ? 2 : SYS == SCG_SYS_QUAD2D ? 6 : SYS == SCG_SYS_QUAD3D ? 12 : 0;   // first-layer width unrolled for this system
     constexpr int NZ = NX + 2 * A;             // z scratch rows: state, noisy action, clipped action
     // With >= 4 warps the env-step section is split: warp 0 = owners (sampling, action map, physics, done, finalize, reset),
     // warp 1 = constraints, warp 2 = reward + mse, warp 3 = next observation.  Smaller CTAs keep everything on the owner lanes.
@@ -684,6 +691,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     constexpr int NC = SCG_MAX_INERTIAL + SCG_NINV + PS;
     __shared__ double s_cand[2 * NC * E];
     __shared__ int s_cand_ep[2 * E];           // episode index held by each candidate slot (-1 = empty)
+    __shared__ int s_cand_raw[2 * E];          // episode index whose random draws sit in the slot, not yet turned into an episode start
     __shared__ int s_epi[E];                   // next episode index of each env, published by its owner lane
     __shared__ float s_rec[2 * (A + 2) * E];   // FAST: act, v, logp of the last two steps, stored to the record by a helper warp
     __shared__ float s_stat[6 * E];            // FAST: episode statistics kept by the record helpers, handed back at the end
@@ -735,7 +743,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     const bool live = owner && n < N;
     EnvRegs<SYS, R> e;
     if (live) env_load<SYS, R>(T, n, e);
-    if (owner) { s_tsteps0[ol] = live ? e.total_steps : 0u; s_epi[ol] = live ? e.episode : 0; s_cand_ep[ol] = -1; s_cand_ep[E + ol] = -1; }
+    if (owner) { s_tsteps0[ol] = live ? e.total_steps : 0u; s_epi[ol] = live ? e.episode : 0; s_cand_ep[ol] = -1; s_cand_ep[E + ol] = -1; s_cand_raw[ol] = -1; s_cand_raw[E + ol] = -1; }
     const bool use_cand = SPLIT && h->n_off_draws == 0;
     for (int i = tid; i < T.L * NX; i += NT) s_xg[i] = (R)T.x_goal[i];
     const float* obs_src = P.obs0 ? P.obs0 : T.st.cur_obs;
@@ -818,12 +826,18 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     // keep the next two episodes of env ee ready (a pure function of (env, episode)); runs while the owners sample and integrate
     // table mode: the env's row of episode `ep` of the [K][N][P] table is staged with a TMA bulk copy (cp.async.bulk + mbarrier) by the
     // out-of-line stage_table_row(): one mbarrier per (candidate slot, env), its parity kept in shared memory
-    auto prepare_candidates = [&]() {
+    // Preparing an episode start costs ~1100 instructions on one warp (~5-6 k cycles: three Philox blocks, the additive draws, reciprocals,
+    // sin / cos of the initial pitch, the reset observation) -- MORE than the owner lanes' whole env step, and some env of the CTA needs one in
+    // 62 % of the steps (C3): the end-of-step barrier was waiting for this helper, not for the owners.  So the job is split in two halves
+    // that run on two warps concurrently: `draw_candidates` (helper role 3: the random draws of the episode into the slot, then a release on
+    // s_cand_raw) and `finish_candidates` (one of the otherwise idle warps: everything derived from the draws, then the release on s_cand_ep the
+    // owner lanes look at).  A candidate now takes two steps instead of one; it is not needed before the env's NEXT episode ends.
+    auto draw_candidates = [&]() {
         const int want = *(volatile int*)&s_epi[ee];
 #pragma unroll 1
         for (int d = 0; d < 2; ++d) {
             const int ep = want + d, slot = ep & 1;
-            if (*(volatile int*)&s_cand_ep[slot * E + ee] != ep) {
+            if (*(volatile int*)&s_cand_ep[slot * E + ee] != ep && *(volatile int*)&s_cand_raw[slot * E + ee] != ep) {
                 double* cd = s_cand + slot * NC * E + ee;
                 const double* staged = nullptr;
 #ifndef SCG_NO_TMA_ROWS
@@ -831,6 +845,17 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                     staged = stage_table_row(s_row + (slot * E + ee) * PROW, T.ep_table + ((size_t)(ep % T.K) * T.N + n0 + ee) * T.P, PROW * 8, &s_rowbar[2 * (slot * E + ee)]);
 #endif
                 reset_draw<SYS, R>(T, h, n0 + ee, ep, cd, E, SCG_MAX_INERTIAL + SCG_NINV, staged);   // inertial at rows 0..3, initial state after the reciprocals
+                sts_release(&s_cand_raw[slot * E + ee], ep);
+            }
+        }
+    };
+    auto finish_candidates = [&]() {
+        const int want = *(volatile int*)&s_epi[ee];
+#pragma unroll 1
+        for (int d = 0; d < 2; ++d) {
+            const int ep = want + d, slot = ep & 1;
+            if (*(volatile int*)&s_cand_ep[slot * E + ee] != ep && lds_acquire(&s_cand_raw[slot * E + ee]) == ep) {
+                double* cd = s_cand + slot * NC * E + ee;
                 EnvRegs<SYS, R> tmp; R initr[NX], st0[NX];
 #pragma unroll
                 for (int j = 0; j < SCG_MAX_INERTIAL; ++j) tmp.inertial[j] = (R)cd[j * E];
@@ -909,8 +934,8 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
         }
         PROF_T(k1);
         SCG_TK(13);
-        if constexpr (SYS != SCG_SYS_QUAD3D && FM != SCG_FM_RUNTIME) mlp_forward_inl<HID, E, NT, A>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
-        else mlp_forward<HID, E, NT, A>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
+        if constexpr (SYS != SCG_SYS_QUAD3D && FM != SCG_FM_RUNTIME) mlp_forward_inl<HID, E, NT, A, NP1>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
+        else mlp_forward<HID, E, NT, A, NP1>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
         if constexpr (SAFE) { safety_models<E, A>(P.safety, P.safety_C, P.safety_H, od, s_oc, s_g, tid, NT); __syncthreads(); }
         if constexpr (XT) { if (have_adv) mlp_forward_n<HID, E, NT, A2M>(s_blob2, L2, s_oc, s_h1, s_out2, od, P.activation, A2); }
         PROF_T(k2);
@@ -1085,12 +1110,13 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
 #endif
         } else if (SPLIT && role <= 3) {
             if (fast && hl) {
-                if (role == 3) prepare_candidates();
+                if (role == 3) { draw_candidates(); if (!DEFER) finish_candidates(); }     // (no idle warp in the small CTA shapes: both halves here)
                 else if (t > 0) process_record(t - 1);
             }
         } else if (DEFER) {                                               // idle warps: record the policy input, draw the next normals
             write_obs_record(t, s_oc, tid, NIDLE);
             if (gen_eps && t + 1 < P.T) make_eps(t + 1);
+            if (fast && warp == 1 && ee < E && n0 + ee < N) finish_candidates();   // second half of the episode-start preparation (see above)
         }
         SCG_TK(23);
         PROF_T(k6);
@@ -1110,7 +1136,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                 mlp_forward_n<HID, E, NT, A2M>(s_blob2, L2, s_tobs, s_h1, s_out2, od, P.activation, A2);
                 if (live && trunc) pstore(P, P.out.d_terminal_v + tn0 + ol, mlp_out<E, NW, A2M>(s_out2, s_blob2, L2, A2, ol));
             } else {
-                mlp_forward<HID, E, NT, A>(s_blob, L, s_tobs, s_h1, s_out, od, P.activation);
+                mlp_forward<HID, E, NT, A, NP1>(s_blob, L, s_tobs, s_h1, s_out, od, P.activation);
                 if (live && trunc) pstore(P, P.out.d_terminal_v + tn0 + ol, mlp_out<E, NW, A>(s_out, s_blob, L, A, ol));
             }
             __syncthreads();
@@ -1134,7 +1160,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     bool boot_adv = false;
     if constexpr (XT) boot_adv = have_adv && P.adv_record;                     // rarl.py:407-408
     if (boot_adv) mlp_forward_n<HID, E, NT, A2M>(s_blob2, L2, s_ol, s_h1, s_out2, od, P.activation, A2);
-    else mlp_forward<HID, E, NT, A>(s_blob, L, s_ol, s_h1, s_out, od, P.activation);
+    else mlp_forward<HID, E, NT, A, NP1>(s_blob, L, s_ol, s_h1, s_out, od, P.activation);
     if (live) {
         if (fast) {
             e.ep_ret = s_stat[ol]; e.ep_len = s_stat[E + ol]; e.ep_cv = s_stat[2 * E + ol];
@@ -1153,16 +1179,26 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
             // compute_returns_and_advantages (ppo_utils.py:374-400): float32 ret / td recursions, float64 GAE accumulator
             float ret = lval, vnext = lval; double adv = 0.0;
             constexpr int CH = 8;            // loads of CH steps are issued together: the scan itself is a serial chain
-            for (int t1 = P.T; t1 > 0; t1 -= CH) {
-                const int cnt = t1 < CH ? t1 : CH;
-                float rr[CH], tv[CH], mm[CH], vv[CH];
+            float rr[CH], tv[CH], mm[CH], vv[CH];
+            auto load_chunk = [&](int t1, float* r_, float* t_, float* m_, float* v_) {
 #pragma unroll
                 for (int j = 0; j < CH; ++j) {
-                    if (j < cnt) {
+                    if (j < t1) {
                         const size_t tn = (size_t)(t1 - 1 - j) * N + n;
-                        rr[j] = P.out.d_rew[tn]; tv[j] = P.out.d_terminal_v[tn]; mm[j] = P.out.d_mask[tn]; vv[j] = P.out.d_v[tn];
+                        r_[j] = P.out.d_rew[tn]; t_[j] = P.out.d_terminal_v[tn]; m_[j] = P.out.d_mask[tn]; v_[j] = P.out.d_v[tn];
                     }
                 }
+            };
+            load_chunk(P.T, rr, tv, mm, vv);
+            for (int t1 = P.T; t1 > 0; t1 -= CH) {
+                const int cnt = t1 < CH ? t1 : CH;
+                // the NEXT chunk's loads are issued before this chunk's serial chain (the stores below touch other steps): the L2 round
+                // trip of a chunk used to sit between two chains
+                float rn[CH], tn_[CH], mn[CH], vn[CH];
+#ifndef SCG_GAE_PREFETCH
+#define SCG_GAE_PREFETCH 1
+#endif
+                if (SCG_GAE_PREFETCH && t1 > CH) load_chunk(t1 - CH, rn, tn_, mn, vn);
 #pragma unroll
                 for (int j = 0; j < CH; ++j) {
                     if (j < cnt) {
@@ -1178,6 +1214,10 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                         vnext = v;
                     }
                 }
+                if (SCG_GAE_PREFETCH) {
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) { rr[j] = rn[j]; tv[j] = tn_[j]; mm[j] = mn[j]; vv[j] = vn[j]; }
+                } else if (t1 > CH) load_chunk(t1 - CH, rr, tv, mm, vv);
             }
         }
     }
