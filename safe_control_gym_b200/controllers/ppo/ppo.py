@@ -195,6 +195,7 @@ class PPO:
                               opt_epochs=self.opt_epochs, mini_batch_size=self.mini_batch_size, activation=self.activation,
                               fused_update=cfg.get('fused_update'))
         self.agent.to(self.device)
+        self._sync_replica(self.agent)
         # pre-/post-processing (ppo.py:70-75).  Inside the fused collector the statistics are frozen for one rollout and updated after it
         # from the raw streams the kernel records (math_and_models/normalization.py)
         self.obs_normalizer, self.reward_normalizer = BaseNormalizer(), BaseNormalizer()
@@ -209,6 +210,18 @@ class PPO:
         self._rollout_out, self._peers, self._peer = {}, {}, None     # cached record buffers / gathered buffers, keyed on the horizon
         self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         self.precision = precision
+
+    def _sync_replica(self, agent):
+        '''Lock-step replicas start from rank 0's parameters: the random initialisation comes from torch's global generator, whose default
+        seed is not the same in every process (nothing on this path seeds it -- the reference leaves that to the experiment script).'''
+        if self.world > 1:
+            import torch.distributed as dist
+            with torch.no_grad():
+                if agent.fused is not None:
+                    dist.broadcast(agent.fused.params, src=0)          # the module's parameters are views into this flat vector
+                else:
+                    for p_ in agent.ac.parameters():
+                        dist.broadcast(p_.data, src=0)
 
     # ------------------------------------------------------------------------------------------
     def reset(self):

@@ -44,6 +44,7 @@ class RARL(PPO):
                                   critic_lr=self.critic_lr, opt_epochs=self.opt_epochs, mini_batch_size=self.mini_batch_size, activation=self.activation,
                                   fused_update=cfg.get('fused_update'))
         self.adversary.to(self.device)
+        self._sync_replica(self.adversary)
         self._adv_rollout_out, self._adv_peers = {}, {}
 
     # ------------------------------------------------------------------------------------------

@@ -923,6 +923,31 @@ __device__ __noinline__ void reset_draw(const DevTables& T, const HotCfg<R>* h, 
     }
 }
 
+// ONE draw slot j of reset_draw (Philox mode only): the warp-cooperative form -- 32 lanes prepare one env's episode, lane j its slot j -- of the
+// collector's reset-candidate helper.  Same stream layout, same arithmetic, same output rows as reset_draw.
+template <int SYS, typename R>
+__device__ __forceinline__ void reset_draw_slot(const HotCfg<R>* h, int n, int k, int j, double* out, int stride, int init_row) {
+    constexpr int NX = SysDims<SYS>::NX;
+    if (j >= SCG_MAX_INERTIAL + NX) return;
+    const bool inertial = j < SCG_MAX_INERTIAL;
+    const int i = inertial ? j : j - SCG_MAX_INERTIAL;
+    const int n_inertial = (SYS == SCG_SYS_CARTPOLE) ? 3 : 4;
+    double v = inertial ? h->inertial_nominal[i] : h->init_nominal[i];
+    const bool on = inertial ? (h->randomized_inertial && i < n_inertial) : (h->randomized_init != 0);
+    if (on) {
+        const int kind = inertial ? h->inertial_kind[i] : h->init_kind[i];
+        if (kind != SCG_RAND_NONE) {
+            const int slot = h->n_off_draws + j;
+            uint32_t x[4]; philox4x32_10((uint32_t)(slot >> 1), (uint32_t)k, h->genv0 + (uint32_t)n, SCG_STREAM_EPISODE, h->key0, h->key1, x);
+            const uint32_t w0 = (slot & 1) ? x[2] : x[0], w1 = (slot & 1) ? x[3] : x[1];
+            const double a = inertial ? h->inertial_a[i] : h->init_a[i], b = inertial ? h->inertial_b[i] : h->init_b[i];
+            if (kind == SCG_RAND_UNIFORM) v += a + (b - a) * u01_d(w0);
+            else v += rand_draw(kind, a, b, w0, w1);
+        }
+    }
+    out[(inertial ? i : init_row + i) * stride] = v;
+}
+
 // reset() of one env (quadrotor.py:328-392, cartpole.py:266-352); the caller builds the observation with make_obs(at_reset).
 template <int SYS, typename R>
 __device__ __forceinline__ void env_reset(const DevTables& T, const HotCfg<R>* h, int n, EnvRegs<SYS, R>& e, R* state) {

@@ -612,12 +612,17 @@ template <int E> static __device__ __noinline__ void norm_obs_pass(float* tile, 
 // (no "memory" clobber on purpose: a clobber inside one arm of pstore's branch is a compiler barrier for EVERY record store -- it undid the
 //  "all loads, then all stores" batching of the record writers and of the GAE scan and cost the single-GPU collector 360 cycles per step on the
 //  owner lanes, measured with the SCG_PROF ticks.  The multicast store has no consumer inside the kernel, so its order is free.)
-__device__ __forceinline__ void multimem_st(float* p, float v) { asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v)); }
+#ifdef SCG_MC_CLOBBER
+#define SCG_MC_CL : "memory"
+#else
+#define SCG_MC_CL
+#endif
+__device__ __forceinline__ void multimem_st(float* p, float v) { asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) SCG_MC_CL); }
 __device__ __forceinline__ void multimem_st(float2* p, float2 v) {
-    asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y));
+    asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) SCG_MC_CL);
 }
 __device__ __forceinline__ void multimem_st(float4* p, float4 v) {
-    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) SCG_MC_CL);
 }
 template <typename V> __device__ __forceinline__ void pstore(const RolloutParams& P, V* ptr, V v) {
     *ptr = v;
@@ -832,6 +837,26 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     // that run on two warps concurrently: `draw_candidates` (helper role 3: the random draws of the episode into the slot, then a release on
     // s_cand_raw) and `finish_candidates` (one of the otherwise idle warps: everything derived from the draws, then the release on s_cand_ep the
     // owner lanes look at).  A candidate now takes two steps instead of one; it is not needed before the env's NEXT episode ends.
+    // Philox mode: the draws of ONE env's episode are made by the whole warp, lane j draw slot j (each slot is an independent counter-based
+    // draw), instead of by the env's lane looping over the slots -- ~10 x shorter per episode, and only a few envs need one in a step.
+    auto draw_candidates_coop = [&]() {              // called by ALL 32 lanes of the helper warp
+        const bool valid = ee < E && n0 + ee < N;
+        const int want = valid ? *(volatile int*)&s_epi[ee] : 0;
+#pragma unroll 1
+        for (int d = 0; d < 2; ++d) {
+            const int ep = want + d, slot = ep & 1;
+            const bool need = valid && *(volatile int*)&s_cand_ep[slot * E + ee] != ep && *(volatile int*)&s_cand_raw[slot * E + ee] != ep;
+            unsigned m = __ballot_sync(0xffffffffu, need);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int ep_s = __shfl_sync(0xffffffffu, ep, src);
+                reset_draw_slot<SYS, R>(h, n0 + src, ep_s, lane, s_cand + (ep_s & 1) * NC * E + src, E, SCG_MAX_INERTIAL + SCG_NINV);
+                __syncwarp();                                    // every lane's row is written (and ordered) before the flag
+                if (lane == src) sts_release(&s_cand_raw[(ep_s & 1) * E + src], ep_s);
+            }
+        }
+    };
     auto draw_candidates = [&]() {
         const int want = *(volatile int*)&s_epi[ee];
 #pragma unroll 1
@@ -1109,7 +1134,10 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
             if (PROF_ON) { long long k5 = clock64(); pacc[0] += k1 - k0; pacc[1] += k2 - k1; pacc[2] += k5 - k2; }
 #endif
         } else if (SPLIT && role <= 3) {
-            if (fast && hl) {
+            if (fast && role == 3 && E == 32 && h->philox) {   // (warp-uniform condition: the cooperative form needs all 32 lanes)
+                draw_candidates_coop();
+                if (!DEFER && hl) finish_candidates();
+            } else if (fast && hl) {
                 if (role == 3) { draw_candidates(); if (!DEFER) finish_candidates(); }     // (no idle warp in the small CTA shapes: both halves here)
                 else if (t > 0) process_record(t - 1);
             }

@@ -665,6 +665,7 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
     constexpr int NC = SCG_MAX_INERTIAL + SCG_NINV + PS;
     __shared__ double s_cand[2 * NC * E];
     __shared__ int s_cand_ep[2 * E];
+    __shared__ int s_cand_raw[2 * E];          // draws of that episode sit in the slot (first half of the preparation, see rollout_kernel)
     __shared__ int s_epi[E];
     __shared__ float s_rec[2 * (A + 2) * E];
     __shared__ float s_stat[6 * E];
@@ -710,7 +711,7 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
     const bool live = owner && n < N;
     EnvRegs<SYS, R> e;
     if (live) env_load<SYS, R>(T, n, e);
-    if (owner) { s_tsteps0[ol] = live ? e.total_steps : 0u; s_epi[ol] = live ? e.episode : 0; s_cand_ep[ol] = -1; s_cand_ep[E + ol] = -1; }
+    if (owner) { s_tsteps0[ol] = live ? e.total_steps : 0u; s_epi[ol] = live ? e.episode : 0; s_cand_ep[ol] = -1; s_cand_ep[E + ol] = -1; s_cand_raw[ol] = -1; s_cand_raw[E + ol] = -1; }
     const bool use_cand = h->n_off_draws == 0;
     float ep_ret_sum = 0.f, ep_len_sum = 0.f, ep_cv_sum = 0.f; int ep_count = 0;
     if constexpr (HID == 64) {
@@ -891,14 +892,43 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
             if (dn) { h_cnt += 1; h_sa += h_a; h_sb += h_b; h_a = 0.f; h_b = 0.f; }
         }
     };
-    auto prepare_candidates = [&]() {
+    // episode-start preparation in two halves on two warps (rollout_kernel: draw_candidates / finish_candidates)
+    auto draw_candidates_coop = [&]() {              // Philox mode, all 32 lanes: lane j makes draw slot j of one env's episode (rollout_kernel)
+        const bool valid = ee < E && n0 + ee < N;
+        const int want = valid ? *(volatile int*)&s_epi[ee] : 0;
+#pragma unroll 1
+        for (int d = 0; d < 2; ++d) {
+            const int ep = want + d, slot = ep & 1;
+            const bool need = valid && *(volatile int*)&s_cand_ep[slot * E + ee] != ep && *(volatile int*)&s_cand_raw[slot * E + ee] != ep;
+            unsigned m = __ballot_sync(0xffffffffu, need);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int ep_s = __shfl_sync(0xffffffffu, ep, src);
+                reset_draw_slot<SYS, R>(h, n0 + src, ep_s, lane, s_cand + (ep_s & 1) * NC * E + src, E, SCG_MAX_INERTIAL + SCG_NINV);
+                __syncwarp();
+                if (lane == src) sts_release(&s_cand_raw[(ep_s & 1) * E + src], ep_s);
+            }
+        }
+    };
+    auto draw_candidates = [&]() {
         const int want = *(volatile int*)&s_epi[ee];
 #pragma unroll 1
         for (int d = 0; d < 2; ++d) {
             const int ep = want + d, slot = ep & 1;
-            if (*(volatile int*)&s_cand_ep[slot * E + ee] != ep) {
+            if (*(volatile int*)&s_cand_ep[slot * E + ee] != ep && *(volatile int*)&s_cand_raw[slot * E + ee] != ep) {
+                reset_draw<SYS, R>(T, h, n0 + ee, ep, s_cand + slot * NC * E + ee, E, SCG_MAX_INERTIAL + SCG_NINV);
+                sts_release(&s_cand_raw[slot * E + ee], ep);
+            }
+        }
+    };
+    auto finish_candidates = [&]() {
+        const int want = *(volatile int*)&s_epi[ee];
+#pragma unroll 1
+        for (int d = 0; d < 2; ++d) {
+            const int ep = want + d, slot = ep & 1;
+            if (*(volatile int*)&s_cand_ep[slot * E + ee] != ep && lds_acquire(&s_cand_raw[slot * E + ee]) == ep) {
                 double* cd = s_cand + slot * NC * E + ee;
-                reset_draw<SYS, R>(T, h, n0 + ee, ep, cd, E, SCG_MAX_INERTIAL + SCG_NINV);
                 EnvRegs<SYS, R> tmp; R initr[NX], st0[NX];
 #pragma unroll
                 for (int j = 0; j < SCG_MAX_INERTIAL; ++j) tmp.inertial[j] = (R)cd[j * E];
@@ -1062,13 +1092,15 @@ __global__ void __launch_bounds__(tc::NT, 1) rollout_tc_kernel(DevTables T, Roll
             }
             fence_proxy_async();          // next / terminal observation tiles: generic-proxy writes -> visible to the tensor core
         } else if (role <= 3) {
-            if (fast && hl) {
-                if (role == 3) prepare_candidates();
+            if (fast && role == 3 && h->philox) draw_candidates_coop();
+            else if (fast && hl) {
+                if (role == 3) draw_candidates();
                 else if (t > 0) process_record(t - 1);
             }
         } else {
             write_obs_record(t, s_oc, tid, NIDLE);
             if (gen_eps && t + 1 < P.T) make_eps(t + 1);
+            if (fast && warp == 1 && ee < E && n0 + ee < N) finish_candidates();
         }
 #ifdef SCG_TC_PROF
         const long long own1 = clock64();
