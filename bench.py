@@ -269,12 +269,13 @@ def run_ours(args):
     from safe_control_gym_b200.engine import HostCollector
     ac_host = build_policy(env, args.hidden)
 
-    def e2e_rate(depth, n_steps):
-        hc = HostCollector(eng, dims, T_HORIZON, depth=depth, use_gae=True, want=want, envs_per_block=args.envs_per_block)
+    def e2e_rate(depth, n_steps, keys=None):
+        hc = HostCollector(eng, dims, T_HORIZON, depth=depth, use_gae=True, want=want, envs_per_block=args.envs_per_block, keys=keys)
+        probe = 'rew' if keys is None else 'ret'
         acc = 0.0
         for _ in range(depth + 1):                     # warm-up (allocates the pinned buffers)
             hc.submit(ac_host)
-            acc += float(hc.fetch()['rew'][0, 0, 0])
+            acc += float(hc.fetch()[probe][0, 0, 0])
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -282,9 +283,9 @@ def run_ours(args):
         for i in range(n_steps):
             hc.submit(ac_host)
             if i >= depth - 1:
-                acc += float(hc.fetch()['rew'][-1, -1, 0])      # the host consumes every record
+                acc += float(hc.fetch()[probe][-1, -1, 0])      # the host consumes every record
         while hc.fetched < hc.submitted:
-            acc += float(hc.fetch()['rew'][-1, -1, 0])
+            acc += float(hc.fetch()[probe][-1, -1, 0])
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
@@ -294,6 +295,8 @@ def run_ours(args):
     e2e_steps = max(8, min(args.steps, 32))
     e2e_serial, h2d_bytes, d2h_bytes, _ = e2e_rate(1, e2e_steps)
     e2e_value, _, _, _ = e2e_rate(2, e2e_steps)
+    # the same with only the keys a host-side PPOAgent.update reads (obs, act, logp, adv, ret, v): 6 of the 9 PPOBuffer keys
+    e2e_upd, _, d2h_upd, _ = e2e_rate(2, e2e_steps, keys=HostCollector.UPDATE_KEYS)
     # the timed regions above last milliseconds: keep the same kernel running for ~2 s so that nvidia-smi (100 ms period)
     # records the clocks and throttle reasons UNDER THIS LOAD
     t_end = time.perf_counter() + 2.0
@@ -334,6 +337,9 @@ def run_ours(args):
             'gpu_launches': int(launches),
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': int(d2h_bytes),
                     'serial_value': e2e_serial, 'steps': e2e_steps,
+                    'update_keys': {'value': e2e_upd, 'd2h_bytes_per_step': int(d2h_upd),
+                                    'what': 'only obs, act, logp, adv, ret, v travel to the host: what the reference PPOAgent.update reads '
+                                            '(ppo_utils.py:56-80); rew / mask / terminal_v feed compute_returns_and_advantages, done in the kernel'},
                     'what': 'engine.HostCollector: host policy parameters -> scg_policy_pack -> H2D, fused rollout, full PPOBuffer record '
                             '(obs, act, rew, mask, v, logp, terminal_v, ret, adv) -> pinned host, consumed by the host every step; 2 records in flight '
                             '(D2H of rollout k overlaps rollout k+1); serial_value = 1 record in flight'},

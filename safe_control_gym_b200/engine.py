@@ -356,10 +356,17 @@ class HostCollector:
     '''The fused collector for HOST-side consumers (the reference keeps policy parameters and the PPOBuffer in host memory,
     ppo_utils.py:241-355): `submit(params)` packs the parameters on the host, copies the blob to the GPU, launches the fused rollout and
     queues the device->host copy of the whole PPOBuffer record into pinned memory; `fetch()` returns the oldest record as numpy-backed
-    views.  `depth` records are in flight: the D2H copy of rollout k runs on a copy stream underneath rollout k+1.'''
+    views.  `depth` records are in flight: the D2H copy of rollout k runs on a copy stream underneath rollout k+1.
+    `keys`: which record keys travel to the host (default: all of them).  The host-side `PPOAgent.update` of the reference consumes
+    obs, act, logp, adv, ret, v (ppo_utils.py:56-80,82-146); rew / mask / terminal_v are only inputs of compute_returns_and_advantages,
+    which the collector kernel has already evaluated.'''
 
-    def __init__(self, eng, dims, T, depth=2, numa_bind=True, **rollout_kw):
+    UPDATE_KEYS = ('obs', 'act', 'logp', 'adv', 'ret', 'v')
+
+    def __init__(self, eng, dims, T, depth=2, numa_bind=True, keys=None, **rollout_kw):
         self.eng, self.dims, self.T, self.depth, self.kw = eng, dims, int(T), int(depth), rollout_kw
+        self.keys = None if keys is None else tuple(keys)
+        self._plan = None
         dev = eng.device
         self.numa_node = bind_to_gpu_numa_node(eng.device_index) if numa_bind else None
         nblob = _abi.lib().scg_policy_blob_floats(*dims)
@@ -392,11 +399,28 @@ class HostCollector:
         self.out[s] = self.eng.rollout(self.blob_dev[s], self.dims, self.T, out=self.out[s], **self.kw)
         self.ev_done[s].record(cur)
         flat = self.out[s]['_flat']
+        if self._plan is None:            # [(key, width, device offset, host offset)] + merged copy segments (adjacent keys travel in one DMA)
+            T_, N_ = self.out[s]['_TN']
+            plan, segs, o, ho = [], [], 0, 0
+            for k, w in self.out[s]['_layout']:
+                n = T_ * N_ * w
+                if self.keys is None or k in self.keys:
+                    plan.append((k, w, o, ho))
+                    if segs and segs[-1][0] + segs[-1][2] == o:
+                        segs[-1][2] += n
+                    else:
+                        segs.append([o, ho, n])
+                    ho += n
+                o += n
+            if self.keys is not None and len(plan) != len(self.keys):
+                raise KeyError(f'HostCollector: unknown record key in {self.keys}')
+            self._plan, self._segs, self._host_numel = plan, segs, ho
         if self.host[s] is None:
-            self.host[s] = torch.empty(flat.shape, dtype=torch.float32).pin_memory()
+            self.host[s] = torch.empty(self._host_numel, dtype=torch.float32).pin_memory()
         self.copy_stream.wait_event(self.ev_done[s])
         with torch.cuda.stream(self.copy_stream):
-            self.host[s].copy_(flat, non_blocking=True)
+            for o, ho, n in self._segs:
+                self.host[s][ho:ho + n].copy_(flat[o:o + n], non_blocking=True)
             self.ev_copied[s].record(self.copy_stream)
         self.submitted += 1
 
@@ -408,10 +432,9 @@ class HostCollector:
         self.ev_copied[s].synchronize()
         self.fetched += 1
         T, N = self.out[s]['_TN']
-        res, o, h = {}, 0, self.host[s].numpy()
-        for k, w in self.out[s]['_layout']:
-            res[k] = h[o:o + T * N * w].reshape(T, N, w)
-            o += T * N * w
+        res, h = {}, self.host[s].numpy()
+        for k, w, _, ho in self._plan:
+            res[k] = h[ho:ho + T * N * w].reshape(T, N, w)
         return res
 
 

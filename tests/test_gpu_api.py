@@ -176,7 +176,7 @@ def test_host_collector_pipelined_records_equal_direct_rollouts():
     torch.manual_seed(3)
     ac = MLPActorCritic(env.observation_space, env.action_space, hidden_dims=[64, 64], activation='tanh')
     recs = []
-    for mode in ('direct', 'host'):
+    for mode in ('direct', 'host', 'host_update_keys'):
         eng = EngineHandle(env, num_envs=N, auto_reset=True, rng_mode='philox', seed=21)
         eng.reset()
         got = []
@@ -187,7 +187,8 @@ def test_host_collector_pipelined_records_equal_direct_rollouts():
                 out = eng.rollout(blob, dims, T, use_gae=True, want=('ret', 'adv'))
                 got.append({k: out[k].cpu().numpy().copy() for k, _ in out['_layout']})
         else:
-            hc = HostCollector(eng, (12, 2, 64), T, depth=2, use_gae=True, want=('ret', 'adv'))
+            keys = HostCollector.UPDATE_KEYS if mode == 'host_update_keys' else None     # only what PPOAgent.update reads travels to the host
+            hc = HostCollector(eng, (12, 2, 64), T, depth=2, use_gae=True, want=('ret', 'adv'), keys=keys)
             for i in range(K):
                 hc.submit(ac)
                 if i >= 1:
@@ -195,13 +196,16 @@ def test_host_collector_pipelined_records_equal_direct_rollouts():
             got.append({k: v.copy() for k, v in hc.fetch().items()})
             with pytest.raises(RuntimeError):
                 hc.fetch()
-            assert hc.h2d_bytes > 0 and hc.d2h_bytes == 4 * T * N * (12 + 2 + 7)
+            assert hc.h2d_bytes > 0 and hc.d2h_bytes == 4 * T * N * (12 + 2 + (7 if keys is None else 4))
+            assert set(got[0]) == (set(keys) if keys else {'obs', 'act', 'rew', 'mask', 'v', 'logp', 'terminal_v', 'ret', 'adv'})
         eng.close()
         recs.append(got)
-    assert len(recs[0]) == len(recs[1]) == K
-    for a, b in zip(*recs):
+    assert len(recs[0]) == len(recs[1]) == len(recs[2]) == K
+    for a, b, c in zip(*recs):
         for k in a:
             np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+        for k in c:
+            np.testing.assert_array_equal(a[k], c[k], err_msg=k)
 
 
 def test_ppo_run_matches_an_oracle_deterministic_rollout(tmp_path):
