@@ -136,3 +136,38 @@ def test_metric_extractor_on_reference_style_and_batched_data():
     np.testing.assert_allclose(ma['worst_case_rmse_at_0.5'], np.sort(rmse)[-2:].mean())
     np.testing.assert_allclose(ma['failure_rate'], np.mean([float(e['cv'].any()) for e in eps]))
     assert compute_cvar(np.arange(10.0), 0.3) == 1.0
+
+
+def test_physics_variants_and_adversary_reach_the_engine_config():
+    '''Host resolution of the ABI-v4 fields: `physics` (Physics enum, base_aviary.py:32-40) with the URDF coefficients and the ground-effect clip
+    height (base_aviary.py:130-131), `adversary_disturbance` with the adversary spaces of benchmark_env.py:288-295.'''
+    from safe_control_gym_b200 import _abi
+    env = H.make_env('quadrotor_2D_track', physics='pyb_gnd_drag_dw', adversary_disturbance='dynamics', adversary_disturbance_scale=0.02, adversary_disturbance_offset=0.001)
+    cfg = env.build_config(num_envs=4)
+    assert cfg.physics == _abi.SCG_PHYS_PYB_GND_DRAG_DW and cfg.adversary_mode == _abi.SCG_ADV_DYNAMICS
+    assert (cfg.adversary_scale, cfg.adversary_offset) == (0.02, 0.001)
+    assert cfg.gnd_eff_coeff == 11.36859 and cfg.prop_radius == 2.31348e-2 and cfg.drag_coeff_xy == 9.1785e-7 and cfg.drag_coeff_z == 10.311e-7
+    # GND_EFF_H_CLIP = 0.25 PROP_RADIUS sqrt(15 MAX_RPM^2 KF GND_EFF_COEFF / MAX_THRUST) with MAX_THRUST = 4 KF MAX_RPM^2
+    assert cfg.gnd_eff_h_clip == pytest.approx(0.25 * 2.31348e-2 * np.sqrt(15 * 11.36859 / 4), rel=1e-12)
+    assert env.adversary_action_space.shape == (2,) and env.adversary_observation_space is env.observation_space
+    for name, mode, dim in (('quadrotor_3D_track', 'dynamics', 3), ('quadrotor_3D_track', 'action', 4), ('cartpole', 'dynamics', 2), ('cartpole', 'action', 1)):
+        e = H.make_env(name, adversary_disturbance=mode)
+        assert e.adversary_action_space.shape == (dim,), (name, mode)
+        assert np.all(e.adversary_action_space.low == -1) and np.all(e.adversary_action_space.high == 1)
+    plain = H.make_env('cartpole')
+    assert plain.build_config().adversary_mode == _abi.SCG_ADV_NONE and plain.build_config().physics == _abi.SCG_PHYS_PYB
+    with pytest.raises(RuntimeError, match='adversary_disturbance does not exist'):
+        plain.set_adversary_control(np.zeros(1))
+    with pytest.raises(NotImplementedError):
+        H.make_env('quadrotor_2D_track', physics='dyn')                 # dead code in the reference too (base_aviary.py:495-498)
+    with pytest.raises(NotImplementedError):
+        H.make_env('cartpole', adversary_disturbance='observation')
+
+
+def test_sibling_controllers_are_registered_with_the_reference_defaults():
+    '''controllers/__init__.py of the reference registers ppo, sac, ddpg, rarl, rap, safe_explorer_ppo (...): the ones built here carry the yaml defaults.'''
+    from safe_control_gym_b200.utils.registration import get_config
+    assert get_config('rarl')['agent_iterations'] == 10 and get_config('rarl')['adversary_iterations'] == 10 and get_config('rarl')['rollout_steps'] == 100
+    assert get_config('sac')['hidden_dim'] == 256 and get_config('sac')['warm_up_steps'] == 1000 and get_config('sac')['init_temperature'] == 0.2
+    assert get_config('ddpg')['warm_up_steps'] == 10000 and get_config('ddpg')['random_process']['func'] == 'OrnsteinUhlenbeckProcess'
+    assert get_config('safe_explorer_ppo')['constraint_hidden_dim'] == 10 and get_config('ppo')['mini_batch_size'] == 64
