@@ -347,7 +347,9 @@ template <int HID, int E> struct RolloutSmem {
 // hidden tile is never stored and the whole forward needs two barriers.
 // NP1: the input-pair count (obs_dim / 2) whose first layer is fully unrolled in this instantiation (0 = none): one per system -- every unrolled
 // copy lengthens the code all eight warps fetch each step, and only one of them is ever executed
-template <int HID, int E, int NTN, int AMAX, int NP1 = 0>
+// BAR: 0 = both barriers are __syncthreads (the two nets of a CTA run in lockstep); 1 = this net's NTN threads (the CTA's FIRST NTN threads) run on
+// their own: the barrier between the layers is a named barrier of that group, and there is no closing barrier (the caller has one)
+template <int HID, int E, int NTN, int AMAX, int NP1 = 0, int BAR = 0>
 __device__ __forceinline__ void net_forward(int tl, int net, int n_out, int w3_row0, const float* __restrict__ s_blob, const BlobLayout L,
                                             const float* __restrict__ s_in, float* __restrict__ s_h1n, float* __restrict__ s_outp,
                                             int obs_dim, int act) {
@@ -441,7 +443,8 @@ __device__ __forceinline__ void net_forward(int tl, int net, int n_out, int w3_r
         *reinterpret_cast<float4*>(d + EG * 4) = make_float4(h[2][j], h[2][j + 1], h[3][j], h[3][j + 1]);
     }
     SCG_TK(16);
-    __syncthreads();
+    if constexpr (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync 1, %0;" ::"n"(NTN) : "memory");
     SCG_TK(17);
     // ---- layer 2: [E x H] . [H x H]          (W2P [net][kp][H][2])
     init_acc(s_blob + L.b2 + net * HID + ul0);
@@ -479,7 +482,7 @@ __device__ __forceinline__ void net_forward(int tl, int net, int n_out, int w3_r
         }
     }
     SCG_TK(21);
-    __syncthreads();
+    if constexpr (BAR == 0) __syncthreads();
     SCG_TK(22);
 }
 
@@ -503,6 +506,14 @@ __device__ __forceinline__ void mlp_forward_inl(const float* __restrict__ s_blob
     constexpr int NETSZ = (HID / 2) * (2 * (E / 4) * 4);
     const int net = threadIdx.x / NTN, tl = threadIdx.x % NTN;
     net_forward<HID, E, NTN, A, NP1>(tl, net, net ? 1 : A, net ? A : 0, s_blob, L, s_in, s_h1 + net * NETSZ, s_outp, obs_dim, act);
+}
+// ONE net (0 = actor, 1 = critic) on the CTA's first NT/2 threads, on their own (net_forward BAR = 1): the decoupled schedule of rollout_kernel
+template <int HID, int E, int NT, int A, int NP1 = 0>
+__device__ __noinline__ void half_forward(int net, const float* __restrict__ s_blob, const BlobLayout L, const float* __restrict__ s_in, float* __restrict__ s_h1,
+                                          float* __restrict__ s_outp, int obs_dim, int act) {
+    constexpr int NTN = NT / 2;
+    constexpr int NETSZ = (HID / 2) * (2 * (E / 4) * 4);
+    net_forward<HID, E, NTN, A, NP1, 1>(threadIdx.x, net, net ? 1 : A, net ? A : 0, s_blob, L, s_in, s_h1 + net * NETSZ, s_outp, obs_dim, act);
 }
 // the same for a network pair whose action width is only known at run time (the adversary: a_dim <= AMAX)
 template <int HID, int E, int NT, int AMAX>
@@ -776,6 +787,16 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
 #define SCG_RELAY_ALWAYS 1      // measured (gpurun_out/r2_cold_ab.log): -0.8 % on C3, -3.2 % on the Quadrotor-3D collector, -0.9 % on C2
 #endif
     const bool relay = fast && (P.n_peers > 0 || P.mc_off != 0 || SCG_RELAY_ALWAYS);   // the owner lanes leave act / v / logp to a helper warp when every store has peer copies
+    // DECOUPLED CRITIC (CA).  Nothing inside a step waits for V(s_t): it only goes into the record.  So the step is cut differently: in the ACTOR
+    // phase warps 0-3 evaluate the actor alone (the critical path: obs -> action) while the helper warps 4-6 work off step t-1 (reward / mse,
+    // constraint rows, record stores, the draws of coming episodes) and the owner warp waits; in the ENV phase the owner warp integrates while warps
+    // 0-3 evaluate the CRITIC on the same observation tile and warps 4-6 do what the idle warps did before (obs record, next normals, second half of
+    // the episode preparation).  The value reaches the record through shared memory one phase later.  Same tiles and summation order: same bits.
+#ifndef SCG_CRITIC_ASYNC
+#define SCG_CRITIC_ASYNC 1
+#endif
+    constexpr bool CA = SCG_CRITIC_ASYNC && SCG_RELAY_ALWAYS && FM == SCG_FM_FAST && !SAFE && !XT && SPLIT && NT == 256 && E == 32;
+    __shared__ __align__(16) float s_vp[CA ? NW * (A + 1) * E : 4];     // the critic's per-warp partial sums (layout of s_out; read with mlp_out)
     const int OBS_TILE = od * E;
     // ---- helper-warp work of the FAST schedule (lane ee = env ee of the CTA)
     const int ee = lane;
@@ -807,7 +828,8 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                 float act[A];
 #pragma unroll
                 for (int k = 0; k < A; ++k) act[k] = rb[k * E];
-                store_policy_record(tnp, act, rb[A * E], rb[(A + 1) * E], dn, fl >> 1);
+                const float vrec = CA ? mlp_out<E, NW, A>(s_vp, s_blob, L, A, ee) : rb[A * E];
+                store_policy_record(tnp, act, vrec, rb[(A + 1) * E], dn, fl >> 1);
             }
             int cv = 0;
             if (nc > 0) cv = env_constraints(T, h->rows, nc, h->con_fast, zb, E, nullptr, P.out.d_cvals ? P.out.d_cvals + tnp * nc : nullptr);
@@ -911,13 +933,13 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     constexpr int NIDLE = SPLIT ? NT - 128 : 0;
     constexpr bool DEFER = NIDLE >= 32 && NIDLE >= E;
     const bool gen_eps = !P.deterministic && philox_eps;
-    auto make_eps = [&](int tt) {                        // lanes tid < E: standard normals of step tt into s_eps[tt & 1]
-        if (tid < E && n0 + tid < N) {
-            const uint32_t idx = s_tsteps0[tid] + (uint32_t)tt;          // == that env's total_steps at step tt
-            float* dst = s_eps + (tt & 1) * A * E + tid;
+    auto make_eps = [&](int tt, int el) {                // threads el < E (el = tid: the first warp(s)): standard normals of step tt into s_eps[tt & 1]
+        if (el < E && n0 + el < N) {
+            const uint32_t idx = s_tsteps0[el] + (uint32_t)tt;           // == that env's total_steps at step tt
+            float* dst = s_eps + (tt & 1) * A * E + el;
 #pragma unroll
             for (int k = 0; k < A; k += 2) {                              // one Philox block serves two action dims
-                uint32_t x[4]; philox4x32_10((uint32_t)(k >> 1), idx, h->genv0 + (uint32_t)(n0 + tid), SCG_STREAM_POLICY, h->key0, h->key1, x);
+                uint32_t x[4]; philox4x32_10((uint32_t)(k >> 1), idx, h->genv0 + (uint32_t)(n0 + el), SCG_STREAM_POLICY, h->key0, h->key1, x);
                 dst[k * E] = normal_from_words<float>(x[0], x[1]);
                 if (k + 1 < A) dst[(k + 1) * E] = normal_from_words<float>(x[2], x[3]);
             }
@@ -934,7 +956,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
             if (k >= od) { k -= od; en += 1; }
         }
     };
-    if (DEFER && gen_eps) make_eps(0);
+    if (DEFER && gen_eps) make_eps(0, tid);
     __syncthreads();
 
     int cur = 0;
@@ -954,12 +976,22 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
             for (int k = 0; k < A; ++k) z[k] = __ldg(P.eps + (tn0 + ol) * A + k);
         }
         if (!DEFER) {
-            if (gen_eps) make_eps(t);
+            if (gen_eps) make_eps(t, tid);
             write_obs_record(t, s_oc, tid, NT);      // (a) PPOBuffer.obs[t] <- observation tile (coalesced)
         }
         PROF_T(k1);
         SCG_TK(13);
-        if constexpr (SYS != SCG_SYS_QUAD3D && FM != SCG_FM_RUNTIME) mlp_forward_inl<HID, E, NT, A, NP1>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
+        if constexpr (CA) {
+            // ACTOR phase: warps 0-3 the actor, warps 4-6 the helpers' work on step t-1, then everybody meets
+            if (warp < 4) {
+                if constexpr (SYS != SCG_SYS_QUAD3D) net_forward<HID, E, NT / 2, A, NP1, 1>(tid, 0, A, 0, s_blob, L, s_oc, s_h1, s_out, od, P.activation);
+                else half_forward<HID, E, NT, A, NP1>(0, s_blob, L, s_oc, s_h1, s_out, od, P.activation);
+            } else if (role == 3) {
+                if (h->philox) draw_candidates_coop();              // (warp-uniform: the cooperative form needs all 32 lanes)
+                else if (hl) draw_candidates();
+            } else if (role != 0 && hl && t > 0) process_record(t - 1);
+            __syncthreads();
+        } else if constexpr (SYS != SCG_SYS_QUAD3D && FM != SCG_FM_RUNTIME) mlp_forward_inl<HID, E, NT, A, NP1>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
         else mlp_forward<HID, E, NT, A, NP1>(s_blob, L, s_oc, s_h1, s_out, od, P.activation);
         if constexpr (SAFE) { safety_models<E, A>(P.safety, P.safety_C, P.safety_H, od, s_oc, s_g, tid, NT); __syncthreads(); }
         if constexpr (XT) { if (have_adv) mlp_forward_n<HID, E, NT, A2M>(s_blob2, L2, s_oc, s_h1, s_out2, od, P.activation, A2); }
@@ -998,7 +1030,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
                     const float d = act[k] - mu[k];
                     logp += -(d * d) * inv2var[k] - lsd[k] - log_sqrt_2pi;   // distributions.py:12-21
                 }
-                val = mlp_out<E, NW, A>(s_out, s_blob, L, A, ol);
+                if constexpr (!CA) val = mlp_out<E, NW, A>(s_out, s_blob, L, A, ol);      // (CA: the critic is still running; the record helper reads it)
                 R action[A], state[NX];
 #pragma unroll
                 for (int k = 0; k < A; ++k) action[k] = (R)act[k];
@@ -1133,6 +1165,14 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
 #ifdef SCG_PROF
             if (PROF_ON) { long long k5 = clock64(); pacc[0] += k1 - k0; pacc[1] += k2 - k1; pacc[2] += k5 - k2; }
 #endif
+        } else if constexpr (CA) {
+            if (warp < 4) {                                               // ENV phase: the critic on the observation the actor just used
+                half_forward<HID, E, NT, A, NP1>(1, s_blob, L, s_oc, s_h1, s_vp, od, P.activation);
+            } else {                                                      // warps 4-6: record the policy input, draw the next normals, finish episode starts
+                write_obs_record(t, s_oc, tid - NT / 2, NT / 2 - 32);
+                if (role == 3 && hl) finish_candidates();
+                if (role == 2 && gen_eps && t + 1 < P.T) make_eps(t + 1, lane);
+            }
         } else if (SPLIT && role <= 3) {
             if (fast && role == 3 && E == 32 && h->philox) {   // (warp-uniform condition: the cooperative form needs all 32 lanes)
                 draw_candidates_coop();
@@ -1143,7 +1183,7 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
             }
         } else if (DEFER) {                                               // idle warps: record the policy input, draw the next normals
             write_obs_record(t, s_oc, tid, NIDLE);
-            if (gen_eps && t + 1 < P.T) make_eps(t + 1);
+            if (gen_eps && t + 1 < P.T) make_eps(t + 1, tid);
             if (fast && warp == 1 && ee < E && n0 + ee < N) finish_candidates();   // second half of the episode-start preparation (see above)
         }
         SCG_TK(23);

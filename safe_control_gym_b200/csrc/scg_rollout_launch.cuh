@@ -142,7 +142,8 @@ static RolloutLaunchResult dispatch_rollout(const RolloutLaunch& e, const scg_ro
     }
 #endif
 #ifdef SCG_PROF
-    if (a->hidden_dim == 64 && (E == 0 || E == 32)) return launch_rollout<SYS, R, 64, 32, 256>(e, P, a, s);
+    if (a->hidden_dim == 64 && (E == 0 || E == 32)) return e.fast_ok ? launch_rollout<SYS, R, 64, 32, 256, false, false, SCG_FM_FAST>(e, P, a, s)
+                                                                     : launch_rollout<SYS, R, 64, 32, 256>(e, P, a, s);
     if (a->hidden_dim == 64 && E == 16) return launch_rollout<SYS, R, 64, 16, 128>(e, P, a, s);
     return RolloutLaunchResult{SCG_EINVAL, cudaSuccess, "SCG_PROF build: only hidden 64 / E 32 or 16"};
 #else
