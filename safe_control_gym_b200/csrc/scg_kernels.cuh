@@ -792,8 +792,13 @@ __global__ void __launch_bounds__(NT, rollout_min_blocks(HID, E, NT)) rollout_ke
     // constraint rows, record stores, the draws of coming episodes) and the owner warp waits; in the ENV phase the owner warp integrates while warps
     // 0-3 evaluate the CRITIC on the same observation tile and warps 4-6 do what the idle warps did before (obs record, next normals, second half of
     // the episode preparation).  The value reaches the record through shared memory one phase later.  Same tiles and summation order: same bits.
+    // MEASURED (gpurun_out/r2_ab33.log, profiles/ab_r02_critic_async.log; all 126 GPU parity tests green with it): SLOWER -- C3 1.173 -> 1.191 ms, CartPole
+    // 0.941 -> 1.043 ms, Quadrotor-3D 4.64 -> 5.18 ms.  Per-warp timing shows why: one net on four warps (one per SM sub-partition) takes 5.0 k cycles
+    // alone and 6.1 k next to the owner warp, against 6.7 k for BOTH nets in lockstep on eight warps -- the forward is bound by the length of each
+    // warp's own instruction stream (LDS latency behind a one-deep operand ping-pong), not by FFMA2 throughput, so halving the work per phase does
+    // not halve the phase.  Off by default; kept as a compile-time variant.
 #ifndef SCG_CRITIC_ASYNC
-#define SCG_CRITIC_ASYNC 1
+#define SCG_CRITIC_ASYNC 0
 #endif
     constexpr bool CA = SCG_CRITIC_ASYNC && SCG_RELAY_ALWAYS && FM == SCG_FM_FAST && !SAFE && !XT && SPLIT && NT == 256 && E == 32;
     __shared__ __align__(16) float s_vp[CA ? NW * (A + 1) * E : 4];     // the critic's per-warp partial sums (layout of s_out; read with mlp_out)
