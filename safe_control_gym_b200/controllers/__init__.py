@@ -1,4 +1,4 @@
-'''Register controllers (safe_control_gym/controllers/__init__.py:29-47): `ppo` (the hot path) and its sibling collectors `safe_explorer_ppo`, `rarl`, `sac` and `ddpg`.'''
+'''Register controllers (safe_control_gym/controllers/__init__.py:29-47): `ppo` (the hot path) and its sibling collectors `safe_explorer_ppo`, `rarl`, `rap`, `sac` and `ddpg`.'''
 
 from safe_control_gym_b200.utils.registration import register
 
@@ -13,6 +13,10 @@ register(idx='safe_explorer_ppo',
 register(idx='rarl',
          entry_point='safe_control_gym_b200.controllers.rarl.rarl:RARL',
          config_entry_point='safe_control_gym_b200.controllers.rarl.rarl:DEFAULT_CONFIG')
+
+register(idx='rap',
+         entry_point='safe_control_gym_b200.controllers.rarl.rap:RAP',
+         config_entry_point='safe_control_gym_b200.controllers.rarl.rap:DEFAULT_CONFIG')
 
 register(idx='sac',
          entry_point='safe_control_gym_b200.controllers.sac.sac:SAC',

@@ -2,6 +2,8 @@
 pyb_gnd_drag_dw, base_aviary.py:243-268,386-460), the adversary input (BenchmarkEnv.set_adversary_control, benchmark_env.py:216-228) through
 the step API and the RARL / RAP collector (second actor-critic, rarl.py:349-418) inside the fused rollout -- all against the CPU oracle,
 whose restatement of these pieces is pinned on the reference's formulas by tests/test_oracle_invariants.py.'''
+import os
+
 import numpy as np
 import pytest
 
@@ -282,4 +284,50 @@ def test_off_policy_controllers_write_the_device_replay_buffer(algo, tmp_path):
                 warm_up_steps=B * 20, train_interval=B * 10, train_batch_size=128, hidden_dim=64, max_buffer_size=B * 50)
     ctl2.reset(); ctl2.load(str(tmp_path / 'model_latest.pt'))
     assert len(ctl2.buffer) == len(ctl.buffer) and torch.equal(ctl2.buffer.data['next_obs'], ctl.buffer.data['next_obs']) and torch.equal(ctl2.obs, ctl.obs)
+    ctl.close(); ctl2.close()
+
+
+@pytest.mark.skipif(not os.environ.get('SCG_RUN_UNVERIFIED'), reason='written after the round\'s GPU budget was spent: has not run on a B200 yet (set SCG_RUN_UNVERIFIED=1)')
+def test_rap_controller_composes_a_population_from_replayed_launches(tmp_path):
+    '''`make('rap', ...)` (rap.py): per-env adversary draw, both players' records of the SAME trajectories (launches replayed from a state snapshot),
+    protagonist updated on the batch, every drawn adversary on its columns; checkpoint carries the population.  The host composition itself is
+    covered on CPU (tests/test_rap_host.py); what only a GPU can show is that the replays are bit-identical.'''
+    from functools import partial
+
+    from safe_control_gym_b200 import configs
+    from safe_control_gym_b200.utils.registration import make
+    env_func = partial(make, 'quadrotor', **dict(configs.get('quadrotor_2D_track'), adversary_disturbance='dynamics', adversary_disturbance_scale=0.05))
+    kw = dict(rollout_batch_size=96, rollout_steps=40, mini_batch_size=64, opt_epochs=2, num_adversaries=3, log_interval=0, save_interval=0,
+              eval_interval=0, tensorboard=False)
+    ctl = make('rap', env_func, training=True, checkpoint_path=str(tmp_path / 'model_latest.pt'), output_dir=str(tmp_path), seed=4, **kw)
+    ctl.reset()
+    assert len(ctl.adversaries) == 3
+    rollouts, splits, stats = ctl.collect_rollouts()
+    assert rollouts['obs'].shape == (40, 96, 12) and rollouts['act'].shape == (40, 96, 2)
+    assert sum(d['act'].shape[1] for _, d in splits) == 96 and all(d['act'].shape[2] == 2 for _, d in splits)
+    # the two launches of a group replayed the same trajectories: the adversary-record launch (the last one made) has the protagonist's observations
+    # and masks in the columns of its group, bit for bit
+    g, d = splits[-1]
+    last = ctl._rap_out[(40, True)]
+    n = d['act'].shape[1]
+    assert torch.equal(last['obs'][:, 96 - n:], rollouts['obs'][:, 96 - n:]) and torch.equal(last['mask'][:, 96 - n:], rollouts['mask'][:, 96 - n:])
+    snap = lambda ag: [p.detach().clone() for p in ag.ac.parameters()]
+    a0, v0 = snap(ctl.agent), [snap(a) for a in ctl.adversaries]
+    res = ctl.train_step()
+    assert any(not torch.equal(a, b) for a, b in zip(a0, snap(ctl.agent)))
+    for idx in range(3):
+        moved = any(not torch.equal(a, b) for a, b in zip(v0[idx], snap(ctl.adversaries[idx])))
+        assert moved == (idx in res['adv_indices']), idx
+        if idx in res['adv_indices']:
+            assert np.isfinite(res[f'policy_loss_adv{idx}'])
+    ctl.save(str(tmp_path / 'model_latest.pt'))
+    state = torch.load(str(tmp_path / 'model_latest.pt'), weights_only=False)
+    assert isinstance(state['adversary'], list) and len(state['adversary']) == 3
+    ctl2 = make('rap', env_func, training=True, checkpoint_path=str(tmp_path / 'model_latest.pt'), output_dir=str(tmp_path), seed=4, **kw)
+    ctl2.reset(); ctl2.load(str(tmp_path / 'model_latest.pt'))
+    for i in range(3):
+        for a, b in zip(snap(ctl.adversaries[i]), snap(ctl2.adversaries[i])):
+            assert torch.equal(a, b)
+    quiet, pushed = ctl.run(n_episodes=8), ctl.run(n_episodes=8, use_adv=True)
+    assert quiet['ep_returns'].shape == (8,) and np.all(np.isfinite(pushed['ep_returns']))
     ctl.close(); ctl2.close()
