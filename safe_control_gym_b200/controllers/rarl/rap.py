@@ -12,8 +12,9 @@ copied out of those two records.  Cost: 2 x |adversaries drawn| launches over al
 fused RAP collector (that would need a per-env adversary index and a second record in the kernel: DESIGN.md 8); at the reference's batch sizes
 (rollout_batch_size 4, two adversaries) the launches are microseconds.
 
-STATUS: host logic covered by the CPU tests (tests/test_rap_host.py, engine replaced by a stand-in); the GPU test (tests/test_gpu_extended.py,
-`SCG_RUN_UNVERIFIED=1`) was written after this round's GPU budget was spent and has not run on a B200 yet.
+STATUS: host logic covered by the CPU tests (tests/test_rap_host.py, engine replaced by a stand-in).  The GPU test (tests/test_gpu_extended.py,
+opt-in with `SCG_RUN_UNVERIFIED=1`) ran ONCE with the last GPU seconds of round 2 and stopped at a host-side unpacking bug in `collect_rollouts`
+(fixed since, and the stand-in engine now checks the same contract); it has not passed on a B200 yet -- treat this class as unverified on the device.
 '''
 
 import time
@@ -77,6 +78,7 @@ class RAP(RARL):
 
     # ------------------------------------------------------------------------------------------
     def _blob_of(self, agent):
+        '''-> (packed rollout blob, dims) of one agent, like PPO._policy_blob / RARL._adversary_blob'''
         from safe_control_gym_b200.engine import pack_policy
         return agent.fused.rollout_blob() if agent.fused is not None else pack_policy(agent.ac, self.device)
 
@@ -89,12 +91,11 @@ class RAP(RARL):
         self.env.reset()                                                 # rap.py:360: every collect starts from fresh episodes
         snap = eng.get_state()
         blob, dims = self._policy_blob()
-        adv_dims = (dims[0], int(self.adv_act_space.shape[0]), dims[2])
         want = ('ret', 'adv', 'cviol', 'mse', 'last', 'episode')
         rollouts, rollouts_adv, stats = {}, {}, {}
         for g, s, e in zip(groups, starts, ends):
             s, e = int(s), int(e)
-            adv_blob = self._blob_of(self.adversaries[int(g)])
+            adv_blob, adv_dims = self._blob_of(self.adversaries[int(g)])     # (packed blob, (obs_dim, adversary act_dim, hidden))
             for adv_record in (False, True):
                 eng.set_state(snap)
                 key = (T, adv_record)

@@ -46,6 +46,7 @@ class _FakeEngine:
         assert self.state == 'snap', 'every launch must replay from the snapshot'
         self.state = 'dirty'
         adv_blob, adv_dims = adversary
+        assert torch.is_tensor(adv_blob) and adv_blob.dtype == torch.float32 and adv_blob.is_contiguous()      # engine.rollout's own checks
         assert adv_dims == (dims[0], self.A2, dims[2])
         gid = int(adv_blob[0])
         self.launches.append((gid, bool(adv_record)))
@@ -83,8 +84,10 @@ def _bare_rap(N, T, K, A=2, A2=3, seed=5):
     ctl._adv_rng = np.random.RandomState(seed)
     ctl.adv_act_space = type('S', (), {'shape': (A2,)})()
     ctl._policy_blob = lambda: (torch.zeros(4), (3, A, 64))
-    ctl.adversaries = list(range(K))
-    ctl._blob_of = lambda agent: torch.full((4,), float(agent))         # the stand-in launch reads the adversary's id from its blob
+    # stand-in agents with the fused-update interface the real ones have (FusedPPOState.rollout_blob -> (blob, dims)); RAP._blob_of itself is the
+    # code under test.  The stand-in launch reads the adversary's id from its blob.
+    fused = lambda i: type('F', (), {'rollout_blob': lambda self: (torch.full((4,), float(i)), (3, A2, 64))})()
+    ctl.adversaries = [type('Agent', (), {'fused': fused(i)})() for i in range(K)]
     return ctl, eng
 
 
