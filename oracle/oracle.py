@@ -149,6 +149,10 @@ class Oracle:
         assert tab.shape[1:] == (self.N, self.D), (tab.shape, self.N, self.D)
         self.lib.scg_oracle_set_noise_table(self.h, _p(tab), C.c_int(tab.shape[0]))
 
+    def set_stale_force_point(self, on=True):
+        '''Reference quirk (off by default, absent from the CUDA path): see scg_oracle_set_stale_force_point in scg_oracle.c.'''
+        self.lib.scg_oracle_set_stale_force_point(self.h, C.c_int(int(bool(on))))
+
     def set_env_state(self, i, state, inertial=None):
         s = np.ascontiguousarray(state, dtype=np.float64)
         inr = None if inertial is None else np.ascontiguousarray(inertial, dtype=np.float64)

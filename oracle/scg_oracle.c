@@ -125,6 +125,7 @@ typedef struct scg_oracle {
     /* tables */
     int K, P; double* ep_table;                  /* [K][N][P] */
     int Tn, D; double* noise_table;              /* [Tn][N][D] */
+    int stale_force_point;                       /* see scg_oracle_set_stale_force_point */
     int n_off_slots;                             /* number of randomised step offsets */
     long noise_cursor;
     oenv* envs;
@@ -203,6 +204,13 @@ void scg_oracle_set_episode_table(scg_oracle* o, const double* tab, int K) {
     free(o->ep_table); o->K = K; size_t n = (size_t)K * o->cfg.num_envs * o->P;
     o->ep_table = (double*)malloc(sizeof(double) * n); memcpy(o->ep_table, tab, sizeof(double) * n);
 }
+/* Reference quirk, OFF by default (the CUDA path does not have it; tests/test_refloop_golden.py switches it on to show that the restatement
+ * reproduces the reference with it).  BA:268-279 applies the dynamics disturbance force with flags=WORLD_FRAME at posObj = self.pos, and under
+ * physics 'pyb' self.pos is only refreshed at the END of a control step (BA:246-251 refreshes per sub-step for the other physics variants only):
+ * from the second sub-step on the force acts at the position the drone had when the control step began, i.e. with the lever arm
+ * (pos_at_step_start - pos_now) about the centre of mass -- a small torque the "force through the CoM" reading does not have. */
+void scg_oracle_set_stale_force_point(scg_oracle* o, int on) { o->stale_force_point = on; }
+
 void scg_oracle_set_noise_table(scg_oracle* o, const double* tab, int Tn) {
     free(o->noise_table); o->Tn = Tn; size_t n = (size_t)Tn * o->cfg.num_envs * (o->D > 0 ? o->D : 1);
     o->noise_table = (double*)malloc(sizeof(double) * n); memcpy(o->noise_table, tab, sizeof(double) * (size_t)Tn * o->cfg.num_envs * o->D);
@@ -261,7 +269,7 @@ static void rpy_from_quat(const double q[4], double rpy[3]) {
 /* ------------------------------------------------------------------------------------------ */
 /* physics: one Bullet stepSimulation() of dt for the free-flying Crazyflie (BA:252-282, 364-384) */
 /* ------------------------------------------------------------------------------------------ */
-static void quad_substep(const scg_config* c, oenv* e, const double rpm[4], const double fdist[3], int has_dist, double dt) {
+static void quad_substep(const scg_config* c, oenv* e, const double rpm[4], const double fdist[3], int has_dist, double dt, const double* force_point) {
     const double m = e->inertial[0];
     const double J[3] = {e->inertial[1], e->inertial[2], e->inertial[3]};
     double R[9]; rot_from_quat(e->quat, R);
@@ -305,6 +313,11 @@ static void quad_substep(const scg_config* c, oenv* e, const double rpm[4], cons
         F[0] += d2[0]; F[1] += d2[1]; F[2] += d2[2];
     }
     if (has_dist) { F[0] += fdist[0]; F[1] += fdist[1]; F[2] += fdist[2]; }
+    if (has_dist && force_point) {                     /* stale application point (scg_oracle_set_stale_force_point): tau_w = (p0 - p) x f, into the body frame */
+        const double ar[3] = {force_point[0] - e->pos[0], force_point[1] - e->pos[1], force_point[2] - e->pos[2]};
+        const double tw[3] = {ar[1] * fdist[2] - ar[2] * fdist[1], ar[2] * fdist[0] - ar[0] * fdist[2], ar[0] * fdist[1] - ar[1] * fdist[0]};
+        for (int r = 0; r < 3; ++r) tau_b[r] += R[r] * tw[0] + R[3 + r] * tw[1] + R[6 + r] * tw[2];
+    }
     /* body rates and Euler's equation with the gyroscopic term (btMultiBody m_useGyroTerm = true) */
     double wb[3] = {R[0] * e->omega[0] + R[3] * e->omega[1] + R[6] * e->omega[2],
                     R[1] * e->omega[0] + R[4] * e->omega[1] + R[7] * e->omega[2],
@@ -638,7 +651,9 @@ static void env_step(scg_oracle* o, int i, const double* action, const double* n
                 e->adv_set = 0;
             }
         }
-        for (int s = 0; s < steps; ++s) quad_substep(c, e, rpm, fd, has_dist, dt);
+        const double pos0[3] = {e->pos[0], e->pos[1], e->pos[2]};
+        const double* fp = (o->stale_force_point && c->physics == SCG_PHYS_PYB && steps > 1) ? pos0 : NULL;
+        for (int s = 0; s < steps; ++s) quad_substep(c, e, rpm, fd, has_dist, dt, fp);
     }
     extract_state(o, e);
     make_obs(o, e, 0, &ns, obs_out);

@@ -1,0 +1,102 @@
+'''The oracle against trajectories recorded from the UNMODIFIED reference environments run in the loop (tools/make_golden_refloop.py +
+tools/ref_harness.py: `Quadrotor.reset()/step()` of the reference executed here with PyBullet replaced by a stand-in rigid body; the files under
+tests/golden/refloop_*.npz are its committed output).
+
+Every case rebuilds the recorded task config through this repo's host env (`make('quadrotor', **cfg)`), draws the episode table and the per-step
+noise table with the host env's own generator seeded like the reference env (same draws in the same order, interleaved the way the reference
+interleaves them: reset draws, then one row per step), hands them to the CPU oracle and steps it with the recorded actions.  Every number the
+reference returned must come back: observations (incl. the terminal one and the one after each reset), reward, done, TimeLimit.truncated, info['mse'],
+out_of_bounds, goal_reached, constraint values / violation flag, the step counter, the state, X_GOAL.
+
+Pinned by this: everything the reference computes around the integrator (action map, PWM / RPM conversion, force application, observation assembly,
+goal look-ahead, reward, termination, constraints, disturbance flow, randomisation order and arithmetic, time limit, reset).  NOT pinned: PyBullet's
+integrator itself (the stand-in integrates the way the oracle's restatement does).'''
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from safe_control_gym_b200.envs import disturbances as dist_mod
+from safe_control_gym_b200.utils.registration import make
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+CASES = ['quad2d_track', 'quad2d_track_short', 'quad3d_track', 'quad3d_track_noise', 'quad2d_stab_noise']
+ATOL = 2e-9        # float64 on both sides; the two integrators associate their sums differently, the horizon amplifies that a little
+
+
+def _close(a, b, what, t, atol=ATOL):
+    np.testing.assert_allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), rtol=1e-9, atol=atol, err_msg=f'{what} at step {t}')
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_oracle_reproduces_the_reference_in_the_loop(case):
+    G = np.load(os.path.join(GOLD, f'refloop_{case}.npz'))
+    cfg = json.loads(str(G['task_config']))
+    env = make('quadrotor', **cfg)
+    T = len(G['rew'])
+    # (a16) the reference trajectory generator, whole table
+    np.testing.assert_allclose(np.asarray(env._x_goal_table(), dtype=np.float64).reshape(G['x_goal'].shape), G['x_goal'], rtol=0, atol=1e-12)
+    assert int(env.CTRL_STEPS) == int(G['ctrl_steps'])
+    # the reference's draws, re-made by the host env's own draw functions on a generator seeded the same way, in the reference's interleaving
+    env.seed(cfg['seed'])
+    obs_dist = {'observation': env.disturbances['observation']} if env.disturbances.get('observation') is not None else None
+    ep_rows, step_rows, reset_draws = [], [], []
+
+    def draw_reset():
+        ep_rows.append(env.draw_episode_row())
+        # the reference also disturbs the observation that reset() returns (quadrotor.py:387 -> _get_observation): one more draw per reset
+        reset_draws.append(dist_mod.draw_step_noise(obs_dist, env.np_random) if obs_dist else [])
+    draw_reset()
+    for t in range(T):
+        step_rows.append(env.draw_step_row())
+        if G['done'][t]:
+            draw_reset()
+    o = H.make_oracle(env, 1, auto_reset=True, rng_mode='table')
+    o.set_episode_table(np.asarray(ep_rows, dtype=np.float64)[:, None, :])
+    if o.D > 0:
+        o.set_noise_table(np.asarray(step_rows, dtype=np.float64)[:, None, :])
+    if env.disturbances.get('dynamics') is not None:
+        # the reference applies the disturbance force at the position the drone had when the control step began (base_aviary.py:268-279 with
+        # physics 'pyb'): a small torque.  The oracle has that behind a switch; the CUDA path does not have it.
+        o.set_stale_force_point(True)
+    nx = env.state_dim
+
+    def check_reset(obs, ep, t):
+        # TABLE mode of the oracle / the kernels carries no noise for the reset observation (the episode row has no slot for it; Philox mode draws it
+        # from its own stream): the oracle returns the undisturbed one.  So: the oracle's reset observation = the reference's reset STATE (+ goal), and
+        # the reference's reset observation = that + the white noise made of the draws the host generator produced at this point of the stream.
+        want = np.array(G['reset_obs'][ep], dtype=np.float64)
+        if obs_dist:
+            std = np.concatenate([np.broadcast_to(np.asarray(d.std, dtype=np.float64), (d.dim,)) for d in env.disturbances['observation'].disturbances])
+            _close(G['reset_state'][ep] + std * np.asarray(reset_draws[ep]), want[:nx], 'reference reset observation = state + std * draw', t)
+            want[:nx] = G['reset_state'][ep]
+        _close(obs, want, 'observation after a reset', t)
+    r = o.reset()
+    check_reset(r['obs'][0], 0, -1)
+    ep, nc = 0, G['cvals'].shape[1]
+    for t in range(T):
+        s = o.step(G['act'][t][None, :])
+        assert bool(s['done'][0]) == bool(G['done'][t]), f'done at step {t}'
+        done = bool(G['done'][t])
+        _close(s['terminal_obs'][0] if done else s['obs'][0], G['obs'][t], 'observation', t)
+        _close(s['terminal_state'][0] if done else s['state'][0], G['state'][t], 'state', t)
+        _close(s['rew'][0], G['rew'][t], 'reward', t)
+        _close(s['mse'][0], G['mse'][t], 'mse', t)
+        assert bool(s['truncated'][0]) == bool(G['truncated'][t]), f'TimeLimit.truncated at step {t}'
+        if s['goal_reached'][0]:
+            # stabilisation goal reached: quadrotor.py:871-874 returns before `self.out_of_bounds` is refreshed, so info['out_of_bounds'] of such a
+            # step is whatever an earlier step left there (and info has no 'goal_reached' key unless the cost is quadratic, :905-906): the episode must
+            # end, the flag itself is not comparable
+            assert done, f'goal reached without done at step {t}'
+        else:
+            assert bool(s['out_of_bounds'][0]) == bool(G['out_of_bounds'][t]), f'out_of_bounds at step {t}'
+        assert int(s['current_step'][0]) == int(G['current_step'][t]), f'current_step at step {t}'
+        if env.constraints is not None:
+            _close(s['cvals'][0][:nc], G['cvals'][t], 'constraint values', t, atol=2e-8)        # (the reference rounds them to 8 decimals: constraints.py:104)
+            assert float(s['cviol'][0]) == float(G['cviol'][t]), f'constraint_violation at step {t}'
+        if done:
+            ep += 1
+            check_reset(s['obs'][0], ep, t)
+    assert ep + 1 == len(G['reset_obs'])

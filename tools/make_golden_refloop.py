@@ -1,0 +1,79 @@
+'''Golden trajectories from the UNMODIFIED reference environments run in the loop (tools/ref_harness.py: PyBullet replaced by a stand-in rigid
+body, casadi / gymnasium / matplotlib by shells).  Run in the build container:  python tools/make_golden_refloop.py  -> tests/golden/refloop_*.npz
+
+Every case drives `Quadrotor.reset()` / `Quadrotor.step()` of /root/reference with a seeded action sequence (reset after every `done`, like
+DummyVecEnv does) and stores what the reference returned at every step: observation, reward, done, info (mse, out_of_bounds, constraint_values,
+constraint_violation, current_step, TimeLimit.truncated, terminal observation), the observation after each reset, X_GOAL, the task config
+(JSON) the env was built from, and the inertial properties each episode ran with.  tests/test_refloop_golden.py rebuilds the same config
+through THIS repo's host env, draws the episode / noise tables with its own generator seeded the same way, and requires the oracle to
+reproduce every recorded number.  What this pins and what it does not: see tools/ref_harness.py.
+'''
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_harness as RH  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
+
+
+def run_case(name, cfg, T, act_seed, act_scale):
+    env = RH.make_quadrotor(**cfg)
+    rng = np.random.default_rng(act_seed)
+    A, od = env.action_dim, env.observation_space.shape[0]
+    nc = env.constraints.num_constraints if env.constraints is not None else 0
+    rec = dict(act=np.zeros((T, A)), obs=np.zeros((T, od)), rew=np.zeros(T), done=np.zeros(T, np.uint8), mse=np.zeros(T), out_of_bounds=np.zeros(T, np.uint8),
+               cvals=np.zeros((T, max(nc, 1))), cviol=np.zeros(T), current_step=np.zeros(T, np.int32), truncated=np.zeros(T, np.uint8),
+               state=np.zeros((T, env.state_dim)), goal_reached=np.zeros(T, np.uint8))
+    reset_obs, reset_state, inertial = [], [], []
+    obs, info = env.reset()
+    reset_obs.append(obs.copy()); reset_state.append(np.array(env.state, dtype=np.float64))
+    inertial.append([env.OVERRIDDEN_QUAD_MASS] + list(env.OVERRIDDEN_QUAD_INERTIA))
+    for t in range(T):
+        # mostly moderate actions; now and then a saturating one so that clipping, constraint violations and terminations occur
+        a = rng.uniform(-1, 1, size=A) * (act_scale if rng.uniform() < 0.9 else 3.0)
+        obs, rew, done, info = env.step(a)
+        rec['act'][t], rec['obs'][t], rec['rew'][t], rec['done'][t] = a, obs, rew, done
+        rec['state'][t] = env.state
+        rec['mse'][t], rec['out_of_bounds'][t] = info['mse'], info.get('out_of_bounds', False)
+        rec['goal_reached'][t] = info.get('goal_reached', False)
+        if nc:
+            rec['cvals'][t], rec['cviol'][t] = info['constraint_values'], info['constraint_violation']
+        rec['current_step'][t] = info['current_step']
+        rec['truncated'][t] = info.get('TimeLimit.truncated', False)
+        if done:
+            obs, info = env.reset()
+            reset_obs.append(obs.copy()); reset_state.append(np.array(env.state, dtype=np.float64))
+            inertial.append([env.OVERRIDDEN_QUAD_MASS] + list(env.OVERRIDDEN_QUAD_INERTIA))
+    path = os.path.join(OUT, f'refloop_{name}.npz')
+    np.savez_compressed(path, task_config=np.array(json.dumps(cfg)), x_goal=np.asarray(env.X_GOAL, dtype=np.float64), reset_obs=np.asarray(reset_obs), reset_state=np.asarray(reset_state),
+                        inertial=np.asarray(inertial), ctrl_steps=np.int32(env.CTRL_STEPS), **rec)
+    print(f'{name}: T={T} episodes={len(reset_obs)} done={int(rec["done"].sum())} truncated={int(rec["truncated"].sum())} '
+          f'oob={int(rec["out_of_bounds"].sum())} cviol={int(rec["cviol"].sum())} -> {os.path.getsize(path)} bytes')
+    env.close()
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    c3 = RH.load_task_config('examples/rl/config_overrides/quadrotor_2D/quadrotor_2D_track.yaml')
+    run_case('quad2d_track', c3, T=500, act_seed=1, act_scale=0.5)
+    # the same with the episode shortened so that the time limit fires (TimeLimit.truncated, benchmark_env.py:497-502)
+    run_case('quad2d_track_short', dict(c3, episode_len_sec=1, seed=7), T=300, act_seed=2, act_scale=0.3)
+    c4 = RH.load_task_config('examples/rl/config_overrides/quadrotor_3D/quadrotor_3D_track.yaml')
+    run_case('quad3d_track', c4, T=400, act_seed=3, act_scale=0.4)
+    # randomised inertial properties (class-default ranges, the additive quirk) + white-noise force on the dynamics + action white noise
+    c4n = dict(c4, randomized_inertial_prop=True, seed=11,
+               disturbances=dict(dynamics=[dict(disturbance_func='white_noise', std=0.01)], action=[dict(disturbance_func='white_noise', std=0.002)]))
+    run_case('quad3d_track_noise', c4n, T=400, act_seed=4, act_scale=0.4)
+    # 2-D stabilisation with the goal tolerance active, observation noise and a step disturbance on the dynamics
+    c2s = dict(c3, task='stabilization', task_info=dict(stabilization_goal=[0.3, 1.1], stabilization_goal_tolerance=0.4), seed=3, obs_goal_horizon=0,
+               disturbances=dict(observation=[dict(disturbance_func='white_noise', std=0.01)],
+                                 dynamics=[dict(disturbance_func='step', magnitude=0.02, step_offset=10)]))
+    run_case('quad2d_stab_noise', c2s, T=300, act_seed=5, act_scale=0.3)
+
+
+if __name__ == '__main__':
+    main()

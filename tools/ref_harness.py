@@ -1,0 +1,370 @@
+'''Reference-in-the-loop harness (build container only; needs /root/reference).
+
+Runs the UNMODIFIED reference environments -- `safe_control_gym/envs/gym_pybullet_drones/quadrotor.py` (+ base_aviary.py, benchmark_env.py,
+constraints.py, disturbances.py, quadrotor_utils.py, transformations.py, normalization.py) and `envs/gym_control/cartpole.py` -- with the
+third-party packages that are NOT installed here replaced by stand-ins:
+
+* `pybullet`: FakeBullet below -- the handful of API calls the envs make, backed by one floating rigid body (quadrotor) or a cart + pole chain
+  (cart-pole) integrated the way DESIGN.md 2 / SURVEY.md 8(c) restate Bullet's `stepSimulation` (symplectic Euler, exponential-map orientation
+  update, gyroscopic term, forces cleared every step).  The physics inside is therefore NOT a pin of PyBullet (only real PyBullet can be: the
+  cart-pole is pinned by tests/golden/cartpole_pybullet_transitions.npz, the quadrotor by tools/record_pybullet_goldens.py when a wheel exists).
+  What it buys: EVERYTHING AROUND the integrator -- action maps, PWM / RPM conversion, which link gets which force in which frame, URDF offsets,
+  observation assembly (Euler angles, body rates), goal look-ahead, rewards, termination, constraint values, disturbance flow, randomisation
+  order, time-limit truncation, reset -- is computed by the reference's own code, and the oracle has to reproduce it.
+* `casadi`: an object that accepts any call / attribute / arithmetic (the symbolic model is built by the constructors but is out of scope).
+* `gymnasium`: `spaces.Box`, `Env`, `utils.seeding.np_random` (same stream: numpy Generator over PCG64 seeded with SeedSequence(seed)).
+* `matplotlib.pyplot`, `pybullet_data`: empty.
+`import safe_control_gym` itself would import every subsystem; empty package shells with the right `__path__` let the env modules load from the
+files where they lie.  No reference file is modified or copied.
+'''
+import math
+import os
+import sys
+import types
+import xml.etree.ElementTree as etxml
+
+import numpy as np
+
+REF_ROOT = '/root/reference'
+REF = os.path.join(REF_ROOT, 'safe_control_gym')
+
+
+# ------------------------------------------------------------------------------------------------
+class _Any:
+    '''casadi stand-in: survives any use, means nothing'''
+    __array_priority__ = 1000
+    __array_ufunc__ = None
+
+    def __init__(self, *a, **k):
+        pass
+
+    def __call__(self, *a, **k):
+        return _Any()
+
+    def __getattr__(self, n):
+        if n.startswith('__') and n.endswith('__'):
+            raise AttributeError(n)
+        return _Any()
+
+    def __getitem__(self, i):
+        return _Any()
+
+    def __setitem__(self, i, v):
+        pass
+
+    def __iter__(self):
+        return iter(())
+
+    def __len__(self):
+        return 0
+
+    def _op(self, *a):
+        return _Any()
+    __add__ = __radd__ = __sub__ = __rsub__ = __mul__ = __rmul__ = __truediv__ = __rtruediv__ = __matmul__ = __rmatmul__ = __pow__ = __rpow__ = _op
+    __neg__ = __pos__ = _op
+
+
+class _AnyModule(types.ModuleType):
+    def __getattr__(self, n):
+        if n.startswith('__') and n.endswith('__'):
+            raise AttributeError(n)
+        return _Any()
+
+
+# ------------------------------------------------------------------------------------------------
+def _quat_mul(a, b):      # (x, y, z, w)
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz, aw * bz + az * bw + ax * by - ay * bx,
+                     aw * bw - ax * bx - ay * by - az * bz])
+
+
+def _rot(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+class FakeBullet(types.ModuleType):
+    '''The PyBullet calls of base_aviary.py / quadrotor.py / cartpole.py on ONE body per client.'''
+    GUI, DIRECT, LINK_FRAME, WORLD_FRAME = 1, 2, 1, 2
+    COV_ENABLE_GUI = COV_ENABLE_RGB_BUFFER_PREVIEW = COV_ENABLE_DEPTH_BUFFER_PREVIEW = COV_ENABLE_SEGMENTATION_MARK_PREVIEW = 0
+    ER_TINY_RENDERER = ER_SEGMENTATION_MASK_OBJECT_AND_LINKINDEX = 0
+    VELOCITY_CONTROL = TORQUE_CONTROL = 0
+    JOINT_PRISMATIC, JOINT_REVOLUTE = 1, 0
+
+    def __init__(self):
+        super().__init__('pybullet')
+        self.log = []
+        self._reset_world()
+
+    def _reset_world(self):
+        self.gravity, self.dt = np.zeros(3), 1.0 / 240
+        self.body = None            # ('quad', dict) | ('cartpole', dict)
+        self.next_id = 0
+
+    def __getattr__(self, n):                           # camera / GUI / logging calls: accepted, ignored
+        if n.startswith('__') and n.endswith('__'):
+            raise AttributeError(n)
+        return lambda *a, **k: None
+
+    # -- world -----------------------------------------------------------------------------------
+    def connect(self, *a, **k):
+        return 0
+
+    def disconnect(self, *a, **k):
+        pass
+
+    def resetSimulation(self, *a, **k):
+        self._reset_world()
+
+    def setGravity(self, gx, gy, gz, **k):
+        self.gravity = np.array([gx, gy, gz], dtype=np.float64)
+
+    def setTimeStep(self, dt, **k):
+        self.dt = float(dt)
+
+    def setRealTimeSimulation(self, *a, **k):
+        pass
+
+    def setAdditionalSearchPath(self, *a, **k):
+        pass
+
+    def configureDebugVisualizer(self, *a, **k):
+        pass
+
+    def resetDebugVisualizerCamera(self, *a, **k):
+        pass
+
+    def setJointMotorControl2(self, *a, **k):       # cartpole.py:310-311 disables the default joint motors: nothing to do, there are none here
+        pass
+
+    def loadURDF(self, path, basePosition=(0, 0, 0), baseOrientation=(0, 0, 0, 1), **k):
+        bid = self.next_id
+        self.next_id += 1
+        if os.path.basename(path) == 'plane.urdf':
+            return bid
+        tree = etxml.parse(path).getroot()
+        if tree.attrib.get('name', '').startswith('cf2') or 'cf2' in os.path.basename(path):
+            # Bullet link index i = child link of the i-th joint of the file.  LINK_FRAME of applyExternalForce / applyExternalTorque is the
+            # link's centre-of-mass (inertial) frame: joint origin + the child link's <inertial><origin> (cf2x.urdf puts the propeller
+            # positions there; the joints have no origin), all fixed and un-rotated here.
+            inertial_origin = {}
+            for l in tree.findall('link'):
+                o = l.find('inertial/origin')
+                assert o is None or all(float(v) == 0 for v in o.attrib.get('rpy', '0 0 0').split())
+                inertial_origin[l.attrib['name']] = np.array([float(v) for v in o.attrib['xyz'].split()]) if o is not None else np.zeros(3)
+            offs = []
+            for j in tree.findall('joint'):
+                o = j.find('origin')
+                assert j.attrib['type'] == 'fixed' and (o is None or all(float(v) == 0 for v in o.attrib.get('rpy', '0 0 0').split()))
+                jo = np.array([float(v) for v in o.attrib['xyz'].split()]) if o is not None else np.zeros(3)
+                offs.append(jo + inertial_origin[j.find('child').attrib['link']])
+            base = tree.find('link')
+            self.body = ('quad', dict(id=bid, mass=float(base.find('inertial/mass').attrib['value']),
+                                      J=np.array([float(base.find('inertial/inertia').attrib[k2]) for k2 in ('ixx', 'iyy', 'izz')]),
+                                      link_off=offs,
+                                      pos=np.array(basePosition, dtype=np.float64), quat=np.array(baseOrientation, dtype=np.float64),
+                                      vel=np.zeros(3), omega=np.zeros(3), F=np.zeros(3), tau=np.zeros(3)))
+        else:                                                      # cartpole_template-derived file written by cartpole.py
+            self.body = ('cartpole', dict(id=bid, urdf=path, q=np.zeros(2), qd=np.zeros(2), mass={}, force=0.0, tap=None,
+                                          pole_len=None))
+            for l in tree.findall('link'):
+                if l.find('inertial/mass') is not None:
+                    self.body[1]['mass'][l.attrib['name']] = float(l.find('inertial/mass').attrib['value'])
+            box = [l for l in tree.findall('link') if l.attrib['name'] == 'pole'][0].find('collision/geometry/box')
+            self.body[1]['pole_box'] = np.array([float(v) for v in box.attrib['size'].split()])
+        return bid
+
+    def changeDynamics(self, bid, linkIndex=-1, mass=None, localInertiaDiagonal=None, linearDamping=None, angularDamping=None, **k):
+        kind, b = self.body
+        link = linkIndex
+        if kind == 'quad':
+            if mass is not None:
+                b['mass'] = float(mass)
+            if localInertiaDiagonal is not None:
+                b['J'] = np.array(localInertiaDiagonal, dtype=np.float64)
+        else:
+            if mass is not None:                       # link -1 = slider (cart) base?  cartpole.py:318-322: linkIndex 0 cart, 1 pole
+                b['mass'][link] = float(mass)
+
+    # -- quadrotor body ----------------------------------------------------------------------------
+    def resetBasePositionAndOrientation(self, bid, pos, quat, **k):
+        b = self.body[1]
+        b['pos'], b['quat'] = np.array(pos, dtype=np.float64), np.array(quat, dtype=np.float64)
+
+    def resetBaseVelocity(self, bid, linearVelocity=(0, 0, 0), angularVelocity=(0, 0, 0), **k):
+        b = self.body[1]
+        b['vel'], b['omega'] = np.array(linearVelocity, dtype=np.float64), np.array(angularVelocity, dtype=np.float64)
+
+    def getBasePositionAndOrientation(self, bid, **k):
+        b = self.body[1]
+        return tuple(b['pos']), tuple(b['quat'])
+
+    def getBaseVelocity(self, bid, **k):
+        b = self.body[1]
+        return tuple(b['vel']), tuple(b['omega'])
+
+    def getQuaternionFromEuler(self, rpy, **k):          # Bullet: ZYX (yaw, pitch, roll) -> (x, y, z, w)
+        r, p, y = (float(v) for v in rpy)
+        cr, sr, cp, sp, cy, sy = math.cos(r / 2), math.sin(r / 2), math.cos(p / 2), math.sin(p / 2), math.cos(y / 2), math.sin(y / 2)
+        return (sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy)
+
+    def getEulerFromQuaternion(self, q, **k):            # Bullet b3Quaternion::getEulerZYX incl. its gimbal branch
+        x, y, z, w = (float(v) for v in q)
+        sqx, sqy, sqz, sqw = x * x, y * y, z * z, w * w
+        sarg = -2.0 * (x * z - w * y)
+        if sarg <= -0.99999:
+            return (0.0, -0.5 * math.pi, 2 * math.atan2(x, -y))
+        if sarg >= 0.99999:
+            return (0.0, 0.5 * math.pi, 2 * math.atan2(-x, y))
+        return (math.atan2(2 * (y * z + w * x), sqw - sqx - sqy + sqz), math.asin(sarg), math.atan2(2 * (x * y + w * z), sqw + sqx - sqy - sqz))
+
+    def getMatrixFromQuaternion(self, q, **k):
+        return tuple(_rot(np.array(q, dtype=np.float64)).reshape(-1))
+
+    def applyExternalForce(self, bid, linkIndex, forceObj, posObj, flags, **k):
+        link = linkIndex
+        kind, b = self.body
+        f, r = np.array(forceObj, dtype=np.float64), np.array(posObj, dtype=np.float64)
+        if kind == 'cartpole':                             # cartpole.py:560-566: tap force on the pole link, WORLD_FRAME at the pole CoM
+            b['tap'] = f
+            return
+        R = _rot(b['quat'])
+        if flags == self.LINK_FRAME:
+            off = b['link_off'][link] if link >= 0 else np.zeros(3)
+            fw, arm = R @ f, R @ (off + r)
+        else:
+            fw, arm = f, r - b['pos']
+        b['F'] += fw
+        b['tau'] += np.cross(arm, fw)
+
+    def applyExternalTorque(self, bid, linkIndex, torqueObj, flags, **k):
+        b = self.body[1]
+        t = np.array(torqueObj, dtype=np.float64)
+        b['tau'] += _rot(b['quat']) @ t if flags == self.LINK_FRAME else t
+
+    def getLinkStates(self, bid, linkIndices, **k):       # base_aviary.py:396 (ground effect): world position of each link frame
+        b = self.body[1]
+        R = _rot(b['quat'])
+        return [(tuple(b['pos'] + R @ b['link_off'][i]),) * 2 for i in linkIndices]
+
+    # -- cart-pole chain -----------------------------------------------------------------------------
+    def resetJointState(self, bid, jointIndex, targetValue, targetVelocity=0.0, **k):
+        b = self.body[1]
+        b['q'][jointIndex], b['qd'][jointIndex] = float(targetValue), float(targetVelocity)
+
+    def getJointState(self, bid, jointIndex, **k):
+        b = self.body[1]
+        return (float(b['q'][jointIndex]), float(b['qd'][jointIndex]), (0.0,) * 6, 0.0)
+
+    def setJointMotorControl2_force(self, force):
+        self.body[1]['force'] = float(force)
+
+    def getNumJoints(self, *a, **k):
+        return 2
+
+    def getDynamicsInfo(self, bid, link, **k):
+        kind, b = self.body
+        if kind == 'quad':
+            return (b['mass'], 0.0, tuple(b['J']))
+        return (b['mass'].get(link, 0.0), 0.0, (0.0, 0.0, 0.0))
+
+    # -- integration -----------------------------------------------------------------------------------
+    def stepSimulation(self, **k):
+        kind, b = self.body
+        dt = self.dt
+        if kind == 'quad':
+            m, J = b['mass'], b['J']
+            R = _rot(b['quat'])
+            F = b['F'] + m * self.gravity
+            wb = R.T @ b['omega']
+            tau_b = R.T @ b['tau']
+            wdot_b = (tau_b - np.cross(wb, J * wb)) / J
+            b['vel'] = b['vel'] + F / m * dt
+            b['omega'] = b['omega'] + (R @ wdot_b) * dt
+            b['pos'] = b['pos'] + b['vel'] * dt
+            w = b['omega']
+            ang = float(np.linalg.norm(w))
+            if ang * dt > 0.25 * math.pi:
+                ang = 0.25 * math.pi / dt
+            kk = (0.5 * dt - dt ** 3 * 0.020833333333 * ang * ang) if ang < 0.001 else math.sin(0.5 * ang * dt) / ang
+            dq = np.array([w[0] * kk, w[1] * kk, w[2] * kk, math.cos(0.5 * ang * dt)])
+            q = _quat_mul(dq, b['quat'])
+            b['quat'] = q / np.linalg.norm(q)
+            b['F'], b['tau'] = np.zeros(3), np.zeros(3)
+        else:
+            raise NotImplementedError('cart-pole chain: pinned by real PyBullet transitions instead (tests/golden/cartpole_pybullet_transitions.npz)')
+
+
+# ------------------------------------------------------------------------------------------------
+_INSTALLED = {}
+
+
+def install():
+    '''Puts the stand-ins and the package shells into sys.modules (idempotent); returns the FakeBullet instance.'''
+    if _INSTALLED:
+        return _INSTALLED['pb']
+    pb = FakeBullet()
+    sys.modules['pybullet'] = pb
+    pd = types.ModuleType('pybullet_data')
+    pd.getDataPath = lambda: '/nonexistent'
+    sys.modules['pybullet_data'] = pd
+    sys.modules['casadi'] = _AnyModule('casadi')
+    mpl, plt = types.ModuleType('matplotlib'), types.ModuleType('matplotlib.pyplot')
+    mpl.pyplot = plt
+    sys.modules['matplotlib'], sys.modules['matplotlib.pyplot'] = mpl, plt
+
+    g, sp, ut, sd = (types.ModuleType(n) for n in ('gymnasium', 'gymnasium.spaces', 'gymnasium.utils', 'gymnasium.utils.seeding'))
+
+    class Box:
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            self.dtype = np.dtype(dtype)
+            self.low = (np.asarray(low, dtype) if shape is None else np.broadcast_to(np.asarray(low, dtype), shape)).copy()
+            self.high = (np.asarray(high, dtype) if shape is None else np.broadcast_to(np.asarray(high, dtype), shape)).copy()
+            self.shape = self.low.shape
+
+        def contains(self, x):
+            x = np.asarray(x)
+            return x.shape == self.shape and bool(np.all(x >= self.low)) and bool(np.all(x <= self.high))
+
+        def seed(self, seed=None):
+            return [seed]
+
+        def sample(self):
+            raise NotImplementedError
+
+    class Env:
+        metadata = {}
+
+        def close(self):
+            pass
+
+    def np_random(seed=None):
+        ss = np.random.SeedSequence(seed)
+        return np.random.Generator(np.random.PCG64(ss)), ss.entropy
+    sp.Box, g.spaces, g.Env, g.Wrapper, g.utils, ut.seeding, sd.np_random = Box, sp, Env, object, ut, sd, np_random
+    for m in (g, sp, ut, sd):
+        sys.modules[m.__name__] = m
+    for name, sub in (('safe_control_gym', ''), ('safe_control_gym.envs', 'envs'), ('safe_control_gym.envs.gym_pybullet_drones', 'envs/gym_pybullet_drones'),
+                      ('safe_control_gym.envs.gym_control', 'envs/gym_control'), ('safe_control_gym.math_and_models', 'math_and_models'),
+                      ('safe_control_gym.controllers', 'controllers'), ('safe_control_gym.controllers.lqr', 'controllers/lqr'),
+                      ('safe_control_gym.utils', 'utils')):
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(REF, sub)]
+        sys.modules[name] = m
+    _INSTALLED['pb'] = pb
+    return pb
+
+
+def load_task_config(rel_yaml):
+    import yaml
+    with open(os.path.join(REF_ROOT, rel_yaml)) as f:
+        return yaml.safe_load(f)['task_config']
+
+
+def make_quadrotor(**task_config):
+    install()
+    from safe_control_gym.envs.gym_pybullet_drones.quadrotor import Quadrotor
+    return Quadrotor(**task_config)
