@@ -22,7 +22,7 @@ from safe_control_gym_b200.envs import disturbances as dist_mod
 from safe_control_gym_b200.utils.registration import make
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = ['quad2d_track', 'quad2d_track_short', 'quad3d_track', 'quad3d_track_noise', 'quad2d_stab_noise']
+CASES = ['quad2d_track', 'quad2d_track_short', 'quad3d_track', 'quad3d_track_noise', 'quad2d_stab_noise', 'cartpole_stab', 'cartpole_track', 'cartpole_noise']
 ATOL = 2e-9        # float64 on both sides; the two integrators associate their sums differently, the horizon amplifies that a little
 
 
@@ -34,7 +34,7 @@ def _close(a, b, what, t, atol=ATOL):
 def test_oracle_reproduces_the_reference_in_the_loop(case):
     G = np.load(os.path.join(GOLD, f'refloop_{case}.npz'))
     cfg = json.loads(str(G['task_config']))
-    env = make('quadrotor', **cfg)
+    env = make(str(G['env_id']), **cfg)
     T = len(G['rew'])
     # (a16) the reference trajectory generator, whole table
     np.testing.assert_allclose(np.asarray(env._x_goal_table(), dtype=np.float64).reshape(G['x_goal'].shape), G['x_goal'], rtol=0, atol=1e-12)
@@ -57,7 +57,7 @@ def test_oracle_reproduces_the_reference_in_the_loop(case):
     o.set_episode_table(np.asarray(ep_rows, dtype=np.float64)[:, None, :])
     if o.D > 0:
         o.set_noise_table(np.asarray(step_rows, dtype=np.float64)[:, None, :])
-    if env.disturbances.get('dynamics') is not None:
+    if str(G['env_id']) == 'quadrotor' and env.disturbances.get('dynamics') is not None:
         # the reference applies the disturbance force at the position the drone had when the control step began (base_aviary.py:268-279 with
         # physics 'pyb'): a small torque.  The oracle has that behind a switch; the CUDA path does not have it.
         o.set_stale_force_point(True)

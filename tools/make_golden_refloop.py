@@ -20,8 +20,13 @@ import ref_harness as RH  # noqa: E402
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
 
 
-def run_case(name, cfg, T, act_seed, act_scale):
-    env = RH.make_quadrotor(**cfg)
+def run_case(name, cfg, T, act_seed, act_scale, env_id='quadrotor'):
+    env = RH.make_quadrotor(**cfg) if env_id == 'quadrotor' else RH.make_cartpole(**cfg)
+
+    def inertial_now():
+        if env_id == 'quadrotor':
+            return [env.OVERRIDDEN_QUAD_MASS] + list(env.OVERRIDDEN_QUAD_INERTIA)
+        return [env.OVERRIDDEN_EFFECTIVE_POLE_LENGTH, env.OVERRIDDEN_CART_MASS, env.OVERRIDDEN_POLE_MASS]
     rng = np.random.default_rng(act_seed)
     A, od = env.action_dim, env.observation_space.shape[0]
     nc = env.constraints.num_constraints if env.constraints is not None else 0
@@ -31,7 +36,7 @@ def run_case(name, cfg, T, act_seed, act_scale):
     reset_obs, reset_state, inertial = [], [], []
     obs, info = env.reset()
     reset_obs.append(obs.copy()); reset_state.append(np.array(env.state, dtype=np.float64))
-    inertial.append([env.OVERRIDDEN_QUAD_MASS] + list(env.OVERRIDDEN_QUAD_INERTIA))
+    inertial.append(inertial_now())
     for t in range(T):
         # mostly moderate actions; now and then a saturating one so that clipping, constraint violations and terminations occur
         a = rng.uniform(-1, 1, size=A) * (act_scale if rng.uniform() < 0.9 else 3.0)
@@ -47,9 +52,9 @@ def run_case(name, cfg, T, act_seed, act_scale):
         if done:
             obs, info = env.reset()
             reset_obs.append(obs.copy()); reset_state.append(np.array(env.state, dtype=np.float64))
-            inertial.append([env.OVERRIDDEN_QUAD_MASS] + list(env.OVERRIDDEN_QUAD_INERTIA))
+            inertial.append(inertial_now())
     path = os.path.join(OUT, f'refloop_{name}.npz')
-    np.savez_compressed(path, task_config=np.array(json.dumps(cfg)), x_goal=np.asarray(env.X_GOAL, dtype=np.float64), reset_obs=np.asarray(reset_obs), reset_state=np.asarray(reset_state),
+    np.savez_compressed(path, task_config=np.array(json.dumps(cfg)), env_id=np.array(env_id), x_goal=np.asarray(env.X_GOAL, dtype=np.float64), reset_obs=np.asarray(reset_obs), reset_state=np.asarray(reset_state),
                         inertial=np.asarray(inertial), ctrl_steps=np.int32(env.CTRL_STEPS), **rec)
     print(f'{name}: T={T} episodes={len(reset_obs)} done={int(rec["done"].sum())} truncated={int(rec["truncated"].sum())} '
           f'oob={int(rec["out_of_bounds"].sum())} cviol={int(rec["cviol"].sum())} -> {os.path.getsize(path)} bytes')
@@ -73,6 +78,15 @@ def main():
                disturbances=dict(observation=[dict(disturbance_func='white_noise', std=0.01)],
                                  dynamics=[dict(disturbance_func='step', magnitude=0.02, step_offset=10)]))
     run_case('quad2d_stab_noise', c2s, T=300, act_seed=5, act_scale=0.3)
+    # cart-pole: the stabilisation and tracking YAMLs verbatim, then randomised inertial properties + white noise on action, tap force and observation
+    cs = RH.load_task_config('examples/rl/config_overrides/cartpole/cartpole_stab.yaml')
+    run_case('cartpole_stab', cs, T=400, act_seed=6, act_scale=0.6, env_id='cartpole')
+    ct = RH.load_task_config('examples/rl/config_overrides/cartpole/cartpole_track.yaml')
+    run_case('cartpole_track', ct, T=400, act_seed=7, act_scale=0.6, env_id='cartpole')
+    cn = dict(cs, randomized_inertial_prop=True, seed=5, obs_wrap_angle=True,
+              disturbances=dict(action=[dict(disturbance_func='white_noise', std=0.05)], dynamics=[dict(disturbance_func='white_noise', std=0.1)],
+                                observation=[dict(disturbance_func='white_noise', std=0.005)]))
+    run_case('cartpole_noise', cn, T=400, act_seed=8, act_scale=0.6, env_id='cartpole')
 
 
 if __name__ == '__main__':

@@ -91,7 +91,7 @@ class FakeBullet(types.ModuleType):
     GUI, DIRECT, LINK_FRAME, WORLD_FRAME = 1, 2, 1, 2
     COV_ENABLE_GUI = COV_ENABLE_RGB_BUFFER_PREVIEW = COV_ENABLE_DEPTH_BUFFER_PREVIEW = COV_ENABLE_SEGMENTATION_MARK_PREVIEW = 0
     ER_TINY_RENDERER = ER_SEGMENTATION_MASK_OBJECT_AND_LINKINDEX = 0
-    VELOCITY_CONTROL = TORQUE_CONTROL = 0
+    VELOCITY_CONTROL, TORQUE_CONTROL = 0, 2
     JOINT_PRISMATIC, JOINT_REVOLUTE = 1, 0
 
     def __init__(self):
@@ -137,8 +137,12 @@ class FakeBullet(types.ModuleType):
     def resetDebugVisualizerCamera(self, *a, **k):
         pass
 
-    def setJointMotorControl2(self, *a, **k):       # cartpole.py:310-311 disables the default joint motors: nothing to do, there are none here
-        pass
+    def setJointMotorControl2(self, bid, jointIndex, controlMode, force=0.0, **k):
+        # cartpole.py:310-311 switches the default velocity motors off (VELOCITY_CONTROL, force 0): there are none here.
+        # cartpole.py:576-581: TORQUE_CONTROL on the slider joint = the force of the next simulation step
+        if controlMode == self.TORQUE_CONTROL:
+            assert jointIndex == 0
+            self.body[1]['force'] = float(force)
 
     def loadURDF(self, path, basePosition=(0, 0, 0), baseOrientation=(0, 0, 0, 1), **k):
         bid = self.next_id
@@ -168,16 +172,18 @@ class FakeBullet(types.ModuleType):
                                       pos=np.array(basePosition, dtype=np.float64), quat=np.array(baseOrientation, dtype=np.float64),
                                       vel=np.zeros(3), omega=np.zeros(3), F=np.zeros(3), tau=np.zeros(3)))
         else:                                                      # cartpole_template-derived file written by cartpole.py
-            self.body = ('cartpole', dict(id=bid, urdf=path, q=np.zeros(2), qd=np.zeros(2), mass={}, force=0.0, tap=None,
-                                          pole_len=None))
-            for l in tree.findall('link'):
-                if l.find('inertial/mass') is not None:
-                    self.body[1]['mass'][l.attrib['name']] = float(l.find('inertial/mass').attrib['value'])
-            box = [l for l in tree.findall('link') if l.attrib['name'] == 'pole'][0].find('collision/geometry/box')
-            self.body[1]['pole_box'] = np.array([float(v) for v in box.attrib['size'].split()])
+            # links of the file: slideBar (base, index -1), cart (index 0, prismatic joint along x), pole (index 1, revolute about y at the cart)
+            pole = [l for l in tree.findall('link') if l.attrib['name'] == 'pole'][0]
+            cart = [l for l in tree.findall('link') if l.attrib['name'] == 'cart'][0]
+            box = np.array([float(v) for v in pole.find('collision/geometry/box').attrib['size'].split()])
+            self.body = ('cartpole', dict(id=bid, q=np.zeros(2), qd=np.zeros(2), force=0.0, Qx=0.0, Qth=0.0,
+                                          mass={0: float(cart.find('inertial/mass').attrib['value']), 1: float(pole.find('inertial/mass').attrib['value'])},
+                                          l=float(pole.find('inertial/origin').attrib['xyz'].split()[-1]), box=box))
         return bid
 
     def changeDynamics(self, bid, linkIndex=-1, mass=None, localInertiaDiagonal=None, linearDamping=None, angularDamping=None, **k):
+        if self.body is None:
+            return
         kind, b = self.body
         link = linkIndex
         if kind == 'quad':
@@ -228,8 +234,11 @@ class FakeBullet(types.ModuleType):
         link = linkIndex
         kind, b = self.body
         f, r = np.array(forceObj, dtype=np.float64), np.array(posObj, dtype=np.float64)
-        if kind == 'cartpole':                             # cartpole.py:560-566: tap force on the pole link, WORLD_FRAME at the pole CoM
-            b['tap'] = f
+        if kind == 'cartpole':                             # cartpole.py:557-566: a world-frame force on the pole link at a world point
+            assert link == 1 and flags == self.WORLD_FRAME
+            arm = r - np.array([b['q'][0], 0.0, 0.0])      # from the pivot (on the cart, at the slider coordinate)
+            b['Qx'] += f[0]                                # generalised forces of (x, theta about +y)
+            b['Qth'] += arm[2] * f[0] - arm[0] * f[2]
             return
         R = _rot(b['quat'])
         if flags == self.LINK_FRAME:
@@ -244,6 +253,13 @@ class FakeBullet(types.ModuleType):
         b = self.body[1]
         t = np.array(torqueObj, dtype=np.float64)
         b['tau'] += _rot(b['quat']) @ t if flags == self.LINK_FRAME else t
+
+    def getLinkState(self, bid, linkIndex, **k):           # cartpole.py:561: [0] = world position of the pole's centre of mass
+        b = self.body[1]
+        assert self.body[0] == 'cartpole' and linkIndex == 1
+        x, th = b['q']
+        p_ = (x + b['l'] * math.sin(th), 0.0, b['l'] * math.cos(th))
+        return (p_, (0.0, 0.0, 0.0, 1.0))
 
     def getLinkStates(self, bid, linkIndices, **k):       # base_aviary.py:396 (ground effect): world position of each link frame
         b = self.body[1]
@@ -295,7 +311,20 @@ class FakeBullet(types.ModuleType):
             b['quat'] = q / np.linalg.norm(q)
             b['F'], b['tau'] = np.zeros(3), np.zeros(3)
         else:
-            raise NotImplementedError('cart-pole chain: pinned by real PyBullet transitions instead (tests/golden/cartpole_pybullet_transitions.npz)')
+            # cart + pole chain.  The pole's inertia about its centre of mass is the one Bullet derives from the collision box when the mass is
+            # (re)set without URDF_USE_INERTIA_FROM_FILE (cartpole.py:301-322) -- the reading that reproduces the real-PyBullet transitions of
+            # tests/golden/cartpole_pybullet_transitions.npz.  Symplectic Euler like the floating body.
+            M, m, l, g = b['mass'][0], b['mass'][1], b['l'], -float(self.gravity[2])
+            Ic = m / 12.0 * (b['box'][2] ** 2 + b['box'][0] ** 2)
+            th, thd = b['q'][1], b['qd'][1]
+            ct, st = math.cos(th), math.sin(th)
+            a11, a12, a22 = M + m, m * l * ct, Ic + m * l * l
+            b1, b2 = b['force'] + b['Qx'] + m * l * st * thd * thd, b['Qth'] + m * g * l * st
+            det = a11 * a22 - a12 * a12
+            qdd = np.array([(a22 * b1 - a12 * b2) / det, (a11 * b2 - a12 * b1) / det])
+            b['qd'] = b['qd'] + qdd * dt
+            b['q'] = b['q'] + b['qd'] * dt
+            b['force'], b['Qx'], b['Qth'] = 0.0, 0.0, 0.0
 
 
 # ------------------------------------------------------------------------------------------------
@@ -362,6 +391,12 @@ def load_task_config(rel_yaml):
     import yaml
     with open(os.path.join(REF_ROOT, rel_yaml)) as f:
         return yaml.safe_load(f)['task_config']
+
+
+def make_cartpole(**task_config):
+    install()
+    from safe_control_gym.envs.gym_control.cartpole import CartPole
+    return CartPole(**task_config)
 
 
 def make_quadrotor(**task_config):
