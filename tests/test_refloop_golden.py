@@ -22,7 +22,8 @@ from safe_control_gym_b200.envs import disturbances as dist_mod
 from safe_control_gym_b200.utils.registration import make
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
-CASES = ['quad2d_track', 'quad2d_track_short', 'quad3d_track', 'quad3d_track_noise', 'quad2d_stab_noise', 'cartpole_stab', 'cartpole_track', 'cartpole_noise']
+CASES = ['quad2d_track', 'quad2d_track_short', 'quad3d_track', 'quad3d_track_noise', 'quad2d_stab_noise', 'quad2d_gnd', 'quad2d_drag', 'quad3d_gnd_drag_dw',
+         'quad2d_adv_dyn', 'quad3d_adv_act', 'quad1d_stab_dist', 'cartpole_stab', 'cartpole_track', 'cartpole_noise', 'cartpole_adv_dyn', 'cartpole_adv_act']
 ATOL = 2e-9        # float64 on both sides; the two integrators associate their sums differently, the horizon amplifies that a little
 
 
@@ -57,7 +58,7 @@ def test_oracle_reproduces_the_reference_in_the_loop(case):
     o.set_episode_table(np.asarray(ep_rows, dtype=np.float64)[:, None, :])
     if o.D > 0:
         o.set_noise_table(np.asarray(step_rows, dtype=np.float64)[:, None, :])
-    if str(G['env_id']) == 'quadrotor' and env.disturbances.get('dynamics') is not None:
+    if str(G['env_id']) == 'quadrotor' and (env.disturbances.get('dynamics') is not None or cfg.get('adversary_disturbance') == 'dynamics'):
         # the reference applies the disturbance force at the position the drone had when the control step began (base_aviary.py:268-279 with
         # physics 'pyb'): a small torque.  The oracle has that behind a switch; the CUDA path does not have it.
         o.set_stale_force_point(True)
@@ -69,14 +70,21 @@ def test_oracle_reproduces_the_reference_in_the_loop(case):
         # the reference's reset observation = that + the white noise made of the draws the host generator produced at this point of the stream.
         want = np.array(G['reset_obs'][ep], dtype=np.float64)
         if obs_dist:
-            std = np.concatenate([np.broadcast_to(np.asarray(d.std, dtype=np.float64), (d.dim,)) for d in env.disturbances['observation'].disturbances])
-            _close(G['reset_state'][ep] + std * np.asarray(reset_draws[ep]), want[:nx], 'reference reset observation = state + std * draw', t)
-            want[:nx] = G['reset_state'][ep]
+            noise, at_zero, o_ = np.zeros(nx), np.zeros(nx), 0
+            for d in env.disturbances['observation'].disturbances:        # white: std * z (disturbances.py:215-223); uniform: low + (high - low) * u (:187-192)
+                z = np.asarray(reset_draws[ep][o_:o_ + d.dim]); o_ += d.dim
+                noise += d.std * z if d.step_draws == 'normal' else d.low + (d.high - d.low) * z
+                at_zero += 0.0 if d.step_draws == 'normal' else d.low
+            _close(G['reset_state'][ep] + noise, want[:nx], 'reference reset observation = state + noise made of the host draw', t)
+            # table mode evaluates the reset-observation noise with the draw replaced by 0: nothing for white noise, `low` for uniform noise
+            want[:nx] = G['reset_state'][ep] + at_zero
         _close(obs, want, 'observation after a reset', t)
     r = o.reset()
     check_reset(r['obs'][0], 0, -1)
     ep, nc = 0, G['cvals'].shape[1]
     for t in range(T):
+        if int(G['adv_dim']) > 0:
+            o.set_adversary_control(G['adv'][t][None, :])          # benchmark_env.py:216-228, before every step (rarl.py:367)
         s = o.step(G['act'][t][None, :])
         assert bool(s['done'][0]) == bool(G['done'][t]), f'done at step {t}'
         done = bool(G['done'][t])

@@ -20,7 +20,7 @@ import ref_harness as RH  # noqa: E402
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
 
 
-def run_case(name, cfg, T, act_seed, act_scale, env_id='quadrotor'):
+def run_case(name, cfg, T, act_seed, act_scale, env_id='quadrotor', adv_scale=None):
     env = RH.make_quadrotor(**cfg) if env_id == 'quadrotor' else RH.make_cartpole(**cfg)
 
     def inertial_now():
@@ -34,12 +34,18 @@ def run_case(name, cfg, T, act_seed, act_scale, env_id='quadrotor'):
                cvals=np.zeros((T, max(nc, 1))), cviol=np.zeros(T), current_step=np.zeros(T, np.int32), truncated=np.zeros(T, np.uint8),
                state=np.zeros((T, env.state_dim)), goal_reached=np.zeros(T, np.uint8))
     reset_obs, reset_state, inertial = [], [], []
+    adv_dim = env.adversary_action_space.shape[0] if adv_scale is not None else 0
+    rec['adv'] = np.zeros((T, max(adv_dim, 1)))
     obs, info = env.reset()
     reset_obs.append(obs.copy()); reset_state.append(np.array(env.state, dtype=np.float64))
     inertial.append(inertial_now())
     for t in range(T):
         # mostly moderate actions; now and then a saturating one so that clipping, constraint violations and terminations occur
         a = rng.uniform(-1, 1, size=A) * (act_scale if rng.uniform() < 0.9 else 3.0)
+        if adv_dim:                                       # rarl.py:367: the adversary's raw action, every step, before env.step
+            adv32 = (rng.uniform(-1, 1, size=adv_dim) * adv_scale).astype(np.float32)     # float32, as it comes out of the adversary's network (rarl.py:362-367)
+            rec['adv'][t] = adv32
+            env.set_adversary_control(adv32)
         obs, rew, done, info = env.step(a)
         rec['act'][t], rec['obs'][t], rec['rew'][t], rec['done'][t] = a, obs, rew, done
         rec['state'][t] = env.state
@@ -55,7 +61,7 @@ def run_case(name, cfg, T, act_seed, act_scale, env_id='quadrotor'):
             inertial.append(inertial_now())
     path = os.path.join(OUT, f'refloop_{name}.npz')
     np.savez_compressed(path, task_config=np.array(json.dumps(cfg)), env_id=np.array(env_id), x_goal=np.asarray(env.X_GOAL, dtype=np.float64), reset_obs=np.asarray(reset_obs), reset_state=np.asarray(reset_state),
-                        inertial=np.asarray(inertial), ctrl_steps=np.int32(env.CTRL_STEPS), **rec)
+                        inertial=np.asarray(inertial), ctrl_steps=np.int32(env.CTRL_STEPS), adv_dim=np.int32(adv_dim), **rec)
     print(f'{name}: T={T} episodes={len(reset_obs)} done={int(rec["done"].sum())} truncated={int(rec["truncated"].sum())} '
           f'oob={int(rec["out_of_bounds"].sum())} cviol={int(rec["cviol"].sum())} -> {os.path.getsize(path)} bytes')
     env.close()
@@ -78,6 +84,24 @@ def main():
                disturbances=dict(observation=[dict(disturbance_func='white_noise', std=0.01)],
                                  dynamics=[dict(disturbance_func='step', magnitude=0.02, step_offset=10)]))
     run_case('quad2d_stab_noise', c2s, T=300, act_seed=5, act_scale=0.3)
+    # non-default physics (base_aviary.py:243-268, 386-460): ground effect in low flight, drag, and all of them in 3-D
+    low = dict(c3, seed=21, init_state=dict(init_x=0, init_x_dot=0, init_z=0.15, init_z_dot=0, init_theta=0, init_theta_dot=0), episode_len_sec=2)
+    run_case('quad2d_gnd', dict(low, physics='pyb_gnd'), T=300, act_seed=9, act_scale=0.4)
+    run_case('quad2d_drag', dict(c3, seed=22, physics='pyb_drag'), T=300, act_seed=10, act_scale=0.5)
+    run_case('quad3d_gnd_drag_dw', dict(c4, seed=23, physics='pyb_gnd_drag_dw'), T=300, act_seed=11, act_scale=0.4)
+    # the adversary input (benchmark_env.py:216-228) in both modes: raw actions in [-1.5, 1.5] so that the clip to [-1, 1] is exercised
+    run_case('quad2d_adv_dyn', dict(c3, seed=24, adversary_disturbance='dynamics', adversary_disturbance_scale=0.02, adversary_disturbance_offset=0.001),
+             T=300, act_seed=12, act_scale=0.4, adv_scale=1.5)
+    run_case('quad3d_adv_act', dict(c4, seed=25, adversary_disturbance='action', adversary_disturbance_scale=0.01), T=300, act_seed=13, act_scale=0.4, adv_scale=1.5)
+    # Quadrotor-1D stabilisation with the three disturbance kinds not used above: impulse (random onset), periodic (random phase), uniform
+    q1 = dict(seed=26, ctrl_freq=50, pyb_freq=500, quad_type=1, normalized_rl_action_space=True, init_state=dict(init_x=1.0, init_x_dot=0.0),
+              randomized_init=True, task='stabilization', task_info=dict(stabilization_goal=[0, 1.2], stabilization_goal_tolerance=0.0), episode_len_sec=2,
+              cost='rl_reward', obs_goal_horizon=0, done_on_out_of_bound=True,      # (the reference cannot disturb an observation that carries goal rows: DI:191)
+              constraints=[dict(constraint_form='default_constraint', constrained_variable='state')],
+              disturbances=dict(action=[dict(disturbance_func='impulse', magnitude=0.02, step_offset=None, duration=3, decay_rate=0.7)],
+                                dynamics=[dict(disturbance_func='periodic', scale=0.01, frequency=2.0)],
+                                observation=[dict(disturbance_func='uniform', low=-0.01, high=0.01)]))
+    run_case('quad1d_stab_dist', q1, T=300, act_seed=14, act_scale=0.5)
     # cart-pole: the stabilisation and tracking YAMLs verbatim, then randomised inertial properties + white noise on action, tap force and observation
     cs = RH.load_task_config('examples/rl/config_overrides/cartpole/cartpole_stab.yaml')
     run_case('cartpole_stab', cs, T=400, act_seed=6, act_scale=0.6, env_id='cartpole')
@@ -87,6 +111,10 @@ def main():
               disturbances=dict(action=[dict(disturbance_func='white_noise', std=0.05)], dynamics=[dict(disturbance_func='white_noise', std=0.1)],
                                 observation=[dict(disturbance_func='white_noise', std=0.005)]))
     run_case('cartpole_noise', cn, T=400, act_seed=8, act_scale=0.6, env_id='cartpole')
+    run_case('cartpole_adv_dyn', dict(cs, seed=27, adversary_disturbance='dynamics', adversary_disturbance_scale=0.5), T=300, act_seed=15, act_scale=0.6,
+             env_id='cartpole', adv_scale=1.5)
+    run_case('cartpole_adv_act', dict(cs, seed=28, adversary_disturbance='action', adversary_disturbance_scale=2.0, adversary_disturbance_offset=0.1), T=300,
+             act_seed=16, act_scale=0.6, env_id='cartpole', adv_scale=1.5)
 
 
 if __name__ == '__main__':
