@@ -1,0 +1,67 @@
+'''The oracle's fused rollout against the PPOBuffer the UNMODIFIED reference controller filled: `PPO.train_step()` of /root/reference
+(controllers/ppo/ppo.py:259-303) on a DummyVecEnv of unmodified reference envs, recorded by tools/make_golden_ppo_loop.py (PyBullet replaced by the
+stand-in of tools/ref_harness.py; tests/golden/ppo_loop_*.npz is the committed output).
+
+The oracle gets what the reference run had: the actor-critic weights, the standard normals `Normal.sample()` drew, env i seeded `seed + i`
+(vectorized_env/__init__.py:31-35) -- through the host env's own draw functions -- and must return the same buffer: obs, act, rew, mask, v, logp,
+terminal_v (critic of the terminal observation where the time limit truncated, ppo.py:274-283), ret and the batch-normalised adv (ppo.py:288-300), and
+the observation the next rollout starts from.  This is the collector loop the fused CUDA kernel replaces, pinned on the
+reference's own controller code; the kernels are compared with the oracle on the GPU.
+
+Tolerances: the policy is float32 on both sides but torch sums its GEMMs in another order than the oracle's loops (1e-7 relative on the mean action);
+the closed loop carries that through the horizon, so trajectories are compared at 2e-5 (50-step episodes) or at the north-star tolerance 1e-4 (250-step episodes: 5 of 7200 observation entries exceed
+2e-5, the largest by 3e-5), and the open-loop-unstable cart-pole freely over its first steps and teacher-forced over the whole buffer.'''
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from safe_control_gym_b200.utils.registration import make
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+@pytest.mark.parametrize('case,tol,horizon', [('quad2d_track', 1e-4, None), ('quad2d_track_short', 2e-5, None), ('cartpole_stab', 2e-4, 12)])
+def test_oracle_rollout_fills_the_buffer_the_reference_controller_filled(case, tol, horizon):
+    G = np.load(os.path.join(GOLD, f'ppo_loop_{case}.npz'))
+    cfg = json.loads(str(G['task_config']))
+    env = make(str(G['env_id']), **cfg)
+    T, N = G['buf_rew'].shape[:2]
+    seed = int(G['seed'])
+    K = int((1 - G['buf_mask']).sum(0).max()) + 2                    # episodes any env needs
+    o = H.make_oracle(env, N, auto_reset=True, rng_mode='table')
+    o.set_episode_table(H.episode_table(env, N, K=K, seed=seed))     # env i draws with its own generator seeded seed + i, in the reference's order
+    r = o.reset()
+    np.testing.assert_allclose(r['obs'], G['obs0'], rtol=1e-9, atol=1e-9, err_msg='observations after PPO.reset()')
+    sd = {k[len('ac__'):].replace('__', '.'): G[k] for k in G.files if k.startswith('ac__')}
+    import torch
+    pol = H.orc.OraclePolicy.from_state_dict({k: torch.as_tensor(v) for k, v in sd.items()}, activation='tanh')
+    use_gae = bool(int(G['use_gae']))
+    out = o.rollout(pol, T, eps=G['eps'].astype(np.float32), gamma=float(G['gamma']), gae_lambda=float(G['gae_lambda']), use_gae=use_gae)
+    # episode boundaries and truncation bootstraps: identical
+    if horizon is None:
+        np.testing.assert_array_equal(out['mask'], G['buf_mask'])
+        assert np.array_equal(out['terminal_v'] != 0, G['buf_terminal_v'] != 0)
+    h = T if horizon is None else horizon
+    for k in ('obs', 'act', 'rew', 'v', 'logp', 'terminal_v'):
+        np.testing.assert_allclose(out[k][:h], G[f'buf_{k}'][:h], rtol=tol, atol=tol, err_msg=k)
+    if horizon is None:
+        np.testing.assert_allclose(out['ret'], G['buf_ret'], rtol=10 * tol, atol=10 * tol, err_msg='ret')
+        adv = out['adv'].astype(np.float64)
+        np.testing.assert_allclose((adv - adv.mean()) / (adv.std() + 1e-6), G['buf_adv'], rtol=0, atol=2e-3, err_msg='normalised adv')     # ppo.py:300
+        np.testing.assert_allclose(out['last_obs'], G['last_obs'], rtol=tol, atol=tol, err_msg='observation the next rollout starts from')
+    else:
+        # beyond the comparable horizon of the unstable plant: what the reference recorded is still a valid record of ITS trajectory -- replay it
+        # (teacher-forced one-step predictions) and require every transition of the whole buffer
+        fresh = H.make_oracle(env, N, auto_reset=True, rng_mode='table')
+        fresh.set_episode_table(H.episode_table(env, N, K=K, seed=seed))
+        fresh.reset()
+        rp = fresh.rollout(pol, T, eps=G['eps'].astype(np.float32), gamma=float(G['gamma']), gae_lambda=float(G['gae_lambda']), use_gae=use_gae,
+                           replay={'obs': G['buf_obs'], 'act': G['buf_act'], 'mask': G['buf_mask']})
+        np.testing.assert_array_equal(rp['mask'], G['buf_mask'])                       # the oracle ends the episodes where the reference did
+        for k in ('rew', 'v', 'logp', 'act'):
+            np.testing.assert_allclose(rp[k], G[f'buf_{k}'], rtol=2e-5, atol=2e-5, err_msg='replay ' + k)
+        cont = G['buf_mask'][:-1, :, 0] == 1                                            # next observation where the episode went on
+        np.testing.assert_allclose(rp['next_obs'][:-1][cont], G['buf_obs'][1:][cont], rtol=2e-5, atol=2e-5, err_msg='replay next_obs')

@@ -94,15 +94,25 @@ class FakeBullet(types.ModuleType):
     VELOCITY_CONTROL, TORQUE_CONTROL = 0, 2
     JOINT_PRISMATIC, JOINT_REVOLUTE = 1, 0
 
+    class World:
+        def __init__(self):
+            self.reset()
+
+        def reset(self):
+            self.gravity, self.dt = np.zeros(3), 1.0 / 240
+            self.body = None        # ('quad', dict) | ('cartpole', dict)
+            self.next_id = 0
+
     def __init__(self):
         super().__init__('pybullet')
-        self.log = []
-        self._reset_world()
+        self.worlds = {}
 
-    def _reset_world(self):
-        self.gravity, self.dt = np.zeros(3), 1.0 / 240
-        self.body = None            # ('quad', dict) | ('cartpole', dict)
-        self.next_id = 0
+    def _w(self, k):
+        '''the world of the call's physicsClientId (one per p.connect(); a call without it goes to the first client, like PyBullet's default)'''
+        cid = k.get('physicsClientId', 0)
+        if cid not in self.worlds:
+            self.worlds[cid] = FakeBullet.World()
+        return self.worlds[cid]
 
     def __getattr__(self, n):                           # camera / GUI / logging calls: accepted, ignored
         if n.startswith('__') and n.endswith('__'):
@@ -111,19 +121,21 @@ class FakeBullet(types.ModuleType):
 
     # -- world -----------------------------------------------------------------------------------
     def connect(self, *a, **k):
-        return 0
+        cid = len(self.worlds)
+        self.worlds[cid] = FakeBullet.World()
+        return cid
 
     def disconnect(self, *a, **k):
         pass
 
     def resetSimulation(self, *a, **k):
-        self._reset_world()
+        self._w(k).reset()
 
     def setGravity(self, gx, gy, gz, **k):
-        self.gravity = np.array([gx, gy, gz], dtype=np.float64)
+        self._w(k).gravity = np.array([gx, gy, gz], dtype=np.float64)
 
     def setTimeStep(self, dt, **k):
-        self.dt = float(dt)
+        self._w(k).dt = float(dt)
 
     def setRealTimeSimulation(self, *a, **k):
         pass
@@ -142,11 +154,11 @@ class FakeBullet(types.ModuleType):
         # cartpole.py:576-581: TORQUE_CONTROL on the slider joint = the force of the next simulation step
         if controlMode == self.TORQUE_CONTROL:
             assert jointIndex == 0
-            self.body[1]['force'] = float(force)
+            self._w(k).body[1]['force'] = float(force)
 
     def loadURDF(self, path, basePosition=(0, 0, 0), baseOrientation=(0, 0, 0, 1), **k):
-        bid = self.next_id
-        self.next_id += 1
+        bid = self._w(k).next_id
+        self._w(k).next_id += 1
         if os.path.basename(path) == 'plane.urdf':
             return bid
         tree = etxml.parse(path).getroot()
@@ -166,7 +178,7 @@ class FakeBullet(types.ModuleType):
                 jo = np.array([float(v) for v in o.attrib['xyz'].split()]) if o is not None else np.zeros(3)
                 offs.append(jo + inertial_origin[j.find('child').attrib['link']])
             base = tree.find('link')
-            self.body = ('quad', dict(id=bid, mass=float(base.find('inertial/mass').attrib['value']),
+            self._w(k).body = ('quad', dict(id=bid, mass=float(base.find('inertial/mass').attrib['value']),
                                       J=np.array([float(base.find('inertial/inertia').attrib[k2]) for k2 in ('ixx', 'iyy', 'izz')]),
                                       link_off=offs,
                                       pos=np.array(basePosition, dtype=np.float64), quat=np.array(baseOrientation, dtype=np.float64),
@@ -176,15 +188,15 @@ class FakeBullet(types.ModuleType):
             pole = [l for l in tree.findall('link') if l.attrib['name'] == 'pole'][0]
             cart = [l for l in tree.findall('link') if l.attrib['name'] == 'cart'][0]
             box = np.array([float(v) for v in pole.find('collision/geometry/box').attrib['size'].split()])
-            self.body = ('cartpole', dict(id=bid, q=np.zeros(2), qd=np.zeros(2), force=0.0, Qx=0.0, Qth=0.0,
+            self._w(k).body = ('cartpole', dict(id=bid, q=np.zeros(2), qd=np.zeros(2), force=0.0, Qx=0.0, Qth=0.0,
                                           mass={0: float(cart.find('inertial/mass').attrib['value']), 1: float(pole.find('inertial/mass').attrib['value'])},
                                           l=float(pole.find('inertial/origin').attrib['xyz'].split()[-1]), box=box))
         return bid
 
     def changeDynamics(self, bid, linkIndex=-1, mass=None, localInertiaDiagonal=None, linearDamping=None, angularDamping=None, **k):
-        if self.body is None:
+        if self._w(k).body is None:
             return
-        kind, b = self.body
+        kind, b = self._w(k).body
         link = linkIndex
         if kind == 'quad':
             if mass is not None:
@@ -197,19 +209,19 @@ class FakeBullet(types.ModuleType):
 
     # -- quadrotor body ----------------------------------------------------------------------------
     def resetBasePositionAndOrientation(self, bid, pos, quat, **k):
-        b = self.body[1]
+        b = self._w(k).body[1]
         b['pos'], b['quat'] = np.array(pos, dtype=np.float64), np.array(quat, dtype=np.float64)
 
     def resetBaseVelocity(self, bid, linearVelocity=(0, 0, 0), angularVelocity=(0, 0, 0), **k):
-        b = self.body[1]
+        b = self._w(k).body[1]
         b['vel'], b['omega'] = np.array(linearVelocity, dtype=np.float64), np.array(angularVelocity, dtype=np.float64)
 
     def getBasePositionAndOrientation(self, bid, **k):
-        b = self.body[1]
+        b = self._w(k).body[1]
         return tuple(b['pos']), tuple(b['quat'])
 
     def getBaseVelocity(self, bid, **k):
-        b = self.body[1]
+        b = self._w(k).body[1]
         return tuple(b['vel']), tuple(b['omega'])
 
     def getQuaternionFromEuler(self, rpy, **k):          # Bullet: ZYX (yaw, pitch, roll) -> (x, y, z, w)
@@ -232,7 +244,7 @@ class FakeBullet(types.ModuleType):
 
     def applyExternalForce(self, bid, linkIndex, forceObj, posObj, flags, **k):
         link = linkIndex
-        kind, b = self.body
+        kind, b = self._w(k).body
         f, r = np.array(forceObj, dtype=np.float64), np.array(posObj, dtype=np.float64)
         if kind == 'cartpole':                             # cartpole.py:557-566: a world-frame force on the pole link at a world point
             assert link == 1 and flags == self.WORLD_FRAME
@@ -250,51 +262,48 @@ class FakeBullet(types.ModuleType):
         b['tau'] += np.cross(arm, fw)
 
     def applyExternalTorque(self, bid, linkIndex, torqueObj, flags, **k):
-        b = self.body[1]
+        b = self._w(k).body[1]
         t = np.array(torqueObj, dtype=np.float64)
         b['tau'] += _rot(b['quat']) @ t if flags == self.LINK_FRAME else t
 
     def getLinkState(self, bid, linkIndex, **k):           # cartpole.py:561: [0] = world position of the pole's centre of mass
-        b = self.body[1]
-        assert self.body[0] == 'cartpole' and linkIndex == 1
+        b = self._w(k).body[1]
+        assert self._w(k).body[0] == 'cartpole' and linkIndex == 1
         x, th = b['q']
         p_ = (x + b['l'] * math.sin(th), 0.0, b['l'] * math.cos(th))
         return (p_, (0.0, 0.0, 0.0, 1.0))
 
     def getLinkStates(self, bid, linkIndices, **k):       # base_aviary.py:396 (ground effect): world position of each link frame
-        b = self.body[1]
+        b = self._w(k).body[1]
         R = _rot(b['quat'])
         return [(tuple(b['pos'] + R @ b['link_off'][i]),) * 2 for i in linkIndices]
 
     # -- cart-pole chain -----------------------------------------------------------------------------
     def resetJointState(self, bid, jointIndex, targetValue, targetVelocity=0.0, **k):
-        b = self.body[1]
+        b = self._w(k).body[1]
         b['q'][jointIndex], b['qd'][jointIndex] = float(targetValue), float(targetVelocity)
 
     def getJointState(self, bid, jointIndex, **k):
-        b = self.body[1]
+        b = self._w(k).body[1]
         return (float(b['q'][jointIndex]), float(b['qd'][jointIndex]), (0.0,) * 6, 0.0)
-
-    def setJointMotorControl2_force(self, force):
-        self.body[1]['force'] = float(force)
 
     def getNumJoints(self, *a, **k):
         return 2
 
     def getDynamicsInfo(self, bid, link, **k):
-        kind, b = self.body
+        kind, b = self._w(k).body
         if kind == 'quad':
             return (b['mass'], 0.0, tuple(b['J']))
         return (b['mass'].get(link, 0.0), 0.0, (0.0, 0.0, 0.0))
 
     # -- integration -----------------------------------------------------------------------------------
     def stepSimulation(self, **k):
-        kind, b = self.body
-        dt = self.dt
+        kind, b = self._w(k).body
+        dt = self._w(k).dt
         if kind == 'quad':
             m, J = b['mass'], b['J']
             R = _rot(b['quat'])
-            F = b['F'] + m * self.gravity
+            F = b['F'] + m * self._w(k).gravity
             wb = R.T @ b['omega']
             tau_b = R.T @ b['tau']
             wdot_b = (tau_b - np.cross(wb, J * wb)) / J
@@ -314,7 +323,7 @@ class FakeBullet(types.ModuleType):
             # cart + pole chain.  The pole's inertia about its centre of mass is the one Bullet derives from the collision box when the mass is
             # (re)set without URDF_USE_INERTIA_FROM_FILE (cartpole.py:301-322) -- the reading that reproduces the real-PyBullet transitions of
             # tests/golden/cartpole_pybullet_transitions.npz.  Symplectic Euler like the floating body.
-            M, m, l, g = b['mass'][0], b['mass'][1], b['l'], -float(self.gravity[2])
+            M, m, l, g = b['mass'][0], b['mass'][1], b['l'], -float(self._w(k).gravity[2])
             Ic = m / 12.0 * (b['box'][2] ** 2 + b['box'][0] ** 2)
             th, thd = b['q'][1], b['qd'][1]
             ct, st = math.cos(th), math.sin(th)
@@ -370,19 +379,57 @@ def install():
         def close(self):
             pass
 
+    class Wrapper(Env):                                   # gymnasium.Wrapper: holds `env`, forwards everything it does not define
+        def __init__(self, env):
+            self.env = env
+
+        def __getattr__(self, n):
+            if n.startswith('__') or n == 'env':
+                raise AttributeError(n)
+            return getattr(self.env, n)
+
+        def step(self, action):
+            return self.env.step(action)
+
+        def reset(self, **kw):
+            return self.env.reset(**kw)
+
+        def close(self):
+            return self.env.close()
+
+        @property
+        def unwrapped(self):
+            return getattr(self.env, 'unwrapped', self.env)
+
     def np_random(seed=None):
         ss = np.random.SeedSequence(seed)
         return np.random.Generator(np.random.PCG64(ss)), ss.entropy
-    sp.Box, g.spaces, g.Env, g.Wrapper, g.utils, ut.seeding, sd.np_random = Box, sp, Env, object, ut, sd, np_random
+    sp.Box, g.spaces, g.Env, g.Wrapper, g.utils, ut.seeding, sd.np_random = Box, sp, Env, Wrapper, ut, sd, np_random
     for m in (g, sp, ut, sd):
         sys.modules[m.__name__] = m
     for name, sub in (('safe_control_gym', ''), ('safe_control_gym.envs', 'envs'), ('safe_control_gym.envs.gym_pybullet_drones', 'envs/gym_pybullet_drones'),
                       ('safe_control_gym.envs.gym_control', 'envs/gym_control'), ('safe_control_gym.math_and_models', 'math_and_models'),
                       ('safe_control_gym.controllers', 'controllers'), ('safe_control_gym.controllers.lqr', 'controllers/lqr'),
-                      ('safe_control_gym.utils', 'utils')):
+                      ('safe_control_gym.utils', 'utils'), ('safe_control_gym.controllers.ppo', 'controllers/ppo'),
+                      ('safe_control_gym.envs.env_wrappers', 'envs/env_wrappers'),
+                      ('safe_control_gym.envs.env_wrappers.vectorized_env', None)):
+        if sub is None:
+            continue                      # (a real package whose __init__ is wanted: make_vec_envs lives there)
         m = types.ModuleType(name)
         m.__path__ = [os.path.join(REF, sub)]
         sys.modules[name] = m
+    for name in ('imageio', 'munch'):                    # imported at module level by utils/logging.py and utils/utils.py, used by neither path here
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except ImportError:
+                sys.modules[name] = _AnyModule(name)
+    try:
+        import torch.utils.tensorboard  # noqa: F401
+    except Exception:
+        tb = types.ModuleType('torch.utils.tensorboard')
+        tb.SummaryWriter = _Any
+        sys.modules['torch.utils.tensorboard'] = tb
     _INSTALLED['pb'] = pb
     return pb
 
@@ -391,6 +438,15 @@ def load_task_config(rel_yaml):
     import yaml
     with open(os.path.join(REF_ROOT, rel_yaml)) as f:
         return yaml.safe_load(f)['task_config']
+
+
+def make_ppo(env_id, task_config, output_dir, **ppo_config):
+    '''The reference PPO controller (controllers/ppo/ppo.py) on a DummyVecEnv of reference envs.'''
+    from functools import partial
+    install()
+    from safe_control_gym.controllers.ppo.ppo import PPO
+    env_func = partial(make_quadrotor if env_id == 'quadrotor' else make_cartpole, **task_config)
+    return PPO(env_func, training=True, output_dir=output_dir, **ppo_config)
 
 
 def make_cartpole(**task_config):
