@@ -410,7 +410,7 @@ def install():
     for name, sub in (('safe_control_gym', ''), ('safe_control_gym.envs', 'envs'), ('safe_control_gym.envs.gym_pybullet_drones', 'envs/gym_pybullet_drones'),
                       ('safe_control_gym.envs.gym_control', 'envs/gym_control'), ('safe_control_gym.math_and_models', 'math_and_models'),
                       ('safe_control_gym.controllers', 'controllers'), ('safe_control_gym.controllers.lqr', 'controllers/lqr'),
-                      ('safe_control_gym.utils', 'utils'), ('safe_control_gym.controllers.ppo', 'controllers/ppo'), ('safe_control_gym.controllers.rarl', 'controllers/rarl'),
+                      ('safe_control_gym.utils', 'utils'), ('safe_control_gym.controllers.ppo', 'controllers/ppo'), ('safe_control_gym.controllers.rarl', 'controllers/rarl'), ('safe_control_gym.controllers.safe_explorer', 'controllers/safe_explorer'),
                       ('safe_control_gym.envs.env_wrappers', 'envs/env_wrappers'),
                       ('safe_control_gym.envs.env_wrappers.vectorized_env', None)):
         if sub is None:
@@ -456,6 +456,15 @@ def make_rarl(env_id, task_config, output_dir, **rarl_config):
     from safe_control_gym.controllers.rarl.rarl import RARL
     env_func = partial(make_quadrotor if env_id == 'quadrotor' else make_cartpole, **task_config)
     return RARL(env_func, training=True, output_dir=output_dir, **rarl_config)
+
+
+def make_safe_ppo(env_id, task_config, output_dir, **config):
+    '''The reference SafeExplorerPPO controller (controllers/safe_explorer/safe_ppo.py) on a DummyVecEnv of reference envs.'''
+    from functools import partial
+    install()
+    from safe_control_gym.controllers.safe_explorer.safe_ppo import SafeExplorerPPO
+    env_func = partial(make_quadrotor if env_id == 'quadrotor' else make_cartpole, **task_config)
+    return SafeExplorerPPO(env_func, training=True, output_dir=output_dir, **config)
 
 
 def make_cartpole(**task_config):
