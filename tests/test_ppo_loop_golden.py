@@ -65,3 +65,29 @@ def test_oracle_rollout_fills_the_buffer_the_reference_controller_filled(case, t
             np.testing.assert_allclose(rp[k], G[f'buf_{k}'], rtol=2e-5, atol=2e-5, err_msg='replay ' + k)
         cont = G['buf_mask'][:-1, :, 0] == 1                                            # next observation where the episode went on
         np.testing.assert_allclose(rp['next_obs'][:-1][cont], G['buf_obs'][1:][cont], rtol=2e-5, atol=2e-5, err_msg='replay next_obs')
+
+
+@pytest.mark.parametrize('case,tol', [('quad2d_track', 2e-4), ('quad2d_track_short', 2e-4), ('cartpole_stab', 2e-3)])
+def test_oracle_deterministic_rollout_reproduces_the_reference_evaluation(case, tol):
+    '''`PPO.run(env=eval_env, n_episodes=4)` of the reference (ppo.py:210-257: mean action, one env seeded seed * 111, RecordEpisodeStatistics' per-episode
+    return / length / constraint-violation / mse sums) against an oracle deterministic rollout of the same policy on one env seeded the same way.
+    (`PPO.run` of this repo is compared with that oracle rollout on the GPU: tests/test_gpu_api.py.)'''
+    import torch
+    G = np.load(os.path.join(GOLD, f'ppo_loop_{case}.npz'))
+    cfg = json.loads(str(G['task_config']))
+    env = make(str(G['env_id']), **cfg)
+    n_ep = len(G['eval_ep_returns'])
+    T = int(G['eval_ep_lengths'].sum())
+    o = H.make_oracle(env, 1, auto_reset=True, rng_mode='table')
+    o.set_episode_table(H.episode_table(env, 1, K=n_ep + 1, seed=int(G['seed']) * 111))
+    o.reset()
+    sd = {k[len('ac1__'):].replace('__', '.'): torch.as_tensor(G[k]) for k in G.files if k.startswith('ac1__')}
+    pol = H.orc.OraclePolicy.from_state_dict(sd, activation='tanh')
+    out = o.rollout(pol, T, deterministic=True, gamma=0.0)            # gamma 0: `rew` stays the env's reward (no gamma * terminal_v added, ppo_utils.py:386)
+    ends = np.nonzero(out['mask'][:, 0, 0] == 0)[0]
+    assert len(ends) == n_ep and ends[-1] == T - 1, (ends, G['eval_ep_lengths'])
+    starts = np.concatenate([[0], ends[:-1] + 1])
+    np.testing.assert_array_equal(ends - starts + 1, G['eval_ep_lengths'].astype(int))
+    for key, rec in (('ep_returns', 'rew'), ('constraint_violation', 'cviol'), ('mse', 'mse')):
+        got = np.array([out[rec][s:e + 1, 0, 0].astype(np.float64).sum() for s, e in zip(starts, ends)])
+        np.testing.assert_allclose(got, G[f'eval_{key}'], rtol=tol, atol=tol, err_msg=key)

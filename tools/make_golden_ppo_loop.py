@@ -38,13 +38,18 @@ def run_case(name, env_id, task_cfg, seed, N, T, use_gae, torch_seed):
     obs0 = np.asarray(ctl.obs).copy()
     torch.manual_seed(torch_seed)
     ctl.train_step()
+    # deterministic evaluation with the UPDATED policy on the controller's own eval env (seeded seed * 111), as learn() calls it (ppo.py:175-178, 210-257)
+    ev = ctl.run(env=ctl.eval_env, n_episodes=4)
+    ev_arrs = {f'eval_{k}': np.asarray(v, dtype=np.float64) for k, v in ev.items() if k in ('ep_returns', 'ep_lengths', 'constraint_violation', 'mse')}
+    ac1 = {f'ac1__{k.replace(".", "__")}': v.detach().numpy().copy() for k, v in ctl.agent.ac.state_dict().items()}
     A = cap['buf']['act'].shape[-1]
     torch.manual_seed(torch_seed)
     eps = np.stack([torch.randn(N, A).numpy() for _ in range(T)])         # Normal.sample() = normal_(0, 1) * std + mean, once per step
     path = os.path.join(OUT, f'ppo_loop_{name}.npz')
     np.savez_compressed(path, task_config=np.array(json.dumps(task_cfg)), env_id=np.array(env_id), seed=np.int32(seed), use_gae=np.int32(use_gae),
                         gamma=np.float64(ctl.gamma), gae_lambda=np.float64(ctl.gae_lambda), eps=eps, obs0=obs0, last_obs=np.asarray(ctl.obs),
-                        **{f'ac__{k.replace(".", "__")}': v for k, v in cap['ac'].items()}, **{f'buf_{k}': v for k, v in cap['buf'].items()})
+                        **ev_arrs, **ac1, **{f'ac__{k.replace(".", "__")}': v for k, v in cap['ac'].items()}, **{f'buf_{k}': v for k, v in cap['buf'].items()})
+    print('   eval:', {k: np.round(v, 4).tolist() for k, v in ev_arrs.items()})
     b = cap['buf']
     print(f'{name}: T={T} N={N} dones={int((1 - b["mask"]).sum())} truncated(terminal_v != 0)={int((b["terminal_v"] != 0).sum())} -> {os.path.getsize(path)} bytes')
     ctl.close()
