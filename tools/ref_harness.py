@@ -368,10 +368,13 @@ def install():
             return x.shape == self.shape and bool(np.all(x >= self.low)) and bool(np.all(x <= self.high))
 
         def seed(self, seed=None):
+            self._rng = np.random.default_rng(seed)
             return [seed]
 
-        def sample(self):
-            raise NotImplementedError
+        def sample(self):                                  # gymnasium.spaces.Box.sample for bounded boxes (its own generator; not the same stream)
+            if not hasattr(self, '_rng'):
+                self._rng = np.random.default_rng()
+            return self._rng.uniform(self.low, self.high).astype(self.dtype)
 
     class Env:
         metadata = {}
@@ -410,7 +413,7 @@ def install():
     for name, sub in (('safe_control_gym', ''), ('safe_control_gym.envs', 'envs'), ('safe_control_gym.envs.gym_pybullet_drones', 'envs/gym_pybullet_drones'),
                       ('safe_control_gym.envs.gym_control', 'envs/gym_control'), ('safe_control_gym.math_and_models', 'math_and_models'),
                       ('safe_control_gym.controllers', 'controllers'), ('safe_control_gym.controllers.lqr', 'controllers/lqr'),
-                      ('safe_control_gym.utils', 'utils'), ('safe_control_gym.controllers.ppo', 'controllers/ppo'), ('safe_control_gym.controllers.rarl', 'controllers/rarl'), ('safe_control_gym.controllers.safe_explorer', 'controllers/safe_explorer'),
+                      ('safe_control_gym.utils', 'utils'), ('safe_control_gym.controllers.ppo', 'controllers/ppo'), ('safe_control_gym.controllers.rarl', 'controllers/rarl'), ('safe_control_gym.controllers.sac', 'controllers/sac'), ('safe_control_gym.controllers.ddpg', 'controllers/ddpg'), ('safe_control_gym.controllers.safe_explorer', 'controllers/safe_explorer'),
                       ('safe_control_gym.envs.env_wrappers', 'envs/env_wrappers'),
                       ('safe_control_gym.envs.env_wrappers.vectorized_env', None)):
         if sub is None:
@@ -465,6 +468,15 @@ def make_safe_ppo(env_id, task_config, output_dir, **config):
     from safe_control_gym.controllers.safe_explorer.safe_ppo import SafeExplorerPPO
     env_func = partial(make_quadrotor if env_id == 'quadrotor' else make_cartpole, **task_config)
     return SafeExplorerPPO(env_func, training=True, output_dir=output_dir, **config)
+
+
+def make_sac(env_id, task_config, output_dir, **config):
+    '''The reference SAC controller (controllers/sac/sac.py) on a DummyVecEnv of reference envs.'''
+    from functools import partial
+    install()
+    from safe_control_gym.controllers.sac.sac import SAC
+    env_func = partial(make_quadrotor if env_id == 'quadrotor' else make_cartpole, **task_config)
+    return SAC(env_func, training=True, output_dir=output_dir, **config)
 
 
 def make_cartpole(**task_config):
