@@ -14,11 +14,11 @@
  *   - MLP forward: PINNED against torch on the shipped checkpoints.
  *   - Env logic around the integrator (both systems): PINNED against the reference's OWN code run here -- quadrotor.py, base_aviary.py,
  *     cartpole.py, benchmark_env.py, constraints.py, disturbances.py, unmodified, with PyBullet replaced by a stand-in (tools/ref_harness.py):
- *     16 recorded cases (tests/golden/refloop_*.npz, tests/test_refloop_golden.py) reproduced to 2e-9 -- observations, state, reward, done,
+ *     21 recorded cases (tests/golden/refloop_*.npz, tests/test_refloop_golden.py) reproduced to 2e-9 -- observations, state, reward, done,
  *     truncation, mse, constraint values, flags, X_GOAL; randomisation order and arithmetic; all five disturbance kinds; the four non-default
  *     physics variants; the adversary input.
- *   - Collector loop: PINNED against the PPOBuffer the reference's own PPO.train_step() filled (tests/golden/ppo_loop_*.npz,
- *     tests/test_ppo_loop_golden.py), GAE against the reference function, sampling against MLPActorCritic.step (tests/test_ppo_reference_golden.py).
+ *   - Collector loops: PINNED against the buffers the reference's own PPO.train_step(), RARL.collect_rollouts() and SafeExplorerPPO.train_step()
+ *     filled (tests/golden/{ppo,rarl,safe}_loop_*.npz, tests/test_{ppo,rarl,safe}_loop_golden.py), PPO.run() evaluation results, GAE against the reference function, sampling against MLPActorCritic.step (tests/test_ppo_reference_golden.py).
  *   - Quadrotor physics vs PyBullet: UNPINNED by data (no PyBullet wheel, no recorded quadrotor
  *     transitions in the reference tree).  It restates the same Bullet btMultiBody semantics that the
  *     cartpole pin validates (symplectic Euler per sub-step, forces re-applied every sub-step) and is

@@ -102,6 +102,17 @@ def main():
                                 dynamics=[dict(disturbance_func='periodic', scale=0.01, frequency=2.0)],
                                 observation=[dict(disturbance_func='uniform', low=-0.01, high=0.01)]))
     run_case('quad1d_stab_dist', q1, T=300, act_seed=14, act_scale=0.5)
+    # after_step's constraint branches (benchmark_env.py:466-496): done_on_violation, the constraint penalty on an exponential reward, hand-written
+    # bounded (active_dims, strict) and linear rows next to the default ones; the other reference trajectories (circle, square)
+    run_case('quad2d_done_on_violation', dict(c3, seed=31, done_on_violation=True), T=200, act_seed=17, act_scale=0.3)
+    run_case('quad2d_penalty', dict(c3, seed=32, use_constraint_penalty=True, constraint_penalty=-1), T=200, act_seed=18, act_scale=0.4)
+    cust = [dict(constraint_form='bounded_constraint', constrained_variable='state', active_dims=[0, 2], lower_bounds=[-0.8, 0.6], upper_bounds=[0.8, 1.6], strict=True),
+            dict(constraint_form='linear_constraint', constrained_variable='state', A=[[1.0, 0.0, 1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, -1.0, 0.5, 0.0]], b=[2.2, 0.9]),
+            dict(constraint_form='default_constraint', constrained_variable='input')]
+    run_case('quad2d_custom_constraints', dict(c3, seed=33, constraints=cust), T=200, act_seed=19, act_scale=0.4)
+    run_case('quad2d_circle', dict(c3, seed=34, task_info=dict(trajectory_type='circle', num_cycles=2, trajectory_plane='xz', trajectory_position_offset=[0.1, 1.0],
+                                                              trajectory_scale=0.7)), T=200, act_seed=20, act_scale=0.4)
+    run_case('quad3d_square', dict(c4, seed=35, task_info=dict(c4['task_info'], trajectory_type='square', trajectory_scale=0.8)), T=200, act_seed=21, act_scale=0.3)
     # cart-pole: the stabilisation and tracking YAMLs verbatim, then randomised inertial properties + white noise on action, tap force and observation
     cs = RH.load_task_config('examples/rl/config_overrides/cartpole/cartpole_stab.yaml')
     run_case('cartpole_stab', cs, T=400, act_seed=6, act_scale=0.6, env_id='cartpole')
