@@ -149,6 +149,17 @@ class Oracle:
         assert tab.shape[1:] == (self.N, self.D), (tab.shape, self.N, self.D)
         self.lib.scg_oracle_set_noise_table(self.h, _p(tab), C.c_int(tab.shape[0]))
 
+    def get_state(self):
+        '''Snapshot of all envs (+ the noise cursor), like EngineHandle.get_state.'''
+        self.lib.scg_oracle_state_bytes.restype = C.c_size_t
+        buf = np.empty(self.lib.scg_oracle_state_bytes(self.h), np.uint8)
+        self.lib.scg_oracle_get_state(self.h, _p(buf))
+        return buf
+
+    def set_state(self, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        self.lib.scg_oracle_set_state(self.h, _p(buf))
+
     def set_stale_force_point(self, on=True):
         '''Reference quirk (off by default, absent from the CUDA path): see scg_oracle_set_stale_force_point in scg_oracle.c.'''
         self.lib.scg_oracle_set_stale_force_point(self.h, C.c_int(int(bool(on))))

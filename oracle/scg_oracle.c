@@ -218,6 +218,18 @@ void scg_oracle_set_episode_table(scg_oracle* o, const double* tab, int K) {
  * (pos_at_step_start - pos_now) about the centre of mass -- a small torque the "force through the CoM" reading does not have. */
 void scg_oracle_set_stale_force_point(scg_oracle* o, int on) { o->stale_force_point = on; }
 
+/* Snapshot / restore of everything a step changes (all envs + the noise-table cursor): the counterpart of scg_get_state / scg_set_state, used by the
+ * tests that replay a rollout from the same start (e.g. the RAP composition, tests/test_rap_reference.py). */
+size_t scg_oracle_state_bytes(const scg_oracle* o) { return sizeof(oenv) * (size_t)o->cfg.num_envs + sizeof(long long); }
+void scg_oracle_get_state(const scg_oracle* o, void* buf) {
+    memcpy(buf, o->envs, sizeof(oenv) * (size_t)o->cfg.num_envs);
+    long long cur = (long long)o->noise_cursor; memcpy((char*)buf + sizeof(oenv) * (size_t)o->cfg.num_envs, &cur, sizeof(cur));
+}
+void scg_oracle_set_state(scg_oracle* o, const void* buf) {
+    memcpy(o->envs, buf, sizeof(oenv) * (size_t)o->cfg.num_envs);
+    long long cur; memcpy(&cur, (const char*)buf + sizeof(oenv) * (size_t)o->cfg.num_envs, sizeof(cur)); o->noise_cursor = cur;
+}
+
 void scg_oracle_set_noise_table(scg_oracle* o, const double* tab, int Tn) {
     free(o->noise_table); o->Tn = Tn; size_t n = (size_t)Tn * o->cfg.num_envs * (o->D > 0 ? o->D : 1);
     o->noise_table = (double*)malloc(sizeof(double) * n); memcpy(o->noise_table, tab, sizeof(double) * (size_t)Tn * o->cfg.num_envs * o->D);

@@ -12,9 +12,12 @@ copied out of those two records.  Cost: 2 x |adversaries drawn| launches over al
 fused RAP collector (that would need a per-env adversary index and a second record in the kernel: DESIGN.md 8); at the reference's batch sizes
 (rollout_batch_size 4, two adversaries) the launches are microseconds.
 
-STATUS: host logic covered by the CPU tests (tests/test_rap_host.py, engine replaced by a stand-in).  The GPU test (tests/test_gpu_extended.py,
-opt-in with `SCG_RUN_UNVERIFIED=1`) ran ONCE with the last GPU seconds of round 2 and stopped at a host-side unpacking bug in `collect_rollouts`
-(fixed since, and the stand-in engine now checks the same contract); it has not passed on a B200 yet -- treat this class as unverified on the device.
+STATUS: `collect_rollouts` is verified against the REFERENCE's own `RAP.collect_rollouts()` on the CPU: tests/test_rap_reference.py runs it on an adapter over
+the oracle (same get_state / set_state / rollout contract as the engine) with the weights, adversary draw and normals of a recorded reference run, and gets
+the protagonist's buffer and every adversary's columns the reference returned; tests/test_rap_host.py covers the bookkeeping against a stand-in engine.  Not yet
+verified on a B200: the CUDA-side plumbing of this class (constructor, blobs of the fused update state, the engine calls, save / load / run) -- its GPU test
+(tests/test_gpu_extended.py, opt-in with `SCG_RUN_UNVERIFIED=1`) ran once with the last GPU seconds of round 2 and stopped at a host-side unpacking bug,
+fixed since.
 '''
 
 import time

@@ -479,6 +479,23 @@ def make_sac(env_id, task_config, output_dir, **config):
     return SAC(env_func, training=True, output_dir=output_dir, **config)
 
 
+def make_rap(env_id, task_config, output_dir, **config):
+    '''The reference RAP controller (controllers/rarl/rap.py) on a DummyVecEnv of reference envs.'''
+    from functools import partial
+    install()
+    from safe_control_gym.controllers.rarl.rap import RAP
+    env_func = partial(make_quadrotor if env_id == 'quadrotor' else make_cartpole, **task_config)
+    # rap.py does not implement BaseController's abstract `select_action` (its run() inlines the call, rap.py:218-220), so the class cannot be
+    # instantiated as shipped; a subclass that only adds that method -- the body RARL has (rarl.py:195-210) -- is the least intrusive way to run it
+    import torch
+
+    class InstantiableRAP(RAP):
+        def select_action(self, obs, info=None):
+            with torch.inference_mode():
+                return self.agent.ac.act(torch.FloatTensor(obs).to(self.device))
+    return InstantiableRAP(env_func, training=True, output_dir=output_dir, **config)
+
+
 def make_cartpole(**task_config):
     install()
     from safe_control_gym.envs.gym_control.cartpole import CartPole
