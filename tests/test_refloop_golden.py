@@ -108,3 +108,20 @@ def test_oracle_reproduces_the_reference_in_the_loop(case):
             ep += 1
             check_reset(s['obs'][0], ep, t)
     assert ep + 1 == len(G['reset_obs'])
+
+
+@pytest.mark.parametrize('name,case', [('quadrotor_2D_track', 'quad2d_track'), ('quadrotor_3D_track', 'quad3d_track'), ('cartpole_stab', 'cartpole_stab')])
+def test_packaged_task_configs_equal_the_reference_yaml(name, case):
+    '''safe_control_gym_b200/configs.py mirrors examples/rl/config_overrides/*/*.yaml of the reference (the task_config each golden was recorded with is the
+    YAML, verbatim): the mirror must resolve to the same engine configuration, field by field, constraints and reference table included.'''
+    from safe_control_gym_b200 import configs
+    G = np.load(os.path.join(GOLD, f'refloop_{case}.npz'))
+    yaml_cfg = json.loads(str(G['task_config']))
+    a, b = make(str(G['env_id']), **yaml_cfg), H.make_env(name)
+    ca, cb = a.build_config(num_envs=3), b.build_config(num_envs=3)
+    import ctypes
+    assert bytes(ctypes.string_at(ctypes.addressof(ca), ctypes.sizeof(ca))) == bytes(ctypes.string_at(ctypes.addressof(cb), ctypes.sizeof(cb)))
+    np.testing.assert_array_equal(np.asarray(a._x_goal_table()), np.asarray(b._x_goal_table()))
+    if a.constraints is not None:
+        for x, y in zip(a.constraints.csr(), b.constraints.csr()):
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
