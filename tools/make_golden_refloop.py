@@ -122,6 +122,18 @@ def main():
               disturbances=dict(action=[dict(disturbance_func='white_noise', std=0.05)], dynamics=[dict(disturbance_func='white_noise', std=0.1)],
                                 observation=[dict(disturbance_func='white_noise', std=0.005)]))
     run_case('cartpole_noise', cn, T=400, act_seed=8, act_scale=0.6, env_id='cartpole')
+    # BASELINE.json config 2: the packaged cartpole.yaml defaults (ctrl 50 / pyb 50: ONE sub-step per control step, physical force actions, class-default init ranges)
+    c2 = dict(seed=1000, ctrl_freq=50, pyb_freq=50, randomized_init=True, task='stabilization', cost='rl_reward', obs_goal_horizon=0, normalized_rl_action_space=False,
+              done_on_out_of_bound=True)
+    # (the reference raises AttributeError in _get_info when the stabilisation goal is reached before `self.out_of_bounds` was ever assigned -- cartpole.py:663-665
+    # returns early, :684 reads the attribute -- which the +-0.05 init range and the 0.05 goal tolerance of these defaults make likely at the first step:
+    # take the first seed whose run gets past that)
+    for sd in range(1000, 1040):
+        try:
+            run_case('cartpole_c2', dict(c2, seed=sd), T=400, act_seed=22, act_scale=4.0, env_id='cartpole')
+            break
+        except AttributeError as ex:
+            print(f'   cartpole_c2 seed {sd}: reference raised {ex}')
     run_case('cartpole_adv_dyn', dict(cs, seed=27, adversary_disturbance='dynamics', adversary_disturbance_scale=0.5), T=300, act_seed=15, act_scale=0.6,
              env_id='cartpole', adv_scale=1.5)
     run_case('cartpole_adv_act', dict(cs, seed=28, adversary_disturbance='action', adversary_disturbance_scale=2.0, adversary_disturbance_offset=0.1), T=300,
