@@ -91,3 +91,41 @@ def test_oracle_deterministic_rollout_reproduces_the_reference_evaluation(case, 
     for key, rec in (('ep_returns', 'rew'), ('constraint_violation', 'cviol'), ('mse', 'mse')):
         got = np.array([out[rec][s:e + 1, 0, 0].astype(np.float64).sum() for s, e in zip(starts, ends)])
         np.testing.assert_allclose(got, G[f'eval_{key}'], rtol=tol, atol=tol, err_msg=key)
+
+
+@pytest.mark.parametrize('case', ['quad2d_track', 'quad2d_track_short', 'cartpole_stab'])
+def test_episode_statistics_of_the_rollout_match_the_reference_wrapper(case):
+    '''`VecRecordEpisodeStatistics` of the reference (record_episode_statistics.py:139-166) logged one return / length / constraint-violation count per episode
+    that ended inside the recorded rollout; the fused rollout hands back per-env sums and counts (scg_rollout_out.d_ep_*).  Recomputed from the reference's own
+    buffer -- which the oracle reproduces, test above -- both views must agree: the multiset of per-episode values, and the oracle's per-env sums.'''
+    import torch
+    G = np.load(os.path.join(GOLD, f'ppo_loop_{case}.npz'))
+    cfg = json.loads(str(G['task_config']))
+    env = make(str(G['env_id']), **cfg)
+    T, N = G['buf_rew'].shape[:2]
+    gamma = float(G['gamma'])
+    rew = G['buf_rew'][..., 0].astype(np.float64) - gamma * G['buf_terminal_v'][..., 0].astype(np.float64)        # undo `rews += gamma * terminal_vals`
+    done = G['buf_mask'][..., 0] == 0
+    rets, lens, per_env_ret, per_env_cnt = [], [], np.zeros(N), np.zeros(N, int)
+    for n in range(N):
+        acc, ln = 0.0, 0
+        for t in range(T):
+            acc += rew[t, n]; ln += 1
+            if done[t, n]:
+                rets.append(acc); lens.append(ln); per_env_ret[n] += acc; per_env_cnt[n] += 1
+                acc, ln = 0.0, 0
+    np.testing.assert_allclose(sorted(rets), sorted(G['stat_returns']), rtol=1e-5, atol=1e-5)
+    assert sorted(lens) == sorted(int(x) for x in G['stat_lengths'])
+    # the oracle's per-env sums for the same rollout
+    K = int(done.sum(0).max()) + 2
+    o = H.make_oracle(env, N, auto_reset=True, rng_mode='table')
+    o.set_episode_table(H.episode_table(env, N, K=K, seed=int(G['seed'])))
+    o.reset()
+    sd = {k[len('ac__'):].replace('__', '.'): torch.as_tensor(G[k]) for k in G.files if k.startswith('ac__')}
+    pol = H.orc.OraclePolicy.from_state_dict(sd, activation='tanh')
+    out = o.rollout(pol, T, eps=G['eps'].astype(np.float32), gamma=gamma, gae_lambda=float(G['gae_lambda']), use_gae=bool(int(G['use_gae'])))
+    if case != 'cartpole_stab':                                  # (the cart-pole's free-running trajectories only agree over the first steps)
+        np.testing.assert_array_equal(out['ep_count'], per_env_cnt)
+        np.testing.assert_allclose(out['ep_return_sum'], per_env_ret, rtol=2e-4, atol=2e-4)
+        assert float(out['ep_length_sum'].sum()) == float(sum(lens))
+        assert float(out['ep_cviol_sum'].sum()) == float(G['stat_cviol'].sum())

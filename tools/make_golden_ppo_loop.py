@@ -24,7 +24,7 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'g
 
 def run_case(name, env_id, task_cfg, seed, N, T, use_gae, torch_seed):
     ppo_cfg = yaml.safe_load(open(os.path.join(RH.REF, 'controllers/ppo/ppo.yaml')))
-    ppo_cfg.update(rollout_batch_size=N, rollout_steps=T, mini_batch_size=32, opt_epochs=1, use_gae=use_gae, seed=seed)
+    ppo_cfg.update(rollout_batch_size=N, rollout_steps=T, mini_batch_size=32, opt_epochs=1, use_gae=use_gae, seed=seed, deque_size=1000)
     ctl = RH.make_ppo(env_id, task_cfg, tempfile.mkdtemp(), **ppo_cfg)
     ctl.reset()
     cap = {}
@@ -38,6 +38,9 @@ def run_case(name, env_id, task_cfg, seed, N, T, use_gae, torch_seed):
     obs0 = np.asarray(ctl.obs).copy()
     torch.manual_seed(torch_seed)
     ctl.train_step()
+    # what VecRecordEpisodeStatistics logged for the episodes that ended inside the rollout (record_episode_statistics.py:139-166), in completion order
+    stats = dict(stat_returns=np.asarray(ctl.env.return_queue, dtype=np.float64), stat_lengths=np.asarray(ctl.env.length_queue, dtype=np.float64),
+                 stat_cviol=np.asarray(ctl.env.queued_stats['constraint_violation'], dtype=np.float64))
     # deterministic evaluation with the UPDATED policy on the controller's own eval env (seeded seed * 111), as learn() calls it (ppo.py:175-178, 210-257)
     ev = ctl.run(env=ctl.eval_env, n_episodes=4)
     ev_arrs = {f'eval_{k}': np.asarray(v, dtype=np.float64) for k, v in ev.items() if k in ('ep_returns', 'ep_lengths', 'constraint_violation', 'mse')}
@@ -48,7 +51,7 @@ def run_case(name, env_id, task_cfg, seed, N, T, use_gae, torch_seed):
     path = os.path.join(OUT, f'ppo_loop_{name}.npz')
     np.savez_compressed(path, task_config=np.array(json.dumps(task_cfg)), env_id=np.array(env_id), seed=np.int32(seed), use_gae=np.int32(use_gae),
                         gamma=np.float64(ctl.gamma), gae_lambda=np.float64(ctl.gae_lambda), eps=eps, obs0=obs0, last_obs=np.asarray(ctl.obs),
-                        **ev_arrs, **ac1, **{f'ac__{k.replace(".", "__")}': v for k, v in cap['ac'].items()}, **{f'buf_{k}': v for k, v in cap['buf'].items()})
+                        **ev_arrs, **ac1, **stats, **{f'ac__{k.replace(".", "__")}': v for k, v in cap['ac'].items()}, **{f'buf_{k}': v for k, v in cap['buf'].items()})
     print('   eval:', {k: np.round(v, 4).tolist() for k, v in ev_arrs.items()})
     b = cap['buf']
     print(f'{name}: T={T} N={N} dones={int((1 - b["mask"]).sum())} truncated(terminal_v != 0)={int((b["terminal_v"] != 0).sum())} -> {os.path.getsize(path)} bytes')
