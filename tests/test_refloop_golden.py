@@ -40,6 +40,16 @@ def test_oracle_reproduces_the_reference_in_the_loop(case):
     # (a16) the reference trajectory generator, whole table
     np.testing.assert_allclose(np.asarray(env._x_goal_table(), dtype=np.float64).reshape(G['x_goal'].shape), G['x_goal'], rtol=0, atol=1e-12)
     assert int(env.CTRL_STEPS) == int(G['ctrl_steps'])
+    # the public surface of the env object (benchmark_env.py / quadrotor.py / cartpole.py attributes a controller reads): spaces incl. dtype, bounds, goals, counts
+    for mine, key in ((env.observation_space.low, 'obs_low'), (env.observation_space.high, 'obs_high'), (env.action_space.low, 'act_low'), (env.action_space.high, 'act_high'),
+                      (env.state_space.low, 'state_low'), (env.state_space.high, 'state_high'), (env.physical_action_bounds[0], 'phys_act_low'),
+                      (env.physical_action_bounds[1], 'phys_act_high')):
+        assert np.asarray(mine).dtype == G['surf_' + key].dtype, key
+        np.testing.assert_array_equal(np.asarray(mine), G['surf_' + key], err_msg=key)
+    np.testing.assert_allclose(np.asarray(env.U_GOAL, dtype=np.float64), G['surf_u_goal'], rtol=0, atol=1e-15)
+    assert float(env.CTRL_TIMESTEP) == float(G['surf_ctrl_timestep']) and int(env.PYB_STEPS_PER_CTRL) == int(G['surf_pyb_steps_per_ctrl'])
+    if env.constraints is not None:
+        assert [env.constraints.num_constraints, env.constraints.num_state_constraints, env.constraints.num_input_constraints] == list(G['surf_n_con'])
     # the reference's draws, re-made by the host env's own draw functions on a generator seeded the same way, in the reference's interleaving
     env.seed(cfg['seed'])
     obs_dist = {'observation': env.disturbances['observation']} if env.disturbances.get('observation') is not None else None

@@ -33,6 +33,14 @@ def run_case(name, cfg, T, act_seed, act_scale, env_id='quadrotor', adv_scale=No
     rec = dict(act=np.zeros((T, A)), obs=np.zeros((T, od)), rew=np.zeros(T), done=np.zeros(T, np.uint8), mse=np.zeros(T), out_of_bounds=np.zeros(T, np.uint8),
                cvals=np.zeros((T, max(nc, 1))), cviol=np.zeros(T), current_step=np.zeros(T, np.int32), truncated=np.zeros(T, np.uint8),
                state=np.zeros((T, env.state_dim)), goal_reached=np.zeros(T, np.uint8))
+    # the public surface a controller reads off the env (spaces, bounds, goals, counts): compared attribute by attribute with the host env of this repo
+    surf = dict(surf_obs_low=env.observation_space.low, surf_obs_high=env.observation_space.high, surf_act_low=env.action_space.low,
+                surf_act_high=env.action_space.high, surf_state_low=env.state_space.low, surf_state_high=env.state_space.high,
+                surf_phys_act_low=np.asarray(env.physical_action_bounds[0]), surf_phys_act_high=np.asarray(env.physical_action_bounds[1]),
+                surf_u_goal=np.asarray(env.U_GOAL, dtype=np.float64), surf_ctrl_timestep=np.float64(env.CTRL_TIMESTEP),
+                surf_pyb_steps_per_ctrl=np.int32(env.PYB_STEPS_PER_CTRL),
+                surf_n_con=np.array([env.constraints.num_constraints, env.constraints.num_state_constraints, env.constraints.num_input_constraints]
+                                    if env.constraints is not None else [0, 0, 0]))
     reset_obs, reset_state, inertial = [], [], []
     adv_dim = env.adversary_action_space.shape[0] if adv_scale is not None else 0
     rec['adv'] = np.zeros((T, max(adv_dim, 1)))
@@ -61,7 +69,7 @@ def run_case(name, cfg, T, act_seed, act_scale, env_id='quadrotor', adv_scale=No
             inertial.append(inertial_now())
     path = os.path.join(OUT, f'refloop_{name}.npz')
     np.savez_compressed(path, task_config=np.array(json.dumps(cfg)), env_id=np.array(env_id), x_goal=np.asarray(env.X_GOAL, dtype=np.float64), reset_obs=np.asarray(reset_obs), reset_state=np.asarray(reset_state),
-                        inertial=np.asarray(inertial), ctrl_steps=np.int32(env.CTRL_STEPS), adv_dim=np.int32(adv_dim), **rec)
+                        inertial=np.asarray(inertial), ctrl_steps=np.int32(env.CTRL_STEPS), adv_dim=np.int32(adv_dim), **surf, **rec)
     print(f'{name}: T={T} episodes={len(reset_obs)} done={int(rec["done"].sum())} truncated={int(rec["truncated"].sum())} '
           f'oob={int(rec["out_of_bounds"].sum())} cviol={int(rec["cviol"].sum())} -> {os.path.getsize(path)} bytes')
     env.close()
