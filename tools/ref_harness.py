@@ -413,7 +413,7 @@ def install():
     for name, sub in (('safe_control_gym', ''), ('safe_control_gym.envs', 'envs'), ('safe_control_gym.envs.gym_pybullet_drones', 'envs/gym_pybullet_drones'),
                       ('safe_control_gym.envs.gym_control', 'envs/gym_control'), ('safe_control_gym.math_and_models', 'math_and_models'),
                       ('safe_control_gym.controllers', 'controllers'), ('safe_control_gym.controllers.lqr', 'controllers/lqr'),
-                      ('safe_control_gym.utils', 'utils'), ('safe_control_gym.controllers.ppo', 'controllers/ppo'), ('safe_control_gym.controllers.rarl', 'controllers/rarl'), ('safe_control_gym.controllers.sac', 'controllers/sac'), ('safe_control_gym.controllers.ddpg', 'controllers/ddpg'), ('safe_control_gym.controllers.safe_explorer', 'controllers/safe_explorer'),
+                      ('safe_control_gym.utils', 'utils'), ('safe_control_gym.controllers.ppo', 'controllers/ppo'), ('safe_control_gym.controllers.rarl', 'controllers/rarl'), ('safe_control_gym.experiments', 'experiments'), ('safe_control_gym.math_and_models.metrics', 'math_and_models/metrics'), ('safe_control_gym.controllers.sac', 'controllers/sac'), ('safe_control_gym.controllers.ddpg', 'controllers/ddpg'), ('safe_control_gym.controllers.safe_explorer', 'controllers/safe_explorer'),
                       ('safe_control_gym.envs.env_wrappers', 'envs/env_wrappers'),
                       ('safe_control_gym.envs.env_wrappers.vectorized_env', None)):
         if sub is None:
@@ -421,6 +421,31 @@ def install():
         m = types.ModuleType(name)
         m.__path__ = [os.path.join(REF, sub)]
         sys.modules[name] = m
+    if 'munch' not in sys.modules:                           # base_experiment.py:9 `munchify`: dicts with attribute access, recursively
+        try:
+            import munch  # noqa: F401
+        except ImportError:
+            mm = types.ModuleType('munch')
+
+            class Munch(dict):
+                __getattr__ = dict.__getitem__
+                __setattr__ = dict.__setitem__
+
+            def munchify(x):
+                if isinstance(x, dict):
+                    return Munch((k, munchify(v)) for k, v in x.items())
+                if isinstance(x, (list, tuple)):
+                    return type(x)(munchify(v) for v in x)
+                return x
+            mm.Munch, mm.munchify = Munch, munchify
+            sys.modules['munch'] = mm
+    if 'termcolor' not in sys.modules:
+        try:
+            import termcolor  # noqa: F401
+        except ImportError:
+            tc = types.ModuleType('termcolor')
+            tc.colored = lambda s, *a, **k: s
+            sys.modules['termcolor'] = tc
     for name in ('imageio', 'munch'):                    # imported at module level by utils/logging.py and utils/utils.py, used by neither path here
         if name not in sys.modules:
             try:
