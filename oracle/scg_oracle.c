@@ -14,7 +14,7 @@
  *   - MLP forward: PINNED against torch on the shipped checkpoints.
  *   - Env logic around the integrator (both systems): PINNED against the reference's OWN code run here -- quadrotor.py, base_aviary.py,
  *     cartpole.py, benchmark_env.py, constraints.py, disturbances.py, unmodified, with PyBullet replaced by a stand-in (tools/ref_harness.py):
- *     22 recorded cases (tests/golden/refloop_*.npz, tests/test_refloop_golden.py) reproduced to 2e-9 -- observations, state, reward, done,
+ *     24 recorded cases (tests/golden/refloop_*.npz, tests/test_refloop_golden.py) reproduced to 2e-9 -- observations, state, reward, done,
  *     truncation, mse, constraint values, flags, X_GOAL; randomisation order and arithmetic; all five disturbance kinds; the four non-default
  *     physics variants; the adversary input.
  *   - Collector loops: PINNED against the buffers the reference's own PPO.train_step(), RARL.collect_rollouts() and SafeExplorerPPO.train_step()

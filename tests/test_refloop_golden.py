@@ -23,7 +23,7 @@ from safe_control_gym_b200.utils.registration import make
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 CASES = ['quad2d_track', 'quad2d_track_short', 'quad3d_track', 'quad3d_track_noise', 'quad2d_stab_noise', 'quad2d_gnd', 'quad2d_drag', 'quad3d_gnd_drag_dw',
-         'quad2d_adv_dyn', 'quad3d_adv_act', 'quad1d_stab_dist', 'quad2d_done_on_violation', 'quad2d_penalty', 'quad2d_custom_constraints', 'quad2d_circle', 'quad3d_square', 'cartpole_stab', 'cartpole_track', 'cartpole_noise', 'cartpole_c2', 'cartpole_adv_dyn', 'cartpole_adv_act']
+         'quad2d_adv_dyn', 'quad3d_adv_act', 'quad1d_stab_dist', 'quad2d_done_on_violation', 'quad2d_penalty', 'quad2d_custom_constraints', 'quad2d_circle', 'quad3d_square', 'quad2d_quadratic_constraint', 'cartpole_abs_bound', 'cartpole_stab', 'cartpole_track', 'cartpole_noise', 'cartpole_c2', 'cartpole_adv_dyn', 'cartpole_adv_act']
 ATOL = 2e-9        # float64 on both sides; the two integrators associate their sums differently, the horizon amplifies that a little
 
 

@@ -118,6 +118,9 @@ def main():
             dict(constraint_form='linear_constraint', constrained_variable='state', A=[[1.0, 0.0, 1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, -1.0, 0.5, 0.0]], b=[2.2, 0.9]),
             dict(constraint_form='default_constraint', constrained_variable='input')]
     run_case('quad2d_custom_constraints', dict(c3, seed=33, constraints=cust), T=200, act_seed=19, act_scale=0.4)
+    quad_con = [dict(constraint_form='quadratic_constraint', constrained_variable='state', P=[[1.0, 0.0, 0.2], [0.0, 0.5, 0.0], [0.2, 0.0, 2.0]], b=2.5, active_dims=[0, 1, 2]),
+                dict(constraint_form='default_constraint', constrained_variable='input')]
+    run_case('quad2d_quadratic_constraint', dict(c3, seed=36, constraints=quad_con), T=200, act_seed=23, act_scale=0.4)
     run_case('quad2d_circle', dict(c3, seed=34, task_info=dict(trajectory_type='circle', num_cycles=2, trajectory_plane='xz', trajectory_position_offset=[0.1, 1.0],
                                                               trajectory_scale=0.7)), T=200, act_seed=20, act_scale=0.4)
     run_case('quad3d_square', dict(c4, seed=35, task_info=dict(c4['task_info'], trajectory_type='square', trajectory_scale=0.8)), T=200, act_seed=21, act_scale=0.3)
@@ -142,6 +145,9 @@ def main():
             break
         except AttributeError as ex:
             print(f'   cartpole_c2 seed {sd}: reference raised {ex}')
+    run_case('cartpole_abs_bound', dict(cs, seed=29, constraints=[dict(constraint_form='abs_bound', constrained_variable='state', bound=0.12, active_dims=2),
+                                                                  dict(constraint_form='default_constraint', constrained_variable='input')]),
+             T=300, act_seed=24, act_scale=0.6, env_id='cartpole')
     run_case('cartpole_adv_dyn', dict(cs, seed=27, adversary_disturbance='dynamics', adversary_disturbance_scale=0.5), T=300, act_seed=15, act_scale=0.6,
              env_id='cartpole', adv_scale=1.5)
     run_case('cartpole_adv_act', dict(cs, seed=28, adversary_disturbance='action', adversary_disturbance_scale=2.0, adversary_disturbance_offset=0.1), T=300,
